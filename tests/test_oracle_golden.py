@@ -1,0 +1,125 @@
+"""Pins oracle/eve_oracle.py to vectors produced by the unmodified reference
+(oracle/gen_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import eve_oracle as O
+from tests import helpers as H
+
+
+@pytest.mark.parametrize('name', H.golden_names())
+def test_eve_forward_matches_reference(name, cfg):
+    gold = H.load_golden(name)
+    H.apply_case_config(cfg, gold)
+    training = bool(gold['meta/training'])
+    B = int(gold['meta/B'])
+    # EVE.__init__ turns requires_grad off for a frozen EyeNet (eve.py:57-59)
+    sd = {k: v.clone().requires_grad_(training and not (cfg.eye_net_frozen and k.startswith('eye_net.')))
+          for k, v in H.case_state_dict(gold, cfg).items()}
+    inputs = H.case_inputs(gold, cfg)
+    kappas = H.case_kappas(gold, B) if training else None
+    out, mid = O.eve_forward(sd, cfg, inputs, training, kappas, with_history=True)
+
+    checked = 0
+    for k, ref in gold.items():
+        if k.startswith('out/'):
+            key = k[4:]
+            if key in out:
+                got = out[key]
+            elif key in mid:
+                got = mid[key]
+            else:
+                continue
+        elif k.startswith('mid/'):
+            key = k[4:]
+            if key not in mid:
+                continue
+            got = mid[key]
+            if key.startswith('history_'):
+                got = got[:, -1]
+        else:
+            continue
+        got = got.detach().numpy()
+        if ref.dtype == np.bool_ or np.issubdtype(ref.dtype, np.integer):
+            assert np.array_equal(got, ref), k
+        else:
+            # fp32 vs fp32 with a different summation order: 2e-4 relative to the
+            # largest magnitude (RefineNet + soft-argmax amplify rounding)
+            assert got.shape == ref.shape, (k, got.shape, ref.shape)
+            tol = 2e-3 if ('final' in key or 'refined' in key) else 2e-4
+            assert H.rel_err(got, ref) < tol, (k, H.rel_err(got, ref))
+        checked += 1
+    assert checked >= 20
+    for must in ('out/full_loss', 'out/left_pupil_size', 'mid/left_g_initial'):
+        assert must in gold
+
+    if training:
+        out['full_loss'].backward()
+        n = 0
+        # parameters whose true gradient is zero (a bias feeding an InstanceNorm) carry
+        # pure rounding noise: floor the comparison at 1e-5 of the largest gradient norm
+        floor = 1e-5 * max(float(v) for k, v in gold.items() if k.startswith('gradnorm/'))
+        for k, ref in gold.items():
+            if not k.startswith('gradnorm/'):
+                continue
+            pname = k[len('gradnorm/'):]
+            g = sd[pname].grad
+            assert g is not None, pname
+            gn = float(g.double().norm())
+            # Gradients that pass through RefineNet are ill-conditioned in fp32: the
+            # reference's own fp32 gradients sit 4-6e-3 (relative, max-norm) away from an
+            # fp64 evaluation of the same graph (measured with this oracle in fp64), so
+            # fp32-vs-fp32 agreement is only meaningful to ~2e-2 there.  EyeNet-only
+            # cases are held to 2e-3.
+            gtol = 2e-2 if cfg.refine_net_enabled else 2e-3
+            assert abs(gn - float(ref)) <= gtol * max(float(ref), 1e-6) + floor, (pname, gn, float(ref))
+            sample = gold['grad/' + pname]
+            gf = g.reshape(-1).numpy()
+            gs = gf if gf.size <= 20000 else gf[::H.GRAD_STRIDE]
+            scale = max(float(np.abs(sample).max()), 1e-12)
+            assert np.max(np.abs(gs - sample)) <= gtol * scale + floor, pname
+            n += 1
+        for k in gold:
+            if k.startswith('gradnone/'):
+                g = sd[k[len('gradnone/'):]].grad
+                assert g is None or float(g.abs().max()) == 0.0, k
+        assert n > 30
+
+
+def test_module_entry_points_match_reference(cfg):
+    gold = H.load_golden('modules')
+    from eve_b200 import synth
+    cfg.override('refine_net_enabled', True)
+    cfg.override('load_screen_content', True)
+    rs = np.random.RandomState(31)
+    sd = synth.make_state_dict(synth.eye_net_param_shapes(cfg), 31, 'eye_net.')
+    patch = torch.from_numpy(rs.uniform(-1, 1, (2, 3, 128, 128)).astype(np.float32))
+    hp = torch.from_numpy(rs.uniform(-.2, .2, (2, 2)).astype(np.float32))
+    st = torch.from_numpy(rs.normal(size=(2, 128)).astype(np.float32))
+    with torch.no_grad():
+        g, p, states = O.eye_net_step(sd, cfg, patch, hp, [st])
+        assert H.rel_err(g.numpy(), gold['eyenet/g']) < 1e-4
+        assert H.rel_err(p.numpy(), gold['eyenet/pupil']) < 1e-4
+        assert H.rel_err(states[0].numpy(), gold['eyenet/state']) < 1e-4
+        assert H.rel_err(O.resnet18_in_features(sd, 'eye_net.cnn_layers.', patch).numpy(),
+                         gold['eyenet/fc']) < 1e-4
+
+        rsd = synth.make_state_dict(synth.refine_net_param_shapes(cfg), 1031, 'refine_net.')
+        px = torch.from_numpy(np.stack([rs.uniform(0, 1920, 2), rs.uniform(0, 1080, 2)], -1)
+                              .astype(np.float32))
+        assert np.array_equal(px.numpy(), gold['refine/px_in'])
+        hm = O.make_heatmaps(px, cfg.gaze_heatmap_sigma_initial)
+        assert H.rel_err(hm.numpy(), gold['refine/heatmap_initial']) < 1e-6
+        screen = torch.from_numpy(rs.uniform(0, 1, (2, 3, 72, 128)).astype(np.float32))
+        prev = torch.from_numpy((0.5 * rs.normal(size=(2, 64, 5, 8))).astype(np.float32))
+        out, states = O.refine_net_step(rsd, cfg, screen, hm, [prev])
+        assert H.rel_err(out.numpy(), gold['refine/heatmap_final']) < 1e-4
+        assert H.rel_err(states[0].numpy(), gold['refine/state']) < 1e-4
+        assert H.rel_err(O.soft_argmax(out).numpy(), gold['refine/softargmax']) < 1e-3
+        onehot = torch.zeros(1, 1, 72, 128)
+        onehot[0, 0, 10, 20] = 1.0
+        got = O.soft_argmax(onehot).numpy()
+        assert H.rel_err(got, gold['refine/softargmax_onehot']) < 1e-5
+        # known answer quoted in SURVEY.md appendix B
+        assert abs(got[0, 0] - 302.36) < 0.05 and abs(got[0, 1] - 152.11) < 0.05
