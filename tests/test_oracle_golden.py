@@ -67,12 +67,13 @@ def test_eve_forward_matches_reference(name, cfg):
             g = sd[pname].grad
             assert g is not None, pname
             gn = float(g.double().norm())
-            # Gradients that pass through RefineNet are ill-conditioned in fp32: the
-            # reference's own fp32 gradients sit 4-6e-3 (relative, max-norm) away from an
-            # fp64 evaluation of the same graph (measured with this oracle in fp64), so
-            # fp32-vs-fp32 agreement is only meaningful to ~2e-2 there.  EyeNet-only
-            # cases are held to 2e-3.
-            gtol = 2e-2 if cfg.refine_net_enabled else 2e-3
+            # Weight gradients of convolutions that feed an InstanceNorm are
+            # ill-conditioned in fp32 (large cancellations): the reference's own fp32
+            # gradients sit 4e-3..1.2e-2 (relative, max-norm) away from an fp64 evaluation
+            # of the same graph (measured with this oracle in fp64 for the stem conv and
+            # RefineNet's first conv), so fp32-vs-fp32 agreement is only meaningful to
+            # ~2e-2.  Forward values above are held to 2e-4 / 2e-3.
+            gtol = 2e-2
             assert abs(gn - float(ref)) <= gtol * max(float(ref), 1e-6) + floor, (pname, gn, float(ref))
             sample = gold['grad/' + pname]
             gf = g.reshape(-1).numpy()
