@@ -78,8 +78,11 @@ def test_eve_forward_matches_reference(name, cfg):
             sample = gold['grad/' + pname]
             gf = g.reshape(-1).numpy()
             gs = gf if gf.size <= 20000 else gf[::H.GRAD_STRIDE]
-            scale = max(float(np.abs(sample).max()), 1e-12)
-            assert np.max(np.abs(gs - sample)) <= gtol * scale + floor, pname
+            # L2 rather than max-norm: a pre-activation within rounding distance of zero
+            # may flip its ReLU mask between two fp32 evaluation orders, which moves a
+            # single gradient element by O(1) of its size.
+            l2 = float(np.linalg.norm(gs.astype(np.float64) - sample))
+            assert l2 <= gtol * float(np.linalg.norm(sample.astype(np.float64))) + floor, pname
             n += 1
         for k in gold:
             if k.startswith('gradnone/'):
