@@ -1,0 +1,184 @@
+// C ABI: error reporting and the single-op entry points (see include/eve_b200.h).
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace eve {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+static int check_conv(const eve_conv_params* p, ConvGeom& g) {
+  EVE_REQUIRE(p, EVE_ERR_NULL, "conv2d: params is NULL");
+  EVE_REQUIRE(p->n >= 0 && p->h > 0 && p->w > 0 && p->cin > 0 && p->cout > 0 && p->ksize > 0 &&
+                  p->stride > 0 && p->pad >= 0 && p->h + 2 * p->pad >= p->ksize &&
+                  p->w + 2 * p->pad >= p->ksize,
+              EVE_ERR_SHAPE, "conv2d: bad geometry n=%d h=%d w=%d cin=%d cout=%d k=%d s=%d p=%d",
+              p->n, p->h, p->w, p->cin, p->cout, p->ksize, p->stride, p->pad);
+  g = make_conv(p->n, p->h, p->w, p->cin, p->cout, p->ksize, p->stride, p->pad);
+  return EVE_OK;
+}
+
+static size_t conv_ws_floats(const ConvGeom& g) {
+  size_t wmat = align_up((size_t)g.Cout * g.K(), 64);
+  size_t wg = conv_wgrad_scratch_floats(g);
+  size_t cs = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
+  return wmat + (wg > cs ? wg : cs) + 64;
+}
+
+}  // namespace eve
+
+using namespace eve;
+
+extern "C" int eve_version(void) { return 100; }
+extern "C" const char* eve_last_error(void) { return g_error; }
+
+extern "C" size_t eve_conv2d_workspace_bytes(const eve_conv_params* p) {
+  ConvGeom g;
+  if (check_conv(p, g) != EVE_OK) return 0;
+  return conv_ws_floats(g) * sizeof(float);
+}
+
+extern "C" int eve_conv2d_fwd(const eve_conv_params* p, const float* x, const float* w,
+                              const float* bias, float* y, void* workspace,
+                              size_t workspace_bytes, eve_stream_t stream) {
+  ConvGeom g;
+  EVE_TRY(check_conv(p, g));
+  if (g.N == 0) return EVE_OK;
+  EVE_REQUIRE(x && w && y && workspace, EVE_ERR_NULL, "conv2d_fwd: NULL pointer");
+  EVE_REQUIRE(workspace_bytes >= conv_ws_floats(g) * sizeof(float), EVE_ERR_WORKSPACE,
+              "conv2d_fwd: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  float* wf = (float*)workspace;
+  EVE_TRY(conv_prep_weights(g, w, wf, nullptr, s));
+  return conv_fwd_simt(g, x, wf, bias, nullptr, y, g.Cout, s);
+}
+
+extern "C" int eve_conv2d_dgrad(const eve_conv_params* p, const float* dy, const float* w,
+                                float* dx, void* workspace, size_t workspace_bytes,
+                                eve_stream_t stream) {
+  ConvGeom g;
+  EVE_TRY(check_conv(p, g));
+  if (g.N == 0) return EVE_OK;
+  EVE_REQUIRE(dy && w && dx && workspace, EVE_ERR_NULL, "conv2d_dgrad: NULL pointer");
+  EVE_REQUIRE(workspace_bytes >= conv_ws_floats(g) * sizeof(float), EVE_ERR_WORKSPACE,
+              "conv2d_dgrad: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  float* wd = (float*)workspace;
+  EVE_TRY(conv_prep_weights(g, w, nullptr, wd, s));
+  return conv_dgrad_simt(g, dy, g.Cout, wd, nullptr, dx, s);
+}
+
+extern "C" int eve_conv2d_wgrad(const eve_conv_params* p, const float* x, const float* dy,
+                                float* dw, float* dbias, void* workspace, size_t workspace_bytes,
+                                eve_stream_t stream) {
+  ConvGeom g;
+  EVE_TRY(check_conv(p, g));
+  EVE_REQUIRE(x && dy && dw && workspace, EVE_ERR_NULL, "conv2d_wgrad: NULL pointer");
+  EVE_REQUIRE(workspace_bytes >= conv_ws_floats(g) * sizeof(float), EVE_ERR_WORKSPACE,
+              "conv2d_wgrad: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  float* scratch = (float*)workspace;
+  if (g.N == 0) {
+    EVE_TRY(fill_zero(dw, (long long)g.Cout * g.K(), s));
+    if (dbias) EVE_TRY(fill_zero(dbias, g.Cout, s));
+    return EVE_OK;
+  }
+  EVE_TRY(conv_wgrad_simt(g, x, dy, g.Cout, dw, scratch, false, s));
+  if (dbias)
+    EVE_TRY(colsum(dy, (long long)g.N * g.OH * g.OW, g.Cout, g.Cout, dbias, scratch, false, s));
+  return EVE_OK;
+}
+
+extern "C" int eve_instnorm_act_fwd(const float* x, int n, int hw, int c, const float* gamma,
+                                    const float* beta, int act, float* y, float* mean,
+                                    float* rstd, eve_stream_t stream) {
+  EVE_REQUIRE(x && y && mean && rstd, EVE_ERR_NULL, "instnorm_act_fwd: NULL pointer");
+  EVE_REQUIRE(n >= 0 && hw > 0 && c > 0 && c % 4 == 0 && act >= 0 && act <= 2, EVE_ERR_SHAPE,
+              "instnorm_act_fwd: bad shape n=%d hw=%d c=%d act=%d", n, hw, c, act);
+  EVE_REQUIRE((gamma == nullptr) == (beta == nullptr), EVE_ERR_NULL,
+              "instnorm_act_fwd: gamma and beta must both be given or both be NULL");
+  if (n == 0) return EVE_OK;
+  cudaStream_t s = as_stream(stream);
+  EVE_TRY(in_stats(x, n, hw, c, mean, rstd, s));
+  return in_apply(x, n, hw, c, mean, rstd, gamma, beta, nullptr, nullptr, nullptr, act, y, s);
+}
+
+extern "C" int eve_instnorm_act_bwd(const float* dy, const float* y, const float* x, int n, int hw,
+                                    int c, const float* mean, const float* rstd,
+                                    const float* gamma, int act, float* dx, float* dgamma,
+                                    float* dbeta, void* workspace, size_t workspace_bytes,
+                                    eve_stream_t stream) {
+  EVE_REQUIRE(dy && x && mean && rstd && dx && workspace, EVE_ERR_NULL,
+              "instnorm_act_bwd: NULL pointer");
+  EVE_REQUIRE(act == ACT_NONE || y, EVE_ERR_NULL, "instnorm_act_bwd: y is NULL");
+  EVE_REQUIRE(n >= 0 && hw > 0 && c > 0 && c % 4 == 0 && act >= 0 && act <= 2, EVE_ERR_SHAPE,
+              "instnorm_act_bwd: bad shape n=%d hw=%d c=%d act=%d", n, hw, c, act);
+  EVE_REQUIRE(workspace_bytes >= in_backward_scratch_floats(n, c) * sizeof(float),
+              EVE_ERR_WORKSPACE, "instnorm_act_bwd: workspace too small");
+  cudaStream_t s = as_stream(stream);
+  if (n == 0) {
+    if (gamma && dgamma) {
+      EVE_TRY(fill_zero(dgamma, c, s));
+      EVE_TRY(fill_zero(dbeta, c, s));
+    }
+    return EVE_OK;
+  }
+  return in_backward(dy, y, x, n, hw, c, mean, rstd, gamma, nullptr, act, nullptr, dx, nullptr, dgamma,
+                     dbeta, (float*)workspace, false, s);
+}
+
+extern "C" int eve_adaptive_maxpool_fwd(const float* x, int n, int h, int w, int c, int oh, int ow,
+                                        float* y, int32_t* idx, eve_stream_t stream) {
+  EVE_REQUIRE(x && y && idx, EVE_ERR_NULL, "adaptive_maxpool_fwd: NULL pointer");
+  EVE_REQUIRE(n >= 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0, EVE_ERR_SHAPE,
+              "adaptive_maxpool_fwd: bad shape");
+  if (n == 0) return EVE_OK;
+  return adaptive_maxpool_fwd(x, n, h, w, c, oh, ow, y, idx, as_stream(stream));
+}
+
+extern "C" int eve_adaptive_maxpool_bwd(const float* dy, const int32_t* idx, int n, int h, int w,
+                                        int c, int oh, int ow, float* dx, eve_stream_t stream) {
+  EVE_REQUIRE(dy && idx && dx, EVE_ERR_NULL, "adaptive_maxpool_bwd: NULL pointer");
+  EVE_REQUIRE(n >= 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0, EVE_ERR_SHAPE,
+              "adaptive_maxpool_bwd: bad shape");
+  if (n == 0) return EVE_OK;
+  return adaptive_maxpool_bwd(dy, idx, n, h, w, c, oh, ow, dx, as_stream(stream));
+}
+
+extern "C" int eve_upsample_bilinear_fwd(const float* x, int n, int h, int w, int c, int oh,
+                                         int ow, float* y, eve_stream_t stream) {
+  EVE_REQUIRE(x && y, EVE_ERR_NULL, "upsample_bilinear_fwd: NULL pointer");
+  EVE_REQUIRE(n >= 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0, EVE_ERR_SHAPE,
+              "upsample_bilinear_fwd: bad shape");
+  if (n == 0) return EVE_OK;
+  return upsample_bilinear_fwd(x, n, h, w, c, oh, ow, y, c, 0, as_stream(stream));
+}
+
+extern "C" int eve_upsample_bilinear_bwd(const float* dy, int n, int h, int w, int c, int oh,
+                                         int ow, float* dx, eve_stream_t stream) {
+  EVE_REQUIRE(dy && dx, EVE_ERR_NULL, "upsample_bilinear_bwd: NULL pointer");
+  EVE_REQUIRE(n >= 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0, EVE_ERR_SHAPE,
+              "upsample_bilinear_bwd: bad shape");
+  if (n == 0) return EVE_OK;
+  return upsample_bilinear_bwd(dy, c, 0, n, h, w, c, oh, ow, dx, as_stream(stream));
+}
+
+extern "C" int eve_nchw_to_nhwc(const float* x, int n, int c, int h, int w, float* y,
+                                eve_stream_t stream) {
+  EVE_REQUIRE(x && y, EVE_ERR_NULL, "nchw_to_nhwc: NULL pointer");
+  return nchw_to_nhwc(x, n, c, h, w, y, as_stream(stream));
+}
+
+extern "C" int eve_nhwc_to_nchw(const float* x, int n, int c, int h, int w, float* y,
+                                eve_stream_t stream) {
+  EVE_REQUIRE(x && y, EVE_ERR_NULL, "nhwc_to_nchw: NULL pointer");
+  return nhwc_to_nchw(x, n, c, h, w, y, as_stream(stream));
+}

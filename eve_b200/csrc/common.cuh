@@ -1,0 +1,182 @@
+// Shared declarations for libeve_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/eve_b200.h"
+
+namespace eve {
+
+// Records a message retrievable through eve_last_error(); thread-local.
+void set_error(const char* fmt, ...);
+
+#define EVE_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      ::eve::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                    \
+                       cudaGetErrorString(e__));                                        \
+      return EVE_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define EVE_LAUNCH_CHECK() EVE_CUDA(cudaGetLastError())
+
+#define EVE_TRY(expr)                                                                   \
+  do {                                                                                  \
+    int rc__ = (expr);                                                                  \
+    if (rc__ != EVE_OK) return rc__;                                                    \
+  } while (0)
+
+#define EVE_REQUIRE(cond, code, ...)                                                    \
+  do {                                                                                  \
+    if (!(cond)) {                                                                      \
+      ::eve::set_error(__VA_ARGS__);                                                    \
+      return (code);                                                                    \
+    }                                                                                   \
+  } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr int kNumSMs = 148;
+
+// Bump allocator over the caller-owned workspace (the library never allocates
+// device memory itself; see include/eve_b200.h "Ownership").
+struct Arena {
+  char* base;
+  size_t cap;
+  size_t off;
+  bool dry;  // size-counting pass: hand out fake pointers
+  Arena(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0), dry(p == nullptr) {}
+  template <typename T>
+  T* get(size_t count) {
+    size_t bytes = align_up(count * sizeof(T), 256);
+    size_t at = off;
+    off += bytes;
+    if (dry) return (T*)(uintptr_t)(256 + at);
+    if (off > cap) return nullptr;
+    return (T*)(base + at);
+  }
+  bool ok() const { return dry || off <= cap; }
+};
+
+// --------------------------------------------------------------------- conv geometry --
+struct ConvGeom {
+  int N, H, W, Cin;     // input, NHWC
+  int OH, OW, Cout;     // output, NHWC
+  int KH, KW, stride, pad;
+  long long in_elems() const { return (long long)N * H * W * Cin; }
+  long long out_elems() const { return (long long)N * OH * OW * Cout; }
+  int K() const { return KH * KW * Cin; }
+};
+inline ConvGeom make_conv(int N, int H, int W, int Cin, int Cout, int k, int stride, int pad) {
+  ConvGeom g;
+  g.N = N; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout; g.KH = k; g.KW = k;
+  g.stride = stride; g.pad = pad;
+  g.OH = (H + 2 * pad - k) / stride + 1;
+  g.OW = (W + 2 * pad - k) / stride + 1;
+  return g;
+}
+
+// ------------------------------------------------------------------------ conv (SIMT) --
+// Weight layouts derived from the OIHW fp32 master (caches in the workspace):
+//   fwd  : wf[(r*KW+q)*Cin + ci][co]
+//   dgrad: wd[(r*KW+q)*Cout + co][ci]
+int conv_prep_weights(const ConvGeom& g, const float* w_oihw, float* wf, float* wd,
+                      cudaStream_t s);
+// y[N,OH,OW,ldo>=Cout] (+bias) (+addend, same layout as y)
+int conv_fwd_simt(const ConvGeom& g, const float* x, const float* wf, const float* bias,
+                  const float* addend, float* y, int ldo, cudaStream_t s);
+// dx[N,H,W,Cin] = dgrad(dy) (+addend)
+int conv_dgrad_simt(const ConvGeom& g, const float* dy, int lddy, const float* wd,
+                    const float* addend, float* dx, cudaStream_t s);
+// dw_oihw (+)= wgrad(x, dy); scratch must hold conv_wgrad_scratch_floats(g)
+size_t conv_wgrad_scratch_floats(const ConvGeom& g);
+int conv_wgrad_simt(const ConvGeom& g, const float* x, const float* dy, int lddy, float* dw_oihw,
+                    float* scratch, bool accumulate, cudaStream_t s);
+// db[c] (+)= sum over rows of dy[rows, ld] (first C columns)
+int colsum(const float* dy, long long rows, int C, int ld, float* db, float* scratch,
+           bool accumulate, cudaStream_t s);
+size_t colsum_scratch_floats(long long rows, int C);
+
+// ------------------------------------------------------------------------------ norms --
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
+
+// Per-(n,c) mean / rstd over HW of x[N,HW,C] (biased variance, eps 1e-5).
+int in_stats(const float* x, int N, int HW, int C, float* mean, float* rstd, cudaStream_t s);
+// y = act( (x-mean)*rstd*gamma + beta  +  residual ), residual optional; if res_mean != null
+// the residual is itself normalised on the fly with (res_mean, res_rstd).  gamma/beta may be
+// null (non-affine).  y may be written with row stride ldy and channel offset (concat).
+int in_apply(const float* x, int N, int HW, int C, const float* mean, const float* rstd,
+             const float* gamma, const float* beta, const float* res, const float* res_mean,
+             const float* res_rstd, int act, float* y, cudaStream_t s);
+// Backward of y = act(IN(x)*gamma+beta + res):
+//   g   = dy * act'(y)                          (written to g_out if non-null: grad wrt res)
+//   dx  = rstd*gamma*( g - mean_hw(g) - xhat*mean_hw(g*xhat) )  (+ addend, optional)
+//   dgamma (+)= sum g*xhat, dbeta (+)= sum g   (if gamma != null)
+// y_for_mask: the saved forward output (sign decides act'); when null the pre-activation
+// xhat*gamma+beta is recomputed instead (only valid when there was no residual).
+int in_backward(const float* dy, const float* y_for_mask, const float* x, int N, int HW, int C,
+                const float* mean, const float* rstd, const float* gamma, const float* beta,
+                int act, const float* addend, float* dx, float* g_out, float* dgamma,
+                float* dbeta, float* scratch, bool accumulate_affine, cudaStream_t s);
+size_t in_backward_scratch_floats(int N, int C);
+
+// ------------------------------------------------------------------------------ pools --
+int nchw_to_nhwc(const float* x, int N, int C, int H, int W, float* y, cudaStream_t s);
+int nhwc_to_nchw(const float* x, int N, int C, int H, int W, float* y, cudaStream_t s);
+// Fused stem tail: y = maxpool3x3s2p1( relu( IN(x) ) ), idx = argmax position (first max,
+// row-major window order, flat h*W+w in the input plane) as int32.
+int in_relu_maxpool(const float* x, int N, int H, int W, int C, const float* mean,
+                    const float* rstd, float* y, int32_t* idx, cudaStream_t s);
+// dx (pre-norm grad input g wrt relu(IN(x)) output, scattered) : g[N,H,W,C] = scatter(dy)
+int maxpool_bwd_scatter(const float* dy, const int32_t* idx, int N, int H, int W, int OH, int OW,
+                        int C, float* g, cudaStream_t s);
+int avgpool_fwd(const float* x, int N, int HW, int C, float* y, cudaStream_t s);
+int avgpool_bwd(const float* dy, int N, int HW, int C, float* dx, cudaStream_t s);
+// torch AdaptiveMaxPool2d semantics: window [floor(i*L/O), ceil((i+1)*L/O))
+int adaptive_maxpool_fwd(const float* x, int N, int H, int W, int C, int OH, int OW, float* y,
+                         int32_t* idx, cudaStream_t s);
+int adaptive_maxpool_bwd(const float* dy, const int32_t* idx, int N, int H, int W, int C, int OH,
+                         int OW, float* dx, cudaStream_t s);
+// bilinear (align_corners=False) upsample of x[N,H,W,C] to [OH,OW], written into
+// y[N,OH,OW,ldy] at channel offset coff (the concat of refine_net.py:123-126)
+int upsample_bilinear_fwd(const float* x, int N, int H, int W, int C, int OH, int OW, float* y,
+                          int ldy, int coff, cudaStream_t s);
+int upsample_bilinear_bwd(const float* dy, int lddy, int coff, int N, int H, int W, int C, int OH,
+                          int OW, float* dx, cudaStream_t s);
+// y[rows, ldy] (cols coff..coff+C) = x[rows, ldx] (cols xoff..xoff+C)
+int copy_channels(const float* x, long long rows, int C, int ldx, int xoff, float* y, int ldy,
+                  int coff, bool accumulate, cudaStream_t s);
+
+}  // namespace eve
+
+namespace eve {
+// ----------------------------------------------------------------------------- linear --
+// nn.Linear as a 1x1 convolution on a 1x1 image.  W is torch's [N_out, K_in] row-major.
+// wt_scratch: K*N floats (transposed copy used by the forward GEMM).
+int linear_fwd(const float* x, int M, int K, const float* W, const float* b, int N, float* y,
+               float* wt_scratch, cudaStream_t s);
+// dx[M,K] = dy[M,N] . W  (+ addend)
+int linear_dgrad(const float* dy, int M, int N, const float* W, int K, const float* addend,
+                 float* dx, cudaStream_t s);
+// dW[N,K] (+)= dy^T x ; db[N] (+)= colsum(dy) when db != null.
+// scratch: linear_wgrad_scratch_floats(M, K, N)
+size_t linear_wgrad_scratch_floats(int M, int K, int N);
+int linear_wgrad(const float* x, const float* dy, int M, int K, int N, float* dW, float* db,
+                 float* scratch, bool accumulate, cudaStream_t s);
+
+// ------------------------------------------------------------------------ elementwise --
+enum Ew { EW_SELU = 0, EW_RELU = 1, EW_TANH_HALFPI = 2, EW_SIGMOID = 3, EW_LEAKY = 4, EW_TANH = 5 };
+// y = f(x)
+int ew_fwd(int op, const float* x, long long n, float* y, cudaStream_t s);
+// dx = dy * f'(.) ; `ref` is x for SELU/RELU/LEAKY and y for TANH_HALFPI/SIGMOID/TANH
+int ew_bwd(int op, const float* dy, const float* ref, long long n, float* dx, cudaStream_t s);
+// y = a + b
+int ew_add(const float* a, const float* b, long long n, float* y, cudaStream_t s);
+int fill_zero(float* p, long long n, cudaStream_t s);
+
+inline cudaStream_t as_stream(eve_stream_t s) { return (cudaStream_t)s; }
+}  // namespace eve

@@ -1,0 +1,355 @@
+// Layout changes, pooling and resampling -- HBM-bound NHWC fp32 kernels.
+//
+// Reference ops replaced: torchvision ResNet.maxpool / avgpool (via eye_net.py:106),
+// nn.AdaptiveMaxPool2d (refine_net.py:93,121), nn.Upsample(bilinear, align_corners=False)
+// + torch.cat (refine_net.py:101,124-126).  A warp always walks 32 consecutive channels of
+// one pixel (128-byte coalesced rows); the arg-max index convention is torch's: first
+// maximum in row-major window order.
+#include "common.cuh"
+
+namespace eve {
+
+namespace {
+
+// [N][R][Cc] -> [N][Cc][R] generic per-image transpose with a 32x32 smem tile.
+// in : rows = R, cols = Cc (cols contiguous)   out: rows = Cc, cols = R
+__global__ void transpose_kernel(const float* __restrict__ x, int R, int Cc,
+                                 float* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const size_t img = (size_t)blockIdx.z * R * Cc;
+  int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[j][threadIdx.x] = x[img + (size_t)r * Cc + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) y[img + (size_t)c * R + r] = tile[threadIdx.x][j];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+in_relu_maxpool_kernel(const float* __restrict__ x, long long total, int H, int W, int C, int OH,
+                       int OW, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       float* __restrict__ y, int32_t* __restrict__ idx) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long t = i / C;
+  int ox = (int)(t % OW);
+  t /= OW;
+  int oy = (int)(t % OH);
+  int n = (int)(t / OH);
+  const float m = mean[(size_t)n * C + c], r = rstd[(size_t)n * C + c];
+  const float* xp = x + (size_t)n * H * W * C + c;
+  float best = -INFINITY;
+  int bi = -1;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    int h = oy * 2 - 1 + dy;
+    if (h < 0 || h >= H) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      int w = ox * 2 - 1 + dx;
+      if (w < 0 || w >= W) continue;
+      float v = (__ldg(xp + (size_t)(h * W + w) * C) - m) * r;
+      v = v > 0.f ? v : 0.f;
+      if (v > best || bi < 0) {
+        best = v;
+        bi = h * W + w;
+      }
+    }
+  }
+  y[i] = best;
+  idx[i] = bi;
+}
+
+// gather form of the max-pool backward (3x3, stride 2, pad 1): deterministic, no atomics
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx, long long total,
+                   int H, int W, int OH, int OW, int C, float* __restrict__ g) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long t = i / C;
+  int w = (int)(t % W);
+  t /= W;
+  int h = (int)(t % H);
+  int n = (int)(t / H);
+  const int me = h * W + w;
+  float s = 0.f;
+  // windows oy with oy*2-1 <= h <= oy*2+1
+  int oy0 = h / 2, oy1 = (h + 1) / 2;
+  int ox0 = w / 2, ox1 = (w + 1) / 2;
+  for (int oy = oy0; oy <= oy1; ++oy) {
+    if (oy >= OH) continue;
+    for (int ox = ox0; ox <= ox1; ++ox) {
+      if (ox >= OW) continue;
+      size_t o = (((size_t)n * OH + oy) * OW + ox) * C + c;
+      if (__ldg(idx + o) == me) s += __ldg(dy + o);
+    }
+  }
+  g[i] = s;
+}
+
+__global__ void avgpool_fwd_kernel(const float* __restrict__ x, int HW, int C,
+                                   float* __restrict__ y) {
+  int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += x[((size_t)n * HW + p) * C + c];
+    y[(size_t)n * C + c] = s / (float)HW;
+  }
+}
+
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dy, long long total, int HW, int C,
+                                   float* __restrict__ dx) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  int n = (int)(i / ((long long)HW * C));
+  dx[i] = dy[(size_t)n * C + c] / (float)HW;
+}
+
+__device__ __forceinline__ int win_start(int i, int L, int O) { return (i * L) / O; }
+__device__ __forceinline__ int win_end(int i, int L, int O) { return ((i + 1) * L + O - 1) / O; }
+
+__global__ void __launch_bounds__(256)
+adaptive_maxpool_fwd_kernel(const float* __restrict__ x, long long total, int H, int W, int C,
+                            int OH, int OW, float* __restrict__ y, int32_t* __restrict__ idx) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long t = i / C;
+  int ox = (int)(t % OW);
+  t /= OW;
+  int oy = (int)(t % OH);
+  int n = (int)(t / OH);
+  const float* xp = x + (size_t)n * H * W * C + c;
+  int h0 = win_start(oy, H, OH), h1 = win_end(oy, H, OH);
+  int w0 = win_start(ox, W, OW), w1 = win_end(ox, W, OW);
+  float best = -INFINITY;
+  int bi = h0 * W + w0;
+  for (int h = h0; h < h1; ++h)
+    for (int w = w0; w < w1; ++w) {
+      float v = __ldg(xp + (size_t)(h * W + w) * C);
+      if (v > best || v != v) {  // torch: (val > max) || isnan(val)
+        best = v;
+        bi = h * W + w;
+      }
+    }
+  y[i] = best;
+  idx[i] = bi;
+}
+
+__global__ void __launch_bounds__(256)
+adaptive_maxpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx,
+                            long long total, int H, int W, int C, int OH, int OW,
+                            float* __restrict__ dx) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long t = i / C;
+  int w = (int)(t % W);
+  t /= W;
+  int h = (int)(t % H);
+  int n = (int)(t / H);
+  const int me = h * W + w;
+  int oy_lo = max(0, (h * OH) / H - 1), oy_hi = min(OH - 1, ((h + 1) * OH + H - 1) / H);
+  int ox_lo = max(0, (w * OW) / W - 1), ox_hi = min(OW - 1, ((w + 1) * OW + W - 1) / W);
+  float s = 0.f;
+  for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    if (h < win_start(oy, H, OH) || h >= win_end(oy, H, OH)) continue;
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      if (w < win_start(ox, W, OW) || w >= win_end(ox, W, OW)) continue;
+      size_t o = (((size_t)n * OH + oy) * OW + ox) * C + c;
+      if (__ldg(idx + o) == me) s += __ldg(dy + o);
+    }
+  }
+  dx[i] = s;
+}
+
+// torch upsample_bilinear2d, align_corners=False: src = scale*(dst+0.5)-0.5 clamped at 0
+__device__ __forceinline__ void bilinear_src(int d, float scale, int in, int& i0, int& i1,
+                                             float& l0, float& l1) {
+  float s = scale * ((float)d + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+  l0 = 1.f - l1;
+}
+
+__global__ void __launch_bounds__(256)
+upsample_fwd_kernel(const float* __restrict__ x, long long total, int H, int W, int C, int OH,
+                    int OW, float sh, float sw, float* __restrict__ y, int ldy, int coff) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long t = i / C;
+  int ox = (int)(t % OW);
+  t /= OW;
+  int oy = (int)(t % OH);
+  int n = (int)(t / OH);
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  bilinear_src(oy, sh, H, y0, y1, ly0, ly1);
+  bilinear_src(ox, sw, W, x0, x1, lx0, lx1);
+  const float* xp = x + (size_t)n * H * W * C + c;
+  float v00 = __ldg(xp + (size_t)(y0 * W + x0) * C), v01 = __ldg(xp + (size_t)(y0 * W + x1) * C);
+  float v10 = __ldg(xp + (size_t)(y1 * W + x0) * C), v11 = __ldg(xp + (size_t)(y1 * W + x1) * C);
+  float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+  y[(((size_t)n * OH + oy) * OW + ox) * ldy + coff + c] = v;
+}
+
+// gather form of the bilinear backward: each input pixel sums over the (few) output pixels
+// whose 2x2 footprint contains it.  Output range bounded from the scale.
+__global__ void __launch_bounds__(256)
+upsample_bwd_kernel(const float* __restrict__ dy, int lddy, int coff, long long total, int H,
+                    int W, int C, int OH, int OW, float sh, float sw, float* __restrict__ dx) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long t = i / C;
+  int w = (int)(t % W);
+  t /= W;
+  int h = (int)(t % H);
+  int n = (int)(t / H);
+  // candidate outputs: src in (h-1, h+1)  =>  dst in ((h-0.5)/s - 0.5 - 1, (h+1.5)/s - 0.5 + 1)
+  int oy_lo = max(0, (int)floorf(((float)h - 0.5f) / sh - 1.5f));
+  int oy_hi = min(OH - 1, (int)ceilf(((float)h + 1.5f) / sh + 0.5f));
+  int ox_lo = max(0, (int)floorf(((float)w - 0.5f) / sw - 1.5f));
+  int ox_hi = min(OW - 1, (int)ceilf(((float)w + 1.5f) / sw + 0.5f));
+  float s = 0.f;
+  for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    int y0, y1;
+    float ly0, ly1;
+    bilinear_src(oy, sh, H, y0, y1, ly0, ly1);
+    float wy = (y0 == h ? ly0 : 0.f) + (y1 == h ? ly1 : 0.f);
+    if (wy == 0.f) continue;
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      int x0, x1;
+      float lx0, lx1;
+      bilinear_src(ox, sw, W, x0, x1, lx0, lx1);
+      float wx = (x0 == w ? lx0 : 0.f) + (x1 == w ? lx1 : 0.f);
+      if (wx == 0.f) continue;
+      s = fmaf(wy * wx, __ldg(dy + (((size_t)n * OH + oy) * OW + ox) * lddy + coff + c), s);
+    }
+  }
+  dx[i] = s;
+}
+
+__global__ void __launch_bounds__(256)
+copy_channels_kernel(const float* __restrict__ x, long long total, int C, int ldx, int xoff,
+                     float* __restrict__ y, int ldy, int coff, int accumulate) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long r = i / C;
+  float v = __ldg(x + r * ldx + xoff + c);
+  float* o = y + r * ldy + coff + c;
+  *o = accumulate ? *o + v : v;
+}
+
+}  // namespace
+
+static int transpose_images(const float* x, int N, int R, int Cc, float* y, cudaStream_t s) {
+  if (N == 0) return EVE_OK;
+  dim3 block(32, 8);
+  for (int n0 = 0; n0 < N; n0 += 65535) {
+    int nb = N - n0 < 65535 ? N - n0 : 65535;
+    dim3 grid(cdiv(Cc, 32), cdiv(R, 32), nb);
+    transpose_kernel<<<grid, block, 0, s>>>(x + (size_t)n0 * R * Cc, R, Cc,
+                                            y + (size_t)n0 * R * Cc);
+    EVE_LAUNCH_CHECK();
+  }
+  return EVE_OK;
+}
+
+int nchw_to_nhwc(const float* x, int N, int C, int H, int W, float* y, cudaStream_t s) {
+  return transpose_images(x, N, C, H * W, y, s);
+}
+int nhwc_to_nchw(const float* x, int N, int C, int H, int W, float* y, cudaStream_t s) {
+  return transpose_images(x, N, H * W, C, y, s);
+}
+
+int in_relu_maxpool(const float* x, int N, int H, int W, int C, const float* mean,
+                    const float* rstd, float* y, int32_t* idx, cudaStream_t s) {
+  int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  long long total = (long long)N * OH * OW * C;
+  in_relu_maxpool_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, H, W, C, OH, OW, mean, rstd, y,
+                                                          idx);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+int maxpool_bwd_scatter(const float* dy, const int32_t* idx, int N, int H, int W, int OH, int OW,
+                        int C, float* g, cudaStream_t s) {
+  long long total = (long long)N * H * W * C;
+  maxpool_bwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(dy, idx, total, H, W, OH, OW, C, g);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+int avgpool_fwd(const float* x, int N, int HW, int C, float* y, cudaStream_t s) {
+  avgpool_fwd_kernel<<<N, 256, 0, s>>>(x, HW, C, y);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+int avgpool_bwd(const float* dy, int N, int HW, int C, float* dx, cudaStream_t s) {
+  long long total = (long long)N * HW * C;
+  avgpool_bwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(dy, total, HW, C, dx);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+int adaptive_maxpool_fwd(const float* x, int N, int H, int W, int C, int OH, int OW, float* y,
+                         int32_t* idx, cudaStream_t s) {
+  long long total = (long long)N * OH * OW * C;
+  adaptive_maxpool_fwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, H, W, C, OH, OW, y, idx);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+int adaptive_maxpool_bwd(const float* dy, const int32_t* idx, int N, int H, int W, int C, int OH,
+                         int OW, float* dx, cudaStream_t s) {
+  long long total = (long long)N * H * W * C;
+  adaptive_maxpool_bwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(dy, idx, total, H, W, C, OH, OW,
+                                                               dx);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+int upsample_bilinear_fwd(const float* x, int N, int H, int W, int C, int OH, int OW, float* y,
+                          int ldy, int coff, cudaStream_t s) {
+  long long total = (long long)N * OH * OW * C;
+  float sh = (float)H / (float)OH, sw = (float)W / (float)OW;
+  upsample_fwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, H, W, C, OH, OW, sh, sw, y, ldy,
+                                                       coff);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+int upsample_bilinear_bwd(const float* dy, int lddy, int coff, int N, int H, int W, int C, int OH,
+                          int OW, float* dx, cudaStream_t s) {
+  long long total = (long long)N * H * W * C;
+  float sh = (float)H / (float)OH, sw = (float)W / (float)OW;
+  upsample_bwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(dy, lddy, coff, total, H, W, C, OH, OW, sh,
+                                                       sw, dx);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+int copy_channels(const float* x, long long rows, int C, int ldx, int xoff, float* y, int ldy,
+                  int coff, bool accumulate, cudaStream_t s) {
+  long long total = rows * C;
+  copy_channels_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, C, ldx, xoff, y, ldy, coff,
+                                                        accumulate ? 1 : 0);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+}  // namespace eve

@@ -1,0 +1,911 @@
+// GazeRefineNet: pre-activation encoder / ConvRNN bottleneck / decoder, forward + backward.
+//
+// Reference: src/models/refine_net.py:35-255 (BasicBlock :35-67, WrapEncoderDecoder :70-129,
+// Bottleneck :132-176, RefineNet :179-255) and the cells in src/models/common.py:331-415.
+// Encoder and decoder run for all batch*steps frames at once (per-sample norms, SURVEY.md
+// 3.3); only the 5x8 bottleneck cells walk over time, on time-major copies of the features.
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace eve {
+namespace {
+
+constexpr int kLevels = 5;
+constexpr int kLevelH[kLevels] = {72, 36, 18, 9, 5};
+constexpr int kLevelW[kLevels] = {128, 64, 32, 16, 8};
+constexpr int kLevelC[kLevels] = {16, 32, 64, 128, 256};  // channels entering each level
+constexpr int kMaxRCells = 4;
+
+struct RBlock {
+  int ic, oc, H, W, act, slot;
+  bool skipconv;
+  ConvGeom g1, g2, gs;
+  const float* x;
+  float *m0, *r0, *y1, *s, *c1, *m1, *r1, *y2, *out;
+};
+
+struct CellTape {
+  // time-major [T][B][P][.]
+  float *xh, *cat2, *r, *z, *n, *h, *h0;
+};
+
+struct RNet {
+  eve_refinenet_params p;
+  int N, B, T, nf;
+  std::vector<std::string> names;
+  int slot_initial, slot_final, slot_rnn;
+  ConvGeom gi0, gi3, gf0, gf2;
+  float *x0, *i0, *im, *ir, *i1, *i2;
+  std::vector<RBlock> enc[kLevels];
+  RBlock dec[kLevels];
+  float* pooled[kLevels];
+  int32_t* pidx[kLevels];
+  float* cat[kLevels];    // decoder inputs
+  float* inner[kLevels];  // output of the module wrapped by level l (at level l+1 resolution)
+  float *bx, *by;         // bottleneck in/out, time-major [T][B][P][nf]
+  CellTape cell[kMaxRCells];
+  float *f0, *f1, *f2, *sig;
+  size_t max_act;
+};
+
+void add_block_names(std::vector<std::string>& v, const std::string& p, bool skip) {
+  const char* base[] = {"layers.0.weight", "layers.0.bias", "layers.2.weight", "layers.2.bias",
+                        "layers.3.weight", "layers.3.bias", "layers.5.weight", "layers.5.bias"};
+  for (const char* b : base) v.push_back(p + b);
+  if (skip) {
+    const char* sk[] = {"skip_layer.0.weight", "skip_layer.0.bias", "skip_layer.2.weight",
+                        "skip_layer.2.bias"};
+    for (const char* b : sk) v.push_back(p + b);
+  }
+}
+
+RBlock make_block(int N, int ic, int oc, int H, int W, int act, int slot) {
+  RBlock k;
+  k.ic = ic; k.oc = oc; k.H = H; k.W = W; k.act = act; k.slot = slot;
+  k.skipconv = ic != oc;
+  k.g1 = make_conv(N, H, W, ic, oc, 3, 1, 1);
+  k.g2 = make_conv(N, H, W, oc, oc, 3, 1, 1);
+  k.gs = make_conv(N, H, W, ic, oc, 1, 1, 0);
+  k.x = nullptr;
+  return k;
+}
+
+void alloc_block(RBlock& k, int N, Arena& sv, size_t& max_act) {
+  size_t pin = (size_t)N * k.H * k.W * k.ic, pout = (size_t)N * k.H * k.W * k.oc;
+  k.m0 = sv.get<float>((size_t)N * k.ic);
+  k.r0 = sv.get<float>((size_t)N * k.ic);
+  k.y1 = sv.get<float>(pin);
+  k.s = k.skipconv ? sv.get<float>(pin) : nullptr;
+  k.c1 = sv.get<float>(pout);
+  k.m1 = sv.get<float>((size_t)N * k.oc);
+  k.r1 = sv.get<float>((size_t)N * k.oc);
+  k.y2 = sv.get<float>(pout);
+  k.out = sv.get<float>(pout);
+  if (pin > max_act) max_act = pin;
+  if (pout > max_act) max_act = pout;
+}
+
+int check_refine(const eve_refinenet_params* p) {
+  EVE_REQUIRE(p, EVE_ERR_NULL, "refinenet: params is NULL");
+  EVE_REQUIRE(p->batch >= 0 && p->steps >= 0, EVE_ERR_SHAPE, "refinenet: bad batch/steps");
+  EVE_REQUIRE(p->in_channels == 4 || p->in_channels == 1, EVE_ERR_CONFIG,
+              "refinenet: in_channels must be 4 (screen + heatmap) or 1, got %d", p->in_channels);
+  EVE_REQUIRE(p->nf > 0 && p->nf % 4 == 0 && p->nf <= 512, EVE_ERR_CONFIG,
+              "refinenet: refine_net_num_features=%d unsupported", p->nf);
+  EVE_REQUIRE(p->rnn_type >= EVE_CRNN_NONE && p->rnn_type <= EVE_CRNN_CGRU, EVE_ERR_CONFIG,
+              "Unknown RNN type for RefineNet: %d", p->rnn_type);
+  EVE_REQUIRE(p->rnn_type == EVE_CRNN_NONE || (p->rnn_cells >= 1 && p->rnn_cells <= kMaxRCells),
+              EVE_ERR_CONFIG, "refinenet: rnn_cells=%d unsupported (1..%d)", p->rnn_cells,
+              kMaxRCells);
+  return EVE_OK;
+}
+
+// Builds names, geometry and (when `sv` is real or dry) the saved-activation layout.
+bool build_rnet(const eve_refinenet_params& p, Arena& sv, RNet& n) {
+  n.p = p;
+  n.B = p.batch; n.T = p.steps; n.N = p.batch * p.steps; n.nf = p.nf;
+  const int N = n.N;
+  n.max_act = 0;
+  auto& nm = n.names;
+  nm.clear();
+  n.slot_initial = 0;
+  for (const char* s : {"initial.0.weight", "initial.0.bias", "initial.1.weight", "initial.1.bias",
+                        "initial.3.weight", "initial.3.bias"})
+    nm.push_back(s);
+  // ---- geometry + names
+  std::string prefix = "network.";
+  const int nenc[kLevels] = {1, 2, 2, 2, 2};
+  for (int l = 0; l < kLevels; ++l) {
+    const int c = kLevelC[l];
+    const int bic = l + 1 < kLevels ? kLevelC[l + 1] : p.nf;
+    const int H = kLevelH[l], W = kLevelW[l];
+    n.enc[l].clear();
+    for (int j = 0; j < nenc[l]; ++j) {
+      int ic = j == 0 ? c : bic;
+      n.enc[l].push_back(make_block(N, ic, bic, H, W, ACT_RELU, (int)nm.size()));
+      add_block_names(nm, prefix + "encoder_blocks." + std::to_string(j) + ".", ic != bic);
+    }
+    const int dic = bic + (p.use_skip ? bic : 0);
+    n.dec[l] = make_block(N, dic, c, H, W, ACT_LEAKY, (int)nm.size());
+    add_block_names(nm, prefix + "decoder_blocks.0.", dic != c);
+    prefix += "between_module.";
+  }
+  n.slot_rnn = (int)nm.size();
+  if (p.rnn_type != EVE_CRNN_NONE) {
+    for (int i = 0; i < p.rnn_cells; ++i) {
+      std::string q = prefix + "rnn_cells." + std::to_string(i) + ".";
+      if (p.rnn_type == EVE_CRNN_CRNN) {
+        nm.push_back(q + "cell.weight"); nm.push_back(q + "cell.bias");
+      } else if (p.rnn_type == EVE_CRNN_CLSTM) {
+        nm.push_back(q + "gates.weight"); nm.push_back(q + "gates.bias");
+      } else {
+        nm.push_back(q + "gates_1.weight"); nm.push_back(q + "gates_1.bias");
+        nm.push_back(q + "gate_2.weight"); nm.push_back(q + "gate_2.bias");
+      }
+    }
+  }
+  n.slot_final = (int)nm.size();
+  for (const char* s : {"final.0.weight", "final.0.bias", "final.2.weight", "final.2.bias"})
+    nm.push_back(s);
+
+  // ---- saved activations
+  const int H0 = kLevelH[0], W0 = kLevelW[0];
+  const size_t P0 = (size_t)N * H0 * W0;
+  n.gi0 = make_conv(N, H0, W0, p.in_channels, 16, 3, 1, 1);
+  n.gi3 = make_conv(N, H0, W0, 16, 16, 3, 1, 1);
+  n.gf0 = make_conv(N, H0, W0, 16, 16, 3, 1, 1);
+  n.gf2 = make_conv(N, H0, W0, 16, 1, 1, 1, 0);
+  n.x0 = sv.get<float>(P0 * p.in_channels);
+  n.i0 = sv.get<float>(P0 * 16);
+  n.im = sv.get<float>((size_t)N * 16);
+  n.ir = sv.get<float>((size_t)N * 16);
+  n.i1 = sv.get<float>(P0 * 16);
+  n.i2 = sv.get<float>(P0 * 16);
+  n.max_act = P0 * 16;
+  const float* cur = n.i2;
+  for (int l = 0; l < kLevels; ++l) {
+    for (auto& k : n.enc[l]) {
+      k.x = cur;
+      alloc_block(k, N, sv, n.max_act);
+      cur = k.out;
+    }
+    const int bic = n.enc[l].back().oc;
+    if (l + 1 < kLevels) {
+      size_t pe = (size_t)N * kLevelH[l + 1] * kLevelW[l + 1] * bic;
+      n.pooled[l] = sv.get<float>(pe);
+      n.pidx[l] = sv.get<int32_t>(pe);
+      cur = n.pooled[l];
+    } else {
+      n.pooled[l] = nullptr;
+      n.pidx[l] = nullptr;
+    }
+  }
+  // bottleneck (time-major)
+  const int P = kLevelH[4] * kLevelW[4];
+  const size_t be = (size_t)N * P * p.nf;
+  n.bx = sv.get<float>(be);
+  n.by = sv.get<float>(be);
+  for (int i = 0; i < kMaxRCells; ++i) n.cell[i] = CellTape{};
+  if (p.rnn_type == EVE_CRNN_CGRU || p.rnn_type == EVE_CRNN_CRNN) {
+    for (int i = 0; i < p.rnn_cells; ++i) {
+      CellTape& c = n.cell[i];
+      c.xh = sv.get<float>(be * 2);
+      c.h = sv.get<float>(be);
+      c.h0 = sv.get<float>((size_t)n.B * P * p.nf);
+      if (p.rnn_type == EVE_CRNN_CGRU) {
+        c.cat2 = sv.get<float>(be * 2);
+        c.r = sv.get<float>(be);
+        c.z = sv.get<float>(be);
+        c.n = sv.get<float>(be);
+      }
+    }
+  }
+  // decoder, innermost first
+  for (int l = kLevels - 1; l >= 0; --l) {
+    RBlock& k = n.dec[l];
+    n.cat[l] = sv.get<float>((size_t)N * k.H * k.W * k.ic);
+    k.x = n.cat[l];
+    alloc_block(k, N, sv, n.max_act);
+  }
+  n.f0 = sv.get<float>(P0 * 16);
+  n.f1 = sv.get<float>(P0 * 16);
+  n.sig = sv.get<float>(P0);
+  return sv.ok();
+}
+
+// ------------------------------------------------------------------ small kernels --
+// x0[n,h,w,4] = (screen[n,0..2,h,w], heatmap[n,0,h,w])
+__global__ void __launch_bounds__(256)
+pack_input_kernel(const float* __restrict__ screen, const float* __restrict__ hm, long long total,
+                  int HW, float* __restrict__ x0) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long n = i / HW;
+  int p = (int)(i % HW);
+  const float* sp = screen + n * 3 * HW + p;
+  reinterpret_cast<float4*>(x0)[i] = make_float4(sp[0], sp[HW], sp[2 * HW], hm[i]);
+}
+
+// x[A][Bd][P][ldx] (first C channels) -> y[Bd][A][P][ldy] (first C channels)
+__global__ void __launch_bounds__(256)
+swap_bt_kernel(const float* __restrict__ x, long long total, int A, int Bd, int P, int C, int ldx,
+               float* __restrict__ y, int ldy) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long t = i / C;
+  int p = (int)(t % P);
+  t /= P;
+  int b = (int)(t % Bd);
+  int a = (int)(t / Bd);
+  y[(((size_t)b * A + a) * P + p) * ldy + c] = x[(((size_t)a * Bd + b) * P + p) * ldx + c];
+}
+
+// xh[row, 0:nf] = x[row], xh[row, nf:2nf] = h[row]
+__global__ void __launch_bounds__(256)
+cat2_kernel(const float* __restrict__ a, const float* __restrict__ b, long long rows, int nf,
+            float* __restrict__ y) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 2 * nf) return;
+  int c = (int)(i % (2 * nf));
+  long long r = i / (2 * nf);
+  y[i] = c < nf ? a[r * nf + c] : b[r * nf + c - nf];
+}
+
+// CGRU middle: g1[row, 2nf] (pre-sigmoid) -> r, z; cat2 = [r*h, x]
+__global__ void __launch_bounds__(256)
+cgru_mid_kernel(const float* __restrict__ g1, const float* __restrict__ x,
+                const float* __restrict__ h, long long rows, int nf, float* __restrict__ r,
+                float* __restrict__ z, float* __restrict__ cat2) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * nf) return;
+  int c = (int)(i % nf);
+  long long row = i / nf;
+  float rv = 1.f / (1.f + expf(-g1[row * 2 * nf + c]));
+  float zv = 1.f / (1.f + expf(-g1[row * 2 * nf + nf + c]));
+  r[i] = rv;
+  z[i] = zv;
+  cat2[row * 2 * nf + c] = rv * h[i];
+  cat2[row * 2 * nf + nf + c] = x[i];
+}
+
+// CGRU out: n = tanh(g2); h' = (1-z) n + z h
+__global__ void __launch_bounds__(256)
+cgru_out_kernel(const float* __restrict__ g2, const float* __restrict__ z,
+                const float* __restrict__ h, long long total, float* __restrict__ n,
+                float* __restrict__ hn) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float nv = tanhf(g2[i]);
+  float zv = z[i];
+  n[i] = nv;
+  hn[i] = (1.f - zv) * nv + zv * h[i];
+}
+
+// CGRU backward, first half: dh' -> dg2pre, dz (kept), direct dh
+__global__ void __launch_bounds__(256)
+cgru_bwd1_kernel(const float* __restrict__ dhn, const float* __restrict__ dcarry,
+                 const float* __restrict__ z, const float* __restrict__ n,
+                 const float* __restrict__ h, long long total, float* __restrict__ dg2,
+                 float* __restrict__ dzbuf, float* __restrict__ dhdir) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float d = dhn[i] + (dcarry ? dcarry[i] : 0.f);
+  float zv = z[i], nv = n[i];
+  dg2[i] = d * (1.f - zv) * (1.f - nv * nv);
+  dzbuf[i] = d * (h[i] - nv) * zv * (1.f - zv);  // already through the sigmoid
+  dhdir[i] = d * zv;
+}
+
+// CGRU backward, second half: dcat2 = [d(rh), dx2] -> dg1pre = [dr*r(1-r), dz']; dh += d(rh)*r
+__global__ void __launch_bounds__(256)
+cgru_bwd2_kernel(const float* __restrict__ dcat2, const float* __restrict__ r,
+                 const float* __restrict__ h, const float* __restrict__ dzbuf, long long rows,
+                 int nf, float* __restrict__ dg1, float* __restrict__ dhdir) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * nf) return;
+  int c = (int)(i % nf);
+  long long row = i / nf;
+  float drh = dcat2[row * 2 * nf + c];
+  float rv = r[i];
+  dg1[row * 2 * nf + c] = drh * h[i] * rv * (1.f - rv);
+  dg1[row * 2 * nf + nf + c] = dzbuf[i];
+  dhdir[i] += drh * rv;
+}
+
+// dx = dcat2[:, nf:] + dxh[:, :nf] ; dh_carry = dhdir + dxh[:, nf:]
+__global__ void __launch_bounds__(256)
+cgru_bwd3_kernel(const float* __restrict__ dcat2, const float* __restrict__ dxh,
+                 const float* __restrict__ dhdir, long long rows, int nf, float* __restrict__ dx,
+                 float* __restrict__ dcarry) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * nf) return;
+  int c = (int)(i % nf);
+  long long row = i / nf;
+  dx[i] = (dcat2 ? dcat2[row * 2 * nf + nf + c] : 0.f) + dxh[row * 2 * nf + c];
+  dcarry[i] = (dhdir ? dhdir[i] : 0.f) + dxh[row * 2 * nf + nf + c];
+}
+
+// CRNN backward: dpre = (dh' + carry) * (1 - h'^2)
+__global__ void __launch_bounds__(256)
+crnn_bwd_kernel(const float* __restrict__ dhn, const float* __restrict__ dcarry,
+                const float* __restrict__ hn, long long total, float* __restrict__ dpre) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float d = dhn[i] + (dcarry ? dcarry[i] : 0.f);
+  float v = hn[i];
+  dpre[i] = d * (1.f - v * v);
+}
+
+// CLSTM pointwise: gates[row,4nf] = (in, forget, out, cell) pre-activation (common.py:376)
+__global__ void __launch_bounds__(256)
+clstm_out_kernel(const float* __restrict__ gates, const float* __restrict__ c, long long rows,
+                 int nf, float* __restrict__ hn, float* __restrict__ cn) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * nf) return;
+  int ch = (int)(i % nf);
+  long long row = i / nf;
+  const float* g = gates + row * 4 * nf + ch;
+  float ig = 1.f / (1.f + expf(-g[0]));
+  float fg = 1.f / (1.f + expf(-g[nf]));
+  float og = 1.f / (1.f + expf(-g[2 * nf]));
+  float cg = tanhf(g[3 * nf]);
+  float cv = fg * c[i] + ig * cg;
+  cn[i] = cv;
+  hn[i] = og * tanhf(cv);
+}
+
+#define LAUNCH1D(kernel, total, ...)                                      \
+  do {                                                                    \
+    long long tot__ = (total);                                            \
+    if (tot__ > 0) {                                                      \
+      kernel<<<cdiv(tot__, 256), 256, 0, s>>>(__VA_ARGS__);               \
+      EVE_LAUNCH_CHECK();                                                 \
+    }                                                                     \
+  } while (0)
+
+// ------------------------------------------------------------------ block fwd/bwd --
+int block_fwd(const RBlock& k, int N, const float* const* w, float* wf, cudaStream_t s) {
+  const float* const* bw = w + k.slot;
+  const int HW = k.H * k.W;
+  EVE_TRY(in_stats(k.x, N, HW, k.ic, k.m0, k.r0, s));
+  EVE_TRY(in_apply(k.x, N, HW, k.ic, k.m0, k.r0, bw[0], bw[1], nullptr, nullptr, nullptr, k.act,
+                   k.y1, s));
+  EVE_TRY(conv_prep_weights(k.g1, bw[2], wf, nullptr, s));
+  EVE_TRY(conv_fwd_simt(k.g1, k.y1, wf, bw[3], nullptr, k.c1, k.oc, s));
+  EVE_TRY(in_stats(k.c1, N, HW, k.oc, k.m1, k.r1, s));
+  EVE_TRY(in_apply(k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], nullptr, nullptr, nullptr, k.act,
+                   k.y2, s));
+  const float* addend = k.x;
+  if (k.skipconv) {
+    EVE_TRY(in_apply(k.x, N, HW, k.ic, k.m0, k.r0, bw[8], bw[9], nullptr, nullptr, nullptr, k.act,
+                     k.s, s));
+    EVE_TRY(conv_prep_weights(k.gs, bw[10], wf, nullptr, s));
+    EVE_TRY(conv_fwd_simt(k.gs, k.s, wf, bw[11], nullptr, k.out, k.oc, s));
+    addend = k.out;
+  }
+  EVE_TRY(conv_prep_weights(k.g2, bw[6], wf, nullptr, s));
+  EVE_TRY(conv_fwd_simt(k.g2, k.y2, wf, bw[7], addend, k.out, k.oc, s));
+  return EVE_OK;
+}
+
+struct BwdScratch {
+  float *wd, *wg, *inb, *t0, *t1, *t2, *ga, *gb;
+};
+
+int conv_param_grads(const ConvGeom& g, const float* x, const float* dy, float* dw, float* db,
+                     float* wg, bool acc, cudaStream_t s) {
+  if (dw) EVE_TRY(conv_wgrad_simt(g, x, dy, g.Cout, dw, wg, acc, s));
+  if (db) EVE_TRY(colsum(dy, (long long)g.N * g.OH * g.OW, g.Cout, g.Cout, db, wg, acc, s));
+  return EVE_OK;
+}
+
+// dout -> dx (grad w.r.t. k.x).  dx must not alias t0..t2.
+int block_bwd(const RBlock& k, int N, const float* const* w, float* const* gr, bool acc,
+              const float* dout, float* dx, const BwdScratch& sc, cudaStream_t s) {
+  const float* const* bw = w + k.slot;
+  float* const* bg = gr + k.slot;
+  const int HW = k.H * k.W;
+  EVE_TRY(conv_param_grads(k.g2, k.y2, dout, bg[6], bg[7], sc.wg, acc, s));
+  EVE_TRY(conv_prep_weights(k.g2, bw[6], nullptr, sc.wd, s));
+  EVE_TRY(conv_dgrad_simt(k.g2, dout, k.oc, sc.wd, nullptr, sc.t0, s));
+  EVE_TRY(in_backward(sc.t0, k.y2, k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], k.act, nullptr,
+                      sc.t1, nullptr, bg[4], bg[5], sc.inb, acc, s));
+  EVE_TRY(conv_param_grads(k.g1, k.y1, sc.t1, bg[2], bg[3], sc.wg, acc, s));
+  EVE_TRY(conv_prep_weights(k.g1, bw[2], nullptr, sc.wd, s));
+  EVE_TRY(conv_dgrad_simt(k.g1, sc.t1, k.oc, sc.wd, nullptr, sc.t0, s));
+  const float* addend = dout;
+  if (k.skipconv) {
+    EVE_TRY(conv_param_grads(k.gs, k.s, dout, bg[10], bg[11], sc.wg, acc, s));
+    EVE_TRY(conv_prep_weights(k.gs, bw[10], nullptr, sc.wd, s));
+    EVE_TRY(conv_dgrad_simt(k.gs, dout, k.oc, sc.wd, nullptr, sc.t2, s));
+    EVE_TRY(in_backward(sc.t2, k.s, k.x, N, HW, k.ic, k.m0, k.r0, bw[8], bw[9], k.act, nullptr,
+                        sc.t1, nullptr, bg[8], bg[9], sc.inb, acc, s));
+    addend = sc.t1;
+  }
+  EVE_TRY(in_backward(sc.t0, k.y1, k.x, N, HW, k.ic, k.m0, k.r0, bw[0], bw[1], k.act, addend, dx,
+                      nullptr, bg[0], bg[1], sc.inb, acc, s));
+  return EVE_OK;
+}
+
+size_t rnet_wmax(const RNet& n) {
+  size_t m = (size_t)512 * 128 * 9;  // decoder level 3: 512 -> 128
+  size_t c = (size_t)4 * n.nf * 2 * n.nf * 9;
+  return m > c ? m : c;
+}
+
+bool build_bwd_scratch(const RNet& n, Arena& ws, BwdScratch& sc) {
+  sc.wd = ws.get<float>(rnet_wmax(n));
+  size_t wg = 0;
+  auto upd = [&](const ConvGeom& g) {
+    size_t v = conv_wgrad_scratch_floats(g);
+    size_t c = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
+    if (v > wg) wg = v;
+    if (c > wg) wg = c;
+  };
+  upd(n.gi0); upd(n.gi3); upd(n.gf0); upd(n.gf2);
+  for (int l = 0; l < kLevels; ++l) {
+    for (auto& k : n.enc[l]) { upd(k.g1); upd(k.g2); upd(k.gs); }
+    upd(n.dec[l].g1); upd(n.dec[l].g2); upd(n.dec[l].gs);
+  }
+  ConvGeom gc = make_conv(n.N, kLevelH[4], kLevelW[4], 2 * n.nf, 4 * n.nf, 3, 1, 1);
+  upd(gc);
+  sc.wg = ws.get<float>(wg);
+  sc.inb = ws.get<float>(in_backward_scratch_floats(n.N, 512));
+  sc.t0 = ws.get<float>(n.max_act);
+  sc.t1 = ws.get<float>(n.max_act);
+  sc.t2 = ws.get<float>(n.max_act);
+  sc.ga = ws.get<float>(n.max_act);
+  sc.gb = ws.get<float>(n.max_act);
+  return ws.ok();
+}
+
+// Backward-only scratch beyond BwdScratch.
+struct BwdExtra {
+  float* dskip[kLevels];      // grad w.r.t. the encoder output of level l coming from the concat
+  float* cb[6];               // bottleneck temporaries, each B*P*4nf
+  float* dcarry[kMaxRCells];  // B*P*nf
+  float *dby, *dbx;           // time-major [T][B][P][nf]
+  float* dg1all[kMaxRCells];  // [T][B][P][2nf]
+  float* dg2all[kMaxRCells];  // [T][B][P][nf]
+  float* cellwd;              // dgrad weight layouts of every cell
+};
+
+bool build_bwd_extra(const RNet& n, Arena& ws, BwdExtra& e) {
+  for (int l = 0; l < kLevels; ++l) {
+    const RBlock& k = n.enc[l].back();
+    e.dskip[l] = n.p.use_skip ? ws.get<float>((size_t)n.N * k.H * k.W * k.oc) : nullptr;
+  }
+  const int P = kLevelH[4] * kLevelW[4];
+  for (int i = 0; i < 6; ++i) e.cb[i] = ws.get<float>((size_t)n.B * P * 4 * n.nf);
+  size_t be = (size_t)n.N * P * n.nf;
+  e.dby = ws.get<float>(be);
+  e.dbx = ws.get<float>(be);
+  const bool rec = n.p.rnn_type == EVE_CRNN_CGRU || n.p.rnn_type == EVE_CRNN_CRNN;
+  for (int i = 0; i < kMaxRCells; ++i) {
+    bool on = rec && i < n.p.rnn_cells;
+    e.dcarry[i] = on ? ws.get<float>((size_t)n.B * P * n.nf) : nullptr;
+    e.dg1all[i] = on ? ws.get<float>(be * 2) : nullptr;
+    e.dg2all[i] = on && n.p.rnn_type == EVE_CRNN_CGRU ? ws.get<float>(be) : nullptr;
+  }
+  e.cellwd = ws.get<float>((size_t)kMaxRCells * 4 * n.nf * 2 * n.nf * 9);
+  return ws.ok();
+}
+
+inline size_t rnet_cellw_floats(const RNet& n) {
+  return (size_t)kMaxRCells * 4 * n.nf * 2 * n.nf * 9;
+}
+
+size_t rnet_fwd_scratch_bytes(const RNet& n) {
+  const int P = kLevelH[4] * kLevelW[4];
+  return align_up(rnet_wmax(n) * sizeof(float), 256) +
+         align_up(rnet_cellw_floats(n) * sizeof(float), 256) +
+         4 * align_up((size_t)n.B * P * 4 * n.nf * sizeof(float), 256) +
+         2 * align_up((size_t)kMaxRCells * n.B * P * n.nf * sizeof(float), 256) + 4096;
+}
+
+}  // namespace
+}  // namespace eve
+
+using namespace eve;
+
+extern "C" int eve_refinenet_num_weights(const eve_refinenet_params* p) {
+  if (check_refine(p) != EVE_OK) return -1;
+  Arena sv(nullptr, 0);
+  RNet n;
+  build_rnet(*p, sv, n);
+  return (int)n.names.size();
+}
+
+extern "C" const char* eve_refinenet_weight_name(const eve_refinenet_params* p, int i) {
+  static thread_local std::string name;
+  if (check_refine(p) != EVE_OK) return nullptr;
+  Arena sv(nullptr, 0);
+  RNet n;
+  build_rnet(*p, sv, n);
+  if (i < 0 || i >= (int)n.names.size()) return nullptr;
+  name = n.names[i];
+  return name.c_str();
+}
+
+extern "C" size_t eve_refinenet_saved_bytes(const eve_refinenet_params* p) {
+  if (check_refine(p) != EVE_OK) return 0;
+  Arena sv(nullptr, 0);
+  RNet n;
+  build_rnet(*p, sv, n);
+  return sv.off + 256;
+}
+
+extern "C" size_t eve_refinenet_workspace_bytes(const eve_refinenet_params* p) {
+  if (check_refine(p) != EVE_OK) return 0;
+  Arena sv(nullptr, 0);
+  RNet n;
+  build_rnet(*p, sv, n);
+  Arena ws(nullptr, 0);
+  BwdScratch sc;
+  BwdExtra ex;
+  build_bwd_scratch(n, ws, sc);
+  build_bwd_extra(n, ws, ex);
+  size_t f = rnet_fwd_scratch_bytes(n);
+  return (ws.off > f ? ws.off : f) + 256;
+}
+
+extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* screen,
+                                 const float* heatmap, const float* h0, const float* c0,
+                                 const float* const* w, float* out, float* hT, float* cT,
+                                 void* saved, size_t saved_bytes, void* workspace,
+                                 size_t workspace_bytes, eve_stream_t stream) {
+  EVE_TRY(check_refine(p));
+  if (p->batch == 0 || p->steps == 0) return EVE_OK;
+  EVE_REQUIRE(heatmap && w && out && saved && workspace, EVE_ERR_NULL,
+              "refinenet_fwd: NULL pointer");
+  EVE_REQUIRE(p->in_channels == 1 || screen, EVE_ERR_NULL, "refinenet_fwd: screen is NULL");
+  cudaStream_t s = as_stream(stream);
+  Arena sv(saved, saved_bytes);
+  RNet n;
+  EVE_REQUIRE(build_rnet(*p, sv, n), EVE_ERR_WORKSPACE,
+              "refinenet_fwd: saved buffer too small (%zu < %zu)", saved_bytes, sv.off);
+  EVE_REQUIRE(workspace_bytes >= rnet_fwd_scratch_bytes(n), EVE_ERR_WORKSPACE,
+              "refinenet_fwd: workspace too small");
+  Arena ws(workspace, workspace_bytes);
+  const int N = n.N, B = n.B, T = n.T, nf = n.nf;
+  const int P = kLevelH[4] * kLevelW[4];
+  float* wf = ws.get<float>(rnet_wmax(n));
+  float* cellw = ws.get<float>(rnet_cellw_floats(n));
+  float* cb[4];
+  for (int i = 0; i < 4; ++i) cb[i] = ws.get<float>((size_t)B * P * 4 * nf);
+  float* h0n = ws.get<float>((size_t)kMaxRCells * B * P * nf);
+  float* c0n = ws.get<float>((size_t)kMaxRCells * B * P * nf);
+  const int HW0 = kLevelH[0] * kLevelW[0];
+
+  // ---- input + initial
+  if (p->in_channels == 4) {
+    LAUNCH1D(pack_input_kernel, (long long)N * HW0, screen, heatmap, (long long)N * HW0, HW0, n.x0);
+  } else {
+    EVE_CUDA(cudaMemcpyAsync(n.x0, heatmap, (size_t)N * HW0 * sizeof(float),
+                             cudaMemcpyDeviceToDevice, s));
+  }
+  EVE_TRY(conv_prep_weights(n.gi0, w[0], wf, nullptr, s));
+  EVE_TRY(conv_fwd_simt(n.gi0, n.x0, wf, w[1], nullptr, n.i0, 16, s));
+  EVE_TRY(in_stats(n.i0, N, HW0, 16, n.im, n.ir, s));
+  EVE_TRY(in_apply(n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], nullptr, nullptr, nullptr, ACT_RELU,
+                   n.i1, s));
+  EVE_TRY(conv_prep_weights(n.gi3, w[4], wf, nullptr, s));
+  EVE_TRY(conv_fwd_simt(n.gi3, n.i1, wf, w[5], nullptr, n.i2, 16, s));
+  // ---- encoder
+  for (int l = 0; l < kLevels; ++l) {
+    for (auto& k : n.enc[l]) EVE_TRY(block_fwd(k, N, w, wf, s));
+    if (l + 1 < kLevels) {
+      const RBlock& k = n.enc[l].back();
+      EVE_TRY(adaptive_maxpool_fwd(k.out, N, k.H, k.W, k.oc, kLevelH[l + 1], kLevelW[l + 1],
+                                   n.pooled[l], n.pidx[l], s));
+    }
+  }
+  // ---- bottleneck over time (time-major)
+  const float* benc = n.enc[4].back().out;  // [B][T][P][nf]
+  const long long E = (long long)P * nf;
+  const long long rows = (long long)B * P;
+  LAUNCH1D(swap_bt_kernel, (long long)N * E, benc, (long long)N * E, B, T, P, nf, nf, n.bx, nf);
+  const float* bout = n.bx;  // what the decoder sees
+  if (p->rnn_type != EVE_CRNN_NONE) {
+    const int nc = p->rnn_cells;
+    if (h0) EVE_TRY(nchw_to_nhwc(h0, nc * B, nf, kLevelH[4], kLevelW[4], h0n, s));
+    else EVE_TRY(fill_zero(h0n, (long long)nc * B * E, s));
+    if (p->rnn_type == EVE_CRNN_CLSTM) {
+      if (c0) EVE_TRY(nchw_to_nhwc(c0, nc * B, nf, kLevelH[4], kLevelW[4], c0n, s));
+      else EVE_TRY(fill_zero(c0n, (long long)nc * B * E, s));
+    }
+    if (p->rnn_type == EVE_CRNN_CLSTM) {
+      // refine_net.py:168-174: with tuple states the features handed on are NOT updated, so
+      // every cell sees the encoder features and the decoder input is unchanged.
+      ConvGeom gg = make_conv(B, kLevelH[4], kLevelW[4], 2 * nf, 4 * nf, 3, 1, 1);
+      for (int i = 0; i < nc; ++i) {
+        const float* const* cw = w + n.slot_rnn + 2 * i;
+        EVE_TRY(conv_prep_weights(gg, cw[0], wf, nullptr, s));
+        float* hcur = h0n + (size_t)i * B * E;
+        float* ccur = c0n + (size_t)i * B * E;
+        for (int t = 0; t < T; ++t) {
+          const float* xt = n.bx + (size_t)t * B * E;
+          LAUNCH1D(cat2_kernel, rows * 2 * nf, xt, hcur, rows, nf, cb[0]);
+          EVE_TRY(conv_fwd_simt(gg, cb[0], wf, cw[1], nullptr, cb[1], 4 * nf, s));
+          LAUNCH1D(clstm_out_kernel, rows * nf, cb[1], ccur, rows, nf, hcur, ccur);
+        }
+      }
+    } else {
+      const bool gru = p->rnn_type == EVE_CRNN_CGRU;
+      ConvGeom g1 = make_conv(B, kLevelH[4], kLevelW[4], 2 * nf, gru ? 2 * nf : nf, 3, 1, 1);
+      ConvGeom g2 = make_conv(B, kLevelH[4], kLevelW[4], 2 * nf, nf, 3, 1, 1);
+      const int wpc = gru ? 4 : 2;
+      // weight copies for both convs of every cell stay resident in the scratch
+      float* wf1[kMaxRCells];
+      float* wf2[kMaxRCells];
+      {
+        float* q = cellw;
+        for (int i = 0; i < nc; ++i) {
+          const float* const* cw = w + n.slot_rnn + wpc * i;
+          wf1[i] = q; q += (size_t)g1.Cout * g1.K();
+          EVE_TRY(conv_prep_weights(g1, cw[0], wf1[i], nullptr, s));
+          wf2[i] = nullptr;
+          if (gru) {
+            wf2[i] = q; q += (size_t)g2.Cout * g2.K();
+            EVE_TRY(conv_prep_weights(g2, cw[2], wf2[i], nullptr, s));
+          }
+        }
+      }
+      for (int i = 0; i < nc; ++i)
+        EVE_CUDA(cudaMemcpyAsync(n.cell[i].h0, h0n + (size_t)i * B * E, (size_t)B * E * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
+      for (int t = 0; t < T; ++t) {
+        const float* xt = n.bx + (size_t)t * B * E;
+        for (int i = 0; i < nc; ++i) {
+          CellTape& c = n.cell[i];
+          const float* const* cw = w + n.slot_rnn + wpc * i;
+          const float* hprev = t == 0 ? c.h0 : c.h + (size_t)(t - 1) * B * E;
+          float* xh = c.xh + (size_t)t * B * E * 2;
+          float* hn = c.h + (size_t)t * B * E;
+          LAUNCH1D(cat2_kernel, rows * 2 * nf, xt, hprev, rows, nf, xh);
+          if (gru) {
+            float* rr = c.r + (size_t)t * B * E;
+            float* zz = c.z + (size_t)t * B * E;
+            float* nn = c.n + (size_t)t * B * E;
+            float* cat2 = c.cat2 + (size_t)t * B * E * 2;
+            EVE_TRY(conv_fwd_simt(g1, xh, wf1[i], cw[1], nullptr, cb[0], 2 * nf, s));
+            LAUNCH1D(cgru_mid_kernel, rows * nf, cb[0], xt, hprev, rows, nf, rr, zz, cat2);
+            EVE_TRY(conv_fwd_simt(g2, cat2, wf2[i], cw[3], nullptr, cb[1], nf, s));
+            LAUNCH1D(cgru_out_kernel, rows * nf, cb[1], zz, hprev, rows * nf, nn, hn);
+          } else {
+            EVE_TRY(conv_fwd_simt(g1, xh, wf1[i], cw[1], nullptr, cb[0], nf, s));
+            EVE_TRY(ew_fwd(EW_TANH, cb[0], rows * nf, hn, s));
+          }
+          xt = hn;
+        }
+        EVE_CUDA(cudaMemcpyAsync(n.by + (size_t)t * B * E, xt, (size_t)B * E * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
+      }
+      bout = n.by;
+      for (int i = 0; i < nc; ++i)
+        EVE_CUDA(cudaMemcpyAsync(h0n + (size_t)i * B * E, n.cell[i].h + (size_t)(T - 1) * B * E,
+                                 (size_t)B * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    if (hT) EVE_TRY(nhwc_to_nchw(h0n, nc * B, nf, kLevelH[4], kLevelW[4], hT, s));
+    if (cT && p->rnn_type == EVE_CRNN_CLSTM)
+      EVE_TRY(nhwc_to_nchw(c0n, nc * B, nf, kLevelH[4], kLevelW[4], cT, s));
+  }
+  // ---- decoder, innermost first.  cat[l] = [module output (upsampled), encoder skip]
+  {
+    const RBlock& k = n.dec[4];
+    // time-major bottleneck output back to batch-major, straight into the concat buffer
+    LAUNCH1D(swap_bt_kernel, (long long)N * E, bout, (long long)N * E, T, B, P, nf, nf, n.cat[4],
+             k.ic);
+    if (p->use_skip)
+      EVE_TRY(copy_channels(n.enc[4].back().out, (long long)N * P, nf, nf, 0, n.cat[4], k.ic, nf,
+                            false, s));
+    EVE_TRY(block_fwd(k, N, w, wf, s));
+  }
+  for (int l = 3; l >= 0; --l) {
+    const RBlock& k = n.dec[l];
+    const RBlock& inner = n.dec[l + 1];
+    const RBlock& e = n.enc[l].back();
+    EVE_TRY(upsample_bilinear_fwd(inner.out, N, inner.H, inner.W, inner.oc, k.H, k.W, n.cat[l],
+                                  k.ic, 0, s));
+    if (p->use_skip)
+      EVE_TRY(copy_channels(e.out, (long long)N * k.H * k.W, e.oc, e.oc, 0, n.cat[l], k.ic,
+                            inner.oc, false, s));
+    EVE_TRY(block_fwd(k, N, w, wf, s));
+  }
+  // ---- final: conv3x3 -> LeakyReLU -> conv1x1 -> sigmoid
+  const float* const* fw = w + n.slot_final;
+  EVE_TRY(conv_prep_weights(n.gf0, fw[0], wf, nullptr, s));
+  EVE_TRY(conv_fwd_simt(n.gf0, n.dec[0].out, wf, fw[1], nullptr, n.f0, 16, s));
+  EVE_TRY(ew_fwd(EW_LEAKY, n.f0, (long long)N * HW0 * 16, n.f1, s));
+  EVE_TRY(conv_prep_weights(n.gf2, fw[2], wf, nullptr, s));
+  EVE_TRY(conv_fwd_simt(n.gf2, n.f1, wf, fw[3], nullptr, out, 1, s));
+  EVE_TRY(ew_fwd(EW_SIGMOID, out, (long long)N * HW0, n.sig, s));
+  EVE_CUDA(cudaMemcpyAsync(out, n.sig, (size_t)N * HW0 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return EVE_OK;
+}
+
+
+extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dout,
+                                 const float* dhT, const float* dcT, const float* const* w,
+                                 float* dheatmap, float* dh0, float* dc0, float* const* gr,
+                                 int accumulate, const void* saved, size_t saved_bytes,
+                                 void* workspace, size_t workspace_bytes, eve_stream_t stream) {
+  EVE_TRY(check_refine(p));
+  if (p->batch == 0 || p->steps == 0) return EVE_OK;
+  EVE_REQUIRE(dout && w && gr && saved && workspace, EVE_ERR_NULL, "refinenet_bwd: NULL pointer");
+  EVE_REQUIRE(!(p->rnn_type == EVE_CRNN_CLSTM && (dhT || dcT)), EVE_ERR_CONFIG,
+              "refinenet_bwd: gradients into CLSTM states are not supported (the CLSTM state "
+              "never reaches the heatmap, refine_net.py:168-174)");
+  cudaStream_t s = as_stream(stream);
+  Arena sv(const_cast<void*>(saved), saved_bytes);
+  RNet n;
+  EVE_REQUIRE(build_rnet(*p, sv, n), EVE_ERR_WORKSPACE, "refinenet_bwd: saved buffer too small");
+  Arena ws(workspace, workspace_bytes);
+  BwdScratch sc;
+  BwdExtra ex;
+  bool ok = build_bwd_scratch(n, ws, sc);
+  ok = build_bwd_extra(n, ws, ex) && ok;
+  EVE_REQUIRE(ok, EVE_ERR_WORKSPACE, "refinenet_bwd: workspace too small (%zu < %zu)",
+              workspace_bytes, ws.off);
+  const int N = n.N, B = n.B, T = n.T, nf = n.nf;
+  const int P = kLevelH[4] * kLevelW[4];
+  const int HW0 = kLevelH[0] * kLevelW[0];
+  const long long E = (long long)P * nf;
+  const long long rows = (long long)B * P;
+  const bool acc = accumulate != 0;
+
+  // ---- final
+  const float* const* fw = w + n.slot_final;
+  float* const* fg = gr + n.slot_final;
+  EVE_TRY(ew_bwd(EW_SIGMOID, dout, n.sig, (long long)N * HW0, sc.t0, s));
+  EVE_TRY(conv_param_grads(n.gf2, n.f1, sc.t0, fg[2], fg[3], sc.wg, acc, s));
+  EVE_TRY(conv_prep_weights(n.gf2, fw[2], nullptr, sc.wd, s));
+  EVE_TRY(conv_dgrad_simt(n.gf2, sc.t0, 1, sc.wd, nullptr, sc.t1, s));
+  EVE_TRY(ew_bwd(EW_LEAKY, sc.t1, n.f0, (long long)N * HW0 * 16, sc.t2, s));
+  EVE_TRY(conv_param_grads(n.gf0, n.dec[0].out, sc.t2, fg[0], fg[1], sc.wg, acc, s));
+  EVE_TRY(conv_prep_weights(n.gf0, fw[0], nullptr, sc.wd, s));
+  float* cur = sc.ga;
+  float* other = sc.gb;
+  EVE_TRY(conv_dgrad_simt(n.gf0, sc.t2, 16, sc.wd, nullptr, cur, s));
+
+  // ---- decoder, outermost first
+  for (int l = 0; l < 4; ++l) {
+    const RBlock& k = n.dec[l];
+    const RBlock& inner = n.dec[l + 1];
+    const RBlock& e = n.enc[l].back();
+    EVE_TRY(block_bwd(k, N, w, gr, acc, cur, other, sc, s));
+    if (p->use_skip)
+      EVE_TRY(copy_channels(other, (long long)N * k.H * k.W, e.oc, k.ic, inner.oc, ex.dskip[l],
+                            e.oc, 0, false, s));
+    EVE_TRY(upsample_bilinear_bwd(other, k.ic, 0, N, inner.H, inner.W, inner.oc, k.H, k.W, cur, s));
+  }
+  {
+    const RBlock& k = n.dec[4];
+    EVE_TRY(block_bwd(k, N, w, gr, acc, cur, other, sc, s));
+    if (p->use_skip)
+      EVE_TRY(copy_channels(other, (long long)N * P, nf, k.ic, nf, ex.dskip[4], nf, 0, false, s));
+    // batch-major [B][T][P][ic] -> time-major [T][B][P][nf]
+    LAUNCH1D(swap_bt_kernel, (long long)N * E, other, (long long)N * E, B, T, P, nf, k.ic, ex.dby,
+             nf);
+  }
+
+  // ---- bottleneck BPTT
+  const float* dbx = ex.dby;  // pass-through unless a recurrent cell transforms the features
+  if (p->rnn_type == EVE_CRNN_CLSTM) {
+    if (!acc)
+      for (int i = 0; i < p->rnn_cells; ++i) {
+        float* const* cg = gr + n.slot_rnn + 2 * i;
+        if (cg[0]) EVE_TRY(fill_zero(cg[0], (long long)4 * nf * 2 * nf * 9, s));
+        if (cg[1]) EVE_TRY(fill_zero(cg[1], 4 * nf, s));
+      }
+    if (dh0) EVE_TRY(fill_zero(dh0, (long long)p->rnn_cells * B * E, s));
+    if (dc0) EVE_TRY(fill_zero(dc0, (long long)p->rnn_cells * B * E, s));
+  } else if (p->rnn_type != EVE_CRNN_NONE) {
+    const bool gru = p->rnn_type == EVE_CRNN_CGRU;
+    const int nc = p->rnn_cells;
+    const int wpc = gru ? 4 : 2;
+    ConvGeom g1 = make_conv(B, kLevelH[4], kLevelW[4], 2 * nf, gru ? 2 * nf : nf, 3, 1, 1);
+    ConvGeom g2 = make_conv(B, kLevelH[4], kLevelW[4], 2 * nf, nf, 3, 1, 1);
+    float* wd1[kMaxRCells];
+    float* wd2[kMaxRCells];
+    {
+      float* q = ex.cellwd;
+      for (int i = 0; i < nc; ++i) {
+        const float* const* cw = w + n.slot_rnn + wpc * i;
+        wd1[i] = q; q += (size_t)g1.Cout * g1.K();
+        EVE_TRY(conv_prep_weights(g1, cw[0], nullptr, wd1[i], s));
+        wd2[i] = nullptr;
+        if (gru) {
+          wd2[i] = q; q += (size_t)g2.Cout * g2.K();
+          EVE_TRY(conv_prep_weights(g2, cw[2], nullptr, wd2[i], s));
+        }
+      }
+    }
+    // initial carries = gradient into the final states
+    for (int i = 0; i < nc; ++i) {
+      if (dhT)
+        EVE_TRY(nchw_to_nhwc(dhT + (size_t)i * B * E, B, nf, kLevelH[4], kLevelW[4], ex.dcarry[i], s));
+      else
+        EVE_TRY(fill_zero(ex.dcarry[i], (long long)B * E, s));
+    }
+    float* dcat2 = ex.cb[0];
+    float* dzbuf = ex.cb[1];
+    float* dhdir = ex.cb[2];
+    float* dxh = ex.cb[3];
+    float* dxa = ex.cb[4];
+    float* dxb = ex.cb[5];
+    for (int t = T - 1; t >= 0; --t) {
+      const float* dcur = ex.dby + (size_t)t * B * E;
+      for (int i = nc - 1; i >= 0; --i) {
+        const CellTape& c = n.cell[i];
+        const float* hprev = t == 0 ? c.h0 : c.h + (size_t)(t - 1) * B * E;
+        float* dg1 = ex.dg1all[i] + (size_t)t * B * E * (gru ? 2 : 1);
+        float* dxo = (i == 0) ? ex.dbx + (size_t)t * B * E : (dcur == dxa ? dxb : dxa);
+        if (gru) {
+          float* dg2 = ex.dg2all[i] + (size_t)t * B * E;
+          LAUNCH1D(cgru_bwd1_kernel, rows * nf, dcur, ex.dcarry[i], c.z + (size_t)t * B * E,
+                   c.n + (size_t)t * B * E, hprev, rows * nf, dg2, dzbuf, dhdir);
+          EVE_TRY(conv_dgrad_simt(g2, dg2, nf, wd2[i], nullptr, dcat2, s));
+          LAUNCH1D(cgru_bwd2_kernel, rows * nf, dcat2, c.r + (size_t)t * B * E, hprev, dzbuf, rows,
+                   nf, dg1, dhdir);
+          EVE_TRY(conv_dgrad_simt(g1, dg1, 2 * nf, wd1[i], nullptr, dxh, s));
+          LAUNCH1D(cgru_bwd3_kernel, rows * nf, dcat2, dxh, dhdir, rows, nf, dxo, ex.dcarry[i]);
+        } else {
+          LAUNCH1D(crnn_bwd_kernel, rows * nf, dcur, ex.dcarry[i], c.h + (size_t)t * B * E,
+                   rows * nf, dg1);
+          EVE_TRY(conv_dgrad_simt(g1, dg1, nf, wd1[i], nullptr, dxh, s));
+          LAUNCH1D(cgru_bwd3_kernel, rows * nf, (const float*)nullptr, dxh, (const float*)nullptr,
+                   rows, nf, dxo, ex.dcarry[i]);
+        }
+        dcur = dxo;
+      }
+    }
+    dbx = ex.dbx;
+    // weight gradients: one batched wgrad over all T*B bottleneck images per conv
+    ConvGeom G1 = make_conv(N, kLevelH[4], kLevelW[4], 2 * nf, g1.Cout, 3, 1, 1);
+    ConvGeom G2 = make_conv(N, kLevelH[4], kLevelW[4], 2 * nf, nf, 3, 1, 1);
+    for (int i = 0; i < nc; ++i) {
+      float* const* cg = gr + n.slot_rnn + wpc * i;
+      EVE_TRY(conv_param_grads(G1, n.cell[i].xh, ex.dg1all[i], cg[0], cg[1], sc.wg, acc, s));
+      if (gru)
+        EVE_TRY(conv_param_grads(G2, n.cell[i].cat2, ex.dg2all[i], cg[2], cg[3], sc.wg, acc, s));
+      if (dh0)
+        EVE_TRY(nhwc_to_nchw(ex.dcarry[i], B, nf, kLevelH[4], kLevelW[4], dh0 + (size_t)i * B * E, s));
+    }
+  }
+
+  // ---- encoder, innermost first.  `cur` <- grad w.r.t. the encoder output of level 4
+  LAUNCH1D(swap_bt_kernel, (long long)N * E, dbx, (long long)N * E, T, B, P, nf, nf, cur, nf);
+  if (p->use_skip) EVE_TRY(ew_add(cur, ex.dskip[4], (long long)N * E, cur, s));
+  for (int l = kLevels - 1; l >= 0; --l) {
+    for (int j = (int)n.enc[l].size() - 1; j >= 0; --j) {
+      EVE_TRY(block_bwd(n.enc[l][j], N, w, gr, acc, cur, other, sc, s));
+      float* tmp = cur; cur = other; other = tmp;
+    }
+    if (l > 0) {
+      const RBlock& e = n.enc[l - 1].back();
+      EVE_TRY(adaptive_maxpool_bwd(cur, n.pidx[l - 1], N, e.H, e.W, e.oc, kLevelH[l], kLevelW[l],
+                                   other, s));
+      if (p->use_skip)
+        EVE_TRY(ew_add(other, ex.dskip[l - 1], (long long)N * e.H * e.W * e.oc, other, s));
+      float* tmp = cur; cur = other; other = tmp;
+    }
+  }
+  // ---- initial
+  EVE_TRY(conv_param_grads(n.gi3, n.i1, cur, gr[4], gr[5], sc.wg, acc, s));
+  EVE_TRY(conv_prep_weights(n.gi3, w[4], nullptr, sc.wd, s));
+  EVE_TRY(conv_dgrad_simt(n.gi3, cur, 16, sc.wd, nullptr, sc.t0, s));
+  EVE_TRY(in_backward(sc.t0, n.i1, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU, nullptr,
+                      sc.t1, nullptr, gr[2], gr[3], sc.inb, acc, s));
+  EVE_TRY(conv_param_grads(n.gi0, n.x0, sc.t1, gr[0], gr[1], sc.wg, acc, s));
+  if (dheatmap) {
+    EVE_TRY(conv_prep_weights(n.gi0, w[0], nullptr, sc.wd, s));
+    EVE_TRY(conv_dgrad_simt(n.gi0, sc.t1, 16, sc.wd, nullptr, sc.t0, s));
+    EVE_TRY(copy_channels(sc.t0, (long long)N * HW0, 1, p->in_channels, p->in_channels - 1, dheatmap,
+                          1, 0, false, s));
+  }
+  return EVE_OK;
+}

@@ -1,0 +1,333 @@
+"""torch.autograd.Function wrappers around the C ABI (eve_b200/lib.py).
+
+Each Function owns nothing but pointers: PyTorch allocates the tensors, the current CUDA
+stream carries the work, `loss.backward()` (reference: src/core/training.py:489) reaches the
+`*_bwd` entry points through these classes.  Under `torch.no_grad()` the activation tape goes
+to a reusable scratch buffer instead of a fresh allocation.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _bytes(nbytes, device, keep, tag):
+    if keep:
+        return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    return L.workspace(nbytes, device, tag)
+
+
+# ------------------------------------------------------------------------ EyeNet CNN --
+class EyeNetCnnFn(torch.autograd.Function):
+    """ResNet-18/InstanceNorm features of eye patches (eye_net.py:106).
+
+    x [N,3,H,W] -> feat [N,nf]; weights in the order of include/eve_b200.h."""
+
+    @staticmethod
+    def forward(ctx, x, nf, *weights):
+        L.require_cuda(x, 'EyeNet CNN')
+        lib = L.load()
+        x = _f32c(x)
+        weights = [_f32c(w) for w in weights]
+        assert len(weights) == 22
+        n, _, h, w_ = x.shape
+        p = L.EyeNetCnnParams(n, int(nf), h, w_)
+        keep = any(ctx.needs_input_grad)
+        saved = _bytes(lib.eve_eyenet_cnn_saved_bytes(C.byref(p)), x.device, keep, 'eye_saved')
+        ws = L.workspace(lib.eve_eyenet_cnn_workspace_bytes(C.byref(p)), x.device)
+        feat = torch.empty((n, int(nf)), dtype=torch.float32, device=x.device)
+        L.check(lib.eve_eyenet_cnn_fwd(C.byref(p), L.ptr(x), L.ptr_table(weights), L.ptr(feat),
+                                       L.ptr(saved), saved.numel(), L.ptr(ws), ws.numel(),
+                                       L.stream_ptr()), 'eve_eyenet_cnn_fwd')
+        if keep:
+            ctx.p = p
+            ctx.saved = saved
+            ctx.save_for_backward(*weights)
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        lib = L.load()
+        weights = ctx.saved_tensors
+        p = ctx.p
+        dfeat = _f32c(dfeat)
+        grads = [torch.empty_like(w) if ctx.needs_input_grad[2 + i] else None
+                 for i, w in enumerate(weights)]
+        ws = L.workspace(lib.eve_eyenet_cnn_workspace_bytes(C.byref(p)), dfeat.device)
+        L.check(lib.eve_eyenet_cnn_bwd(C.byref(p), L.ptr(dfeat), L.ptr_table(weights),
+                                       L.ptr_table(grads), 0, L.ptr(ctx.saved), ctx.saved.numel(),
+                                       L.ptr(ws), ws.numel(), L.stream_ptr()),
+                'eve_eyenet_cnn_bwd')
+        ctx.saved = None
+        return (None, None) + tuple(grads)
+
+
+# ----------------------------------------------------------------------- EyeNet tail --
+class EyeNetTailFn(torch.autograd.Function):
+    """fc_common -> RNN cells / static_fc -> gaze + pupil heads over whole sequences
+    (eye_net.py:109-140).  cfg = (use_head_pose, rnn_type_code, rnn_cells).
+
+    feat [S,T,nf], head_pose [S,T,2] or None, h0/c0 [cells,S,nf] or None ->
+    g [S,T,2], pupil [S,T], hT, cT ([cells,S,nf] or None)."""
+
+    @staticmethod
+    def forward(ctx, feat, head_pose, h0, c0, cfg, *weights):
+        L.require_cuda(feat, 'EyeNet tail')
+        lib = L.load()
+        use_hp, rnn_type, cells = cfg
+        feat, head_pose, h0, c0 = _f32c(feat), _f32c(head_pose), _f32c(h0), _f32c(c0)
+        weights = [_f32c(w) for w in weights]
+        S, T, nf = feat.shape
+        p = L.EyeNetTailParams(S, T, nf, int(bool(use_hp)), rnn_type, cells)
+        nw = lib.eve_eyenet_tail_num_weights(C.byref(p))
+        if nw < 0:
+            raise ValueError(L.last_error())
+        assert nw == len(weights), (nw, len(weights))
+        keep = any(ctx.needs_input_grad)
+        saved = _bytes(lib.eve_eyenet_tail_saved_bytes(C.byref(p)), feat.device, keep, 'tail_saved')
+        ws = L.workspace(lib.eve_eyenet_tail_workspace_bytes(C.byref(p)), feat.device)
+        dev = feat.device
+        g = torch.empty((S, T, 2), dtype=torch.float32, device=dev)
+        pupil = torch.empty((S, T), dtype=torch.float32, device=dev)
+        hT = cT = None
+        if rnn_type != 0:
+            hT = torch.empty((cells, S, nf), dtype=torch.float32, device=dev)
+            if rnn_type == L.EYE_RNN_TYPES['LSTM']:
+                cT = torch.empty((cells, S, nf), dtype=torch.float32, device=dev)
+        L.check(lib.eve_eyenet_tail_fwd(C.byref(p), L.ptr(feat), L.ptr(head_pose), L.ptr(h0),
+                                        L.ptr(c0), L.ptr_table(weights), L.ptr(g), L.ptr(pupil),
+                                        L.ptr(hT), L.ptr(cT), L.ptr(saved), saved.numel(),
+                                        L.ptr(ws), ws.numel(), L.stream_ptr()),
+                'eve_eyenet_tail_fwd')
+        if keep:
+            ctx.p = p
+            ctx.saved = saved
+            ctx.has_h0 = h0 is not None
+            ctx.has_c0 = c0 is not None
+            ctx.save_for_backward(*weights)
+        ctx.set_materialize_grads(False)
+        return g, pupil, hT, cT
+
+    @staticmethod
+    def backward(ctx, dg, dpupil, dhT, dcT):
+        lib = L.load()
+        weights = ctx.saved_tensors
+        p = ctx.p
+        dev = weights[0].device
+        S, T, nf = p.batch, p.steps, p.nf
+        dg = _f32c(dg) if dg is not None else torch.zeros((S, T, 2), device=dev)
+        dpupil = _f32c(dpupil) if dpupil is not None else torch.zeros((S, T), device=dev)
+        dhT, dcT = _f32c(dhT), _f32c(dcT)
+        dfeat = torch.empty((S, T, nf), dtype=torch.float32, device=dev)
+        dh0 = torch.empty((p.rnn_cells, S, nf), device=dev) \
+            if (ctx.has_h0 and ctx.needs_input_grad[2]) else None
+        dc0 = torch.empty((p.rnn_cells, S, nf), device=dev) \
+            if (ctx.has_c0 and ctx.needs_input_grad[3]) else None
+        grads = [torch.empty_like(w) if ctx.needs_input_grad[5 + i] else None
+                 for i, w in enumerate(weights)]
+        ws = L.workspace(lib.eve_eyenet_tail_workspace_bytes(C.byref(p)), dev)
+        L.check(lib.eve_eyenet_tail_bwd(C.byref(p), L.ptr(dg), L.ptr(dpupil), L.ptr(dhT),
+                                        L.ptr(dcT), L.ptr_table(weights), L.ptr(dfeat), L.ptr(dh0),
+                                        L.ptr(dc0), L.ptr_table(grads), 0, L.ptr(ctx.saved),
+                                        ctx.saved.numel(), L.ptr(ws), ws.numel(), L.stream_ptr()),
+                'eve_eyenet_tail_bwd')
+        ctx.saved = None
+        return (dfeat, None, dh0, dc0, None) + tuple(grads)
+
+
+# ------------------------------------------------------------------------- RefineNet --
+def refinenet_weight_names(p):
+    lib = L.load()
+    n = lib.eve_refinenet_num_weights(C.byref(p))
+    if n < 0:
+        raise ValueError(L.last_error())
+    return [lib.eve_refinenet_weight_name(C.byref(p), i).decode() for i in range(n)]
+
+
+class RefineNetFn(torch.autograd.Function):
+    """RefineNet.forward over whole sequences (refine_net.py:237-255).
+    cfg = (in_channels, use_skip, rnn_type_code, rnn_cells, nf).
+
+    screen [B,T,3,72,128] or None, heatmap [B,T,1,72,128], h0/c0 [cells,B,nf,5,8] or None ->
+    out [B,T,1,72,128], hT, cT."""
+
+    @staticmethod
+    def forward(ctx, screen, heatmap, h0, c0, cfg, *weights):
+        L.require_cuda(heatmap, 'RefineNet')
+        lib = L.load()
+        in_c, use_skip, rnn_type, cells, nf = cfg
+        screen, heatmap, h0, c0 = _f32c(screen), _f32c(heatmap), _f32c(h0), _f32c(c0)
+        weights = [_f32c(w) for w in weights]
+        B, T = heatmap.shape[:2]
+        if tuple(heatmap.shape[2:]) != (1, 72, 128):
+            raise ValueError('RefineNet needs 72x128 heatmaps (screen_size [128, 72]), got %s'
+                             % (tuple(heatmap.shape),))
+        p = L.RefineNetParams(B, T, in_c, int(bool(use_skip)), rnn_type, cells, nf)
+        nw = lib.eve_refinenet_num_weights(C.byref(p))
+        if nw < 0:
+            raise ValueError(L.last_error())
+        assert nw == len(weights), (nw, len(weights))
+        keep = any(ctx.needs_input_grad)
+        dev = heatmap.device
+        saved = _bytes(lib.eve_refinenet_saved_bytes(C.byref(p)), dev, keep, 'refine_saved')
+        ws = L.workspace(lib.eve_refinenet_workspace_bytes(C.byref(p)), dev)
+        out = torch.empty((B, T, 1, 72, 128), dtype=torch.float32, device=dev)
+        hT = cT = None
+        if rnn_type != 0:
+            hT = torch.empty((cells, B, nf, 5, 8), dtype=torch.float32, device=dev)
+            if rnn_type == L.REFINE_RNN_TYPES['CLSTM']:
+                cT = torch.empty((cells, B, nf, 5, 8), dtype=torch.float32, device=dev)
+        L.check(lib.eve_refinenet_fwd(C.byref(p), L.ptr(screen), L.ptr(heatmap), L.ptr(h0),
+                                      L.ptr(c0), L.ptr_table(weights), L.ptr(out), L.ptr(hT),
+                                      L.ptr(cT), L.ptr(saved), saved.numel(), L.ptr(ws), ws.numel(),
+                                      L.stream_ptr()), 'eve_refinenet_fwd')
+        if keep:
+            ctx.p = p
+            ctx.saved = saved
+            ctx.has_h0 = h0 is not None
+            ctx.save_for_backward(*weights)
+        ctx.set_materialize_grads(False)
+        return out, hT, cT
+
+    @staticmethod
+    def backward(ctx, dout, dhT, dcT):
+        lib = L.load()
+        weights = ctx.saved_tensors
+        p = ctx.p
+        dev = weights[0].device
+        B, T = p.batch, p.steps
+        dout = _f32c(dout) if dout is not None else torch.zeros((B, T, 1, 72, 128), device=dev)
+        if p.rnn_type == L.REFINE_RNN_TYPES['CLSTM']:
+            dhT = dcT = None   # the CLSTM state never reaches the heatmap (refine_net.py:168-174)
+        dhT, dcT = _f32c(dhT), _f32c(dcT)
+        dheat = torch.empty((B, T, 1, 72, 128), device=dev) if ctx.needs_input_grad[1] else None
+        dh0 = torch.empty((p.rnn_cells, B, p.nf, 5, 8), device=dev) \
+            if (ctx.has_h0 and ctx.needs_input_grad[2]) else None
+        grads = [torch.empty_like(w) if ctx.needs_input_grad[5 + i] else None
+                 for i, w in enumerate(weights)]
+        ws = L.workspace(lib.eve_refinenet_workspace_bytes(C.byref(p)), dev)
+        L.check(lib.eve_refinenet_bwd(C.byref(p), L.ptr(dout), L.ptr(dhT), L.ptr(dcT),
+                                      L.ptr_table(weights), L.ptr(dheat), L.ptr(dh0), None,
+                                      L.ptr_table(grads), 0, L.ptr(ctx.saved), ctx.saved.numel(),
+                                      L.ptr(ws), ws.numel(), L.stream_ptr()), 'eve_refinenet_bwd')
+        ctx.saved = None
+        return (None, dheat, dh0, None, None) + tuple(grads)
+
+
+# --------------------------------------------------------------------- heatmap / PoG --
+class HeatmapFn(torch.autograd.Function):
+    """batch_make_heatmaps (common.py:226-243): centres [n,2] px -> [n,1,H,W]."""
+
+    @staticmethod
+    def forward(ctx, centres, sigma, size_wh, screen_wh):
+        L.require_cuda(centres, 'make_heatmap')
+        lib = L.load()
+        centres = _f32c(centres)
+        n = centres.shape[0]
+        p = L.HeatmapParams(n, int(size_wh[0]), int(size_wh[1]), float(screen_wh[0]),
+                            float(screen_wh[1]), float(sigma))
+        out = torch.empty((n, 1, int(size_wh[1]), int(size_wh[0])), dtype=torch.float32,
+                          device=centres.device)
+        L.check(lib.eve_heatmap_fwd(C.byref(p), L.ptr(centres), L.ptr(out), L.stream_ptr()),
+                'eve_heatmap_fwd')
+        ctx.p = p
+        ctx.save_for_backward(centres)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.load()
+        centres, = ctx.saved_tensors
+        dout = _f32c(dout)
+        dc = torch.empty_like(centres)
+        L.check(lib.eve_heatmap_bwd(C.byref(ctx.p), L.ptr(centres), L.ptr(dout), L.ptr(dc),
+                                    L.stream_ptr()), 'eve_heatmap_bwd')
+        return dc, None, None, None
+
+
+class SoftArgmaxFn(torch.autograd.Function):
+    """soft_argmax (common.py:294-323): heatmaps [n,1,H,W] -> PoG [n,2] px."""
+
+    @staticmethod
+    def forward(ctx, heatmaps, screen_wh):
+        L.require_cuda(heatmaps, 'soft_argmax')
+        lib = L.load()
+        heatmaps = _f32c(heatmaps)
+        n, _, h, w = heatmaps.shape
+        p = L.HeatmapParams(n, w, h, float(screen_wh[0]), float(screen_wh[1]), 1.0)
+        out = torch.empty((n, 2), dtype=torch.float32, device=heatmaps.device)
+        L.check(lib.eve_soft_argmax_fwd(C.byref(p), L.ptr(heatmaps), L.ptr(out), L.stream_ptr()),
+                'eve_soft_argmax_fwd')
+        ctx.p = p
+        ctx.save_for_backward(heatmaps)
+        return out
+
+    @staticmethod
+    def backward(ctx, dpog):
+        lib = L.load()
+        heatmaps, = ctx.saved_tensors
+        dpog = _f32c(dpog)
+        dh = torch.empty_like(heatmaps)
+        L.check(lib.eve_soft_argmax_bwd(C.byref(ctx.p), L.ptr(heatmaps), L.ptr(dpog), L.ptr(dh),
+                                        L.stream_ptr()), 'eve_soft_argmax_bwd')
+        return dh, None
+
+
+class PogFn(torch.autograd.Function):
+    """to_screen_coordinates (common.py:149-179): gradient flows to the gaze direction only
+    (origin, rotation and calibration are data)."""
+
+    @staticmethod
+    def forward(ctx, origin, g, rot, inv_cam, ppm, screen_wh):
+        L.require_cuda(g, 'to_screen_coordinates')
+        lib = L.load()
+        origin, g, rot, inv_cam, ppm = (_f32c(t) for t in (origin, g, rot, inv_cam, ppm))
+        n = g.shape[0]
+        mm = torch.empty((n, 2), dtype=torch.float32, device=g.device)
+        px = torch.empty((n, 2), dtype=torch.float32, device=g.device)
+        L.check(lib.eve_pog_fwd(n, L.ptr(origin), L.ptr(g), L.ptr(rot), L.ptr(inv_cam), L.ptr(ppm),
+                                float(screen_wh[0]), float(screen_wh[1]), L.ptr(mm), L.ptr(px),
+                                L.stream_ptr()), 'eve_pog_fwd')
+        ctx.screen = (float(screen_wh[0]), float(screen_wh[1]))
+        ctx.save_for_backward(origin, g, rot, inv_cam, ppm)
+        ctx.set_materialize_grads(False)
+        return mm, px
+
+    @staticmethod
+    def backward(ctx, dmm, dpx):
+        lib = L.load()
+        origin, g, rot, inv_cam, ppm = ctx.saved_tensors
+        if dmm is None and dpx is None:
+            return None, None, None, None, None, None
+        dmm, dpx = _f32c(dmm), _f32c(dpx)
+        dg = torch.empty_like(g)
+        L.check(lib.eve_pog_bwd(g.shape[0], L.ptr(origin), L.ptr(g), L.ptr(rot), L.ptr(inv_cam),
+                                L.ptr(ppm), ctx.screen[0], ctx.screen[1], L.ptr(dmm), L.ptr(dpx),
+                                L.ptr(dg), L.stream_ptr()), 'eve_pog_bwd')
+        return None, dg, None, None, None, None
+
+
+# ------------------------------------------------------------------- fused optimiser --
+def adam_clip_step(params, grads, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8,
+                   weight_decay=0.0, max_norm=0.0, grad_scale=1.0):
+    """clip_grad_norm_ + Adam on flat fp32 buffers (training.py:492-502).  Returns the
+    pre-clip gradient norm as a 1-element device tensor."""
+    lib = L.load()
+    L.require_cuda(params, 'adam_clip_step')
+    p = L.AdamParams(params.numel(), lr, betas[0], betas[1], eps, weight_decay, max_norm,
+                     grad_scale, int(step))
+    ws = L.workspace(lib.eve_adam_clip_workspace_bytes(C.byref(p)), params.device, 'adam')
+    norm = torch.empty(1, dtype=torch.float32, device=params.device)
+    L.check(lib.eve_adam_clip_step(C.byref(p), L.ptr(params), L.ptr(grads), L.ptr(exp_avg),
+                                   L.ptr(exp_avg_sq), L.ptr(norm), L.ptr(ws), ws.numel(),
+                                   L.stream_ptr()), 'eve_adam_clip_step')
+    return norm

@@ -1,0 +1,225 @@
+/* libeve_b200.so -- C ABI of the B200-native EVE hot path (EyeNet + GazeRefineNet, fwd + bwd).
+ *
+ * The reference (swook/EVE) is pure Python/PyTorch and has no FFI of its own; this header
+ * IS the boundary a maintainer binds with ctypes.  Each entry point
+ * names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer (fp32 unless stated) owned by the caller.  The library
+ *    never allocates or frees device memory; scratch comes from `workspace`, activations that
+ *    backward needs are kept in the caller's `saved` buffer.  Sizes: eve_*_saved_bytes(),
+ *    eve_*_workspace_bytes().
+ *  - Tensors crossing the boundary use the reference's layouts (NCHW images, [rows, features]
+ *    vectors, OIHW conv weights, [out, in] linear weights).  NHWC is internal.
+ *  - All work is enqueued on `stream` (a cudaStream_t); no entry synchronises the device.
+ *  - Return value: EVE_OK or an EVE_ERR_* code; eve_last_error() gives the message for the
+ *    calling thread.  Nothing aborts and nothing falls back to another implementation.
+ *  - `weights` / `grads` are tables of device pointers in the order documented per entry;
+ *    a grads slot may be NULL (that gradient is skipped).  `accumulate` != 0 adds into grads.
+ */
+#ifndef EVE_B200_H
+#define EVE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVE_OK 0
+#define EVE_ERR_SHAPE 1     /* bad dimension / unsupported size            */
+#define EVE_ERR_CONFIG 2    /* unsupported knob combination                */
+#define EVE_ERR_CUDA 3      /* a CUDA runtime call or launch failed        */
+#define EVE_ERR_WORKSPACE 4 /* workspace / saved buffer too small          */
+#define EVE_ERR_NULL 5      /* a required pointer is NULL                  */
+
+typedef void* eve_stream_t; /* cudaStream_t */
+
+int eve_version(void);
+const char* eve_last_error(void);
+
+/* ------------------------------------------------------------------ building blocks --
+ * Exposed so that each kernel family can be parity-tested on its own.  NHWC fp32. */
+
+/* nn.Conv2d (refine_net.py:47,51,60,214,216,221,223; torchvision resnet conv3x3/conv1x1/conv1;
+ * common.py:338,362,395-398).  x[N,H,W,Cin], w OIHW, bias[Cout] or NULL, y[N,OH,OW,Cout]. */
+typedef struct {
+  int n, h, w, cin, cout, ksize, stride, pad;
+} eve_conv_params;
+size_t eve_conv2d_workspace_bytes(const eve_conv_params* p);
+int eve_conv2d_fwd(const eve_conv_params* p, const float* x, const float* w, const float* bias,
+                   float* y, void* workspace, size_t workspace_bytes, eve_stream_t stream);
+/* dx = d(loss)/dx given dy */
+int eve_conv2d_dgrad(const eve_conv_params* p, const float* dy, const float* w, float* dx,
+                     void* workspace, size_t workspace_bytes, eve_stream_t stream);
+/* dw (OIHW) and dbias (may be NULL) */
+int eve_conv2d_wgrad(const eve_conv_params* p, const float* x, const float* dy, float* dw,
+                     float* dbias, void* workspace, size_t workspace_bytes, eve_stream_t stream);
+
+/* nn.InstanceNorm2d(eps=1e-5, biased variance, no running stats) + activation
+ * (eye_net.py:50; refine_net.py:46,50,59,215).  act: 0 none, 1 ReLU, 2 LeakyReLU(0.01).
+ * gamma/beta NULL => non-affine.  mean/rstd [N,C] are outputs of fwd, inputs of bwd. */
+int eve_instnorm_act_fwd(const float* x, int n, int hw, int c, const float* gamma,
+                         const float* beta, int act, float* y, float* mean, float* rstd,
+                         eve_stream_t stream);
+int eve_instnorm_act_bwd(const float* dy, const float* y, const float* x, int n, int hw, int c,
+                         const float* mean, const float* rstd, const float* gamma, int act,
+                         float* dx, float* dgamma, float* dbeta, void* workspace,
+                         size_t workspace_bytes, eve_stream_t stream);
+
+/* nn.AdaptiveMaxPool2d (refine_net.py:93,121): idx = int32 flat h*W+w of the first maximum. */
+int eve_adaptive_maxpool_fwd(const float* x, int n, int h, int w, int c, int oh, int ow, float* y,
+                             int32_t* idx, eve_stream_t stream);
+int eve_adaptive_maxpool_bwd(const float* dy, const int32_t* idx, int n, int h, int w, int c,
+                             int oh, int ow, float* dx, eve_stream_t stream);
+/* nn.Upsample(bilinear, align_corners=False) (refine_net.py:101,124) */
+int eve_upsample_bilinear_fwd(const float* x, int n, int h, int w, int c, int oh, int ow, float* y,
+                              eve_stream_t stream);
+int eve_upsample_bilinear_bwd(const float* dy, int n, int h, int w, int c, int oh, int ow,
+                              float* dx, eve_stream_t stream);
+/* layout helpers */
+int eve_nchw_to_nhwc(const float* x, int n, int c, int h, int w, float* y, eve_stream_t stream);
+int eve_nhwc_to_nchw(const float* x, int n, int c, int h, int w, float* y, eve_stream_t stream);
+
+/* -------------------------------------------------------------------- EyeNet: CNN --
+ * torchvision ResNet(BasicBlock,[2,2,2,2], num_classes=nf, norm_layer=InstanceNorm2d) as called
+ * at eye_net.py:48-50,106: conv7x7s2 -> IN -> ReLU -> maxpool3x3s2 -> 8 BasicBlocks -> avgpool
+ * -> fc.  x[n,3,128,128] NCHW -> feat[n,nf].
+ * weights (22+1): conv1, then per layer l=1..4, block b=0..1: conv1, conv2, (downsample.0 when
+ * l>1 && b==0), then fc.weight, fc.bias.  grads: same order. */
+#define EVE_EYENET_CNN_NUM_WEIGHTS 22
+typedef struct {
+  int n;  /* number of eye patches (B*T*2 when time-batched) */
+  int nf; /* fc output features (eye_net_rnn_num_features / eye_net_static_num_features) */
+  int h, w; /* patch size, 128 x 128 */
+} eve_eyenet_cnn_params;
+size_t eve_eyenet_cnn_saved_bytes(const eve_eyenet_cnn_params* p);
+size_t eve_eyenet_cnn_workspace_bytes(const eve_eyenet_cnn_params* p);
+int eve_eyenet_cnn_fwd(const eve_eyenet_cnn_params* p, const float* x, const float* const* weights,
+                       float* feat, void* saved, size_t saved_bytes, void* workspace,
+                       size_t workspace_bytes, eve_stream_t stream);
+int eve_eyenet_cnn_bwd(const eve_eyenet_cnn_params* p, const float* dfeat,
+                       const float* const* weights, float* const* grads, int accumulate,
+                       const void* saved, size_t saved_bytes, void* workspace,
+                       size_t workspace_bytes, eve_stream_t stream);
+
+/* ------------------------------------------------------------------- EyeNet: tail --
+ * eye_net.py:109-140 over whole sequences: cat(head pose) -> fc_common -> RNN cells (or
+ * static_fc) -> gaze head (tanh * pi/2) and pupil head (ReLU).
+ * feat[batch,steps,nf], head_pose[batch,steps,2] (NULL iff !use_head_pose),
+ * h0/c0[cells,batch,nf] initial states (NULL => zeros; c0 only for LSTM),
+ * g[batch,steps,2], pupil[batch,steps], hT/cT[cells,batch,nf] final states (may be NULL).
+ * weights: fc_common.0.{w,b}, fc_common.2.{w,b}, then rnn: per cell {w_ih,w_hh,b_ih,b_hh} or
+ * static: static_fc.0.{w,b}; then fc_to_gaze.0.{w,b}, fc_to_gaze.2.w, fc_to_pupil.0.{w,b},
+ * fc_to_pupil.2.{w,b}. */
+#define EVE_RNN_NONE 0
+#define EVE_RNN_RNN 1
+#define EVE_RNN_LSTM 2
+#define EVE_RNN_GRU 3
+typedef struct {
+  int batch, steps, nf;
+  int use_head_pose;
+  int rnn_type;  /* EVE_RNN_*; NONE = static_fc path (eye_net_use_rnn = False) */
+  int rnn_cells;
+} eve_eyenet_tail_params;
+int eve_eyenet_tail_num_weights(const eve_eyenet_tail_params* p);
+size_t eve_eyenet_tail_saved_bytes(const eve_eyenet_tail_params* p);
+size_t eve_eyenet_tail_workspace_bytes(const eve_eyenet_tail_params* p);
+int eve_eyenet_tail_fwd(const eve_eyenet_tail_params* p, const float* feat, const float* head_pose,
+                        const float* h0, const float* c0, const float* const* weights, float* g,
+                        float* pupil, float* hT, float* cT, void* saved, size_t saved_bytes,
+                        void* workspace, size_t workspace_bytes, eve_stream_t stream);
+/* dg, dpupil required; dhT/dcT may be NULL (no gradient into the final state);
+ * dfeat required; dh0/dc0 may be NULL. */
+int eve_eyenet_tail_bwd(const eve_eyenet_tail_params* p, const float* dg, const float* dpupil,
+                        const float* dhT, const float* dcT, const float* const* weights,
+                        float* dfeat, float* dh0, float* dc0, float* const* grads, int accumulate,
+                        const void* saved, size_t saved_bytes, void* workspace,
+                        size_t workspace_bytes, eve_stream_t stream);
+
+/* ---------------------------------------------------------------------- RefineNet --
+ * refine_net.py:237-255 over whole sequences: cat(screen, heatmap) -> initial -> 5-level
+ * pre-activation encoder (AdaptiveMaxPool between levels) -> ConvRNN bottleneck stepped over
+ * `steps` -> decoder (bilinear upsample + skip concat) -> final -> sigmoid.
+ * screen[batch,steps,3,72,128] NCHW (NULL iff in_channels == 1), heatmap[batch,steps,1,72,128],
+ * h0/c0[cells,batch,nf,5,8] NCHW (NULL => zeros), out[batch,steps,1,72,128],
+ * hT/cT like h0 (may be NULL).  Weight order: eve_refinenet_weight_name(). */
+#define EVE_CRNN_NONE 0
+#define EVE_CRNN_CRNN 1
+#define EVE_CRNN_CLSTM 2
+#define EVE_CRNN_CGRU 3
+typedef struct {
+  int batch, steps;
+  int in_channels; /* 4 with screen content, 1 without (refine_net.py:183) */
+  int use_skip;    /* refine_net_use_skip_connections */
+  int rnn_type;    /* EVE_CRNN_*; NONE = refine_net_use_rnn False */
+  int rnn_cells;
+  int nf;          /* refine_net_num_features (64) */
+} eve_refinenet_params;
+int eve_refinenet_num_weights(const eve_refinenet_params* p);
+/* name of weight slot i relative to `refine_net.` (e.g. "network.encoder_blocks.0.layers.2.weight");
+ * NULL when i is out of range.  The string lives in thread-local storage. */
+const char* eve_refinenet_weight_name(const eve_refinenet_params* p, int i);
+size_t eve_refinenet_saved_bytes(const eve_refinenet_params* p);
+size_t eve_refinenet_workspace_bytes(const eve_refinenet_params* p);
+int eve_refinenet_fwd(const eve_refinenet_params* p, const float* screen, const float* heatmap,
+                      const float* h0, const float* c0, const float* const* weights, float* out,
+                      float* hT, float* cT, void* saved, size_t saved_bytes, void* workspace,
+                      size_t workspace_bytes, eve_stream_t stream);
+int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dout, const float* dhT,
+                      const float* dcT, const float* const* weights, float* dheatmap, float* dh0,
+                      float* dc0, float* const* grads, int accumulate, const void* saved,
+                      size_t saved_bytes, void* workspace, size_t workspace_bytes,
+                      eve_stream_t stream);
+
+/* ------------------------------------------------------------- gaze <-> screen ops --
+ * common.py:226-243 make_heatmap / batch_make_heatmaps: centres_px[n,2] (screen pixels) ->
+ * out[n,1,hm_h,hm_w] = exp(-((x-cx)^2+(y-cy)^2)/(2 sigma^2)) + 1e-8. */
+typedef struct {
+  int n, hm_w, hm_h;
+  float screen_w, screen_h; /* actual_screen_size (1920, 1080) */
+  float sigma;
+} eve_heatmap_params;
+int eve_heatmap_fwd(const eve_heatmap_params* p, const float* centres_px, float* out,
+                    eve_stream_t stream);
+int eve_heatmap_bwd(const eve_heatmap_params* p, const float* centres_px, const float* dout,
+                    float* dcentres, eve_stream_t stream);
+/* common.py:294-323 soft_argmax: heatmaps[n,1,hm_h,hm_w] -> pog_px[n,2] (softmax(100 h),
+ * expectation over linspace(0,1) grids, scaled to the screen and clamped). */
+int eve_soft_argmax_fwd(const eve_heatmap_params* p, const float* heatmaps, float* pog_px,
+                        eve_stream_t stream);
+int eve_soft_argmax_bwd(const eve_heatmap_params* p, const float* heatmaps, const float* dpog,
+                        float* dheatmaps, eve_stream_t stream);
+/* common.py:149-179 to_screen_coordinates (+ :32-40, :89-126): per sample
+ * origin[n,3], g[n,2] (pitch, yaw), rot[n,3,3], inv_cam[n,4,4], ppm[n,2] ->
+ * pog_mm[n,2], pog_px[n,2] (clamped to the screen).  bwd: gradient w.r.t. g only. */
+int eve_pog_fwd(int n, const float* origin, const float* g, const float* rot,
+                const float* inv_cam, const float* ppm, float screen_w, float screen_h,
+                float* pog_mm, float* pog_px, eve_stream_t stream);
+int eve_pog_bwd(int n, const float* origin, const float* g, const float* rot,
+                const float* inv_cam, const float* ppm, float screen_w, float screen_h,
+                const float* dpog_mm, const float* dpog_px, float* dg, eve_stream_t stream);
+
+/* ------------------------------------------------------------------ optimiser step --
+ * training.py:492-502 + train.py:49-55: clip_grad_norm_(max_norm) then Adam with L2
+ * weight decay, on ONE flat fp32 buffer (the buffer the NCCL allreduce ran on).
+ * grad_scale is applied to the gradients first (1/world_size after a sum-allreduce).
+ * norm_out[1] receives the pre-clip global L2 norm (device pointer, may be NULL).
+ * workspace: eve_adam_clip_workspace_bytes(). */
+typedef struct {
+  long long count;
+  float lr, beta1, beta2, eps, weight_decay;
+  float max_norm;   /* <= 0 disables clipping */
+  float grad_scale;
+  int step;         /* 1-based Adam step for bias correction */
+} eve_adam_params;
+size_t eve_adam_clip_workspace_bytes(const eve_adam_params* p);
+int eve_adam_clip_step(const eve_adam_params* p, float* params, const float* grads, float* exp_avg,
+                       float* exp_avg_sq, float* norm_out, void* workspace, size_t workspace_bytes,
+                       eve_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVE_B200_H */

@@ -1,0 +1,360 @@
+"""Parity of the B200 path, called through the drop-in modules (which call the C ABI),
+against (1) golden vectors produced by the unmodified reference and (2) the CPU oracle on
+seeded inputs for the knob combinations the goldens do not carry gradients for.
+
+Tolerances: BASELINE.json's north_star asks for 1e-3 relative on fp32 gaze vectors / PoG;
+the forward comparisons below hold 2e-4 (EyeNet side) and 2e-3 on quantities that pass
+through RefineNet + soft-argmax at random weights (the reference's own fp32 noise floor there,
+SURVEY.md 7.2); weight gradients are compared in L2 at 2e-2 like tests/test_oracle_golden.py
+documents.  Index outputs (validity masks, timestamps) are bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import eve_oracle as O       # noqa: E402  (checker only)
+from tests import gpu_util as G          # noqa: E402
+from tests import helpers as H           # noqa: E402
+
+
+def _load(model, sd):
+    model.load_state_dict(sd, strict=True)
+    return model.cuda()
+
+
+def _cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+# ------------------------------------------------------------------ module entry points --
+def test_module_entry_points_match_reference(cfg):
+    from eve_b200 import synth
+    from eve_b200.models import EyeNet, RefineNet
+    from eve_b200.models.common import batch_make_heatmaps, soft_argmax
+    gold = H.load_golden('modules')
+    cfg.override('refine_net_enabled', True)
+    cfg.override('load_screen_content', True)
+    rs = np.random.RandomState(31)
+    net = _load(EyeNet(), synth.make_state_dict(synth.eye_net_param_shapes(cfg), 31))
+    patch = torch.from_numpy(rs.uniform(-1, 1, (2, 3, 128, 128)).astype(np.float32)).cuda()
+    hp = torch.from_numpy(rs.uniform(-.2, .2, (2, 2)).astype(np.float32)).cuda()
+    st = torch.from_numpy(rs.normal(size=(2, 128)).astype(np.float32)).cuda()
+    with torch.no_grad():
+        assert H.rel_err(net.cnn_features(patch).cpu().numpy(), gold['eyenet/fc']) < 1e-4
+        out = {}
+        net({'left_eye_patch': patch, 'left_h': hp}, out, side='left',
+            previous_output_dict={'left_eye_rnn_states_0': st})
+        assert H.rel_err(out['left_g_initial'].cpu().numpy(), gold['eyenet/g']) < 1e-4
+        assert H.rel_err(out['left_pupil_size'].cpu().numpy(), gold['eyenet/pupil']) < 1e-4
+        assert H.rel_err(out['left_eye_rnn_states_0'].cpu().numpy(), gold['eyenet/state']) < 1e-4
+
+        rnet = _load(RefineNet(), synth.make_state_dict(synth.refine_net_param_shapes(cfg), 1031))
+        px = torch.from_numpy(np.stack([rs.uniform(0, 1920, 2), rs.uniform(0, 1080, 2)], -1)
+                              .astype(np.float32)).cuda()
+        hm = batch_make_heatmaps(px, cfg.gaze_heatmap_sigma_initial)
+        screen = torch.from_numpy(rs.uniform(0, 1, (2, 3, 72, 128)).astype(np.float32)).cuda()
+        prev = torch.from_numpy((0.5 * rs.normal(size=(2, 64, 5, 8))).astype(np.float32)).cuda()
+        out = {'heatmap_initial': hm}
+        rnet({'screen_frame': screen}, out, previous_output_dict={'refinenet_rnn_states_0': prev})
+        assert H.rel_err(out['heatmap_final'].cpu().numpy(), gold['refine/heatmap_final']) < 1e-4
+        assert H.rel_err(out['refinenet_rnn_states_0'].cpu().numpy(), gold['refine/state']) < 1e-4
+        assert H.rel_err(soft_argmax(out['heatmap_final']).cpu().numpy(),
+                         gold['refine/softargmax']) < 1e-3
+
+
+# ----------------------------------------------------------------------- golden EVE cases --
+@pytest.mark.parametrize('name', H.golden_names())
+def test_eve_forward_backward_matches_reference(name, cfg):
+    from eve_b200.models import EVE
+    gold = H.load_golden(name)
+    H.apply_case_config(cfg, gold)
+    training = bool(gold['meta/training'])
+    model = _load(EVE(output_predictions=True), H.case_state_dict(gold, cfg))
+    model.train(training)
+    inputs = _cuda(H.case_inputs(gold, cfg))
+    np.random.seed(int(gold['meta/seed']))       # kappas come from np.random (eve.py:468)
+    if training:
+        out = model({'synthetic': inputs}, create_images=True, current_epoch=0.0)
+    else:
+        with torch.no_grad():
+            out = model(inputs, create_images=True)
+    mid = model.last_intermediates
+
+    checked = 0
+    for k, ref in gold.items():
+        if k.startswith('out/'):
+            key = k[4:]
+            if key not in out or out[key] is None:
+                continue
+            got = out[key]
+        elif k.startswith('mid/'):
+            key = k[4:]
+            if key not in mid:
+                continue
+            got = mid[key]
+            if key.startswith('history_'):
+                got = got[:, -1]
+        else:
+            continue
+        got = got.detach().cpu().numpy()
+        if ref.dtype == np.bool_ or np.issubdtype(ref.dtype, np.integer):
+            assert np.array_equal(got, ref), k
+        else:
+            assert got.shape == ref.shape, (k, got.shape, ref.shape)
+            tol = 2e-3 if ('final' in key or 'refined' in key or key == 'full_loss') else 2e-4
+            assert H.rel_err(got, ref) < tol, (k, H.rel_err(got, ref))
+        checked += 1
+    assert checked >= 20, checked
+    for must in ('full_loss', 'left_pupil_size', 'g_initial', 'PoG_px_initial'):
+        assert must in out
+
+    if training:
+        out['full_loss'].backward()
+        params = dict(model.named_parameters())
+        floor = 1e-5 * max(float(v) for k, v in gold.items() if k.startswith('gradnorm/'))
+        n = 0
+        for k, ref in gold.items():
+            if not k.startswith('gradnorm/'):
+                continue
+            pname = k[len('gradnorm/'):]
+            g = params[pname].grad
+            assert g is not None, pname
+            gn = float(g.double().norm())
+            gtol = 2e-2
+            assert abs(gn - float(ref)) <= gtol * max(float(ref), 1e-6) + floor, \
+                (pname, gn, float(ref))
+            sample = gold['grad/' + pname]
+            gf = g.reshape(-1).cpu().numpy()
+            gs = gf if gf.size <= 20000 else gf[::H.GRAD_STRIDE]
+            l2 = float(np.linalg.norm(gs.astype(np.float64) - sample))
+            assert l2 <= gtol * float(np.linalg.norm(sample.astype(np.float64))) + floor, \
+                (pname, l2)
+            n += 1
+        for k in gold:
+            if k.startswith('gradnone/'):
+                g = params[k[len('gradnone/'):]].grad
+                assert g is None or float(g.abs().max()) == 0.0, k
+        assert n > 30
+
+
+# --------------------------------------------------- oracle comparisons with gradients --
+TAIL_CASES = [('GRU', 1, True), ('LSTM', 1, True), ('RNN', 2, True), ('LSTM', 2, False),
+              (None, 1, True), ('GRU', 2, False)]
+
+
+@pytest.mark.parametrize('rnn,cells,head_pose', TAIL_CASES)
+def test_eyenet_tail_sequences_with_state_and_gradients(cfg, rnn, cells, head_pose):
+    """eye_net.py:109-140 for every RNN variant, with non-zero initial states and gradients
+    w.r.t. features, initial states and every weight."""
+    from eve_b200 import synth
+    from eve_b200.models import EyeNet
+    cfg.override('eye_net_use_rnn', rnn is not None)
+    if rnn:
+        cfg.override('eye_net_rnn_type', rnn)
+        cfg.override('eye_net_rnn_num_cells', cells)
+    cfg.override('eye_net_use_head_pose_input', head_pose)
+    sd = synth.make_state_dict(synth.eye_net_param_shapes(cfg), 77)
+    net = _load(EyeNet(), sd)
+    S, T, nf = 3, 4, 128
+    g = torch.Generator().manual_seed(8)
+    feat = torch.randn(S, T, nf, generator=g)
+    hp = torch.rand(S, T, 2, generator=g) - 0.5
+    h0 = torch.randn(cells, S, nf, generator=g) * 0.5 if rnn else None
+    c0 = torch.randn(cells, S, nf, generator=g) * 0.5 if rnn == 'LSTM' else None
+    wg = torch.randn(S, T, 2, generator=g)
+    wp = torch.randn(S, T, generator=g)
+    wh = torch.randn(cells, S, nf, generator=g) if rnn else None
+
+    # oracle (fp64, CPU)
+    osd = {'eye_net.' + k: v.double().requires_grad_(True) for k, v in sd.items()}
+    f64 = feat.double().requires_grad_(True)
+    h64 = h0.double().requires_grad_(True) if rnn else None
+    c64 = c0.double().requires_grad_(True) if c0 is not None else None
+    states = None
+    if rnn:
+        states = [(h64[i], c64[i]) if rnn == 'LSTM' else h64[i] for i in range(cells)]
+    gs, ps = [], []
+    for t in range(T):
+        go, po, states = O.eye_net_tail_step(osd, cfg, f64[:, t], hp[:, t].double(), states or None)
+        gs.append(go)
+        ps.append(po)
+    og, op = torch.stack(gs, 1), torch.stack(ps, 1)
+    loss = (og * wg.double()).sum() + (op * wp.double()).sum()
+    if rnn:
+        fin = torch.stack([s[0] if isinstance(s, tuple) else s for s in states], 0)
+        loss = loss + (fin * wh.double()).sum()
+    loss.backward()
+
+    fc = feat.cuda().requires_grad_(True)
+    hc = h0.cuda().requires_grad_(True) if rnn else None
+    cc = c0.cuda().requires_grad_(True) if c0 is not None else None
+    gg, gp, hT, cT = net.tail_sequence(fc, hp.cuda(), hc, cc)
+    assert G.rel(gg, og) < 2e-5
+    assert G.rel(gp, op) < 2e-5
+    closs = (gg * wg.cuda()).sum() + (gp * wp.cuda()).sum()
+    if rnn:
+        assert G.rel(hT, fin) < 2e-5
+        closs = closs + (hT * wh.cuda()).sum()
+    closs.backward()
+    assert G.rel(fc.grad, f64.grad) < 1e-4
+    if rnn:
+        assert G.rel(hc.grad, h64.grad) < 1e-4
+    if cc is not None:
+        assert G.rel(cc.grad, c64.grad) < 1e-4
+    for name, p in net.named_parameters():
+        if name.startswith('cnn_layers.'):
+            continue
+        want = osd['eye_net.' + name].grad
+        assert p.grad is not None, name
+        assert G.rel(p.grad, want) < 2e-4, name
+
+
+def test_eyenet_cnn_gradients_match_oracle(cfg):
+    """ResNet-18/InstanceNorm forward + every conv weight gradient against the fp64 oracle."""
+    from eve_b200 import synth
+    from eve_b200.models import EyeNet
+    sd = synth.make_state_dict(synth.eye_net_param_shapes(cfg), 78)
+    net = _load(EyeNet(), sd)
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(3, 3, 128, 128, generator=g) * 2 - 1
+    wf = torch.randn(3, 128, generator=g)
+    osd = {'eye_net.' + k: v.double().requires_grad_(k.startswith('cnn_layers.'))
+           for k, v in sd.items()}
+    want = O.resnet18_in_features(osd, 'eye_net.cnn_layers.', x.double())
+    (want * wf.double()).sum().backward()
+    got = net.cnn_features(x.cuda())
+    assert G.rel(got, want) < 2e-5
+    (got * wf.cuda()).sum().backward()
+    for name, p in net.named_parameters():
+        if not name.startswith('cnn_layers.'):
+            continue
+        ref = osd['eye_net.' + name].grad
+        l2 = float((p.grad.double().cpu() - ref).norm() / (ref.norm() + 1e-30))
+        assert l2 < 1e-3, (name, l2)
+
+
+REFINE_CASES = [('CGRU', 1, True, True), ('CRNN', 2, True, True), ('CGRU', 2, False, False),
+                ('CLSTM', 1, True, True), (None, 1, True, False)]
+
+
+@pytest.mark.parametrize('rnn,cells,skip,screen', REFINE_CASES)
+def test_refinenet_sequences_with_state_and_gradients(cfg, rnn, cells, skip, screen):
+    """refine_net.py:237-255 over B x T with non-zero initial states: heatmaps, final states
+    and gradients w.r.t. the input heatmap, the initial state and every weight."""
+    from eve_b200 import synth
+    from eve_b200.models import RefineNet
+    cfg.override('refine_net_enabled', True)
+    cfg.override('load_screen_content', screen)
+    cfg.override('refine_net_use_skip_connections', skip)
+    cfg.override('refine_net_use_rnn', rnn is not None)
+    if rnn:
+        cfg.override('refine_net_rnn_type', rnn)
+        cfg.override('refine_net_rnn_num_cells', cells)
+    sd = synth.make_state_dict(synth.refine_net_param_shapes(cfg), 79)
+    net = _load(RefineNet(), sd)
+    B, T = 2, 3
+    g = torch.Generator().manual_seed(10)
+    px = torch.stack([torch.rand(B, T, generator=g) * 1920, torch.rand(B, T, generator=g) * 1080], -1)
+    hm = O.make_heatmaps(px, 10.0)
+    scr = torch.rand(B, T, 3, 72, 128, generator=g) if screen else None
+    h0 = torch.randn(cells, B, 64, 5, 8, generator=g) * 0.5 if rnn else None
+    c0 = torch.randn(cells, B, 64, 5, 8, generator=g) * 0.5 if rnn == 'CLSTM' else None
+    wo = torch.randn(B, T, 1, 72, 128, generator=g)
+    wh = torch.randn(cells, B, 64, 5, 8, generator=g) if rnn in ('CGRU', 'CRNN') else None
+
+    osd = {'refine_net.' + k: v.double().requires_grad_(True) for k, v in sd.items()}
+    hm64 = hm.double().requires_grad_(True)
+    h64 = h0.double().requires_grad_(True) if rnn else None
+    states = None
+    if rnn:
+        states = [(h64[i], c0[i].double()) if rnn == 'CLSTM' else h64[i] for i in range(cells)]
+    outs = []
+    for t in range(T):
+        o, states = O.refine_net_step(osd, cfg, scr[:, t].double() if screen else None,
+                                      hm64[:, t], states or None)
+        outs.append(o)
+    want = torch.stack(outs, 1)
+    loss = (want * wo.double()).sum()
+    if wh is not None:
+        fin = torch.stack(list(states), 0)
+        loss = loss + (fin * wh.double()).sum()
+    loss.backward()
+
+    hmc = hm.cuda().requires_grad_(True)
+    hc = h0.cuda().requires_grad_(True) if rnn else None
+    got, hT, cT = net.sequence(scr.cuda() if screen else None, hmc, hc,
+                               c0.cuda() if c0 is not None else None)
+    assert G.rel(got, want) < 1e-4
+    closs = (got * wo.cuda()).sum()
+    if wh is not None:
+        assert G.rel(hT, fin) < 1e-4
+        closs = closs + (hT * wh.cuda()).sum()
+    elif rnn == 'CLSTM':
+        fin_h = torch.stack([s[0] for s in states], 0)
+        fin_c = torch.stack([s[1] for s in states], 0)
+        assert G.rel(hT, fin_h) < 1e-4 and G.rel(cT, fin_c) < 1e-4
+    closs.backward()
+    ref = hm64.grad
+    l2 = float((hmc.grad.double().cpu() - ref).norm() / (ref.norm() + 1e-30))
+    assert l2 < 1e-3, l2
+    if wh is not None:
+        ref = h64.grad
+        l2 = float((hc.grad.double().cpu() - ref).norm() / (ref.norm() + 1e-30))
+        assert l2 < 1e-3, l2
+    worst = 0.0
+    for name, p in net.named_parameters():
+        ref = osd['refine_net.' + name].grad
+        if ref is None or float(ref.norm()) == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) < 1e-6, name
+            continue
+        assert p.grad is not None, name
+        l2 = float((p.grad.double().cpu() - ref).norm() / (ref.norm() + 1e-30))
+        worst = max(worst, l2)
+        # biases that feed an InstanceNorm have an exactly-zero true gradient: noise only
+        if float(ref.norm()) < 1e-9 * float(want.numel()):
+            continue
+        assert l2 < 5e-3, (name, l2)
+    assert worst < 5e-2
+
+
+def test_per_step_and_time_batched_paths_agree(cfg):
+    """EyeNet.forward / RefineNet.forward called once per time step with
+    previous_output_dict (the reference's own calling pattern, eve.py:91-147) give what the
+    time-batched EVE.forward computes."""
+    from eve_b200 import synth
+    from eve_b200.models import EVE
+    from eve_b200.models.common import batch_make_heatmaps
+    cfg.override('refine_net_enabled', True)
+    cfg.override('load_screen_content', True)
+    B, T = 2, 3
+    sd = synth.make_state_dict(synth.eye_net_param_shapes(cfg), 5, 'eye_net.')
+    sd.update(synth.make_state_dict(synth.refine_net_param_shapes(cfg), 1005, 'refine_net.'))
+    model = _load(EVE(output_predictions=True), sd).eval()
+    inputs = _cuda(synth.make_clip_batch(B, T, seed=5))
+    with torch.no_grad():
+        out = model(dict(inputs))
+        mid = model.last_intermediates
+        prev = None
+        for t in range(T):
+            sub = {k: v[:, t] for k, v in inputs.items()}
+            o = {}
+            model.eye_net(sub, o, side='left', previous_output_dict=prev)
+            model.eye_net(sub, o, side='right', previous_output_dict=prev)
+            assert G.rel(o['left_g_initial'], mid['left_g_initial'][:, t]) < 1e-5
+            assert G.rel(o['right_pupil_size'], mid['right_pupil_size'][:, t]) < 1e-5
+            o['heatmap_initial'] = mid['heatmap_initial'][:, t]
+            model.refine_net(sub, o, previous_output_dict=prev)
+            assert G.rel(o['heatmap_final'], mid['heatmap_final'][:, t]) < 1e-4
+            prev = o
+    assert out['PoG_px_final'].shape == (B, T, 2)
+
+
+def test_empty_and_single_frame_inputs(cfg):
+    from eve_b200 import synth
+    from eve_b200.models import EyeNet
+    net = _load(EyeNet(), synth.make_state_dict(synth.eye_net_param_shapes(cfg), 3))
+    with torch.no_grad():
+        assert net.cnn_features(torch.zeros(0, 3, 128, 128, device='cuda')).shape == (0, 128)
+        f = net.cnn_features(torch.zeros(1, 3, 128, 128, device='cuda'))
+        assert f.shape == (1, 128) and bool(torch.isfinite(f).all())
