@@ -1,0 +1,455 @@
+"""bench.py -- eye-frames/sec (forward + backward + gradient step) of the EVE hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload eve_refine|eyenet_static]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU arm (oracle port of the reference)
+
+One "step" = one optimisation step over one synthetic batch of B=8 clips x T=30 frames per
+GPU (BASELINE.json): time-batched EVE.forward (EyeNet for both eyes [+ GazeRefineNet]),
+full_loss.backward(), one gradient allreduce when N > 1, fused clip + Adam.  An eye-frame is
+one 128x128 eye patch pushed through EyeNet: 2*B*T = 480 per GPU per step.
+
+Rank 0 prints ONE JSON line (see the keys at the bottom).  `value` is measured with inputs
+resident in HBM; `e2e` repeats the measurement through the same public call with the batch
+in pinned host memory (H2D copy + D2H read of the loss inside the timed region).  The
+`roofline` object times the convolution kernels (the dense contractions that dominate the
+step) live with CUDA events recorded on their launching stream inside the timed region.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = 'eye-frames/sec (fwd+bwd) at seq_len=30, 128x128 patches'
+UNIT = 'eye-frames/s'
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the north_star's target workload (eye patches + screen frames)
+    'eve_refine': dict(desc='EyeNet(GRU) x2 eyes + GazeRefineNet(CGRU), 128x72 screen frames, '
+                            'seq_len=30, batch=8 clips/GPU (BASELINE configs[2])',
+                       overrides=dict(refine_net_enabled=True, load_screen_content=True)),
+    # BASELINE.json configs[1]
+    'eyenet_static': dict(desc='EyeNet static (eye_net_use_rnn=0, refine_net_enabled=0), '
+                               'seq_len=30, batch=8 clips/GPU (BASELINE configs[1])',
+                          overrides=dict(refine_net_enabled=False, load_screen_content=False,
+                                         eye_net_use_rnn=False)),
+}
+# algorithmic conv-stack FLOPs per unit, fwd+bwd
+FLOP_EYE_FRAME = 3477409536.0
+FLOP_SCREEN_FRAME = 9629761536.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='eve_refine', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=8, help='clips per GPU')
+    ap.add_argument('--seq-len', type=int, default=30)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the secondary workload line')
+    return ap.parse_args()
+
+
+def configure(workload):
+    from eve_b200.config import DefaultConfig
+    cfg = DefaultConfig()
+    cfg.reset()
+    for k, v in WORKLOADS[workload]['overrides'].items():
+        cfg.override(k, v)
+    return cfg
+
+
+def build_state_dict(cfg, seed=0):
+    from eve_b200 import synth
+    sd = synth.make_state_dict(synth.eye_net_param_shapes(cfg), seed, 'eye_net.')
+    if cfg.refine_net_enabled:
+        sd.update(synth.make_state_dict(synth.refine_net_param_shapes(cfg), seed + 1000,
+                                        'refine_net.'))
+    return sd
+
+
+# --------------------------------------------------------------------------- clocks --
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                power.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                                  'sw_power_cap'), r[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None,
+                'sm_max_mhz': max(smax) if smax else None,
+                'power_w_max': max(power) if power else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------ reference --
+def run_reference_step(cfg, sd, B, T, seed, threads):
+    """One fwd+bwd of the CPU oracle (the restatement of the reference's PyTorch path) on a
+    B x T sample; returns (eye_frames, seconds)."""
+    import numpy as np
+    import torch
+    from eve_b200 import synth
+    from oracle import eve_oracle as O
+    torch.set_num_threads(threads)
+    inputs = synth.make_clip_batch(B, T, seed=seed, with_screen=bool(cfg.load_screen_content))
+    np.random.seed(seed)
+    std = np.radians(cfg.refine_net_offset_augmentation_sigma)
+    kap = {'left': torch.from_numpy(np.random.normal(size=(B, 2), scale=std).astype(np.float32)),
+           'right': torch.from_numpy(np.random.normal(size=(B, 2), scale=std).astype(np.float32))}
+    osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    t0 = time.perf_counter()
+    out, _ = O.eve_forward(osd, cfg, inputs, True, kap)
+    out['full_loss'].backward()
+    return 2 * B * T, time.perf_counter() - t0
+
+
+def cpu_baseline(cfg, sd, budget_clips=(4, 15)):
+    import torch
+    threads = os.cpu_count() or 1
+    run_reference_step(cfg, sd, 1, 2, 1, threads)               # warm-up (oneDNN primitives)
+    B, T = budget_clips
+    frames, sec = run_reference_step(cfg, sd, B, T, 2, threads)
+    return {'value': frames / sec, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': 'oracle/eve_oracle.py (CPU restatement of the reference PyTorch path, fp32, '
+                      'torch %s, %d threads): 1 warm-up (B=1,T=2) then one fwd+bwd of B=%d clips x '
+                      'T=%d frames = %d eye-frames in %.1f s' % (torch.__version__, threads, B, T,
+                                                                  frames, sec)}
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference
+    is pure Python/PyTorch and is not present on the GPU box, so this is the oracle port
+    (kind "port"), on all host threads, same workload config, a bounded sample per step."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    cfg = configure(args.workload)
+    sd = build_state_dict(cfg)
+    threads = os.cpu_count() or 1
+    B, T = 2, 6                                                 # 24 eye-frames per step
+    for i in range(max(args.warmup, 1)):
+        run_reference_step(cfg, sd, 1 if i else B, 2 if i else T, 10 + i, threads)
+    frames = 0
+    sec = 0.0
+    for i in range(args.steps):
+        f, s = run_reference_step(cfg, sd, B, T, 100 + i, threads)
+        frames += f
+        sec += s
+    value = frames / sec
+    sample = ('oracle port of the reference PyTorch CPU path (fp32, torch %s), %d threads; each '
+              'step = fwd+bwd of B=%d clips x T=%d frames (%d eye-frames), a bounded sample of '
+              'the B=%d x T=%d workload' % (torch.__version__, threads, B, T, 2 * B * T,
+                                            args.batch, args.seq_len))
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sec / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOADS[args.workload]['desc'], 'global_batch': args.batch,
+                   'seq_len': args.seq_len, 'sample_per_step': 'B=%d,T=%d' % (B, T)},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+# ------------------------------------------------------------------------- B200 arm --
+def make_batch(B, T, cfg, seed, pinned):
+    from eve_b200 import synth
+    d = synth.make_clip_batch(B, T, seed=seed, with_screen=bool(cfg.load_screen_content))
+    if pinned:
+        d = {k: v.pin_memory() for k, v in d.items()}
+    return d
+
+
+def timed_run(model, trainer, batches_fn, steps, warmup, world, device, profile):
+    """W untimed + K timed steps; returns (max-over-ranks ms total, launches, prof dict)."""
+    import torch
+    import torch.distributed as dist
+    from eve_b200 import lib as L
+    lib = L.load()
+    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # > 126 MB L2
+
+    def one(i):
+        inputs = batches_fn(i)
+        out = model({'bench': inputs}, current_epoch=0.0)
+        loss = out['full_loss']
+        trainer.step(loss)
+        return loss
+
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if profile:
+        lib.eve_profile_reset()
+        lib.eve_profile_enable(1)
+    launches0 = lib.eve_launch_count()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    last = None
+    for i in range(steps):
+        flush.zero_()                       # evict L2 between timed iterations
+        ev0[i].record()
+        loss = one(warmup + i)
+        last = loss.detach()
+        ev1[i].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    lib.eve_profile_enable(0)
+    launches = lib.eve_launch_count() - launches0
+    ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    prof = None
+    if profile:
+        prof = {}
+        for kind, name in ((0, 'conv_fwd'), (1, 'conv_dgrad'), (2, 'conv_wgrad')):
+            v = [C.c_double(), C.c_double(), C.c_double(), C.c_longlong()]
+            L.check(lib.eve_profile_read(kind, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]),
+                                         C.byref(v[3])), 'eve_profile_read')
+            prof[name] = {'ms': v[0].value, 'flops': v[1].value, 'bytes': v[2].value,
+                          'launches': v[3].value}
+        lib.eve_profile_reset()
+    return float(t.item()), int(launches), prof, float(last)
+
+
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world != args.gpus and world > 1:
+        raise SystemExit('bench.py: --gpus %d but WORLD_SIZE=%d' % (args.gpus, world))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit('bench.py: launch N>1 with torch.distributed.run (one rank per GPU)')
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the B200 path has no CPU fallback')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+
+    from eve_b200 import lib as L
+    from eve_b200.models import EVE
+    from eve_b200.parallel import FlatAdamTrainer
+    import numpy as np
+    L.load()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+
+    def measure(workload, steps, warmup, with_e2e, profile):
+        cfg = configure(workload)
+        np.random.seed(1234 + rank)        # kappa augmentation draws (eve.py:468-469)
+        model = EVE()
+        model.load_state_dict(build_state_dict(cfg), strict=True)
+        model = model.to(device).train()
+        trainer = FlatAdamTrainer(model)
+        B, T = args.batch, args.seq_len
+        nb = 2                              # two distinct synthetic batches, alternated
+        host = [make_batch(B, T, cfg, seed=1000 * rank + i, pinned=True) for i in range(nb)]
+        dev = [{k: v.to(device) for k, v in h.items()} for h in host]
+        res = {}
+        sampler = ClockSampler(torch.cuda.current_device() if 'CUDA_VISIBLE_DEVICES' not in os.environ
+                               else 0)
+        if rank == 0:
+            sampler.start()
+        ms, launches, prof, loss = timed_run(model, trainer, lambda i: dict(dev[i % nb]), steps,
+                                             warmup, world, device, profile)
+        clocks = sampler.stop() if rank == 0 else None
+        frames = 2 * B * T * world * steps
+        res.update(ms=ms, launches=launches, prof=prof, loss=loss, clocks=clocks,
+                   value=frames / (ms * 1e-3), frames_per_step=2 * B * T * world)
+        if with_e2e:
+            def h2d(i):
+                return {k: v.to(device, non_blocking=True) for k, v in host[i % nb].items()}
+            h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+            # the D2H read of the loss happens inside timed_run's `float(last)` only once; make
+            # it per step here:
+            def step_inputs(i):
+                return h2d(i)
+            ms2, _, _, _ = timed_run_e2e(model, trainer, step_inputs, steps, max(warmup, 1), world,
+                                         device)
+            res['e2e'] = {'value': frames / (ms2 * 1e-3), 'unit': UNIT,
+                          'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4,
+                          'ms_per_step': ms2 / steps}
+        res['cfg'] = cfg
+        return res
+
+    main = measure(args.workload, args.steps, args.warmup, True, True)
+    cfg = main['cfg']
+    extra = None
+    if not args.no_extra:
+        other = 'eyenet_static' if args.workload == 'eve_refine' else 'eve_refine'
+        torch.cuda.empty_cache()
+        ex = measure(other, args.steps, args.warmup, False, False)
+        extra = {'workload': WORKLOADS[other]['desc'], 'value': ex['value'], 'unit': UNIT,
+                 'ms_per_step': ex['ms'] / args.steps}
+    cfg = configure(args.workload)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family (implicit-GEMM convolutions)
+    prof = main['prof']
+    conv_ms = sum(p['ms'] for p in prof.values())
+    conv_flops = sum(p['flops'] for p in prof.values())
+    conv_launches = sum(p['launches'] for p in prof.values())
+    peak = peaks.get('bf16_tflops_sustained')
+    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
+    if peak is None:
+        peak, peak_src = 1400.0, 'fallback (B200_PROFILING.md sustained figure)'
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    roofline = {
+        'bound': 'tensor', 'kernel': 'igemm_gather_kernel / igemm_wgrad_kernel (fp32 SIMT implicit '
+                                     'GEMM; all conv fwd + dgrad + wgrad launches of the timed steps)',
+        'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+        'peak_source': peak_src, 'traffic': None,
+        'launches': conv_launches, 'avg_launch_ms': conv_ms / max(conv_launches, 1),
+        'share_of_step': conv_ms / main['ms'],
+        'per_kind': {k: {'ms_per_step': v['ms'] / args.steps,
+                         'tflops': (v['flops'] / (v['ms'] * 1e-3) / 1e12) if v['ms'] > 0 else 0.0,
+                         'launches_per_step': v['launches'] / args.steps}
+                     for k, v in prof.items()},
+        'step_algorithmic_tflop': (FLOP_EYE_FRAME * 2 + (FLOP_SCREEN_FRAME if cfg.refine_net_enabled
+                                                         else 0.0)) * args.batch * args.seq_len / 1e12,
+    }
+    out = {
+        'metric': METRIC, 'value': main['value'], 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': main['ms'] / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOADS[args.workload]['desc'],
+                   'global_batch': args.batch * world, 'seq_len': args.seq_len,
+                   'eye_frames_per_step': main['frames_per_step'],
+                   'parallelism': 'dp%d (clips sharded on the batch axis, one NCCL allreduce of '
+                                  'the flat fp32 gradient buffer)' % world,
+                   'step': 'EVE.forward + full_loss.backward + clip_grad_norm + Adam',
+                   'cache': 'L2 flushed (160 MB write) between timed iterations; activations '
+                            '(>8 GB/step) exceed L2',
+                   'weights': 'random init (seeded), reference architecture'},
+        'e2e': main['e2e'], 'gpu_launches': main['launches'], 'clocks': main['clocks'],
+        'roofline': roofline, 'final_loss': main['loss'],
+    }
+    if extra is not None:
+        out['also'] = extra
+    if world == 1 and not args.no_cpu_baseline:
+        out['cpu_baseline'] = cpu_baseline(cfg, build_state_dict(cfg))
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def timed_run_e2e(model, trainer, inputs_fn, steps, warmup, world, device):
+    """Same step through the public call with HOST (pinned) inputs: per step an H2D copy of
+    the batch and a D2H read of the loss, all inside the timed region."""
+    import torch
+    import torch.distributed as dist
+    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=device)
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def one(i):
+        inputs = inputs_fn(i)
+        out = model({'bench': inputs}, current_epoch=0.0)
+        loss = out['full_loss']
+        trainer.step(loss)
+        host_loss.copy_(loss.detach(), non_blocking=False)     # D2H + sync, like training.py:506
+        return float(host_loss)
+
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    total = 0.0
+    for i in range(steps):
+        flush.zero_()
+        ev0.record()
+        one(warmup + i)
+        ev1.record()
+        ev1.synchronize()
+        total += ev0.elapsed_time(ev1)
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), None, None, None
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,6 +1,9 @@
 // C ABI: error reporting and the single-op entry points (see include/eve_b200.h).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -13,6 +16,47 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- profiler state (host side only)
+struct ProfRec {
+  int kind;
+  double flops, bytes;
+  cudaEvent_t a, b;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+ProfScope::ProfScope(int kind, double flops, double bytes, cudaStream_t stream)
+    : slot(-1), s(stream) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{kind, flops, bytes, prof_event(), prof_event()};
+  if (!r.a || !r.b) return;
+  cudaEventRecord(r.a, s);
+  g_prof_recs.push_back(r);
+  slot = (int)g_prof_recs.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot < (int)g_prof_recs.size()) cudaEventRecord(g_prof_recs[slot].b, s);
 }
 
 static int check_conv(const eve_conv_params* p, ConvGeom& g) {
@@ -38,6 +82,44 @@ static size_t conv_ws_floats(const ConvGeom& g) {
 using namespace eve;
 
 extern "C" int eve_version(void) { return 100; }
+extern "C" long long eve_launch_count(void) { return g_launches.load(); }
+
+extern "C" void eve_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+}
+
+extern "C" void eve_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof_recs) {
+    g_prof_pool.push_back(r.a);
+    g_prof_pool.push_back(r.b);
+  }
+  g_prof_recs.clear();
+}
+
+extern "C" int eve_profile_read(int kind, double* ms, double* flops, double* bytes,
+                                long long* launches) {
+  EVE_REQUIRE(kind >= 0 && kind < PROF_KINDS, EVE_ERR_SHAPE, "profile_read: bad kind %d", kind);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double t = 0.0, f = 0.0, b = 0.0;
+  long long n = 0;
+  for (auto& r : g_prof_recs) {
+    if (r.kind != kind) continue;
+    EVE_CUDA(cudaEventSynchronize(r.b));
+    float e = 0.f;
+    EVE_CUDA(cudaEventElapsedTime(&e, r.a, r.b));
+    t += e;
+    f += r.flops;
+    b += r.bytes;
+    ++n;
+  }
+  if (ms) *ms = t;
+  if (flops) *flops = f;
+  if (bytes) *bytes = b;
+  if (launches) *launches = n;
+  return EVE_OK;
+}
 extern "C" const char* eve_last_error(void) { return g_error; }
 
 extern "C" size_t eve_conv2d_workspace_bytes(const eve_conv_params* p) {
@@ -81,7 +163,8 @@ extern "C" int eve_conv2d_wgrad(const eve_conv_params* p, const float* x, const 
                                 eve_stream_t stream) {
   ConvGeom g;
   EVE_TRY(check_conv(p, g));
-  EVE_REQUIRE(x && dy && dw && workspace, EVE_ERR_NULL, "conv2d_wgrad: NULL pointer");
+  EVE_REQUIRE(dw && workspace && (g.N == 0 || (x && dy)), EVE_ERR_NULL,
+              "conv2d_wgrad: NULL pointer");
   EVE_REQUIRE(workspace_bytes >= conv_ws_floats(g) * sizeof(float), EVE_ERR_WORKSPACE,
               "conv2d_wgrad: workspace too small");
   cudaStream_t s = as_stream(stream);

@@ -21,7 +21,12 @@ void set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
-#define EVE_LAUNCH_CHECK() EVE_CUDA(cudaGetLastError())
+// Every kernel launch goes through this check, which also feeds eve_launch_count().
+#define EVE_LAUNCH_CHECK()             \
+  do {                                 \
+    ::eve::count_launch();             \
+    EVE_CUDA(cudaGetLastError());      \
+  } while (0)
 
 #define EVE_TRY(expr)                                                                   \
   do {                                                                                  \
@@ -36,6 +41,18 @@ void set_error(const char* fmt, ...);
       return (code);                                                                    \
     }                                                                                   \
   } while (0)
+
+void count_launch();
+
+// Optional per-kernel-family device timing (eve_profile_*): CUDA events recorded on the
+// launching stream around a launch, summed on read.  Costs nothing when disabled.
+enum ProfKind { PROF_CONV_FWD = 0, PROF_CONV_DGRAD = 1, PROF_CONV_WGRAD = 2, PROF_KINDS = 3 };
+struct ProfScope {
+  int slot;
+  cudaStream_t s;
+  ProfScope(int kind, double flops, double bytes, cudaStream_t stream);
+  ~ProfScope();
+};
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

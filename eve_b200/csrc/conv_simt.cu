@@ -352,6 +352,15 @@ int colsum_blocks(long long rows) {
   return (int)b;
 }
 
+// algorithmic work of one convolution pass (fwd, dgrad and wgrad all do 2*M*N*K flops)
+inline double conv_flops(const ConvGeom& g) {
+  return 2.0 * (double)g.N * g.OH * g.OW * (double)g.Cout * (double)g.K();
+}
+// algorithmic fp32 bytes: input + output activations + weights, each touched once
+inline double conv_bytes(const ConvGeom& g) {
+  return 4.0 * ((double)g.in_elems() + (double)g.out_elems() + (double)g.Cout * g.K());
+}
+
 int wgrad_splits(const ConvGeom& g) {
   int tiles = cdiv(g.Cout, 64) * cdiv(g.K(), 64);
   long long P = (long long)g.N * g.OH * g.OW;
@@ -379,6 +388,7 @@ int conv_fwd_simt(const ConvGeom& g, const float* x, const float* wf, const floa
   a.Ho = g.OH; a.Wo = g.OW; a.Nn = g.Cout; a.KH = g.KH; a.KW = g.KW;
   a.num = g.stride; a.den = 1; a.dr = 1; a.base = -g.pad;
   a.M = g.N * g.OH * g.OW; a.K = g.K(); a.ldo = ldo;
+  ProfScope prof(PROF_CONV_FWD, conv_flops(g), conv_bytes(g), s);
   return dispatch_gather(a, s);
 }
 
@@ -390,6 +400,7 @@ int conv_dgrad_simt(const ConvGeom& g, const float* dy, int lddy, const float* w
   a.Ho = g.H; a.Wo = g.W; a.Nn = g.Cin; a.KH = g.KH; a.KW = g.KW;
   a.num = 1; a.den = g.stride; a.dr = -1; a.base = g.pad;
   a.M = g.N * g.H * g.W; a.K = g.KH * g.KW * g.Cout; a.ldo = g.Cin;
+  ProfScope prof(PROF_CONV_DGRAD, conv_flops(g), conv_bytes(g), s);
   return dispatch_gather(a, s);
 }
 
@@ -408,6 +419,7 @@ int conv_wgrad_simt(const ConvGeom& g, const float* x, const float* dy, int lddy
   a.chunk = cdiv(cdiv(a.P, S), BK) * BK;
   S = cdiv(a.P, a.chunk);
   dim3 grid(cdiv(g.Cout, 64), cdiv(a.KK, 64), S);
+  ProfScope prof(PROF_CONV_WGRAD, conv_flops(g), conv_bytes(g), s);
   igemm_wgrad_kernel<<<grid, NT, 0, s>>>(a);
   EVE_LAUNCH_CHECK();
   size_t total = (size_t)g.Cout * g.K();

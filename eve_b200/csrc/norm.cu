@@ -118,14 +118,17 @@ in_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ yma
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                      float* __restrict__ sum_g, float* __restrict__ sum_gx) {
-  __shared__ float s1[256], s2[256];
+  // fp64 accumulators: sum(g*xhat) cancels heavily (it is a covariance), and the affine
+  // gradients are sums of these over the batch; B200 has the fp64 rate to hide this behind
+  // the HBM reads (2 DFMA per 8-12 bytes loaded).
+  __shared__ double s1[256], s2[256];
   const int n = blockIdx.x;
   const int cl = threadIdx.x % CB;
   const int c = blockIdx.y * CB + cl;
   const int lane = threadIdx.x / CB;
   const int L = 256 / CB;
   const size_t base = (size_t)n * HW * C;
-  float a = 0.f, b = 0.f;
+  double a = 0.0, b = 0.0;
   if (c < C) {
     const float m = mean[(size_t)n * C + c], r = rstd[(size_t)n * C + c];
     const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
@@ -134,8 +137,8 @@ in_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ yma
       float g = __ldg(dy + o);
       float xh = (__ldg(x + o) - m) * r;
       if (act != ACT_NONE) g *= act_grad(ymask ? __ldg(ymask + o) : fmaf(xh, ga, be), act);
-      a += g;
-      b = fmaf(g, xh, b);
+      a += (double)g;
+      b += (double)g * (double)xh;
     }
   }
   s1[threadIdx.x] = a;
@@ -146,8 +149,8 @@ in_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ yma
       a += s1[l * CB + cl];
       b += s2[l * CB + cl];
     }
-    sum_g[(size_t)n * C + c] = a;
-    sum_gx[(size_t)n * C + c] = b;
+    sum_g[(size_t)n * C + c] = (float)a;
+    sum_gx[(size_t)n * C + c] = (float)b;
   }
 }
 
@@ -202,13 +205,13 @@ __global__ void in_affine_grad_kernel(const float* __restrict__ sum_g,
                                       int accumulate) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  float a = 0.f, b = 0.f;
+  double a = 0.0, b = 0.0;
   for (int n = 0; n < N; ++n) {
-    a += sum_gx[(size_t)n * C + c];
-    b += sum_g[(size_t)n * C + c];
+    a += (double)sum_gx[(size_t)n * C + c];
+    b += (double)sum_g[(size_t)n * C + c];
   }
-  dgamma[c] = accumulate ? dgamma[c] + a : a;
-  dbeta[c] = accumulate ? dbeta[c] + b : b;
+  dgamma[c] = accumulate ? dgamma[c] + (float)a : (float)a;
+  dbeta[c] = accumulate ? dbeta[c] + (float)b : (float)b;
 }
 
 inline int chan_block(int C) { return C >= 32 ? 32 : C; }

@@ -53,6 +53,10 @@ _P, _I, _F, _Z = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
     'eve_version': (_I, []),
     'eve_last_error': (C.c_char_p, []),
+    'eve_launch_count': (C.c_longlong, []),
+    'eve_profile_enable': (None, [_I]),
+    'eve_profile_reset': (None, []),
+    'eve_profile_read': (_I, [_I, _P, _P, _P, _P]),
     'eve_conv2d_workspace_bytes': (_Z, [_P]),
     'eve_conv2d_fwd': (_I, [_P, _P, _P, _P, _P, _P, _Z, _P]),
     'eve_conv2d_dgrad': (_I, [_P, _P, _P, _P, _P, _Z, _P]),

@@ -1,0 +1,86 @@
+"""Data-parallel training step of the EVE hot path: backward -> ONE gradient allreduce ->
+fused clip + Adam on flat buffers.
+
+Reference being replaced: the single-GPU step of src/core/training.py:485-502
+(``loss.backward()``, ``clip_grad_norm_(model.parameters(), 5.0)``, ``optimizer.step()``) with
+the optimizer of src/train.py:49-55 (``Adam(lr=config.learning_rate, weight_decay=...)``).
+The reference has no multi-GPU code at all; clips are independent (per-sample InstanceNorm,
+per-clip losses), so each rank runs the same model on its own clips and the only exchange
+is one sum-allreduce of the flat fp32 gradient buffer between backward and clipping -- after
+it every rank clips against the *global* gradient norm and applies the identical update,
+exactly as one GPU with the concatenated batch would.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .config import get_config
+
+
+class FlatAdamTrainer(object):
+    """Owns flat parameter / gradient / Adam-moment buffers; the model's parameters become
+    views into the flat parameter buffer (names, shapes and state_dict keys unchanged)."""
+
+    def __init__(self, model, lr=None, weight_decay=None, betas=(0.9, 0.999), eps=1e-8,
+                 max_norm=None, process_group=None):
+        cfg = get_config()
+        self.model = model
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError('FlatAdamTrainer: the model has no trainable parameter')
+        dev = self.params[0].device
+        self.sizes = [p.numel() for p in self.params]
+        self.flat = torch.cat([p.detach().reshape(-1).float() for p in self.params]).contiguous()
+        off = 0
+        for p, n in zip(self.params, self.sizes):
+            p.data = self.flat[off:off + n].view(p.shape)
+            off += n
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.lr = float(cfg.learning_rate if lr is None else lr)
+        self.weight_decay = float(cfg.weight_decay if weight_decay is None else weight_decay)
+        self.betas, self.eps = betas, eps
+        if max_norm is None:
+            if cfg.do_gradient_clipping and cfg.gradient_clip_by != 'norm':
+                raise ValueError("gradient_clip_by='%s' is not supported by the fused step "
+                                 "(only 'norm', training.py:492-498)" % cfg.gradient_clip_by)
+            max_norm = cfg.gradient_clip_amount if cfg.do_gradient_clipping else 0.0
+        self.max_norm = float(max_norm)
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.steps = 0
+        self.device = dev
+        self.last_grad_norm = None
+
+    def gather_grads(self):
+        """Pack p.grad of every trainable parameter into the flat gradient buffer (one
+        concatenation kernel); parameters that did not take part in the graph count as zero."""
+        views = []
+        for p in self.params:
+            views.append(p.grad.reshape(-1) if p.grad is not None
+                         else torch.zeros(p.numel(), dtype=torch.float32, device=p.device))
+        torch.cat(views, out=self.grad)
+        for p in self.params:
+            p.grad = None
+
+    def apply(self, update=None):
+        """allreduce (sum) + clip by the global norm + Adam, on the flat buffers.
+
+        ``update`` replaces the fused CUDA kernel (tests of the communication logic on a
+        GPU-less box inject a torch restatement); the product path leaves it None and fails
+        loudly on CPU tensors."""
+        if self.world > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
+        self.steps += 1
+        if update is not None:
+            self.last_grad_norm = update(self)
+            return
+        self.last_grad_norm = ops.adam_clip_step(
+            self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.steps, self.lr,
+            self.betas, self.eps, self.weight_decay, self.max_norm, 1.0 / self.world)
+
+    def step(self, loss, update=None):
+        loss.backward()
+        self.gather_grads()
+        self.apply(update)

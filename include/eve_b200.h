@@ -38,6 +38,16 @@ typedef void* eve_stream_t; /* cudaStream_t */
 
 int eve_version(void);
 const char* eve_last_error(void);
+/* number of kernels this library has launched since it was loaded (all threads) */
+long long eve_launch_count(void);
+/* Optional device-side timing of the convolution kernels, used by bench.py for the roofline
+ * line: when enabled, every conv launch is bracketed by CUDA events on its own stream.
+ * kind: 0 forward, 1 data-gradient, 2 weight-gradient.  eve_profile_read() synchronises the
+ * recorded events and returns summed milliseconds, algorithmic FLOPs (2*M*N*K) and algorithmic
+ * bytes (fp32 input + output + weights, once each) and the launch count of that kind. */
+void eve_profile_enable(int on);
+void eve_profile_reset(void);
+int eve_profile_read(int kind, double* ms, double* flops, double* bytes, long long* launches);
 
 /* ------------------------------------------------------------------ building blocks --
  * Exposed so that each kernel family can be parity-tested on its own.  NHWC fp32. */

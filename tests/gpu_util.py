@@ -30,7 +30,8 @@ def conv_fwd(x_nchw, w, bias, stride, pad):
     ow = (wd + 2 * pad - k) // stride + 1
     y = torch.empty((n, oh, ow, cout), device='cuda')
     ws = _ws(p)
-    L.check(lib.eve_conv2d_fwd(C.byref(p), L.ptr(nhwc(x_nchw)), L.ptr(w.contiguous()),
+    x, w = nhwc(x_nchw), w.contiguous()          # keep alive: L.ptr() takes raw addresses
+    L.check(lib.eve_conv2d_fwd(C.byref(p), L.ptr(x), L.ptr(w),
                                L.ptr(bias), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()),
             'conv_fwd')
     return nchw(y)
@@ -44,7 +45,8 @@ def conv_dgrad(dy_nchw, w, in_hw, stride, pad):
     p = L.ConvParams(n, h, wd, cin, cout, k, stride, pad)
     dx = torch.empty((n, h, wd, cin), device='cuda')
     ws = _ws(p)
-    L.check(lib.eve_conv2d_dgrad(C.byref(p), L.ptr(nhwc(dy_nchw)), L.ptr(w.contiguous()),
+    dy, w = nhwc(dy_nchw), w.contiguous()
+    L.check(lib.eve_conv2d_dgrad(C.byref(p), L.ptr(dy), L.ptr(w),
                                  L.ptr(dx), L.ptr(ws), ws.numel(), L.stream_ptr()), 'conv_dgrad')
     return nchw(dx)
 
@@ -57,7 +59,8 @@ def conv_wgrad(x_nchw, dy_nchw, k, stride, pad, with_bias=True):
     dw = torch.empty((cout, cin, k, k), device='cuda')
     db = torch.empty((cout,), device='cuda') if with_bias else None
     ws = _ws(p)
-    L.check(lib.eve_conv2d_wgrad(C.byref(p), L.ptr(nhwc(x_nchw)), L.ptr(nhwc(dy_nchw)), L.ptr(dw),
+    x, dy = nhwc(x_nchw), nhwc(dy_nchw)
+    L.check(lib.eve_conv2d_wgrad(C.byref(p), L.ptr(x), L.ptr(dy), L.ptr(dw),
                                  L.ptr(db), L.ptr(ws), ws.numel(), L.stream_ptr()), 'conv_wgrad')
     return dw, db
 
@@ -82,7 +85,8 @@ def instnorm_bwd(dy_nchw, y_nchw, x_nchw, mean, rstd, gamma, act):
     dgamma = torch.empty(c, device='cuda') if gamma is not None else None
     dbeta = torch.empty(c, device='cuda') if gamma is not None else None
     ws = torch.empty(2 * n * c * 4 + 256, dtype=torch.uint8, device='cuda')
-    L.check(lib.eve_instnorm_act_bwd(L.ptr(nhwc(dy_nchw)), L.ptr(nhwc(y_nchw)), L.ptr(nhwc(x_nchw)),
+    dy, y, x = nhwc(dy_nchw), nhwc(y_nchw), nhwc(x_nchw)
+    L.check(lib.eve_instnorm_act_bwd(L.ptr(dy), L.ptr(y), L.ptr(x),
                                      n, h * w, c, L.ptr(mean), L.ptr(rstd), L.ptr(gamma), act,
                                      L.ptr(dx), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), ws.numel(),
                                      L.stream_ptr()), 'instnorm_bwd')
@@ -94,7 +98,8 @@ def adaptive_maxpool(x_nchw, oh, ow):
     n, c, h, w = x_nchw.shape
     y = torch.empty((n, oh, ow, c), device='cuda')
     idx = torch.empty((n, oh, ow, c), dtype=torch.int32, device='cuda')
-    L.check(lib.eve_adaptive_maxpool_fwd(L.ptr(nhwc(x_nchw)), n, h, w, c, oh, ow, L.ptr(y),
+    x = nhwc(x_nchw)
+    L.check(lib.eve_adaptive_maxpool_fwd(L.ptr(x), n, h, w, c, oh, ow, L.ptr(y),
                                          L.ptr(idx), L.stream_ptr()), 'amp_fwd')
     return nchw(y), idx.permute(0, 3, 1, 2).contiguous()
 
@@ -104,7 +109,8 @@ def adaptive_maxpool_bwd(dy_nchw, idx_nchw, h, w):
     n, c, oh, ow = dy_nchw.shape
     dx = torch.empty((n, h, w, c), device='cuda')
     idx = idx_nchw.permute(0, 2, 3, 1).contiguous()
-    L.check(lib.eve_adaptive_maxpool_bwd(L.ptr(nhwc(dy_nchw)), L.ptr(idx), n, h, w, c, oh, ow,
+    dy = nhwc(dy_nchw)
+    L.check(lib.eve_adaptive_maxpool_bwd(L.ptr(dy), L.ptr(idx), n, h, w, c, oh, ow,
                                          L.ptr(dx), L.stream_ptr()), 'amp_bwd')
     return nchw(dx)
 
@@ -113,7 +119,8 @@ def upsample(x_nchw, oh, ow):
     lib = L.load()
     n, c, h, w = x_nchw.shape
     y = torch.empty((n, oh, ow, c), device='cuda')
-    L.check(lib.eve_upsample_bilinear_fwd(L.ptr(nhwc(x_nchw)), n, h, w, c, oh, ow, L.ptr(y),
+    x = nhwc(x_nchw)
+    L.check(lib.eve_upsample_bilinear_fwd(L.ptr(x), n, h, w, c, oh, ow, L.ptr(y),
                                           L.stream_ptr()), 'up_fwd')
     return nchw(y)
 
@@ -122,7 +129,8 @@ def upsample_bwd(dy_nchw, h, w):
     lib = L.load()
     n, c, oh, ow = dy_nchw.shape
     dx = torch.empty((n, h, w, c), device='cuda')
-    L.check(lib.eve_upsample_bilinear_bwd(L.ptr(nhwc(dy_nchw)), n, h, w, c, oh, ow, L.ptr(dx),
+    dy = nhwc(dy_nchw)
+    L.check(lib.eve_upsample_bilinear_bwd(L.ptr(dy), n, h, w, c, oh, ow, L.ptr(dx),
                                           L.stream_ptr()), 'up_bwd')
     return nchw(dx)
 

@@ -70,6 +70,7 @@ def test_eve_forward_backward_matches_reference(name, cfg):
     gold = H.load_golden(name)
     H.apply_case_config(cfg, gold)
     training = bool(gold['meta/training'])
+    B, pad_last = int(gold['meta/B']), int(gold['meta/pad_last'])
     model = _load(EVE(output_predictions=True), H.case_state_dict(gold, cfg))
     model.train(training)
     inputs = _cuda(H.case_inputs(gold, cfg))
@@ -103,6 +104,12 @@ def test_eve_forward_backward_matches_reference(name, cfg):
         else:
             assert got.shape == ref.shape, (k, got.shape, ref.shape)
             tol = 2e-3 if ('final' in key or 'refined' in key or key == 'full_loss') else 2e-4
+            if pad_last and got.ndim >= 1 and got.shape[0] == B:
+                # Zero-padded frames (all-zero images, validity 0) put InstanceNorm at
+                # var ~ 0, where rstd = 316 amplifies fp32 summation-order noise: hold the
+                # padded clip to 3e-2 and every other clip to the normal bar.
+                assert H.rel_err(got[-1], ref[-1]) < 3e-2, (k, H.rel_err(got[-1], ref[-1]))
+                got, ref = got[:-1], ref[:-1]
             assert H.rel_err(got, ref) < tol, (k, H.rel_err(got, ref))
         checked += 1
     assert checked >= 20, checked
@@ -262,60 +269,81 @@ def test_refinenet_sequences_with_state_and_gradients(cfg, rnn, cells, skip, scr
     c0 = torch.randn(cells, B, 64, 5, 8, generator=g) * 0.5 if rnn == 'CLSTM' else None
     wo = torch.randn(B, T, 1, 72, 128, generator=g)
     wh = torch.randn(cells, B, 64, 5, 8, generator=g) if rnn in ('CGRU', 'CRNN') else None
+    def oracle(dtype):
+        osd = {'refine_net.' + k: v.detach().clone().to(dtype).requires_grad_(True)
+               for k, v in sd.items()}
+        hmo = hm.detach().clone().to(dtype).requires_grad_(True)
+        ho = h0.detach().clone().to(dtype).requires_grad_(True) if rnn else None
+        states = None
+        if rnn:
+            states = [(ho[i], c0[i].to(dtype)) if rnn == 'CLSTM' else ho[i] for i in range(cells)]
+        outs = []
+        for t in range(T):
+            o, states = O.refine_net_step(osd, cfg, scr[:, t].to(dtype) if screen else None,
+                                          hmo[:, t], states or None)
+            outs.append(o)
+        want = torch.stack(outs, 1)
+        loss = (want * wo.to(dtype)).sum()
+        fin = None
+        if rnn:
+            fin = [torch.stack([s[0] if isinstance(s, tuple) else s for s in states], 0)]
+            if rnn == 'CLSTM':
+                fin.append(torch.stack([s[1] for s in states], 0))
+            if wh is not None:
+                loss = loss + (fin[0] * wh.to(dtype)).sum()
+        loss.backward()
+        grads = {k: v.grad for k, v in osd.items()}
+        return want.detach(), fin, hmo.grad, (ho.grad if rnn else None), grads
 
-    osd = {'refine_net.' + k: v.double().requires_grad_(True) for k, v in sd.items()}
-    hm64 = hm.double().requires_grad_(True)
-    h64 = h0.double().requires_grad_(True) if rnn else None
-    states = None
-    if rnn:
-        states = [(h64[i], c0[i].double()) if rnn == 'CLSTM' else h64[i] for i in range(cells)]
-    outs = []
-    for t in range(T):
-        o, states = O.refine_net_step(osd, cfg, scr[:, t].double() if screen else None,
-                                      hm64[:, t], states or None)
-        outs.append(o)
-    want = torch.stack(outs, 1)
-    loss = (want * wo.double()).sum()
-    if wh is not None:
-        fin = torch.stack(list(states), 0)
-        loss = loss + (fin * wh.double()).sum()
-    loss.backward()
+    want, fin, dhm64, dh64, g64 = oracle(torch.float64)
+    _, _, dhm32, dh32, g32 = oracle(torch.float32)
 
-    hmc = hm.cuda().requires_grad_(True)
-    hc = h0.cuda().requires_grad_(True) if rnn else None
+    def l2(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        return float((a - b).norm() / (b.norm() + 1e-30))
+
+    hmc = hm.detach().cuda().requires_grad_(True)
+    hc = h0.detach().cuda().requires_grad_(True) if rnn else None
     got, hT, cT = net.sequence(scr.cuda() if screen else None, hmc, hc,
                                c0.cuda() if c0 is not None else None)
     assert G.rel(got, want) < 1e-4
     closs = (got * wo.cuda()).sum()
+    if rnn:
+        assert G.rel(hT, fin[0]) < 1e-4
+        if rnn == 'CLSTM':
+            assert G.rel(cT, fin[1]) < 1e-4
     if wh is not None:
-        assert G.rel(hT, fin) < 1e-4
         closs = closs + (hT * wh.cuda()).sum()
-    elif rnn == 'CLSTM':
-        fin_h = torch.stack([s[0] for s in states], 0)
-        fin_c = torch.stack([s[1] for s in states], 0)
-        assert G.rel(hT, fin_h) < 1e-4 and G.rel(cT, fin_c) < 1e-4
     closs.backward()
-    ref = hm64.grad
-    l2 = float((hmc.grad.double().cpu() - ref).norm() / (ref.norm() + 1e-30))
-    assert l2 < 1e-3, l2
+
+    # Gradients: RefineNet at random weights is ill-conditioned (InstanceNorm over nearly
+    # constant maps), so the yardstick is the fp32 noise of the reference arithmetic itself:
+    # our fp32 result must be as close to the fp64 truth as the oracle's own fp32 run,
+    # within a factor 3 (+1e-4 absolute floor on the relative L2 error).
+    def bar(ref32, ref64):
+        return 3.0 * l2(ref32, ref64) + 1e-4
+
+    assert l2(hmc.grad, dhm64) < bar(dhm32, dhm64), (l2(hmc.grad, dhm64), l2(dhm32, dhm64))
     if wh is not None:
-        ref = h64.grad
-        l2 = float((hc.grad.double().cpu() - ref).norm() / (ref.norm() + 1e-30))
-        assert l2 < 1e-3, l2
-    worst = 0.0
+        assert l2(hc.grad, dh64) < bar(dh32, dh64), (l2(hc.grad, dh64), l2(dh32, dh64))
+    scale = max(float(v.norm()) for v in g64.values() if v is not None)
+    rows = []
     for name, p in net.named_parameters():
-        ref = osd['refine_net.' + name].grad
+        ref = g64['refine_net.' + name]
         if ref is None or float(ref.norm()) == 0.0:
             assert p.grad is None or float(p.grad.abs().max()) < 1e-6, name
             continue
         assert p.grad is not None, name
-        l2 = float((p.grad.double().cpu() - ref).norm() / (ref.norm() + 1e-30))
-        worst = max(worst, l2)
-        # biases that feed an InstanceNorm have an exactly-zero true gradient: noise only
-        if float(ref.norm()) < 1e-9 * float(want.numel()):
+        if float(ref.norm()) < 1e-6 * scale:
+            # a bias feeding an InstanceNorm: the true gradient is zero, both sides are noise
+            assert float(p.grad.norm()) < 1e-3 * scale, name
             continue
-        assert l2 < 5e-3, (name, l2)
-    assert worst < 5e-2
+        rows.append((name, l2(p.grad, ref), l2(g32['refine_net.' + name], ref)))
+    assert len(rows) > 40
+    # the fp32 noise level of this network / input (single tensors can be lucky)
+    noise = float(np.median([e32 for _, _, e32 in rows]))
+    for name, e, e32 in rows:
+        assert e < 3.0 * max(e32, noise) + 1e-4, (name, e, e32, noise)
 
 
 def test_per_step_and_time_batched_paths_agree(cfg):
