@@ -21,6 +21,8 @@ class FlatAdamTrainer(object):
     """Owns flat parameter / gradient / Adam-moment buffers; the model's parameters become
     views into the flat parameter buffer (names, shapes and state_dict keys unchanged)."""
 
+    ALIGN = 64   # floats
+
     def __init__(self, model, lr=None, weight_decay=None, betas=(0.9, 0.999), eps=1e-8,
                  max_norm=None, process_group=None):
         cfg = get_config()
@@ -30,12 +32,19 @@ class FlatAdamTrainer(object):
             raise ValueError('FlatAdamTrainer: the model has no trainable parameter')
         dev = self.params[0].device
         self.sizes = [p.numel() for p in self.params]
-        self.flat = torch.cat([p.detach().reshape(-1).float() for p in self.params]).contiguous()
-        off = 0
-        for p, n in zip(self.params, self.sizes):
-            p.data = self.flat[off:off + n].view(p.shape)
-            off += n
+        # every parameter starts on a 256-byte boundary (the kernels read weights / norm gains
+        # with 16-byte vector loads); the padding stays zero in all four buffers
+        self.offsets, off = [], 0
+        for n in self.sizes:
+            self.offsets.append(off)
+            off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        for p, o, n in zip(self.params, self.offsets, self.sizes):
+            self.flat[o:o + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat[o:o + n].view(p.shape)
         self.grad = torch.zeros_like(self.flat)
+        self.grad_views = [self.grad[o:o + n].view(p.shape)
+                           for p, o, n in zip(self.params, self.offsets, self.sizes)]
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.lr = float(cfg.learning_rate if lr is None else lr)
@@ -54,13 +63,14 @@ class FlatAdamTrainer(object):
         self.last_grad_norm = None
 
     def gather_grads(self):
-        """Pack p.grad of every trainable parameter into the flat gradient buffer (one
-        concatenation kernel); parameters that did not take part in the graph count as zero."""
-        views = []
-        for p in self.params:
-            views.append(p.grad.reshape(-1) if p.grad is not None
-                         else torch.zeros(p.numel(), dtype=torch.float32, device=p.device))
-        torch.cat(views, out=self.grad)
+        """Pack p.grad of every trainable parameter into the flat gradient buffer (one fused
+        multi-tensor copy); parameters that did not take part in the graph count as zero."""
+        have = [(v, p.grad) for v, p in zip(self.grad_views, self.params) if p.grad is not None]
+        missing = [v for v, p in zip(self.grad_views, self.params) if p.grad is None]
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        for v in missing:
+            v.zero_()
         for p in self.params:
             p.grad = None
 

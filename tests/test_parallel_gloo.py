@@ -50,7 +50,8 @@ def _worker(rank, world, port, ret):
     tr = FlatAdamTrainer(model, lr=1e-2, weight_decay=1e-3, max_norm=0.05)
     for _ in range(3):
         tr.step(model(_data(rank)), update=host_update)
-    ret[rank] = (tr.flat.clone(), float(tr.last_grad_norm))
+    packed = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    ret[rank] = (packed.clone(), float(tr.last_grad_norm))
     dist.destroy_process_group()
 
 
@@ -95,4 +96,5 @@ def test_parameters_are_views_of_the_flat_buffer_and_keep_their_names():
     assert list(model.state_dict().keys()) == keys
     tr.flat.zero_()
     assert all(float(p.abs().max()) == 0.0 for p in model.parameters())
-    assert tr.flat.numel() == sum(p.numel() for p in model.parameters())
+    assert tr.flat.numel() >= sum(p.numel() for p in model.parameters())
+    assert all((p.data_ptr() - tr.flat.data_ptr()) % 256 == 0 for p in model.parameters())
