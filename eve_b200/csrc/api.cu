@@ -70,11 +70,11 @@ static int check_conv(const eve_conv_params* p, ConvGeom& g) {
   return EVE_OK;
 }
 
-static size_t conv_ws_floats(const ConvGeom& g) {
-  size_t wmat = align_up((size_t)g.Cout * g.K(), 64);
+static size_t conv_ws_bytes(const ConvGeom& g) {
   size_t wg = conv_wgrad_scratch_floats(g);
   size_t cs = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
-  return wmat + (wg > cs ? wg : cs) + 64;
+  return conv_scratch_bytes((size_t)g.in_elems(), (size_t)g.out_elems(), (size_t)g.Cout * g.K(),
+                            wg > cs ? wg : cs);
 }
 
 }  // namespace eve
@@ -125,8 +125,11 @@ extern "C" const char* eve_last_error(void) { return g_error; }
 extern "C" size_t eve_conv2d_workspace_bytes(const eve_conv_params* p) {
   ConvGeom g;
   if (check_conv(p, g) != EVE_OK) return 0;
-  return conv_ws_floats(g) * sizeof(float);
+  return conv_ws_bytes(g);
 }
+
+extern "C" void eve_set_conv_mode(int mode) { set_conv_mode(mode); }
+extern "C" int eve_get_conv_mode(void) { return conv_mode(); }
 
 extern "C" int eve_conv2d_fwd(const eve_conv_params* p, const float* x, const float* w,
                               const float* bias, float* y, void* workspace,
@@ -135,12 +138,10 @@ extern "C" int eve_conv2d_fwd(const eve_conv_params* p, const float* x, const fl
   EVE_TRY(check_conv(p, g));
   if (g.N == 0) return EVE_OK;
   EVE_REQUIRE(x && w && y && workspace, EVE_ERR_NULL, "conv2d_fwd: NULL pointer");
-  EVE_REQUIRE(workspace_bytes >= conv_ws_floats(g) * sizeof(float), EVE_ERR_WORKSPACE,
+  EVE_REQUIRE(workspace_bytes >= conv_ws_bytes(g), EVE_ERR_WORKSPACE,
               "conv2d_fwd: workspace too small");
-  cudaStream_t s = as_stream(stream);
-  float* wf = (float*)workspace;
-  EVE_TRY(conv_prep_weights(g, w, wf, nullptr, s));
-  return conv_fwd_simt(g, x, wf, bias, nullptr, y, g.Cout, s);
+  ConvScratch sc{(char*)workspace, workspace_bytes};
+  return conv_fwd(g, x, w, bias, nullptr, y, sc, as_stream(stream));
 }
 
 extern "C" int eve_conv2d_dgrad(const eve_conv_params* p, const float* dy, const float* w,
@@ -150,12 +151,10 @@ extern "C" int eve_conv2d_dgrad(const eve_conv_params* p, const float* dy, const
   EVE_TRY(check_conv(p, g));
   if (g.N == 0) return EVE_OK;
   EVE_REQUIRE(dy && w && dx && workspace, EVE_ERR_NULL, "conv2d_dgrad: NULL pointer");
-  EVE_REQUIRE(workspace_bytes >= conv_ws_floats(g) * sizeof(float), EVE_ERR_WORKSPACE,
+  EVE_REQUIRE(workspace_bytes >= conv_ws_bytes(g), EVE_ERR_WORKSPACE,
               "conv2d_dgrad: workspace too small");
-  cudaStream_t s = as_stream(stream);
-  float* wd = (float*)workspace;
-  EVE_TRY(conv_prep_weights(g, w, nullptr, wd, s));
-  return conv_dgrad_simt(g, dy, g.Cout, wd, nullptr, dx, s);
+  ConvScratch sc{(char*)workspace, workspace_bytes};
+  return conv_dgrad(g, dy, w, nullptr, dx, sc, as_stream(stream));
 }
 
 extern "C" int eve_conv2d_wgrad(const eve_conv_params* p, const float* x, const float* dy,
@@ -165,19 +164,16 @@ extern "C" int eve_conv2d_wgrad(const eve_conv_params* p, const float* x, const 
   EVE_TRY(check_conv(p, g));
   EVE_REQUIRE(dw && workspace && (g.N == 0 || (x && dy)), EVE_ERR_NULL,
               "conv2d_wgrad: NULL pointer");
-  EVE_REQUIRE(workspace_bytes >= conv_ws_floats(g) * sizeof(float), EVE_ERR_WORKSPACE,
+  EVE_REQUIRE(workspace_bytes >= conv_ws_bytes(g), EVE_ERR_WORKSPACE,
               "conv2d_wgrad: workspace too small");
   cudaStream_t s = as_stream(stream);
-  float* scratch = (float*)workspace;
   if (g.N == 0) {
     EVE_TRY(fill_zero(dw, (long long)g.Cout * g.K(), s));
     if (dbias) EVE_TRY(fill_zero(dbias, g.Cout, s));
     return EVE_OK;
   }
-  EVE_TRY(conv_wgrad_simt(g, x, dy, g.Cout, dw, scratch, false, s));
-  if (dbias)
-    EVE_TRY(colsum(dy, (long long)g.N * g.OH * g.OW, g.Cout, g.Cout, dbias, scratch, false, s));
-  return EVE_OK;
+  ConvScratch sc{(char*)workspace, workspace_bytes};
+  return conv_wgrad(g, x, dy, dw, dbias, false, sc, s);
 }
 
 extern "C" int eve_instnorm_act_fwd(const float* x, int n, int hw, int c, const float* gamma,

@@ -118,6 +118,38 @@ int colsum(const float* dy, long long rows, int C, int ld, float* db, float* scr
            bool accumulate, cudaStream_t s);
 size_t colsum_scratch_floats(long long rows, int C);
 
+// --------------------------------------------------------------------- conv (tcgen05) --
+bool conv_tc_supported(const ConvGeom& g);
+int split_bf16(const float* x, long long n, void* hi, void* lo, cudaStream_t s);
+int conv_tc_prep_weights(const ConvGeom& g, const float* w_oihw, bool dgrad, void* hi, void* lo,
+                         cudaStream_t s);
+int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* w_hi,
+                const void* w_lo, const float* bias, const float* addend, float* y, int npass,
+                cudaStream_t s);
+
+// ------------------------------------------------------------------- conv (dispatch) --
+// The entry points the networks call.  They take the fp32 NHWC activations and the OIHW fp32
+// master weights, derive whatever operand layouts the chosen kernel needs inside `scratch`
+// (a slice of the caller's workspace) and launch either the tcgen05 kernel (conv_tc.cu) or
+// the fp32 CUDA-core kernel (conv_simt.cu).
+//   mode 0: fp32 CUDA cores everywhere (exact)      mode 1: tcgen05, split-bf16 x3 (default)
+//   mode 2: tcgen05, single bf16 pass (fastest, ~1e-2 relative error)
+int conv_mode();
+void set_conv_mode(int mode);
+struct ConvScratch {
+  char* base;
+  size_t bytes;
+};
+// bytes needed for any convolution with at most these many input / output / weight elements
+size_t conv_scratch_bytes(size_t max_in_elems, size_t max_out_elems, size_t max_w_elems,
+                          size_t wgrad_partial_floats);
+int conv_fwd(const ConvGeom& g, const float* x, const float* w_oihw, const float* bias,
+             const float* addend, float* y, const ConvScratch& sc, cudaStream_t s);
+int conv_dgrad(const ConvGeom& g, const float* dy, const float* w_oihw, const float* addend,
+               float* dx, const ConvScratch& sc, cudaStream_t s);
+int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw_oihw, float* dbias,
+               bool accumulate, const ConvScratch& sc, cudaStream_t s);
+
 // ------------------------------------------------------------------------------ norms --
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
 

@@ -1,0 +1,114 @@
+// Convolution dispatch: picks the tcgen05 tensor-core kernel (conv_tc.cu) when the geometry
+// is dense enough for it and the fp32 CUDA-core implicit GEMM (conv_simt.cu) otherwise, and
+// derives the operand layouts each of them needs inside the caller's scratch slice.
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace eve {
+
+namespace {
+int g_mode = -1;
+
+struct Carve {
+  char* p;
+  char* end;
+  template <typename T>
+  T* get(size_t n) {
+    size_t bytes = align_up(n * sizeof(T), 1024);
+    char* r = p;
+    p += bytes;
+    return p <= end ? (T*)r : nullptr;
+  }
+};
+
+// dgrad of a stride-1 "same" convolution is itself a stride-1 "same" convolution of dy with
+// the flipped, channel-transposed filter.
+ConvGeom dgrad_as_fwd(const ConvGeom& g) {
+  return make_conv(g.N, g.OH, g.OW, g.Cout, g.Cin, g.KH, 1, g.KH - 1 - g.pad);
+}
+}  // namespace
+
+int conv_mode() {
+  if (g_mode < 0) {
+    const char* e = getenv("EVE_B200_CONV_MODE");
+    g_mode = e ? atoi(e) : 1;
+    if (g_mode < 0 || g_mode > 2) g_mode = 1;
+  }
+  return g_mode;
+}
+void set_conv_mode(int mode) { g_mode = (mode < 0 || mode > 2) ? 1 : mode; }
+
+size_t conv_scratch_bytes(size_t max_in, size_t max_out, size_t max_w, size_t wgrad_floats) {
+  size_t m = max_in > max_out ? max_in : max_out;
+  size_t weights = 2 * align_up(max_w * sizeof(float), 1024);          // fp32 layout or hi+lo
+  size_t planes = 2 * align_up(m * 2, 1024);                           // hi + lo of one operand
+  size_t partial = align_up(wgrad_floats * sizeof(float), 1024);
+  return weights + 2 * planes + partial + 4096;
+}
+
+int conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* bias,
+             const float* addend, float* y, const ConvScratch& sc, cudaStream_t s) {
+  Carve c{sc.base, sc.base + sc.bytes};
+  const size_t wel = (size_t)g.Cout * g.K();
+  const int mode = conv_mode();
+  if (mode != 0 && conv_tc_supported(g)) {
+    const int npass = mode == 1 ? 3 : 1;
+    uint16_t* w_hi = c.get<uint16_t>(wel);
+    uint16_t* w_lo = c.get<uint16_t>(wel);
+    uint16_t* x_hi = c.get<uint16_t>((size_t)g.in_elems());
+    uint16_t* x_lo = c.get<uint16_t>((size_t)g.in_elems());
+    EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_fwd: scratch too small");
+    EVE_TRY(conv_tc_prep_weights(g, w, false, w_hi, npass == 3 ? w_lo : nullptr, s));
+    EVE_TRY(split_bf16(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, s));
+    ProfScope prof(PROF_CONV_FWD, 2.0 * g.out_elems() * (double)g.K(),
+                   4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
+    return conv_tc_run(g, x_hi, x_lo, w_hi, w_lo, bias, addend, y, npass, s);
+  }
+  float* wf = c.get<float>(wel);
+  EVE_REQUIRE(wf, EVE_ERR_WORKSPACE, "conv_fwd: scratch too small");
+  EVE_TRY(conv_prep_weights(g, w, wf, nullptr, s));
+  return conv_fwd_simt(g, x, wf, bias, addend, y, g.Cout, s);
+}
+
+int conv_dgrad(const ConvGeom& g, const float* dy, const float* w, const float* addend, float* dx,
+               const ConvScratch& sc, cudaStream_t s) {
+  Carve c{sc.base, sc.base + sc.bytes};
+  const size_t wel = (size_t)g.Cout * g.K();
+  const int mode = conv_mode();
+  if (mode != 0 && g.stride == 1) {
+    ConvGeom f = dgrad_as_fwd(g);
+    if (conv_tc_supported(f) && f.OH == g.H && f.OW == g.W) {
+      const int npass = mode == 1 ? 3 : 1;
+      uint16_t* w_hi = c.get<uint16_t>(wel);
+      uint16_t* w_lo = c.get<uint16_t>(wel);
+      uint16_t* d_hi = c.get<uint16_t>((size_t)g.out_elems());
+      uint16_t* d_lo = c.get<uint16_t>((size_t)g.out_elems());
+      EVE_REQUIRE(d_lo, EVE_ERR_WORKSPACE, "conv_dgrad: scratch too small");
+      EVE_TRY(conv_tc_prep_weights(g, w, true, w_hi, npass == 3 ? w_lo : nullptr, s));
+      EVE_TRY(split_bf16(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, s));
+      ProfScope prof(PROF_CONV_DGRAD, 2.0 * g.out_elems() * (double)g.K(),
+                     4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
+      return conv_tc_run(f, d_hi, d_lo, w_hi, w_lo, nullptr, addend, dx, npass, s);
+    }
+  }
+  float* wd = c.get<float>(wel);
+  EVE_REQUIRE(wd, EVE_ERR_WORKSPACE, "conv_dgrad: scratch too small");
+  EVE_TRY(conv_prep_weights(g, w, nullptr, wd, s));
+  return conv_dgrad_simt(g, dy, g.Cout, wd, addend, dx, s);
+}
+
+int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, float* dbias,
+               bool accumulate, const ConvScratch& sc, cudaStream_t s) {
+  Carve c{sc.base, sc.base + sc.bytes};
+  size_t need = conv_wgrad_scratch_floats(g);
+  size_t cs = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
+  float* part = c.get<float>(need > cs ? need : cs);
+  EVE_REQUIRE(part, EVE_ERR_WORKSPACE, "conv_wgrad: scratch too small");
+  if (dw) EVE_TRY(conv_wgrad_simt(g, x, dy, g.Cout, dw, part, accumulate, s));
+  if (dbias)
+    EVE_TRY(colsum(dy, (long long)g.N * g.OH * g.OW, g.Cout, g.Cout, dbias, part, accumulate, s));
+  return EVE_OK;
+}
+
+}  // namespace eve

@@ -1,0 +1,525 @@
+// tcgen05 implicit-GEMM convolution for sm_100a: TMA-staged NHWC tiles -> shared memory
+// (128B swizzle) -> tcgen05.mma (accumulators in TMEM) -> tcgen05.ld epilogue.
+//
+// Replaces the cuDNN/ATen convolution calls behind every nn.Conv2d on the hot path whose
+// GEMM is dense enough for the tensor cores (torchvision ResNet layers via eye_net.py:48-50,
+// RefineNet blocks refine_net.py:45-62, ConvRNN gates common.py:338-398).
+//
+// GEMM view (stride 1, "same" padding):  D[m=(n,h,w)][co] = sum_{tap=(r,q)} sum_ci
+//        X[n, h+r-pad, w+q-pad, ci] * Wk[co][tap*Cin+ci]
+//  * A operand: for one filter tap the 128 rows of a tile are a (bw x bh x bn) box of
+//    pixels shifted by the tap offset, 64 channels deep -- one 4-D TMA box load from the NHWC
+//    tensor; out-of-bounds pixels are zero-filled by TMA, which IS the zero padding.
+//  * B operand: weights pre-arranged K-major [Cout][taps*Cin], one 2-D TMA box per K block.
+//  * Precision: fp32 activations/weights are split into bf16 hi + lo planes; with npass = 3
+//    the kernel issues hi*hi + hi*lo + lo*hi per K step (products exact to ~2^-16, fp32
+//    accumulation in TMEM), npass = 1 is plain bf16.
+//  * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 =
+//    epilogue (TMEM -> registers -> +bias/+addend -> fp32 NHWC global).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace eve {
+namespace {
+
+// ------------------------------------------------------------------ PTX wrappers --
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmap_prefetch(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; issued by one thread on behalf of the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 B, 8-row groups
+// 1024 B apart).  Advancing by 16 bf16 along K = +32 B on the start address.
+__device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+struct TcParams {
+  int N, H, W, Cin, Cout, KH, KW, pad;
+  int bw, bh, bn;           // pixel box of one M tile (bw == W)
+  int tiles_h;              // ceil(H / bh)
+  int kchunks;              // Cin / 64
+  const float* bias;        // [Cout] or null
+  const float* addend;      // [N,H,W,Cout] or null
+  float* out;               // [N,H,W,Cout]
+};
+
+constexpr int kTileM = 128;
+constexpr int kTileK = 64;  // bf16 elements = one 128-byte swizzle row
+constexpr int kThreads = 192;
+
+template <int BN, int NPASS>
+struct TcCfg {
+  static constexpr int kABytes = kTileM * kTileK * 2;
+  static constexpr int kBBytes = BN * kTileK * 2;
+  static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
+  static constexpr int kStageBytes = (kABytes + kBBytes) * kPlanes;
+  static constexpr int kBudget = 224 * 1024;
+  static constexpr int kStagesRaw = (kBudget - 2048) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const TcParams p) {
+  using Cfg = TcCfg<BN, NPASS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* tmem_full = empty + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int th = tile % p.tiles_h;
+  const int tn = tile / p.tiles_h;
+  const int h0 = th * p.bh;
+  const int n0 = tn * p.bn;
+  const int co0 = blockIdx.y * BN;
+  const int taps = p.KH * p.KW;
+  const int iters = taps * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tmap_prefetch(&tmA_hi);
+    tmap_prefetch(&tmB_hi);
+    if (NPASS == 3) {
+      tmap_prefetch(&tmA_lo);
+      tmap_prefetch(&tmB_lo);
+    }
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const uint32_t rows = p.bw * p.bh * p.bn;
+      const uint32_t tx = (rows * 128u + (uint32_t)Cfg::kBBytes) * Cfg::kPlanes;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + s * Cfg::kStageBytes;
+        const int tap = it / p.kchunks;
+        const int kc = it - tap * p.kchunks;
+        const int r = tap / p.KW, q = tap - r * p.KW;
+        mbar_expect_tx(&full[s], tx);
+        tma_load_4d(st, &tmA_hi, &full[s], kc * kTileK, q - p.pad, h0 + r - p.pad, n0);
+        tma_load_2d(st + Cfg::kABytes * Cfg::kPlanes, &tmB_hi, &full[s],
+                    tap * p.Cin + kc * kTileK, co0);
+        if (NPASS == 3) {
+          tma_load_4d(st + Cfg::kABytes, &tmA_lo, &full[s], kc * kTileK, q - p.pad,
+                      h0 + r - p.pad, n0);
+          tma_load_2d(st + Cfg::kABytes * 2 + Cfg::kBBytes, &tmB_lo, &full[s],
+                      tap * p.Cin + kc * kTileK, co0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = BN
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(kTileM >> 4) << 24);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % Cfg::kStages;
+      const uint32_t ph = (it / Cfg::kStages) & 1;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint32_t b_hi = a_hi + Cfg::kABytes * Cfg::kPlanes;
+        const uint64_t da_hi = kmajor_sw128_desc(a_hi);
+        const uint64_t db_hi = kmajor_sw128_desc(b_hi);
+        const uint64_t da_lo = kmajor_sw128_desc(a_hi + Cfg::kABytes);
+        const uint64_t db_lo = kmajor_sw128_desc(b_hi + Cfg::kBBytes);
+#pragma unroll
+        for (int k = 0; k < kTileK / 16; ++k) {
+          const uint64_t adv = (uint64_t)(k * 2);  // 32 bytes >> 4
+          if (NPASS == 3) {
+            // small terms first so they are not absorbed by a large partial sum
+            umma_bf16(tmem_base, da_lo + adv, db_hi + adv, idesc, (it | k) != 0);
+            umma_bf16(tmem_base, da_hi + adv, db_lo + adv, idesc, 1);
+            umma_bf16(tmem_base, da_hi + adv, db_hi + adv, idesc, 1);
+          } else {
+            umma_bf16(tmem_base, da_hi + adv, db_hi + adv, idesc, (it | k) != 0);
+          }
+        }
+        umma_commit(&empty[s]);
+        if (it == iters - 1) umma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue =====================
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+    const int m = quad * 32 + lane;         // tile row = TMEM lane
+    const int iw = m % p.bw;
+    const int ih = (m / p.bw) % p.bh;
+    const int in = m / (p.bw * p.bh);
+    const int h = h0 + ih, n = n0 + in;
+    const bool valid = in < p.bn && h < p.H && n < p.N;
+    const size_t row = ((size_t)(n * p.H + h) * p.W + iw) * p.Cout + co0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      if (valid) {
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + co0 + c0 + j);
+        }
+        if (p.addend) {
+          const float4* a4 = reinterpret_cast<const float4*>(p.addend + row + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 a = __ldg(a4 + j);
+            v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+          }
+        }
+        float4* o4 = reinterpret_cast<float4*>(p.out + row + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------ operand preparation --
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ x, long long n4, __nv_bfloat16* __restrict__ hi,
+                  __nv_bfloat16* __restrict__ lo) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+  float f[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2bfloat16_rn(f[j]);
+    l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+  }
+  reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+  if (lo) reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+}
+
+// OIHW fp32 -> K-major bf16 hi/lo.  flip == 0: forward  Wk[co][(r*KW+q)*Cin + ci]
+//                                  flip == 1: dgrad    Wk[ci][((KH-1-r)*KW + (KW-1-q))*Cout + co]
+__global__ void __launch_bounds__(256)
+prep_weights_tc_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int flip,
+                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  size_t total = (size_t)Cout * Cin * KH * KW;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int q = (int)(i % KW);
+  size_t t = i / KW;
+  int r = (int)(t % KH);
+  t /= KH;
+  int ci = (int)(t % Cin);
+  int co = (int)(t / Cin);
+  float v = w[i];
+  size_t o;
+  if (!flip)
+    o = (size_t)co * ((size_t)KH * KW * Cin) + (size_t)(r * KW + q) * Cin + ci;
+  else
+    o = (size_t)ci * ((size_t)KH * KW * Cout) + (size_t)((KH - 1 - r) * KW + (KW - 1 - q)) * Cout + co;
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[o] = h;
+  if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// ------------------------------------------------------------------ host helpers --
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh,
+                  int bn) {
+  EncodeTiledFn enc = encode_fn();
+  EVE_REQUIRE(enc, EVE_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled is not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kTileK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EVE_REQUIRE(r == CUDA_SUCCESS, EVE_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled(A) failed: %d",
+              (int)r);
+  return EVE_OK;
+}
+
+int make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  EVE_REQUIRE(enc, EVE_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled is not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kTileK, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EVE_REQUIRE(r == CUDA_SUCCESS, EVE_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled(B) failed: %d",
+              (int)r);
+  return EVE_OK;
+}
+
+// pixel box (bw, bh, bn) with bw == W, bw*bh*bn <= 128, maximising useful rows per MMA
+void pick_box(int N, int H, int W, int& bw, int& bh, int& bn) {
+  bw = W;
+  double best = -1.0;
+  bh = 1;
+  bn = 1;
+  for (int h = 1; h <= H && W * h <= kTileM; ++h) {
+    int nmax = kTileM / (W * h);
+    for (int n = 1; n <= nmax && n <= (h == H ? N : 1); ++n) {
+      // spanning several images only makes sense when the box covers whole images
+      double eff = ((double)H / (double)(cdiv(H, h) * h)) * ((double)(W * h * n) / kTileM) *
+                   ((double)N / (double)(cdiv(N, n) * n));
+      if (eff > best + 1e-9) {
+        best = eff;
+        bh = h;
+        bn = n;
+      }
+    }
+  }
+}
+
+template <int BN, int NPASS>
+int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+              const CUtensorMap& b_lo, const TcParams& p, int grid_x, int grid_y,
+              cudaStream_t s) {
+  using Cfg = TcCfg<BN, NPASS>;
+  static bool configured = false;
+  if (!configured) {
+    EVE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NPASS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  conv_tc_kernel<BN, NPASS><<<dim3(grid_x, grid_y), kThreads, Cfg::kSmemBytes, s>>>(a_hi, a_lo, b_hi,
+                                                                                  b_lo, p);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------- public API --
+bool conv_tc_supported(const ConvGeom& g) {
+  if (g.stride != 1 || g.KH != g.KW) return false;
+  if (g.OH != g.H || g.OW != g.W) return false;        // "same" padding only
+  if (g.Cin % kTileK != 0 || g.Cout % 64 != 0) return false;
+  if (g.W > kTileM || g.W < 1) return false;
+  if (g.KH != 1 && g.KH != 3) return false;
+  if (g.N < 1) return false;
+  return true;
+}
+
+size_t conv_tc_plane_elems(const ConvGeom& g) { return (size_t)g.in_elems(); }
+
+int split_bf16(const float* x, long long n, void* hi, void* lo, cudaStream_t s) {
+  EVE_REQUIRE(n % 4 == 0, EVE_ERR_SHAPE, "split_bf16: element count must be a multiple of 4");
+  long long n4 = n / 4;
+  if (n4 == 0) return EVE_OK;
+  split_bf16_kernel<<<cdiv(n4, 256), 256, 0, s>>>(x, n4, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+int conv_tc_prep_weights(const ConvGeom& g, const float* w_oihw, bool dgrad, void* hi, void* lo,
+                         cudaStream_t s) {
+  size_t total = (size_t)g.Cout * g.Cin * g.KH * g.KW;
+  prep_weights_tc_kernel<<<cdiv(total, 256), 256, 0, s>>>(w_oihw, g.Cout, g.Cin, g.KH, g.KW,
+                                                          dgrad ? 1 : 0, (__nv_bfloat16*)hi,
+                                                          (__nv_bfloat16*)lo);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+// y[N,H,W,Cout] = conv(x) (+bias) (+addend).  x_hi/x_lo: bf16 NHWC planes of the input;
+// w_hi/w_lo: K-major weights [Cout][KH*KW*Cin].  npass: 3 (split bf16) or 1 (plain bf16).
+int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* w_hi,
+                const void* w_lo, const float* bias, const float* addend, float* y, int npass,
+                cudaStream_t s) {
+  EVE_REQUIRE(conv_tc_supported(g), EVE_ERR_SHAPE, "conv_tc: unsupported geometry");
+  EVE_REQUIRE(npass == 1 || npass == 3, EVE_ERR_CONFIG, "conv_tc: npass must be 1 or 3");
+  TcParams p;
+  p.N = g.N; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.Cout = g.Cout;
+  p.KH = g.KH; p.KW = g.KW; p.pad = g.pad;
+  pick_box(g.N, g.H, g.W, p.bw, p.bh, p.bn);
+  p.tiles_h = cdiv(g.H, p.bh);
+  p.kchunks = g.Cin / kTileK;
+  p.bias = bias; p.addend = addend; p.out = y;
+  const int tiles_n = cdiv(g.N, p.bn);
+  const int BN = (g.Cout % 128 == 0) ? 128 : 64;
+  const int K = g.KH * g.KW * g.Cin;
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  EVE_TRY(make_map_nhwc(&a_hi, x_hi, g.N, g.H, g.W, g.Cin, p.bw, p.bh, p.bn));
+  EVE_TRY(make_map_2d(&b_hi, w_hi, g.Cout, K, BN));
+  if (npass == 3) {
+    EVE_TRY(make_map_nhwc(&a_lo, x_lo, g.N, g.H, g.W, g.Cin, p.bw, p.bh, p.bn));
+    EVE_TRY(make_map_2d(&b_lo, w_lo, g.Cout, K, BN));
+  } else {
+    a_lo = a_hi;
+    b_lo = b_hi;
+  }
+  const int gx = p.tiles_h * tiles_n, gy = g.Cout / BN;
+  if (BN == 128)
+    return npass == 3 ? launch_tc<128, 3>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s)
+                      : launch_tc<128, 1>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+  return npass == 3 ? launch_tc<64, 3>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s)
+                    : launch_tc<64, 1>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+}
+
+}  // namespace eve

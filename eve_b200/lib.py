@@ -57,6 +57,8 @@ SIGNATURES = {
     'eve_profile_enable': (None, [_I]),
     'eve_profile_reset': (None, []),
     'eve_profile_read': (_I, [_I, _P, _P, _P, _P]),
+    'eve_set_conv_mode': (None, [_I]),
+    'eve_get_conv_mode': (_I, []),
     'eve_conv2d_workspace_bytes': (_Z, [_P]),
     'eve_conv2d_fwd': (_I, [_P, _P, _P, _P, _P, _P, _Z, _P]),
     'eve_conv2d_dgrad': (_I, [_P, _P, _P, _P, _P, _Z, _P]),

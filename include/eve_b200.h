@@ -57,6 +57,14 @@ int eve_profile_read(int kind, double* ms, double* flops, double* bytes, long lo
 typedef struct {
   int n, h, w, cin, cout, ksize, stride, pad;
 } eve_conv_params;
+/* Kernel selection for every convolution in the library (process-wide):
+ *   0 = fp32 CUDA-core implicit GEMM everywhere (exact fp32 products)
+ *   1 = tcgen05 tensor cores with split-bf16 operands (hi*hi + hi*lo + lo*hi, fp32 accumulate in
+ *       TMEM; products exact to ~2^-16) wherever the geometry allows -- the default
+ *   2 = tcgen05 with a single bf16 pass (fastest; ~1e-2 relative error, outside the 1e-3 bar)
+ * The default can also be set with the environment variable EVE_B200_CONV_MODE. */
+void eve_set_conv_mode(int mode);
+int eve_get_conv_mode(void);
 size_t eve_conv2d_workspace_bytes(const eve_conv_params* p);
 int eve_conv2d_fwd(const eve_conv_params* p, const float* x, const float* w, const float* bias,
                    float* y, void* workspace, size_t workspace_bytes, eve_stream_t stream);

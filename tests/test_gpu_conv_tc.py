@@ -1,0 +1,70 @@
+"""tcgen05 implicit-GEMM convolution (conv_tc.cu) against fp64 arithmetic.
+
+mode 1 (split bf16, three MMAs per K step) must reproduce fp32-level results (<= 3e-5
+relative, the bar the parity tests of the whole network rest on); mode 2 (single bf16 pass)
+is reported against its expected ~1e-2 error; mode 0 is the fp32 CUDA-core kernel."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from eve_b200 import lib as L            # noqa: E402
+from tests import gpu_util as G          # noqa: E402
+
+# (n, cin, h, w, cout, k) -- stride 1, "same" padding: the geometries the tensor-core path takes
+TC_CASES = [
+    (3, 64, 32, 32, 64, 3),      # EyeNet layer1 (box 32x4x1)
+    (2, 128, 16, 16, 128, 3),    # layer2 (box 16x8x1)
+    (4, 256, 8, 8, 256, 3),      # layer3 (box 8x8x2, two images per tile)
+    (9, 512, 4, 4, 512, 3),      # layer4 (box 4x4x8, ragged last tile)
+    (2, 64, 36, 64, 64, 3),      # RefineNet level 1 (box 64x2x1)
+    (2, 128, 18, 32, 128, 3),    # level 2 (18 rows: partial last tile)
+    (2, 256, 9, 16, 256, 3),     # level 3
+    (5, 128, 5, 8, 128, 3),      # ConvGRU gates (box 8x5x3 = 120 rows)
+    (2, 64, 72, 128, 64, 1),     # 1x1
+    (2, 512, 9, 16, 128, 3),     # decoder 512 -> 128
+    (1, 64, 72, 128, 64, 3),     # full-resolution map, one image row per tile
+]
+
+
+@pytest.fixture()
+def conv_mode():
+    lib = L.load()
+    prev = lib.eve_get_conv_mode()
+    yield lib.eve_set_conv_mode
+    lib.eve_set_conv_mode(prev)
+
+
+@pytest.mark.parametrize('case', TC_CASES)
+def test_tensor_core_conv_forward_and_dgrad(case, conv_mode):
+    n, cin, h, w, cout, k = case
+    pad = k // 2
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    xd = x.double().requires_grad_(True)
+    y = F.conv2d(xd, wt.double(), b.double(), padding=pad)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy.double())
+    errs = {}
+    for mode in (1, 2, 0):
+        conv_mode(mode)
+        got = G.conv_fwd(x.cuda(), wt.cuda(), b.cuda(), 1, pad)
+        dx = G.conv_dgrad(dy.cuda(), wt.cuda(), (h, w), 1, pad)
+        torch.cuda.synchronize()
+        errs[mode] = (G.rel(got, y), G.rel(dx, xd.grad))
+    assert max(errs[0]) < 2e-5, errs
+    assert max(errs[1]) < 3e-5, errs            # split-bf16: fp32-class accuracy
+    assert 1e-4 < max(errs[2]) < 3e-2, errs     # single bf16 pass really is bf16
+
+
+def test_mode_switch_is_visible():
+    lib = L.load()
+    prev = lib.eve_get_conv_mode()
+    lib.eve_set_conv_mode(2)
+    assert lib.eve_get_conv_mode() == 2
+    lib.eve_set_conv_mode(prev)
