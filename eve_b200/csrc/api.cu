@@ -71,10 +71,8 @@ static int check_conv(const eve_conv_params* p, ConvGeom& g) {
 }
 
 static size_t conv_ws_bytes(const ConvGeom& g) {
-  size_t wg = conv_wgrad_scratch_floats(g);
-  size_t cs = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
   return conv_scratch_bytes((size_t)g.in_elems(), (size_t)g.out_elems(), (size_t)g.Cout * g.K(),
-                            wg > cs ? wg : cs);
+                            conv_partial_floats(g));
 }
 
 }  // namespace eve

@@ -127,6 +127,14 @@ int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const voi
                 const void* w_lo, const float* bias, const float* addend, float* y, int npass,
                 cudaStream_t s);
 
+bool conv_tc_wgrad_supported(const ConvGeom& g);
+size_t conv_tc_wgrad_partial_floats(const ConvGeom& g);
+int conv_tc_wgrad_run(const ConvGeom& g, const void* d_hi, const void* d_lo, const void* x_hi,
+                      const void* x_lo, float* part, int npass, int* splits_out, cudaStream_t s);
+// dw_oihw (+)= sum over splits of part[z][co][(r*KW+q)*Cin+ci]
+int wgrad_reduce(const float* part, int splits, const ConvGeom& g, float* dw_oihw, bool accumulate,
+                 cudaStream_t s);
+
 // ------------------------------------------------------------------- conv (dispatch) --
 // The entry points the networks call.  They take the fp32 NHWC activations and the OIHW fp32
 // master weights, derive whatever operand layouts the chosen kernel needs inside `scratch`
@@ -143,6 +151,8 @@ struct ConvScratch {
 // bytes needed for any convolution with at most these many input / output / weight elements
 size_t conv_scratch_bytes(size_t max_in_elems, size_t max_out_elems, size_t max_w_elems,
                           size_t wgrad_partial_floats);
+// split-K partial / bias-reduction floats the weight gradient of `g` may need (any kernel)
+size_t conv_partial_floats(const ConvGeom& g);
 int conv_fwd(const ConvGeom& g, const float* x, const float* w_oihw, const float* bias,
              const float* addend, float* y, const ConvScratch& sc, cudaStream_t s);
 int conv_dgrad(const ConvGeom& g, const float* dy, const float* w_oihw, const float* addend,

@@ -1,6 +1,7 @@
 // Convolution dispatch: picks the tcgen05 tensor-core kernel (conv_tc.cu) when the geometry
 // is dense enough for it and the fp32 CUDA-core implicit GEMM (conv_simt.cu) otherwise, and
 // derives the operand layouts each of them needs inside the caller's scratch slice.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -45,6 +46,13 @@ size_t conv_scratch_bytes(size_t max_in, size_t max_out, size_t max_w, size_t wg
   size_t planes = 2 * align_up(m * 2, 1024);                           // hi + lo of one operand
   size_t partial = align_up(wgrad_floats * sizeof(float), 1024);
   return weights + 2 * planes + partial + 4096;
+}
+
+size_t conv_partial_floats(const ConvGeom& g) {
+  size_t a = conv_wgrad_scratch_floats(g);
+  size_t b = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
+  size_t c = conv_tc_wgrad_partial_floats(g);
+  return std::max(a, std::max(b, c));
 }
 
 int conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* bias,
@@ -101,6 +109,30 @@ int conv_dgrad(const ConvGeom& g, const float* dy, const float* w, const float* 
 int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, float* dbias,
                bool accumulate, const ConvScratch& sc, cudaStream_t s) {
   Carve c{sc.base, sc.base + sc.bytes};
+  const int mode = conv_mode();
+  if (dw && mode != 0 && conv_tc_wgrad_supported(g)) {
+    const int npass = mode == 1 ? 3 : 1;
+    size_t pf = conv_tc_wgrad_partial_floats(g);
+    size_t cs = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
+    float* part = c.get<float>(pf > cs ? pf : cs);
+    uint16_t* d_hi = c.get<uint16_t>((size_t)g.out_elems());
+    uint16_t* d_lo = c.get<uint16_t>((size_t)g.out_elems());
+    uint16_t* x_hi = c.get<uint16_t>((size_t)g.in_elems());
+    uint16_t* x_lo = c.get<uint16_t>((size_t)g.in_elems());
+    EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_wgrad: scratch too small");
+    EVE_TRY(split_bf16(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, s));
+    EVE_TRY(split_bf16(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, s));
+    int splits = 0;
+    {
+      ProfScope prof(PROF_CONV_WGRAD, 2.0 * g.out_elems() * (double)g.K(),
+                     4.0 * (g.in_elems() + g.out_elems() + (double)g.Cout * g.K()), s);
+      EVE_TRY(conv_tc_wgrad_run(g, d_hi, d_lo, x_hi, x_lo, part, npass, &splits, s));
+      EVE_TRY(wgrad_reduce(part, splits, g, dw, accumulate, s));
+    }
+    if (dbias)
+      EVE_TRY(colsum(dy, (long long)g.N * g.OH * g.OW, g.Cout, g.Cout, dbias, part, accumulate, s));
+    return EVE_OK;
+  }
   size_t need = conv_wgrad_scratch_floats(g);
   size_t cs = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
   float* part = c.get<float>(need > cs ? need : cs);

@@ -429,6 +429,15 @@ int conv_wgrad_simt(const ConvGeom& g, const float* x, const float* dy, int lddy
   return EVE_OK;
 }
 
+int wgrad_reduce(const float* part, int splits, const ConvGeom& g, float* dw, bool accumulate,
+                 cudaStream_t s) {
+  size_t total = (size_t)g.Cout * g.K();
+  wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, s>>>(part, splits, g.Cout, g.Cin, g.KH * g.KW, dw,
+                                                      accumulate ? 1 : 0);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
 size_t colsum_scratch_floats(long long rows, int C) { return (size_t)colsum_blocks(rows) * C; }
 
 int colsum(const float* dy, long long rows, int C, int ld, float* db, float* scratch,

@@ -320,6 +320,192 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
 }
 
+// =============================================================== weight gradient ====
+// dW[co][(r,q)][ci] = sum over pixels p=(n,h,w) of dy[n, h-r+pad, w-q+pad, co] * x[n,h,w,ci]
+// as a GEMM whose K dimension is the pixel index.  Both operands come straight from the NHWC
+// bf16 planes with the same 4-D TMA boxes as the forward pass, i.e. they sit in shared memory
+// as [pixel rows][64 channels] -- "MN-major" for the tensor core (instruction-descriptor
+// major bits set):
+//   A (M side): the dy box shifted by the filter tap (TMA zero-fill = the padding); a
+//               128-row M block is two 64-channel units, each a (tap, 64-co block) pair
+//   B (N side): the unshifted x box, Nblk = 64..256 input channels
+// Each CTA owns one (M block, N block, pixel split) and accumulates its split in TMEM; a
+// deterministic second kernel sums the splits into the OIHW gradient.
+struct TcWgradParams {
+  int N, H, W, Cin, Cout, KH, KW, pad;
+  int bw, bh, bn, rows;     // pixel box of one K step group (rows = bw*bh*bn, multiple of 16)
+  int tiles_h, tiles_total; // pixel tiles: tiles_h per image column block, total over (n, h)
+  int tiles_per_split;
+  int units;                // taps * (Cout / 64)
+  int cout_blocks;          // Cout / 64
+  int nblk;                 // input channels per CTA (multiple of 64, <= 256)
+  int stages;
+  float* part;              // [splits][Cout][taps*Cin]
+};
+
+constexpr int kWgBlockBytes = 64 * 128;  // one [64 pixel rows][64 channels] bf16 box
+
+__device__ __forceinline__ uint64_t mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
+                     const __grid_constant__ CUtensorMap tmD_lo,
+                     const __grid_constant__ CUtensorMap tmX_hi,
+                     const __grid_constant__ CUtensorMap tmX_lo, const TcWgradParams p) {
+  constexpr int kPlanes = NPASS == 3 ? 2 : 1;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  const int nbB = p.nblk >> 6;
+  const int plane_bytes = (2 + nbB) * kWgBlockBytes;
+  const int stage_bytes = plane_bytes * kPlanes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mb = blockIdx.x;          // M block: units 2*mb, 2*mb+1
+  const int nb = blockIdx.y;          // N block
+  const int sp = blockIdx.z;          // pixel split
+  const int t_begin = sp * p.tiles_per_split;
+  const int t_end = min(p.tiles_total, t_begin + p.tiles_per_split);
+  const int iters = max(t_end - t_begin, 0);
+  const int u0 = 2 * mb;
+  const int u1 = min(2 * mb + 1, p.units - 1);
+  const uint32_t tmem_cols = p.nblk < 32 ? 32 : p.nblk;
+
+  if (warp == 0 && lane == 0) {
+    tmap_prefetch(&tmD_hi);
+    tmap_prefetch(&tmX_hi);
+    if (NPASS == 3) {
+      tmap_prefetch(&tmD_lo);
+      tmap_prefetch(&tmX_lo);
+    }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t tx = (uint32_t)(2 + nbB) * (uint32_t)p.rows * 128u * kPlanes;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + s * stage_bytes;
+        const int tile = t_begin + it;
+        const int th = tile % p.tiles_h;
+        const int tn = tile / p.tiles_h;
+        const int h0 = th * p.bh, n0 = tn * p.bn;
+        mbar_expect_tx(&full[s], tx);
+#pragma unroll
+        for (int pl = 0; pl < kPlanes; ++pl) {
+          uint8_t* base = st + pl * plane_bytes;
+          const CUtensorMap* md = pl == 0 ? &tmD_hi : &tmD_lo;
+          const CUtensorMap* mx = pl == 0 ? &tmX_hi : &tmX_lo;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int u = b == 0 ? u0 : u1;
+            const int tap = u / p.cout_blocks;
+            const int cb = u - tap * p.cout_blocks;
+            const int r = tap / p.KW, q = tap - r * p.KW;
+            tma_load_4d(base + b * kWgBlockBytes, md, &full[s], cb * 64, p.pad - q,
+                        h0 + p.pad - r, n0);
+          }
+          for (int b = 0; b < nbB; ++b)
+            tma_load_4d(base + (2 + b) * kWgBlockBytes, mx, &full[s], nb * p.nblk + b * 64, 0, h0,
+                        n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // D fp32, A/B bf16, both MN-major, M = 128, N = nblk
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(p.nblk >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const int ksteps = p.rows >> 4;
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
+        const uint32_t b_hi = a_hi + 2 * kWgBlockBytes;
+        const uint32_t a_lo = a_hi + plane_bytes;
+        const uint32_t b_lo = b_hi + plane_bytes;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint32_t adv = (uint32_t)k * 2048u;   // 16 pixel rows of 128 bytes
+          const uint64_t dah = mnmajor_sw128_desc(a_hi + adv, kWgBlockBytes);
+          const uint64_t dbh = mnmajor_sw128_desc(b_hi + adv, kWgBlockBytes);
+          if (NPASS == 3) {
+            const uint64_t dal = mnmajor_sw128_desc(a_lo + adv, kWgBlockBytes);
+            const uint64_t dbl = mnmajor_sw128_desc(b_lo + adv, kWgBlockBytes);
+            umma_bf16(tmem_base, dal, dbh, idesc, (it | k) != 0);
+            umma_bf16(tmem_base, dah, dbl, idesc, 1);
+            umma_bf16(tmem_base, dah, dbh, idesc, 1);
+          } else {
+            umma_bf16(tmem_base, dah, dbh, idesc, (it | k) != 0);
+          }
+        }
+        umma_commit(&empty[s]);
+        if (it == iters - 1) umma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int u = 2 * mb + (m >> 6);
+    const bool valid = u < p.units;
+    const int tap = valid ? u / p.cout_blocks : 0;
+    const int cb = valid ? u - tap * p.cout_blocks : 0;
+    const int co = cb * 64 + (m & 63);
+    const size_t KK = (size_t)p.KH * p.KW * p.Cin;
+    float* dst = p.part + ((size_t)sp * p.Cout + co) * KK + (size_t)tap * p.Cin + (size_t)nb * p.nblk;
+    if (iters > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < p.nblk; c0 += 32) {
+      float v[32];
+      if (iters > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (valid) {
+        float4* o4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------ operand preparation --
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float* __restrict__ x, long long n4, __nv_bfloat16* __restrict__ hi,
@@ -520,6 +706,113 @@ int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const voi
                       : launch_tc<128, 1>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
   return npass == 3 ? launch_tc<64, 3>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s)
                     : launch_tc<64, 1>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+}
+
+// pixel box for the wgrad K loop: bw == W, rows = bw*bh*bn <= 64 and a multiple of 16
+static bool pick_wgrad_box(int N, int H, int W, int& bh, int& bn) {
+  double best = -1.0;
+  bh = bn = 0;
+  for (int h = 1; h <= H && W * h <= 64; ++h) {
+    int nmax = 64 / (W * h);
+    for (int n = 1; n <= nmax && n <= (h == H ? N : 1); ++n) {
+      int rows = W * h * n;
+      if (rows % 16 != 0) continue;
+      double eff = ((double)H / (double)(cdiv(H, h) * h)) * ((double)N / (double)(cdiv(N, n) * n)) *
+                   (0.5 + 0.5 * rows / 64.0);   // prefer full 64-row boxes
+      if (eff > best + 1e-9) {
+        best = eff;
+        bh = h;
+        bn = n;
+      }
+    }
+  }
+  return bh > 0;
+}
+
+bool conv_tc_wgrad_supported(const ConvGeom& g) {
+  if (g.stride != 1 || g.KH != g.KW || (g.KH != 1 && g.KH != 3)) return false;
+  if (g.OH != g.H || g.OW != g.W) return false;
+  if (g.Cin % 64 != 0 || g.Cout % 64 != 0) return false;
+  if (g.W > 64 || g.N < 1) return false;
+  int bh, bn;
+  return pick_wgrad_box(g.N, g.H, g.W, bh, bn);
+}
+
+static void wgrad_plan(const ConvGeom& g, TcWgradParams& p, int& mblocks, int& nblocks,
+                       int& splits, int npass) {
+  p.N = g.N; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.Cout = g.Cout;
+  p.KH = g.KH; p.KW = g.KW; p.pad = g.pad;
+  p.bw = g.W;
+  pick_wgrad_box(g.N, g.H, g.W, p.bh, p.bn);
+  p.rows = p.bw * p.bh * p.bn;
+  p.tiles_h = cdiv(g.H, p.bh);
+  p.tiles_total = p.tiles_h * cdiv(g.N, p.bn);
+  p.cout_blocks = g.Cout / 64;
+  p.units = g.KH * g.KW * p.cout_blocks;
+  p.nblk = g.Cin % 256 == 0 ? 256 : (g.Cin % 128 == 0 ? 128 : 64);
+  mblocks = cdiv(p.units, 2);
+  nblocks = g.Cin / p.nblk;
+  const int planes = npass == 3 ? 2 : 1;
+  const int stage_bytes = (2 + p.nblk / 64) * kWgBlockBytes * planes;
+  p.stages = (220 * 1024) / stage_bytes;
+  if (p.stages > 6) p.stages = 6;
+  int want = cdiv(3 * kNumSMs, mblocks * nblocks);
+  int max_splits = cdiv(p.tiles_total, 4);          // at least 4 pixel tiles per CTA
+  splits = want < max_splits ? want : max_splits;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = cdiv(p.tiles_total, splits);
+  splits = cdiv(p.tiles_total, p.tiles_per_split);
+}
+
+size_t conv_tc_wgrad_partial_floats(const ConvGeom& g) {
+  if (!conv_tc_wgrad_supported(g)) return 0;
+  TcWgradParams p;
+  int mb, nb, sp;
+  wgrad_plan(g, p, mb, nb, sp, 3);
+  return (size_t)sp * g.Cout * g.K();
+}
+
+// part[splits][Cout][KH*KW*Cin] <- per-split partial weight gradients; returns the split count
+int conv_tc_wgrad_run(const ConvGeom& g, const void* d_hi, const void* d_lo, const void* x_hi,
+                      const void* x_lo, float* part, int npass, int* splits_out,
+                      cudaStream_t s) {
+  EVE_REQUIRE(conv_tc_wgrad_supported(g), EVE_ERR_SHAPE, "conv_tc_wgrad: unsupported geometry");
+  TcWgradParams p;
+  int mb, nb, sp;
+  wgrad_plan(g, p, mb, nb, sp, npass);
+  p.part = part;
+  CUtensorMap md_hi, md_lo, mx_hi, mx_lo;
+  // boxes are [bn][bh][bw][64 ch]; the dy and x grids have the same shape ("same" padding)
+  EVE_TRY(make_map_nhwc(&md_hi, d_hi, g.N, g.H, g.W, g.Cout, p.bw, p.bh, p.bn));
+  EVE_TRY(make_map_nhwc(&mx_hi, x_hi, g.N, g.H, g.W, g.Cin, p.bw, p.bh, p.bn));
+  if (npass == 3) {
+    EVE_TRY(make_map_nhwc(&md_lo, d_lo, g.N, g.H, g.W, g.Cout, p.bw, p.bh, p.bn));
+    EVE_TRY(make_map_nhwc(&mx_lo, x_lo, g.N, g.H, g.W, g.Cin, p.bw, p.bh, p.bn));
+  } else {
+    md_lo = md_hi;
+    mx_lo = mx_hi;
+  }
+  const int planes = npass == 3 ? 2 : 1;
+  const int smem = p.stages * (2 + p.nblk / 64) * kWgBlockBytes * planes + 1024 + 256;
+  static bool cfg3 = false, cfg1 = false;
+  if (npass == 3 && !cfg3) {
+    EVE_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel<3>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cfg3 = true;
+  }
+  if (npass == 1 && !cfg1) {
+    EVE_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel<1>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cfg1 = true;
+  }
+  dim3 grid(mb, nb, sp);
+  if (npass == 3)
+    conv_tc_wgrad_kernel<3><<<grid, kThreads, smem, s>>>(md_hi, md_lo, mx_hi, mx_lo, p);
+  else
+    conv_tc_wgrad_kernel<1><<<grid, kThreads, smem, s>>>(md_hi, md_lo, mx_hi, mx_lo, p);
+  EVE_LAUNCH_CHECK();
+  *splits_out = sp;
+  return EVE_OK;
 }
 
 }  // namespace eve

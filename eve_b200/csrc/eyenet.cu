@@ -3,6 +3,8 @@
 // Reference: src/models/eye_net.py:37-150 and torchvision.models.resnet (BasicBlock, ResNet)
 // as instantiated at eye_net.py:48-50.  The CNN runs for all patches of a step at once
 // (norms are per sample); only the RNN cell walks over time.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace eve {
@@ -100,10 +102,28 @@ int check_cnn(const eve_eyenet_cnn_params* p) {
   return EVE_OK;
 }
 
+// conv scratch (operand planes, weight layouts, split-K partials) big enough for every
+// convolution of the CNN
+size_t cnn_conv_scratch_bytes(const CnnTape& t) {
+  size_t mi = 0, mo = 0, mw = 0, mp = 0;
+  auto upd = [&](const ConvGeom& g) {
+    mi = std::max(mi, (size_t)g.in_elems());
+    mo = std::max(mo, (size_t)g.out_elems());
+    mw = std::max(mw, (size_t)g.Cout * g.K());
+    mp = std::max(mp, conv_partial_floats(g));
+  };
+  upd(t.stem);
+  for (int i = 0; i < 8; ++i) {
+    upd(t.blk[i].g1);
+    upd(t.blk[i].g2);
+    if (t.blk[i].down) upd(t.blk[i].gd);
+  }
+  return conv_scratch_bytes(mi, mo, mw, mp);
+}
+
 size_t cnn_fwd_scratch(const CnnTape& t) {
-  // one transposed weight copy at a time (largest: 512*512*9) + fc transpose
-  return align_up((size_t)512 * 512 * 9 * sizeof(float), 256) +
-         align_up((size_t)512 * t.nf * sizeof(float), 256);
+  return align_up(cnn_conv_scratch_bytes(t), 256) +
+         align_up((size_t)512 * t.nf * sizeof(float), 256) + 1024;
 }
 
 }  // namespace
@@ -125,25 +145,14 @@ namespace {
 
 // Scratch plan of the backward pass (dry-run capable).
 struct CnnBwdScratch {
-  float *wd, *wg, *inb, *ga, *gb, *t0, *t1, *t2, *t3, *stem_g, *stem_d, *dpooled;
+  float *wg, *inb, *ga, *gb, *t0, *t1, *t2, *t3, *stem_g, *stem_d, *dpooled;
+  ConvScratch cs;
 };
 
 bool build_cnn_bwd_scratch(const CnnTape& t, Arena& ws, CnnBwdScratch& s) {
-  s.wd = ws.get<float>((size_t)512 * 512 * 9);
-  size_t wg = 0;
-  auto upd = [&](const ConvGeom& g) {
-    size_t v = conv_wgrad_scratch_floats(g);
-    if (v > wg) wg = v;
-  };
-  upd(t.stem);
-  for (int i = 0; i < 8; ++i) {
-    upd(t.blk[i].g1);
-    upd(t.blk[i].g2);
-    if (t.blk[i].down) upd(t.blk[i].gd);
-  }
-  size_t lw = linear_wgrad_scratch_floats(t.N, 512, t.nf);
-  if (lw > wg) wg = lw;
-  s.wg = ws.get<float>(wg);
+  s.cs.bytes = cnn_conv_scratch_bytes(t);
+  s.cs.base = ws.get<char>(s.cs.bytes);
+  s.wg = ws.get<float>(linear_wgrad_scratch_floats(t.N, 512, t.nf));
   s.inb = ws.get<float>(in_backward_scratch_floats(t.N, 512));
   s.ga = ws.get<float>(t.max_act);
   s.gb = ws.get<float>(t.max_act);
@@ -187,30 +196,28 @@ extern "C" int eve_eyenet_cnn_fwd(const eve_eyenet_cnn_params* p, const float* x
   EVE_REQUIRE(workspace_bytes >= cnn_fwd_scratch(t), EVE_ERR_WORKSPACE,
               "eyenet_cnn_fwd: workspace too small");
   Arena ws(workspace, workspace_bytes);
-  float* wf = ws.get<float>((size_t)512 * 512 * 9);
+  ConvScratch cs;
+  cs.bytes = cnn_conv_scratch_bytes(t);
+  cs.base = ws.get<char>(cs.bytes);
   float* wfc = ws.get<float>((size_t)512 * t.nf);
   const int N = t.N;
 
   EVE_TRY(nchw_to_nhwc(x, N, 3, p->h, p->w, t.x, s));
-  EVE_TRY(conv_prep_weights(t.stem, w[0], wf, nullptr, s));
-  EVE_TRY(conv_fwd_simt(t.stem, t.x, wf, nullptr, nullptr, t.c1, 64, s));
+  EVE_TRY(conv_fwd(t.stem, t.x, w[0], nullptr, nullptr, t.c1, cs, s));
   EVE_TRY(in_stats(t.c1, N, t.stem.OH * t.stem.OW, 64, t.c1m, t.c1r, s));
   EVE_TRY(in_relu_maxpool(t.c1, N, t.stem.OH, t.stem.OW, 64, t.c1m, t.c1r, t.p, t.pidx, s));
   for (int i = 0; i < 8; ++i) {
     BlockTape& k = t.blk[i];
     const int slot = block_slot(i);
     const int C = k.g1.Cout, HW = k.g1.OH * k.g1.OW;
-    EVE_TRY(conv_prep_weights(k.g1, w[slot], wf, nullptr, s));
-    EVE_TRY(conv_fwd_simt(k.g1, k.in, wf, nullptr, nullptr, k.a, C, s));
+    EVE_TRY(conv_fwd(k.g1, k.in, w[slot], nullptr, nullptr, k.a, cs, s));
     EVE_TRY(in_stats(k.a, N, HW, C, k.am, k.ar, s));
     EVE_TRY(in_apply(k.a, N, HW, C, k.am, k.ar, nullptr, nullptr, nullptr, nullptr, nullptr,
                      ACT_RELU, k.y, s));
-    EVE_TRY(conv_prep_weights(k.g2, w[slot + 1], wf, nullptr, s));
-    EVE_TRY(conv_fwd_simt(k.g2, k.y, wf, nullptr, nullptr, k.b, C, s));
+    EVE_TRY(conv_fwd(k.g2, k.y, w[slot + 1], nullptr, nullptr, k.b, cs, s));
     EVE_TRY(in_stats(k.b, N, HW, C, k.bm, k.br, s));
     if (k.down) {
-      EVE_TRY(conv_prep_weights(k.gd, w[slot + 2], wf, nullptr, s));
-      EVE_TRY(conv_fwd_simt(k.gd, k.in, wf, nullptr, nullptr, k.d, C, s));
+      EVE_TRY(conv_fwd(k.gd, k.in, w[slot + 2], nullptr, nullptr, k.d, cs, s));
       EVE_TRY(in_stats(k.d, N, HW, C, k.dm, k.dr, s));
       EVE_TRY(in_apply(k.b, N, HW, C, k.bm, k.br, nullptr, nullptr, k.d, k.dm, k.dr, ACT_RELU,
                        k.out, s));
@@ -264,28 +271,25 @@ extern "C" int eve_eyenet_cnn_bwd(const eve_eyenet_cnn_params* p, const float* d
                         gskip, nullptr, nullptr, sc.inb, false, s));
     // conv2
     if (gr[slot + 1])
-      EVE_TRY(conv_wgrad_simt(k.g2, k.y, db, C, gr[slot + 1], sc.wg, acc, s));
+      EVE_TRY(conv_wgrad(k.g2, k.y, db, gr[slot + 1], nullptr, acc, sc.cs, s));
     float* dy = sc.t2;
-    EVE_TRY(conv_prep_weights(k.g2, w[slot + 1], nullptr, sc.wd, s));
-    EVE_TRY(conv_dgrad_simt(k.g2, db, C, sc.wd, nullptr, dy, s));
+    EVE_TRY(conv_dgrad(k.g2, db, w[slot + 1], nullptr, dy, sc.cs, s));
     // y = relu(IN(a))
     float* da = sc.t0;
     EVE_TRY(in_backward(dy, k.y, k.a, N, HW, C, k.am, k.ar, nullptr, nullptr, ACT_RELU, nullptr, da,
                         nullptr, nullptr, nullptr, sc.inb, false, s));
-    if (gr[slot]) EVE_TRY(conv_wgrad_simt(k.g1, k.in, da, C, gr[slot], sc.wg, acc, s));
+    if (gr[slot]) EVE_TRY(conv_wgrad(k.g1, k.in, da, gr[slot], nullptr, acc, sc.cs, s));
     const float* addend = gskip;
     if (k.down) {
       float* dd = sc.t2;
       EVE_TRY(in_backward(gskip, nullptr, k.d, N, HW, C, k.dm, k.dr, nullptr, nullptr, ACT_NONE,
                           nullptr, dd, nullptr, nullptr, nullptr, sc.inb, false, s));
       if (gr[slot + 2])
-        EVE_TRY(conv_wgrad_simt(k.gd, k.in, dd, C, gr[slot + 2], sc.wg, acc, s));
-      EVE_TRY(conv_prep_weights(k.gd, w[slot + 2], nullptr, sc.wd, s));
-      EVE_TRY(conv_dgrad_simt(k.gd, dd, C, sc.wd, nullptr, sc.t3, s));
+        EVE_TRY(conv_wgrad(k.gd, k.in, dd, gr[slot + 2], nullptr, acc, sc.cs, s));
+      EVE_TRY(conv_dgrad(k.gd, dd, w[slot + 2], nullptr, sc.t3, sc.cs, s));
       addend = sc.t3;
     }
-    EVE_TRY(conv_prep_weights(k.g1, w[slot], nullptr, sc.wd, s));
-    EVE_TRY(conv_dgrad_simt(k.g1, da, C, sc.wd, addend, dnext, s));
+    EVE_TRY(conv_dgrad(k.g1, da, w[slot], addend, dnext, sc.cs, s));
     float* tmp = dout;
     dout = dnext;
     dnext = tmp;
@@ -297,7 +301,7 @@ extern "C" int eve_eyenet_cnn_bwd(const eve_eyenet_cnn_params* p, const float* d
     EVE_TRY(maxpool_bwd_scatter(dout, t.pidx, N, OH, OW, PH, PW, 64, sc.stem_g, s));
     EVE_TRY(in_backward(sc.stem_g, nullptr, t.c1, N, OH * OW, 64, t.c1m, t.c1r, nullptr, nullptr,
                         ACT_RELU, nullptr, sc.stem_d, nullptr, nullptr, nullptr, sc.inb, false, s));
-    EVE_TRY(conv_wgrad_simt(t.stem, t.x, sc.stem_d, 64, gr[0], sc.wg, acc, s));
+    EVE_TRY(conv_wgrad(t.stem, t.x, sc.stem_d, gr[0], nullptr, acc, sc.cs, s));
   }
   return EVE_OK;
 }

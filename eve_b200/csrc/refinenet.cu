@@ -4,6 +4,7 @@
 // Bottleneck :132-176, RefineNet :179-255) and the cells in src/models/common.py:331-415.
 // Encoder and decoder run for all batch*steps frames at once (per-sample norms, SURVEY.md
 // 3.3); only the 5x8 bottleneck cells walk over time, on time-major copies of the features.
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -367,14 +368,14 @@ clstm_out_kernel(const float* __restrict__ gates, const float* __restrict__ c, l
   } while (0)
 
 // ------------------------------------------------------------------ block fwd/bwd --
-int block_fwd(const RBlock& k, int N, const float* const* w, float* wf, cudaStream_t s) {
+int block_fwd(const RBlock& k, int N, const float* const* w, const ConvScratch& cs,
+              cudaStream_t s) {
   const float* const* bw = w + k.slot;
   const int HW = k.H * k.W;
   EVE_TRY(in_stats(k.x, N, HW, k.ic, k.m0, k.r0, s));
   EVE_TRY(in_apply(k.x, N, HW, k.ic, k.m0, k.r0, bw[0], bw[1], nullptr, nullptr, nullptr, k.act,
                    k.y1, s));
-  EVE_TRY(conv_prep_weights(k.g1, bw[2], wf, nullptr, s));
-  EVE_TRY(conv_fwd_simt(k.g1, k.y1, wf, bw[3], nullptr, k.c1, k.oc, s));
+  EVE_TRY(conv_fwd(k.g1, k.y1, bw[2], bw[3], nullptr, k.c1, cs, s));
   EVE_TRY(in_stats(k.c1, N, HW, k.oc, k.m1, k.r1, s));
   EVE_TRY(in_apply(k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], nullptr, nullptr, nullptr, k.act,
                    k.y2, s));
@@ -382,24 +383,21 @@ int block_fwd(const RBlock& k, int N, const float* const* w, float* wf, cudaStre
   if (k.skipconv) {
     EVE_TRY(in_apply(k.x, N, HW, k.ic, k.m0, k.r0, bw[8], bw[9], nullptr, nullptr, nullptr, k.act,
                      k.s, s));
-    EVE_TRY(conv_prep_weights(k.gs, bw[10], wf, nullptr, s));
-    EVE_TRY(conv_fwd_simt(k.gs, k.s, wf, bw[11], nullptr, k.out, k.oc, s));
+    EVE_TRY(conv_fwd(k.gs, k.s, bw[10], bw[11], nullptr, k.out, cs, s));
     addend = k.out;
   }
-  EVE_TRY(conv_prep_weights(k.g2, bw[6], wf, nullptr, s));
-  EVE_TRY(conv_fwd_simt(k.g2, k.y2, wf, bw[7], addend, k.out, k.oc, s));
+  EVE_TRY(conv_fwd(k.g2, k.y2, bw[6], bw[7], addend, k.out, cs, s));
   return EVE_OK;
 }
 
 struct BwdScratch {
-  float *wd, *wg, *inb, *t0, *t1, *t2, *ga, *gb;
+  float *inb, *t0, *t1, *t2, *ga, *gb;
+  ConvScratch cs;
 };
 
 int conv_param_grads(const ConvGeom& g, const float* x, const float* dy, float* dw, float* db,
-                     float* wg, bool acc, cudaStream_t s) {
-  if (dw) EVE_TRY(conv_wgrad_simt(g, x, dy, g.Cout, dw, wg, acc, s));
-  if (db) EVE_TRY(colsum(dy, (long long)g.N * g.OH * g.OW, g.Cout, g.Cout, db, wg, acc, s));
-  return EVE_OK;
+                     const ConvScratch& cs, bool acc, cudaStream_t s) {
+  return conv_wgrad(g, x, dy, dw, db, acc, cs, s);
 }
 
 // dout -> dx (grad w.r.t. k.x).  dx must not alias t0..t2.
@@ -408,19 +406,16 @@ int block_bwd(const RBlock& k, int N, const float* const* w, float* const* gr, b
   const float* const* bw = w + k.slot;
   float* const* bg = gr + k.slot;
   const int HW = k.H * k.W;
-  EVE_TRY(conv_param_grads(k.g2, k.y2, dout, bg[6], bg[7], sc.wg, acc, s));
-  EVE_TRY(conv_prep_weights(k.g2, bw[6], nullptr, sc.wd, s));
-  EVE_TRY(conv_dgrad_simt(k.g2, dout, k.oc, sc.wd, nullptr, sc.t0, s));
+  EVE_TRY(conv_param_grads(k.g2, k.y2, dout, bg[6], bg[7], sc.cs, acc, s));
+  EVE_TRY(conv_dgrad(k.g2, dout, bw[6], nullptr, sc.t0, sc.cs, s));
   EVE_TRY(in_backward(sc.t0, k.y2, k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], k.act, nullptr,
                       sc.t1, nullptr, bg[4], bg[5], sc.inb, acc, s));
-  EVE_TRY(conv_param_grads(k.g1, k.y1, sc.t1, bg[2], bg[3], sc.wg, acc, s));
-  EVE_TRY(conv_prep_weights(k.g1, bw[2], nullptr, sc.wd, s));
-  EVE_TRY(conv_dgrad_simt(k.g1, sc.t1, k.oc, sc.wd, nullptr, sc.t0, s));
+  EVE_TRY(conv_param_grads(k.g1, k.y1, sc.t1, bg[2], bg[3], sc.cs, acc, s));
+  EVE_TRY(conv_dgrad(k.g1, sc.t1, bw[2], nullptr, sc.t0, sc.cs, s));
   const float* addend = dout;
   if (k.skipconv) {
-    EVE_TRY(conv_param_grads(k.gs, k.s, dout, bg[10], bg[11], sc.wg, acc, s));
-    EVE_TRY(conv_prep_weights(k.gs, bw[10], nullptr, sc.wd, s));
-    EVE_TRY(conv_dgrad_simt(k.gs, dout, k.oc, sc.wd, nullptr, sc.t2, s));
+    EVE_TRY(conv_param_grads(k.gs, k.s, dout, bg[10], bg[11], sc.cs, acc, s));
+    EVE_TRY(conv_dgrad(k.gs, dout, bw[10], nullptr, sc.t2, sc.cs, s));
     EVE_TRY(in_backward(sc.t2, k.s, k.x, N, HW, k.ic, k.m0, k.r0, bw[8], bw[9], k.act, nullptr,
                         sc.t1, nullptr, bg[8], bg[9], sc.inb, acc, s));
     addend = sc.t1;
@@ -430,29 +425,26 @@ int block_bwd(const RBlock& k, int N, const float* const* w, float* const* gr, b
   return EVE_OK;
 }
 
-size_t rnet_wmax(const RNet& n) {
-  size_t m = (size_t)512 * 128 * 9;  // decoder level 3: 512 -> 128
-  size_t c = (size_t)4 * n.nf * 2 * n.nf * 9;
-  return m > c ? m : c;
-}
-
-bool build_bwd_scratch(const RNet& n, Arena& ws, BwdScratch& sc) {
-  sc.wd = ws.get<float>(rnet_wmax(n));
-  size_t wg = 0;
+size_t rnet_conv_scratch_bytes(const RNet& n) {
+  size_t mi = 0, mo = 0, mw = 0, mp = 0;
   auto upd = [&](const ConvGeom& g) {
-    size_t v = conv_wgrad_scratch_floats(g);
-    size_t c = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
-    if (v > wg) wg = v;
-    if (c > wg) wg = c;
+    mi = std::max(mi, (size_t)g.in_elems());
+    mo = std::max(mo, (size_t)g.out_elems());
+    mw = std::max(mw, (size_t)g.Cout * g.K());
+    mp = std::max(mp, conv_partial_floats(g));
   };
   upd(n.gi0); upd(n.gi3); upd(n.gf0); upd(n.gf2);
   for (int l = 0; l < kLevels; ++l) {
     for (auto& k : n.enc[l]) { upd(k.g1); upd(k.g2); upd(k.gs); }
     upd(n.dec[l].g1); upd(n.dec[l].g2); upd(n.dec[l].gs);
   }
-  ConvGeom gc = make_conv(n.N, kLevelH[4], kLevelW[4], 2 * n.nf, 4 * n.nf, 3, 1, 1);
-  upd(gc);
-  sc.wg = ws.get<float>(wg);
+  upd(make_conv(n.N, kLevelH[4], kLevelW[4], 2 * n.nf, 4 * n.nf, 3, 1, 1));
+  return conv_scratch_bytes(mi, mo, mw, mp);
+}
+
+bool build_bwd_scratch(const RNet& n, Arena& ws, BwdScratch& sc) {
+  sc.cs.bytes = rnet_conv_scratch_bytes(n);
+  sc.cs.base = ws.get<char>(sc.cs.bytes);
   sc.inb = ws.get<float>(in_backward_scratch_floats(n.N, 512));
   sc.t0 = ws.get<float>(n.max_act);
   sc.t1 = ws.get<float>(n.max_act);
@@ -470,7 +462,6 @@ struct BwdExtra {
   float *dby, *dbx;           // time-major [T][B][P][nf]
   float* dg1all[kMaxRCells];  // [T][B][P][2nf]
   float* dg2all[kMaxRCells];  // [T][B][P][nf]
-  float* cellwd;              // dgrad weight layouts of every cell
 };
 
 bool build_bwd_extra(const RNet& n, Arena& ws, BwdExtra& e) {
@@ -490,18 +481,12 @@ bool build_bwd_extra(const RNet& n, Arena& ws, BwdExtra& e) {
     e.dg1all[i] = on ? ws.get<float>(be * 2) : nullptr;
     e.dg2all[i] = on && n.p.rnn_type == EVE_CRNN_CGRU ? ws.get<float>(be) : nullptr;
   }
-  e.cellwd = ws.get<float>((size_t)kMaxRCells * 4 * n.nf * 2 * n.nf * 9);
   return ws.ok();
-}
-
-inline size_t rnet_cellw_floats(const RNet& n) {
-  return (size_t)kMaxRCells * 4 * n.nf * 2 * n.nf * 9;
 }
 
 size_t rnet_fwd_scratch_bytes(const RNet& n) {
   const int P = kLevelH[4] * kLevelW[4];
-  return align_up(rnet_wmax(n) * sizeof(float), 256) +
-         align_up(rnet_cellw_floats(n) * sizeof(float), 256) +
+  return align_up(rnet_conv_scratch_bytes(n), 256) +
          4 * align_up((size_t)n.B * P * 4 * n.nf * sizeof(float), 256) +
          2 * align_up((size_t)kMaxRCells * n.B * P * n.nf * sizeof(float), 256) + 4096;
 }
@@ -572,8 +557,9 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
   Arena ws(workspace, workspace_bytes);
   const int N = n.N, B = n.B, T = n.T, nf = n.nf;
   const int P = kLevelH[4] * kLevelW[4];
-  float* wf = ws.get<float>(rnet_wmax(n));
-  float* cellw = ws.get<float>(rnet_cellw_floats(n));
+  ConvScratch cs;
+  cs.bytes = rnet_conv_scratch_bytes(n);
+  cs.base = ws.get<char>(cs.bytes);
   float* cb[4];
   for (int i = 0; i < 4; ++i) cb[i] = ws.get<float>((size_t)B * P * 4 * nf);
   float* h0n = ws.get<float>((size_t)kMaxRCells * B * P * nf);
@@ -587,16 +573,14 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
     EVE_CUDA(cudaMemcpyAsync(n.x0, heatmap, (size_t)N * HW0 * sizeof(float),
                              cudaMemcpyDeviceToDevice, s));
   }
-  EVE_TRY(conv_prep_weights(n.gi0, w[0], wf, nullptr, s));
-  EVE_TRY(conv_fwd_simt(n.gi0, n.x0, wf, w[1], nullptr, n.i0, 16, s));
+  EVE_TRY(conv_fwd(n.gi0, n.x0, w[0], w[1], nullptr, n.i0, cs, s));
   EVE_TRY(in_stats(n.i0, N, HW0, 16, n.im, n.ir, s));
   EVE_TRY(in_apply(n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], nullptr, nullptr, nullptr, ACT_RELU,
                    n.i1, s));
-  EVE_TRY(conv_prep_weights(n.gi3, w[4], wf, nullptr, s));
-  EVE_TRY(conv_fwd_simt(n.gi3, n.i1, wf, w[5], nullptr, n.i2, 16, s));
+  EVE_TRY(conv_fwd(n.gi3, n.i1, w[4], w[5], nullptr, n.i2, cs, s));
   // ---- encoder
   for (int l = 0; l < kLevels; ++l) {
-    for (auto& k : n.enc[l]) EVE_TRY(block_fwd(k, N, w, wf, s));
+    for (auto& k : n.enc[l]) EVE_TRY(block_fwd(k, N, w, cs, s));
     if (l + 1 < kLevels) {
       const RBlock& k = n.enc[l].back();
       EVE_TRY(adaptive_maxpool_fwd(k.out, N, k.H, k.W, k.oc, kLevelH[l + 1], kLevelW[l + 1],
@@ -623,13 +607,12 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
       ConvGeom gg = make_conv(B, kLevelH[4], kLevelW[4], 2 * nf, 4 * nf, 3, 1, 1);
       for (int i = 0; i < nc; ++i) {
         const float* const* cw = w + n.slot_rnn + 2 * i;
-        EVE_TRY(conv_prep_weights(gg, cw[0], wf, nullptr, s));
         float* hcur = h0n + (size_t)i * B * E;
         float* ccur = c0n + (size_t)i * B * E;
         for (int t = 0; t < T; ++t) {
           const float* xt = n.bx + (size_t)t * B * E;
           LAUNCH1D(cat2_kernel, rows * 2 * nf, xt, hcur, rows, nf, cb[0]);
-          EVE_TRY(conv_fwd_simt(gg, cb[0], wf, cw[1], nullptr, cb[1], 4 * nf, s));
+          EVE_TRY(conv_fwd(gg, cb[0], cw[0], cw[1], nullptr, cb[1], cs, s));
           LAUNCH1D(clstm_out_kernel, rows * nf, cb[1], ccur, rows, nf, hcur, ccur);
         }
       }
@@ -638,22 +621,6 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
       ConvGeom g1 = make_conv(B, kLevelH[4], kLevelW[4], 2 * nf, gru ? 2 * nf : nf, 3, 1, 1);
       ConvGeom g2 = make_conv(B, kLevelH[4], kLevelW[4], 2 * nf, nf, 3, 1, 1);
       const int wpc = gru ? 4 : 2;
-      // weight copies for both convs of every cell stay resident in the scratch
-      float* wf1[kMaxRCells];
-      float* wf2[kMaxRCells];
-      {
-        float* q = cellw;
-        for (int i = 0; i < nc; ++i) {
-          const float* const* cw = w + n.slot_rnn + wpc * i;
-          wf1[i] = q; q += (size_t)g1.Cout * g1.K();
-          EVE_TRY(conv_prep_weights(g1, cw[0], wf1[i], nullptr, s));
-          wf2[i] = nullptr;
-          if (gru) {
-            wf2[i] = q; q += (size_t)g2.Cout * g2.K();
-            EVE_TRY(conv_prep_weights(g2, cw[2], wf2[i], nullptr, s));
-          }
-        }
-      }
       for (int i = 0; i < nc; ++i)
         EVE_CUDA(cudaMemcpyAsync(n.cell[i].h0, h0n + (size_t)i * B * E, (size_t)B * E * sizeof(float),
                                  cudaMemcpyDeviceToDevice, s));
@@ -671,12 +638,12 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
             float* zz = c.z + (size_t)t * B * E;
             float* nn = c.n + (size_t)t * B * E;
             float* cat2 = c.cat2 + (size_t)t * B * E * 2;
-            EVE_TRY(conv_fwd_simt(g1, xh, wf1[i], cw[1], nullptr, cb[0], 2 * nf, s));
+            EVE_TRY(conv_fwd(g1, xh, cw[0], cw[1], nullptr, cb[0], cs, s));
             LAUNCH1D(cgru_mid_kernel, rows * nf, cb[0], xt, hprev, rows, nf, rr, zz, cat2);
-            EVE_TRY(conv_fwd_simt(g2, cat2, wf2[i], cw[3], nullptr, cb[1], nf, s));
+            EVE_TRY(conv_fwd(g2, cat2, cw[2], cw[3], nullptr, cb[1], cs, s));
             LAUNCH1D(cgru_out_kernel, rows * nf, cb[1], zz, hprev, rows * nf, nn, hn);
           } else {
-            EVE_TRY(conv_fwd_simt(g1, xh, wf1[i], cw[1], nullptr, cb[0], nf, s));
+            EVE_TRY(conv_fwd(g1, xh, cw[0], cw[1], nullptr, cb[0], cs, s));
             EVE_TRY(ew_fwd(EW_TANH, cb[0], rows * nf, hn, s));
           }
           xt = hn;
@@ -702,7 +669,7 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
     if (p->use_skip)
       EVE_TRY(copy_channels(n.enc[4].back().out, (long long)N * P, nf, nf, 0, n.cat[4], k.ic, nf,
                             false, s));
-    EVE_TRY(block_fwd(k, N, w, wf, s));
+    EVE_TRY(block_fwd(k, N, w, cs, s));
   }
   for (int l = 3; l >= 0; --l) {
     const RBlock& k = n.dec[l];
@@ -713,15 +680,13 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
     if (p->use_skip)
       EVE_TRY(copy_channels(e.out, (long long)N * k.H * k.W, e.oc, e.oc, 0, n.cat[l], k.ic,
                             inner.oc, false, s));
-    EVE_TRY(block_fwd(k, N, w, wf, s));
+    EVE_TRY(block_fwd(k, N, w, cs, s));
   }
   // ---- final: conv3x3 -> LeakyReLU -> conv1x1 -> sigmoid
   const float* const* fw = w + n.slot_final;
-  EVE_TRY(conv_prep_weights(n.gf0, fw[0], wf, nullptr, s));
-  EVE_TRY(conv_fwd_simt(n.gf0, n.dec[0].out, wf, fw[1], nullptr, n.f0, 16, s));
+  EVE_TRY(conv_fwd(n.gf0, n.dec[0].out, fw[0], fw[1], nullptr, n.f0, cs, s));
   EVE_TRY(ew_fwd(EW_LEAKY, n.f0, (long long)N * HW0 * 16, n.f1, s));
-  EVE_TRY(conv_prep_weights(n.gf2, fw[2], wf, nullptr, s));
-  EVE_TRY(conv_fwd_simt(n.gf2, n.f1, wf, fw[3], nullptr, out, 1, s));
+  EVE_TRY(conv_fwd(n.gf2, n.f1, fw[2], fw[3], nullptr, out, cs, s));
   EVE_TRY(ew_fwd(EW_SIGMOID, out, (long long)N * HW0, n.sig, s));
   EVE_CUDA(cudaMemcpyAsync(out, n.sig, (size_t)N * HW0 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return EVE_OK;
@@ -761,15 +726,13 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
   const float* const* fw = w + n.slot_final;
   float* const* fg = gr + n.slot_final;
   EVE_TRY(ew_bwd(EW_SIGMOID, dout, n.sig, (long long)N * HW0, sc.t0, s));
-  EVE_TRY(conv_param_grads(n.gf2, n.f1, sc.t0, fg[2], fg[3], sc.wg, acc, s));
-  EVE_TRY(conv_prep_weights(n.gf2, fw[2], nullptr, sc.wd, s));
-  EVE_TRY(conv_dgrad_simt(n.gf2, sc.t0, 1, sc.wd, nullptr, sc.t1, s));
+  EVE_TRY(conv_param_grads(n.gf2, n.f1, sc.t0, fg[2], fg[3], sc.cs, acc, s));
+  EVE_TRY(conv_dgrad(n.gf2, sc.t0, fw[2], nullptr, sc.t1, sc.cs, s));
   EVE_TRY(ew_bwd(EW_LEAKY, sc.t1, n.f0, (long long)N * HW0 * 16, sc.t2, s));
-  EVE_TRY(conv_param_grads(n.gf0, n.dec[0].out, sc.t2, fg[0], fg[1], sc.wg, acc, s));
-  EVE_TRY(conv_prep_weights(n.gf0, fw[0], nullptr, sc.wd, s));
+  EVE_TRY(conv_param_grads(n.gf0, n.dec[0].out, sc.t2, fg[0], fg[1], sc.cs, acc, s));
   float* cur = sc.ga;
   float* other = sc.gb;
-  EVE_TRY(conv_dgrad_simt(n.gf0, sc.t2, 16, sc.wd, nullptr, cur, s));
+  EVE_TRY(conv_dgrad(n.gf0, sc.t2, fw[0], nullptr, cur, sc.cs, s));
 
   // ---- decoder, outermost first
   for (int l = 0; l < 4; ++l) {
@@ -809,21 +772,6 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
     const int wpc = gru ? 4 : 2;
     ConvGeom g1 = make_conv(B, kLevelH[4], kLevelW[4], 2 * nf, gru ? 2 * nf : nf, 3, 1, 1);
     ConvGeom g2 = make_conv(B, kLevelH[4], kLevelW[4], 2 * nf, nf, 3, 1, 1);
-    float* wd1[kMaxRCells];
-    float* wd2[kMaxRCells];
-    {
-      float* q = ex.cellwd;
-      for (int i = 0; i < nc; ++i) {
-        const float* const* cw = w + n.slot_rnn + wpc * i;
-        wd1[i] = q; q += (size_t)g1.Cout * g1.K();
-        EVE_TRY(conv_prep_weights(g1, cw[0], nullptr, wd1[i], s));
-        wd2[i] = nullptr;
-        if (gru) {
-          wd2[i] = q; q += (size_t)g2.Cout * g2.K();
-          EVE_TRY(conv_prep_weights(g2, cw[2], nullptr, wd2[i], s));
-        }
-      }
-    }
     // initial carries = gradient into the final states
     for (int i = 0; i < nc; ++i) {
       if (dhT)
@@ -841,6 +789,7 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
       const float* dcur = ex.dby + (size_t)t * B * E;
       for (int i = nc - 1; i >= 0; --i) {
         const CellTape& c = n.cell[i];
+        const float* const* cw = w + n.slot_rnn + wpc * i;
         const float* hprev = t == 0 ? c.h0 : c.h + (size_t)(t - 1) * B * E;
         float* dg1 = ex.dg1all[i] + (size_t)t * B * E * (gru ? 2 : 1);
         float* dxo = (i == 0) ? ex.dbx + (size_t)t * B * E : (dcur == dxa ? dxb : dxa);
@@ -848,15 +797,15 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
           float* dg2 = ex.dg2all[i] + (size_t)t * B * E;
           LAUNCH1D(cgru_bwd1_kernel, rows * nf, dcur, ex.dcarry[i], c.z + (size_t)t * B * E,
                    c.n + (size_t)t * B * E, hprev, rows * nf, dg2, dzbuf, dhdir);
-          EVE_TRY(conv_dgrad_simt(g2, dg2, nf, wd2[i], nullptr, dcat2, s));
+          EVE_TRY(conv_dgrad(g2, dg2, cw[2], nullptr, dcat2, sc.cs, s));
           LAUNCH1D(cgru_bwd2_kernel, rows * nf, dcat2, c.r + (size_t)t * B * E, hprev, dzbuf, rows,
                    nf, dg1, dhdir);
-          EVE_TRY(conv_dgrad_simt(g1, dg1, 2 * nf, wd1[i], nullptr, dxh, s));
+          EVE_TRY(conv_dgrad(g1, dg1, cw[0], nullptr, dxh, sc.cs, s));
           LAUNCH1D(cgru_bwd3_kernel, rows * nf, dcat2, dxh, dhdir, rows, nf, dxo, ex.dcarry[i]);
         } else {
           LAUNCH1D(crnn_bwd_kernel, rows * nf, dcur, ex.dcarry[i], c.h + (size_t)t * B * E,
                    rows * nf, dg1);
-          EVE_TRY(conv_dgrad_simt(g1, dg1, nf, wd1[i], nullptr, dxh, s));
+          EVE_TRY(conv_dgrad(g1, dg1, cw[0], nullptr, dxh, sc.cs, s));
           LAUNCH1D(cgru_bwd3_kernel, rows * nf, (const float*)nullptr, dxh, (const float*)nullptr,
                    rows, nf, dxo, ex.dcarry[i]);
         }
@@ -869,9 +818,9 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
     ConvGeom G2 = make_conv(N, kLevelH[4], kLevelW[4], 2 * nf, nf, 3, 1, 1);
     for (int i = 0; i < nc; ++i) {
       float* const* cg = gr + n.slot_rnn + wpc * i;
-      EVE_TRY(conv_param_grads(G1, n.cell[i].xh, ex.dg1all[i], cg[0], cg[1], sc.wg, acc, s));
+      EVE_TRY(conv_param_grads(G1, n.cell[i].xh, ex.dg1all[i], cg[0], cg[1], sc.cs, acc, s));
       if (gru)
-        EVE_TRY(conv_param_grads(G2, n.cell[i].cat2, ex.dg2all[i], cg[2], cg[3], sc.wg, acc, s));
+        EVE_TRY(conv_param_grads(G2, n.cell[i].cat2, ex.dg2all[i], cg[2], cg[3], sc.cs, acc, s));
       if (dh0)
         EVE_TRY(nhwc_to_nchw(ex.dcarry[i], B, nf, kLevelH[4], kLevelW[4], dh0 + (size_t)i * B * E, s));
     }
@@ -895,15 +844,13 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
     }
   }
   // ---- initial
-  EVE_TRY(conv_param_grads(n.gi3, n.i1, cur, gr[4], gr[5], sc.wg, acc, s));
-  EVE_TRY(conv_prep_weights(n.gi3, w[4], nullptr, sc.wd, s));
-  EVE_TRY(conv_dgrad_simt(n.gi3, cur, 16, sc.wd, nullptr, sc.t0, s));
+  EVE_TRY(conv_param_grads(n.gi3, n.i1, cur, gr[4], gr[5], sc.cs, acc, s));
+  EVE_TRY(conv_dgrad(n.gi3, cur, w[4], nullptr, sc.t0, sc.cs, s));
   EVE_TRY(in_backward(sc.t0, n.i1, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU, nullptr,
                       sc.t1, nullptr, gr[2], gr[3], sc.inb, acc, s));
-  EVE_TRY(conv_param_grads(n.gi0, n.x0, sc.t1, gr[0], gr[1], sc.wg, acc, s));
+  EVE_TRY(conv_param_grads(n.gi0, n.x0, sc.t1, gr[0], gr[1], sc.cs, acc, s));
   if (dheatmap) {
-    EVE_TRY(conv_prep_weights(n.gi0, w[0], nullptr, sc.wd, s));
-    EVE_TRY(conv_dgrad_simt(n.gi0, sc.t1, 16, sc.wd, nullptr, sc.t0, s));
+    EVE_TRY(conv_dgrad(n.gi0, sc.t1, w[0], nullptr, sc.t0, sc.cs, s));
     EVE_TRY(copy_channels(sc.t0, (long long)N * HW0, 1, p->in_channels, p->in_channels - 1, dheatmap,
                           1, 0, false, s));
   }

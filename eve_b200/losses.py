@@ -63,12 +63,12 @@ class EuclideanLoss(_Loss):
 
 
 class CrossEntropyLoss(_Loss):
-    """cross_entropy.py:29-35: F.binary_cross_entropy per frame (log clamped at -100)."""
+    """cross_entropy.py:29-35: F.binary_cross_entropy per frame.  The torch op is kept (not
+    a log/clamp restatement) because its backward stays finite when the sigmoid saturates
+    to exactly 0 or 1, which a clamp-of-log formulation does not (0 * inf)."""
 
     def per_frame(self, a, b):
-        la = torch.clamp(torch.log(a), min=-100.0)
-        l1a = torch.clamp(torch.log(1.0 - a), min=-100.0)
-        return (-(b * la + (1.0 - b) * l1a)).mean(dim=_feature_dims(a))
+        return F.binary_cross_entropy(a, b, reduction='none').mean(dim=_feature_dims(a))
 
 
 cross_entropy_loss = CrossEntropyLoss()

@@ -402,10 +402,9 @@ def euclidean_per_frame(a, b):
 
 
 def bce_per_frame(a, b):
-    """cross_entropy.py:29-35: F.binary_cross_entropy per frame (log clamped at -100)."""
-    la = torch.clamp(torch.log(a), min=-100.0)
-    l1a = torch.clamp(torch.log(1.0 - a), min=-100.0)
-    return (-(b * la + (1.0 - b) * l1a)).mean(dim=_feature_dims(a))
+    """cross_entropy.py:29-35: F.binary_cross_entropy per frame (the reference's own call;
+    its backward stays finite when a saturates to exactly 0 or 1)."""
+    return F.binary_cross_entropy(a, b, reduction='none').mean(dim=_feature_dims(a))
 
 
 # ------------------------------------------------------------------------------- EVE --

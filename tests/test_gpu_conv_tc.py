@@ -39,7 +39,7 @@ def conv_mode():
 
 
 @pytest.mark.parametrize('case', TC_CASES)
-def test_tensor_core_conv_forward_and_dgrad(case, conv_mode):
+def test_tensor_core_conv_forward_dgrad_wgrad(case, conv_mode):
     n, cin, h, w, cout, k = case
     pad = k // 2
     g = torch.Generator().manual_seed(sum(case))
@@ -47,7 +47,8 @@ def test_tensor_core_conv_forward_and_dgrad(case, conv_mode):
     wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
     b = torch.randn(cout, generator=g)
     xd = x.double().requires_grad_(True)
-    y = F.conv2d(xd, wt.double(), b.double(), padding=pad)
+    wd = wt.double().requires_grad_(True)
+    y = F.conv2d(xd, wd, b.double(), padding=pad)
     dy = torch.randn(y.shape, generator=g)
     y.backward(dy.double())
     errs = {}
@@ -55,8 +56,10 @@ def test_tensor_core_conv_forward_and_dgrad(case, conv_mode):
         conv_mode(mode)
         got = G.conv_fwd(x.cuda(), wt.cuda(), b.cuda(), 1, pad)
         dx = G.conv_dgrad(dy.cuda(), wt.cuda(), (h, w), 1, pad)
+        dw, db = G.conv_wgrad(x.cuda(), dy.cuda(), k, 1, pad)
         torch.cuda.synchronize()
-        errs[mode] = (G.rel(got, y), G.rel(dx, xd.grad))
+        errs[mode] = (G.rel(got, y), G.rel(dx, xd.grad), G.rel(dw, wd.grad))
+        assert G.rel(db, dy.double().sum(dim=(0, 2, 3))) < 2e-5
     assert max(errs[0]) < 2e-5, errs
     assert max(errs[1]) < 3e-5, errs            # split-bf16: fp32-class accuracy
     assert 1e-4 < max(errs[2]) < 3e-2, errs     # single bf16 pass really is bf16

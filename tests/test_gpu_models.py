@@ -18,6 +18,20 @@ from tests import gpu_util as G          # noqa: E402
 from tests import helpers as H           # noqa: E402
 
 
+@pytest.fixture(params=[0, 1], ids=['fp32-simt', 'tcgen05-bf16x3'])
+def conv_mode(request):
+    """Run under both kernel selections: 0 = fp32 CUDA cores everywhere (exact products),
+    1 = tcgen05 split-bf16 (the default product path).  Yields a tolerance multiplier: the
+    split-bf16 products carry ~2^-17 relative representation error instead of fp32's 2^-24,
+    which InstanceNorm over nearly constant maps (RefineNet at random weights) amplifies."""
+    from eve_b200 import lib as L
+    lib = L.load()
+    prev = lib.eve_get_conv_mode()
+    lib.eve_set_conv_mode(request.param)
+    yield {0: 1.0, 1: 5.0}[request.param]
+    lib.eve_set_conv_mode(prev)
+
+
 def _load(model, sd):
     model.load_state_dict(sd, strict=True)
     return model.cuda()
@@ -28,7 +42,8 @@ def _cuda(d):
 
 
 # ------------------------------------------------------------------ module entry points --
-def test_module_entry_points_match_reference(cfg):
+def test_module_entry_points_match_reference(cfg, conv_mode):
+    tolx = conv_mode
     from eve_b200 import synth
     from eve_b200.models import EyeNet, RefineNet
     from eve_b200.models.common import batch_make_heatmaps, soft_argmax
@@ -57,15 +72,16 @@ def test_module_entry_points_match_reference(cfg):
         prev = torch.from_numpy((0.5 * rs.normal(size=(2, 64, 5, 8))).astype(np.float32)).cuda()
         out = {'heatmap_initial': hm}
         rnet({'screen_frame': screen}, out, previous_output_dict={'refinenet_rnn_states_0': prev})
-        assert H.rel_err(out['heatmap_final'].cpu().numpy(), gold['refine/heatmap_final']) < 1e-4
-        assert H.rel_err(out['refinenet_rnn_states_0'].cpu().numpy(), gold['refine/state']) < 1e-4
+        assert H.rel_err(out['heatmap_final'].cpu().numpy(), gold['refine/heatmap_final']) < 1e-4 * tolx
+        assert H.rel_err(out['refinenet_rnn_states_0'].cpu().numpy(), gold['refine/state']) < 1e-4 * tolx
         assert H.rel_err(soft_argmax(out['heatmap_final']).cpu().numpy(),
                          gold['refine/softargmax']) < 1e-3
 
 
 # ----------------------------------------------------------------------- golden EVE cases --
 @pytest.mark.parametrize('name', H.golden_names())
-def test_eve_forward_backward_matches_reference(name, cfg):
+def test_eve_forward_backward_matches_reference(name, cfg, conv_mode):
+    tolx = conv_mode
     from eve_b200.models import EVE
     gold = H.load_golden(name)
     H.apply_case_config(cfg, gold)
@@ -104,6 +120,8 @@ def test_eve_forward_backward_matches_reference(name, cfg):
         else:
             assert got.shape == ref.shape, (k, got.shape, ref.shape)
             tol = 2e-3 if ('final' in key or 'refined' in key or key == 'full_loss') else 2e-4
+            if tol == 2e-3 and tolx > 1:
+                tol = 5e-3          # still inside the 1e-3 bar on PoG: see DESIGN.md (precision)
             if pad_last and got.ndim >= 1 and got.shape[0] == B:
                 # Zero-padded frames (all-zero images, validity 0) put InstanceNorm at
                 # var ~ 0, where rstd = 316 amplifies fp32 summation-order noise: hold the
@@ -128,7 +146,7 @@ def test_eve_forward_backward_matches_reference(name, cfg):
             g = params[pname].grad
             assert g is not None, pname
             gn = float(g.double().norm())
-            gtol = 2e-2
+            gtol = 2e-2 * (2.0 if tolx > 1 else 1.0)
             assert abs(gn - float(ref)) <= gtol * max(float(ref), 1e-6) + floor, \
                 (pname, gn, float(ref))
             sample = gold['grad/' + pname]
@@ -217,7 +235,8 @@ def test_eyenet_tail_sequences_with_state_and_gradients(cfg, rnn, cells, head_po
         assert G.rel(p.grad, want) < 2e-4, name
 
 
-def test_eyenet_cnn_gradients_match_oracle(cfg):
+def test_eyenet_cnn_gradients_match_oracle(cfg, conv_mode):
+    tolx = conv_mode
     """ResNet-18/InstanceNorm forward + every conv weight gradient against the fp64 oracle."""
     from eve_b200 import synth
     from eve_b200.models import EyeNet
@@ -231,14 +250,14 @@ def test_eyenet_cnn_gradients_match_oracle(cfg):
     want = O.resnet18_in_features(osd, 'eye_net.cnn_layers.', x.double())
     (want * wf.double()).sum().backward()
     got = net.cnn_features(x.cuda())
-    assert G.rel(got, want) < 2e-5
+    assert G.rel(got, want) < 2e-5 * tolx
     (got * wf.cuda()).sum().backward()
     for name, p in net.named_parameters():
         if not name.startswith('cnn_layers.'):
             continue
         ref = osd['eye_net.' + name].grad
         l2 = float((p.grad.double().cpu() - ref).norm() / (ref.norm() + 1e-30))
-        assert l2 < 1e-3, (name, l2)
+        assert l2 < 1e-3 * tolx, (name, l2)
 
 
 REFINE_CASES = [('CGRU', 1, True, True), ('CRNN', 2, True, True), ('CGRU', 2, False, False),
@@ -246,11 +265,12 @@ REFINE_CASES = [('CGRU', 1, True, True), ('CRNN', 2, True, True), ('CGRU', 2, Fa
 
 
 @pytest.mark.parametrize('rnn,cells,skip,screen', REFINE_CASES)
-def test_refinenet_sequences_with_state_and_gradients(cfg, rnn, cells, skip, screen):
+def test_refinenet_sequences_with_state_and_gradients(cfg, rnn, cells, skip, screen, conv_mode):
     """refine_net.py:237-255 over B x T with non-zero initial states: heatmaps, final states
     and gradients w.r.t. the input heatmap, the initial state and every weight."""
     from eve_b200 import synth
     from eve_b200.models import RefineNet
+    tolx = conv_mode
     cfg.override('refine_net_enabled', True)
     cfg.override('load_screen_content', screen)
     cfg.override('refine_net_use_skip_connections', skip)
@@ -306,12 +326,12 @@ def test_refinenet_sequences_with_state_and_gradients(cfg, rnn, cells, skip, scr
     hc = h0.detach().cuda().requires_grad_(True) if rnn else None
     got, hT, cT = net.sequence(scr.cuda() if screen else None, hmc, hc,
                                c0.cuda() if c0 is not None else None)
-    assert G.rel(got, want) < 1e-4
+    assert G.rel(got, want) < 1e-4 * tolx
     closs = (got * wo.cuda()).sum()
     if rnn:
-        assert G.rel(hT, fin[0]) < 1e-4
+        assert G.rel(hT, fin[0]) < 1e-4 * tolx
         if rnn == 'CLSTM':
-            assert G.rel(cT, fin[1]) < 1e-4
+            assert G.rel(cT, fin[1]) < 1e-4 * tolx
     if wh is not None:
         closs = closs + (hT * wh.cuda()).sum()
     closs.backward()
@@ -321,7 +341,7 @@ def test_refinenet_sequences_with_state_and_gradients(cfg, rnn, cells, skip, scr
     # our fp32 result must be as close to the fp64 truth as the oracle's own fp32 run,
     # within a factor 3 (+1e-4 absolute floor on the relative L2 error).
     def bar(ref32, ref64):
-        return 3.0 * l2(ref32, ref64) + 1e-4
+        return 3.0 * tolx * l2(ref32, ref64) + 1e-4
 
     assert l2(hmc.grad, dhm64) < bar(dhm32, dhm64), (l2(hmc.grad, dhm64), l2(dhm32, dhm64))
     if wh is not None:
@@ -343,7 +363,7 @@ def test_refinenet_sequences_with_state_and_gradients(cfg, rnn, cells, skip, scr
     # the fp32 noise level of this network / input (single tensors can be lucky)
     noise = float(np.median([e32 for _, _, e32 in rows]))
     for name, e, e32 in rows:
-        assert e < 3.0 * max(e32, noise) + 1e-4, (name, e, e32, noise)
+        assert e < 3.0 * tolx * max(e32, noise) + 1e-4, (name, e, e32, noise)
 
 
 def test_per_step_and_time_batched_paths_agree(cfg):
