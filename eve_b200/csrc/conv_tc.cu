@@ -139,37 +139,53 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 B, 8-row groups
-// 1024 B apart).  Advancing by 16 bf16 along K = +32 B on the start address.
-__device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
-         (2ull << 61);
+// Shared-memory matrix descriptors.  `cw` = channels per row of the staged box (64, 32 or 16
+// bf16 = 128, 64 or 32 bytes), which fixes the TMA / UMMA swizzle mode:
+//   64 -> SWIZZLE_128B (layout type 2), 32 -> SWIZZLE_64B (4), 16 -> SWIZZLE_32B (6);
+// 8 consecutive rows form one swizzle atom of 8 * row_bytes bytes (= the stride byte offset).
+__device__ __forceinline__ uint64_t desc_layout_bits(int cw) {
+  return cw == 64 ? (2ull << 61) : (cw == 32 ? (4ull << 61) : (6ull << 61));
+}
+// K-major (forward / dgrad operands: K = channels runs along the row)
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t saddr, int cw) {
+  const uint64_t sbo = (uint64_t)((cw * 2 * 8) >> 4);
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) |
+         desc_layout_bits(cw);
+}
+// MN-major (wgrad operands: M/N = channels runs along the row, K = pixel rows); lbo = byte
+// distance between consecutive cw-channel blocks
+__device__ __forceinline__ uint64_t mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes, int cw) {
+  const uint64_t sbo = (uint64_t)((cw * 2 * 8) >> 4);
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         (sbo << 32) | (1ull << 46) | desc_layout_bits(cw);
 }
 
 struct TcParams {
-  int N, H, W, Cin, Cout, KH, KW, pad;
-  int bw, bh, bn;           // pixel box of one M tile (bw == W)
-  int tiles_h;              // ceil(H / bh)
-  int kchunks;              // Cin / 64
+  int N, OH, OW, Cin, Cout, KH, KW, pad, stride;
+  int bw, bh, bn;           // output-pixel box of one M tile (bw == OW)
+  int tiles_h;              // ceil(OH / bh)
+  int kc;                   // channels per K chunk: 64, 32 or 16
+  int kchunks;              // Cin / kc
   const float* bias;        // [Cout] or null
-  const float* addend;      // [N,H,W,Cout] or null
-  float* out;               // [N,H,W,Cout]
+  const float* addend;      // [N,OH,OW,Cout] or null
+  float* out;               // [N,OH,OW,Cout]
 };
 
 constexpr int kTileM = 128;
-constexpr int kTileK = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int kThreads = 192;
 
 template <int BN, int NPASS>
 struct TcCfg {
-  static constexpr int kABytes = kTileM * kTileK * 2;
-  static constexpr int kBBytes = BN * kTileK * 2;
+  static constexpr int kABytes = kTileM * 64 * 2;      // slot sizes for the widest chunk
+  static constexpr int kBRows = BN < 8 ? 8 : BN;
+  static constexpr int kBBytes = (BN * 64 * 2) < 1024 ? 1024 : BN * 64 * 2;
   static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
   static constexpr int kStageBytes = (kABytes + kBBytes) * kPlanes;
   static constexpr int kBudget = 224 * 1024;
   static constexpr int kStagesRaw = (kBudget - 2048) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
 };
 
 template <int BN, int NPASS>
@@ -211,7 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -221,7 +237,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===================== TMA producer =====================
     if (elect_one()) {
       const uint32_t rows = p.bw * p.bh * p.bn;
-      const uint32_t tx = (rows * 128u + (uint32_t)Cfg::kBBytes) * Cfg::kPlanes;
+      const uint32_t tx = (rows + (uint32_t)BN) * (uint32_t)(p.kc * 2) * Cfg::kPlanes;
       for (int it = 0; it < iters; ++it) {
         const int s = it % Cfg::kStages;
         const uint32_t ph = (it / Cfg::kStages) & 1;
@@ -231,14 +247,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int kc = it - tap * p.kchunks;
         const int r = tap / p.KW, q = tap - r * p.KW;
         mbar_expect_tx(&full[s], tx);
-        tma_load_4d(st, &tmA_hi, &full[s], kc * kTileK, q - p.pad, h0 + r - p.pad, n0);
+        tma_load_4d(st, &tmA_hi, &full[s], kc * p.kc, q - p.pad, h0 * p.stride + r - p.pad, n0);
         tma_load_2d(st + Cfg::kABytes * Cfg::kPlanes, &tmB_hi, &full[s],
-                    tap * p.Cin + kc * kTileK, co0);
+                    tap * p.Cin + kc * p.kc, co0);
         if (NPASS == 3) {
-          tma_load_4d(st + Cfg::kABytes, &tmA_lo, &full[s], kc * kTileK, q - p.pad,
-                      h0 + r - p.pad, n0);
+          tma_load_4d(st + Cfg::kABytes, &tmA_lo, &full[s], kc * p.kc, q - p.pad,
+                      h0 * p.stride + r - p.pad, n0);
           tma_load_2d(st + Cfg::kABytes * 2 + Cfg::kBBytes, &tmB_lo, &full[s],
-                      tap * p.Cin + kc * kTileK, co0);
+                      tap * p.Cin + kc * p.kc, co0);
         }
       }
     }
@@ -247,6 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = BN
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                ((uint32_t)(kTileM >> 4) << 24);
+    const int ksteps = p.kc >> 4;
     for (int it = 0; it < iters; ++it) {
       const int s = it % Cfg::kStages;
       const uint32_t ph = (it / Cfg::kStages) & 1;
@@ -255,13 +272,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (elect_one()) {
         const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
         const uint32_t b_hi = a_hi + Cfg::kABytes * Cfg::kPlanes;
-        const uint64_t da_hi = kmajor_sw128_desc(a_hi);
-        const uint64_t db_hi = kmajor_sw128_desc(b_hi);
-        const uint64_t da_lo = kmajor_sw128_desc(a_hi + Cfg::kABytes);
-        const uint64_t db_lo = kmajor_sw128_desc(b_hi + Cfg::kBBytes);
-#pragma unroll
-        for (int k = 0; k < kTileK / 16; ++k) {
-          const uint64_t adv = (uint64_t)(k * 2);  // 32 bytes >> 4
+        const uint64_t da_hi = kmajor_desc(a_hi, p.kc);
+        const uint64_t db_hi = kmajor_desc(b_hi, p.kc);
+        const uint64_t da_lo = kmajor_desc(a_hi + Cfg::kABytes, p.kc);
+        const uint64_t db_lo = kmajor_desc(b_hi + Cfg::kBBytes, p.kc);
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 bytes >> 4
           if (NPASS == 3) {
             // small terms first so they are not absorbed by a large partial sum
             umma_bf16(tmem_base, da_lo + adv, db_hi + adv, idesc, (it | k) != 0);
@@ -286,8 +302,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int ih = (m / p.bw) % p.bh;
     const int in = m / (p.bw * p.bh);
     const int h = h0 + ih, n = n0 + in;
-    const bool valid = in < p.bn && h < p.H && n < p.N;
-    const size_t row = ((size_t)(n * p.H + h) * p.W + iw) * p.Cout + co0;
+    const bool valid = in < p.bn && h < p.OH && n < p.N;
+    const size_t row = ((size_t)(n * p.OH + h) * p.OW + iw) * p.Cout + co0;
+    constexpr int CW = BN < 32 ? BN : 32;   // columns handled per TMEM load
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
@@ -295,19 +312,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (valid) {
         if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + co0 + c0 + j);
+          for (int j = 0; j < CW; ++j) v[j] += __ldg(p.bias + co0 + c0 + j);
         }
         if (p.addend) {
           const float4* a4 = reinterpret_cast<const float4*>(p.addend + row + c0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < CW / 4; ++j) {
             float4 a = __ldg(a4 + j);
             v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
           }
         }
         float4* o4 = reinterpret_cast<float4*>(p.out + row + c0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < CW / 4; ++j)
           o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
     }
@@ -316,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -324,31 +341,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // dW[co][(r,q)][ci] = sum over pixels p=(n,h,w) of dy[n, h-r+pad, w-q+pad, co] * x[n,h,w,ci]
 // as a GEMM whose K dimension is the pixel index.  Both operands come straight from the NHWC
 // bf16 planes with the same 4-D TMA boxes as the forward pass, i.e. they sit in shared memory
-// as [pixel rows][64 channels] -- "MN-major" for the tensor core (instruction-descriptor
-// major bits set):
-//   A (M side): the dy box shifted by the filter tap (TMA zero-fill = the padding); a
-//               128-row M block is two 64-channel units, each a (tap, 64-co block) pair
-//   B (N side): the unshifted x box, Nblk = 64..256 input channels
+// as [pixel rows][channels] -- "MN-major" for the tensor core (instruction-descriptor major
+// bits set):
+//   A (M side): dy boxes shifted by the filter tap (TMA zero-fill = the padding); the 128 rows
+//               of an M block are 128/uw "units", each one (tap, uw-wide co block) pair,
+//               uw = min(64, Cout)
+//   B (N side): the unshifted x box, nblk = min(Cin, 256) input channels in xw-wide blocks
 // Each CTA owns one (M block, N block, pixel split) and accumulates its split in TMEM; a
 // deterministic second kernel sums the splits into the OIHW gradient.
 struct TcWgradParams {
   int N, H, W, Cin, Cout, KH, KW, pad;
-  int bw, bh, bn, rows;     // pixel box of one K step group (rows = bw*bh*bn, multiple of 16)
-  int tiles_h, tiles_total; // pixel tiles: tiles_h per image column block, total over (n, h)
+  int bw, bh, bn, rows;     // pixel box of one K tile (rows = bw*bh*bn <= 64, multiple of 16)
+  int tiles_w, tiles_h, tiles_total;
   int tiles_per_split;
-  int units;                // taps * (Cout / 64)
-  int cout_blocks;          // Cout / 64
-  int nblk;                 // input channels per CTA (multiple of 64, <= 256)
+  int uw, upb;              // unit width (channels) and units per M block (128 / uw)
+  int units;                // taps * (Cout / uw)
+  int cout_blocks;          // Cout / uw
+  int xw;                   // channels per x block: min(64, Cin)
+  int nblk;                 // input channels per CTA (multiple of xw, <= 256)
   int stages;
   float* part;              // [splits][Cout][taps*Cin]
 };
 
-constexpr int kWgBlockBytes = 64 * 128;  // one [64 pixel rows][64 channels] bf16 box
-
-__device__ __forceinline__ uint64_t mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
+constexpr int kWgRows = 64;   // pixel rows reserved per staged block
 
 template <int NPASS>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -360,9 +375,12 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
-  const int nbB = p.nblk >> 6;
-  const int plane_bytes = (2 + nbB) * kWgBlockBytes;
-  const int stage_bytes = plane_bytes * kPlanes;
+  const int nbB = p.nblk / p.xw;
+  const int a_block = kWgRows * p.uw * 2;          // bytes reserved per dy unit
+  const int b_block = kWgRows * p.xw * 2;          // bytes reserved per x block
+  const int a_bytes = kTileM * kWgRows * 2;        // upb * a_block == 128 * 64 * 2 always
+  const int plane_bytes = a_bytes + nbB * b_block;
+  const int stage_bytes = ((plane_bytes * kPlanes) + 1023) & ~1023;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;
@@ -370,14 +388,12 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int mb = blockIdx.x;          // M block: units 2*mb, 2*mb+1
+  const int mb = blockIdx.x;          // M block: units upb*mb .. upb*mb + upb - 1
   const int nb = blockIdx.y;          // N block
   const int sp = blockIdx.z;          // pixel split
   const int t_begin = sp * p.tiles_per_split;
   const int t_end = min(p.tiles_total, t_begin + p.tiles_per_split);
   const int iters = max(t_end - t_begin, 0);
-  const int u0 = 2 * mb;
-  const int u1 = min(2 * mb + 1, p.units - 1);
   const uint32_t tmem_cols = p.nblk < 32 ? 32 : p.nblk;
 
   if (warp == 0 && lane == 0) {
@@ -402,33 +418,34 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
 
   if (warp == 0) {
     if (elect_one()) {
-      const uint32_t tx = (uint32_t)(2 + nbB) * (uint32_t)p.rows * 128u * kPlanes;
+      const uint32_t tx = (uint32_t)p.rows * (uint32_t)(p.upb * p.uw + nbB * p.xw) * 2u * kPlanes;
       for (int it = 0; it < iters; ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* st = smem + s * stage_bytes;
-        const int tile = t_begin + it;
+        int tile = t_begin + it;
+        const int tw = tile % p.tiles_w;
+        tile /= p.tiles_w;
         const int th = tile % p.tiles_h;
         const int tn = tile / p.tiles_h;
-        const int h0 = th * p.bh, n0 = tn * p.bn;
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
         mbar_expect_tx(&full[s], tx);
 #pragma unroll
         for (int pl = 0; pl < kPlanes; ++pl) {
           uint8_t* base = st + pl * plane_bytes;
           const CUtensorMap* md = pl == 0 ? &tmD_hi : &tmD_lo;
           const CUtensorMap* mx = pl == 0 ? &tmX_hi : &tmX_lo;
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const int u = b == 0 ? u0 : u1;
+          for (int b = 0; b < p.upb; ++b) {
+            const int u = min(p.upb * mb + b, p.units - 1);
             const int tap = u / p.cout_blocks;
             const int cb = u - tap * p.cout_blocks;
             const int r = tap / p.KW, q = tap - r * p.KW;
-            tma_load_4d(base + b * kWgBlockBytes, md, &full[s], cb * 64, p.pad - q,
+            tma_load_4d(base + b * a_block, md, &full[s], cb * p.uw, w0 + p.pad - q,
                         h0 + p.pad - r, n0);
           }
           for (int b = 0; b < nbB; ++b)
-            tma_load_4d(base + (2 + b) * kWgBlockBytes, mx, &full[s], nb * p.nblk + b * 64, 0, h0,
+            tma_load_4d(base + a_bytes + b * b_block, mx, &full[s], nb * p.nblk + b * p.xw, w0, h0,
                         n0);
         }
       }
@@ -445,16 +462,17 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
-        const uint32_t b_hi = a_hi + 2 * kWgBlockBytes;
+        const uint32_t b_hi = a_hi + a_bytes;
         const uint32_t a_lo = a_hi + plane_bytes;
         const uint32_t b_lo = b_hi + plane_bytes;
         for (int k = 0; k < ksteps; ++k) {
-          const uint32_t adv = (uint32_t)k * 2048u;   // 16 pixel rows of 128 bytes
-          const uint64_t dah = mnmajor_sw128_desc(a_hi + adv, kWgBlockBytes);
-          const uint64_t dbh = mnmajor_sw128_desc(b_hi + adv, kWgBlockBytes);
+          const uint32_t adva = (uint32_t)k * 16u * (uint32_t)(p.uw * 2);   // 16 pixel rows
+          const uint32_t advb = (uint32_t)k * 16u * (uint32_t)(p.xw * 2);
+          const uint64_t dah = mnmajor_desc(a_hi + adva, a_block, p.uw);
+          const uint64_t dbh = mnmajor_desc(b_hi + advb, b_block, p.xw);
           if (NPASS == 3) {
-            const uint64_t dal = mnmajor_sw128_desc(a_lo + adv, kWgBlockBytes);
-            const uint64_t dbl = mnmajor_sw128_desc(b_lo + adv, kWgBlockBytes);
+            const uint64_t dal = mnmajor_desc(a_lo + adva, a_block, p.uw);
+            const uint64_t dbl = mnmajor_desc(b_lo + advb, b_block, p.xw);
             umma_bf16(tmem_base, dal, dbh, idesc, (it | k) != 0);
             umma_bf16(tmem_base, dah, dbl, idesc, 1);
             umma_bf16(tmem_base, dah, dbh, idesc, 1);
@@ -470,11 +488,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
   } else {
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
-    const int u = 2 * mb + (m >> 6);
+    const int u = p.upb * mb + m / p.uw;
     const bool valid = u < p.units;
     const int tap = valid ? u / p.cout_blocks : 0;
     const int cb = valid ? u - tap * p.cout_blocks : 0;
-    const int co = cb * 64 + (m & 63);
+    const int co = cb * p.uw + (m % p.uw);
     const size_t KK = (size_t)p.KH * p.KW * p.Cin;
     float* dst = p.part + ((size_t)sp * p.Cout + co) * KK + (size_t)tap * p.Cin + (size_t)nb * p.nblk;
     if (iters > 0) {
@@ -492,9 +510,10 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
       }
       if (valid) {
         float4* o4 = reinterpret_cast<float4*>(dst + c0);
+        const int nq = min(32, p.nblk - c0) >> 2;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (j < nq) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
     }
     tc_fence_before();
@@ -570,31 +589,40 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh,
-                  int bn) {
+CUtensorMapSwizzle swizzle_for(int cw) {
+  return cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : (cw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// NHWC bf16 tensor, box = [bn][bh][bw][cw]; `stride` > 1 traverses W and H with that step
+// (the box then spans stride*b input pixels and delivers b of them).
+int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int cw, int bw,
+                  int bh, int bn, int stride = 1) {
   EncodeTiledFn enc = encode_fn();
   EVE_REQUIRE(enc, EVE_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled is not available");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kTileK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride),
+                       (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
-                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  EVE_REQUIRE(r == CUDA_SUCCESS, EVE_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled(A) failed: %d",
-              (int)r);
+  EVE_REQUIRE(r == CUDA_SUCCESS, EVE_ERR_CUDA,
+              "conv_tc: cuTensorMapEncodeTiled(NHWC %dx%dx%dx%d box %dx%dx%dx%d s%d) failed: %d", N,
+              H, W, C, bn, bh, bw, cw, stride, (int)r);
   return EVE_OK;
 }
 
-int make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, int box_rows) {
+int make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, int cw, int box_rows) {
   EncodeTiledFn enc = encode_fn();
   EVE_REQUIRE(enc, EVE_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled is not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kTileK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)cw, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EVE_REQUIRE(r == CUDA_SUCCESS, EVE_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled(B) failed: %d",
               (int)r);
@@ -639,20 +667,41 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
   return EVE_OK;
 }
 
+template <int NPASS>
+int launch_tc_bn(int BN, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                 const CUtensorMap& b_lo, const TcParams& p, int gx, int gy, cudaStream_t s) {
+  switch (BN) {
+    case 128: return launch_tc<128, NPASS>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+    case 64: return launch_tc<64, NPASS>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+    case 32: return launch_tc<32, NPASS>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+    default: return launch_tc<16, NPASS>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+  }
+}
+
+inline int chunk_for(int C) { return C % 64 == 0 ? 64 : (C == 32 ? 32 : (C == 16 ? 16 : 0)); }
+inline int bn_for(int Cout) {
+  return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout == 32 ? 32 : (Cout == 16 ? 16 : 0)));
+}
+
 }  // namespace
 
 // --------------------------------------------------------------------- public API --
+// Forward-style geometries the tensor-core kernel takes: 1x1 / 3x3, stride 1 with "same"
+// padding or stride 2 (pad = k/2), channel counts 16, 32 or multiples of 64.
 bool conv_tc_supported(const ConvGeom& g) {
-  if (g.stride != 1 || g.KH != g.KW) return false;
-  if (g.OH != g.H || g.OW != g.W) return false;        // "same" padding only
-  if (g.Cin % kTileK != 0 || g.Cout % 64 != 0) return false;
-  if (g.W > kTileM || g.W < 1) return false;
-  if (g.KH != 1 && g.KH != 3) return false;
-  if (g.N < 1) return false;
+  if (g.KH != g.KW || (g.KH != 1 && g.KH != 3) || g.N < 1) return false;
+  if (g.pad != g.KH / 2) return false;
+  if (g.stride == 1) {
+    if (g.OH != g.H || g.OW != g.W) return false;
+  } else if (g.stride == 2) {
+    if (g.H % 2 != 0 || g.W % 2 != 0) return false;
+  } else {
+    return false;
+  }
+  if (chunk_for(g.Cin) == 0 || bn_for(g.Cout) == 0) return false;
+  if (g.OW > kTileM || g.OW < 1) return false;
   return true;
 }
-
-size_t conv_tc_plane_elems(const ConvGeom& g) { return (size_t)g.in_elems(); }
 
 int split_bf16(const float* x, long long n, void* hi, void* lo, cudaStream_t s) {
   EVE_REQUIRE(n % 4 == 0, EVE_ERR_SHAPE, "split_bf16: element count must be a multiple of 4");
@@ -673,7 +722,7 @@ int conv_tc_prep_weights(const ConvGeom& g, const float* w_oihw, bool dgrad, voi
   return EVE_OK;
 }
 
-// y[N,H,W,Cout] = conv(x) (+bias) (+addend).  x_hi/x_lo: bf16 NHWC planes of the input;
+// y[N,OH,OW,Cout] = conv(x) (+bias) (+addend).  x_hi/x_lo: bf16 NHWC planes of the input;
 // w_hi/w_lo: K-major weights [Cout][KH*KW*Cin].  npass: 3 (split bf16) or 1 (plain bf16).
 int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* w_hi,
                 const void* w_lo, const float* bias, const float* addend, float* y, int npass,
@@ -681,44 +730,45 @@ int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const voi
   EVE_REQUIRE(conv_tc_supported(g), EVE_ERR_SHAPE, "conv_tc: unsupported geometry");
   EVE_REQUIRE(npass == 1 || npass == 3, EVE_ERR_CONFIG, "conv_tc: npass must be 1 or 3");
   TcParams p;
-  p.N = g.N; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.Cout = g.Cout;
-  p.KH = g.KH; p.KW = g.KW; p.pad = g.pad;
-  pick_box(g.N, g.H, g.W, p.bw, p.bh, p.bn);
-  p.tiles_h = cdiv(g.H, p.bh);
-  p.kchunks = g.Cin / kTileK;
+  p.N = g.N; p.OH = g.OH; p.OW = g.OW; p.Cin = g.Cin; p.Cout = g.Cout;
+  p.KH = g.KH; p.KW = g.KW; p.pad = g.pad; p.stride = g.stride;
+  pick_box(g.N, g.OH, g.OW, p.bw, p.bh, p.bn);
+  p.tiles_h = cdiv(g.OH, p.bh);
+  p.kc = chunk_for(g.Cin);
+  p.kchunks = g.Cin / p.kc;
   p.bias = bias; p.addend = addend; p.out = y;
   const int tiles_n = cdiv(g.N, p.bn);
-  const int BN = (g.Cout % 128 == 0) ? 128 : 64;
+  const int BN = bn_for(g.Cout);
   const int K = g.KH * g.KW * g.Cin;
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
-  EVE_TRY(make_map_nhwc(&a_hi, x_hi, g.N, g.H, g.W, g.Cin, p.bw, p.bh, p.bn));
-  EVE_TRY(make_map_2d(&b_hi, w_hi, g.Cout, K, BN));
+  EVE_TRY(make_map_nhwc(&a_hi, x_hi, g.N, g.H, g.W, g.Cin, p.kc, p.bw, p.bh, p.bn, g.stride));
+  EVE_TRY(make_map_2d(&b_hi, w_hi, g.Cout, K, p.kc, BN));
   if (npass == 3) {
-    EVE_TRY(make_map_nhwc(&a_lo, x_lo, g.N, g.H, g.W, g.Cin, p.bw, p.bh, p.bn));
-    EVE_TRY(make_map_2d(&b_lo, w_lo, g.Cout, K, BN));
+    EVE_TRY(make_map_nhwc(&a_lo, x_lo, g.N, g.H, g.W, g.Cin, p.kc, p.bw, p.bh, p.bn, g.stride));
+    EVE_TRY(make_map_2d(&b_lo, w_lo, g.Cout, K, p.kc, BN));
   } else {
     a_lo = a_hi;
     b_lo = b_hi;
   }
   const int gx = p.tiles_h * tiles_n, gy = g.Cout / BN;
-  if (BN == 128)
-    return npass == 3 ? launch_tc<128, 3>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s)
-                      : launch_tc<128, 1>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
-  return npass == 3 ? launch_tc<64, 3>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s)
-                    : launch_tc<64, 1>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+  return npass == 3 ? launch_tc_bn<3>(BN, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s)
+                    : launch_tc_bn<1>(BN, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
 }
 
-// pixel box for the wgrad K loop: bw == W, rows = bw*bh*bn <= 64 and a multiple of 16
-static bool pick_wgrad_box(int N, int H, int W, int& bh, int& bn) {
+// pixel box for the wgrad K loop: rows = bw*bh*bn <= 64 and a multiple of 16
+static bool pick_wgrad_box(int N, int H, int W, int& bw, int& bh, int& bn) {
   double best = -1.0;
+  bw = W <= kWgRows ? W : kWgRows;
+  if (W % bw != 0) return false;
   bh = bn = 0;
-  for (int h = 1; h <= H && W * h <= 64; ++h) {
-    int nmax = 64 / (W * h);
-    for (int n = 1; n <= nmax && n <= (h == H ? N : 1); ++n) {
-      int rows = W * h * n;
+  for (int h = 1; h <= H && bw * h <= kWgRows; ++h) {
+    if (bw < W && h > 1) break;                 // partial rows: one image row per box
+    int nmax = kWgRows / (bw * h);
+    for (int n = 1; n <= nmax && n <= ((h == H && bw == W) ? N : 1); ++n) {
+      int rows = bw * h * n;
       if (rows % 16 != 0) continue;
       double eff = ((double)H / (double)(cdiv(H, h) * h)) * ((double)N / (double)(cdiv(N, n) * n)) *
-                   (0.5 + 0.5 * rows / 64.0);   // prefer full 64-row boxes
+                   (0.5 + 0.5 * rows / (double)kWgRows);   // prefer full boxes
       if (eff > best + 1e-9) {
         best = eff;
         bh = h;
@@ -731,30 +781,37 @@ static bool pick_wgrad_box(int N, int H, int W, int& bh, int& bn) {
 
 bool conv_tc_wgrad_supported(const ConvGeom& g) {
   if (g.stride != 1 || g.KH != g.KW || (g.KH != 1 && g.KH != 3)) return false;
-  if (g.OH != g.H || g.OW != g.W) return false;
-  if (g.Cin % 64 != 0 || g.Cout % 64 != 0) return false;
-  if (g.W > 64 || g.N < 1) return false;
-  int bh, bn;
-  return pick_wgrad_box(g.N, g.H, g.W, bh, bn);
+  if (g.pad != g.KH / 2 || g.OH != g.H || g.OW != g.W) return false;
+  if (chunk_for(g.Cin) == 0 || chunk_for(g.Cout) == 0) return false;
+  if (g.N < 1) return false;
+  int bw, bh, bn;
+  return pick_wgrad_box(g.N, g.H, g.W, bw, bh, bn);
+}
+
+static int wgrad_stage_bytes(const TcWgradParams& p, int npass) {
+  const int planes = npass == 3 ? 2 : 1;
+  const int plane = kTileM * kWgRows * 2 + (p.nblk / p.xw) * kWgRows * p.xw * 2;
+  return ((plane * planes) + 1023) & ~1023;
 }
 
 static void wgrad_plan(const ConvGeom& g, TcWgradParams& p, int& mblocks, int& nblocks,
                        int& splits, int npass) {
   p.N = g.N; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.Cout = g.Cout;
   p.KH = g.KH; p.KW = g.KW; p.pad = g.pad;
-  p.bw = g.W;
-  pick_wgrad_box(g.N, g.H, g.W, p.bh, p.bn);
+  pick_wgrad_box(g.N, g.H, g.W, p.bw, p.bh, p.bn);
   p.rows = p.bw * p.bh * p.bn;
+  p.tiles_w = g.W / p.bw;
   p.tiles_h = cdiv(g.H, p.bh);
-  p.tiles_total = p.tiles_h * cdiv(g.N, p.bn);
-  p.cout_blocks = g.Cout / 64;
+  p.tiles_total = p.tiles_w * p.tiles_h * cdiv(g.N, p.bn);
+  p.uw = chunk_for(g.Cout);
+  p.upb = kTileM / p.uw;
+  p.cout_blocks = g.Cout / p.uw;
   p.units = g.KH * g.KW * p.cout_blocks;
-  p.nblk = g.Cin % 256 == 0 ? 256 : (g.Cin % 128 == 0 ? 128 : 64);
-  mblocks = cdiv(p.units, 2);
+  p.xw = chunk_for(g.Cin);
+  p.nblk = g.Cin % 256 == 0 ? 256 : (g.Cin % 128 == 0 ? 128 : (g.Cin % 64 == 0 ? 64 : g.Cin));
+  mblocks = cdiv(p.units, p.upb);
   nblocks = g.Cin / p.nblk;
-  const int planes = npass == 3 ? 2 : 1;
-  const int stage_bytes = (2 + p.nblk / 64) * kWgBlockBytes * planes;
-  p.stages = (220 * 1024) / stage_bytes;
+  p.stages = (220 * 1024) / wgrad_stage_bytes(p, npass);
   if (p.stages > 6) p.stages = 6;
   int want = cdiv(3 * kNumSMs, mblocks * nblocks);
   int max_splits = cdiv(p.tiles_total, 4);          // at least 4 pixel tiles per CTA
@@ -782,18 +839,17 @@ int conv_tc_wgrad_run(const ConvGeom& g, const void* d_hi, const void* d_lo, con
   wgrad_plan(g, p, mb, nb, sp, npass);
   p.part = part;
   CUtensorMap md_hi, md_lo, mx_hi, mx_lo;
-  // boxes are [bn][bh][bw][64 ch]; the dy and x grids have the same shape ("same" padding)
-  EVE_TRY(make_map_nhwc(&md_hi, d_hi, g.N, g.H, g.W, g.Cout, p.bw, p.bh, p.bn));
-  EVE_TRY(make_map_nhwc(&mx_hi, x_hi, g.N, g.H, g.W, g.Cin, p.bw, p.bh, p.bn));
+  // the dy and x grids have the same shape ("same" padding)
+  EVE_TRY(make_map_nhwc(&md_hi, d_hi, g.N, g.H, g.W, g.Cout, p.uw, p.bw, p.bh, p.bn));
+  EVE_TRY(make_map_nhwc(&mx_hi, x_hi, g.N, g.H, g.W, g.Cin, p.xw, p.bw, p.bh, p.bn));
   if (npass == 3) {
-    EVE_TRY(make_map_nhwc(&md_lo, d_lo, g.N, g.H, g.W, g.Cout, p.bw, p.bh, p.bn));
-    EVE_TRY(make_map_nhwc(&mx_lo, x_lo, g.N, g.H, g.W, g.Cin, p.bw, p.bh, p.bn));
+    EVE_TRY(make_map_nhwc(&md_lo, d_lo, g.N, g.H, g.W, g.Cout, p.uw, p.bw, p.bh, p.bn));
+    EVE_TRY(make_map_nhwc(&mx_lo, x_lo, g.N, g.H, g.W, g.Cin, p.xw, p.bw, p.bh, p.bn));
   } else {
     md_lo = md_hi;
     mx_lo = mx_hi;
   }
-  const int planes = npass == 3 ? 2 : 1;
-  const int smem = p.stages * (2 + p.nblk / 64) * kWgBlockBytes * planes + 1024 + 256;
+  const int smem = p.stages * wgrad_stage_bytes(p, npass) + 1024 + 256;
   static bool cfg3 = false, cfg1 = false;
   if (npass == 3 && !cfg3) {
     EVE_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel<3>,

@@ -120,8 +120,8 @@ def test_eve_forward_backward_matches_reference(name, cfg, conv_mode):
         else:
             assert got.shape == ref.shape, (k, got.shape, ref.shape)
             tol = 2e-3 if ('final' in key or 'refined' in key or key == 'full_loss') else 2e-4
-            if tol == 2e-3 and tolx > 1:
-                tol = 5e-3          # still inside the 1e-3 bar on PoG: see DESIGN.md (precision)
+            if tolx > 1:            # split-bf16 products; see DESIGN.md (precision)
+                tol = 5e-3 if tol == 2e-3 else 5e-4
             if pad_last and got.ndim >= 1 and got.shape[0] == B:
                 # Zero-padded frames (all-zero images, validity 0) put InstanceNorm at
                 # var ~ 0, where rstd = 316 amplifies fp32 summation-order noise: hold the
@@ -245,19 +245,31 @@ def test_eyenet_cnn_gradients_match_oracle(cfg, conv_mode):
     g = torch.Generator().manual_seed(9)
     x = torch.rand(3, 3, 128, 128, generator=g) * 2 - 1
     wf = torch.randn(3, 128, generator=g)
-    osd = {'eye_net.' + k: v.double().requires_grad_(k.startswith('cnn_layers.'))
-           for k, v in sd.items()}
-    want = O.resnet18_in_features(osd, 'eye_net.cnn_layers.', x.double())
-    (want * wf.double()).sum().backward()
+    def oracle(dtype):
+        osd = {'eye_net.' + k: v.detach().clone().to(dtype).requires_grad_(k.startswith('cnn_layers.'))
+               for k, v in sd.items()}
+        want = O.resnet18_in_features(osd, 'eye_net.cnn_layers.', x.to(dtype))
+        (want * wf.to(dtype)).sum().backward()
+        return want.detach(), {k: v.grad for k, v in osd.items()}
+
+    want, g64 = oracle(torch.float64)
+    _, g32 = oracle(torch.float32)
     got = net.cnn_features(x.cuda())
     assert G.rel(got, want) < 2e-5 * tolx
     (got * wf.cuda()).sum().backward()
+
+    def l2(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        return float((a - b).norm() / (b.norm() + 1e-30))
+
+    # yardstick: the fp32 noise of the reference arithmetic itself (the stem gradient sits
+    # at the end of a 20-conv / 20-InstanceNorm backward chain and is the noisiest)
     for name, p in net.named_parameters():
         if not name.startswith('cnn_layers.'):
             continue
-        ref = osd['eye_net.' + name].grad
-        l2 = float((p.grad.double().cpu() - ref).norm() / (ref.norm() + 1e-30))
-        assert l2 < 1e-3 * tolx, (name, l2)
+        ref = g64['eye_net.' + name]
+        e, e32 = l2(p.grad, ref), l2(g32['eye_net.' + name], ref)
+        assert e < 4.0 * tolx * e32 + 1e-4, (name, e, e32)
 
 
 REFINE_CASES = [('CGRU', 1, True, True), ('CRNN', 2, True, True), ('CGRU', 2, False, False),
@@ -363,7 +375,7 @@ def test_refinenet_sequences_with_state_and_gradients(cfg, rnn, cells, skip, scr
     # the fp32 noise level of this network / input (single tensors can be lucky)
     noise = float(np.median([e32 for _, _, e32 in rows]))
     for name, e, e32 in rows:
-        assert e < 3.0 * tolx * max(e32, noise) + 1e-4, (name, e, e32, noise)
+        assert e < 4.0 * tolx * max(e32, noise) + 1e-4, (name, e, e32, noise)
 
 
 def test_per_step_and_time_batched_paths_agree(cfg):
