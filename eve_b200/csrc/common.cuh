@@ -120,12 +120,15 @@ size_t colsum_scratch_floats(long long rows, int C);
 
 // --------------------------------------------------------------------- conv (tcgen05) --
 bool conv_tc_supported(const ConvGeom& g);
-int split_bf16(const float* x, long long n, void* hi, void* lo, cudaStream_t s);
+// operand planes: fmt 1 = bf16 (fp32 exponent range: gradients), fmt 0 = fp16 (11-bit mantissa:
+// forward activations, which the normalisations keep far below 65504)
+enum TcFormat { TC_F16 = 0, TC_BF16 = 1 };
+int split_planes(const float* x, long long n, void* hi, void* lo, int fmt, cudaStream_t s);
 int conv_tc_prep_weights(const ConvGeom& g, const float* w_oihw, bool dgrad, void* hi, void* lo,
-                         cudaStream_t s);
+                         int fmt, float scale, cudaStream_t s);
 int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* w_hi,
                 const void* w_lo, const float* bias, const float* addend, float* y, int npass,
-                cudaStream_t s);
+                int fmt, float out_scale, cudaStream_t s);
 
 bool conv_tc_wgrad_supported(const ConvGeom& g);
 size_t conv_tc_wgrad_partial_floats(const ConvGeom& g);

@@ -30,6 +30,17 @@ ConvGeom dgrad_as_fwd(const ConvGeom& g) {
 }
 }  // namespace
 
+// debugging aid: EVE_B200_TC_MASK selects which passes may use the tensor-core kernels
+// (bit 0 forward, bit 1 data gradient, bit 2 weight gradient; default all)
+static int tc_mask() {
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("EVE_B200_TC_MASK");
+    m = e ? atoi(e) : 7;
+  }
+  return m;
+}
+
 int conv_mode() {
   if (g_mode < 0) {
     const char* e = getenv("EVE_B200_CONV_MODE");
@@ -60,18 +71,23 @@ int conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* bia
   Carve c{sc.base, sc.base + sc.bytes};
   const size_t wel = (size_t)g.Cout * g.K();
   const int mode = conv_mode();
-  if (mode != 0 && conv_tc_supported(g)) {
+  if (mode != 0 && (tc_mask() & 1) && conv_tc_supported(g)) {
     const int npass = mode == 1 ? 3 : 1;
     uint16_t* w_hi = c.get<uint16_t>(wel);
     uint16_t* w_lo = c.get<uint16_t>(wel);
     uint16_t* x_hi = c.get<uint16_t>((size_t)g.in_elems());
     uint16_t* x_lo = c.get<uint16_t>((size_t)g.in_elems());
     EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_fwd: scratch too small");
-    EVE_TRY(conv_tc_prep_weights(g, w, false, w_hi, npass == 3 ? w_lo : nullptr, s));
-    EVE_TRY(split_bf16(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, s));
+    // forward, split mode: fp16 planes (22 mantissa bits for hi + lo); weights pre-scaled by
+    // 2^6 so that their lo parts stay normal, undone exactly in the epilogue.  The single-pass
+    // mode keeps bf16.
+    const int fmt = npass == 3 ? TC_F16 : TC_BF16;
+    const float wscale = npass == 3 ? 64.f : 1.f;
+    EVE_TRY(conv_tc_prep_weights(g, w, false, w_hi, npass == 3 ? w_lo : nullptr, fmt, wscale, s));
+    EVE_TRY(split_planes(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, fmt, s));
     ProfScope prof(PROF_CONV_FWD, 2.0 * g.out_elems() * (double)g.K(),
                    4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
-    return conv_tc_run(g, x_hi, x_lo, w_hi, w_lo, bias, addend, y, npass, s);
+    return conv_tc_run(g, x_hi, x_lo, w_hi, w_lo, bias, addend, y, npass, fmt, 1.f / wscale, s);
   }
   float* wf = c.get<float>(wel);
   EVE_REQUIRE(wf, EVE_ERR_WORKSPACE, "conv_fwd: scratch too small");
@@ -84,7 +100,7 @@ int conv_dgrad(const ConvGeom& g, const float* dy, const float* w, const float* 
   Carve c{sc.base, sc.base + sc.bytes};
   const size_t wel = (size_t)g.Cout * g.K();
   const int mode = conv_mode();
-  if (mode != 0 && g.stride == 1) {
+  if (mode != 0 && (tc_mask() & 2) && g.stride == 1) {
     ConvGeom f = dgrad_as_fwd(g);
     if (conv_tc_supported(f) && f.OH == g.H && f.OW == g.W) {
       const int npass = mode == 1 ? 3 : 1;
@@ -93,11 +109,11 @@ int conv_dgrad(const ConvGeom& g, const float* dy, const float* w, const float* 
       uint16_t* d_hi = c.get<uint16_t>((size_t)g.out_elems());
       uint16_t* d_lo = c.get<uint16_t>((size_t)g.out_elems());
       EVE_REQUIRE(d_lo, EVE_ERR_WORKSPACE, "conv_dgrad: scratch too small");
-      EVE_TRY(conv_tc_prep_weights(g, w, true, w_hi, npass == 3 ? w_lo : nullptr, s));
-      EVE_TRY(split_bf16(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, s));
+      EVE_TRY(conv_tc_prep_weights(g, w, true, w_hi, npass == 3 ? w_lo : nullptr, TC_BF16, 1.f, s));
+      EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
       ProfScope prof(PROF_CONV_DGRAD, 2.0 * g.out_elems() * (double)g.K(),
                      4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
-      return conv_tc_run(f, d_hi, d_lo, w_hi, w_lo, nullptr, addend, dx, npass, s);
+      return conv_tc_run(f, d_hi, d_lo, w_hi, w_lo, nullptr, addend, dx, npass, TC_BF16, 1.f, s);
     }
   }
   float* wd = c.get<float>(wel);
@@ -110,7 +126,7 @@ int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, fl
                bool accumulate, const ConvScratch& sc, cudaStream_t s) {
   Carve c{sc.base, sc.base + sc.bytes};
   const int mode = conv_mode();
-  if (dw && mode != 0 && conv_tc_wgrad_supported(g)) {
+  if (dw && mode != 0 && (tc_mask() & 4) && conv_tc_wgrad_supported(g)) {
     const int npass = mode == 1 ? 3 : 1;
     size_t pf = conv_tc_wgrad_partial_floats(g);
     size_t cs = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
@@ -120,8 +136,8 @@ int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, fl
     uint16_t* x_hi = c.get<uint16_t>((size_t)g.in_elems());
     uint16_t* x_lo = c.get<uint16_t>((size_t)g.in_elems());
     EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_wgrad: scratch too small");
-    EVE_TRY(split_bf16(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, s));
-    EVE_TRY(split_bf16(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, s));
+    EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
+    EVE_TRY(split_planes(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, TC_BF16, s));
     int splits = 0;
     {
       ProfScope prof(PROF_CONV_WGRAD, 2.0 * g.out_elems() * (double)g.K(),

@@ -18,6 +18,7 @@
 //    epilogue (TMEM -> registers -> +bias/+addend -> fp32 NHWC global).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -166,6 +167,8 @@ struct TcParams {
   int tiles_h;              // ceil(OH / bh)
   int kc;                   // channels per K chunk: 64, 32 or 16
   int kchunks;              // Cin / kc
+  int fmt;                  // operand format: 0 = fp16 planes, 1 = bf16 planes
+  float out_scale;          // accumulator scale undoing the weight pre-scale (fp16 planes)
   const float* bias;        // [Cout] or null
   const float* addend;      // [N,OH,OW,Cout] or null
   float* out;               // [N,OH,OW,Cout]
@@ -261,8 +264,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = BN
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                               ((uint32_t)(kTileM >> 4) << 24);
+    // (A/B format field: 0 = fp16, 1 = bf16)
+    const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const int ksteps = p.kc >> 4;
     for (int it = 0; it < iters; ++it) {
       const int s = it % Cfg::kStages;
@@ -310,6 +314,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
       if (valid) {
+        if (p.out_scale != 1.f) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) v[j] *= p.out_scale;
+        }
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < CW; ++j) v[j] += __ldg(p.bias + co0 + c0 + j);
@@ -543,11 +551,31 @@ split_bf16_kernel(const float* __restrict__ x, long long n4, __nv_bfloat16* __re
   if (lo) reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
 }
 
+// fp16 variant for forward activations (bounded by the normalisations: |x| << 65504):
+// hi + lo carries 22 mantissa bits instead of bf16's 16.
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ x, long long n4, __half* __restrict__ hi,
+                 __half* __restrict__ lo) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+  float f[4] = {v.x, v.y, v.z, v.w};
+  __half h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2half_rn(f[j]);
+    l[j] = __float2half_rn(f[j] - __half2float(h[j]));
+  }
+  reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+  if (lo) reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+}
+
 // OIHW fp32 -> K-major bf16 hi/lo.  flip == 0: forward  Wk[co][(r*KW+q)*Cin + ci]
 //                                  flip == 1: dgrad    Wk[ci][((KH-1-r)*KW + (KW-1-q))*Cout + co]
 __global__ void __launch_bounds__(256)
 prep_weights_tc_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int flip,
-                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                       int fmt, float scale, uint16_t* __restrict__ hi,
+                       uint16_t* __restrict__ lo) {
   size_t total = (size_t)Cout * Cin * KH * KW;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -563,9 +591,16 @@ prep_weights_tc_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, i
     o = (size_t)co * ((size_t)KH * KW * Cin) + (size_t)(r * KW + q) * Cin + ci;
   else
     o = (size_t)ci * ((size_t)KH * KW * Cout) + (size_t)((KH - 1 - r) * KW + (KW - 1 - q)) * Cout + co;
-  __nv_bfloat16 h = __float2bfloat16_rn(v);
-  hi[o] = h;
-  if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+  if (fmt == 1) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[o] = __bfloat16_as_ushort(h);
+    if (lo) lo[o] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+  } else {
+    v *= scale;   // power of two: keeps hi and lo in fp16's normal range, undone in the epilogue
+    __half h = __float2half_rn(v);
+    hi[o] = __half_as_ushort(h);
+    if (lo) lo[o] = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+  }
 }
 
 // ------------------------------------------------------------------ host helpers --
@@ -597,7 +632,7 @@ CUtensorMapSwizzle swizzle_for(int cw) {
 // NHWC bf16 tensor, box = [bn][bh][bw][cw]; `stride` > 1 traverses W and H with that step
 // (the box then spans stride*b input pixels and delivers b of them).
 int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int cw, int bw,
-                  int bh, int bn, int stride = 1) {
+                  int bh, int bn, int stride = 1, int fmt = 1) {
   EncodeTiledFn enc = encode_fn();
   EVE_REQUIRE(enc, EVE_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled is not available");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -605,8 +640,9 @@ int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
   cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride),
                        (cuuint32_t)bn};
   cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
-                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw),
+  CUresult r = enc(m, fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                   4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EVE_REQUIRE(r == CUDA_SUCCESS, EVE_ERR_CUDA,
               "conv_tc: cuTensorMapEncodeTiled(NHWC %dx%dx%dx%d box %dx%dx%dx%d s%d) failed: %d", N,
@@ -614,15 +650,17 @@ int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
   return EVE_OK;
 }
 
-int make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, int cw, int box_rows) {
+int make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, int cw, int box_rows,
+                int fmt = 1) {
   EncodeTiledFn enc = encode_fn();
   EVE_REQUIRE(enc, EVE_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled is not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
   cuuint32_t box[2] = {(cuuint32_t)cw, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw),
+  CUresult r = enc(m, fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                   2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EVE_REQUIRE(r == CUDA_SUCCESS, EVE_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled(B) failed: %d",
               (int)r);
@@ -703,21 +741,24 @@ bool conv_tc_supported(const ConvGeom& g) {
   return true;
 }
 
-int split_bf16(const float* x, long long n, void* hi, void* lo, cudaStream_t s) {
-  EVE_REQUIRE(n % 4 == 0, EVE_ERR_SHAPE, "split_bf16: element count must be a multiple of 4");
+int split_planes(const float* x, long long n, void* hi, void* lo, int fmt, cudaStream_t s) {
+  EVE_REQUIRE(n % 4 == 0, EVE_ERR_SHAPE, "split_planes: element count must be a multiple of 4");
   long long n4 = n / 4;
   if (n4 == 0) return EVE_OK;
-  split_bf16_kernel<<<cdiv(n4, 256), 256, 0, s>>>(x, n4, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  if (fmt == 1)
+    split_bf16_kernel<<<cdiv(n4, 256), 256, 0, s>>>(x, n4, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  else
+    split_f16_kernel<<<cdiv(n4, 256), 256, 0, s>>>(x, n4, (__half*)hi, (__half*)lo);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }
 
 int conv_tc_prep_weights(const ConvGeom& g, const float* w_oihw, bool dgrad, void* hi, void* lo,
-                         cudaStream_t s) {
+                         int fmt, float scale, cudaStream_t s) {
   size_t total = (size_t)g.Cout * g.Cin * g.KH * g.KW;
   prep_weights_tc_kernel<<<cdiv(total, 256), 256, 0, s>>>(w_oihw, g.Cout, g.Cin, g.KH, g.KW,
-                                                          dgrad ? 1 : 0, (__nv_bfloat16*)hi,
-                                                          (__nv_bfloat16*)lo);
+                                                          dgrad ? 1 : 0, fmt, scale, (uint16_t*)hi,
+                                                          (uint16_t*)lo);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }
@@ -726,7 +767,7 @@ int conv_tc_prep_weights(const ConvGeom& g, const float* w_oihw, bool dgrad, voi
 // w_hi/w_lo: K-major weights [Cout][KH*KW*Cin].  npass: 3 (split bf16) or 1 (plain bf16).
 int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* w_hi,
                 const void* w_lo, const float* bias, const float* addend, float* y, int npass,
-                cudaStream_t s) {
+                int fmt, float out_scale, cudaStream_t s) {
   EVE_REQUIRE(conv_tc_supported(g), EVE_ERR_SHAPE, "conv_tc: unsupported geometry");
   EVE_REQUIRE(npass == 1 || npass == 3, EVE_ERR_CONFIG, "conv_tc: npass must be 1 or 3");
   TcParams p;
@@ -737,15 +778,17 @@ int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const voi
   p.kc = chunk_for(g.Cin);
   p.kchunks = g.Cin / p.kc;
   p.bias = bias; p.addend = addend; p.out = y;
+  p.fmt = fmt; p.out_scale = out_scale;
   const int tiles_n = cdiv(g.N, p.bn);
   const int BN = bn_for(g.Cout);
   const int K = g.KH * g.KW * g.Cin;
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
-  EVE_TRY(make_map_nhwc(&a_hi, x_hi, g.N, g.H, g.W, g.Cin, p.kc, p.bw, p.bh, p.bn, g.stride));
-  EVE_TRY(make_map_2d(&b_hi, w_hi, g.Cout, K, p.kc, BN));
+  EVE_TRY(make_map_nhwc(&a_hi, x_hi, g.N, g.H, g.W, g.Cin, p.kc, p.bw, p.bh, p.bn, g.stride, fmt));
+  EVE_TRY(make_map_2d(&b_hi, w_hi, g.Cout, K, p.kc, BN, fmt));
   if (npass == 3) {
-    EVE_TRY(make_map_nhwc(&a_lo, x_lo, g.N, g.H, g.W, g.Cin, p.kc, p.bw, p.bh, p.bn, g.stride));
-    EVE_TRY(make_map_2d(&b_lo, w_lo, g.Cout, K, p.kc, BN));
+    EVE_TRY(make_map_nhwc(&a_lo, x_lo, g.N, g.H, g.W, g.Cin, p.kc, p.bw, p.bh, p.bn, g.stride,
+                          fmt));
+    EVE_TRY(make_map_2d(&b_lo, w_lo, g.Cout, K, p.kc, BN, fmt));
   } else {
     a_lo = a_hi;
     b_lo = b_hi;

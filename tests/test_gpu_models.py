@@ -21,14 +21,15 @@ from tests import helpers as H           # noqa: E402
 @pytest.fixture(params=[0, 1], ids=['fp32-simt', 'tcgen05-bf16x3'])
 def conv_mode(request):
     """Run under both kernel selections: 0 = fp32 CUDA cores everywhere (exact products),
-    1 = tcgen05 split-bf16 (the default product path).  Yields a tolerance multiplier: the
-    split-bf16 products carry ~2^-17 relative representation error instead of fp32's 2^-24,
-    which InstanceNorm over nearly constant maps (RefineNet at random weights) amplifies."""
+    1 = tcgen05 split operands (the default product path: forward convolutions on fp16
+    hi + lo planes = 22 mantissa bits, gradients on bf16 hi + lo planes).  Yields a tolerance
+    multiplier: measured, mode 1 sits at 1.5-3x the fp32 noise of the reference arithmetic
+    itself on RefineNet heatmaps / states and at 4e-6 on EyeNet features."""
     from eve_b200 import lib as L
     lib = L.load()
     prev = lib.eve_get_conv_mode()
     lib.eve_set_conv_mode(request.param)
-    yield {0: 1.0, 1: 5.0}[request.param]
+    yield {0: 1.0, 1: 3.0}[request.param]
     lib.eve_set_conv_mode(prev)
 
 
@@ -120,8 +121,8 @@ def test_eve_forward_backward_matches_reference(name, cfg, conv_mode):
         else:
             assert got.shape == ref.shape, (k, got.shape, ref.shape)
             tol = 2e-3 if ('final' in key or 'refined' in key or key == 'full_loss') else 2e-4
-            if tolx > 1:            # split-bf16 products; see DESIGN.md (precision)
-                tol = 5e-3 if tol == 2e-3 else 5e-4
+            if tolx > 1:            # split-operand products; see DESIGN.md (precision)
+                tol = 4e-3 if tol == 2e-3 else 4e-4
             if pad_last and got.ndim >= 1 and got.shape[0] == B:
                 # Zero-padded frames (all-zero images, validity 0) put InstanceNorm at
                 # var ~ 0, where rstd = 316 amplifies fp32 summation-order noise: hold the
