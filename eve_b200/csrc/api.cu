@@ -71,7 +71,7 @@ static int check_conv(const eve_conv_params* p, ConvGeom& g) {
 }
 
 static size_t conv_ws_bytes(const ConvGeom& g) {
-  return conv_scratch_bytes((size_t)g.in_elems(), (size_t)g.out_elems(), (size_t)g.Cout * g.K(),
+  return conv_scratch_bytes(conv_operand_elems(g), (size_t)g.out_elems(), (size_t)g.Cout * g.K(),
                             conv_partial_floats(g));
 }
 

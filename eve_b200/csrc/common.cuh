@@ -130,6 +130,10 @@ int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const voi
                 const void* w_lo, const float* bias, const float* addend, float* y, int npass,
                 int fmt, float out_scale, cudaStream_t s);
 
+bool conv_tc_dgrad_s2_supported(const ConvGeom& g);
+int conv_tc_dgrad_s2_run(const ConvGeom& g, const void* d_hi, const void* d_lo, const void* w_hi,
+                         const void* w_lo, const float* addend, float* dx, int npass,
+                         cudaStream_t s);
 bool conv_tc_wgrad_supported(const ConvGeom& g);
 size_t conv_tc_wgrad_partial_floats(const ConvGeom& g);
 int conv_tc_wgrad_run(const ConvGeom& g, const void* d_hi, const void* d_lo, const void* x_hi,
@@ -156,6 +160,9 @@ size_t conv_scratch_bytes(size_t max_in_elems, size_t max_out_elems, size_t max_
                           size_t wgrad_partial_floats);
 // split-K partial / bias-reduction floats the weight gradient of `g` may need (any kernel)
 size_t conv_partial_floats(const ConvGeom& g);
+// largest operand (elements) any pass of `g` stages as 16-bit planes (covers the stem's
+// materialised patch matrix)
+size_t conv_operand_elems(const ConvGeom& g);
 int conv_fwd(const ConvGeom& g, const float* x, const float* w_oihw, const float* bias,
              const float* addend, float* y, const ConvScratch& sc, cudaStream_t s);
 int conv_dgrad(const ConvGeom& g, const float* dy, const float* w_oihw, const float* addend,

@@ -4,12 +4,102 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace eve {
 
 namespace {
 int g_mode = -1;
+
+// ---------------------------------------------------------------- stem (7x7, Cin = 3) --
+// torchvision ResNet.conv1 (eye_net.py:48-50): K = 7*7*3 = 147 is too thin for a TMA box per
+// tap, so the patch matrix is materialised once ([pixels][192] 16-bit hi/lo planes, K padded
+// with zeros) and the convolution / its weight gradient run as 1x1 tensor-core GEMMs.
+constexpr int kStemK = 192;
+
+__device__ __forceinline__ void split16(float v, int fmt, uint16_t& h, uint16_t& l) {
+  if (fmt == TC_BF16) {
+    __nv_bfloat16 hb = __float2bfloat16_rn(v);
+    h = __bfloat16_as_ushort(hb);
+    l = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hb)));
+  } else {
+    __half hh = __float2half_rn(v);
+    h = __half_as_ushort(hh);
+    l = __half_as_ushort(__float2half_rn(v - __half2float(hh)));
+  }
+}
+
+// one thread = one output pixel x 8 consecutive k (one 16-byte store per plane)
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ x, long long total, int H, int W, int OH, int OW,
+                   int fmt, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int kg = (int)(i % (kStemK / 8));
+  long long pix = i / (kStemK / 8);
+  const int ox = (int)(pix % OW);
+  long long t = pix / OW;
+  const int oy = (int)(t % OH);
+  const int n = (int)(t / OH);
+  const float* xp = x + (size_t)n * H * W * 3;
+  uint16_t h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = kg * 8 + j;
+    float v = 0.f;
+    if (k < 147) {
+      const int tap = k / 3, c = k - tap * 3;
+      const int r = tap / 7, q = tap - r * 7;
+      const int iy = oy * 2 + r - 3, ix = ox * 2 + q - 3;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xp + ((size_t)iy * W + ix) * 3 + c);
+    }
+    split16(v, fmt, h[j], l[j]);
+  }
+  reinterpret_cast<uint4*>(hi)[i] = *reinterpret_cast<uint4*>(h);
+  if (lo) reinterpret_cast<uint4*>(lo)[i] = *reinterpret_cast<uint4*>(l);
+}
+
+// OIHW [64][3][7][7] -> [64][192] (k = (r*7+q)*3 + c, zero padded)
+__global__ void stem_prep_weights_kernel(const float* __restrict__ w, int Cout, int fmt,
+                                         float scale, uint16_t* __restrict__ hi,
+                                         uint16_t* __restrict__ lo) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * kStemK) return;
+  const int k = i % kStemK, co = i / kStemK;
+  float v = 0.f;
+  if (k < 147) {
+    const int tap = k / 3, c = k - tap * 3;
+    v = w[((size_t)co * 3 + c) * 49 + tap] * scale;
+  }
+  uint16_t h, l;
+  split16(v, fmt, h, l);
+  hi[i] = h;
+  if (lo) lo[i] = l;
+}
+
+// dw_oihw[co][c][r][q] (+)= sum_z part[z][co][(r*7+q)*3 + c]
+__global__ void stem_wgrad_reduce_kernel(const float* __restrict__ part, int S, int Cout,
+                                         float* __restrict__ dw, int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * 147) return;
+  const int tap = i % 49;
+  const int c = (i / 49) % 3;
+  const int co = i / 147;
+  float a = 0.f;
+  for (int z = 0; z < S; ++z) a += part[((size_t)z * Cout + co) * kStemK + tap * 3 + c];
+  dw[i] = accumulate ? dw[i] + a : a;
+}
+
+inline bool is_stem(const ConvGeom& g) {
+  return g.KH == 7 && g.KW == 7 && g.stride == 2 && g.pad == 3 && g.Cin == 3 && g.Cout == 64 &&
+         g.OW <= 64 && g.OW >= 1;
+}
+inline ConvGeom stem_gemm(const ConvGeom& g) {
+  return make_conv(g.N, g.OH, g.OW, kStemK, g.Cout, 1, 1, 0);
+}
 
 struct Carve {
   char* p;
@@ -63,7 +153,14 @@ size_t conv_partial_floats(const ConvGeom& g) {
   size_t a = conv_wgrad_scratch_floats(g);
   size_t b = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
   size_t c = conv_tc_wgrad_partial_floats(g);
+  if (is_stem(g)) c = std::max(c, conv_tc_wgrad_partial_floats(stem_gemm(g)));
   return std::max(a, std::max(b, c));
+}
+
+size_t conv_operand_elems(const ConvGeom& g) {
+  size_t m = std::max((size_t)g.in_elems(), (size_t)g.out_elems());
+  if (is_stem(g)) m = std::max(m, (size_t)stem_gemm(g).in_elems());
+  return m;
 }
 
 int conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* bias,
@@ -88,6 +185,27 @@ int conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* bia
     ProfScope prof(PROF_CONV_FWD, 2.0 * g.out_elems() * (double)g.K(),
                    4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
     return conv_tc_run(g, x_hi, x_lo, w_hi, w_lo, bias, addend, y, npass, fmt, 1.f / wscale, s);
+  }
+  if (mode != 0 && (tc_mask() & 1) && is_stem(g)) {
+    const int npass = mode == 1 ? 3 : 1;
+    const int fmt = npass == 3 ? TC_F16 : TC_BF16;
+    const float wscale = npass == 3 ? 64.f : 1.f;
+    const ConvGeom gg = stem_gemm(g);
+    uint16_t* w_hi = c.get<uint16_t>((size_t)g.Cout * kStemK);
+    uint16_t* w_lo = c.get<uint16_t>((size_t)g.Cout * kStemK);
+    uint16_t* x_hi = c.get<uint16_t>((size_t)gg.in_elems());
+    uint16_t* x_lo = c.get<uint16_t>((size_t)gg.in_elems());
+    EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_fwd(stem): scratch too small");
+    stem_prep_weights_kernel<<<cdiv(g.Cout * kStemK, 256), 256, 0, s>>>(
+        w, g.Cout, fmt, wscale, w_hi, npass == 3 ? w_lo : nullptr);
+    EVE_LAUNCH_CHECK();
+    const long long total = (long long)g.N * g.OH * g.OW * (kStemK / 8);
+    stem_im2col_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, g.H, g.W, g.OH, g.OW, fmt, x_hi,
+                                                       npass == 3 ? x_lo : nullptr);
+    EVE_LAUNCH_CHECK();
+    ProfScope prof(PROF_CONV_FWD, 2.0 * g.out_elems() * (double)g.K(),
+                   4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
+    return conv_tc_run(gg, x_hi, x_lo, w_hi, w_lo, bias, addend, y, npass, fmt, 1.f / wscale, s);
   }
   float* wf = c.get<float>(wel);
   EVE_REQUIRE(wf, EVE_ERR_WORKSPACE, "conv_fwd: scratch too small");
@@ -115,6 +233,29 @@ int conv_dgrad(const ConvGeom& g, const float* dy, const float* w, const float* 
                      4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
       return conv_tc_run(f, d_hi, d_lo, w_hi, w_lo, nullptr, addend, dx, npass, TC_BF16, 1.f, s);
     }
+  }
+  if (mode != 0 && (tc_mask() & 2) && conv_tc_dgrad_s2_supported(g)) {
+    const int npass = mode == 1 ? 3 : 1;
+    uint16_t* w_hi = c.get<uint16_t>(wel);
+    uint16_t* w_lo = c.get<uint16_t>(wel);
+    uint16_t* d_hi = c.get<uint16_t>((size_t)g.out_elems());
+    uint16_t* d_lo = c.get<uint16_t>((size_t)g.out_elems());
+    EVE_REQUIRE(d_lo, EVE_ERR_WORKSPACE, "conv_dgrad: scratch too small");
+    EVE_TRY(conv_tc_prep_weights(g, w, true, w_hi, npass == 3 ? w_lo : nullptr, TC_BF16, 1.f, s));
+    EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
+    if (g.KH == 1) {
+      // only even/even pixels receive data: the rest is the addend (or zero)
+      if (addend) {
+        if (addend != dx)
+          EVE_CUDA(cudaMemcpyAsync(dx, addend, (size_t)g.in_elems() * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, s));
+      } else {
+        EVE_TRY(fill_zero(dx, g.in_elems(), s));
+      }
+    }
+    ProfScope prof(PROF_CONV_DGRAD, 2.0 * g.out_elems() * (double)g.K(),
+                   4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
+    return conv_tc_dgrad_s2_run(g, d_hi, d_lo, w_hi, w_lo, addend, dx, npass, s);
   }
   float* wd = c.get<float>(wel);
   EVE_REQUIRE(wd, EVE_ERR_WORKSPACE, "conv_dgrad: scratch too small");
@@ -144,6 +285,35 @@ int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, fl
                      4.0 * (g.in_elems() + g.out_elems() + (double)g.Cout * g.K()), s);
       EVE_TRY(conv_tc_wgrad_run(g, d_hi, d_lo, x_hi, x_lo, part, npass, &splits, s));
       EVE_TRY(wgrad_reduce(part, splits, g, dw, accumulate, s));
+    }
+    if (dbias)
+      EVE_TRY(colsum(dy, (long long)g.N * g.OH * g.OW, g.Cout, g.Cout, dbias, part, accumulate, s));
+    return EVE_OK;
+  }
+  if (dw && mode != 0 && (tc_mask() & 4) && is_stem(g) && conv_tc_wgrad_supported(stem_gemm(g))) {
+    const int npass = mode == 1 ? 3 : 1;
+    const ConvGeom gg = stem_gemm(g);
+    size_t pf = conv_tc_wgrad_partial_floats(gg);
+    size_t cs = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
+    float* part = c.get<float>(pf > cs ? pf : cs);
+    uint16_t* d_hi = c.get<uint16_t>((size_t)g.out_elems());
+    uint16_t* d_lo = c.get<uint16_t>((size_t)g.out_elems());
+    uint16_t* x_hi = c.get<uint16_t>((size_t)gg.in_elems());
+    uint16_t* x_lo = c.get<uint16_t>((size_t)gg.in_elems());
+    EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_wgrad(stem): scratch too small");
+    EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
+    const long long total = (long long)g.N * g.OH * g.OW * (kStemK / 8);
+    stem_im2col_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, g.H, g.W, g.OH, g.OW, TC_BF16,
+                                                       x_hi, npass == 3 ? x_lo : nullptr);
+    EVE_LAUNCH_CHECK();
+    int splits = 0;
+    {
+      ProfScope prof(PROF_CONV_WGRAD, 2.0 * g.out_elems() * (double)g.K(),
+                     4.0 * (g.in_elems() + g.out_elems() + (double)g.Cout * g.K()), s);
+      EVE_TRY(conv_tc_wgrad_run(gg, d_hi, d_lo, x_hi, x_lo, part, npass, &splits, s));
+      stem_wgrad_reduce_kernel<<<cdiv(g.Cout * 147, 256), 256, 0, s>>>(part, splits, g.Cout, dw,
+                                                                      accumulate ? 1 : 0);
+      EVE_LAUNCH_CHECK();
     }
     if (dbias)
       EVE_TRY(colsum(dy, (long long)g.N * g.OH * g.OW, g.Cout, g.Cout, dbias, part, accumulate, s));

@@ -162,8 +162,15 @@ __device__ __forceinline__ uint64_t mnmajor_desc(uint32_t saddr, uint32_t lbo_by
 }
 
 struct TcParams {
-  int N, OH, OW, Cin, Cout, KH, KW, pad, stride;
-  int bw, bh, bn;           // output-pixel box of one M tile (bw == OW)
+  int N, OH, OW, Cin, Cout, stride;   // OH x OW: the pixel grid the M tiles walk over
+  // filter taps as explicit tables: input offset (in input pixels, before the traversal
+  // stride is applied to the tile origin) and the K offset of the tap's weights in B
+  int ntaps;
+  int tap_dh[9], tap_dw[9], tap_koff[9];
+  // where grid pixel (h, w) lands in the output tensor: (h*out_mul + out_ah, w*out_mul + out_aw)
+  // of an out_H x out_W image (the parity classes of a stride-2 data gradient use mul = 2)
+  int out_mul, out_ah, out_aw, out_H, out_W;
+  int bw, bh, bn;           // grid-pixel box of one M tile (bw == OW)
   int tiles_h;              // ceil(OH / bh)
   int kc;                   // channels per K chunk: 64, 32 or 16
   int kchunks;              // Cin / kc
@@ -213,8 +220,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int h0 = th * p.bh;
   const int n0 = tn * p.bn;
   const int co0 = blockIdx.y * BN;
-  const int taps = p.KH * p.KW;
-  const int iters = taps * p.kchunks;
+  const int iters = p.ntaps * p.kchunks;
 
   if (warp == 0 && lane == 0) {
     tmap_prefetch(&tmA_hi);
@@ -248,16 +254,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         uint8_t* st = smem + s * Cfg::kStageBytes;
         const int tap = it / p.kchunks;
         const int kc = it - tap * p.kchunks;
-        const int r = tap / p.KW, q = tap - r * p.KW;
+        const int wi = p.tap_dw[tap], hi = h0 * p.stride + p.tap_dh[tap];
+        const int kb = p.tap_koff[tap] + kc * p.kc;
         mbar_expect_tx(&full[s], tx);
-        tma_load_4d(st, &tmA_hi, &full[s], kc * p.kc, q - p.pad, h0 * p.stride + r - p.pad, n0);
-        tma_load_2d(st + Cfg::kABytes * Cfg::kPlanes, &tmB_hi, &full[s],
-                    tap * p.Cin + kc * p.kc, co0);
+        tma_load_4d(st, &tmA_hi, &full[s], kc * p.kc, wi, hi, n0);
+        tma_load_2d(st + Cfg::kABytes * Cfg::kPlanes, &tmB_hi, &full[s], kb, co0);
         if (NPASS == 3) {
-          tma_load_4d(st + Cfg::kABytes, &tmA_lo, &full[s], kc * p.kc, q - p.pad,
-                      h0 * p.stride + r - p.pad, n0);
-          tma_load_2d(st + Cfg::kABytes * 2 + Cfg::kBBytes, &tmB_lo, &full[s],
-                      tap * p.Cin + kc * p.kc, co0);
+          tma_load_4d(st + Cfg::kABytes, &tmA_lo, &full[s], kc * p.kc, wi, hi, n0);
+          tma_load_2d(st + Cfg::kABytes * 2 + Cfg::kBBytes, &tmB_lo, &full[s], kb, co0);
         }
       }
     }
@@ -307,7 +311,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int in = m / (p.bw * p.bh);
     const int h = h0 + ih, n = n0 + in;
     const bool valid = in < p.bn && h < p.OH && n < p.N;
-    const size_t row = ((size_t)(n * p.OH + h) * p.OW + iw) * p.Cout + co0;
+    const size_t row = ((size_t)(n * p.out_H + h * p.out_mul + p.out_ah) * p.out_W +
+                        iw * p.out_mul + p.out_aw) * p.Cout + co0;
     constexpr int CW = BN < 32 ? BN : 32;   // columns handled per TMEM load
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -365,9 +370,14 @@ struct TcWgradParams {
   int uw, upb;              // unit width (channels) and units per M block (128 / uw)
   int units;                // taps * (Cout / uw)
   int cout_blocks;          // Cout / uw
-  int xw;                   // channels per x block: min(64, Cin)
-  int nblk;                 // input channels per CTA (multiple of xw, <= 256)
+  int xw;                   // channels per N-side block: min(64, C_n)
+  int nblk;                 // N-side channels per CTA (multiple of xw, <= 256)
   int stages;
+  // swap == 0: M side = dy (shifted by pad - tap), N side = x            (stride 1)
+  // swap == 1: M side = x (shifted by tap - pad, traversal stride 2), N side = dy (stride 2);
+  //            then uw / units / cout_blocks describe the *input* channels and the epilogue
+  //            writes the transposed tile
+  int swap, mstride;
   float* part;              // [splits][Cout][taps*Cin]
 };
 
@@ -449,8 +459,10 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
             const int tap = u / p.cout_blocks;
             const int cb = u - tap * p.cout_blocks;
             const int r = tap / p.KW, q = tap - r * p.KW;
-            tma_load_4d(base + b * a_block, md, &full[s], cb * p.uw, w0 + p.pad - q,
-                        h0 + p.pad - r, n0);
+            const int dw = p.swap ? q - p.pad : p.pad - q;
+            const int dh = p.swap ? r - p.pad : p.pad - r;
+            tma_load_4d(base + b * a_block, md, &full[s], cb * p.uw, w0 * p.mstride + dw,
+                        h0 * p.mstride + dh, n0);
           }
           for (int b = 0; b < nbB; ++b)
             tma_load_4d(base + a_bytes + b * b_block, mx, &full[s], nb * p.nblk + b * p.xw, w0, h0,
@@ -500,9 +512,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
     const bool valid = u < p.units;
     const int tap = valid ? u / p.cout_blocks : 0;
     const int cb = valid ? u - tap * p.cout_blocks : 0;
-    const int co = cb * p.uw + (m % p.uw);
+    const int mc = cb * p.uw + (m % p.uw);      // channel on the M side (co, or ci when swapped)
     const size_t KK = (size_t)p.KH * p.KW * p.Cin;
-    float* dst = p.part + ((size_t)sp * p.Cout + co) * KK + (size_t)tap * p.Cin + (size_t)nb * p.nblk;
+    float* dst = p.swap
+        ? p.part + ((size_t)sp * p.Cout + (size_t)nb * p.nblk) * KK + (size_t)tap * p.Cin + mc
+        : p.part + ((size_t)sp * p.Cout + mc) * KK + (size_t)tap * p.Cin + (size_t)nb * p.nblk;
     if (iters > 0) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
@@ -516,12 +530,17 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      if (valid) {
+      if (valid && !p.swap) {
         float4* o4 = reinterpret_cast<float4*>(dst + c0);
         const int nq = min(32, p.nblk - c0) >> 2;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (j < nq) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else if (valid) {
+        const int nv = min(32, p.nblk - c0);      // column n = output channel: rows KK apart
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nv) dst[(size_t)(c0 + j) * KK] = v[j];
       }
     }
     tc_fence_before();
@@ -763,39 +782,97 @@ int conv_tc_prep_weights(const ConvGeom& g, const float* w_oihw, bool dgrad, voi
   return EVE_OK;
 }
 
-// y[N,OH,OW,Cout] = conv(x) (+bias) (+addend).  x_hi/x_lo: bf16 NHWC planes of the input;
-// w_hi/w_lo: K-major weights [Cout][KH*KW*Cin].  npass: 3 (split bf16) or 1 (plain bf16).
+static int tc_launch(const TcParams& p0, const void* x_hi, const void* x_lo, int inN, int inH,
+                     int inW, const void* w_hi, const void* w_lo, int wrows, int wcols, int npass,
+                     int fmt, cudaStream_t s) {
+  TcParams p = p0;
+  pick_box(p.N, p.OH, p.OW, p.bw, p.bh, p.bn);
+  p.tiles_h = cdiv(p.OH, p.bh);
+  p.kc = chunk_for(p.Cin);
+  p.kchunks = p.Cin / p.kc;
+  p.fmt = fmt;
+  const int tiles_n = cdiv(p.N, p.bn);
+  const int BN = bn_for(p.Cout);
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  EVE_TRY(make_map_nhwc(&a_hi, x_hi, inN, inH, inW, p.Cin, p.kc, p.bw, p.bh, p.bn, p.stride, fmt));
+  EVE_TRY(make_map_2d(&b_hi, w_hi, wrows, wcols, p.kc, BN, fmt));
+  if (npass == 3) {
+    EVE_TRY(make_map_nhwc(&a_lo, x_lo, inN, inH, inW, p.Cin, p.kc, p.bw, p.bh, p.bn, p.stride,
+                          fmt));
+    EVE_TRY(make_map_2d(&b_lo, w_lo, wrows, wcols, p.kc, BN, fmt));
+  } else {
+    a_lo = a_hi;
+    b_lo = b_hi;
+  }
+  const int gx = p.tiles_h * tiles_n, gy = p.Cout / BN;
+  return npass == 3 ? launch_tc_bn<3>(BN, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s)
+                    : launch_tc_bn<1>(BN, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+}
+
+// y[N,OH,OW,Cout] = conv(x) (+bias) (+addend).  x_hi/x_lo: 16-bit NHWC planes of the input;
+// w_hi/w_lo: K-major weights [Cout][KH*KW*Cin].  npass: 3 (split operands) or 1 (plain bf16).
 int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* w_hi,
                 const void* w_lo, const float* bias, const float* addend, float* y, int npass,
                 int fmt, float out_scale, cudaStream_t s) {
   EVE_REQUIRE(conv_tc_supported(g), EVE_ERR_SHAPE, "conv_tc: unsupported geometry");
   EVE_REQUIRE(npass == 1 || npass == 3, EVE_ERR_CONFIG, "conv_tc: npass must be 1 or 3");
   TcParams p;
-  p.N = g.N; p.OH = g.OH; p.OW = g.OW; p.Cin = g.Cin; p.Cout = g.Cout;
-  p.KH = g.KH; p.KW = g.KW; p.pad = g.pad; p.stride = g.stride;
-  pick_box(g.N, g.OH, g.OW, p.bw, p.bh, p.bn);
-  p.tiles_h = cdiv(g.OH, p.bh);
-  p.kc = chunk_for(g.Cin);
-  p.kchunks = g.Cin / p.kc;
-  p.bias = bias; p.addend = addend; p.out = y;
-  p.fmt = fmt; p.out_scale = out_scale;
-  const int tiles_n = cdiv(g.N, p.bn);
-  const int BN = bn_for(g.Cout);
-  const int K = g.KH * g.KW * g.Cin;
-  CUtensorMap a_hi, a_lo, b_hi, b_lo;
-  EVE_TRY(make_map_nhwc(&a_hi, x_hi, g.N, g.H, g.W, g.Cin, p.kc, p.bw, p.bh, p.bn, g.stride, fmt));
-  EVE_TRY(make_map_2d(&b_hi, w_hi, g.Cout, K, p.kc, BN, fmt));
-  if (npass == 3) {
-    EVE_TRY(make_map_nhwc(&a_lo, x_lo, g.N, g.H, g.W, g.Cin, p.kc, p.bw, p.bh, p.bn, g.stride,
-                          fmt));
-    EVE_TRY(make_map_2d(&b_lo, w_lo, g.Cout, K, p.kc, BN, fmt));
-  } else {
-    a_lo = a_hi;
-    b_lo = b_hi;
-  }
-  const int gx = p.tiles_h * tiles_n, gy = g.Cout / BN;
-  return npass == 3 ? launch_tc_bn<3>(BN, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s)
-                    : launch_tc_bn<1>(BN, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+  p.N = g.N; p.OH = g.OH; p.OW = g.OW; p.Cin = g.Cin; p.Cout = g.Cout; p.stride = g.stride;
+  p.ntaps = g.KH * g.KW;
+  for (int r = 0; r < g.KH; ++r)
+    for (int q = 0; q < g.KW; ++q) {
+      int t = r * g.KW + q;
+      p.tap_dh[t] = r - g.pad;
+      p.tap_dw[t] = q - g.pad;
+      p.tap_koff[t] = t * g.Cin;
+    }
+  p.out_mul = 1; p.out_ah = 0; p.out_aw = 0; p.out_H = g.OH; p.out_W = g.OW;
+  p.bias = bias; p.addend = addend; p.out = y; p.out_scale = out_scale;
+  return tc_launch(p, x_hi, x_lo, g.N, g.H, g.W, w_hi, w_lo, g.Cout, g.KH * g.KW * g.Cin, npass,
+                   fmt, s);
+}
+
+// Data gradient of a stride-2 convolution (3x3 pad 1 or 1x1 pad 0) as four stride-1
+// tensor-core passes, one per output-pixel parity class (a, b): dx[2i+a, 2j+b] only receives
+// the taps r with (a + pad - r) even, read from dy[i + (a+pad-r)/2, ...].  `w_hi/w_lo` hold
+// the dgrad weight layout of conv_tc_prep_weights(dgrad = true): row ci, column
+// ((KH-1-r)*KW + (KW-1-q))*Cout + co.  dx must be zero-filled by the caller when KH == 1
+// (odd pixels receive nothing); addend (if any) has dx's layout.
+bool conv_tc_dgrad_s2_supported(const ConvGeom& g) {
+  if (g.stride != 2 || g.KH != g.KW || (g.KH != 1 && g.KH != 3) || g.pad != g.KH / 2) return false;
+  if (g.H % 2 != 0 || g.W % 2 != 0 || g.OH != g.H / 2 || g.OW != g.W / 2) return false;
+  if (chunk_for(g.Cout) == 0 || bn_for(g.Cin) == 0) return false;
+  if (g.OW > kTileM || g.N < 1) return false;
+  return true;
+}
+
+int conv_tc_dgrad_s2_run(const ConvGeom& g, const void* d_hi, const void* d_lo, const void* w_hi,
+                         const void* w_lo, const float* addend, float* dx, int npass,
+                         cudaStream_t s) {
+  EVE_REQUIRE(conv_tc_dgrad_s2_supported(g), EVE_ERR_SHAPE, "conv_tc_dgrad_s2: unsupported geometry");
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      TcParams p;
+      p.N = g.N; p.OH = g.OH; p.OW = g.OW;       // class grid == dy grid
+      p.Cin = g.Cout; p.Cout = g.Cin; p.stride = 1;
+      p.ntaps = 0;
+      for (int r = 0; r < g.KH; ++r) {
+        if ((a + g.pad - r) % 2 != 0) continue;
+        for (int q = 0; q < g.KW; ++q) {
+          if ((b + g.pad - q) % 2 != 0) continue;
+          int t = p.ntaps++;
+          p.tap_dh[t] = (a + g.pad - r) / 2;
+          p.tap_dw[t] = (b + g.pad - q) / 2;
+          p.tap_koff[t] = ((g.KH - 1 - r) * g.KW + (g.KW - 1 - q)) * g.Cout;
+        }
+      }
+      if (p.ntaps == 0) continue;                // 1x1: only the even/even class gets data
+      p.out_mul = 2; p.out_ah = a; p.out_aw = b; p.out_H = g.H; p.out_W = g.W;
+      p.bias = nullptr; p.addend = addend; p.out = dx; p.out_scale = 1.f;
+      EVE_TRY(tc_launch(p, d_hi, d_lo, g.N, g.OH, g.OW, w_hi, w_lo, g.Cin, g.KH * g.KW * g.Cout,
+                        npass, TC_BF16, s));
+    }
+  return EVE_OK;
 }
 
 // pixel box for the wgrad K loop: rows = bw*bh*bn <= 64 and a multiple of 16
@@ -823,12 +900,18 @@ static bool pick_wgrad_box(int N, int H, int W, int& bw, int& bh, int& bn) {
 }
 
 bool conv_tc_wgrad_supported(const ConvGeom& g) {
-  if (g.stride != 1 || g.KH != g.KW || (g.KH != 1 && g.KH != 3)) return false;
-  if (g.pad != g.KH / 2 || g.OH != g.H || g.OW != g.W) return false;
+  if (g.KH != g.KW || (g.KH != 1 && g.KH != 3) || g.pad != g.KH / 2) return false;
+  if (g.stride == 1) {
+    if (g.OH != g.H || g.OW != g.W) return false;
+  } else if (g.stride == 2) {
+    if (g.H % 2 != 0 || g.W % 2 != 0) return false;
+  } else {
+    return false;
+  }
   if (chunk_for(g.Cin) == 0 || chunk_for(g.Cout) == 0) return false;
   if (g.N < 1) return false;
   int bw, bh, bn;
-  return pick_wgrad_box(g.N, g.H, g.W, bw, bh, bn);
+  return pick_wgrad_box(g.N, g.OH, g.OW, bw, bh, bn);
 }
 
 static int wgrad_stage_bytes(const TcWgradParams& p, int npass) {
@@ -839,21 +922,25 @@ static int wgrad_stage_bytes(const TcWgradParams& p, int npass) {
 
 static void wgrad_plan(const ConvGeom& g, TcWgradParams& p, int& mblocks, int& nblocks,
                        int& splits, int npass) {
-  p.N = g.N; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.Cout = g.Cout;
+  p.N = g.N; p.H = g.OH; p.W = g.OW; p.Cin = g.Cin; p.Cout = g.Cout;   // tiles walk the dy grid
   p.KH = g.KH; p.KW = g.KW; p.pad = g.pad;
-  pick_wgrad_box(g.N, g.H, g.W, p.bw, p.bh, p.bn);
+  p.swap = g.stride == 2 ? 1 : 0;
+  p.mstride = g.stride;
+  pick_wgrad_box(g.N, g.OH, g.OW, p.bw, p.bh, p.bn);
   p.rows = p.bw * p.bh * p.bn;
-  p.tiles_w = g.W / p.bw;
-  p.tiles_h = cdiv(g.H, p.bh);
+  p.tiles_w = g.OW / p.bw;
+  p.tiles_h = cdiv(g.OH, p.bh);
   p.tiles_total = p.tiles_w * p.tiles_h * cdiv(g.N, p.bn);
-  p.uw = chunk_for(g.Cout);
+  const int Cm = p.swap ? g.Cin : g.Cout;      // channels on the M side / N side
+  const int Cn = p.swap ? g.Cout : g.Cin;
+  p.uw = chunk_for(Cm);
   p.upb = kTileM / p.uw;
-  p.cout_blocks = g.Cout / p.uw;
+  p.cout_blocks = Cm / p.uw;
   p.units = g.KH * g.KW * p.cout_blocks;
-  p.xw = chunk_for(g.Cin);
-  p.nblk = g.Cin % 256 == 0 ? 256 : (g.Cin % 128 == 0 ? 128 : (g.Cin % 64 == 0 ? 64 : g.Cin));
+  p.xw = chunk_for(Cn);
+  p.nblk = Cn % 256 == 0 ? 256 : (Cn % 128 == 0 ? 128 : (Cn % 64 == 0 ? 64 : Cn));
   mblocks = cdiv(p.units, p.upb);
-  nblocks = g.Cin / p.nblk;
+  nblocks = Cn / p.nblk;
   p.stages = (220 * 1024) / wgrad_stage_bytes(p, npass);
   if (p.stages > 6) p.stages = 6;
   int want = cdiv(3 * kNumSMs, mblocks * nblocks);
@@ -881,14 +968,24 @@ int conv_tc_wgrad_run(const ConvGeom& g, const void* d_hi, const void* d_lo, con
   int mb, nb, sp;
   wgrad_plan(g, p, mb, nb, sp, npass);
   p.part = part;
+  // md_* = M-side maps, mx_* = N-side maps (see TcWgradParams::swap)
   CUtensorMap md_hi, md_lo, mx_hi, mx_lo;
-  // the dy and x grids have the same shape ("same" padding)
-  EVE_TRY(make_map_nhwc(&md_hi, d_hi, g.N, g.H, g.W, g.Cout, p.uw, p.bw, p.bh, p.bn));
-  EVE_TRY(make_map_nhwc(&mx_hi, x_hi, g.N, g.H, g.W, g.Cin, p.xw, p.bw, p.bh, p.bn));
-  if (npass == 3) {
-    EVE_TRY(make_map_nhwc(&md_lo, d_lo, g.N, g.H, g.W, g.Cout, p.uw, p.bw, p.bh, p.bn));
-    EVE_TRY(make_map_nhwc(&mx_lo, x_lo, g.N, g.H, g.W, g.Cin, p.xw, p.bw, p.bh, p.bn));
+  if (!p.swap) {
+    EVE_TRY(make_map_nhwc(&md_hi, d_hi, g.N, g.OH, g.OW, g.Cout, p.uw, p.bw, p.bh, p.bn));
+    EVE_TRY(make_map_nhwc(&mx_hi, x_hi, g.N, g.H, g.W, g.Cin, p.xw, p.bw, p.bh, p.bn));
+    if (npass == 3) {
+      EVE_TRY(make_map_nhwc(&md_lo, d_lo, g.N, g.OH, g.OW, g.Cout, p.uw, p.bw, p.bh, p.bn));
+      EVE_TRY(make_map_nhwc(&mx_lo, x_lo, g.N, g.H, g.W, g.Cin, p.xw, p.bw, p.bh, p.bn));
+    }
   } else {
+    EVE_TRY(make_map_nhwc(&md_hi, x_hi, g.N, g.H, g.W, g.Cin, p.uw, p.bw, p.bh, p.bn, 2));
+    EVE_TRY(make_map_nhwc(&mx_hi, d_hi, g.N, g.OH, g.OW, g.Cout, p.xw, p.bw, p.bh, p.bn));
+    if (npass == 3) {
+      EVE_TRY(make_map_nhwc(&md_lo, x_lo, g.N, g.H, g.W, g.Cin, p.uw, p.bw, p.bh, p.bn, 2));
+      EVE_TRY(make_map_nhwc(&mx_lo, d_lo, g.N, g.OH, g.OW, g.Cout, p.xw, p.bw, p.bh, p.bn));
+    }
+  }
+  if (npass != 3) {
     md_lo = md_hi;
     mx_lo = mx_hi;
   }

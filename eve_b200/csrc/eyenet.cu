@@ -107,7 +107,7 @@ int check_cnn(const eve_eyenet_cnn_params* p) {
 size_t cnn_conv_scratch_bytes(const CnnTape& t) {
   size_t mi = 0, mo = 0, mw = 0, mp = 0;
   auto upd = [&](const ConvGeom& g) {
-    mi = std::max(mi, (size_t)g.in_elems());
+    mi = std::max(mi, conv_operand_elems(g));
     mo = std::max(mo, (size_t)g.out_elems());
     mw = std::max(mw, (size_t)g.Cout * g.K());
     mp = std::max(mp, conv_partial_floats(g));

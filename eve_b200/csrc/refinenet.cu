@@ -428,7 +428,7 @@ int block_bwd(const RBlock& k, int N, const float* const* w, float* const* gr, b
 size_t rnet_conv_scratch_bytes(const RNet& n) {
   size_t mi = 0, mo = 0, mw = 0, mp = 0;
   auto upd = [&](const ConvGeom& g) {
-    mi = std::max(mi, (size_t)g.in_elems());
+    mi = std::max(mi, conv_operand_elems(g));
     mo = std::max(mo, (size_t)g.out_elems());
     mw = std::max(mw, (size_t)g.Cout * g.K());
     mp = std::max(mp, conv_partial_floats(g));
