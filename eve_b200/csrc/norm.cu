@@ -25,50 +25,70 @@ __device__ __forceinline__ float act_grad(float y, int act) {
   return 1.f;
 }
 
-// grid (N, C/CB); block = CB channels x L pixel lanes (CB*L = 256)
-// Shifted sums (shift = first pixel) keep the variance accurate when |mean| >> std.
+// grid (N, ceil(C4/CQ)); block 256 = CQ channel-quads x L pixel lanes.  Every thread owns 4
+// consecutive channels (one 16-byte load per pixel) and walks pixels lane, lane+L, ... with two
+// loads in flight.  Shifted sums (shift = first pixel) keep the variance accurate when
+// |mean| >> std.
 __global__ void __launch_bounds__(256) in_stats_kernel(const float* __restrict__ x, int HW, int C,
-                                                       int CB, float* __restrict__ mean,
+                                                       int CQ, float* __restrict__ mean,
                                                        float* __restrict__ rstd) {
-  __shared__ float s1[256], s2[256];
+  __shared__ float4 s1[256], s2[256];
   const int n = blockIdx.x;
-  const int cl = threadIdx.x % CB;
-  const int c = blockIdx.y * CB + cl;
-  const int lane = threadIdx.x / CB;
-  const int L = 256 / CB;
-  const float* xp = x + (size_t)n * HW * C;
-  float a = 0.f, b = 0.f, shift = 0.f;
-  if (c < C) {
-    shift = __ldg(xp + c);
-    // 4 independent accumulators for ILP
-    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  const int ql = threadIdx.x % CQ;
+  const int q = blockIdx.y * CQ + ql;          // channel quad
+  const int lane = threadIdx.x / CQ;
+  const int L = 256 / CQ;
+  const int C4 = C >> 2;
+  const float4* xp = reinterpret_cast<const float4*>(x + (size_t)n * HW * C);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, sh = a;
+  if (q < C4) {
+    sh = __ldg(xp + q);
+    float4 a1 = a, b1 = a;
     int p = lane;
     for (; p + L < HW; p += 2 * L) {
-      float v0 = __ldg(xp + (size_t)p * C + c) - shift;
-      float v1 = __ldg(xp + (size_t)(p + L) * C + c) - shift;
-      a0 += v0; b0 = fmaf(v0, v0, b0);
-      a1 += v1; b1 = fmaf(v1, v1, b1);
+      float4 v0 = __ldg(xp + (size_t)p * C4 + q);
+      float4 v1 = __ldg(xp + (size_t)(p + L) * C4 + q);
+      v0.x -= sh.x; v0.y -= sh.y; v0.z -= sh.z; v0.w -= sh.w;
+      v1.x -= sh.x; v1.y -= sh.y; v1.z -= sh.z; v1.w -= sh.w;
+      a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+      b.x = fmaf(v0.x, v0.x, b.x); b.y = fmaf(v0.y, v0.y, b.y);
+      b.z = fmaf(v0.z, v0.z, b.z); b.w = fmaf(v0.w, v0.w, b.w);
+      a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+      b1.x = fmaf(v1.x, v1.x, b1.x); b1.y = fmaf(v1.y, v1.y, b1.y);
+      b1.z = fmaf(v1.z, v1.z, b1.z); b1.w = fmaf(v1.w, v1.w, b1.w);
     }
     if (p < HW) {
-      float v0 = __ldg(xp + (size_t)p * C + c) - shift;
-      a0 += v0; b0 = fmaf(v0, v0, b0);
+      float4 v0 = __ldg(xp + (size_t)p * C4 + q);
+      v0.x -= sh.x; v0.y -= sh.y; v0.z -= sh.z; v0.w -= sh.w;
+      a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+      b.x = fmaf(v0.x, v0.x, b.x); b.y = fmaf(v0.y, v0.y, b.y);
+      b.z = fmaf(v0.z, v0.z, b.z); b.w = fmaf(v0.w, v0.w, b.w);
     }
-    a = a0 + a1;
-    b = b0 + b1;
+    a.x += a1.x; a.y += a1.y; a.z += a1.z; a.w += a1.w;
+    b.x += b1.x; b.y += b1.y; b.z += b1.z; b.w += b1.w;
   }
   s1[threadIdx.x] = a;
   s2[threadIdx.x] = b;
   __syncthreads();
-  if (lane == 0 && c < C) {
+  if (lane == 0 && q < C4) {
     for (int l = 1; l < L; ++l) {
-      a += s1[l * CB + cl];
-      b += s2[l * CB + cl];
+      float4 t = s1[l * CQ + ql], u = s2[l * CQ + ql];
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      b.x += u.x; b.y += u.y; b.z += u.z; b.w += u.w;
     }
-    float inv = 1.f / (float)HW;
-    float m = a * inv;
-    float var = fmaxf(b * inv - m * m, 0.f);
-    mean[(size_t)n * C + c] = m + shift;
-    rstd[(size_t)n * C + c] = rsqrtf(var + kEps);
+    const float inv = 1.f / (float)HW;
+    float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    float sv[4] = {sh.x, sh.y, sh.z, sh.w};
+    float mo[4], ro[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float m = av[j] * inv;
+      float var = fmaxf(bv[j] * inv - m * m, 0.f);
+      mo[j] = m + sv[j];
+      ro[j] = rsqrtf(var + kEps);
+    }
+    reinterpret_cast<float4*>(mean + (size_t)n * C)[q] = make_float4(mo[0], mo[1], mo[2], mo[3]);
+    reinterpret_cast<float4*>(rstd + (size_t)n * C)[q] = make_float4(ro[0], ro[1], ro[2], ro[3]);
   }
 }
 
@@ -114,43 +134,84 @@ in_apply_kernel(const float* __restrict__ x, long long total4, int HW, int C,
 // grid (N, C/CB); same thread layout as in_stats_kernel.
 __global__ void __launch_bounds__(256)
 in_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ ymask,
-                     const float* __restrict__ x, int HW, int C, int CB,
+                     const float* __restrict__ x, int HW, int C, int CQ,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                      float* __restrict__ sum_g, float* __restrict__ sum_gx) {
-  // fp64 accumulators: sum(g*xhat) cancels heavily (it is a covariance), and the affine
+  // Same thread layout as in_stats_kernel (4 channels per thread, 16-byte loads).  fp64
+  // accumulators: sum(g*xhat) cancels heavily (it is a covariance), and the affine
   // gradients are sums of these over the batch; B200 has the fp64 rate to hide this behind
-  // the HBM reads (2 DFMA per 8-12 bytes loaded).
-  __shared__ double s1[256], s2[256];
+  // the HBM reads (8 DFMA per 32-48 bytes loaded).
+  __shared__ double s1[256 * 4];
+  __shared__ double s2[256 * 4];
   const int n = blockIdx.x;
-  const int cl = threadIdx.x % CB;
-  const int c = blockIdx.y * CB + cl;
-  const int lane = threadIdx.x / CB;
-  const int L = 256 / CB;
-  const size_t base = (size_t)n * HW * C;
-  double a = 0.0, b = 0.0;
-  if (c < C) {
-    const float m = mean[(size_t)n * C + c], r = rstd[(size_t)n * C + c];
-    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-    for (int p = lane; p < HW; p += L) {
-      size_t o = base + (size_t)p * C + c;
-      float g = __ldg(dy + o);
-      float xh = (__ldg(x + o) - m) * r;
-      if (act != ACT_NONE) g *= act_grad(ymask ? __ldg(ymask + o) : fmaf(xh, ga, be), act);
-      a += (double)g;
-      b += (double)g * (double)xh;
+  const int ql = threadIdx.x % CQ;
+  const int q = blockIdx.y * CQ + ql;
+  const int lane = threadIdx.x / CQ;
+  const int L = 256 / CQ;
+  const int C4 = C >> 2;
+  const size_t base4 = (size_t)n * HW * C4;
+  const float4* dp = reinterpret_cast<const float4*>(dy) + base4;
+  const float4* xp = reinterpret_cast<const float4*>(x) + base4;
+  const float4* yp = ymask ? reinterpret_cast<const float4*>(ymask) + base4 : nullptr;
+  double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+  if (q < C4) {
+    const float4 m4 = reinterpret_cast<const float4*>(mean + (size_t)n * C)[q];
+    const float4 r4 = reinterpret_cast<const float4*>(rstd + (size_t)n * C)[q];
+    const float m[4] = {m4.x, m4.y, m4.z, m4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w};
+    float ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gamma) {
+      float4 g4 = reinterpret_cast<const float4*>(gamma)[q];
+      ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w;
+    }
+    if (beta) {
+      float4 b4 = reinterpret_cast<const float4*>(beta)[q];
+      be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
+    }
+    auto body = [&](const float4& d4, const float4& x4, const float4& y4) {
+      const float d[4] = {d4.x, d4.y, d4.z, d4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+      const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float xh = (xv[j] - m[j]) * r[j];
+        float g = d[j];
+        if (act != ACT_NONE) g *= act_grad(yp ? yv[j] : fmaf(xh, ga[j], be[j]), act);
+        a[j] += (double)g;
+        b[j] += (double)g * (double)xh;
+      }
+    };
+    int p = lane;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (; p + L < HW; p += 2 * L) {
+      const size_t o0 = (size_t)p * C4 + q, o1 = (size_t)(p + L) * C4 + q;
+      float4 d0 = __ldg(dp + o0), d1 = __ldg(dp + o1);
+      float4 x0 = __ldg(xp + o0), x1 = __ldg(xp + o1);
+      float4 y0 = yp ? __ldg(yp + o0) : z4, y1 = yp ? __ldg(yp + o1) : z4;
+      body(d0, x0, y0);
+      body(d1, x1, y1);
+    }
+    if (p < HW) {
+      const size_t o0 = (size_t)p * C4 + q;
+      body(__ldg(dp + o0), __ldg(xp + o0), yp ? __ldg(yp + o0) : z4);
     }
   }
-  s1[threadIdx.x] = a;
-  s2[threadIdx.x] = b;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s1[threadIdx.x * 4 + j] = a[j];
+    s2[threadIdx.x * 4 + j] = b[j];
+  }
   __syncthreads();
-  if (lane == 0 && c < C) {
-    for (int l = 1; l < L; ++l) {
-      a += s1[l * CB + cl];
-      b += s2[l * CB + cl];
-    }
-    sum_g[(size_t)n * C + c] = (float)a;
-    sum_gx[(size_t)n * C + c] = (float)b;
+  if (lane == 0 && q < C4) {
+    for (int l = 1; l < L; ++l)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a[j] += s1[(l * CQ + ql) * 4 + j];
+        b[j] += s2[(l * CQ + ql) * 4 + j];
+      }
+    reinterpret_cast<float4*>(sum_g + (size_t)n * C)[q] =
+        make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
+    reinterpret_cast<float4*>(sum_gx + (size_t)n * C)[q] =
+        make_float4((float)b[0], (float)b[1], (float)b[2], (float)b[3]);
   }
 }
 
@@ -214,15 +275,16 @@ __global__ void in_affine_grad_kernel(const float* __restrict__ sum_g,
   dbeta[c] = accumulate ? dbeta[c] + (float)b : (float)b;
 }
 
-inline int chan_block(int C) { return C >= 32 ? 32 : C; }
+// channel quads per block: up to 16 (64 channels), never more than the tensor has
+inline int quad_block(int C) { int q = C >> 2; return q >= 16 ? 16 : (q >= 8 ? 8 : (q >= 4 ? 4 : (q >= 2 ? 2 : 1))); }
 
 }  // namespace
 
 int in_stats(const float* x, int N, int HW, int C, float* mean, float* rstd, cudaStream_t s) {
-  int CB = chan_block(C);
-  EVE_REQUIRE(256 % CB == 0, EVE_ERR_SHAPE, "in_stats: C=%d unsupported", C);
-  dim3 grid(N, cdiv(C, CB));
-  in_stats_kernel<<<grid, 256, 0, s>>>(x, HW, C, CB, mean, rstd);
+  EVE_REQUIRE(C % 4 == 0, EVE_ERR_SHAPE, "in_stats: C=%d must be a multiple of 4", C);
+  int CQ = quad_block(C);
+  dim3 grid(N, cdiv(C >> 2, CQ));
+  in_stats_kernel<<<grid, 256, 0, s>>>(x, HW, C, CQ, mean, rstd);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }
@@ -245,11 +307,11 @@ int in_backward(const float* dy, const float* y_for_mask, const float* x, int N,
                 int act, const float* addend, float* dx, float* g_out, float* dgamma,
                 float* dbeta, float* scratch, bool accumulate_affine, cudaStream_t s) {
   EVE_REQUIRE(C % 4 == 0, EVE_ERR_SHAPE, "in_backward: C=%d must be a multiple of 4", C);
-  int CB = chan_block(C);
+  int CQ = quad_block(C);
   float* sum_g = scratch;
   float* sum_gx = scratch + (size_t)N * C;
-  dim3 grid(N, cdiv(C, CB));
-  in_bwd_reduce_kernel<<<grid, 256, 0, s>>>(dy, y_for_mask, x, HW, C, CB, mean, rstd, gamma, beta,
+  dim3 grid(N, cdiv(C >> 2, CQ));
+  in_bwd_reduce_kernel<<<grid, 256, 0, s>>>(dy, y_for_mask, x, HW, C, CQ, mean, rstd, gamma, beta,
                                             act, sum_g, sum_gx);
   EVE_LAUNCH_CHECK();
   long long total4 = (long long)N * HW * C / 4;
