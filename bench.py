@@ -218,61 +218,81 @@ def make_batch(B, T, cfg, seed, pinned):
     return d
 
 
-def timed_run(model, trainer, batches_fn, steps, warmup, world, device, profile):
-    """W untimed + K timed steps; returns (max-over-ranks ms total, launches, prof dict)."""
+def _barrier_sync(world):
     import torch
     import torch.distributed as dist
-    from eve_b200 import lib as L
-    lib = L.load()
-    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # > 126 MB L2
-
-    def one(i):
-        inputs = batches_fn(i)
-        out = model({'bench': inputs}, current_epoch=0.0)
-        loss = out['full_loss']
-        trainer.step(loss)
-        return loss
-
-    for i in range(warmup):
-        one(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    if profile:
-        lib.eve_profile_reset()
-        lib.eve_profile_enable(1)
-    launches0 = lib.eve_launch_count()
+
+
+def timed_graph_run(step_fn, inputs_fn, steps, extra_warmup, world, device, read_loss):
+    """K timed replays of the captured step (L2 flushed between them); returns max-over-ranks
+    total ms and the last loss.  ``read_loss``: D2H read of the loss inside every timed step."""
+    import torch
+    import torch.distributed as dist
+    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # > 126 MB L2
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    for i in range(extra_warmup):
+        step_fn(inputs_fn(i))
+    _barrier_sync(world)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     last = None
     for i in range(steps):
         flush.zero_()                       # evict L2 between timed iterations
         ev0[i].record()
-        loss = one(warmup + i)
-        last = loss.detach()
+        loss = step_fn(inputs_fn(extra_warmup + i))
+        if read_loss:
+            host_loss.copy_(loss, non_blocking=False)      # D2H + sync, like training.py:506
+            last = float(host_loss)
         ev1[i].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    lib.eve_profile_enable(0)
-    launches = lib.eve_launch_count() - launches0
+    _barrier_sync(world)
+    if last is None:
+        last = float(loss)
     ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    prof = None
-    if profile:
-        prof = {}
-        for kind, name in ((0, 'conv_fwd'), (1, 'conv_dgrad'), (2, 'conv_wgrad')):
-            v = [C.c_double(), C.c_double(), C.c_double(), C.c_longlong()]
-            L.check(lib.eve_profile_read(kind, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]),
-                                         C.byref(v[3])), 'eve_profile_read')
-            prof[name] = {'ms': v[0].value, 'flops': v[1].value, 'bytes': v[2].value,
-                          'launches': v[3].value}
-        lib.eve_profile_reset()
-    return float(t.item()), int(launches), prof, float(last)
+    return float(t.item()), last
+
+
+def profiled_eager_run(model, trainer, inputs_fn, steps, world, device):
+    """The same step launched eagerly with the library's conv profiler on: CUDA events around
+    every convolution kernel on its launching stream.  Returns (total ms, per-kind dict)."""
+    import torch
+    from eve_b200 import lib as L
+    lib = L.load()
+    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=device)
+
+    def one(i):
+        out = model({'bench': dict(inputs_fn(i))}, current_epoch=0.0)
+        trainer.step(out['full_loss'])
+
+    one(0)
+    _barrier_sync(world)
+    lib.eve_profile_reset()
+    lib.eve_profile_enable(1)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    for i in range(steps):
+        flush.zero_()
+        ev0[i].record()
+        one(1 + i)
+        ev1[i].record()
+    _barrier_sync(world)
+    lib.eve_profile_enable(0)
+    ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    prof = {}
+    for kind, name in ((0, 'conv_fwd'), (1, 'conv_dgrad'), (2, 'conv_wgrad')):
+        v = [C.c_double(), C.c_double(), C.c_double(), C.c_longlong()]
+        L.check(lib.eve_profile_read(kind, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]),
+                                     C.byref(v[3])), 'eve_profile_read')
+        prof[name] = {'ms': v[0].value, 'flops': v[1].value, 'bytes': v[2].value,
+                      'launches': v[3].value}
+    lib.eve_profile_reset()
+    return ms, prof
 
 
 def b200_arm(args):
@@ -305,6 +325,8 @@ def b200_arm(args):
         pass
 
     def measure(workload, steps, warmup, with_e2e, profile):
+        from eve_b200.graph import GraphedTrainStep
+        lib = L.load()
         cfg = configure(workload)
         np.random.seed(1234 + rank)        # kappa augmentation draws (eve.py:468-469)
         model = EVE()
@@ -316,29 +338,31 @@ def b200_arm(args):
         host = [make_batch(B, T, cfg, seed=1000 * rank + i, pinned=True) for i in range(nb)]
         dev = [{k: v.to(device) for k, v in h.items()} for h in host]
         res = {}
-        sampler = ClockSampler(torch.cuda.current_device() if 'CUDA_VISIBLE_DEVICES' not in os.environ
-                               else 0)
+        # W eager warm-up steps, then the step is captured once as a CUDA graph
+        n0 = lib.eve_launch_count()
+        step_fn = GraphedTrainStep(model, trainer, dev[0], warmup=max(warmup, 3), tag='bench')
+        launches_per_step = (lib.eve_launch_count() - n0) // (max(warmup, 3) + 1)
+        sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        ms, launches, prof, loss = timed_run(model, trainer, lambda i: dict(dev[i % nb]), steps,
-                                             warmup, world, device, profile)
+        ms, loss = timed_graph_run(step_fn, lambda i: dev[i % nb], steps, 1, world, device, False)
         clocks = sampler.stop() if rank == 0 else None
         frames = 2 * B * T * world * steps
-        res.update(ms=ms, launches=launches, prof=prof, loss=loss, clocks=clocks,
+        res.update(ms=ms, launches=launches_per_step * steps, loss=loss, clocks=clocks,
                    value=frames / (ms * 1e-3), frames_per_step=2 * B * T * world)
         if with_e2e:
-            def h2d(i):
-                return {k: v.to(device, non_blocking=True) for k, v in host[i % nb].items()}
+            # same call, HOST (pinned) inputs: H2D of the batch + D2H of the loss every step
             h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
-            # the D2H read of the loss happens inside timed_run's `float(last)` only once; make
-            # it per step here:
-            def step_inputs(i):
-                return h2d(i)
-            ms2, _, _, _ = timed_run_e2e(model, trainer, step_inputs, steps, max(warmup, 1), world,
-                                         device)
+            ms2, _ = timed_graph_run(step_fn, lambda i: host[i % nb], steps, 1, world, device, True)
             res['e2e'] = {'value': frames / (ms2 * 1e-3), 'unit': UNIT,
                           'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4,
                           'ms_per_step': ms2 / steps}
+        step_fn.close()
+        if profile:
+            pms, prof = profiled_eager_run(model, trainer, lambda i: dev[i % nb], steps, world,
+                                           device)
+            res['prof'] = prof
+            res['prof_ms'] = pms
         res['cfg'] = cfg
         return res
 
@@ -360,6 +384,7 @@ def b200_arm(args):
 
     # ---- roofline of the dominant kernel family (implicit-GEMM convolutions)
     prof = main['prof']
+    prof_steps = args.steps
     conv_ms = sum(p['ms'] for p in prof.values())
     conv_flops = sum(p['flops'] for p in prof.values())
     conv_launches = sum(p['launches'] for p in prof.values())
@@ -369,12 +394,16 @@ def b200_arm(args):
         peak, peak_src = 1400.0, 'fallback (B200_PROFILING.md sustained figure)'
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {
-        'bound': 'tensor', 'kernel': 'igemm_gather_kernel / igemm_wgrad_kernel (fp32 SIMT implicit '
-                                     'GEMM; all conv fwd + dgrad + wgrad launches of the timed steps)',
+        'bound': 'tensor', 'kernel': 'conv_tc_kernel / conv_tc_wgrad_kernel (tcgen05 implicit GEMM, '
+                                     'split fp16/bf16 operands = 3 MMAs per product) + the few '
+                                     'CUDA-core convs left; all conv fwd + dgrad + wgrad launches',
         'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
         'peak_source': peak_src, 'traffic': None,
         'launches': conv_launches, 'avg_launch_ms': conv_ms / max(conv_launches, 1),
-        'share_of_step': conv_ms / main['ms'],
+        'share_of_step': conv_ms / main['prof_ms'],
+        'timed_in': 'the same K steps launched eagerly (kernel-by-kernel, events on the launching '
+                    'stream) right after the graph-replayed timed region; kernels are identical',
+        'eager_ms_per_step': main['prof_ms'] / prof_steps,
         'per_kind': {k: {'ms_per_step': v['ms'] / args.steps,
                          'tflops': (v['flops'] / (v['ms'] * 1e-3) / 1e12) if v['ms'] > 0 else 0.0,
                          'launches_per_step': v['launches'] / args.steps}
@@ -392,7 +421,9 @@ def b200_arm(args):
                    'eye_frames_per_step': main['frames_per_step'],
                    'parallelism': 'dp%d (clips sharded on the batch axis, one NCCL allreduce of '
                                   'the flat fp32 gradient buffer)' % world,
-                   'step': 'EVE.forward + full_loss.backward + clip_grad_norm + Adam',
+                   'step': 'EVE.forward + full_loss.backward + clip_grad_norm + Adam, captured once '
+                           'as a CUDA graph and replayed',
+                   'conv_mode': 'tcgen05 split operands (fp16 hi+lo forward, bf16 hi+lo gradients)',
                    'cache': 'L2 flushed (160 MB write) between timed iterations; activations '
                             '(>8 GB/step) exceed L2',
                    'weights': 'random init (seeded), reference architecture'},
@@ -406,46 +437,6 @@ def b200_arm(args):
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
-
-
-def timed_run_e2e(model, trainer, inputs_fn, steps, warmup, world, device):
-    """Same step through the public call with HOST (pinned) inputs: per step an H2D copy of
-    the batch and a D2H read of the loss, all inside the timed region."""
-    import torch
-    import torch.distributed as dist
-    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=device)
-    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
-
-    def one(i):
-        inputs = inputs_fn(i)
-        out = model({'bench': inputs}, current_epoch=0.0)
-        loss = out['full_loss']
-        trainer.step(loss)
-        host_loss.copy_(loss.detach(), non_blocking=False)     # D2H + sync, like training.py:506
-        return float(host_loss)
-
-    for i in range(warmup):
-        one(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    total = 0.0
-    for i in range(steps):
-        flush.zero_()
-        ev0.record()
-        one(warmup + i)
-        ev1.record()
-        ev1.synchronize()
-        total += ev0.elapsed_time(ev1)
-    if world > 1:
-        dist.barrier()
-    t = torch.tensor([total], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item()), None, None, None
 
 
 def main():

@@ -44,7 +44,9 @@ sqnorm_partial_kernel(const float* __restrict__ g, long long n, float scale,
 
 // one block: norm = sqrt(sum partials) (deterministic order); coef = min(1, max_norm/(norm+1e-6))
 __global__ void norm_final_kernel(const float* __restrict__ part, int nparts, float max_norm,
-                                  float* __restrict__ stat, float* __restrict__ norm_out) {
+                                  float* __restrict__ stat, float* __restrict__ norm_out,
+                                  int* __restrict__ step_dev, int step_host, float beta1,
+                                  float beta2) {
   __shared__ double sm[256];
   double a = 0.0;
   for (int i = threadIdx.x; i < nparts; i += blockDim.x) a += (double)part[i];
@@ -64,14 +66,23 @@ __global__ void norm_final_kernel(const float* __restrict__ part, int nparts, fl
     stat[0] = norm;
     stat[1] = coef;
     if (norm_out) norm_out[0] = norm;
+    // bias corrections for this step (device-side counter when the step runs from a graph)
+    int step = step_host;
+    if (step_dev) {
+      step = *step_dev + 1;
+      *step_dev = step;
+    }
+    stat[2] = (float)(1.0 - pow((double)beta1, (double)step));
+    stat[3] = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   }
 }
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, long long n, const float* __restrict__ stat, float scale,
-            float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+            float lr, float b1, float b2, float eps, float wd) {
   const float coef = stat[1] * scale;
+  const float bc1 = stat[2], bc2_sqrt = stat[3];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float pv = p[i];
@@ -99,7 +110,8 @@ extern "C" int eve_adam_clip_step(const eve_adam_params* p, float* params, const
                                   float* exp_avg, float* exp_avg_sq, float* norm_out,
                                   void* workspace, size_t workspace_bytes, eve_stream_t stream) {
   EVE_REQUIRE(p, EVE_ERR_NULL, "adam_clip_step: params is NULL");
-  EVE_REQUIRE(p->count >= 0 && p->step >= 1, EVE_ERR_SHAPE, "adam_clip_step: bad count/step");
+  EVE_REQUIRE(p->count >= 0 && (p->step >= 1 || p->step_dev), EVE_ERR_SHAPE,
+              "adam_clip_step: bad count/step");
   if (p->count == 0) return EVE_OK;
   EVE_REQUIRE(params && grads && exp_avg && exp_avg_sq && workspace, EVE_ERR_NULL,
               "adam_clip_step: NULL pointer");
@@ -110,13 +122,12 @@ extern "C" int eve_adam_clip_step(const eve_adam_params* p, float* params, const
   float* stat = part + kNormBlocks;
   sqnorm_partial_kernel<<<kNormBlocks, 256, 0, s>>>(grads, p->count, p->grad_scale, part);
   EVE_LAUNCH_CHECK();
-  norm_final_kernel<<<1, 256, 0, s>>>(part, kNormBlocks, p->max_norm, stat, norm_out);
+  norm_final_kernel<<<1, 256, 0, s>>>(part, kNormBlocks, p->max_norm, stat, norm_out, p->step_dev,
+                                      p->step, p->beta1, p->beta2);
   EVE_LAUNCH_CHECK();
-  const float bc1 = (float)(1.0 - pow((double)p->beta1, (double)p->step));
-  const float bc2 = (float)(1.0 - pow((double)p->beta2, (double)p->step));
   adam_kernel<<<kNormBlocks * 2, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, p->count, stat,
                                               p->grad_scale, p->lr, p->beta1, p->beta2, p->eps,
-                                              p->weight_decay, bc1, sqrtf(bc2));
+                                              p->weight_decay);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }

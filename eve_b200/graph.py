@@ -1,0 +1,78 @@
+"""One training step of the EVE hot path as a replayable CUDA graph.
+
+The step (time-batched ``EVE.forward``, ``full_loss.backward()``, gradient packing, optional
+NCCL allreduce, fused clip + Adam) launches ~1.5k kernels from Python; captured once, a replay
+costs one ``cudaGraphLaunch``.  Everything data-dependent stays outside the capture:
+  * inputs are copied into static device buffers before each replay (H2D straight from the
+    caller's pinned tensors);
+  * the per-clip kappa augmentation draws (np.random, eve.py:468-469) are made on the host in
+    the reference's order and copied into static [B, 2] buffers;
+  * the Adam step count lives on the device (eve_adam_params.step_dev).
+The math is the eager path's, kernel for kernel -- tests/test_gpu_graph.py holds the two
+bit-identical.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class GraphedTrainStep(object):
+    def __init__(self, model, trainer, example_inputs, current_epoch=0.0, warmup=3,
+                 tag='train', capture=True):
+        self.model = model
+        self.trainer = trainer
+        self.tag = tag
+        self.epoch = float(current_epoch)
+        dev = trainer.device
+        self.static_in = {k: torch.empty_like(v, device=dev) for k, v in example_inputs.items()}
+        B = next(iter(example_inputs.values())).shape[0]
+        self.kappa_host = {s: torch.empty((B, 2), dtype=torch.float32).pin_memory()
+                           for s in ('left', 'right')}
+        model.kappa_buffers = {s: torch.zeros((B, 2), dtype=torch.float32, device=dev)
+                               for s in ('left', 'right')}
+        self.batch = B
+        self.loss = None
+        self.graph = None
+        self._load(example_inputs)
+        # warm-up on a side stream (allocator pools, lazy kernel attributes, NCCL channels)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                self._eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if capture:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._eager()
+            torch.cuda.synchronize(dev)
+
+    def _eager(self):
+        out = self.model({self.tag: dict(self.static_in)}, current_epoch=self.epoch)
+        loss = out['full_loss']
+        self.trainer.step(loss)
+        return loss.detach()
+
+    def _load(self, inputs):
+        for k, v in inputs.items():
+            self.static_in[k].copy_(v, non_blocking=True)
+        left, right = self.model.draw_kappas(self.batch)
+        self.kappa_host['left'].copy_(torch.from_numpy(left.astype(np.float32)))
+        self.kappa_host['right'].copy_(torch.from_numpy(right.astype(np.float32)))
+        for s in ('left', 'right'):
+            self.model.kappa_buffers[s].copy_(self.kappa_host[s], non_blocking=True)
+
+    def __call__(self, inputs):
+        """Run one optimisation step on ``inputs`` (host or device tensors with the example's
+        shapes); returns the loss as a 0-dim device tensor (valid until the next call)."""
+        self._load(inputs)
+        if self.graph is None:          # capture=False: same data path, eager launches
+            self.loss = self._eager()
+            return self.loss
+        self.graph.replay()
+        self.trainer.steps += 1
+        return self.loss
+
+    def close(self):
+        self.model.kappa_buffers = None

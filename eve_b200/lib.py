@@ -42,7 +42,8 @@ class HeatmapParams(C.Structure):
 class AdamParams(C.Structure):
     _fields_ = [('count', C.c_longlong), ('lr', C.c_float), ('beta1', C.c_float),
                 ('beta2', C.c_float), ('eps', C.c_float), ('weight_decay', C.c_float),
-                ('max_norm', C.c_float), ('grad_scale', C.c_float), ('step', C.c_int)]
+                ('max_norm', C.c_float), ('grad_scale', C.c_float), ('step', C.c_int),
+                ('step_dev', C.c_void_p)]
 
 
 EYE_RNN_TYPES = {None: 0, 'RNN': 1, 'LSTM': 2, 'GRU': 3}

@@ -26,6 +26,7 @@ class EVE(nn.Module):
     def __init__(self, output_predictions=False):
         super(EVE, self).__init__()
         self.output_predictions = output_predictions
+        self.kappa_buffers = None     # see calculate_additional_labels / eve_b200.graph
         self.eye_net = EyeNet()
         if config.eye_net_load_pretrained:
             self._load_pretrained(self.eye_net)
@@ -238,6 +239,15 @@ class EVE(nn.Module):
                 out['metric_ang_g_' + stage] = term(LS.angular_loss, 'g_' + stage, 'g')
 
     # ---------------------------------------------------------------------- labels --
+    @staticmethod
+    def draw_kappas(batch_size):
+        """Per-clip fake kappa offsets: the same np.random draws, in the same order, as the
+        reference (eve.py:468-469)."""
+        kappa_std = np.radians(config.refine_net_offset_augmentation_sigma)
+        left = np.random.normal(size=(batch_size, 2), loc=0.0, scale=kappa_std)
+        right = np.random.normal(size=(batch_size, 2), loc=0.0, scale=kappa_std)
+        return left, right
+
     def calculate_additional_labels(self, full_input_dict, current_epoch=None):
         """eve.py:441-543 without the Python loops over the batch."""
         d = full_input_dict
@@ -252,13 +262,17 @@ class EVE(nn.Module):
         if self.training and config.refine_net_do_offset_augmentation:
             assert current_epoch is not None
             assert isinstance(current_epoch, float)
-            kappa_std = np.radians(config.refine_net_offset_augmentation_sigma)
-            # same draws, same order as the reference (np.random, eve.py:468-469)
-            left_kappas = np.random.normal(size=(batch_size, 2), loc=0.0, scale=kappa_std)
-            right_kappas = np.random.normal(size=(batch_size, 2), loc=0.0, scale=kappa_std)
-            for side, k in (('left', left_kappas), ('right', right_kappas)):
-                k = np.repeat(np.expand_dims(k, axis=1), sequence_len, axis=1)
-                d[side + '_kappa_fake'] = torch.tensor(k.astype(np.float32)).to(dev)
+            if self.kappa_buffers is not None:
+                # static device buffers [B, 2] filled by the caller (CUDA-graph replay: the
+                # host draw + H2D copy cannot sit inside a captured step)
+                for side in ('left', 'right'):
+                    d[side + '_kappa_fake'] = self.kappa_buffers[side].unsqueeze(1).expand(
+                        batch_size, sequence_len, 2)
+            else:
+                left_kappas, right_kappas = self.draw_kappas(batch_size)
+                for side, k in (('left', left_kappas), ('right', right_kappas)):
+                    k = np.repeat(np.expand_dims(k, axis=1), sequence_len, axis=1)
+                    d[side + '_kappa_fake'] = torch.tensor(k.astype(np.float32)).to(dev)
         if 'left_o' in d:
             d['o'] = torch.stack([d['left_o'], d['right_o']], dim=-1).mean(dim=-1).detach()
             d['o_validity'] = d['left_o_validity']

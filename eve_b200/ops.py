@@ -318,13 +318,14 @@ class PogFn(torch.autograd.Function):
 
 # ------------------------------------------------------------------- fused optimiser --
 def adam_clip_step(params, grads, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8,
-                   weight_decay=0.0, max_norm=0.0, grad_scale=1.0):
+                   weight_decay=0.0, max_norm=0.0, grad_scale=1.0, step_dev=None):
     """clip_grad_norm_ + Adam on flat fp32 buffers (training.py:492-502).  Returns the
-    pre-clip gradient norm as a 1-element device tensor."""
+    pre-clip gradient norm as a 1-element device tensor.  ``step_dev`` (int32 device tensor)
+    makes the kernel keep the step count itself, so the call can live in a CUDA graph."""
     lib = L.load()
     L.require_cuda(params, 'adam_clip_step')
     p = L.AdamParams(params.numel(), lr, betas[0], betas[1], eps, weight_decay, max_norm,
-                     grad_scale, int(step))
+                     grad_scale, int(step), None if step_dev is None else step_dev.data_ptr())
     ws = L.workspace(lib.eve_adam_clip_workspace_bytes(C.byref(p)), params.device, 'adam')
     norm = torch.empty(1, dtype=torch.float32, device=params.device)
     L.check(lib.eve_adam_clip_step(C.byref(p), L.ptr(params), L.ptr(grads), L.ptr(exp_avg),

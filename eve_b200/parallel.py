@@ -59,6 +59,8 @@ class FlatAdamTrainer(object):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.steps = 0
+        # device-side copy of the step counter (what the fused kernel uses: graph-replayable)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev) if dev.type == 'cuda' else None
         self.device = dev
         self.last_grad_norm = None
 
@@ -88,7 +90,8 @@ class FlatAdamTrainer(object):
             return
         self.last_grad_norm = ops.adam_clip_step(
             self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.steps, self.lr,
-            self.betas, self.eps, self.weight_decay, self.max_norm, 1.0 / self.world)
+            self.betas, self.eps, self.weight_decay, self.max_norm, 1.0 / self.world,
+            step_dev=self.step_dev)
 
     def step(self, loss, update=None):
         loss.backward()

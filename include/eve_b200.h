@@ -230,7 +230,9 @@ typedef struct {
   float lr, beta1, beta2, eps, weight_decay;
   float max_norm;   /* <= 0 disables clipping */
   float grad_scale;
-  int step;         /* 1-based Adam step for bias correction */
+  int step;         /* 1-based Adam step for bias correction (ignored when step_dev is set) */
+  int* step_dev;    /* optional DEVICE counter: the kernel increments it and uses the new value as
+                       the step -- lets one captured CUDA graph be replayed for every step */
 } eve_adam_params;
 size_t eve_adam_clip_workspace_bytes(const eve_adam_params* p);
 int eve_adam_clip_step(const eve_adam_params* p, float* params, const float* grads, float* exp_avg,
