@@ -104,3 +104,28 @@ def test_cpu_tensors_are_refused(cfg):
     net = EyeNet()
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         net.cnn_features(torch.zeros(1, 3, 128, 128))
+
+
+def test_integration_shim_routes_reference_imports(tmp_path, monkeypatch):
+    """The three-line `src/models/__init__.py` of INTEGRATION.md makes the reference's own
+    import statements (`from models.eve import EVE`, `from models.common import ...`) resolve
+    to this package."""
+    import importlib
+    import sys
+    text = open(os.path.join(os.path.dirname(HEADER), '..', 'INTEGRATION.md')).read()
+    start = text.index('# src/models/__init__.py')
+    shim = text[start:text.index('```', start)]
+    pkg = tmp_path / 'models'
+    pkg.mkdir()
+    (pkg / '__init__.py').write_text(shim)
+    monkeypatch.syspath_prepend(str(tmp_path))
+    for k in [k for k in sys.modules if k == 'models' or k.startswith('models.')]:
+        monkeypatch.delitem(sys.modules, k)
+    importlib.invalidate_caches()
+    from models.eve import EVE as RefPathEVE                      # noqa: E402
+    from models.common import pitchyaw_to_vector, soft_argmax     # noqa: E402,F401
+    from models.eye_net import EyeNet as RefPathEyeNet            # noqa: E402
+    import eve_b200.models as M
+    assert RefPathEVE is M.EVE and RefPathEyeNet is M.EyeNet
+    for k in [k for k in sys.modules if k == 'models' or k.startswith('models.')]:
+        monkeypatch.delitem(sys.modules, k)
