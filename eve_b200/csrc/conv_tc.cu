@@ -37,6 +37,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -172,6 +175,8 @@ struct TcParams {
   int out_mul, out_ah, out_aw, out_H, out_W;
   int bw, bh, bn;           // grid-pixel box of one M tile (bw == OW)
   int tiles_h;              // ceil(OH / bh)
+  int tiles_m;              // M tiles: tiles_h * ceil(N / bn)
+  int tiles_co;             // N tiles: Cout / BN
   int kc;                   // channels per K chunk: 64, 32 or 16
   int kchunks;              // Cin / kc
   int fmt;                  // operand format: 0 = fp16 planes, 1 = bf16 planes
@@ -195,7 +200,7 @@ struct TcCfg {
   static constexpr int kStagesRaw = (kBudget - 2048) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;   // per accumulator buffer (x2)
 };
 
 template <int BN, int NPASS>
@@ -203,24 +208,23 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const TcParams p) {
+  // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator
+  // is double-buffered in TMEM so the epilogue of tile i overlaps the K loop of tile i+1; the
+  // shared-memory ring simply keeps rolling across tile boundaries.
   using Cfg = TcCfg<BN, NPASS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty = full + Cfg::kStages;
-  uint64_t* tmem_full = empty + Cfg::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + Cfg::kStages;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int th = tile % p.tiles_h;
-  const int tn = tile / p.tiles_h;
-  const int h0 = th * p.bh;
-  const int n0 = tn * p.bn;
-  const int co0 = blockIdx.y * BN;
   const int iters = p.ntaps * p.kchunks;
+  const int total_tiles = p.tiles_m * p.tiles_co;
 
   if (warp == 0 && lane == 0) {
     tmap_prefetch(&tmA_hi);
@@ -233,10 +237,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 128);   // every epilogue thread arrives
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -247,106 +254,135 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (elect_one()) {
       const uint32_t rows = p.bw * p.bh * p.bn;
       const uint32_t tx = (rows + (uint32_t)BN) * (uint32_t)(p.kc * 2) * Cfg::kPlanes;
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % Cfg::kStages;
-        const uint32_t ph = (it / Cfg::kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* st = smem + s * Cfg::kStageBytes;
-        const int tap = it / p.kchunks;
-        const int kc = it - tap * p.kchunks;
-        const int wi = p.tap_dw[tap], hi = h0 * p.stride + p.tap_dh[tap];
-        const int kb = p.tap_koff[tap] + kc * p.kc;
-        mbar_expect_tx(&full[s], tx);
-        tma_load_4d(st, &tmA_hi, &full[s], kc * p.kc, wi, hi, n0);
-        tma_load_2d(st + Cfg::kABytes * Cfg::kPlanes, &tmB_hi, &full[s], kb, co0);
-        if (NPASS == 3) {
-          tma_load_4d(st + Cfg::kABytes, &tmA_lo, &full[s], kc * p.kc, wi, hi, n0);
-          tma_load_2d(st + Cfg::kABytes * 2 + Cfg::kBBytes, &tmB_lo, &full[s], kb, co0);
+      uint32_t g = 0;   // global K-iteration counter: stage = g % kStages
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tco = tile % p.tiles_co;
+        const int tm = tile / p.tiles_co;
+        const int h0 = (tm % p.tiles_h) * p.bh;
+        const int n0 = (tm / p.tiles_h) * p.bn;
+        const int co0 = tco * BN;
+        for (int it = 0; it < iters; ++it, ++g) {
+          const int s = g % Cfg::kStages;
+          const uint32_t ph = (g / Cfg::kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * Cfg::kStageBytes;
+          const int tap = it / p.kchunks;
+          const int kc = it - tap * p.kchunks;
+          const int wi = p.tap_dw[tap], hi = h0 * p.stride + p.tap_dh[tap];
+          const int kb = p.tap_koff[tap] + kc * p.kc;
+          mbar_expect_tx(&full[s], tx);
+          tma_load_4d(st, &tmA_hi, &full[s], kc * p.kc, wi, hi, n0);
+          tma_load_2d(st + Cfg::kABytes * Cfg::kPlanes, &tmB_hi, &full[s], kb, co0);
+          if (NPASS == 3) {
+            tma_load_4d(st + Cfg::kABytes, &tmA_lo, &full[s], kc * p.kc, wi, hi, n0);
+            tma_load_2d(st + Cfg::kABytes * 2 + Cfg::kBBytes, &tmB_lo, &full[s], kb, co0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = BN
-    // (A/B format field: 0 = fp16, 1 = bf16)
+    // instruction descriptor: D fp32, A/B fp16 or bf16 (format field 0 / 1), both K-major,
+    // M = 128, N = BN
     const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const int ksteps = p.kc >> 4;
-    for (int it = 0; it < iters; ++it) {
-      const int s = it % Cfg::kStages;
-      const uint32_t ph = (it / Cfg::kStages) & 1;
-      mbar_wait(&full[s], ph);
+    uint32_t g = 0, local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const uint32_t buf = local & 1;
+      const uint32_t use = local >> 1;
+      mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t b_hi = a_hi + Cfg::kABytes * Cfg::kPlanes;
-        const uint64_t da_hi = kmajor_desc(a_hi, p.kc);
-        const uint64_t db_hi = kmajor_desc(b_hi, p.kc);
-        const uint64_t da_lo = kmajor_desc(a_hi + Cfg::kABytes, p.kc);
-        const uint64_t db_lo = kmajor_desc(b_hi + Cfg::kBBytes, p.kc);
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 bytes >> 4
-          if (NPASS == 3) {
-            // small terms first so they are not absorbed by a large partial sum
-            umma_bf16(tmem_base, da_lo + adv, db_hi + adv, idesc, (it | k) != 0);
-            umma_bf16(tmem_base, da_hi + adv, db_lo + adv, idesc, 1);
-            umma_bf16(tmem_base, da_hi + adv, db_hi + adv, idesc, 1);
-          } else {
-            umma_bf16(tmem_base, da_hi + adv, db_hi + adv, idesc, (it | k) != 0);
+      const uint32_t tmem_d = tmem_base + buf * Cfg::kTmemCols;
+      for (int it = 0; it < iters; ++it, ++g) {
+        const int s = g % Cfg::kStages;
+        const uint32_t ph = (g / Cfg::kStages) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t b_hi = a_hi + Cfg::kABytes * Cfg::kPlanes;
+          const uint64_t da_hi = kmajor_desc(a_hi, p.kc);
+          const uint64_t db_hi = kmajor_desc(b_hi, p.kc);
+          const uint64_t da_lo = kmajor_desc(a_hi + Cfg::kABytes, p.kc);
+          const uint64_t db_lo = kmajor_desc(b_hi + Cfg::kBBytes, p.kc);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);  // 16 elements = 32 bytes >> 4
+            if (NPASS == 3) {
+              // small terms first so they are not absorbed by a large partial sum
+              umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, (it | k) != 0);
+              umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
+              umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1);
+            } else {
+              umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (it | k) != 0);
+            }
           }
+          umma_commit(&empty[s]);
+          if (it == iters - 1) umma_commit(&tmem_full[buf]);
         }
-        umma_commit(&empty[s]);
-        if (it == iters - 1) umma_commit(tmem_full);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ===================== epilogue =====================
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
     const int m = quad * 32 + lane;         // tile row = TMEM lane
     const int iw = m % p.bw;
     const int ih = (m / p.bw) % p.bh;
     const int in = m / (p.bw * p.bh);
-    const int h = h0 + ih, n = n0 + in;
-    const bool valid = in < p.bn && h < p.OH && n < p.N;
-    const size_t row = ((size_t)(n * p.out_H + h * p.out_mul + p.out_ah) * p.out_W +
-                        iw * p.out_mul + p.out_aw) * p.Cout + co0;
     constexpr int CW = BN < 32 ? BN : 32;   // columns handled per TMEM load
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const uint32_t buf = local & 1;
+      const uint32_t use = local >> 1;
+      const int tco = tile % p.tiles_co;
+      const int tm = tile / p.tiles_co;
+      const int h = (tm % p.tiles_h) * p.bh + ih;
+      const int n = (tm / p.tiles_h) * p.bn + in;
+      const int co0 = tco * BN;
+      const bool valid = in < p.bn && h < p.OH && n < p.N;
+      const size_t row = ((size_t)(n * p.out_H + h * p.out_mul + p.out_ah) * p.out_W +
+                          iw * p.out_mul + p.out_aw) * p.Cout + co0;
+      mbar_wait(&tmem_full[buf], use & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * Cfg::kTmemCols + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-      if (valid) {
-        if (p.out_scale != 1.f) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_d + (uint32_t)c0, v);
+        if (valid) {
+          if (p.out_scale != 1.f) {
 #pragma unroll
-          for (int j = 0; j < CW; ++j) v[j] *= p.out_scale;
-        }
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < CW; ++j) v[j] += __ldg(p.bias + co0 + c0 + j);
-        }
-        if (p.addend) {
-          const float4* a4 = reinterpret_cast<const float4*>(p.addend + row + c0);
-#pragma unroll
-          for (int j = 0; j < CW / 4; ++j) {
-            float4 a = __ldg(a4 + j);
-            v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+            for (int j = 0; j < CW; ++j) v[j] *= p.out_scale;
           }
-        }
-        float4* o4 = reinterpret_cast<float4*>(p.out + row + c0);
+          if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < CW / 4; ++j)
-          o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < CW; ++j) v[j] += __ldg(p.bias + co0 + c0 + j);
+          }
+          if (p.addend) {
+            const float4* a4 = reinterpret_cast<const float4*>(p.addend + row + c0);
+#pragma unroll
+            for (int j = 0; j < CW / 4; ++j) {
+              float4 a = __ldg(a4 + j);
+              v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+            }
+          }
+          float4* o4 = reinterpret_cast<float4*>(p.out + row + c0);
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j)
+            o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
       }
+      // all of this thread's TMEM reads have completed (tcgen05.wait::ld): release the buffer
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[buf]);
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    tmem_dealloc(tmem_base, 2 * Cfg::kTmemCols);
   }
 }
 
@@ -709,7 +745,7 @@ void pick_box(int N, int H, int W, int& bw, int& bh, int& bn) {
 
 template <int BN, int NPASS>
 int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-              const CUtensorMap& b_lo, const TcParams& p, int grid_x, int grid_y,
+              const CUtensorMap& b_lo, const TcParams& p0, int tiles_m, int tiles_co,
               cudaStream_t s) {
   using Cfg = TcCfg<BN, NPASS>;
   static bool configured = false;
@@ -718,8 +754,12 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  conv_tc_kernel<BN, NPASS><<<dim3(grid_x, grid_y), kThreads, Cfg::kSmemBytes, s>>>(a_hi, a_lo, b_hi,
-                                                                                  b_lo, p);
+  TcParams p = p0;
+  p.tiles_m = tiles_m;
+  p.tiles_co = tiles_co;
+  const long long total = (long long)tiles_m * tiles_co;
+  const int grid = (int)(total < kNumSMs ? total : kNumSMs);   // one persistent CTA per SM
+  conv_tc_kernel<BN, NPASS><<<grid, kThreads, Cfg::kSmemBytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }
