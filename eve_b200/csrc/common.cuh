@@ -169,6 +169,10 @@ int conv_dgrad(const ConvGeom& g, const float* dy, const float* w_oihw, const fl
                float* dx, const ConvScratch& sc, cudaStream_t s);
 int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw_oihw, float* dbias,
                bool accumulate, const ConvScratch& sc, cudaStream_t s);
+// both gradients of one convolution (dw/dbias and dx, each optional) from one split of dy
+int conv_bwd(const ConvGeom& g, const float* x, const float* dy, const float* w_oihw, float* dw,
+             float* dbias, bool accumulate, const float* addend, float* dx, const ConvScratch& sc,
+             cudaStream_t s);
 
 // ------------------------------------------------------------------------------ norms --
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };

@@ -329,4 +329,62 @@ int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, fl
   return EVE_OK;
 }
 
+// Weight gradient and data gradient of one convolution sharing ONE split of dy (both tensor-core
+// passes read the same bf16 hi/lo planes).  Falls back to the two separate entry points when
+// either pass is not taken by the tensor-core kernels.
+int conv_bwd(const ConvGeom& g, const float* x, const float* dy, const float* w, float* dw,
+             float* dbias, bool accumulate, const float* addend, float* dx, const ConvScratch& sc,
+             cudaStream_t s) {
+  const int mode = conv_mode();
+  const bool s1 = g.stride == 1 && conv_tc_supported(dgrad_as_fwd(g));
+  const bool s2 = conv_tc_dgrad_s2_supported(g);
+  const bool fused = dw && dx && mode != 0 && (tc_mask() & 6) == 6 && conv_tc_wgrad_supported(g) &&
+                     (s1 || s2);
+  if (!fused) {
+    if (dw || dbias) EVE_TRY(conv_wgrad(g, x, dy, dw, dbias, accumulate, sc, s));
+    if (dx) EVE_TRY(conv_dgrad(g, dy, w, addend, dx, sc, s));
+    return EVE_OK;
+  }
+  Carve c{sc.base, sc.base + sc.bytes};
+  const int npass = mode == 1 ? 3 : 1;
+  const size_t wel = (size_t)g.Cout * g.K();
+  size_t pf = conv_tc_wgrad_partial_floats(g);
+  size_t cs = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
+  float* part = c.get<float>(pf > cs ? pf : cs);
+  uint16_t* w_hi = c.get<uint16_t>(wel);
+  uint16_t* w_lo = c.get<uint16_t>(wel);
+  uint16_t* d_hi = c.get<uint16_t>((size_t)g.out_elems());
+  uint16_t* d_lo = c.get<uint16_t>((size_t)g.out_elems());
+  uint16_t* x_hi = c.get<uint16_t>((size_t)g.in_elems());
+  uint16_t* x_lo = c.get<uint16_t>((size_t)g.in_elems());
+  EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_bwd: scratch too small");
+  EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
+  EVE_TRY(split_planes(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, TC_BF16, s));
+  EVE_TRY(conv_tc_prep_weights(g, w, true, w_hi, npass == 3 ? w_lo : nullptr, TC_BF16, 1.f, s));
+  const double flops = 2.0 * g.out_elems() * (double)g.K();
+  const double bytes = 4.0 * (g.in_elems() + g.out_elems() + (double)wel);
+  {
+    int splits = 0;
+    ProfScope prof(PROF_CONV_WGRAD, flops, bytes, s);
+    EVE_TRY(conv_tc_wgrad_run(g, d_hi, d_lo, x_hi, x_lo, part, npass, &splits, s));
+    EVE_TRY(wgrad_reduce(part, splits, g, dw, accumulate, s));
+  }
+  if (dbias)
+    EVE_TRY(colsum(dy, (long long)g.N * g.OH * g.OW, g.Cout, g.Cout, dbias, part, accumulate, s));
+  if (s2 && g.KH == 1) {
+    if (addend) {
+      if (addend != dx)
+        EVE_CUDA(cudaMemcpyAsync(dx, addend, (size_t)g.in_elems() * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
+    } else {
+      EVE_TRY(fill_zero(dx, g.in_elems(), s));
+    }
+  }
+  ProfScope prof(PROF_CONV_DGRAD, flops, bytes, s);
+  if (s1)
+    return conv_tc_run(dgrad_as_fwd(g), d_hi, d_lo, w_hi, w_lo, nullptr, addend, dx, npass, TC_BF16,
+                       1.f, s);
+  return conv_tc_dgrad_s2_run(g, d_hi, d_lo, w_hi, w_lo, addend, dx, npass, s);
+}
+
 }  // namespace eve

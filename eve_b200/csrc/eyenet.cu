@@ -269,27 +269,23 @@ extern "C" int eve_eyenet_cnn_bwd(const eve_eyenet_cnn_params* p, const float* d
     // out = relu(IN(b) + skip)
     EVE_TRY(in_backward(dout, k.out, k.b, N, HW, C, k.bm, k.br, nullptr, nullptr, ACT_RELU, nullptr, db,
                         gskip, nullptr, nullptr, sc.inb, false, s));
-    // conv2
-    if (gr[slot + 1])
-      EVE_TRY(conv_wgrad(k.g2, k.y, db, gr[slot + 1], nullptr, acc, sc.cs, s));
+    // conv2: weight gradient + data gradient from one split of db
     float* dy = sc.t2;
-    EVE_TRY(conv_dgrad(k.g2, db, w[slot + 1], nullptr, dy, sc.cs, s));
+    EVE_TRY(conv_bwd(k.g2, k.y, db, w[slot + 1], gr[slot + 1], nullptr, acc, nullptr, dy, sc.cs, s));
     // y = relu(IN(a))
     float* da = sc.t0;
     EVE_TRY(in_backward(dy, k.y, k.a, N, HW, C, k.am, k.ar, nullptr, nullptr, ACT_RELU, nullptr, da,
                         nullptr, nullptr, nullptr, sc.inb, false, s));
-    if (gr[slot]) EVE_TRY(conv_wgrad(k.g1, k.in, da, gr[slot], nullptr, acc, sc.cs, s));
     const float* addend = gskip;
     if (k.down) {
       float* dd = sc.t2;
       EVE_TRY(in_backward(gskip, nullptr, k.d, N, HW, C, k.dm, k.dr, nullptr, nullptr, ACT_NONE,
                           nullptr, dd, nullptr, nullptr, nullptr, sc.inb, false, s));
-      if (gr[slot + 2])
-        EVE_TRY(conv_wgrad(k.gd, k.in, dd, gr[slot + 2], nullptr, acc, sc.cs, s));
-      EVE_TRY(conv_dgrad(k.gd, dd, w[slot + 2], nullptr, sc.t3, sc.cs, s));
+      EVE_TRY(conv_bwd(k.gd, k.in, dd, w[slot + 2], gr[slot + 2], nullptr, acc, nullptr, sc.t3, sc.cs,
+                       s));
       addend = sc.t3;
     }
-    EVE_TRY(conv_dgrad(k.g1, da, w[slot], addend, dnext, sc.cs, s));
+    EVE_TRY(conv_bwd(k.g1, k.in, da, w[slot], gr[slot], nullptr, acc, addend, dnext, sc.cs, s));
     float* tmp = dout;
     dout = dnext;
     dnext = tmp;

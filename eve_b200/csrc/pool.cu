@@ -29,22 +29,33 @@ __global__ void transpose_kernel(const float* __restrict__ x, int R, int Cc,
   }
 }
 
+// ---- every kernel below: one thread = 4 consecutive channels (16-byte accesses) ----
+struct F4 {
+  float v[4];
+  __device__ __forceinline__ F4() {}
+  __device__ __forceinline__ F4(float4 f) { v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w; }
+  __device__ __forceinline__ float4 f4() const { return make_float4(v[0], v[1], v[2], v[3]); }
+};
+__device__ __forceinline__ F4 ld4(const float* p) { return F4(__ldg(reinterpret_cast<const float4*>(p))); }
+__device__ __forceinline__ void st4(float* p, const F4& a) { *reinterpret_cast<float4*>(p) = a.f4(); }
+
 __global__ void __launch_bounds__(256)
-in_relu_maxpool_kernel(const float* __restrict__ x, long long total, int H, int W, int C, int OH,
+in_relu_maxpool_kernel(const float* __restrict__ x, long long total4, int H, int W, int C, int OH,
                        int OW, const float* __restrict__ mean, const float* __restrict__ rstd,
                        float* __restrict__ y, int32_t* __restrict__ idx) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int c = (int)(i % C);
-  long long t = i / C;
+  if (i >= total4) return;
+  const int C4 = C >> 2;
+  int c = (int)(i % C4) * 4;
+  long long t = i / C4;
   int ox = (int)(t % OW);
   t /= OW;
   int oy = (int)(t % OH);
   int n = (int)(t / OH);
-  const float m = mean[(size_t)n * C + c], r = rstd[(size_t)n * C + c];
+  const F4 m = ld4(mean + (size_t)n * C + c), r = ld4(rstd + (size_t)n * C + c);
   const float* xp = x + (size_t)n * H * W * C + c;
-  float best = -INFINITY;
-  int bi = -1;
+  float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int bi[4] = {-1, -1, -1, -1};
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
     int h = oy * 2 - 1 + dy;
@@ -53,32 +64,37 @@ in_relu_maxpool_kernel(const float* __restrict__ x, long long total, int H, int 
     for (int dx = 0; dx < 3; ++dx) {
       int w = ox * 2 - 1 + dx;
       if (w < 0 || w >= W) continue;
-      float v = (__ldg(xp + (size_t)(h * W + w) * C) - m) * r;
-      v = v > 0.f ? v : 0.f;
-      if (v > best || bi < 0) {
-        best = v;
-        bi = h * W + w;
+      F4 xv = ld4(xp + (size_t)(h * W + w) * C);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = (xv.v[j] - m.v[j]) * r.v[j];
+        v = v > 0.f ? v : 0.f;
+        if (v > best[j] || bi[j] < 0) {
+          best[j] = v;
+          bi[j] = h * W + w;
+        }
       }
     }
   }
-  y[i] = best;
-  idx[i] = bi;
+  *reinterpret_cast<float4*>(y + i * 4) = make_float4(best[0], best[1], best[2], best[3]);
+  *reinterpret_cast<int4*>(idx + i * 4) = make_int4(bi[0], bi[1], bi[2], bi[3]);
 }
 
 // gather form of the max-pool backward (3x3, stride 2, pad 1): deterministic, no atomics
 __global__ void __launch_bounds__(256)
-maxpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx, long long total,
+maxpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx, long long total4,
                    int H, int W, int OH, int OW, int C, float* __restrict__ g) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int c = (int)(i % C);
-  long long t = i / C;
+  if (i >= total4) return;
+  const int C4 = C >> 2;
+  int c = (int)(i % C4) * 4;
+  long long t = i / C4;
   int w = (int)(t % W);
   t /= W;
   int h = (int)(t % H);
   int n = (int)(t / H);
   const int me = h * W + w;
-  float s = 0.f;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
   // windows oy with oy*2-1 <= h <= oy*2+1
   int oy0 = h / 2, oy1 = (h + 1) / 2;
   int ox0 = w / 2, ox1 = (w + 1) / 2;
@@ -87,10 +103,15 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx
     for (int ox = ox0; ox <= ox1; ++ox) {
       if (ox >= OW) continue;
       size_t o = (((size_t)n * OH + oy) * OW + ox) * C + c;
-      if (__ldg(idx + o) == me) s += __ldg(dy + o);
+      int4 id = __ldg(reinterpret_cast<const int4*>(idx + o));
+      F4 d = ld4(dy + o);
+      if (id.x == me) s[0] += d.v[0];
+      if (id.y == me) s[1] += d.v[1];
+      if (id.z == me) s[2] += d.v[2];
+      if (id.w == me) s[3] += d.v[3];
     }
   }
-  g[i] = s;
+  *reinterpret_cast<float4*>(g + i * 4) = make_float4(s[0], s[1], s[2], s[3]);
 }
 
 __global__ void avgpool_fwd_kernel(const float* __restrict__ x, int HW, int C,
@@ -116,12 +137,13 @@ __device__ __forceinline__ int win_start(int i, int L, int O) { return (i * L) /
 __device__ __forceinline__ int win_end(int i, int L, int O) { return ((i + 1) * L + O - 1) / O; }
 
 __global__ void __launch_bounds__(256)
-adaptive_maxpool_fwd_kernel(const float* __restrict__ x, long long total, int H, int W, int C,
+adaptive_maxpool_fwd_kernel(const float* __restrict__ x, long long total4, int H, int W, int C,
                             int OH, int OW, float* __restrict__ y, int32_t* __restrict__ idx) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int c = (int)(i % C);
-  long long t = i / C;
+  if (i >= total4) return;
+  const int C4 = C >> 2;
+  int c = (int)(i % C4) * 4;
+  long long t = i / C4;
   int ox = (int)(t % OW);
   t /= OW;
   int oy = (int)(t % OH);
@@ -129,28 +151,34 @@ adaptive_maxpool_fwd_kernel(const float* __restrict__ x, long long total, int H,
   const float* xp = x + (size_t)n * H * W * C + c;
   int h0 = win_start(oy, H, OH), h1 = win_end(oy, H, OH);
   int w0 = win_start(ox, W, OW), w1 = win_end(ox, W, OW);
-  float best = -INFINITY;
-  int bi = h0 * W + w0;
+  float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int bi[4];
+  bi[0] = bi[1] = bi[2] = bi[3] = h0 * W + w0;
   for (int h = h0; h < h1; ++h)
     for (int w = w0; w < w1; ++w) {
-      float v = __ldg(xp + (size_t)(h * W + w) * C);
-      if (v > best || v != v) {  // torch: (val > max) || isnan(val)
-        best = v;
-        bi = h * W + w;
+      F4 xv = ld4(xp + (size_t)(h * W + w) * C);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = xv.v[j];
+        if (v > best[j] || v != v) {  // torch: (val > max) || isnan(val)
+          best[j] = v;
+          bi[j] = h * W + w;
+        }
       }
     }
-  y[i] = best;
-  idx[i] = bi;
+  *reinterpret_cast<float4*>(y + i * 4) = make_float4(best[0], best[1], best[2], best[3]);
+  *reinterpret_cast<int4*>(idx + i * 4) = make_int4(bi[0], bi[1], bi[2], bi[3]);
 }
 
 __global__ void __launch_bounds__(256)
 adaptive_maxpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx,
-                            long long total, int H, int W, int C, int OH, int OW,
+                            long long total4, int H, int W, int C, int OH, int OW,
                             float* __restrict__ dx) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int c = (int)(i % C);
-  long long t = i / C;
+  if (i >= total4) return;
+  const int C4 = C >> 2;
+  int c = (int)(i % C4) * 4;
+  long long t = i / C4;
   int w = (int)(t % W);
   t /= W;
   int h = (int)(t % H);
@@ -158,16 +186,21 @@ adaptive_maxpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restr
   const int me = h * W + w;
   int oy_lo = max(0, (h * OH) / H - 1), oy_hi = min(OH - 1, ((h + 1) * OH + H - 1) / H);
   int ox_lo = max(0, (w * OW) / W - 1), ox_hi = min(OW - 1, ((w + 1) * OW + W - 1) / W);
-  float s = 0.f;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
   for (int oy = oy_lo; oy <= oy_hi; ++oy) {
     if (h < win_start(oy, H, OH) || h >= win_end(oy, H, OH)) continue;
     for (int ox = ox_lo; ox <= ox_hi; ++ox) {
       if (w < win_start(ox, W, OW) || w >= win_end(ox, W, OW)) continue;
       size_t o = (((size_t)n * OH + oy) * OW + ox) * C + c;
-      if (__ldg(idx + o) == me) s += __ldg(dy + o);
+      int4 id = __ldg(reinterpret_cast<const int4*>(idx + o));
+      F4 d = ld4(dy + o);
+      if (id.x == me) s[0] += d.v[0];
+      if (id.y == me) s[1] += d.v[1];
+      if (id.z == me) s[2] += d.v[2];
+      if (id.w == me) s[3] += d.v[3];
     }
   }
-  dx[i] = s;
+  *reinterpret_cast<float4*>(dx + i * 4) = make_float4(s[0], s[1], s[2], s[3]);
 }
 
 // torch upsample_bilinear2d, align_corners=False: src = scale*(dst+0.5)-0.5 clamped at 0
@@ -183,12 +216,13 @@ __device__ __forceinline__ void bilinear_src(int d, float scale, int in, int& i0
 }
 
 __global__ void __launch_bounds__(256)
-upsample_fwd_kernel(const float* __restrict__ x, long long total, int H, int W, int C, int OH,
+upsample_fwd_kernel(const float* __restrict__ x, long long total4, int H, int W, int C, int OH,
                     int OW, float sh, float sw, float* __restrict__ y, int ldy, int coff) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int c = (int)(i % C);
-  long long t = i / C;
+  if (i >= total4) return;
+  const int C4 = C >> 2;
+  int c = (int)(i % C4) * 4;
+  long long t = i / C4;
   int ox = (int)(t % OW);
   t /= OW;
   int oy = (int)(t % OH);
@@ -198,21 +232,25 @@ upsample_fwd_kernel(const float* __restrict__ x, long long total, int H, int W, 
   bilinear_src(oy, sh, H, y0, y1, ly0, ly1);
   bilinear_src(ox, sw, W, x0, x1, lx0, lx1);
   const float* xp = x + (size_t)n * H * W * C + c;
-  float v00 = __ldg(xp + (size_t)(y0 * W + x0) * C), v01 = __ldg(xp + (size_t)(y0 * W + x1) * C);
-  float v10 = __ldg(xp + (size_t)(y1 * W + x0) * C), v11 = __ldg(xp + (size_t)(y1 * W + x1) * C);
-  float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
-  y[(((size_t)n * OH + oy) * OW + ox) * ldy + coff + c] = v;
+  F4 v00 = ld4(xp + (size_t)(y0 * W + x0) * C), v01 = ld4(xp + (size_t)(y0 * W + x1) * C);
+  F4 v10 = ld4(xp + (size_t)(y1 * W + x0) * C), v11 = ld4(xp + (size_t)(y1 * W + x1) * C);
+  F4 o;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o.v[j] = ly0 * (lx0 * v00.v[j] + lx1 * v01.v[j]) + ly1 * (lx0 * v10.v[j] + lx1 * v11.v[j]);
+  st4(y + (((size_t)n * OH + oy) * OW + ox) * ldy + coff + c, o);
 }
 
 // gather form of the bilinear backward: each input pixel sums over the (few) output pixels
 // whose 2x2 footprint contains it.  Output range bounded from the scale.
 __global__ void __launch_bounds__(256)
-upsample_bwd_kernel(const float* __restrict__ dy, int lddy, int coff, long long total, int H,
+upsample_bwd_kernel(const float* __restrict__ dy, int lddy, int coff, long long total4, int H,
                     int W, int C, int OH, int OW, float sh, float sw, float* __restrict__ dx) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int c = (int)(i % C);
-  long long t = i / C;
+  if (i >= total4) return;
+  const int C4 = C >> 2;
+  int c = (int)(i % C4) * 4;
+  long long t = i / C4;
   int w = (int)(t % W);
   t /= W;
   int h = (int)(t % H);
@@ -222,7 +260,7 @@ upsample_bwd_kernel(const float* __restrict__ dy, int lddy, int coff, long long 
   int oy_hi = min(OH - 1, (int)ceilf(((float)h + 1.5f) / sh + 0.5f));
   int ox_lo = max(0, (int)floorf(((float)w - 0.5f) / sw - 1.5f));
   int ox_hi = min(OW - 1, (int)ceilf(((float)w + 1.5f) / sw + 0.5f));
-  float s = 0.f;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
   for (int oy = oy_lo; oy <= oy_hi; ++oy) {
     int y0, y1;
     float ly0, ly1;
@@ -235,10 +273,13 @@ upsample_bwd_kernel(const float* __restrict__ dy, int lddy, int coff, long long 
       bilinear_src(ox, sw, W, x0, x1, lx0, lx1);
       float wx = (x0 == w ? lx0 : 0.f) + (x1 == w ? lx1 : 0.f);
       if (wx == 0.f) continue;
-      s = fmaf(wy * wx, __ldg(dy + (((size_t)n * OH + oy) * OW + ox) * lddy + coff + c), s);
+      F4 d = ld4(dy + (((size_t)n * OH + oy) * OW + ox) * lddy + coff + c);
+      const float wt = wy * wx;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[j] = fmaf(wt, d.v[j], s[j]);
     }
   }
-  dx[i] = s;
+  *reinterpret_cast<float4*>(dx + i * 4) = make_float4(s[0], s[1], s[2], s[3]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -251,6 +292,24 @@ copy_channels_kernel(const float* __restrict__ x, long long total, int C, int ld
   float v = __ldg(x + r * ldx + xoff + c);
   float* o = y + r * ldy + coff + c;
   *o = accumulate ? *o + v : v;
+}
+
+__global__ void __launch_bounds__(256)
+copy_channels4_kernel(const float* __restrict__ x, long long total4, int C, int ldx, int xoff,
+                      float* __restrict__ y, int ldy, int coff, int accumulate) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int C4 = C >> 2;
+  int c = (int)(i % C4) * 4;
+  long long r = i / C4;
+  F4 v = ld4(x + r * ldx + xoff + c);
+  float* o = y + r * ldy + coff + c;
+  if (accumulate) {
+    F4 a(*reinterpret_cast<float4*>(o));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v.v[j] += a.v[j];
+  }
+  st4(o, v);
 }
 
 }  // namespace
@@ -278,7 +337,8 @@ int nhwc_to_nchw(const float* x, int N, int C, int H, int W, float* y, cudaStrea
 int in_relu_maxpool(const float* x, int N, int H, int W, int C, const float* mean,
                     const float* rstd, float* y, int32_t* idx, cudaStream_t s) {
   int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
-  long long total = (long long)N * OH * OW * C;
+  EVE_REQUIRE(C % 4 == 0, EVE_ERR_SHAPE, "in_relu_maxpool: C must be a multiple of 4");
+  long long total = (long long)N * OH * OW * (C / 4);
   in_relu_maxpool_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, H, W, C, OH, OW, mean, rstd, y,
                                                           idx);
   EVE_LAUNCH_CHECK();
@@ -287,7 +347,8 @@ int in_relu_maxpool(const float* x, int N, int H, int W, int C, const float* mea
 
 int maxpool_bwd_scatter(const float* dy, const int32_t* idx, int N, int H, int W, int OH, int OW,
                         int C, float* g, cudaStream_t s) {
-  long long total = (long long)N * H * W * C;
+  EVE_REQUIRE(C % 4 == 0, EVE_ERR_SHAPE, "maxpool_bwd: C must be a multiple of 4");
+  long long total = (long long)N * H * W * (C / 4);
   maxpool_bwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(dy, idx, total, H, W, OH, OW, C, g);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
@@ -308,7 +369,8 @@ int avgpool_bwd(const float* dy, int N, int HW, int C, float* dx, cudaStream_t s
 
 int adaptive_maxpool_fwd(const float* x, int N, int H, int W, int C, int OH, int OW, float* y,
                          int32_t* idx, cudaStream_t s) {
-  long long total = (long long)N * OH * OW * C;
+  EVE_REQUIRE(C % 4 == 0, EVE_ERR_SHAPE, "adaptive_maxpool: C must be a multiple of 4");
+  long long total = (long long)N * OH * OW * (C / 4);
   adaptive_maxpool_fwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, H, W, C, OH, OW, y, idx);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
@@ -316,7 +378,8 @@ int adaptive_maxpool_fwd(const float* x, int N, int H, int W, int C, int OH, int
 
 int adaptive_maxpool_bwd(const float* dy, const int32_t* idx, int N, int H, int W, int C, int OH,
                          int OW, float* dx, cudaStream_t s) {
-  long long total = (long long)N * H * W * C;
+  EVE_REQUIRE(C % 4 == 0, EVE_ERR_SHAPE, "adaptive_maxpool: C must be a multiple of 4");
+  long long total = (long long)N * H * W * (C / 4);
   adaptive_maxpool_bwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(dy, idx, total, H, W, C, OH, OW,
                                                                dx);
   EVE_LAUNCH_CHECK();
@@ -325,7 +388,9 @@ int adaptive_maxpool_bwd(const float* dy, const int32_t* idx, int N, int H, int 
 
 int upsample_bilinear_fwd(const float* x, int N, int H, int W, int C, int OH, int OW, float* y,
                           int ldy, int coff, cudaStream_t s) {
-  long long total = (long long)N * OH * OW * C;
+  EVE_REQUIRE(C % 4 == 0 && ldy % 4 == 0 && coff % 4 == 0, EVE_ERR_SHAPE,
+              "upsample_bilinear: channel counts must be multiples of 4");
+  long long total = (long long)N * OH * OW * (C / 4);
   float sh = (float)H / (float)OH, sw = (float)W / (float)OW;
   upsample_fwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, H, W, C, OH, OW, sh, sw, y, ldy,
                                                        coff);
@@ -335,7 +400,9 @@ int upsample_bilinear_fwd(const float* x, int N, int H, int W, int C, int OH, in
 
 int upsample_bilinear_bwd(const float* dy, int lddy, int coff, int N, int H, int W, int C, int OH,
                           int OW, float* dx, cudaStream_t s) {
-  long long total = (long long)N * H * W * C;
+  EVE_REQUIRE(C % 4 == 0 && lddy % 4 == 0 && coff % 4 == 0, EVE_ERR_SHAPE,
+              "upsample_bilinear: channel counts must be multiples of 4");
+  long long total = (long long)N * H * W * (C / 4);
   float sh = (float)H / (float)OH, sw = (float)W / (float)OW;
   upsample_bwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(dy, lddy, coff, total, H, W, C, OH, OW, sh,
                                                        sw, dx);
@@ -345,6 +412,13 @@ int upsample_bilinear_bwd(const float* dy, int lddy, int coff, int N, int H, int
 
 int copy_channels(const float* x, long long rows, int C, int ldx, int xoff, float* y, int ldy,
                   int coff, bool accumulate, cudaStream_t s) {
+  if (C % 4 == 0 && ldx % 4 == 0 && xoff % 4 == 0 && ldy % 4 == 0 && coff % 4 == 0) {
+    long long total4 = rows * (C / 4);
+    copy_channels4_kernel<<<cdiv(total4, 256), 256, 0, s>>>(x, total4, C, ldx, xoff, y, ldy, coff,
+                                                            accumulate ? 1 : 0);
+    EVE_LAUNCH_CHECK();
+    return EVE_OK;
+  }
   long long total = rows * C;
   copy_channels_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, C, ldx, xoff, y, ldy, coff,
                                                         accumulate ? 1 : 0);

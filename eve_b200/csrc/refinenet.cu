@@ -18,6 +18,7 @@ constexpr int kLevelH[kLevels] = {72, 36, 18, 9, 5};
 constexpr int kLevelW[kLevels] = {128, 64, 32, 16, 8};
 constexpr int kLevelC[kLevels] = {16, 32, 64, 128, 256};  // channels entering each level
 constexpr int kMaxRCells = 4;
+constexpr int kInitC = 16;   // initial.0 input channels after zero padding
 
 struct RBlock {
   int ic, oc, H, W, act, slot;
@@ -154,11 +155,11 @@ bool build_rnet(const eve_refinenet_params& p, Arena& sv, RNet& n) {
   // ---- saved activations
   const int H0 = kLevelH[0], W0 = kLevelW[0];
   const size_t P0 = (size_t)N * H0 * W0;
-  n.gi0 = make_conv(N, H0, W0, p.in_channels, 16, 3, 1, 1);
+  n.gi0 = make_conv(N, H0, W0, kInitC, 16, 3, 1, 1);   // input zero-padded to 16 channels
   n.gi3 = make_conv(N, H0, W0, 16, 16, 3, 1, 1);
   n.gf0 = make_conv(N, H0, W0, 16, 16, 3, 1, 1);
   n.gf2 = make_conv(N, H0, W0, 16, 1, 1, 1, 0);
-  n.x0 = sv.get<float>(P0 * p.in_channels);
+  n.x0 = sv.get<float>(P0 * kInitC);
   n.i0 = sv.get<float>(P0 * 16);
   n.im = sv.get<float>((size_t)N * 16);
   n.ir = sv.get<float>((size_t)N * 16);
@@ -211,24 +212,138 @@ bool build_rnet(const eve_refinenet_params& p, Arena& sv, RNet& n) {
     alloc_block(k, N, sv, n.max_act);
   }
   n.f0 = sv.get<float>(P0 * 16);
-  n.f1 = sv.get<float>(P0 * 16);
+  n.f1 = nullptr;
   n.sig = sv.get<float>(P0);
   return sv.ok();
 }
 
 // ------------------------------------------------------------------ small kernels --
-// x0[n,h,w,4] = (screen[n,0..2,h,w], heatmap[n,0,h,w])
+// x0[n,h,w,16] = (screen[n,0..2,h,w], heatmap[n,0,h,w], 0 ...)  or  (heatmap, 0 ...)
 __global__ void __launch_bounds__(256)
 pack_input_kernel(const float* __restrict__ screen, const float* __restrict__ hm, long long total,
                   int HW, float* __restrict__ x0) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  long long n = i / HW;
-  int p = (int)(i % HW);
-  const float* sp = screen + n * 3 * HW + p;
-  reinterpret_cast<float4*>(x0)[i] = make_float4(sp[0], sp[HW], sp[2 * HW], hm[i]);
+  float4 v;
+  if (screen) {
+    long long n = i / HW;
+    int p = (int)(i % HW);
+    const float* sp = screen + n * 3 * HW + p;
+    v = make_float4(sp[0], sp[HW], sp[2 * HW], hm[i]);
+  } else {
+    v = make_float4(hm[i], 0.f, 0.f, 0.f);
+  }
+  float4* o = reinterpret_cast<float4*>(x0 + i * kInitC);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  o[0] = v; o[1] = z; o[2] = z; o[3] = z;
 }
 
+// Fused head (refine_net.py:220-224 after final.0): LeakyReLU -> conv1x1 (16 -> 1) -> sigmoid.
+// One thread per pixel reads its 16 channels (64 bytes) once.
+constexpr int kHeadC = 16;
+__global__ void __launch_bounds__(256)
+final_head_fwd_kernel(const float* __restrict__ f0, const float* __restrict__ w,
+                      const float* __restrict__ b, long long rows, float* __restrict__ out,
+                      float* __restrict__ sig) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float4* fp = reinterpret_cast<const float4*>(f0 + i * kHeadC);
+  float acc = __ldg(b);
+#pragma unroll
+  for (int q = 0; q < kHeadC / 4; ++q) {
+    float4 v = __ldg(fp + q);
+    float4 ww = __ldg(reinterpret_cast<const float4*>(w) + q);
+    acc = fmaf(v.x > 0.f ? v.x : 0.01f * v.x, ww.x, acc);
+    acc = fmaf(v.y > 0.f ? v.y : 0.01f * v.y, ww.y, acc);
+    acc = fmaf(v.z > 0.f ? v.z : 0.01f * v.z, ww.z, acc);
+    acc = fmaf(v.w > 0.f ? v.w : 0.01f * v.w, ww.w, acc);
+  }
+  float sg = 1.f / (1.f + expf(-acc));
+  out[i] = sg;
+  sig[i] = sg;
+}
+
+// backward of the fused head: df0 = dpre * w * leaky'(f0), per-block partial sums of
+// dW[c] = sum dpre * leaky(f0)[c] and db = sum dpre  (part[block][17])
+__global__ void __launch_bounds__(256)
+final_head_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ sig,
+                      const float* __restrict__ f0, const float* __restrict__ w, long long rows,
+                      float* __restrict__ df0, float* __restrict__ part) {
+  __shared__ float sm[8][kHeadC + 1];
+  float acc[kHeadC + 1];
+#pragma unroll
+  for (int c = 0; c <= kHeadC; ++c) acc[c] = 0.f;
+  float wv[kHeadC];
+#pragma unroll
+  for (int c = 0; c < kHeadC; ++c) wv[c] = __ldg(w + c);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float sg = __ldg(sig + i);
+    const float dpre = __ldg(dout + i) * sg * (1.f - sg);
+    const float4* fp = reinterpret_cast<const float4*>(f0 + i * kHeadC);
+    float4* dp = reinterpret_cast<float4*>(df0 + i * kHeadC);
+#pragma unroll
+    for (int q = 0; q < kHeadC / 4; ++q) {
+      float4 v = __ldg(fp + q);
+      float x[4] = {v.x, v.y, v.z, v.w}, d[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool pos = x[j] > 0.f;
+        acc[q * 4 + j] = fmaf(dpre, pos ? x[j] : 0.01f * x[j], acc[q * 4 + j]);
+        d[j] = dpre * wv[q * 4 + j] * (pos ? 1.f : 0.01f);
+      }
+      dp[q] = make_float4(d[0], d[1], d[2], d[3]);
+    }
+    acc[kHeadC] += dpre;
+  }
+#pragma unroll
+  for (int c = 0; c <= kHeadC; ++c) {
+    float v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5][c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x <= kHeadC) {
+    float v = 0.f;
+    for (int wp = 0; wp < 8; ++wp) v += sm[wp][threadIdx.x];
+    part[(size_t)blockIdx.x * (kHeadC + 1) + threadIdx.x] = v;
+  }
+}
+
+__global__ void final_head_reduce_kernel(const float* __restrict__ part, int nblocks,
+                                         float* __restrict__ dw, float* __restrict__ db,
+                                         int accumulate) {
+  int c = threadIdx.x;
+  if (c > kHeadC) return;
+  double a = 0.0;
+  for (int b = 0; b < nblocks; ++b) a += (double)part[(size_t)b * (kHeadC + 1) + c];
+  float* dst = c < kHeadC ? (dw ? dw + c : nullptr) : db;
+  if (dst) *dst = accumulate ? *dst + (float)a : (float)a;
+}
+constexpr int kHeadBlocks = 148 * 4;
+
+// initial.0 runs on the tensor cores with its 4 (or 1) input channels zero-padded to 16:
+// w[16][in_c][3][3] <-> wp[16][16][3][3]
+__global__ void pad_cin_kernel(const float* __restrict__ w, int cout, int cin, int cpad,
+                               float* __restrict__ wp) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * cpad * 9) return;
+  int t = i % 9;
+  int ci = (i / 9) % cpad;
+  int co = i / (9 * cpad);
+  wp[i] = ci < cin ? w[((size_t)co * cin + ci) * 9 + t] : 0.f;
+}
+__global__ void unpad_cin_kernel(const float* __restrict__ dwp, int cout, int cin, int cpad,
+                                 float* __restrict__ dw, int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * cin * 9) return;
+  int t = i % 9;
+  int ci = (i / 9) % cin;
+  int co = i / (9 * cin);
+  float v = dwp[((size_t)co * cpad + ci) * 9 + t];
+  dw[i] = accumulate ? dw[i] + v : v;
+}
 // x[A][Bd][P][ldx] (first C channels) -> y[Bd][A][P][ldy] (first C channels)
 __global__ void __launch_bounds__(256)
 swap_bt_kernel(const float* __restrict__ x, long long total, int A, int Bd, int P, int C, int ldx,
@@ -406,16 +521,13 @@ int block_bwd(const RBlock& k, int N, const float* const* w, float* const* gr, b
   const float* const* bw = w + k.slot;
   float* const* bg = gr + k.slot;
   const int HW = k.H * k.W;
-  EVE_TRY(conv_param_grads(k.g2, k.y2, dout, bg[6], bg[7], sc.cs, acc, s));
-  EVE_TRY(conv_dgrad(k.g2, dout, bw[6], nullptr, sc.t0, sc.cs, s));
+  EVE_TRY(conv_bwd(k.g2, k.y2, dout, bw[6], bg[6], bg[7], acc, nullptr, sc.t0, sc.cs, s));
   EVE_TRY(in_backward(sc.t0, k.y2, k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], k.act, nullptr,
                       sc.t1, nullptr, bg[4], bg[5], sc.inb, acc, s));
-  EVE_TRY(conv_param_grads(k.g1, k.y1, sc.t1, bg[2], bg[3], sc.cs, acc, s));
-  EVE_TRY(conv_dgrad(k.g1, sc.t1, bw[2], nullptr, sc.t0, sc.cs, s));
+  EVE_TRY(conv_bwd(k.g1, k.y1, sc.t1, bw[2], bg[2], bg[3], acc, nullptr, sc.t0, sc.cs, s));
   const float* addend = dout;
   if (k.skipconv) {
-    EVE_TRY(conv_param_grads(k.gs, k.s, dout, bg[10], bg[11], sc.cs, acc, s));
-    EVE_TRY(conv_dgrad(k.gs, dout, bw[10], nullptr, sc.t2, sc.cs, s));
+    EVE_TRY(conv_bwd(k.gs, k.s, dout, bw[10], bg[10], bg[11], acc, nullptr, sc.t2, sc.cs, s));
     EVE_TRY(in_backward(sc.t2, k.s, k.x, N, HW, k.ic, k.m0, k.r0, bw[8], bw[9], k.act, nullptr,
                         sc.t1, nullptr, bg[8], bg[9], sc.inb, acc, s));
     addend = sc.t1;
@@ -488,7 +600,7 @@ size_t rnet_fwd_scratch_bytes(const RNet& n) {
   const int P = kLevelH[4] * kLevelW[4];
   return align_up(rnet_conv_scratch_bytes(n), 256) +
          4 * align_up((size_t)n.B * P * 4 * n.nf * sizeof(float), 256) +
-         2 * align_up((size_t)kMaxRCells * n.B * P * n.nf * sizeof(float), 256) + 4096;
+         2 * align_up((size_t)kMaxRCells * n.B * P * n.nf * sizeof(float), 256) + 4096 + 16384;
 }
 
 }  // namespace
@@ -567,13 +679,12 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
   const int HW0 = kLevelH[0] * kLevelW[0];
 
   // ---- input + initial
-  if (p->in_channels == 4) {
-    LAUNCH1D(pack_input_kernel, (long long)N * HW0, screen, heatmap, (long long)N * HW0, HW0, n.x0);
-  } else {
-    EVE_CUDA(cudaMemcpyAsync(n.x0, heatmap, (size_t)N * HW0 * sizeof(float),
-                             cudaMemcpyDeviceToDevice, s));
-  }
-  EVE_TRY(conv_fwd(n.gi0, n.x0, w[0], w[1], nullptr, n.i0, cs, s));
+  LAUNCH1D(pack_input_kernel, (long long)N * HW0, p->in_channels == 4 ? screen : nullptr, heatmap,
+           (long long)N * HW0, HW0, n.x0);
+  float* w0p = ws.get<float>((size_t)16 * kInitC * 9);
+  EVE_REQUIRE(w0p, EVE_ERR_WORKSPACE, "refinenet_fwd: workspace too small");
+  LAUNCH1D(pad_cin_kernel, 16 * kInitC * 9, w[0], 16, p->in_channels, kInitC, w0p);
+  EVE_TRY(conv_fwd(n.gi0, n.x0, w0p, w[1], nullptr, n.i0, cs, s));
   EVE_TRY(in_stats(n.i0, N, HW0, 16, n.im, n.ir, s));
   EVE_TRY(in_apply(n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], nullptr, nullptr, nullptr, ACT_RELU,
                    n.i1, s));
@@ -685,10 +796,8 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
   // ---- final: conv3x3 -> LeakyReLU -> conv1x1 -> sigmoid
   const float* const* fw = w + n.slot_final;
   EVE_TRY(conv_fwd(n.gf0, n.dec[0].out, fw[0], fw[1], nullptr, n.f0, cs, s));
-  EVE_TRY(ew_fwd(EW_LEAKY, n.f0, (long long)N * HW0 * 16, n.f1, s));
-  EVE_TRY(conv_fwd(n.gf2, n.f1, fw[2], fw[3], nullptr, out, cs, s));
-  EVE_TRY(ew_fwd(EW_SIGMOID, out, (long long)N * HW0, n.sig, s));
-  EVE_CUDA(cudaMemcpyAsync(out, n.sig, (size_t)N * HW0 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  LAUNCH1D(final_head_fwd_kernel, (long long)N * HW0, n.f0, fw[2], fw[3], (long long)N * HW0, out,
+           n.sig);
   return EVE_OK;
 }
 
@@ -725,14 +834,17 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
   // ---- final
   const float* const* fw = w + n.slot_final;
   float* const* fg = gr + n.slot_final;
-  EVE_TRY(ew_bwd(EW_SIGMOID, dout, n.sig, (long long)N * HW0, sc.t0, s));
-  EVE_TRY(conv_param_grads(n.gf2, n.f1, sc.t0, fg[2], fg[3], sc.cs, acc, s));
-  EVE_TRY(conv_dgrad(n.gf2, sc.t0, fw[2], nullptr, sc.t1, sc.cs, s));
-  EVE_TRY(ew_bwd(EW_LEAKY, sc.t1, n.f0, (long long)N * HW0 * 16, sc.t2, s));
-  EVE_TRY(conv_param_grads(n.gf0, n.dec[0].out, sc.t2, fg[0], fg[1], sc.cs, acc, s));
+  {
+    float* hpart = sc.t0;   // [kHeadBlocks][17]
+    final_head_bwd_kernel<<<kHeadBlocks, 256, 0, s>>>(dout, n.sig, n.f0, fw[2], (long long)N * HW0,
+                                                      sc.t2, hpart);
+    EVE_LAUNCH_CHECK();
+    final_head_reduce_kernel<<<1, 32, 0, s>>>(hpart, kHeadBlocks, fg[2], fg[3], acc ? 1 : 0);
+    EVE_LAUNCH_CHECK();
+  }
   float* cur = sc.ga;
   float* other = sc.gb;
-  EVE_TRY(conv_dgrad(n.gf0, sc.t2, fw[0], nullptr, cur, sc.cs, s));
+  EVE_TRY(conv_bwd(n.gf0, n.dec[0].out, sc.t2, fw[0], fg[0], fg[1], acc, nullptr, cur, sc.cs, s));
 
   // ---- decoder, outermost first
   for (int l = 0; l < 4; ++l) {
@@ -844,15 +956,24 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
     }
   }
   // ---- initial
-  EVE_TRY(conv_param_grads(n.gi3, n.i1, cur, gr[4], gr[5], sc.cs, acc, s));
-  EVE_TRY(conv_dgrad(n.gi3, cur, w[4], nullptr, sc.t0, sc.cs, s));
+  EVE_TRY(conv_bwd(n.gi3, n.i1, cur, w[4], gr[4], gr[5], acc, nullptr, sc.t0, sc.cs, s));
   EVE_TRY(in_backward(sc.t0, n.i1, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU, nullptr,
                       sc.t1, nullptr, gr[2], gr[3], sc.inb, acc, s));
-  EVE_TRY(conv_param_grads(n.gi0, n.x0, sc.t1, gr[0], gr[1], sc.cs, acc, s));
-  if (dheatmap) {
-    EVE_TRY(conv_dgrad(n.gi0, sc.t1, w[0], nullptr, sc.t0, sc.cs, s));
-    EVE_TRY(copy_channels(sc.t0, (long long)N * HW0, 1, p->in_channels, p->in_channels - 1, dheatmap,
-                          1, 0, false, s));
+  {
+    // zero-padded weights (and their gradient) live at the head of t2, which is free here
+    float* w0p = sc.t2;
+    float* dw0p = sc.t2 + 16 * kInitC * 9;
+    LAUNCH1D(pad_cin_kernel, 16 * kInitC * 9, w[0], 16, p->in_channels, kInitC, w0p);
+    EVE_TRY(conv_bwd(n.gi0, n.x0, sc.t1, w0p, gr[0] ? dw0p : nullptr, nullptr, false, nullptr,
+                     dheatmap ? sc.t0 : nullptr, sc.cs, s));
+    if (gr[1])
+      EVE_TRY(colsum(sc.t1, (long long)N * HW0, 16, 16, gr[1], sc.t2 + 2 * 16 * kInitC * 9, acc, s));
+    if (gr[0])
+      LAUNCH1D(unpad_cin_kernel, 16 * p->in_channels * 9, dw0p, 16, p->in_channels, kInitC, gr[0],
+               acc ? 1 : 0);
+    if (dheatmap)
+      EVE_TRY(copy_channels(sc.t0, (long long)N * HW0, 1, kInitC, p->in_channels - 1, dheatmap, 1, 0,
+                            false, s));
   }
   return EVE_OK;
 }

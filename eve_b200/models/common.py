@@ -6,8 +6,11 @@ three memory-bound pieces -- ``to_screen_coordinates`` (:149-179), ``batch_make_
 C ABI (eve_b200/ops.py), the remaining per-sample 3x3 algebra is batched torch arithmetic on
 the GPU (no Python loop over the batch, unlike :243, :276-287).
 """
+import math
+
 import torch
 import torch.nn.functional as F
+from torch import nn
 
 from .. import ops
 from ..config import get_config
@@ -186,3 +189,80 @@ def all_gaze_history_maps(history_timestamps, heatmaps, validity):
     wgt = gaze_history_weights(history_timestamps, validity)            # [B, T, T]
     flat = heatmaps.reshape(B, T, -1)
     return torch.bmm(wgt.detach(), flat).reshape(heatmaps.shape)
+
+
+# ------------------------------------------------------------------- ConvRNN cells --
+# Stand-alone modules with the reference's names, constructor arguments, parameter names and
+# per-step forward contract (common.py:326-415).  RefineNet itself runs these recurrences inside
+# eve_refinenet_{fwd,bwd} over whole sequences; the classes exist so that code importing them
+# from ``models.common`` keeps working, and they execute the same library convolution.
+class Flatten(nn.Module):
+    def forward(self, x):
+        return x.view(x.size()[0], -1)
+
+
+class _ConvParam(nn.Module):
+    """Holds ``weight`` / ``bias`` under the name the reference's nn.Conv2d child had."""
+
+    def __init__(self, cin, cout, k=3):
+        super(_ConvParam, self).__init__()
+        fan_in = cin * k * k
+        bound = 1.0 / math.sqrt(fan_in)
+        self.weight = nn.Parameter((torch.rand(cout, cin, k, k) * 2 - 1) * bound)
+        self.bias = nn.Parameter((torch.rand(cout) * 2 - 1) * bound)
+        self.padding = k // 2
+
+    def forward(self, x):
+        return ops.conv2d(x, self.weight, self.bias, 1, self.padding)
+
+
+class CRNNCell(nn.Module):
+    """common.py:331-352: h' = tanh(conv3x3(cat[x, h]))."""
+
+    def __init__(self, input_size, hidden_size):
+        super(CRNNCell, self).__init__()
+        self.input_size, self.hidden_size = input_size, hidden_size
+        self.cell = _ConvParam(input_size + hidden_size, hidden_size)
+
+    def forward(self, x, previous_states=None):
+        h = previous_states
+        if h is None:
+            h = x.new_zeros([x.shape[0], self.hidden_size] + list(x.shape[2:]))
+        return torch.tanh(self.cell(torch.cat([x, h], dim=1)))
+
+
+class CLSTMCell(nn.Module):
+    """common.py:355-385: gates chunked as (in, forget, out, cell)."""
+
+    def __init__(self, input_size, hidden_size):
+        super(CLSTMCell, self).__init__()
+        self.input_size, self.hidden_size = input_size, hidden_size
+        self.gates = _ConvParam(input_size + hidden_size, 4 * hidden_size)
+
+    def forward(self, x, previous_states=None):
+        if previous_states is None:
+            shape = [x.shape[0], self.hidden_size] + list(x.shape[2:])
+            h, c = x.new_zeros(shape), x.new_zeros(shape)
+        else:
+            h, c = previous_states
+        gi, gf, go, gc = self.gates(torch.cat([x, h], dim=1)).chunk(4, 1)
+        cell = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gc)
+        return torch.sigmoid(go) * torch.tanh(cell), cell
+
+
+class CGRUCell(nn.Module):
+    """common.py:388-415 (note the [r*h, x] order of the second concatenation, :412)."""
+
+    def __init__(self, input_size, hidden_size):
+        super(CGRUCell, self).__init__()
+        self.input_size, self.hidden_size = input_size, hidden_size
+        self.gates_1 = _ConvParam(input_size + hidden_size, 2 * hidden_size)
+        self.gate_2 = _ConvParam(input_size + hidden_size, hidden_size)
+
+    def forward(self, x, previous_states=None):
+        h = previous_states
+        if h is None:
+            h = x.new_zeros([x.shape[0], self.hidden_size] + list(x.shape[2:]))
+        r, z = torch.sigmoid(self.gates_1(torch.cat([x, h], dim=1))).chunk(2, 1)
+        n = torch.tanh(self.gate_2(torch.cat([r * h, x], dim=1)))
+        return (1.0 - z) * n + z * h

@@ -26,6 +26,59 @@ def _bytes(nbytes, device, keep, tag):
     return L.workspace(nbytes, device, tag)
 
 
+# --------------------------------------------------------------------------- conv2d --
+class Conv2dFn(torch.autograd.Function):
+    """nn.Conv2d on NCHW tensors through eve_conv2d_{fwd,dgrad,wgrad} (used by the stand-alone
+    ConvRNN cell modules of models/common.py; the networks call the fused entries instead)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding):
+        L.require_cuda(x, 'conv2d')
+        lib = L.load()
+        x, weight, bias = _f32c(x), _f32c(weight), _f32c(bias)
+        n, cin, h, w = x.shape
+        cout, _, k, _ = weight.shape
+        p = L.ConvParams(n, h, w, cin, cout, k, int(stride), int(padding))
+        oh = (h + 2 * padding - k) // stride + 1
+        ow = (w + 2 * padding - k) // stride + 1
+        xh = x.permute(0, 2, 3, 1).contiguous()
+        yh = torch.empty((n, oh, ow, cout), dtype=torch.float32, device=x.device)
+        nbytes = lib.eve_conv2d_workspace_bytes(C.byref(p))
+        if nbytes == 0:
+            raise ValueError(L.last_error())
+        ws = L.workspace(nbytes, x.device)
+        L.check(lib.eve_conv2d_fwd(C.byref(p), L.ptr(xh), L.ptr(weight), L.ptr(bias), L.ptr(yh),
+                                   L.ptr(ws), ws.numel(), L.stream_ptr()), 'eve_conv2d_fwd')
+        ctx.p = p
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(xh, weight)
+        return yh.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        xh, weight = ctx.saved_tensors
+        p = ctx.p
+        dyh = _f32c(dy.permute(0, 2, 3, 1))
+        ws = L.workspace(lib.eve_conv2d_workspace_bytes(C.byref(p)), xh.device)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dxh = torch.empty_like(xh)
+            L.check(lib.eve_conv2d_dgrad(C.byref(p), L.ptr(dyh), L.ptr(weight), L.ptr(dxh), L.ptr(ws),
+                                         ws.numel(), L.stream_ptr()), 'eve_conv2d_dgrad')
+            dx = dxh.permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.empty_like(weight)
+            db = torch.empty(weight.shape[0], device=xh.device) if ctx.has_bias else None
+            L.check(lib.eve_conv2d_wgrad(C.byref(p), L.ptr(xh), L.ptr(dyh), L.ptr(dw), L.ptr(db),
+                                         L.ptr(ws), ws.numel(), L.stream_ptr()), 'eve_conv2d_wgrad')
+        return dx, dw, db, None, None
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0):
+    return Conv2dFn.apply(x, weight, bias, stride, padding)
+
+
 # ------------------------------------------------------------------------ EyeNet CNN --
 class EyeNetCnnFn(torch.autograd.Function):
     """ResNet-18/InstanceNorm features of eye patches (eye_net.py:106).

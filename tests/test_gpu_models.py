@@ -139,31 +139,57 @@ def test_eve_forward_backward_matches_reference(name, cfg, conv_mode):
         out['full_loss'].backward()
         params = dict(model.named_parameters())
         floor = 1e-5 * max(float(v) for k, v in gold.items() if k.startswith('gradnorm/'))
-        n = 0
+
+        def grad_errors(named):
+            errs = {}
+            for k, ref in gold.items():
+                if not k.startswith('gradnorm/'):
+                    continue
+                pname = k[len('gradnorm/'):]
+                g = named[pname].grad
+                assert g is not None, pname
+                sample = gold['grad/' + pname]
+                gf = g.reshape(-1).cpu().numpy()
+                gs = gf if gf.size <= 20000 else gf[::H.GRAD_STRIDE]
+                errs[pname] = (abs(float(g.double().norm()) - float(ref)), float(ref),
+                               float(np.linalg.norm(gs.astype(np.float64) - sample)),
+                               float(np.linalg.norm(sample.astype(np.float64))))
+            return errs
+
+        errs = grad_errors(params)
+        # RefineNet gradients at random weights carry several % of pure fp32 ordering noise
+        # (the reference's own fp32 run sits 0.4-1.2e-2 from an fp64 evaluation, see
+        # test_refinenet_sequences_* for the noise-relative check); observed up to 3.3e-2.
+        gtol = 5e-2
+        base = None
+        if tolx > 1:
+            # split-operand mode: additionally allow 3x whatever discrepancy the exact-fp32
+            # kernels show on the same tensor (i.e. summation-order noise alone) -- the EyeNet
+            # tail tensors that receive RefineNet's gradient through the heatmap are the
+            # noisiest (2 % in fp32 mode)
+            from eve_b200 import lib as L
+            lib = L.load()
+            lib.eve_set_conv_mode(0)
+            try:
+                twin = _load(EVE(output_predictions=True), H.case_state_dict(gold, cfg)).train()
+                np.random.seed(int(gold['meta/seed']))
+                twin({'synthetic': _cuda(H.case_inputs(gold, cfg))}, create_images=True,
+                     current_epoch=0.0)['full_loss'].backward()
+                base = grad_errors(dict(twin.named_parameters()))
+            finally:
+                lib.eve_set_conv_mode(1)
         bad = []
-        for k, ref in gold.items():
-            if not k.startswith('gradnorm/'):
-                continue
-            pname = k[len('gradnorm/'):]
-            g = params[pname].grad
-            assert g is not None, pname
-            gn = float(g.double().norm())
-            # (split-operand mode: EyeNet-tail tensors that also receive RefineNet's gradient
-            #  through the heatmap sit at 4.3 % L2 here; fp32 mode holds 2 %)
-            #  RefineNet gradients at random weights carry several % of pure fp32 ordering noise
-            #  (the reference's own fp32 run sits 0.4-1.2e-2 from an fp64 evaluation, see
-            #  test_refinenet_sequences_* for the noise-relative check); observed up to 3.3e-2.
-            gtol = 5e-2 if tolx == 1 else 6e-2
-            if abs(gn - float(ref)) > gtol * max(float(ref), 1e-6) + floor:
-                bad.append((pname, 'norm', gn, float(ref)))
-            sample = gold['grad/' + pname]
-            gf = g.reshape(-1).cpu().numpy()
-            gs = gf if gf.size <= 20000 else gf[::H.GRAD_STRIDE]
-            l2 = float(np.linalg.norm(gs.astype(np.float64) - sample))
-            lim = gtol * float(np.linalg.norm(sample.astype(np.float64))) + floor
-            if l2 > lim:
-                bad.append((pname, 'l2', l2, lim))
-            n += 1
+        for pname, (dn, rn, dl2, rl2) in errs.items():
+            lim_n = gtol * max(rn, 1e-6) + floor
+            lim_l = gtol * rl2 + floor
+            if base is not None:
+                lim_n = max(lim_n, 3.0 * base[pname][0])
+                lim_l = max(lim_l, 3.0 * base[pname][2])
+            if dn > lim_n:
+                bad.append((pname, 'norm', dn, lim_n))
+            if dl2 > lim_l:
+                bad.append((pname, 'l2', dl2, lim_l))
+        n = len(errs)
         assert not bad, bad
         for k in gold:
             if k.startswith('gradnone/'):
@@ -429,3 +455,40 @@ def test_empty_and_single_frame_inputs(cfg):
         assert net.cnn_features(torch.zeros(0, 3, 128, 128, device='cuda')).shape == (0, 128)
         f = net.cnn_features(torch.zeros(1, 3, 128, 128, device='cuda'))
         assert f.shape == (1, 128) and bool(torch.isfinite(f).all())
+
+
+@pytest.mark.parametrize('kind', ['CRNN', 'CLSTM', 'CGRU'])
+def test_standalone_conv_rnn_cells(cfg, kind, conv_mode):
+    """models.common.{CRNNCell, CLSTMCell, CGRUCell}: same parameter names as the reference
+    modules and the same step arithmetic (oracle: common.py:331-415), with gradients."""
+    from eve_b200.models import common as MC
+    tolx = conv_mode
+    cls = {'CRNN': MC.CRNNCell, 'CLSTM': MC.CLSTMCell, 'CGRU': MC.CGRUCell}[kind]
+    cell = cls(input_size=64, hidden_size=64).cuda()
+    names = {'CRNN': {'cell.weight', 'cell.bias'}, 'CLSTM': {'gates.weight', 'gates.bias'},
+             'CGRU': {'gates_1.weight', 'gates_1.bias', 'gate_2.weight', 'gate_2.bias'}}[kind]
+    assert set(cell.state_dict().keys()) == names
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 64, 5, 8, generator=g)
+    h = torch.randn(2, 64, 5, 8, generator=g) * 0.5
+    c = torch.randn(2, 64, 5, 8, generator=g) * 0.5
+    sd = {'p.' + k: v.detach().cpu().double().requires_grad_(True) for k, v in cell.state_dict().items()}
+    x64 = x.double().requires_grad_(True)
+    state = (h.double(), c.double()) if kind == 'CLSTM' else h.double()
+    want = O.conv_rnn_cell(kind, sd, 'p.', x64, state)
+    want_h = want[0] if kind == 'CLSTM' else want
+    want_h.sum().backward()
+    xc = x.cuda().requires_grad_(True)
+    got = cell(xc, (h.cuda(), c.cuda()) if kind == 'CLSTM' else h.cuda())
+    got_h = got[0] if kind == 'CLSTM' else got
+    assert G.rel(got_h, want_h) < 2e-5 * tolx
+    if kind == 'CLSTM':
+        assert G.rel(got[1], want[1]) < 2e-5 * tolx
+    got_h.sum().backward()
+    assert G.rel(xc.grad, x64.grad) < 1e-4 * tolx
+    for k, p in cell.named_parameters():
+        assert G.rel(p.grad, sd['p.' + k].grad) < 1e-4 * tolx, k
+    # zero initial state when no previous state is given (common.py:344-346)
+    with torch.no_grad():
+        first = cell(xc)
+    assert (first[0] if kind == 'CLSTM' else first).shape == (2, 64, 5, 8)
