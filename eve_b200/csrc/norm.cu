@@ -260,19 +260,27 @@ in_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ ymas
 }
 
 // dgamma[c] (+)= sum_n sum_gx[n,c]; dbeta[c] (+)= sum_n sum_g[n,c]
-__global__ void in_affine_grad_kernel(const float* __restrict__ sum_g,
-                                      const float* __restrict__ sum_gx, int N, int C,
-                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                      int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel, lanes stride over n (fixed order: deterministic), fp64 partials
+__global__ void __launch_bounds__(256)
+in_affine_grad_kernel(const float* __restrict__ sum_g, const float* __restrict__ sum_gx, int N,
+                      int C, float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double a = 0.0, b = 0.0;
-  for (int n = 0; n < N; ++n) {
+  for (int n = lane; n < N; n += 32) {
     a += (double)sum_gx[(size_t)n * C + c];
     b += (double)sum_g[(size_t)n * C + c];
   }
-  dgamma[c] = accumulate ? dgamma[c] + (float)a : (float)a;
-  dbeta[c] = accumulate ? dbeta[c] + (float)b : (float)b;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    dgamma[c] = accumulate ? dgamma[c] + (float)a : (float)a;
+    dbeta[c] = accumulate ? dbeta[c] + (float)b : (float)b;
+  }
 }
 
 // channel quads per block: up to 16 (64 channels), never more than the tensor has
@@ -320,7 +328,7 @@ int in_backward(const float* dy, const float* y_for_mask, const float* x, int N,
                                                         addend, dx, g_out);
   EVE_LAUNCH_CHECK();
   if (gamma && dgamma) {
-    in_affine_grad_kernel<<<cdiv(C, 128), 128, 0, s>>>(sum_g, sum_gx, N, C, dgamma, dbeta,
+    in_affine_grad_kernel<<<cdiv(C, 8), 256, 0, s>>>(sum_g, sum_gx, N, C, dgamma, dbeta,
                                                        accumulate_affine ? 1 : 0);
     EVE_LAUNCH_CHECK();
   }

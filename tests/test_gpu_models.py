@@ -496,3 +496,59 @@ def test_standalone_conv_rnn_cells(cfg, kind, conv_mode):
     with torch.no_grad():
         first = cell(xc)
     assert (first[0] if kind == 'CLSTM' else first).shape == (2, 64, 5, 8)
+
+
+def test_inference_stream_900_frames_in_chunks(cfg):
+    """BASELINE config 5 at full size: RefineNet over a 900-frame stream (B=1, no grad).
+    Size-independent property: processing the stream in three 300-frame chunks with the
+    ConvGRU state carried across chunk boundaries reproduces the one-shot result, and frames are
+    independent of the batch they were processed in (per-sample norms)."""
+    from eve_b200 import synth
+    from eve_b200.models import RefineNet
+    from eve_b200.models.common import batch_make_heatmaps
+    cfg.override('refine_net_enabled', True)
+    cfg.override('load_screen_content', True)
+    net = _load(RefineNet(), synth.make_state_dict(synth.refine_net_param_shapes(cfg), 11)).eval()
+    T = 900
+    g = torch.Generator().manual_seed(12)
+    px = torch.stack([torch.rand(1, T, generator=g) * 1920, torch.rand(1, T, generator=g) * 1080], -1)
+    screen = torch.rand(1, T, 3, 72, 128, generator=g).cuda()
+    with torch.no_grad():
+        hm = batch_make_heatmaps(px.cuda(), cfg.gaze_heatmap_sigma_initial)
+        full, hT, _ = net.sequence(screen, hm)
+        outs, state = [], None
+        for t0 in range(0, T, 300):
+            o, state, _ = net.sequence(screen[:, t0:t0 + 300], hm[:, t0:t0 + 300], state)
+            outs.append(o)
+        chunked = torch.cat(outs, 1)
+    assert full.shape == (1, T, 1, 72, 128)
+    assert bool(torch.isfinite(full).all())
+    assert torch.equal(chunked, full)
+    assert torch.equal(state, hT)
+    assert float(full.min()) > 0.0 and float(full.max()) < 1.0
+
+
+def test_long_clip_training_step_t60(cfg):
+    """BASELINE config 4 per-GPU shape (B=8, T=60, full EVE): one optimisation step runs,
+    the loss is finite, and the gradient norm equals the norm of the packed flat buffer."""
+    from eve_b200 import synth
+    from eve_b200.models import EVE
+    from eve_b200.parallel import FlatAdamTrainer
+    cfg.override('refine_net_enabled', True)
+    cfg.override('load_screen_content', True)
+    sd = synth.make_state_dict(synth.eye_net_param_shapes(cfg), 21, 'eye_net.')
+    sd.update(synth.make_state_dict(synth.refine_net_param_shapes(cfg), 1021, 'refine_net.'))
+    model = _load(EVE(), sd).train()
+    tr = FlatAdamTrainer(model, lr=1e-5)
+    inputs = _cuda(synth.make_clip_batch(8, 60, seed=3))
+    np.random.seed(0)
+    out = model({'x': inputs}, current_epoch=0.0)
+    assert out['left_pupil_size'].shape == (8, 60)
+    out['full_loss'].backward()
+    tr.gather_grads()
+    want = float(tr.grad.double().norm())
+    tr.apply()
+    assert np.isfinite(float(out['full_loss']))
+    assert abs(float(tr.last_grad_norm) - want) < 1e-4 * want
+    del out, model, tr
+    torch.cuda.empty_cache()
