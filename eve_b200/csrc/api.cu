@@ -2,6 +2,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -124,6 +126,63 @@ extern "C" size_t eve_conv2d_workspace_bytes(const eve_conv_params* p) {
   ConvGeom g;
   if (check_conv(p, g) != EVE_OK) return 0;
   return conv_ws_bytes(g);
+}
+
+// ---- tuning options (process-wide; see include/eve_b200.h)
+namespace eve {
+struct Opt {
+  const char* name;
+  int value, lo, hi;
+  const char* env;
+  bool env_read;
+};
+static Opt g_opts[OPT_COUNT] = {
+    {"tc_stage_cap", 24, 2, 24, "EVE_B200_TC_STAGE_CAP", false},
+    {"tc_row_kernel", 1, 0, 1, "EVE_B200_TC_ROW_KERNEL", false},
+    {"tc_row_base_offset", 1, 0, 1, "EVE_B200_TC_ROW_BASE_OFFSET", false},
+    {"tc_row_copies", 1, 1, 3, "EVE_B200_TC_ROW_COPIES", false},
+    {"tc_row_strips", 0, 0, 128, "EVE_B200_TC_ROW_STRIPS", false},
+    {"tc_row_wgrad", 1, 0, 1, "EVE_B200_TC_ROW_WGRAD", false},
+    {"tc_mixed_wgrad", 1, 0, 1, "EVE_B200_TC_MIXED_WGRAD", false},
+    {"fused_planes", 1, 0, 1, "EVE_B200_FUSED_PLANES", false},
+};
+int get_option(int key) {
+  if (key < 0 || key >= OPT_COUNT) return 0;
+  Opt& o = g_opts[key];
+  if (!o.env_read) {
+    o.env_read = true;
+    const char* e = getenv(o.env);
+    if (e) {
+      int v = atoi(e);
+      if (v >= o.lo && v <= o.hi) o.value = v;
+    }
+  }
+  return o.value;
+}
+}  // namespace eve
+
+extern "C" int eve_set_option(const char* name, int value) {
+  EVE_REQUIRE(name, EVE_ERR_NULL, "eve_set_option: name is NULL");
+  for (int k = 0; k < OPT_COUNT; ++k)
+    if (strcmp(g_opts[k].name, name) == 0) {
+      EVE_REQUIRE(value >= g_opts[k].lo && value <= g_opts[k].hi, EVE_ERR_CONFIG,
+                  "eve_set_option: %s=%d outside [%d, %d]", name, value, g_opts[k].lo, g_opts[k].hi);
+      g_opts[k].env_read = true;
+      g_opts[k].value = value;
+      return EVE_OK;
+    }
+  EVE_REQUIRE(false, EVE_ERR_CONFIG, "eve_set_option: unknown option '%s'", name);
+  return EVE_ERR_CONFIG;
+}
+extern "C" int eve_get_option(const char* name, int* value) {
+  EVE_REQUIRE(name && value, EVE_ERR_NULL, "eve_get_option: NULL argument");
+  for (int k = 0; k < OPT_COUNT; ++k)
+    if (strcmp(g_opts[k].name, name) == 0) {
+      *value = get_option(k);
+      return EVE_OK;
+    }
+  EVE_REQUIRE(false, EVE_ERR_CONFIG, "eve_get_option: unknown option '%s'", name);
+  return EVE_ERR_CONFIG;
 }
 
 extern "C" void eve_set_conv_mode(int mode) { set_conv_mode(mode); }

@@ -137,7 +137,7 @@ int conv_tc_dgrad_s2_run(const ConvGeom& g, const void* d_hi, const void* d_lo, 
 bool conv_tc_wgrad_supported(const ConvGeom& g);
 size_t conv_tc_wgrad_partial_floats(const ConvGeom& g);
 int conv_tc_wgrad_run(const ConvGeom& g, const void* d_hi, const void* d_lo, const void* x_hi,
-                      const void* x_lo, float* part, int npass, int* splits_out, cudaStream_t s);
+                      const void* x_lo, float* part, int npass, int* splits_out, cudaStream_t s, int x_fmt = TC_BF16);
 // dw_oihw (+)= sum over splits of part[z][co][(r*KW+q)*Cin+ci]
 int wgrad_reduce(const float* part, int splits, const ConvGeom& g, float* dw_oihw, bool accumulate,
                  cudaStream_t s);
@@ -151,6 +151,20 @@ int wgrad_reduce(const float* part, int splits, const ConvGeom& g, float* dw_oih
 //   mode 2: tcgen05, single bf16 pass (fastest, ~1e-2 relative error)
 int conv_mode();
 void set_conv_mode(int mode);
+// tuning options (eve_set_option / eve_get_option; every one has an EVE_B200_* env default)
+enum OptKey {
+  OPT_TC_STAGE_CAP = 0,      // max ring stages of the tcgen05 conv kernel
+  OPT_TC_ROW_KERNEL,         // halo-row tcgen05 kernel for 3x3 stride-1 layers with W == 128
+  OPT_TC_ROW_BASE_OFFSET,    // row-shifted descriptors carry base_offset = (addr >> 7) & 7
+  OPT_TC_ROW_COPIES,         // 1 = shifted descriptors, 2 = hybrid, 3 = three pre-shifted copies
+  OPT_TC_ROW_STRIPS,         // 0 = automatic; otherwise the number of row strips per image
+  OPT_TC_ROW_WGRAD,          // halo-row weight-gradient kernel (W == 128)
+  OPT_TC_MIXED_WGRAD,        // wgrad reads the forward's fp16 x planes next to bf16 dy planes
+  OPT_FUSED_PLANES,          // producers emit the 16-bit operand planes of the next convolution
+  OPT_COUNT
+};
+int get_option(int key);
+inline int tc_stage_cap() { return get_option(OPT_TC_STAGE_CAP); }
 struct ConvScratch {
   char* base;
   size_t bytes;

@@ -277,13 +277,16 @@ int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, fl
     uint16_t* x_hi = c.get<uint16_t>((size_t)g.in_elems());
     uint16_t* x_lo = c.get<uint16_t>((size_t)g.in_elems());
     EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_wgrad: scratch too small");
+    // x planes: fp16 (the forward's format, 22 mantissa bits) next to bf16 dy planes when the
+    // mixed-format weight gradient is enabled
+    const int xfmt = (npass == 3 && get_option(OPT_TC_MIXED_WGRAD)) ? TC_F16 : TC_BF16;
     EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
-    EVE_TRY(split_planes(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, TC_BF16, s));
+    EVE_TRY(split_planes(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, xfmt, s));
     int splits = 0;
     {
       ProfScope prof(PROF_CONV_WGRAD, 2.0 * g.out_elems() * (double)g.K(),
                      4.0 * (g.in_elems() + g.out_elems() + (double)g.Cout * g.K()), s);
-      EVE_TRY(conv_tc_wgrad_run(g, d_hi, d_lo, x_hi, x_lo, part, npass, &splits, s));
+      EVE_TRY(conv_tc_wgrad_run(g, d_hi, d_lo, x_hi, x_lo, part, npass, &splits, s, xfmt));
       EVE_TRY(wgrad_reduce(part, splits, g, dw, accumulate, s));
     }
     if (dbias)
@@ -358,15 +361,16 @@ int conv_bwd(const ConvGeom& g, const float* x, const float* dy, const float* w,
   uint16_t* x_hi = c.get<uint16_t>((size_t)g.in_elems());
   uint16_t* x_lo = c.get<uint16_t>((size_t)g.in_elems());
   EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_bwd: scratch too small");
+  const int xfmt = (npass == 3 && get_option(OPT_TC_MIXED_WGRAD)) ? TC_F16 : TC_BF16;
   EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
-  EVE_TRY(split_planes(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, TC_BF16, s));
+  EVE_TRY(split_planes(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, xfmt, s));
   EVE_TRY(conv_tc_prep_weights(g, w, true, w_hi, npass == 3 ? w_lo : nullptr, TC_BF16, 1.f, s));
   const double flops = 2.0 * g.out_elems() * (double)g.K();
   const double bytes = 4.0 * (g.in_elems() + g.out_elems() + (double)wel);
   {
     int splits = 0;
     ProfScope prof(PROF_CONV_WGRAD, flops, bytes, s);
-    EVE_TRY(conv_tc_wgrad_run(g, d_hi, d_lo, x_hi, x_lo, part, npass, &splits, s));
+    EVE_TRY(conv_tc_wgrad_run(g, d_hi, d_lo, x_hi, x_lo, part, npass, &splits, s, xfmt));
     EVE_TRY(wgrad_reduce(part, splits, g, dw, accumulate, s));
   }
   if (dbias)

@@ -284,20 +284,38 @@ __global__ void __launch_bounds__(NT) igemm_wgrad_kernel(WgradArgs a) {
 }
 
 // dw_oihw[co][ci][r][q] (+)= sum_z part[z][co][(r*KW+q)*Cin+ci]   (deterministic order)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int S, int Cout, int Cin,
-                                    int KHW, float* __restrict__ dw, int accumulate) {
-  size_t total = (size_t)Cout * Cin * KHW;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int tap = (int)(i % KHW);
-  size_t tmp = i / KHW;
-  int ci = (int)(tmp % Cin);
-  int co = (int)(tmp / Cin);
-  size_t KK = (size_t)KHW * Cin;
-  size_t src = (size_t)co * KK + (size_t)tap * Cin + ci;
-  float s = 0.f;
-  for (int z = 0; z < S; ++z) s += part[(size_t)z * Cout * KK + src];
-  dw[i] = accumulate ? dw[i] + s : s;
+// block = 64 consecutive source elements (coalesced reads of every split) x 4 split lanes;
+// lane l sums splits l, l+4, ... with four loads in flight, lanes are combined in fixed order.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ part, int S, int Cout, int Cin, int KHW,
+                    float* __restrict__ dw, int accumulate) {
+  __shared__ float sm[256];
+  const size_t KK = (size_t)KHW * Cin;
+  const size_t total = (size_t)Cout * KK;
+  const int tx = threadIdx.x & 63, tz = threadIdx.x >> 6;
+  const size_t src = (size_t)blockIdx.x * 64 + tx;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (src < total) {
+    const float* p = part + src;
+    int z = tz;
+    for (; z + 12 < S; z += 16) {
+      a0 += p[(size_t)z * total];
+      a1 += p[(size_t)(z + 4) * total];
+      a2 += p[(size_t)(z + 8) * total];
+      a3 += p[(size_t)(z + 12) * total];
+    }
+    for (; z < S; z += 4) a0 += p[(size_t)z * total];
+  }
+  sm[threadIdx.x] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (tz == 0 && src < total) {
+    const float s = (sm[tx] + sm[64 + tx]) + (sm[128 + tx] + sm[192 + tx]);
+    const int co = (int)(src / KK);
+    const int rem = (int)(src - (size_t)co * KK);
+    const int tap = rem / Cin, ci = rem - tap * Cin;
+    const size_t i = ((size_t)co * Cin + ci) * KHW + tap;
+    dw[i] = accumulate ? dw[i] + s : s;
+  }
 }
 
 // Derived weight layouts.
@@ -336,13 +354,25 @@ __global__ void colsum_partial_kernel(const float* __restrict__ dy, long long ro
   }
 }
 
-__global__ void colsum_final_kernel(const float* __restrict__ part, int nblk, int C,
-                                    float* __restrict__ db, int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel: lanes stride over the partial blocks in a fixed order, then a shuffle
+// tree (deterministic); the serial one-thread-per-channel loop cost 35-60 us per bias gradient
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ db,
+                    int accumulate) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
-  float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += part[(size_t)b * C + c];
-  db[c] = accumulate ? db[c] + s : s;
+  float s0 = 0.f, s1 = 0.f;
+  int b = lane;
+  for (; b + 32 < nblk; b += 64) {
+    s0 += part[(size_t)b * C + c];
+    s1 += part[(size_t)(b + 32) * C + c];
+  }
+  if (b < nblk) s0 += part[(size_t)b * C + c];
+  float s = s0 + s1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) db[c] = accumulate ? db[c] + s : s;
 }
 
 int colsum_blocks(long long rows) {
@@ -423,7 +453,7 @@ int conv_wgrad_simt(const ConvGeom& g, const float* x, const float* dy, int lddy
   igemm_wgrad_kernel<<<grid, NT, 0, s>>>(a);
   EVE_LAUNCH_CHECK();
   size_t total = (size_t)g.Cout * g.K();
-  wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, s>>>(scratch, S, g.Cout, g.Cin, g.KH * g.KW, dw,
+  wgrad_reduce_kernel<<<cdiv(total, 64), 256, 0, s>>>(scratch, S, g.Cout, g.Cin, g.KH * g.KW, dw,
                                                       accumulate ? 1 : 0);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
@@ -432,7 +462,7 @@ int conv_wgrad_simt(const ConvGeom& g, const float* x, const float* dy, int lddy
 int wgrad_reduce(const float* part, int splits, const ConvGeom& g, float* dw, bool accumulate,
                  cudaStream_t s) {
   size_t total = (size_t)g.Cout * g.K();
-  wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, s>>>(part, splits, g.Cout, g.Cin, g.KH * g.KW, dw,
+  wgrad_reduce_kernel<<<cdiv(total, 64), 256, 0, s>>>(part, splits, g.Cout, g.Cin, g.KH * g.KW, dw,
                                                       accumulate ? 1 : 0);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
@@ -451,7 +481,7 @@ int colsum(const float* dy, long long rows, int C, int ld, float* db, float* scr
   colsum_partial_kernel<<<grid, threads, threads * sizeof(float), s>>>(dy, rows, C, ld, rpb,
                                                                         scratch);
   EVE_LAUNCH_CHECK();
-  colsum_final_kernel<<<cdiv(C, 128), 128, 0, s>>>(scratch, nblk, C, db, accumulate ? 1 : 0);
+  colsum_final_kernel<<<cdiv(C, 8), 256, 0, s>>>(scratch, nblk, C, db, accumulate ? 1 : 0);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }

@@ -180,6 +180,9 @@ struct TcParams {
   int kc;                   // channels per K chunk: 64, 32 or 16
   int kchunks;              // Cin / kc
   int fmt;                  // operand format: 0 = fp16 planes, 1 = bf16 planes
+  // shared-memory ring geometry (sized for the actual chunk width, so that thin-channel layers
+  // keep enough bytes in flight): slot = [A hi][A lo][B hi][B lo]
+  int a_bytes, b_bytes, stage_bytes, stages;
   float out_scale;          // accumulator scale undoing the weight pre-scale (fp16 planes)
   const float* bias;        // [Cout] or null
   const float* addend;      // [N,OH,OW,Cout] or null
@@ -189,17 +192,13 @@ struct TcParams {
 constexpr int kTileM = 128;
 constexpr int kThreads = 192;
 
+constexpr int kMaxStages = 24;
+constexpr int kSmemBudget = 224 * 1024;
+constexpr int kBarrierBytes = 512;     // (2 * kMaxStages + 4) mbarriers + the TMEM slot
+
 template <int BN, int NPASS>
 struct TcCfg {
-  static constexpr int kABytes = kTileM * 64 * 2;      // slot sizes for the widest chunk
-  static constexpr int kBRows = BN < 8 ? 8 : BN;
-  static constexpr int kBBytes = (BN * 64 * 2) < 1024 ? 1024 : BN * 64 * 2;
   static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
-  static constexpr int kStageBytes = (kABytes + kBBytes) * kPlanes;
-  static constexpr int kBudget = 224 * 1024;
-  static constexpr int kStagesRaw = (kBudget - 2048) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;   // per accumulator buffer (x2)
 };
 
@@ -215,9 +214,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* empty = full + Cfg::kStages;
-  uint64_t* tmem_full = empty + Cfg::kStages;     // [2]
+  const int kStages = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * p.stage_bytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;          // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -233,7 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       tmap_prefetch(&tmA_lo);
       tmap_prefetch(&tmB_lo);
     }
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -262,20 +262,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int n0 = (tm / p.tiles_h) * p.bn;
         const int co0 = tco * BN;
         for (int it = 0; it < iters; ++it, ++g) {
-          const int s = g % Cfg::kStages;
-          const uint32_t ph = (g / Cfg::kStages) & 1;
+          const int s = g % kStages;
+          const uint32_t ph = (g / kStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* st = smem + s * Cfg::kStageBytes;
+          uint8_t* st = smem + s * p.stage_bytes;
           const int tap = it / p.kchunks;
           const int kc = it - tap * p.kchunks;
           const int wi = p.tap_dw[tap], hi = h0 * p.stride + p.tap_dh[tap];
           const int kb = p.tap_koff[tap] + kc * p.kc;
           mbar_expect_tx(&full[s], tx);
           tma_load_4d(st, &tmA_hi, &full[s], kc * p.kc, wi, hi, n0);
-          tma_load_2d(st + Cfg::kABytes * Cfg::kPlanes, &tmB_hi, &full[s], kb, co0);
+          tma_load_2d(st + p.a_bytes * Cfg::kPlanes, &tmB_hi, &full[s], kb, co0);
           if (NPASS == 3) {
-            tma_load_4d(st + Cfg::kABytes, &tmA_lo, &full[s], kc * p.kc, wi, hi, n0);
-            tma_load_2d(st + Cfg::kABytes * 2 + Cfg::kBBytes, &tmB_lo, &full[s], kb, co0);
+            tma_load_4d(st + p.a_bytes, &tmA_lo, &full[s], kc * p.kc, wi, hi, n0);
+            tma_load_2d(st + p.a_bytes * 2 + p.b_bytes, &tmB_lo, &full[s], kb, co0);
           }
         }
       }
@@ -295,17 +295,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * Cfg::kTmemCols;
       for (int it = 0; it < iters; ++it, ++g) {
-        const int s = g % Cfg::kStages;
-        const uint32_t ph = (g / Cfg::kStages) & 1;
+        const int s = g % kStages;
+        const uint32_t ph = (g / kStages) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
-          const uint32_t b_hi = a_hi + Cfg::kABytes * Cfg::kPlanes;
+          const uint32_t a_hi = smem_u32(smem + s * p.stage_bytes);
+          const uint32_t b_hi = a_hi + p.a_bytes * Cfg::kPlanes;
           const uint64_t da_hi = kmajor_desc(a_hi, p.kc);
           const uint64_t db_hi = kmajor_desc(b_hi, p.kc);
-          const uint64_t da_lo = kmajor_desc(a_hi + Cfg::kABytes, p.kc);
-          const uint64_t db_lo = kmajor_desc(b_hi + Cfg::kBBytes, p.kc);
+          const uint64_t da_lo = kmajor_desc(a_hi + p.a_bytes, p.kc);
+          const uint64_t db_lo = kmajor_desc(b_hi + p.b_bytes, p.kc);
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t adv = (uint64_t)(k * 2);  // 16 elements = 32 bytes >> 4
             if (NPASS == 3) {
@@ -386,6 +386,242 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
 }
 
+// ============================================================= halo-row kernel (W == 128) ==
+// 3x3 stride-1 "same" convolutions over 128-pixel-wide maps (RefineNet level 0, refine_net.py:
+// 45-62,213-222) have so few channels (16..64) that the generic kernel above is bound by the
+// L2 -> shared-memory operand stream: it re-reads every input pixel once per filter tap (9x).
+// Here an M tile is one output image row, input rows are staged ONCE in a ring of row slots
+// (each 130 pixels wide: w = -1..128, zero-filled by TMA outside the image) and reused by the
+// three output rows that touch them; the three horizontal taps are the SAME staged row read
+// through shared-memory descriptors whose start address is shifted by q pixels.  All nine
+// [Cout][Cin] weight tiles stay resident in shared memory.  Where a shifted start is not
+// representable in a swizzle mode, `ncopies` > 1 stages pre-shifted copies instead (tables
+// q_copy / q_shift).  A CTA owns strips of consecutive output rows of one image.
+struct TcRowParams {
+  int N, H, Cin, Cout;
+  int strips, rows_per_strip, items;   // work item = (image, strip); items = N * strips
+  int kc;                              // == Cin: one K chunk (16, 32 or 64 channels)
+  int fmt;
+  int ncopies;                         // staged copies per input row (1, 2 or 3)
+  int copy_w0[3];                      // first input pixel of each copy's 130-pixel box
+  int q_copy[3], q_shift[3];           // horizontal tap q reads copy q_copy[q] shifted by q_shift[q] pixels
+  int row_bytes;                       // one copy of one plane (130 pixels), 1024-byte aligned
+  int slot_bytes;                      // row_bytes * ncopies * planes
+  int slots;                           // ring depth (>= 4)
+  int w_tap_bytes;                     // one tap's [BN][kc] weight tile of one plane (>= 1024)
+  int base_offset;                     // shifted descriptors carry (start >> 7) & 7 in bits 49..51
+  float out_scale;
+  const float* bias;
+  const float* addend;
+  float* out;
+};
+
+constexpr int kRowBox = 130;           // 128 pixels + one halo pixel on each side
+
+__device__ __forceinline__ uint64_t kmajor_desc_shifted(uint32_t saddr, int cw, int with_base) {
+  uint64_t d = kmajor_desc(saddr, cw);
+  if (with_base) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  return d;
+}
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                   const TcRowParams p) {
+  constexpr int kPlanes = NPASS == 3 ? 2 : 1;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* wsm = smem;                                        // [9 taps][planes][w_tap_bytes]
+  uint8_t* ring = smem + 9 * kPlanes * p.w_tap_bytes;         // [slots][copies][planes][row_bytes]
+  const int slots = p.slots;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)slots * p.slot_bytes);
+  uint64_t* empty = full + slots;
+  uint64_t* wfull = empty + slots;
+  uint64_t* tmem_full = wfull + 1;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tmap_prefetch(&tmA_hi);
+    tmap_prefetch(&tmB_hi);
+    if (NPASS == 3) {
+      tmap_prefetch(&tmA_lo);
+      tmap_prefetch(&tmB_lo);
+    }
+    for (int s = 0; s < slots; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(wfull, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_expect_tx(wfull, 9u * kPlanes * (uint32_t)BN * (uint32_t)(p.kc * 2));
+      for (int t = 0; t < 9; ++t) {
+        tma_load_2d(wsm + (size_t)(t * kPlanes) * p.w_tap_bytes, &tmB_hi, wfull, t * p.Cin, 0);
+        if (NPASS == 3)
+          tma_load_2d(wsm + (size_t)(t * kPlanes + 1) * p.w_tap_bytes, &tmB_lo, wfull, t * p.Cin, 0);
+      }
+      const uint32_t tx = (uint32_t)kRowBox * (uint32_t)(p.kc * 2) * kPlanes * (uint32_t)p.ncopies;
+      uint32_t g = 0;   // staged-row counter: slot = g % slots
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int n = item / p.strips;
+        const int h0 = (item - n * p.strips) * p.rows_per_strip;
+        const int h1 = min(p.H, h0 + p.rows_per_strip);
+        for (int hr = h0 - 1; hr <= h1; ++hr, ++g) {
+          const int s = g % slots;
+          const uint32_t ph = (g / slots) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* dst = ring + (size_t)s * p.slot_bytes;
+          mbar_expect_tx(&full[s], tx);
+          for (int c = 0; c < p.ncopies; ++c) {
+            tma_load_4d(dst + (size_t)(c * kPlanes) * p.row_bytes, &tmA_hi, &full[s], 0,
+                        p.copy_w0[c], hr, n);
+            if (NPASS == 3)
+              tma_load_4d(dst + (size_t)(c * kPlanes + 1) * p.row_bytes, &tmA_lo, &full[s], 0,
+                          p.copy_w0[c], hr, n);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const int ksteps = p.kc >> 4;
+    const uint32_t pix_bytes = (uint32_t)(p.kc * 2);
+    mbar_wait(wfull, 0);
+    tc_fence_after();
+    const uint32_t w_base = smem_u32(wsm);
+    uint32_t g = 0, local = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int n = item / p.strips;
+      const int h0 = (item - n * p.strips) * p.rows_per_strip;
+      const int h1 = min(p.H, h0 + p.rows_per_strip);
+      for (int h = h0; h < h1; ++h, ++g, ++local) {
+        const uint32_t buf = local & 1;
+        const uint32_t use = local >> 1;
+        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * kTmemCols;
+        for (int r = 0; r < 3; ++r) {
+          const uint32_t e = g + (uint32_t)r;          // staged row h + r - 1
+          const int s = e % slots;
+          mbar_wait(&full[s], (e / slots) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t slot_base = smem_u32(ring + (size_t)s * p.slot_bytes);
+            for (int q = 0; q < 3; ++q) {
+              const int t = r * 3 + q;
+              const uint32_t a_hi = slot_base + (uint32_t)(p.q_copy[q] * kPlanes) * (uint32_t)p.row_bytes +
+                                    (uint32_t)p.q_shift[q] * pix_bytes;
+              const uint32_t a_lo = a_hi + (uint32_t)p.row_bytes;
+              const uint32_t b_hi = w_base + (uint32_t)(t * kPlanes) * (uint32_t)p.w_tap_bytes;
+              const uint32_t b_lo = b_hi + (uint32_t)p.w_tap_bytes;
+              const uint64_t da_hi = kmajor_desc_shifted(a_hi, p.kc, p.base_offset);
+              const uint64_t da_lo = kmajor_desc_shifted(a_lo, p.kc, p.base_offset);
+              const uint64_t db_hi = kmajor_desc(b_hi, p.kc);
+              const uint64_t db_lo = kmajor_desc(b_lo, p.kc);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t adv = (uint64_t)(k * 2);
+                if (NPASS == 3) {
+                  umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, (t | k) != 0);
+                  umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
+                  umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1);
+                } else {
+                  umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (t | k) != 0);
+                }
+              }
+            }
+            if (r == 2) {
+              umma_commit(&empty[g % slots]);       // row h - 1 is not needed any more
+              umma_commit(&tmem_full[buf]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // end of the strip: the two trailing rows (h1 - 1, h1) are released as well
+      if (elect_one()) {
+        umma_commit(&empty[g % slots]);
+        umma_commit(&empty[(g + 1) % slots]);
+      }
+      __syncwarp();
+      g += 2;
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;         // output pixel w = TMEM lane
+    constexpr int CW = BN < 32 ? BN : 32;
+    uint32_t local = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int n = item / p.strips;
+      const int h0 = (item - n * p.strips) * p.rows_per_strip;
+      const int h1 = min(p.H, h0 + p.rows_per_strip);
+      for (int h = h0; h < h1; ++h, ++local) {
+        const uint32_t buf = local & 1;
+        const uint32_t use = local >> 1;
+        const size_t row = ((size_t)(n * p.H + h) * kTileM + m) * p.Cout;
+        mbar_wait(&tmem_full[buf], use & 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * kTmemCols + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_d + (uint32_t)c0, v);
+          if (p.out_scale != 1.f) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] *= p.out_scale;
+          }
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] += __ldg(p.bias + c0 + j);
+          }
+          if (p.addend) {
+            const float4* a4 = reinterpret_cast<const float4*>(p.addend + row + c0);
+#pragma unroll
+            for (int j = 0; j < CW / 4; ++j) {
+              float4 a = __ldg(a4 + j);
+              v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+            }
+          }
+          float4* o4 = reinterpret_cast<float4*>(p.out + row + c0);
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j)
+            o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[buf]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * kTmemCols);
+  }
+}
+
 // =============================================================== weight gradient ====
 // dW[co][(r,q)][ci] = sum over pixels p=(n,h,w) of dy[n, h-r+pad, w-q+pad, co] * x[n,h,w,ci]
 // as a GEMM whose K dimension is the pixel index.  Both operands come straight from the NHWC
@@ -414,6 +650,7 @@ struct TcWgradParams {
   //            then uw / units / cout_blocks describe the *input* channels and the epilogue
   //            writes the transposed tile
   int swap, mstride;
+  int fmt_m, fmt_n;         // operand formats of the M-side / N-side planes (0 = fp16, 1 = bf16)
   float* part;              // [splits][Cout][taps*Cin]
 };
 
@@ -507,8 +744,9 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
       }
     }
   } else if (warp == 1) {
-    // D fp32, A/B bf16, both MN-major, M = 128, N = nblk
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+    // D fp32, A/B fp16 or bf16 (independently), both MN-major, M = 128, N = nblk
+    const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt_m << 7) | ((uint32_t)p.fmt_n << 10) |
+                           (1u << 15) | (1u << 16) |
                            ((uint32_t)(p.nblk >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const int ksteps = p.rows >> 4;
     for (int it = 0; it < iters; ++it) {
@@ -751,15 +989,23 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
   static bool configured = false;
   if (!configured) {
     EVE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NPASS>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   TcParams p = p0;
   p.tiles_m = tiles_m;
   p.tiles_co = tiles_co;
+  // ring slots sized for this layer's chunk width (swizzle atoms need 1024-byte alignment)
+  p.a_bytes = kTileM * p.kc * 2;
+  p.b_bytes = BN * p.kc * 2 < 1024 ? 1024 : BN * p.kc * 2;
+  p.stage_bytes = (p.a_bytes + p.b_bytes) * Cfg::kPlanes;
+  p.stages = (kSmemBudget - 1024 - kBarrierBytes) / p.stage_bytes;
+  const int cap = tc_stage_cap();
+  if (p.stages > cap) p.stages = cap;
+  const int smem_bytes = p.stages * p.stage_bytes + 1024 /*align*/ + kBarrierBytes;
   const long long total = (long long)tiles_m * tiles_co;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);   // one persistent CTA per SM
-  conv_tc_kernel<BN, NPASS><<<grid, kThreads, Cfg::kSmemBytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+  conv_tc_kernel<BN, NPASS><<<grid, kThreads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }
@@ -849,6 +1095,117 @@ static int tc_launch(const TcParams& p0, const void* x_hi, const void* x_lo, int
                     : launch_tc_bn<1>(BN, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
 }
 
+// ---- halo-row kernel: planning and launch
+static bool row_geometry_ok(const ConvGeom& g) {
+  if (g.KH != 3 || g.KW != 3 || g.stride != 1 || g.pad != 1) return false;
+  if (g.W != kTileM || g.OW != kTileM || g.OH != g.H || g.N < 1) return false;
+  if (g.Cin != 16 && g.Cin != 32 && g.Cin != 64) return false;
+  if (g.Cout != 16 && g.Cout != 32 && g.Cout != 64) return false;
+  return true;
+}
+
+static bool row_plan(const ConvGeom& g, int npass, TcRowParams& p, int& smem_bytes) {
+  if (!row_geometry_ok(g)) return false;
+  const int planes = npass == 3 ? 2 : 1;
+  p.N = g.N; p.H = g.H; p.Cin = g.Cin; p.Cout = g.Cout;
+  p.kc = g.Cin;
+  // how the three horizontal taps are read: 1 = one staged copy, descriptor shifted by q pixels;
+  // 2 = hybrid (shifts that change the swizzle phase inside a 128-byte line come from a second /
+  // third pre-shifted copy); 3 = three pre-shifted copies, no shifted descriptor at all
+  const int mode = get_option(OPT_TC_ROW_COPIES);
+  int nc = 1;
+  if (mode == 3) nc = 3;
+  else if (mode == 2) nc = g.Cin == 64 ? 1 : (g.Cin == 32 ? 2 : 3);
+  p.ncopies = nc;
+  for (int q = 0; q < 3; ++q) {
+    if (nc == 1) { p.q_copy[q] = 0; p.q_shift[q] = q; }
+    else if (nc == 3) { p.q_copy[q] = q; p.q_shift[q] = 0; }
+    else { p.q_copy[q] = q == 1 ? 1 : 0; p.q_shift[q] = q == 2 ? 2 : 0; }
+  }
+  p.copy_w0[0] = -1; p.copy_w0[1] = nc == 2 ? 0 : 0; p.copy_w0[2] = 1;
+  p.row_bytes = (int)align_up((size_t)kRowBox * g.Cin * 2, 1024);
+  p.slot_bytes = p.row_bytes * nc * planes;
+  p.w_tap_bytes = g.Cout * g.Cin * 2 < 1024 ? 1024 : g.Cout * g.Cin * 2;
+  const int fixed = 9 * planes * p.w_tap_bytes + 1024 + kBarrierBytes;
+  p.slots = (227 * 1024 - fixed) / p.slot_bytes;
+  if (p.slots > kMaxStages) p.slots = kMaxStages;
+  if (p.slots < 4) return false;
+  smem_bytes = fixed + p.slots * p.slot_bytes;
+  p.base_offset = get_option(OPT_TC_ROW_BASE_OFFSET);
+  // strips of consecutive output rows per work item: balance over the SMs vs halo re-reads
+  int forced = get_option(OPT_TC_ROW_STRIPS);
+  int best_s = 1;
+  double best = -1.0;
+  for (int st = 1; st <= g.H; ++st) {
+    const int rps = cdiv(g.H, st);
+    if (cdiv(g.H, rps) != st) continue;           // skip strip counts that leave empty strips
+    const long long items = (long long)g.N * st;
+    const double balance = (double)items / (double)(cdiv(items, kNumSMs) * kNumSMs);
+    const double eff = balance * (double)rps / (double)(rps + 1);
+    if (forced ? st == forced : eff > best + 1e-9) { best = eff; best_s = st; }
+  }
+  p.strips = best_s;
+  p.rows_per_strip = cdiv(g.H, best_s);
+  p.items = g.N * p.strips;
+  return true;
+}
+
+bool conv_tc_row_supported(const ConvGeom& g) {
+  if (!get_option(OPT_TC_ROW_KERNEL)) return false;
+  TcRowParams p;
+  int smem;
+  return row_plan(g, 3, p, smem);
+}
+
+template <int BN, int NPASS>
+static int launch_row(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                      const CUtensorMap& b_lo, const TcRowParams& p, int smem_bytes,
+                      cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    EVE_CUDA(cudaFuncSetAttribute(conv_tc_row_kernel<BN, NPASS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  conv_tc_row_kernel<BN, NPASS><<<grid, kThreads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+static int conv_tc_row_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* w_hi,
+                           const void* w_lo, const float* bias, const float* addend, float* y,
+                           int npass, int fmt, float out_scale, cudaStream_t s) {
+  TcRowParams p;
+  int smem = 0;
+  EVE_REQUIRE(row_plan(g, npass, p, smem), EVE_ERR_SHAPE, "conv_tc_row: unsupported geometry");
+  p.fmt = fmt;
+  p.out_scale = out_scale;
+  p.bias = bias; p.addend = addend; p.out = y;
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  EVE_TRY(make_map_nhwc(&a_hi, x_hi, g.N, g.H, g.W, g.Cin, g.Cin, kRowBox, 1, 1, 1, fmt));
+  EVE_TRY(make_map_2d(&b_hi, w_hi, g.Cout, 9 * g.Cin, g.Cin, g.Cout, fmt));
+  if (npass == 3) {
+    EVE_TRY(make_map_nhwc(&a_lo, x_lo, g.N, g.H, g.W, g.Cin, g.Cin, kRowBox, 1, 1, 1, fmt));
+    EVE_TRY(make_map_2d(&b_lo, w_lo, g.Cout, 9 * g.Cin, g.Cin, g.Cout, fmt));
+  } else {
+    a_lo = a_hi;
+    b_lo = b_hi;
+  }
+#define EVE_ROW_CASE(BN_)                                                                      \
+  case BN_:                                                                                    \
+    return npass == 3 ? launch_row<BN_, 3>(a_hi, a_lo, b_hi, b_lo, p, smem, s)                 \
+                      : launch_row<BN_, 1>(a_hi, a_lo, b_hi, b_lo, p, smem, s);
+  switch (g.Cout) {
+    EVE_ROW_CASE(16)
+    EVE_ROW_CASE(32)
+    EVE_ROW_CASE(64)
+  }
+#undef EVE_ROW_CASE
+  EVE_REQUIRE(false, EVE_ERR_SHAPE, "conv_tc_row: Cout=%d", g.Cout);
+  return EVE_ERR_SHAPE;
+}
+
 // y[N,OH,OW,Cout] = conv(x) (+bias) (+addend).  x_hi/x_lo: 16-bit NHWC planes of the input;
 // w_hi/w_lo: K-major weights [Cout][KH*KW*Cin].  npass: 3 (split operands) or 1 (plain bf16).
 int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* w_hi,
@@ -856,6 +1213,8 @@ int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const voi
                 int fmt, float out_scale, cudaStream_t s) {
   EVE_REQUIRE(conv_tc_supported(g), EVE_ERR_SHAPE, "conv_tc: unsupported geometry");
   EVE_REQUIRE(npass == 1 || npass == 3, EVE_ERR_CONFIG, "conv_tc: npass must be 1 or 3");
+  if (conv_tc_row_supported(g))
+    return conv_tc_row_run(g, x_hi, x_lo, w_hi, w_lo, bias, addend, y, npass, fmt, out_scale, s);
   TcParams p;
   p.N = g.N; p.OH = g.OH; p.OW = g.OW; p.Cin = g.Cin; p.Cout = g.Cout; p.stride = g.stride;
   p.ntaps = g.KH * g.KW;
@@ -1002,26 +1361,29 @@ size_t conv_tc_wgrad_partial_floats(const ConvGeom& g) {
 // part[splits][Cout][KH*KW*Cin] <- per-split partial weight gradients; returns the split count
 int conv_tc_wgrad_run(const ConvGeom& g, const void* d_hi, const void* d_lo, const void* x_hi,
                       const void* x_lo, float* part, int npass, int* splits_out,
-                      cudaStream_t s) {
+                      cudaStream_t s, int x_fmt) {
   EVE_REQUIRE(conv_tc_wgrad_supported(g), EVE_ERR_SHAPE, "conv_tc_wgrad: unsupported geometry");
   TcWgradParams p;
   int mb, nb, sp;
   wgrad_plan(g, p, mb, nb, sp, npass);
   p.part = part;
+  // dy planes are always bf16 (gradient range); x planes are bf16 or the forward's fp16 planes
+  p.fmt_m = p.swap ? x_fmt : TC_BF16;
+  p.fmt_n = p.swap ? TC_BF16 : x_fmt;
   // md_* = M-side maps, mx_* = N-side maps (see TcWgradParams::swap)
   CUtensorMap md_hi, md_lo, mx_hi, mx_lo;
   if (!p.swap) {
     EVE_TRY(make_map_nhwc(&md_hi, d_hi, g.N, g.OH, g.OW, g.Cout, p.uw, p.bw, p.bh, p.bn));
-    EVE_TRY(make_map_nhwc(&mx_hi, x_hi, g.N, g.H, g.W, g.Cin, p.xw, p.bw, p.bh, p.bn));
+    EVE_TRY(make_map_nhwc(&mx_hi, x_hi, g.N, g.H, g.W, g.Cin, p.xw, p.bw, p.bh, p.bn, 1, x_fmt));
     if (npass == 3) {
       EVE_TRY(make_map_nhwc(&md_lo, d_lo, g.N, g.OH, g.OW, g.Cout, p.uw, p.bw, p.bh, p.bn));
-      EVE_TRY(make_map_nhwc(&mx_lo, x_lo, g.N, g.H, g.W, g.Cin, p.xw, p.bw, p.bh, p.bn));
+      EVE_TRY(make_map_nhwc(&mx_lo, x_lo, g.N, g.H, g.W, g.Cin, p.xw, p.bw, p.bh, p.bn, 1, x_fmt));
     }
   } else {
-    EVE_TRY(make_map_nhwc(&md_hi, x_hi, g.N, g.H, g.W, g.Cin, p.uw, p.bw, p.bh, p.bn, 2));
+    EVE_TRY(make_map_nhwc(&md_hi, x_hi, g.N, g.H, g.W, g.Cin, p.uw, p.bw, p.bh, p.bn, 2, x_fmt));
     EVE_TRY(make_map_nhwc(&mx_hi, d_hi, g.N, g.OH, g.OW, g.Cout, p.xw, p.bw, p.bh, p.bn));
     if (npass == 3) {
-      EVE_TRY(make_map_nhwc(&md_lo, x_lo, g.N, g.H, g.W, g.Cin, p.uw, p.bw, p.bh, p.bn, 2));
+      EVE_TRY(make_map_nhwc(&md_lo, x_lo, g.N, g.H, g.W, g.Cin, p.uw, p.bw, p.bh, p.bn, 2, x_fmt));
       EVE_TRY(make_map_nhwc(&mx_lo, d_lo, g.N, g.OH, g.OW, g.Cout, p.xw, p.bw, p.bh, p.bn));
     }
   }

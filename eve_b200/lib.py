@@ -60,6 +60,8 @@ SIGNATURES = {
     'eve_profile_read': (_I, [_I, _P, _P, _P, _P]),
     'eve_set_conv_mode': (None, [_I]),
     'eve_get_conv_mode': (_I, []),
+    'eve_set_option': (_I, [C.c_char_p, _I]),
+    'eve_get_option': (_I, [C.c_char_p, _P]),
     'eve_conv2d_workspace_bytes': (_Z, [_P]),
     'eve_conv2d_fwd': (_I, [_P, _P, _P, _P, _P, _P, _Z, _P]),
     'eve_conv2d_dgrad': (_I, [_P, _P, _P, _P, _P, _Z, _P]),
@@ -123,6 +125,17 @@ def last_error():
 def check(rc, what):
     if rc != 0:
         raise RuntimeError('%s failed (code %d): %s' % (what, rc, last_error()))
+
+
+def set_option(name, value):
+    """Process-wide tuning switch of the tensor-core path (include/eve_b200.h: eve_set_option)."""
+    check(load().eve_set_option(name.encode(), int(value)), 'eve_set_option(%s)' % name)
+
+
+def get_option(name):
+    v = C.c_int(0)
+    check(load().eve_get_option(name.encode(), C.byref(v)), 'eve_get_option(%s)' % name)
+    return v.value
 
 
 def ptr(t):

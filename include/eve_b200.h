@@ -65,6 +65,22 @@ typedef struct {
  * The default can also be set with the environment variable EVE_B200_CONV_MODE. */
 void eve_set_conv_mode(int mode);
 int eve_get_conv_mode(void);
+/* Tuning switches of the tensor-core path (process-wide, default = fastest validated setting;
+ * each also reads an EVE_B200_<NAME> environment default).  They select between kernels that
+ * compute the same result, so that every variant can be parity-tested and A/B-timed:
+ *   "tc_stage_cap"        2..24  ring depth limit of the implicit-GEMM kernel
+ *   "tc_row_kernel"       0/1    halo-row kernel (input rows staged once, filter taps taken as
+ *                                shifted shared-memory descriptors) for 3x3 stride-1, W == 128
+ *   "tc_row_base_offset"  0/1    descriptor base-offset convention of those shifted operands
+ *   "tc_row_copies"       1..3   1 = one staged copy per input row, taps via shifted descriptors;
+ *                                3 = three pre-shifted copies; 2 = per swizzle mode
+ *   "tc_row_strips"       0..128 row strips per image (0 = automatic)
+ *   "tc_row_wgrad"        0/1    halo-row weight-gradient kernel
+ *   "tc_mixed_wgrad"      0/1    weight gradients from fp16 x planes x bf16 dy planes
+ *   "fused_planes"        0/1    InstanceNorm kernels emit the next conv's 16-bit operand planes
+ * Unknown names / out-of-range values return EVE_ERR_CONFIG. */
+int eve_set_option(const char* name, int value);
+int eve_get_option(const char* name, int* value);
 size_t eve_conv2d_workspace_bytes(const eve_conv_params* p);
 int eve_conv2d_fwd(const eve_conv_params* p, const float* x, const float* w, const float* bias,
                    float* y, void* workspace, size_t workspace_bytes, eve_stream_t stream);
