@@ -139,12 +139,8 @@ struct Opt {
 static Opt g_opts[OPT_COUNT] = {
     {"tc_stage_cap", 24, 2, 24, "EVE_B200_TC_STAGE_CAP", false},
     {"tc_row_kernel", 1, 0, 1, "EVE_B200_TC_ROW_KERNEL", false},
-    {"tc_row_base_offset", 1, 0, 1, "EVE_B200_TC_ROW_BASE_OFFSET", false},
-    {"tc_row_copies", 1, 1, 3, "EVE_B200_TC_ROW_COPIES", false},
     {"tc_row_strips", 0, 0, 128, "EVE_B200_TC_ROW_STRIPS", false},
     {"tc_row_wgrad", 1, 0, 1, "EVE_B200_TC_ROW_WGRAD", false},
-    {"tc_mixed_wgrad", 1, 0, 1, "EVE_B200_TC_MIXED_WGRAD", false},
-    {"fused_planes", 1, 0, 1, "EVE_B200_FUSED_PLANES", false},
 };
 int get_option(int key) {
   if (key < 0 || key >= OPT_COUNT) return 0;

@@ -155,12 +155,8 @@ void set_conv_mode(int mode);
 enum OptKey {
   OPT_TC_STAGE_CAP = 0,      // max ring stages of the tcgen05 conv kernel
   OPT_TC_ROW_KERNEL,         // halo-row tcgen05 kernel for 3x3 stride-1 layers with W == 128
-  OPT_TC_ROW_BASE_OFFSET,    // row-shifted descriptors carry base_offset = (addr >> 7) & 7
-  OPT_TC_ROW_COPIES,         // 1 = shifted descriptors, 2 = hybrid, 3 = three pre-shifted copies
   OPT_TC_ROW_STRIPS,         // 0 = automatic; otherwise the number of row strips per image
   OPT_TC_ROW_WGRAD,          // halo-row weight-gradient kernel (W == 128)
-  OPT_TC_MIXED_WGRAD,        // wgrad reads the forward's fp16 x planes next to bf16 dy planes
-  OPT_FUSED_PLANES,          // producers emit the 16-bit operand planes of the next convolution
   OPT_COUNT
 };
 int get_option(int key);

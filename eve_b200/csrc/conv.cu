@@ -277,9 +277,9 @@ int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, fl
     uint16_t* x_hi = c.get<uint16_t>((size_t)g.in_elems());
     uint16_t* x_lo = c.get<uint16_t>((size_t)g.in_elems());
     EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_wgrad: scratch too small");
-    // x planes: fp16 (the forward's format, 22 mantissa bits) next to bf16 dy planes when the
-    // mixed-format weight gradient is enabled
-    const int xfmt = (npass == 3 && get_option(OPT_TC_MIXED_WGRAD)) ? TC_F16 : TC_BF16;
+    // tcgen05 kind::f16 needs both operands in ONE 16-bit format (an fp16 x bf16 descriptor is an
+    // illegal instruction on sm_100a), so x is split again as bf16 next to the bf16 dy planes
+    const int xfmt = TC_BF16;
     EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
     EVE_TRY(split_planes(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, xfmt, s));
     int splits = 0;
@@ -361,7 +361,7 @@ int conv_bwd(const ConvGeom& g, const float* x, const float* dy, const float* w,
   uint16_t* x_hi = c.get<uint16_t>((size_t)g.in_elems());
   uint16_t* x_lo = c.get<uint16_t>((size_t)g.in_elems());
   EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_bwd: scratch too small");
-  const int xfmt = (npass == 3 && get_option(OPT_TC_MIXED_WGRAD)) ? TC_F16 : TC_BF16;
+  const int xfmt = TC_BF16;     // same format as dy: mixed fp16 x bf16 MMAs are illegal
   EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
   EVE_TRY(split_planes(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, xfmt, s));
   EVE_TRY(conv_tc_prep_weights(g, w, true, w_hi, npass == 3 ? w_lo : nullptr, TC_BF16, 1.f, s));

@@ -16,6 +16,8 @@
 //    accumulation in TMEM), npass = 1 is plain bf16.
 //  * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 =
 //    epilogue (TMEM -> registers -> +bias/+addend -> fp32 NHWC global).
+#include <algorithm>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -389,27 +391,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // ============================================================= halo-row kernel (W == 128) ==
 // 3x3 stride-1 "same" convolutions over 128-pixel-wide maps (RefineNet level 0, refine_net.py:
 // 45-62,213-222) have so few channels (16..64) that the generic kernel above is bound by the
-// L2 -> shared-memory operand stream: it re-reads every input pixel once per filter tap (9x).
-// Here an M tile is one output image row, input rows are staged ONCE in a ring of row slots
-// (each 130 pixels wide: w = -1..128, zero-filled by TMA outside the image) and reused by the
-// three output rows that touch them; the three horizontal taps are the SAME staged row read
-// through shared-memory descriptors whose start address is shifted by q pixels.  All nine
-// [Cout][Cin] weight tiles stay resident in shared memory.  Where a shifted start is not
-// representable in a swizzle mode, `ncopies` > 1 stages pre-shifted copies instead (tables
-// q_copy / q_shift).  A CTA owns strips of consecutive output rows of one image.
+// L2 -> shared-memory operand stream (every input pixel is re-read once per filter tap, 9x) and
+// by the single MMA-issuing thread (a few MMAs per ring stage).  Here an M tile is one output
+// image row; input rows are staged ONCE in a ring of row slots (each 130 pixels wide: w = -1..128,
+// zero-filled by TMA outside the image) and reused by the three output rows that touch them; the
+// three horizontal taps are the SAME staged row read through shared-memory descriptors whose
+// start address is shifted by q pixels (measured on B200: the 32/64/128-byte swizzle is a
+// function of the absolute shared-memory address, so a row-shifted start needs no base offset).
+// All nine [Cout][Cin] weight tiles stay resident in shared memory; channel counts are template
+// parameters so that the issuing thread only adds immediates to two descriptor bases per MMA.
+// A CTA owns strips of consecutive output rows of one image.
 struct TcRowParams {
-  int N, H, Cin, Cout;
+  int N, H, Cout;
   int strips, rows_per_strip, items;   // work item = (image, strip); items = N * strips
-  int kc;                              // == Cin: one K chunk (16, 32 or 64 channels)
   int fmt;
-  int ncopies;                         // staged copies per input row (1, 2 or 3)
-  int copy_w0[3];                      // first input pixel of each copy's 130-pixel box
-  int q_copy[3], q_shift[3];           // horizontal tap q reads copy q_copy[q] shifted by q_shift[q] pixels
-  int row_bytes;                       // one copy of one plane (130 pixels), 1024-byte aligned
-  int slot_bytes;                      // row_bytes * ncopies * planes
   int slots;                           // ring depth (>= 4)
-  int w_tap_bytes;                     // one tap's [BN][kc] weight tile of one plane (>= 1024)
-  int base_offset;                     // shifted descriptors carry (start >> 7) & 7 in bits 49..51
   float out_scale;
   const float* bias;
   const float* addend;
@@ -418,26 +414,34 @@ struct TcRowParams {
 
 constexpr int kRowBox = 130;           // 128 pixels + one halo pixel on each side
 
-__device__ __forceinline__ uint64_t kmajor_desc_shifted(uint32_t saddr, int cw, int with_base) {
-  uint64_t d = kmajor_desc(saddr, cw);
-  if (with_base) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
-  return d;
-}
+template <int BN, int NPASS, int KC>
+struct RowCfg {
+  static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
+  static constexpr int kRowBytes = (kRowBox * KC * 2 + 1023) / 1024 * 1024;   // one plane of one row
+  static constexpr int kSlotBytes = kRowBytes * kPlanes;
+  static constexpr int kTapBytes = BN * KC * 2 < 1024 ? 1024 : BN * KC * 2;    // one tap, one plane
+  static constexpr int kWeightBytes = 9 * kPlanes * kTapBytes;
+  static constexpr int kFixedBytes = kWeightBytes + 1024 + kBarrierBytes;
+  static constexpr int kSlotsRaw = (227 * 1024 - kFixedBytes) / kSlotBytes;
+  static constexpr int kSlots = kSlotsRaw > kMaxStages ? kMaxStages : kSlotsRaw;
+  static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+};
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, int KC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    const TcRowParams p) {
-  constexpr int kPlanes = NPASS == 3 ? 2 : 1;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  using Cfg = RowCfg<BN, NPASS, KC>;
+  constexpr int kPlanes = Cfg::kPlanes;
+  constexpr uint32_t kTmemCols = Cfg::kTmemCols;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
-  uint8_t* wsm = smem;                                        // [9 taps][planes][w_tap_bytes]
-  uint8_t* ring = smem + 9 * kPlanes * p.w_tap_bytes;         // [slots][copies][planes][row_bytes]
+  uint8_t* wsm = smem;                                        // [9 taps][planes][kTapBytes]
+  uint8_t* ring = smem + Cfg::kWeightBytes;                   // [slots][planes][kRowBytes]
   const int slots = p.slots;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)slots * p.slot_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)slots * Cfg::kSlotBytes);
   uint64_t* empty = full + slots;
   uint64_t* wfull = empty + slots;
   uint64_t* tmem_full = wfull + 1;      // [2]
@@ -474,13 +478,14 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_expect_tx(wfull, 9u * kPlanes * (uint32_t)BN * (uint32_t)(p.kc * 2));
+      mbar_expect_tx(wfull, 9u * kPlanes * (uint32_t)(BN * KC * 2));
+#pragma unroll 1
       for (int t = 0; t < 9; ++t) {
-        tma_load_2d(wsm + (size_t)(t * kPlanes) * p.w_tap_bytes, &tmB_hi, wfull, t * p.Cin, 0);
+        tma_load_2d(wsm + (size_t)(t * kPlanes) * Cfg::kTapBytes, &tmB_hi, wfull, t * KC, 0);
         if (NPASS == 3)
-          tma_load_2d(wsm + (size_t)(t * kPlanes + 1) * p.w_tap_bytes, &tmB_lo, wfull, t * p.Cin, 0);
+          tma_load_2d(wsm + (size_t)(t * kPlanes + 1) * Cfg::kTapBytes, &tmB_lo, wfull, t * KC, 0);
       }
-      const uint32_t tx = (uint32_t)kRowBox * (uint32_t)(p.kc * 2) * kPlanes * (uint32_t)p.ncopies;
+      constexpr uint32_t tx = (uint32_t)(kRowBox * KC * 2) * kPlanes;
       uint32_t g = 0;   // staged-row counter: slot = g % slots
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int n = item / p.strips;
@@ -490,15 +495,10 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           const int s = g % slots;
           const uint32_t ph = (g / slots) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* dst = ring + (size_t)s * p.slot_bytes;
+          uint8_t* dst = ring + (size_t)s * Cfg::kSlotBytes;
           mbar_expect_tx(&full[s], tx);
-          for (int c = 0; c < p.ncopies; ++c) {
-            tma_load_4d(dst + (size_t)(c * kPlanes) * p.row_bytes, &tmA_hi, &full[s], 0,
-                        p.copy_w0[c], hr, n);
-            if (NPASS == 3)
-              tma_load_4d(dst + (size_t)(c * kPlanes + 1) * p.row_bytes, &tmA_lo, &full[s], 0,
-                          p.copy_w0[c], hr, n);
-          }
+          tma_load_4d(dst, &tmA_hi, &full[s], 0, -1, hr, n);
+          if (NPASS == 3) tma_load_4d(dst + Cfg::kRowBytes, &tmA_lo, &full[s], 0, -1, hr, n);
         }
       }
     }
@@ -506,11 +506,16 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     // ===================== MMA issuer =====================
     const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-    const int ksteps = p.kc >> 4;
-    const uint32_t pix_bytes = (uint32_t)(p.kc * 2);
+    constexpr int kSteps = KC / 16;
+    constexpr uint32_t kPix16 = (uint32_t)(KC * 2) >> 4;        // one pixel, in 16-byte units
+    constexpr uint32_t kRow16 = (uint32_t)Cfg::kRowBytes >> 4;
+    constexpr uint32_t kTap16 = (uint32_t)Cfg::kTapBytes >> 4;
     mbar_wait(wfull, 0);
     tc_fence_after();
-    const uint32_t w_base = smem_u32(wsm);
+    // descriptor = constant high part + (shared address >> 4); all later offsets are immediates
+    const uint64_t desc0 = kmajor_desc(0u, KC);
+    const uint64_t b_base = desc0 + (uint64_t)(smem_u32(wsm) >> 4);
+    const uint32_t ring16 = smem_u32(ring) >> 4;
     uint32_t g = 0, local = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int n = item / p.strips;
@@ -522,37 +527,34 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * kTmemCols;
+#pragma unroll
         for (int r = 0; r < 3; ++r) {
           const uint32_t e = g + (uint32_t)r;          // staged row h + r - 1
-          const int s = e % slots;
-          mbar_wait(&full[s], (e / slots) & 1);
+          const uint32_t s = e % (uint32_t)slots;
+          mbar_wait(&full[s], (e / (uint32_t)slots) & 1);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t slot_base = smem_u32(ring + (size_t)s * p.slot_bytes);
+            const uint64_t a_base = desc0 + (uint64_t)(ring16 + s * ((uint32_t)Cfg::kSlotBytes >> 4));
+#pragma unroll
             for (int q = 0; q < 3; ++q) {
-              const int t = r * 3 + q;
-              const uint32_t a_hi = slot_base + (uint32_t)(p.q_copy[q] * kPlanes) * (uint32_t)p.row_bytes +
-                                    (uint32_t)p.q_shift[q] * pix_bytes;
-              const uint32_t a_lo = a_hi + (uint32_t)p.row_bytes;
-              const uint32_t b_hi = w_base + (uint32_t)(t * kPlanes) * (uint32_t)p.w_tap_bytes;
-              const uint32_t b_lo = b_hi + (uint32_t)p.w_tap_bytes;
-              const uint64_t da_hi = kmajor_desc_shifted(a_hi, p.kc, p.base_offset);
-              const uint64_t da_lo = kmajor_desc_shifted(a_lo, p.kc, p.base_offset);
-              const uint64_t db_hi = kmajor_desc(b_hi, p.kc);
-              const uint64_t db_lo = kmajor_desc(b_lo, p.kc);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t adv = (uint64_t)(k * 2);
+#pragma unroll
+              for (int k = 0; k < kSteps; ++k) {
+                constexpr uint32_t two = 2;
+                const uint64_t da_hi = a_base + (uint64_t)(q * kPix16 + k * two);
+                const uint64_t da_lo = da_hi + kRow16;
+                const uint64_t db_hi = b_base + (uint64_t)((r * 3 + q) * kPlanes * kTap16 + k * two);
+                const uint64_t db_lo = db_hi + kTap16;
                 if (NPASS == 3) {
-                  umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, (t | k) != 0);
-                  umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
-                  umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1);
+                  umma_bf16(tmem_d, da_lo, db_hi, idesc, (r | q | k) != 0);
+                  umma_bf16(tmem_d, da_hi, db_lo, idesc, 1);
+                  umma_bf16(tmem_d, da_hi, db_hi, idesc, 1);
                 } else {
-                  umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (t | k) != 0);
+                  umma_bf16(tmem_d, da_hi, db_hi, idesc, (r | q | k) != 0);
                 }
               }
             }
             if (r == 2) {
-              umma_commit(&empty[g % slots]);       // row h - 1 is not needed any more
+              umma_commit(&empty[g % (uint32_t)slots]);     // row h - 1 is not needed any more
               umma_commit(&tmem_full[buf]);
             }
           }
@@ -561,8 +563,8 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       }
       // end of the strip: the two trailing rows (h1 - 1, h1) are released as well
       if (elect_one()) {
-        umma_commit(&empty[g % slots]);
-        umma_commit(&empty[(g + 1) % slots]);
+        umma_commit(&empty[g % (uint32_t)slots]);
+        umma_commit(&empty[(g + 1) % (uint32_t)slots]);
       }
       __syncwarp();
       g += 2;
@@ -580,7 +582,7 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       for (int h = h0; h < h1; ++h, ++local) {
         const uint32_t buf = local & 1;
         const uint32_t use = local >> 1;
-        const size_t row = ((size_t)(n * p.H + h) * kTileM + m) * p.Cout;
+        const size_t row = ((size_t)(n * p.H + h) * kTileM + m) * BN;
         mbar_wait(&tmem_full[buf], use & 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * kTmemCols + ((uint32_t)(quad * 32) << 16);
@@ -823,6 +825,199 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ===================================================== halo-row weight gradient (W == 128) ==
+// Same staging idea as conv_tc_row_kernel for dW of 3x3 stride-1 convolutions over 128-pixel-wide
+// maps: ring entry rho holds the dy row rho (130 pixels, halo zero-filled by TMA) and the x row
+// rho.  For the x row h and filter row r the GEMM  D_r[(q, co)][ci] += dy[h-r+1, w-q+1, co] *
+// x[h, w, ci]  runs over K = the 128 pixels of the row in 16-pixel steps; the three horizontal
+// taps are three M blocks of ONE MN-major descriptor whose leading-dimension offset is one pixel
+// (M block b reads the dy row shifted by b pixels, i.e. q = 2 - b; the remaining M blocks read
+// further-shifted data into TMEM lanes nobody looks at).  Each CTA keeps three accumulators
+// (one per filter row) in TMEM over all the rows it owns and writes one partial gradient; the
+// deterministic second stage (wgrad_reduce) sums the per-CTA partials.
+struct TcWgRowParams {
+  int N, H;
+  int strips, rows_per_strip, items;
+  int slots;
+  float* part;              // [gridDim.x][Cout][9 * Cin]
+};
+
+template <int NPASS, int CIN, int COUT>
+struct WgRowCfg {
+  static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
+  static constexpr int kDRowBytes = (kRowBox * COUT * 2 + 1023) / 1024 * 1024;   // one dy plane
+  static constexpr int kXRowBytes = kTileM * CIN * 2;                            // one x plane
+  static constexpr int kSlotBytes = kPlanes * (kDRowBytes + kXRowBytes);
+  static constexpr int kSlotsRaw = (227 * 1024 - 1024 - kBarrierBytes) / kSlotBytes;
+  static constexpr int kSlots = kSlotsRaw > kMaxStages ? kMaxStages : kSlotsRaw;
+  static constexpr uint32_t kTmemCols = CIN == 16 ? 64u : (CIN == 32 ? 128u : 256u);   // >= 3 * CIN
+};
+
+template <int NPASS, int CIN, int COUT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
+                         const __grid_constant__ CUtensorMap tmD_lo,
+                         const __grid_constant__ CUtensorMap tmX_hi,
+                         const __grid_constant__ CUtensorMap tmX_lo, const TcWgRowParams p) {
+  using Cfg = WgRowCfg<NPASS, CIN, COUT>;
+  constexpr int kPlanes = Cfg::kPlanes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  const int slots = p.slots;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)slots * Cfg::kSlotBytes);
+  uint64_t* empty = full + slots;
+  uint64_t* tmem_full = empty + slots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tmap_prefetch(&tmD_hi);
+    tmap_prefetch(&tmX_hi);
+    if (NPASS == 3) {
+      tmap_prefetch(&tmD_lo);
+      tmap_prefetch(&tmX_lo);
+    }
+    for (int s = 0; s < slots; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      constexpr uint32_t tx_d = (uint32_t)(kRowBox * COUT * 2) * kPlanes;
+      constexpr uint32_t tx_x = (uint32_t)(kTileM * CIN * 2) * kPlanes;
+      uint32_t g = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int n = item / p.strips;
+        const int h0 = (item - n * p.strips) * p.rows_per_strip;
+        const int h1 = min(p.H, h0 + p.rows_per_strip);
+        for (int hr = h0 - 1; hr <= h1; ++hr, ++g) {
+          const int s = g % slots;
+          mbar_wait(&empty[s], ((g / slots) & 1) ^ 1);
+          uint8_t* dst = ring + (size_t)s * Cfg::kSlotBytes;
+          const bool with_x = hr >= h0 && hr < h1;
+          mbar_expect_tx(&full[s], tx_d + (with_x ? tx_x : 0u));
+          tma_load_4d(dst, &tmD_hi, &full[s], 0, -1, hr, n);
+          if (NPASS == 3) tma_load_4d(dst + Cfg::kDRowBytes, &tmD_lo, &full[s], 0, -1, hr, n);
+          if (with_x) {
+            uint8_t* xd = dst + kPlanes * Cfg::kDRowBytes;
+            tma_load_4d(xd, &tmX_hi, &full[s], 0, 0, hr, n);
+            if (NPASS == 3) tma_load_4d(xd + Cfg::kXRowBytes, &tmX_lo, &full[s], 0, 0, hr, n);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // D fp32, A/B bf16, both MN-major, M = 128, N = CIN
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(CIN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    // per 16-pixel K step the operands advance by 16 pixel rows; everything in 16-byte units
+    constexpr uint32_t kDStep16 = (uint32_t)(16 * COUT * 2) >> 4;
+    constexpr uint32_t kXStep16 = (uint32_t)(16 * CIN * 2) >> 4;
+    constexpr uint32_t kDRow16 = (uint32_t)Cfg::kDRowBytes >> 4;
+    constexpr uint32_t kXRow16 = (uint32_t)Cfg::kXRowBytes >> 4;
+    constexpr uint32_t kSlot16 = (uint32_t)Cfg::kSlotBytes >> 4;
+    // M side: leading-dimension offset = one pixel -> M block b is the row shifted by b pixels
+    const uint64_t d_desc0 = mnmajor_desc(0u, (uint32_t)(COUT * 2), COUT);
+    const uint64_t x_desc0 = mnmajor_desc(0u, (uint32_t)Cfg::kXRowBytes, CIN);
+    const uint32_t ring16 = smem_u32(ring) >> 4;
+    uint32_t g = 0;
+    uint32_t acc0 = 0;           // 0 until the first row has been accumulated
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int n = item / p.strips;
+      const int h0 = (item - n * p.strips) * p.rows_per_strip;
+      const int h1 = min(p.H, h0 + p.rows_per_strip);
+      for (int h = h0; h < h1; ++h, ++g) {
+        uint32_t sl[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const uint32_t e = g + (uint32_t)j;
+          sl[j] = e % (uint32_t)slots;
+          mbar_wait(&full[sl[j]], (e / (uint32_t)slots) & 1);
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t xb = x_desc0 + (uint64_t)(ring16 + sl[1] * kSlot16 + kPlanes * kDRow16);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            // dy row h - r + 1 is ring entry g + 2 - r (entry g holds row h - 1)
+            const uint64_t db = d_desc0 + (uint64_t)(ring16 + sl[2 - r] * kSlot16);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(r * CIN);
+#pragma unroll
+            for (int ks = 0; ks < kTileM / 16; ++ks) {
+              const uint64_t dah = db + (uint64_t)(ks * kDStep16);
+              const uint64_t dbh = xb + (uint64_t)(ks * kXStep16);
+              if (NPASS == 3) {
+                const uint64_t dal = dah + kDRow16;
+                const uint64_t dbl = dbh + kXRow16;
+                umma_bf16(tmem_d, dal, dbh, idesc, ks == 0 ? acc0 : 1u);
+                umma_bf16(tmem_d, dah, dbl, idesc, 1);
+                umma_bf16(tmem_d, dah, dbh, idesc, 1);
+              } else {
+                umma_bf16(tmem_d, dah, dbh, idesc, ks == 0 ? acc0 : 1u);
+              }
+            }
+          }
+          umma_commit(&empty[sl[0]]);
+        }
+        __syncwarp();
+        acc0 = 1;
+      }
+      if (elect_one()) {
+        umma_commit(&empty[g % (uint32_t)slots]);
+        umma_commit(&empty[(g + 1) % (uint32_t)slots]);
+      }
+      __syncwarp();
+      g += 2;
+    }
+    if (elect_one()) umma_commit(tmem_full);
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int b = m / COUT;                   // M block = horizontal shift
+    const int co = m - b * COUT;
+    const bool valid = b < 3;
+    const int q = 2 - b;
+    constexpr size_t KK = (size_t)9 * CIN;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int r = 0; r < 3; ++r) {
+      float* dst = p.part + ((size_t)blockIdx.x * COUT + co) * KK + (size_t)(r * 3 + q) * CIN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < CIN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(r * CIN + c0), v);
+        if (valid) {
+          float4* o4 = reinterpret_cast<float4*>(dst + c0);
+          constexpr int nq = (CIN < 32 ? CIN : 32) >> 2;
+#pragma unroll
+          for (int j = 0; j < nq; ++j)
+            o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -1095,91 +1290,91 @@ static int tc_launch(const TcParams& p0, const void* x_hi, const void* x_lo, int
                     : launch_tc_bn<1>(BN, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
 }
 
-// ---- halo-row kernel: planning and launch
+// ---- halo-row kernels: planning and launch
 static bool row_geometry_ok(const ConvGeom& g) {
   if (g.KH != 3 || g.KW != 3 || g.stride != 1 || g.pad != 1) return false;
   if (g.W != kTileM || g.OW != kTileM || g.OH != g.H || g.N < 1) return false;
   if (g.Cin != 16 && g.Cin != 32 && g.Cin != 64) return false;
   if (g.Cout != 16 && g.Cout != 32 && g.Cout != 64) return false;
+  if (g.Cin == 64 && g.Cout == 64) return false;    // nine resident 64x64 taps leave < 4 row slots
   return true;
 }
 
-static bool row_plan(const ConvGeom& g, int npass, TcRowParams& p, int& smem_bytes) {
-  if (!row_geometry_ok(g)) return false;
-  const int planes = npass == 3 ? 2 : 1;
-  p.N = g.N; p.H = g.H; p.Cin = g.Cin; p.Cout = g.Cout;
-  p.kc = g.Cin;
-  // how the three horizontal taps are read: 1 = one staged copy, descriptor shifted by q pixels;
-  // 2 = hybrid (shifts that change the swizzle phase inside a 128-byte line come from a second /
-  // third pre-shifted copy); 3 = three pre-shifted copies, no shifted descriptor at all
-  const int mode = get_option(OPT_TC_ROW_COPIES);
-  int nc = 1;
-  if (mode == 3) nc = 3;
-  else if (mode == 2) nc = g.Cin == 64 ? 1 : (g.Cin == 32 ? 2 : 3);
-  p.ncopies = nc;
-  for (int q = 0; q < 3; ++q) {
-    if (nc == 1) { p.q_copy[q] = 0; p.q_shift[q] = q; }
-    else if (nc == 3) { p.q_copy[q] = q; p.q_shift[q] = 0; }
-    else { p.q_copy[q] = q == 1 ? 1 : 0; p.q_shift[q] = q == 2 ? 2 : 0; }
-  }
-  p.copy_w0[0] = -1; p.copy_w0[1] = nc == 2 ? 0 : 0; p.copy_w0[2] = 1;
-  p.row_bytes = (int)align_up((size_t)kRowBox * g.Cin * 2, 1024);
-  p.slot_bytes = p.row_bytes * nc * planes;
-  p.w_tap_bytes = g.Cout * g.Cin * 2 < 1024 ? 1024 : g.Cout * g.Cin * 2;
-  const int fixed = 9 * planes * p.w_tap_bytes + 1024 + kBarrierBytes;
-  p.slots = (227 * 1024 - fixed) / p.slot_bytes;
-  if (p.slots > kMaxStages) p.slots = kMaxStages;
-  if (p.slots < 4) return false;
-  smem_bytes = fixed + p.slots * p.slot_bytes;
-  p.base_offset = get_option(OPT_TC_ROW_BASE_OFFSET);
-  // strips of consecutive output rows per work item: balance over the SMs vs halo re-reads
-  int forced = get_option(OPT_TC_ROW_STRIPS);
+// strips of consecutive rows per work item: balance over the SMs vs halo rows staged twice
+static void pick_strips(int N, int H, int& strips, int& rows_per_strip) {
+  const int forced = get_option(OPT_TC_ROW_STRIPS);
   int best_s = 1;
   double best = -1.0;
-  for (int st = 1; st <= g.H; ++st) {
-    const int rps = cdiv(g.H, st);
-    if (cdiv(g.H, rps) != st) continue;           // skip strip counts that leave empty strips
-    const long long items = (long long)g.N * st;
+  for (int st = 1; st <= H; ++st) {
+    const int rps = cdiv(H, st);
+    if (cdiv(H, rps) != st) continue;             // skip strip counts that leave empty strips
+    const long long items = (long long)N * st;
     const double balance = (double)items / (double)(cdiv(items, kNumSMs) * kNumSMs);
     const double eff = balance * (double)rps / (double)(rps + 1);
-    if (forced ? st == forced : eff > best + 1e-9) { best = eff; best_s = st; }
+    if (forced ? st == forced : eff > best + 1e-9) {
+      best = eff;
+      best_s = st;
+    }
   }
-  p.strips = best_s;
-  p.rows_per_strip = cdiv(g.H, best_s);
-  p.items = g.N * p.strips;
-  return true;
+  strips = best_s;
+  rows_per_strip = cdiv(H, best_s);
 }
 
 bool conv_tc_row_supported(const ConvGeom& g) {
-  if (!get_option(OPT_TC_ROW_KERNEL)) return false;
-  TcRowParams p;
-  int smem;
-  return row_plan(g, 3, p, smem);
+  return get_option(OPT_TC_ROW_KERNEL) != 0 && row_geometry_ok(g);
 }
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, int KC>
 static int launch_row(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                      const CUtensorMap& b_lo, const TcRowParams& p, int smem_bytes,
-                      cudaStream_t s) {
+                      const CUtensorMap& b_lo, TcRowParams p, cudaStream_t s) {
+  using Cfg = RowCfg<BN, NPASS, KC>;
+  if (Cfg::kSlots < 4) {
+    EVE_REQUIRE(false, EVE_ERR_SHAPE, "conv_tc_row: %d -> %d channels do not fit", KC, BN);
+    return EVE_ERR_SHAPE;
+  }
   static bool configured = false;
   if (!configured) {
-    EVE_CUDA(cudaFuncSetAttribute(conv_tc_row_kernel<BN, NPASS>,
+    EVE_CUDA(cudaFuncSetAttribute(conv_tc_row_kernel<BN, NPASS, KC>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
+  p.slots = Cfg::kSlots;
+  const int smem_bytes = Cfg::kFixedBytes + Cfg::kSlots * Cfg::kSlotBytes;
   const int grid = p.items < kNumSMs ? p.items : kNumSMs;
-  conv_tc_row_kernel<BN, NPASS><<<grid, kThreads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+  conv_tc_row_kernel<BN, NPASS, KC><<<grid, kThreads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
+}
+
+template <int BN, int KC>
+static int launch_row_np(int npass, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                         const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcRowParams& p,
+                         cudaStream_t s) {
+  return npass == 3 ? launch_row<BN, 3, KC>(a_hi, a_lo, b_hi, b_lo, p, s)
+                    : launch_row<BN, 1, KC>(a_hi, a_lo, b_hi, b_lo, p, s);
+}
+
+template <int BN>
+static int launch_row_kc(int kc, int npass, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                         const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcRowParams& p,
+                         cudaStream_t s) {
+  switch (kc) {
+    case 16: return launch_row_np<BN, 16>(npass, a_hi, a_lo, b_hi, b_lo, p, s);
+    case 32: return launch_row_np<BN, 32>(npass, a_hi, a_lo, b_hi, b_lo, p, s);
+    default: return launch_row_np<BN, 64>(npass, a_hi, a_lo, b_hi, b_lo, p, s);
+  }
 }
 
 static int conv_tc_row_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* w_hi,
                            const void* w_lo, const float* bias, const float* addend, float* y,
                            int npass, int fmt, float out_scale, cudaStream_t s) {
+  EVE_REQUIRE(row_geometry_ok(g), EVE_ERR_SHAPE, "conv_tc_row: unsupported geometry");
   TcRowParams p;
-  int smem = 0;
-  EVE_REQUIRE(row_plan(g, npass, p, smem), EVE_ERR_SHAPE, "conv_tc_row: unsupported geometry");
+  p.N = g.N; p.H = g.H; p.Cout = g.Cout;
+  pick_strips(g.N, g.H, p.strips, p.rows_per_strip);
+  p.items = g.N * p.strips;
   p.fmt = fmt;
+  p.slots = 0;
   p.out_scale = out_scale;
   p.bias = bias; p.addend = addend; p.out = y;
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
@@ -1192,18 +1387,11 @@ static int conv_tc_row_run(const ConvGeom& g, const void* x_hi, const void* x_lo
     a_lo = a_hi;
     b_lo = b_hi;
   }
-#define EVE_ROW_CASE(BN_)                                                                      \
-  case BN_:                                                                                    \
-    return npass == 3 ? launch_row<BN_, 3>(a_hi, a_lo, b_hi, b_lo, p, smem, s)                 \
-                      : launch_row<BN_, 1>(a_hi, a_lo, b_hi, b_lo, p, smem, s);
   switch (g.Cout) {
-    EVE_ROW_CASE(16)
-    EVE_ROW_CASE(32)
-    EVE_ROW_CASE(64)
+    case 16: return launch_row_kc<16>(g.Cin, npass, a_hi, a_lo, b_hi, b_lo, p, s);
+    case 32: return launch_row_kc<32>(g.Cin, npass, a_hi, a_lo, b_hi, b_lo, p, s);
+    default: return launch_row_kc<64>(g.Cin, npass, a_hi, a_lo, b_hi, b_lo, p, s);
   }
-#undef EVE_ROW_CASE
-  EVE_REQUIRE(false, EVE_ERR_SHAPE, "conv_tc_row: Cout=%d", g.Cout);
-  return EVE_ERR_SHAPE;
 }
 
 // y[N,OH,OW,Cout] = conv(x) (+bias) (+addend).  x_hi/x_lo: 16-bit NHWC planes of the input;
@@ -1350,11 +1538,80 @@ static void wgrad_plan(const ConvGeom& g, TcWgradParams& p, int& mblocks, int& n
   splits = cdiv(p.tiles_total, p.tiles_per_split);
 }
 
+// ---- halo-row weight gradient: W == 128, 3x3 stride 1, Cout in {16, 32} (three pixel-shifted M
+// blocks of Cout channels must fit the 128-row MMA), Cin in {16, 32, 64}
+bool conv_tc_wgrad_row_supported(const ConvGeom& g) {
+  if (!get_option(OPT_TC_ROW_WGRAD) || !row_geometry_ok(g)) return false;
+  return g.Cout == 16 || g.Cout == 32;
+}
+
+template <int NPASS, int CIN, int COUT>
+static int launch_wgrad_row(const CUtensorMap& d_hi, const CUtensorMap& d_lo, const CUtensorMap& x_hi,
+                            const CUtensorMap& x_lo, TcWgRowParams p, int grid, cudaStream_t s) {
+  using Cfg = WgRowCfg<NPASS, CIN, COUT>;
+  static_assert(Cfg::kSlots >= 4, "halo-row wgrad: ring too shallow");
+  static bool configured = false;
+  if (!configured) {
+    EVE_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_row_kernel<NPASS, CIN, COUT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  p.slots = Cfg::kSlots;
+  const int smem_bytes = Cfg::kSlots * Cfg::kSlotBytes + 1024 + kBarrierBytes;
+  conv_tc_wgrad_row_kernel<NPASS, CIN, COUT><<<grid, kThreads, smem_bytes, s>>>(d_hi, d_lo, x_hi, x_lo, p);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+template <int CIN, int COUT>
+static int launch_wgrad_row_np(int npass, const CUtensorMap& d_hi, const CUtensorMap& d_lo,
+                               const CUtensorMap& x_hi, const CUtensorMap& x_lo,
+                               const TcWgRowParams& p, int grid, cudaStream_t s) {
+  return npass == 3 ? launch_wgrad_row<3, CIN, COUT>(d_hi, d_lo, x_hi, x_lo, p, grid, s)
+                    : launch_wgrad_row<1, CIN, COUT>(d_hi, d_lo, x_hi, x_lo, p, grid, s);
+}
+
+static int conv_tc_wgrad_row_run(const ConvGeom& g, const void* d_hi, const void* d_lo,
+                                 const void* x_hi, const void* x_lo, float* part, int npass,
+                                 int* splits_out, cudaStream_t s) {
+  TcWgRowParams p;
+  p.N = g.N; p.H = g.H;
+  pick_strips(g.N, g.H, p.strips, p.rows_per_strip);
+  p.items = g.N * p.strips;
+  p.slots = 0;
+  p.part = part;
+  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  CUtensorMap md_hi, md_lo, mx_hi, mx_lo;
+  EVE_TRY(make_map_nhwc(&md_hi, d_hi, g.N, g.H, g.W, g.Cout, g.Cout, kRowBox, 1, 1));
+  EVE_TRY(make_map_nhwc(&mx_hi, x_hi, g.N, g.H, g.W, g.Cin, g.Cin, kTileM, 1, 1));
+  if (npass == 3) {
+    EVE_TRY(make_map_nhwc(&md_lo, d_lo, g.N, g.H, g.W, g.Cout, g.Cout, kRowBox, 1, 1));
+    EVE_TRY(make_map_nhwc(&mx_lo, x_lo, g.N, g.H, g.W, g.Cin, g.Cin, kTileM, 1, 1));
+  } else {
+    md_lo = md_hi;
+    mx_lo = mx_hi;
+  }
+  *splits_out = grid;
+  const int key = g.Cin * 100 + g.Cout;
+  switch (key) {
+    case 1616: return launch_wgrad_row_np<16, 16>(npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
+    case 1632: return launch_wgrad_row_np<16, 32>(npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
+    case 3216: return launch_wgrad_row_np<32, 16>(npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
+    case 3232: return launch_wgrad_row_np<32, 32>(npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
+    case 6416: return launch_wgrad_row_np<64, 16>(npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
+    case 6432: return launch_wgrad_row_np<64, 32>(npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
+  }
+  EVE_REQUIRE(false, EVE_ERR_SHAPE, "conv_tc_wgrad_row: %d -> %d channels", g.Cin, g.Cout);
+  return EVE_ERR_SHAPE;
+}
+
 size_t conv_tc_wgrad_partial_floats(const ConvGeom& g) {
   if (!conv_tc_wgrad_supported(g)) return 0;
   TcWgradParams p;
   int mb, nb, sp;
   wgrad_plan(g, p, mb, nb, sp, 3);
+  // the halo-row kernel writes one partial per CTA
+  if (row_geometry_ok(g) && (g.Cout == 16 || g.Cout == 32)) sp = std::max(sp, kNumSMs);
   return (size_t)sp * g.Cout * g.K();
 }
 
@@ -1363,6 +1620,8 @@ int conv_tc_wgrad_run(const ConvGeom& g, const void* d_hi, const void* d_lo, con
                       const void* x_lo, float* part, int npass, int* splits_out,
                       cudaStream_t s, int x_fmt) {
   EVE_REQUIRE(conv_tc_wgrad_supported(g), EVE_ERR_SHAPE, "conv_tc_wgrad: unsupported geometry");
+  if (conv_tc_wgrad_row_supported(g) && x_fmt == TC_BF16)
+    return conv_tc_wgrad_row_run(g, d_hi, d_lo, x_hi, x_lo, part, npass, splits_out, s);
   TcWgradParams p;
   int mb, nb, sp;
   wgrad_plan(g, p, mb, nb, sp, npass);

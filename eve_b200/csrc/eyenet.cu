@@ -274,7 +274,7 @@ extern "C" int eve_eyenet_cnn_bwd(const eve_eyenet_cnn_params* p, const float* d
     EVE_TRY(conv_bwd(k.g2, k.y, db, w[slot + 1], gr[slot + 1], nullptr, acc, nullptr, dy, sc.cs, s));
     // y = relu(IN(a))
     float* da = sc.t0;
-    EVE_TRY(in_backward(dy, k.y, k.a, N, HW, C, k.am, k.ar, nullptr, nullptr, ACT_RELU, nullptr, da,
+    EVE_TRY(in_backward(dy, nullptr, k.a, N, HW, C, k.am, k.ar, nullptr, nullptr, ACT_RELU, nullptr, da,
                         nullptr, nullptr, nullptr, sc.inb, false, s));
     const float* addend = gskip;
     if (k.down) {

@@ -522,17 +522,20 @@ int block_bwd(const RBlock& k, int N, const float* const* w, float* const* gr, b
   float* const* bg = gr + k.slot;
   const int HW = k.H * k.W;
   EVE_TRY(conv_bwd(k.g2, k.y2, dout, bw[6], bg[6], bg[7], acc, nullptr, sc.t0, sc.cs, s));
-  EVE_TRY(in_backward(sc.t0, k.y2, k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], k.act, nullptr,
+  // activation masks are recomputed from (x, mean, rstd, gamma, beta) -- the same arithmetic as
+  // in_apply -- instead of being read back from the saved activations (4 bytes/element less in
+  // both backward passes of every normalisation)
+  EVE_TRY(in_backward(sc.t0, nullptr, k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], k.act, nullptr,
                       sc.t1, nullptr, bg[4], bg[5], sc.inb, acc, s));
   EVE_TRY(conv_bwd(k.g1, k.y1, sc.t1, bw[2], bg[2], bg[3], acc, nullptr, sc.t0, sc.cs, s));
   const float* addend = dout;
   if (k.skipconv) {
     EVE_TRY(conv_bwd(k.gs, k.s, dout, bw[10], bg[10], bg[11], acc, nullptr, sc.t2, sc.cs, s));
-    EVE_TRY(in_backward(sc.t2, k.s, k.x, N, HW, k.ic, k.m0, k.r0, bw[8], bw[9], k.act, nullptr,
+    EVE_TRY(in_backward(sc.t2, nullptr, k.x, N, HW, k.ic, k.m0, k.r0, bw[8], bw[9], k.act, nullptr,
                         sc.t1, nullptr, bg[8], bg[9], sc.inb, acc, s));
     addend = sc.t1;
   }
-  EVE_TRY(in_backward(sc.t0, k.y1, k.x, N, HW, k.ic, k.m0, k.r0, bw[0], bw[1], k.act, addend, dx,
+  EVE_TRY(in_backward(sc.t0, nullptr, k.x, N, HW, k.ic, k.m0, k.r0, bw[0], bw[1], k.act, addend, dx,
                       nullptr, bg[0], bg[1], sc.inb, acc, s));
   return EVE_OK;
 }
@@ -957,7 +960,7 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
   }
   // ---- initial
   EVE_TRY(conv_bwd(n.gi3, n.i1, cur, w[4], gr[4], gr[5], acc, nullptr, sc.t0, sc.cs, s));
-  EVE_TRY(in_backward(sc.t0, n.i1, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU, nullptr,
+  EVE_TRY(in_backward(sc.t0, nullptr, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU, nullptr,
                       sc.t1, nullptr, gr[2], gr[3], sc.inb, acc, s));
   {
     // zero-padded weights (and their gradient) live at the head of t2, which is free here

@@ -71,13 +71,8 @@ int eve_get_conv_mode(void);
  *   "tc_stage_cap"        2..24  ring depth limit of the implicit-GEMM kernel
  *   "tc_row_kernel"       0/1    halo-row kernel (input rows staged once, filter taps taken as
  *                                shifted shared-memory descriptors) for 3x3 stride-1, W == 128
- *   "tc_row_base_offset"  0/1    descriptor base-offset convention of those shifted operands
- *   "tc_row_copies"       1..3   1 = one staged copy per input row, taps via shifted descriptors;
- *                                3 = three pre-shifted copies; 2 = per swizzle mode
  *   "tc_row_strips"       0..128 row strips per image (0 = automatic)
  *   "tc_row_wgrad"        0/1    halo-row weight-gradient kernel
- *   "tc_mixed_wgrad"      0/1    weight gradients from fp16 x planes x bf16 dy planes
- *   "fused_planes"        0/1    InstanceNorm kernels emit the next conv's 16-bit operand planes
  * Unknown names / out-of-range values return EVE_ERR_CONFIG. */
 int eve_set_option(const char* name, int value);
 int eve_get_option(const char* name, int* value);

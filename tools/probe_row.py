@@ -26,14 +26,7 @@ def prof_ms(kind, fn, iters=3):
     return v[0].value / iters
 
 
-VARIANTS = [
-    ('generic', dict(tc_row_kernel=0)),
-    ('shift+boff', dict(tc_row_kernel=1, tc_row_copies=1, tc_row_base_offset=1)),
-    ('shift', dict(tc_row_kernel=1, tc_row_copies=1, tc_row_base_offset=0)),
-    ('hybrid+boff', dict(tc_row_kernel=1, tc_row_copies=2, tc_row_base_offset=1)),
-    ('hybrid', dict(tc_row_kernel=1, tc_row_copies=2, tc_row_base_offset=0)),
-    ('copies3', dict(tc_row_kernel=1, tc_row_copies=3, tc_row_base_offset=0)),
-]
+VARIANTS = [('generic', dict(tc_row_kernel=0)), ('row', dict(tc_row_kernel=1))]
 CASES = [(16, 16), (16, 32), (32, 32), (64, 16), (32, 16), (16, 64)]
 
 
@@ -67,25 +60,45 @@ for cin, cout in CASES:
             except Exception as e:  # noqa: BLE001
                 print('  %2d->%2d %-12s strips=%d  ERROR %s' % (cin, cout, name, strips, e), flush=True)
 
-print('== mixed-format wgrad (fp16 x planes x bf16 dy planes): rel err dw vs fp64')
-for (n, cin, h, w, cout, k, st) in [(2, 16, 72, 128, 16, 3, 1), (3, 64, 32, 32, 64, 3, 1),
-                                    (3, 64, 32, 32, 128, 3, 2), (2, 128, 18, 32, 128, 3, 1)]:
-    g = torch.Generator().manual_seed(n + cin + cout)
-    x = torch.randn(n, cin, h, w, generator=g)
-    wd = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).double().requires_grad_(True)
-    y = F.conv2d(x.double(), wd, None, stride=st, padding=k // 2)
+print('== halo-row wgrad accuracy (N=3, 72x128, 3x3): rel err dw / db vs fp64')
+for cin, cout in [(16, 16), (16, 32), (32, 32), (64, 16), (32, 16), (64, 32)]:
+    g = torch.Generator().manual_seed(cin * 100 + cout + 7)
+    x = torch.randn(3, cin, 72, 128, generator=g)
+    wd = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).double().requires_grad_(True)
+    y = F.conv2d(x.double(), wd, None, padding=1)
     dy = torch.randn(y.shape, generator=g)
     y.backward(dy.double())
-    for mixed in (0, 1):
-        L.set_option('tc_mixed_wgrad', mixed)
+    for row in (0, 1):
+        for strips in ((0, 3, 72) if row else (0,)):
+            L.set_option('tc_row_wgrad', row)
+            L.set_option('tc_row_strips', strips)
+            try:
+                dw, db = G.conv_wgrad(x.cuda(), dy.cuda(), 3, 1, 1)
+                torch.cuda.synchronize()
+                print('  %2d->%2d row=%d strips=%2d  dw %.2e' % (cin, cout, row, strips, G.rel(dw, wd.grad)),
+                      flush=True)
+            except Exception as e:  # noqa: BLE001
+                print('  %2d->%2d row=%d strips=%d ERROR %s' % (cin, cout, row, strips, e), flush=True)
+L.set_option('tc_row_strips', 0)
+
+print('== wgrad kernel time at the bench geometry (N=240, 72x128), ms (kernel + split reduce)')
+for cin, cout in [(16, 16), (16, 32), (32, 32), (64, 16)]:
+    x = torch.randn(240, 72, 128, cin, device='cuda')
+    dy = torch.randn(240, 72, 128, cout, device='cuda')
+    dw = torch.empty(cout, cin, 3, 3, device='cuda')
+    p = L.ConvParams(240, 72, 128, cin, cout, 3, 1, 1)
+    ws = torch.empty(lib.eve_conv2d_workspace_bytes(C.byref(p)), dtype=torch.uint8, device='cuda')
+
+    def runw():
+        L.check(lib.eve_conv2d_wgrad(C.byref(p), L.ptr(x), L.ptr(dy), L.ptr(dw), None, L.ptr(ws),
+                                     ws.numel(), L.stream_ptr()), 'wgrad')
+    for row in (0, 1):
+        L.set_option('tc_row_wgrad', row)
         try:
-            dw, db = G.conv_wgrad(x.cuda(), dy.cuda(), k, st, k // 2)
-            torch.cuda.synchronize()
-            print('  n%d %d->%d %dx%d k%d s%d mixed=%d  dw %.2e' % (n, cin, cout, h, w, k, st, mixed,
-                                                                 G.rel(dw, wd.grad)), flush=True)
+            print('  %2d->%2d row=%d  %.3f ms' % (cin, cout, row, prof_ms(2, runw)), flush=True)
         except Exception as e:  # noqa: BLE001
-            print('  mixed=%d ERROR %s' % (mixed, e), flush=True)
-L.set_option('tc_mixed_wgrad', 0)
+            print('  %2d->%2d row=%d ERROR %s' % (cin, cout, row, e), flush=True)
+    del x, dy, ws
 
 print('== kernel time at the bench geometry (N=240, 72x128), conv kernel only, ms')
 for cin, cout in CASES[:4]:
@@ -100,7 +113,7 @@ for cin, cout in CASES[:4]:
                                    ws.numel(), L.stream_ptr()), 'fwd')
     for name, opts in VARIANTS:
         apply(opts, 0)
-        for cap in ((6, 24) if name == 'generic' else (24,)):
+        for cap in (24,):
             L.set_option('tc_stage_cap', cap)
             try:
                 print('  %2d->%2d %-12s stage_cap=%2d  %.3f ms' % (cin, cout, name, cap, prof_ms(0, run)),
