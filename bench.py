@@ -272,6 +272,11 @@ def profiled_eager_run(model, trainer, inputs_fn, steps, world, device):
 
     one(0)
     _barrier_sync(world)
+    # `ncu --profile-from-start off ... python bench.py` captures exactly these eagerly launched
+    # steps (the launch list / DRAM traffic under profiles/); a no-op without a profiler attached
+    ncu_range = os.environ.get('EVE_BENCH_NCU_RANGE') == '1'
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStart()
     lib.eve_profile_reset()
     lib.eve_profile_enable(1)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -283,6 +288,8 @@ def profiled_eager_run(model, trainer, inputs_fn, steps, world, device):
         ev1[i].record()
     _barrier_sync(world)
     lib.eve_profile_enable(0)
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
     prof = {}
     for kind, name in ((0, 'conv_fwd'), (1, 'conv_dgrad'), (2, 'conv_wgrad')):
@@ -393,12 +400,23 @@ def b200_arm(args):
     if peak is None:
         peak, peak_src = 1400.0, 'fallback (B200_PROFILING.md sustained figure)'
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    # DRAM bytes per conv launch, from the committed ncu pass over this same command
+    # (dram__bytes_read.sum + dram__bytes_write.sum of every conv kernel of one step / launches)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(REPO, 'profiles', 'conv_traffic.json')
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get('workload') == args.workload:
+            traffic = tj.get('dram_bytes_per_conv_launch')
+            traffic_src = tj.get('source')
     roofline = {
-        'bound': 'tensor', 'kernel': 'conv_tc_kernel / conv_tc_wgrad_kernel (tcgen05 implicit GEMM, '
-                                     'split fp16/bf16 operands = 3 MMAs per product) + the few '
-                                     'CUDA-core convs left; all conv fwd + dgrad + wgrad launches',
+        'bound': 'tensor', 'kernel': 'conv_tc_kernel / conv_tc_row_kernel / conv_tc_wgrad_kernel / '
+                                     'conv_tc_wgrad_row_kernel (tcgen05 implicit GEMM, split '
+                                     'fp16/bf16 operands = 3 MMAs per product) + the few CUDA-core '
+                                     'convs left; all conv fwd + dgrad + wgrad launches',
         'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-        'peak_source': peak_src, 'traffic': None,
+        'peak_source': peak_src, 'traffic': traffic, 'traffic_source': traffic_src,
         'launches': conv_launches, 'avg_launch_ms': conv_ms / max(conv_launches, 1),
         'share_of_step': conv_ms / main['prof_ms'],
         'timed_in': 'the same K steps launched eagerly (kernel-by-kernel, events on the launching '

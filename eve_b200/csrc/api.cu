@@ -141,6 +141,8 @@ static Opt g_opts[OPT_COUNT] = {
     {"tc_row_kernel", 1, 0, 1, "EVE_B200_TC_ROW_KERNEL", false},
     {"tc_row_strips", 0, 0, 128, "EVE_B200_TC_ROW_STRIPS", false},
     {"tc_row_wgrad", 1, 0, 1, "EVE_B200_TC_ROW_WGRAD", false},
+    {"tc_wgrad_waves", 3, 1, 8, "EVE_B200_TC_WGRAD_WAVES", false},
+    {"fused_planes", 1, 0, 1, "EVE_B200_FUSED_PLANES", false},
 };
 int get_option(int key) {
   if (key < 0 || key >= OPT_COUNT) return 0;

@@ -157,6 +157,8 @@ enum OptKey {
   OPT_TC_ROW_KERNEL,         // halo-row tcgen05 kernel for 3x3 stride-1 layers with W == 128
   OPT_TC_ROW_STRIPS,         // 0 = automatic; otherwise the number of row strips per image
   OPT_TC_ROW_WGRAD,          // halo-row weight-gradient kernel (W == 128)
+  OPT_TC_WGRAD_WAVES,        // full waves of CTAs the split-K weight gradient is sized for
+  OPT_FUSED_PLANES,          // InstanceNorm kernels emit the consuming convolution's operand planes
   OPT_COUNT
 };
 int get_option(int key);
@@ -173,12 +175,27 @@ size_t conv_partial_floats(const ConvGeom& g);
 // largest operand (elements) any pass of `g` stages as 16-bit planes (covers the stem's
 // materialised patch matrix)
 size_t conv_operand_elems(const ConvGeom& g);
+// x == nullptr: the caller has already written the input's operand planes where
+// conv_x_planes_fwd() points (only when conv_x_fusable(g)).
 int conv_fwd(const ConvGeom& g, const float* x, const float* w_oihw, const float* bias,
              const float* addend, float* y, const ConvScratch& sc, cudaStream_t s);
+// Producer/consumer fusion of the operand split: true when conv_fwd AND conv_bwd of `g` both take
+// the split tensor-core path, so that the producer of x may write its 16-bit planes straight into
+// the scratch slice (fp16 planes for conv_fwd, bf16 planes for conv_bwd) and pass x = nullptr.
+bool conv_x_fusable(const ConvGeom& g);
+void conv_x_planes_fwd(const ConvGeom& g, const ConvScratch& sc, void** hi, void** lo);
+void conv_x_planes_bwd(const ConvGeom& g, const ConvScratch& sc, void** hi, void** lo);
 int conv_dgrad(const ConvGeom& g, const float* dy, const float* w_oihw, const float* addend,
                float* dx, const ConvScratch& sc, cudaStream_t s);
 int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw_oihw, float* dbias,
                bool accumulate, const ConvScratch& sc, cudaStream_t s);
+// Weights of a convolution that is applied many times in a row (ConvRNN cells): prepared once into
+// the top of the scratch slice; conv_fwd / stride-1 conv_dgrad calls with the same weight pointer
+// then skip their own preparation until conv_prepared_clear().  *top_used accumulates the bytes
+// taken from the top (start at 0).  A no-op when the tensor-core path would not be taken.
+int conv_prepare_weights(const ConvGeom& g, const float* w_oihw, bool dgrad, const ConvScratch& sc,
+                         size_t* top_used, cudaStream_t s);
+void conv_prepared_clear();
 // both gradients of one convolution (dw/dbias and dx, each optional) from one split of dy
 int conv_bwd(const ConvGeom& g, const float* x, const float* dy, const float* w_oihw, float* dw,
              float* dbias, bool accumulate, const float* addend, float* dx, const ConvScratch& sc,
@@ -195,6 +212,19 @@ int in_stats(const float* x, int N, int HW, int C, float* mean, float* rstd, cud
 int in_apply(const float* x, int N, int HW, int C, const float* mean, const float* rstd,
              const float* gamma, const float* beta, const float* res, const float* res_mean,
              const float* res_rstd, int act, float* y, cudaStream_t s);
+// y = act(IN(x)*gamma+beta) written as the 16-bit hi/lo operand planes (fmt: TcFormat) of the
+// convolution that consumes it, and as fp32 when y != null
+int in_apply_planes(const float* x, int N, int HW, int C, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, int act, int fmt, float* y, void* hi,
+                    void* lo, cudaStream_t s);
+// act(IN(x)) feeding convolution `g`: as fp32 `y` (forward; conv_* then split it themselves) or,
+// when conv_x_fusable(g), straight into the convolution's 16-bit operand planes inside its scratch
+// slice (*fused = true: pass x = nullptr to conv_fwd / conv_bwd).  backward = true re-derives the
+// bf16 planes conv_bwd needs from the saved pre-norm tensor (nothing to do when not fusable: the
+// forward pass kept y).
+int norm_act_into_conv(const ConvGeom& g, bool backward, const float* x, int N, int HW, int C,
+                       const float* mean, const float* rstd, const float* gamma, const float* beta,
+                       int act, float* y, const ConvScratch& cs, bool* fused, cudaStream_t s);
 // Backward of y = act(IN(x)*gamma+beta + res):
 //   g   = dy * act'(y)                          (written to g_out if non-null: grad wrt res)
 //   dx  = rstd*gamma*( g - mean_hw(g) - xhat*mean_hw(g*xhat) )  (+ addend, optional)

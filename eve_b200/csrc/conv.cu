@@ -18,7 +18,7 @@ int g_mode = -1;
 // torchvision ResNet.conv1 (eye_net.py:48-50): K = 7*7*3 = 147 is too thin for a TMA box per
 // tap, so the patch matrix is materialised once ([pixels][192] 16-bit hi/lo planes, K padded
 // with zeros) and the convolution / its weight gradient run as 1x1 tensor-core GEMMs.
-constexpr int kStemK = 192;
+constexpr int kStemK = 160;        // 147 rounded up to five 32-channel K chunks
 
 __device__ __forceinline__ void split16(float v, int fmt, uint16_t& h, uint16_t& l) {
   if (fmt == TC_BF16) {
@@ -32,37 +32,52 @@ __device__ __forceinline__ void split16(float v, int fmt, uint16_t& h, uint16_t&
   }
 }
 
-// one thread = one output pixel x 8 consecutive k (one 16-byte store per plane)
+// One block = one output row of one image.  The seven input rows it touches are staged in shared
+// memory with coalesced loads (the gather itself then never leaves the SM); every work item is
+// one output pixel x 8 consecutive k, i.e. one 16-byte store per plane, consecutive items writing
+// consecutive addresses.
 __global__ void __launch_bounds__(256)
-stem_im2col_kernel(const float* __restrict__ x, long long total, int H, int W, int OH, int OW,
-                   int fmt, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int kg = (int)(i % (kStemK / 8));
-  long long pix = i / (kStemK / 8);
-  const int ox = (int)(pix % OW);
-  long long t = pix / OW;
-  const int oy = (int)(t % OH);
-  const int n = (int)(t / OH);
-  const float* xp = x + (size_t)n * H * W * 3;
-  uint16_t h[8], l[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = kg * 8 + j;
-    float v = 0.f;
-    if (k < 147) {
-      const int tap = k / 3, c = k - tap * 3;
-      const int r = tap / 7, q = tap - r * 7;
-      const int iy = oy * 2 + r - 3, ix = ox * 2 + q - 3;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xp + ((size_t)iy * W + ix) * 3 + c);
+stem_im2col_kernel(const float* __restrict__ x, int H, int W, int OH, int OW, int fmt,
+                   uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  extern __shared__ float srow[];                 // [7][W * 3]
+  const int oy = blockIdx.x % OH;
+  const int n = blockIdx.x / OH;
+  const int rowlen = W * 3;
+  for (int r = 0; r < 7; ++r) {
+    const int iy = oy * 2 + r - 3;
+    float* dst = srow + r * rowlen;
+    if (iy >= 0 && iy < H) {
+      const float* src = x + ((size_t)n * H + iy) * rowlen;
+      for (int i = threadIdx.x; i < rowlen; i += blockDim.x) dst[i] = __ldg(src + i);
+    } else {
+      for (int i = threadIdx.x; i < rowlen; i += blockDim.x) dst[i] = 0.f;
     }
-    split16(v, fmt, h[j], l[j]);
   }
-  reinterpret_cast<uint4*>(hi)[i] = *reinterpret_cast<uint4*>(h);
-  if (lo) reinterpret_cast<uint4*>(lo)[i] = *reinterpret_cast<uint4*>(l);
+  __syncthreads();
+  constexpr int kGroups = kStemK / 8;
+  const size_t out0 = ((size_t)n * OH + oy) * OW * kGroups;
+  for (int item = threadIdx.x; item < OW * kGroups; item += blockDim.x) {
+    const int ox = item / kGroups;
+    const int kg = item - ox * kGroups;
+    uint16_t h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kg * 8 + j;
+      float v = 0.f;
+      if (k < 147) {
+        const int tap = k / 3, c = k - tap * 3;
+        const int r = tap / 7, q = tap - r * 7;
+        const int ix = ox * 2 + q - 3;
+        if (ix >= 0 && ix < W) v = srow[r * rowlen + ix * 3 + c];
+      }
+      split16(v, fmt, h[j], l[j]);
+    }
+    reinterpret_cast<uint4*>(hi)[out0 + item] = *reinterpret_cast<uint4*>(h);
+    if (lo) reinterpret_cast<uint4*>(lo)[out0 + item] = *reinterpret_cast<uint4*>(l);
+  }
 }
 
-// OIHW [64][3][7][7] -> [64][192] (k = (r*7+q)*3 + c, zero padded)
+// OIHW [64][3][7][7] -> [64][kStemK] (k = (r*7+q)*3 + c, zero padded)
 __global__ void stem_prep_weights_kernel(const float* __restrict__ w, int Cout, int fmt,
                                          float scale, uint16_t* __restrict__ hi,
                                          uint16_t* __restrict__ lo) {
@@ -95,7 +110,7 @@ __global__ void stem_wgrad_reduce_kernel(const float* __restrict__ part, int S, 
 
 inline bool is_stem(const ConvGeom& g) {
   return g.KH == 7 && g.KW == 7 && g.stride == 2 && g.pad == 3 && g.Cin == 3 && g.Cout == 64 &&
-         g.OW <= 64 && g.OW >= 1;
+         g.OW <= 64 && g.OW >= 1 && g.W <= 512;
 }
 inline ConvGeom stem_gemm(const ConvGeom& g) {
   return make_conv(g.N, g.OH, g.OW, kStemK, g.Cout, 1, 1, 0);
@@ -163,28 +178,106 @@ size_t conv_operand_elems(const ConvGeom& g) {
   return m;
 }
 
+// ---- prepared weights: a caller that applies the same convolution many times (the ConvRNN cells
+// step through time) prepares the tensor-core weight layout once, at the TOP of the conv scratch,
+// and conv_fwd / conv_dgrad find it here by weight pointer instead of re-deriving it per call.
+struct PreparedW {
+  const float* w;
+  int dgrad, npass;
+  const uint16_t *hi, *lo;
+};
+static thread_local PreparedW g_prepared[8];
+static thread_local int g_nprepared = 0;
+
+static const PreparedW* find_prepared(const float* w, bool dgrad, int npass) {
+  for (int i = 0; i < g_nprepared; ++i)
+    if (g_prepared[i].w == w && g_prepared[i].dgrad == (dgrad ? 1 : 0) && g_prepared[i].npass == npass)
+      return &g_prepared[i];
+  return nullptr;
+}
+
+// scratch layout of the split tensor-core paths (shared by the kernels' callers and by the
+// producers that write operand planes in place, see conv_x_planes_*)
+struct FwdCarve {
+  uint16_t *w_hi, *w_lo, *x_hi, *x_lo;
+};
+static bool carve_fwd(const ConvGeom& g, const ConvScratch& sc, FwdCarve& f) {
+  Carve c{sc.base, sc.base + sc.bytes};
+  const size_t wel = (size_t)g.Cout * g.K();
+  f.w_hi = c.get<uint16_t>(wel);
+  f.w_lo = c.get<uint16_t>(wel);
+  f.x_hi = c.get<uint16_t>((size_t)g.in_elems());
+  f.x_lo = c.get<uint16_t>((size_t)g.in_elems());
+  return f.x_lo != nullptr;
+}
+struct BwdCarve {
+  float* part;
+  uint16_t *w_hi, *w_lo, *d_hi, *d_lo, *x_hi, *x_lo;
+};
+static bool carve_bwd(const ConvGeom& g, const ConvScratch& sc, BwdCarve& b) {
+  Carve c{sc.base, sc.base + sc.bytes};
+  const size_t wel = (size_t)g.Cout * g.K();
+  size_t pf = conv_tc_wgrad_partial_floats(g);
+  size_t cs = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
+  b.part = c.get<float>(pf > cs ? pf : cs);
+  b.w_hi = c.get<uint16_t>(wel);
+  b.w_lo = c.get<uint16_t>(wel);
+  b.d_hi = c.get<uint16_t>((size_t)g.out_elems());
+  b.d_lo = c.get<uint16_t>((size_t)g.out_elems());
+  b.x_hi = c.get<uint16_t>((size_t)g.in_elems());
+  b.x_lo = c.get<uint16_t>((size_t)g.in_elems());
+  return b.x_lo != nullptr;
+}
+
+static bool bwd_dgrad_s1(const ConvGeom& g) {
+  return g.stride == 1 && conv_tc_supported(dgrad_as_fwd(g));
+}
+
+bool conv_x_fusable(const ConvGeom& g) {
+  if (!get_option(OPT_FUSED_PLANES) || conv_mode() != 1 || tc_mask() != 7) return false;
+  if (!conv_tc_supported(g) || !conv_tc_wgrad_supported(g)) return false;
+  return bwd_dgrad_s1(g) || conv_tc_dgrad_s2_supported(g);
+}
+void conv_x_planes_fwd(const ConvGeom& g, const ConvScratch& sc, void** hi, void** lo) {
+  FwdCarve f;
+  carve_fwd(g, sc, f);
+  *hi = f.x_hi;
+  *lo = f.x_lo;
+}
+void conv_x_planes_bwd(const ConvGeom& g, const ConvScratch& sc, void** hi, void** lo) {
+  BwdCarve b;
+  carve_bwd(g, sc, b);
+  *hi = b.x_hi;
+  *lo = b.x_lo;
+}
+
 int conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* bias,
              const float* addend, float* y, const ConvScratch& sc, cudaStream_t s) {
   Carve c{sc.base, sc.base + sc.bytes};
   const size_t wel = (size_t)g.Cout * g.K();
   const int mode = conv_mode();
+  EVE_REQUIRE(x || conv_x_fusable(g), EVE_ERR_NULL,
+              "conv_fwd: x is NULL but the convolution does not take pre-split operand planes");
   if (mode != 0 && (tc_mask() & 1) && conv_tc_supported(g)) {
     const int npass = mode == 1 ? 3 : 1;
-    uint16_t* w_hi = c.get<uint16_t>(wel);
-    uint16_t* w_lo = c.get<uint16_t>(wel);
-    uint16_t* x_hi = c.get<uint16_t>((size_t)g.in_elems());
-    uint16_t* x_lo = c.get<uint16_t>((size_t)g.in_elems());
-    EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_fwd: scratch too small");
+    FwdCarve f;
+    EVE_REQUIRE(carve_fwd(g, sc, f), EVE_ERR_WORKSPACE, "conv_fwd: scratch too small");
     // forward, split mode: fp16 planes (22 mantissa bits for hi + lo); weights pre-scaled by
     // 2^6 so that their lo parts stay normal, undone exactly in the epilogue.  The single-pass
     // mode keeps bf16.
     const int fmt = npass == 3 ? TC_F16 : TC_BF16;
     const float wscale = npass == 3 ? 64.f : 1.f;
-    EVE_TRY(conv_tc_prep_weights(g, w, false, w_hi, npass == 3 ? w_lo : nullptr, fmt, wscale, s));
-    EVE_TRY(split_planes(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, fmt, s));
+    if (const PreparedW* pw = find_prepared(w, false, npass)) {
+      f.w_hi = const_cast<uint16_t*>(pw->hi);
+      f.w_lo = const_cast<uint16_t*>(pw->lo);
+    } else {
+      EVE_TRY(conv_tc_prep_weights(g, w, false, f.w_hi, npass == 3 ? f.w_lo : nullptr, fmt, wscale, s));
+    }
+    if (x) EVE_TRY(split_planes(x, g.in_elems(), f.x_hi, npass == 3 ? f.x_lo : nullptr, fmt, s));
     ProfScope prof(PROF_CONV_FWD, 2.0 * g.out_elems() * (double)g.K(),
                    4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
-    return conv_tc_run(g, x_hi, x_lo, w_hi, w_lo, bias, addend, y, npass, fmt, 1.f / wscale, s);
+    return conv_tc_run(g, f.x_hi, f.x_lo, f.w_hi, f.w_lo, bias, addend, y, npass, fmt,
+                       1.f / wscale, s);
   }
   if (mode != 0 && (tc_mask() & 1) && is_stem(g)) {
     const int npass = mode == 1 ? 3 : 1;
@@ -199,9 +292,8 @@ int conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* bia
     stem_prep_weights_kernel<<<cdiv(g.Cout * kStemK, 256), 256, 0, s>>>(
         w, g.Cout, fmt, wscale, w_hi, npass == 3 ? w_lo : nullptr);
     EVE_LAUNCH_CHECK();
-    const long long total = (long long)g.N * g.OH * g.OW * (kStemK / 8);
-    stem_im2col_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, g.H, g.W, g.OH, g.OW, fmt, x_hi,
-                                                       npass == 3 ? x_lo : nullptr);
+    stem_im2col_kernel<<<g.N * g.OH, 256, 7 * g.W * 3 * sizeof(float), s>>>(
+        x, g.H, g.W, g.OH, g.OW, fmt, x_hi, npass == 3 ? x_lo : nullptr);
     EVE_LAUNCH_CHECK();
     ProfScope prof(PROF_CONV_FWD, 2.0 * g.out_elems() * (double)g.K(),
                    4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
@@ -227,7 +319,12 @@ int conv_dgrad(const ConvGeom& g, const float* dy, const float* w, const float* 
       uint16_t* d_hi = c.get<uint16_t>((size_t)g.out_elems());
       uint16_t* d_lo = c.get<uint16_t>((size_t)g.out_elems());
       EVE_REQUIRE(d_lo, EVE_ERR_WORKSPACE, "conv_dgrad: scratch too small");
-      EVE_TRY(conv_tc_prep_weights(g, w, true, w_hi, npass == 3 ? w_lo : nullptr, TC_BF16, 1.f, s));
+      if (const PreparedW* pw = find_prepared(w, true, npass)) {
+        w_hi = const_cast<uint16_t*>(pw->hi);
+        w_lo = const_cast<uint16_t*>(pw->lo);
+      } else {
+        EVE_TRY(conv_tc_prep_weights(g, w, true, w_hi, npass == 3 ? w_lo : nullptr, TC_BF16, 1.f, s));
+      }
       EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
       ProfScope prof(PROF_CONV_DGRAD, 2.0 * g.out_elems() * (double)g.K(),
                      4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
@@ -305,9 +402,8 @@ int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, fl
     uint16_t* x_lo = c.get<uint16_t>((size_t)gg.in_elems());
     EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_wgrad(stem): scratch too small");
     EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
-    const long long total = (long long)g.N * g.OH * g.OW * (kStemK / 8);
-    stem_im2col_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, g.H, g.W, g.OH, g.OW, TC_BF16,
-                                                       x_hi, npass == 3 ? x_lo : nullptr);
+    stem_im2col_kernel<<<g.N * g.OH, 256, 7 * g.W * 3 * sizeof(float), s>>>(
+        x, g.H, g.W, g.OH, g.OW, TC_BF16, x_hi, npass == 3 ? x_lo : nullptr);
     EVE_LAUNCH_CHECK();
     int splits = 0;
     {
@@ -339,43 +435,46 @@ int conv_bwd(const ConvGeom& g, const float* x, const float* dy, const float* w,
              float* dbias, bool accumulate, const float* addend, float* dx, const ConvScratch& sc,
              cudaStream_t s) {
   const int mode = conv_mode();
-  const bool s1 = g.stride == 1 && conv_tc_supported(dgrad_as_fwd(g));
+  const bool s1 = bwd_dgrad_s1(g);
   const bool s2 = conv_tc_dgrad_s2_supported(g);
-  const bool fused = dw && dx && mode != 0 && (tc_mask() & 6) == 6 && conv_tc_wgrad_supported(g) &&
+  const bool fused = dw && mode != 0 && (tc_mask() & 6) == 6 && conv_tc_wgrad_supported(g) &&
                      (s1 || s2);
+  if (!x && !dw) {   // only the data gradient is wanted: x is not needed at all
+    if (dbias)
+      EVE_TRY(conv_wgrad(g, nullptr, dy, nullptr, dbias, accumulate, sc, s));
+    if (dx) EVE_TRY(conv_dgrad(g, dy, w, addend, dx, sc, s));
+    return EVE_OK;
+  }
+  EVE_REQUIRE(x || (fused && conv_x_fusable(g)), EVE_ERR_NULL,
+              "conv_bwd: x is NULL but the convolution does not take pre-split operand planes");
   if (!fused) {
     if (dw || dbias) EVE_TRY(conv_wgrad(g, x, dy, dw, dbias, accumulate, sc, s));
     if (dx) EVE_TRY(conv_dgrad(g, dy, w, addend, dx, sc, s));
     return EVE_OK;
   }
-  Carve c{sc.base, sc.base + sc.bytes};
   const int npass = mode == 1 ? 3 : 1;
   const size_t wel = (size_t)g.Cout * g.K();
-  size_t pf = conv_tc_wgrad_partial_floats(g);
-  size_t cs = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
-  float* part = c.get<float>(pf > cs ? pf : cs);
-  uint16_t* w_hi = c.get<uint16_t>(wel);
-  uint16_t* w_lo = c.get<uint16_t>(wel);
-  uint16_t* d_hi = c.get<uint16_t>((size_t)g.out_elems());
-  uint16_t* d_lo = c.get<uint16_t>((size_t)g.out_elems());
-  uint16_t* x_hi = c.get<uint16_t>((size_t)g.in_elems());
-  uint16_t* x_lo = c.get<uint16_t>((size_t)g.in_elems());
-  EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_bwd: scratch too small");
-  const int xfmt = TC_BF16;     // same format as dy: mixed fp16 x bf16 MMAs are illegal
-  EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
-  EVE_TRY(split_planes(x, g.in_elems(), x_hi, npass == 3 ? x_lo : nullptr, xfmt, s));
-  EVE_TRY(conv_tc_prep_weights(g, w, true, w_hi, npass == 3 ? w_lo : nullptr, TC_BF16, 1.f, s));
+  BwdCarve b;
+  EVE_REQUIRE(carve_bwd(g, sc, b), EVE_ERR_WORKSPACE, "conv_bwd: scratch too small");
+  float* part = b.part;
+  // tcgen05 kind::f16 needs both operands in ONE 16-bit format (an fp16 x bf16 instruction
+  // descriptor is an illegal instruction on sm_100a), so x is split as bf16 next to dy
+  EVE_TRY(split_planes(dy, g.out_elems(), b.d_hi, npass == 3 ? b.d_lo : nullptr, TC_BF16, s));
+  if (x) EVE_TRY(split_planes(x, g.in_elems(), b.x_hi, npass == 3 ? b.x_lo : nullptr, TC_BF16, s));
+  if (dx)
+    EVE_TRY(conv_tc_prep_weights(g, w, true, b.w_hi, npass == 3 ? b.w_lo : nullptr, TC_BF16, 1.f, s));
   const double flops = 2.0 * g.out_elems() * (double)g.K();
   const double bytes = 4.0 * (g.in_elems() + g.out_elems() + (double)wel);
   {
     int splits = 0;
     ProfScope prof(PROF_CONV_WGRAD, flops, bytes, s);
-    EVE_TRY(conv_tc_wgrad_run(g, d_hi, d_lo, x_hi, x_lo, part, npass, &splits, s, xfmt));
+    EVE_TRY(conv_tc_wgrad_run(g, b.d_hi, b.d_lo, b.x_hi, b.x_lo, part, npass, &splits, s));
     EVE_TRY(wgrad_reduce(part, splits, g, dw, accumulate, s));
   }
   if (dbias)
     EVE_TRY(colsum(dy, (long long)g.N * g.OH * g.OW, g.Cout, g.Cout, dbias, part, accumulate, s));
-  if (s2 && g.KH == 1) {
+  if (!dx) return EVE_OK;
+  if (!s1 && g.KH == 1) {
     if (addend) {
       if (addend != dx)
         EVE_CUDA(cudaMemcpyAsync(dx, addend, (size_t)g.in_elems() * sizeof(float),
@@ -386,9 +485,60 @@ int conv_bwd(const ConvGeom& g, const float* x, const float* dy, const float* w,
   }
   ProfScope prof(PROF_CONV_DGRAD, flops, bytes, s);
   if (s1)
-    return conv_tc_run(dgrad_as_fwd(g), d_hi, d_lo, w_hi, w_lo, nullptr, addend, dx, npass, TC_BF16,
-                       1.f, s);
-  return conv_tc_dgrad_s2_run(g, d_hi, d_lo, w_hi, w_lo, addend, dx, npass, s);
+    return conv_tc_run(dgrad_as_fwd(g), b.d_hi, b.d_lo, b.w_hi, b.w_lo, nullptr, addend, dx, npass,
+                       TC_BF16, 1.f, s);
+  return conv_tc_dgrad_s2_run(g, b.d_hi, b.d_lo, b.w_hi, b.w_lo, addend, dx, npass, s);
+}
+
+void conv_prepared_clear() { g_nprepared = 0; }
+
+// Prepare the weights of `g` for repeated conv_fwd (dgrad = false) or stride-1 conv_dgrad
+// (dgrad = true) calls.  Storage is taken from the top of the scratch slice, below `*top_used`
+// bytes already handed out there; nothing is registered (and the per-call preparation stays in
+// place) when the convolution would not take the split tensor-core path or when the region could
+// collide with the operand planes conv_fwd / conv_dgrad carve from the bottom.
+int conv_prepare_weights(const ConvGeom& g, const float* w, bool dgrad, const ConvScratch& sc,
+                         size_t* top_used, cudaStream_t s) {
+  const int mode = conv_mode();
+  if (mode == 0 || g_nprepared >= 8) return EVE_OK;
+  const int npass = mode == 1 ? 3 : 1;
+  if (!dgrad && !((tc_mask() & 1) && conv_tc_supported(g))) return EVE_OK;
+  if (dgrad && !((tc_mask() & 2) && g.stride == 1 && conv_tc_supported(dgrad_as_fwd(g)))) return EVE_OK;
+  const size_t wel = (size_t)g.Cout * g.K();
+  const size_t plane = align_up(wel * sizeof(uint16_t), 1024);
+  // bottom-up carve of the consumer: two weight planes + two operand planes
+  const size_t opnd = (size_t)(dgrad ? g.out_elems() : g.in_elems());
+  const size_t bottom = 2 * plane + 2 * align_up(opnd * sizeof(uint16_t), 1024);
+  if (bottom + *top_used + 2 * plane + 1024 > sc.bytes) return EVE_OK;
+  char* top = sc.base + ((sc.bytes - *top_used - 2 * plane) & ~(size_t)1023);
+  *top_used = (size_t)(sc.base + sc.bytes - top);
+  uint16_t* hi = (uint16_t*)top;
+  uint16_t* lo = (uint16_t*)(top + plane);
+  const int fmt = (!dgrad && npass == 3) ? TC_F16 : TC_BF16;
+  const float wscale = (!dgrad && npass == 3) ? 64.f : 1.f;
+  EVE_TRY(conv_tc_prep_weights(g, w, dgrad, hi, npass == 3 ? lo : nullptr, fmt, wscale, s));
+  g_prepared[g_nprepared++] = PreparedW{w, dgrad ? 1 : 0, npass, hi, lo};
+  return EVE_OK;
+}
+
+// act(IN(x)) feeding convolution `g`: either as fp32 `y` (then conv_* split it themselves) or,
+// when the convolution takes pre-split operands, straight into its 16-bit operand planes inside
+// the conv scratch (returns with *fused = true; the caller then passes x = nullptr to conv_*).
+int norm_act_into_conv(const ConvGeom& g, bool backward, const float* x, int N, int HW, int C,
+                              const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, int act, float* y, const ConvScratch& cs,
+                              bool* fused, cudaStream_t s) {
+  *fused = conv_x_fusable(g);
+  if (*fused) {
+    void *hi = nullptr, *lo = nullptr;
+    if (backward) conv_x_planes_bwd(g, cs, &hi, &lo);
+    else conv_x_planes_fwd(g, cs, &hi, &lo);
+    EVE_REQUIRE(lo, EVE_ERR_WORKSPACE, "norm_act_into_conv: conv scratch too small");
+    return in_apply_planes(x, N, HW, C, mean, rstd, gamma, beta, act, backward ? TC_BF16 : TC_F16,
+                           nullptr, hi, lo, s);
+  }
+  if (backward) return EVE_OK;       // the forward pass kept the fp32 activation in the tape
+  return in_apply(x, N, HW, C, mean, rstd, gamma, beta, nullptr, nullptr, nullptr, act, y, s);
 }
 
 }  // namespace eve

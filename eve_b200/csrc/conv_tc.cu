@@ -414,31 +414,34 @@ struct TcRowParams {
 
 constexpr int kRowBox = 130;           // 128 pixels + one halo pixel on each side
 
-template <int BN, int NPASS, int KC>
+template <int BN, int NPASS, int KC, int KS>
 struct RowCfg {
   static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
   static constexpr int kRowBytes = (kRowBox * KC * 2 + 1023) / 1024 * 1024;   // one plane of one row
   static constexpr int kSlotBytes = kRowBytes * kPlanes;
   static constexpr int kTapBytes = BN * KC * 2 < 1024 ? 1024 : BN * KC * 2;    // one tap, one plane
-  static constexpr int kWeightBytes = 9 * kPlanes * kTapBytes;
+  static constexpr int kTaps = KS * KS;                 // 3x3 or 1x1
+  static constexpr int kHalo = KS / 2;
+  static constexpr int kWeightBytes = kTaps * kPlanes * kTapBytes;
   static constexpr int kFixedBytes = kWeightBytes + 1024 + kBarrierBytes;
   static constexpr int kSlotsRaw = (227 * 1024 - kFixedBytes) / kSlotBytes;
   static constexpr int kSlots = kSlotsRaw > kMaxStages ? kMaxStages : kSlotsRaw;
   static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
 };
 
-template <int BN, int NPASS, int KC>
+template <int BN, int NPASS, int KC, int KS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    const TcRowParams p) {
-  using Cfg = RowCfg<BN, NPASS, KC>;
+  using Cfg = RowCfg<BN, NPASS, KC, KS>;
   constexpr int kPlanes = Cfg::kPlanes;
+  constexpr int kHalo = Cfg::kHalo;
   constexpr uint32_t kTmemCols = Cfg::kTmemCols;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
-  uint8_t* wsm = smem;                                        // [9 taps][planes][kTapBytes]
+  uint8_t* wsm = smem;                                        // [taps][planes][kTapBytes]
   uint8_t* ring = smem + Cfg::kWeightBytes;                   // [slots][planes][kRowBytes]
   const int slots = p.slots;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)slots * Cfg::kSlotBytes);
@@ -478,9 +481,9 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_expect_tx(wfull, 9u * kPlanes * (uint32_t)(BN * KC * 2));
+      mbar_expect_tx(wfull, (uint32_t)Cfg::kTaps * kPlanes * (uint32_t)(BN * KC * 2));
 #pragma unroll 1
-      for (int t = 0; t < 9; ++t) {
+      for (int t = 0; t < Cfg::kTaps; ++t) {
         tma_load_2d(wsm + (size_t)(t * kPlanes) * Cfg::kTapBytes, &tmB_hi, wfull, t * KC, 0);
         if (NPASS == 3)
           tma_load_2d(wsm + (size_t)(t * kPlanes + 1) * Cfg::kTapBytes, &tmB_lo, wfull, t * KC, 0);
@@ -491,7 +494,7 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         const int n = item / p.strips;
         const int h0 = (item - n * p.strips) * p.rows_per_strip;
         const int h1 = min(p.H, h0 + p.rows_per_strip);
-        for (int hr = h0 - 1; hr <= h1; ++hr, ++g) {
+        for (int hr = h0 - kHalo; hr < h1 + kHalo; ++hr, ++g) {
           const int s = g % slots;
           const uint32_t ph = (g / slots) & 1;
           mbar_wait(&empty[s], ph ^ 1);
@@ -528,21 +531,22 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * kTmemCols;
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const uint32_t e = g + (uint32_t)r;          // staged row h + r - 1
+        for (int r = 0; r < KS; ++r) {
+          const uint32_t e = g + (uint32_t)r;          // staged row h + r - halo
           const uint32_t s = e % (uint32_t)slots;
           mbar_wait(&full[s], (e / (uint32_t)slots) & 1);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t a_base = desc0 + (uint64_t)(ring16 + s * ((uint32_t)Cfg::kSlotBytes >> 4));
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
+            for (int q = 0; q < KS; ++q) {
 #pragma unroll
               for (int k = 0; k < kSteps; ++k) {
                 constexpr uint32_t two = 2;
-                const uint64_t da_hi = a_base + (uint64_t)(q * kPix16 + k * two);
+                // the staged box starts at pixel -1: tap q reads it shifted by q + 1 - halo pixels
+                const uint64_t da_hi = a_base + (uint64_t)((q + 1 - kHalo) * kPix16 + k * two);
                 const uint64_t da_lo = da_hi + kRow16;
-                const uint64_t db_hi = b_base + (uint64_t)((r * 3 + q) * kPlanes * kTap16 + k * two);
+                const uint64_t db_hi = b_base + (uint64_t)((r * KS + q) * kPlanes * kTap16 + k * two);
                 const uint64_t db_lo = db_hi + kTap16;
                 if (NPASS == 3) {
                   umma_bf16(tmem_d, da_lo, db_hi, idesc, (r | q | k) != 0);
@@ -553,21 +557,23 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 }
               }
             }
-            if (r == 2) {
-              umma_commit(&empty[g % (uint32_t)slots]);     // row h - 1 is not needed any more
+            if (r == KS - 1) {
+              umma_commit(&empty[g % (uint32_t)slots]);     // row h - halo is not needed any more
               umma_commit(&tmem_full[buf]);
             }
           }
           __syncwarp();
         }
       }
-      // end of the strip: the two trailing rows (h1 - 1, h1) are released as well
-      if (elect_one()) {
-        umma_commit(&empty[g % (uint32_t)slots]);
-        umma_commit(&empty[(g + 1) % (uint32_t)slots]);
+      // end of the strip: the trailing halo rows (h1 - 1, h1) are released as well
+      if (KS == 3) {
+        if (elect_one()) {
+          umma_commit(&empty[g % (uint32_t)slots]);
+          umma_commit(&empty[(g + 1) % (uint32_t)slots]);
+        }
+        __syncwarp();
+        g += 2;
       }
-      __syncwarp();
-      g += 2;
     }
   } else {
     // ===================== epilogue =====================
@@ -657,6 +663,7 @@ struct TcWgradParams {
 };
 
 constexpr int kWgRows = 64;   // pixel rows reserved per staged block
+constexpr int kWgradChainPixels = 4096;   // target length of one fp32 accumulation chain
 
 template <int NPASS>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -687,7 +694,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
   const int t_begin = sp * p.tiles_per_split;
   const int t_end = min(p.tiles_total, t_begin + p.tiles_per_split);
   const int iters = max(t_end - t_begin, 0);
-  const uint32_t tmem_cols = p.nblk < 32 ? 32 : p.nblk;
+  uint32_t tmem_cols = 32;                 // allocation granularity: powers of two >= 32
+  while (tmem_cols < (uint32_t)p.nblk) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     tmap_prefetch(&tmD_hi);
@@ -842,10 +850,10 @@ struct TcWgRowParams {
   int N, H;
   int strips, rows_per_strip, items;
   int slots;
-  float* part;              // [gridDim.x][Cout][9 * Cin]
+  float* part;              // [gridDim.x][Cout][KS * KS * Cin]
 };
 
-template <int NPASS, int CIN, int COUT>
+template <int NPASS, int CIN, int COUT, int KS>
 struct WgRowCfg {
   static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
   static constexpr int kDRowBytes = (kRowBox * COUT * 2 + 1023) / 1024 * 1024;   // one dy plane
@@ -853,25 +861,31 @@ struct WgRowCfg {
   static constexpr int kSlotBytes = kPlanes * (kDRowBytes + kXRowBytes);
   static constexpr int kSlotsRaw = (227 * 1024 - 1024 - kBarrierBytes) / kSlotBytes;
   static constexpr int kSlots = kSlotsRaw > kMaxStages ? kMaxStages : kSlotsRaw;
-  static constexpr uint32_t kTmemCols = CIN == 16 ? 64u : (CIN == 32 ? 128u : 256u);   // >= 3 * CIN
+  // two accumulator sets (three filter rows x CIN columns each), flushed alternately
+  static constexpr int kHalo = KS / 2;
+  static constexpr uint32_t kSetCols = KS * CIN;
+  static constexpr uint32_t kTmemCols = CIN == 16 ? 128u : (CIN == 32 ? 256u : 512u);   // >= 2 * 3 * CIN
 };
+constexpr int kWgFlushRows = kWgradChainPixels / kTileM;   // image rows per accumulation chain
 
-template <int NPASS, int CIN, int COUT>
+template <int NPASS, int CIN, int COUT, int KS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
                          const __grid_constant__ CUtensorMap tmD_lo,
                          const __grid_constant__ CUtensorMap tmX_hi,
                          const __grid_constant__ CUtensorMap tmX_lo, const TcWgRowParams p) {
-  using Cfg = WgRowCfg<NPASS, CIN, COUT>;
+  using Cfg = WgRowCfg<NPASS, CIN, COUT, KS>;
   constexpr int kPlanes = Cfg::kPlanes;
+  constexpr int kHalo = Cfg::kHalo;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   const int slots = p.slots;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)slots * Cfg::kSlotBytes);
   uint64_t* empty = full + slots;
-  uint64_t* tmem_full = empty + slots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + slots;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -887,7 +901,10 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -895,6 +912,14 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // rows this CTA owns (all roles walk the same items in the same order)
+  int total_rows = 0;
+  for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    const int n = item / p.strips;
+    const int h0 = (item - n * p.strips) * p.rows_per_strip;
+    total_rows += min(p.H, h0 + p.rows_per_strip) - h0;
+  }
 
   if (warp == 0) {
     if (elect_one()) {
@@ -905,7 +930,7 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
         const int n = item / p.strips;
         const int h0 = (item - n * p.strips) * p.rows_per_strip;
         const int h1 = min(p.H, h0 + p.rows_per_strip);
-        for (int hr = h0 - 1; hr <= h1; ++hr, ++g) {
+        for (int hr = h0 - kHalo; hr < h1 + kHalo; ++hr, ++g) {
           const int s = g % slots;
           mbar_wait(&empty[s], ((g / slots) & 1) ^ 1);
           uint8_t* dst = ring + (size_t)s * Cfg::kSlotBytes;
@@ -936,27 +961,39 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
     const uint64_t x_desc0 = mnmajor_desc(0u, (uint32_t)Cfg::kXRowBytes, CIN);
     const uint32_t ring16 = smem_u32(ring) >> 4;
     uint32_t g = 0;
-    uint32_t acc0 = 0;           // 0 until the first row has been accumulated
+    int row = 0;                 // rows accumulated so far by this CTA
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int n = item / p.strips;
       const int h0 = (item - n * p.strips) * p.rows_per_strip;
       const int h1 = min(p.H, h0 + p.rows_per_strip);
-      for (int h = h0; h < h1; ++h, ++g) {
-        uint32_t sl[3];
+      for (int h = h0; h < h1; ++h, ++g, ++row) {
+        // accumulation chains of kWgFlushRows rows alternate between the two accumulator sets
+        const uint32_t chain = (uint32_t)(row / kWgFlushRows);
+        const uint32_t set = chain & 1;
+        const bool chain_start = row % kWgFlushRows == 0;
+        const bool chain_end = row % kWgFlushRows == kWgFlushRows - 1 || row == total_rows - 1;
+        if (chain_start) {
+          mbar_wait(&tmem_empty[set], ((chain >> 1) & 1) ^ 1);   // the epilogue drained this set
+          tc_fence_after();
+        }
+        uint32_t sl[KS];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
+        for (int j = 0; j < KS; ++j) {
           const uint32_t e = g + (uint32_t)j;
           sl[j] = e % (uint32_t)slots;
           mbar_wait(&full[sl[j]], (e / (uint32_t)slots) & 1);
         }
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t xb = x_desc0 + (uint64_t)(ring16 + sl[1] * kSlot16 + kPlanes * kDRow16);
+          const uint32_t acc0 = chain_start ? 0u : 1u;
+          const uint64_t xb = x_desc0 + (uint64_t)(ring16 + sl[kHalo] * kSlot16 + kPlanes * kDRow16);
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            // dy row h - r + 1 is ring entry g + 2 - r (entry g holds row h - 1)
-            const uint64_t db = d_desc0 + (uint64_t)(ring16 + sl[2 - r] * kSlot16);
-            const uint32_t tmem_d = tmem_base + (uint32_t)(r * CIN);
+          for (int r = 0; r < KS; ++r) {
+            // dy row h - r + halo is ring entry g + 2 * halo - r (entry g holds row h - halo); the
+            // staged box starts at pixel -1, so a 1x1 filter reads it one pixel in
+            const uint64_t db = d_desc0 + (uint64_t)(ring16 + sl[2 * kHalo - r] * kSlot16 +
+                                                     (1 - kHalo) * ((uint32_t)(COUT * 2) >> 4));
+            const uint32_t tmem_d = tmem_base + set * Cfg::kSetCols + (uint32_t)(r * CIN);
 #pragma unroll
             for (int ks = 0; ks < kTileM / 16; ++ks) {
               const uint64_t dah = db + (uint64_t)(ks * kDStep16);
@@ -973,47 +1010,62 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
             }
           }
           umma_commit(&empty[sl[0]]);
+          if (chain_end) umma_commit(&tmem_full[set]);
         }
         __syncwarp();
-        acc0 = 1;
       }
-      if (elect_one()) {
-        umma_commit(&empty[g % (uint32_t)slots]);
-        umma_commit(&empty[(g + 1) % (uint32_t)slots]);
+      if (KS == 3) {
+        if (elect_one()) {
+          umma_commit(&empty[g % (uint32_t)slots]);
+          umma_commit(&empty[(g + 1) % (uint32_t)slots]);
+        }
+        __syncwarp();
+        g += 2;
       }
-      __syncwarp();
-      g += 2;
     }
-    if (elect_one()) umma_commit(tmem_full);
-    __syncwarp();
   } else {
+    // epilogue: drain each finished chain into this CTA's partial gradient (same thread, same
+    // address, fixed order: deterministic fp32 additions with round-to-nearest)
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
     const int b = m / COUT;                   // M block = horizontal shift
     const int co = m - b * COUT;
-    const bool valid = b < 3;
-    const int q = 2 - b;
-    constexpr size_t KK = (size_t)9 * CIN;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
+    const bool valid = b < KS;
+    const int q = KS - 1 - b;
+    constexpr size_t KK = (size_t)KS * KS * CIN;
+    const int chains = (total_rows + kWgFlushRows - 1) / kWgFlushRows;
+    for (int chain = 0; chain < chains; ++chain) {
+      const uint32_t set = (uint32_t)chain & 1;
+      mbar_wait(&tmem_full[set], ((uint32_t)chain >> 1) & 1);
+      tc_fence_after();
 #pragma unroll 1
-    for (int r = 0; r < 3; ++r) {
-      float* dst = p.part + ((size_t)blockIdx.x * COUT + co) * KK + (size_t)(r * 3 + q) * CIN;
+      for (int r = 0; r < KS; ++r) {
+        float* dst = p.part + ((size_t)blockIdx.x * COUT + co) * KK + (size_t)(r * KS + q) * CIN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < CIN; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(r * CIN + c0), v);
-        if (valid) {
-          float4* o4 = reinterpret_cast<float4*>(dst + c0);
-          constexpr int nq = (CIN < 32 ? CIN : 32) >> 2;
+        for (int c0 = 0; c0 < CIN; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + set * Cfg::kSetCols +
+                        (uint32_t)(r * CIN + c0), v);
+          if (valid) {
+            float4* o4 = reinterpret_cast<float4*>(dst + c0);
+            constexpr int nq = (CIN < 32 ? CIN : 32) >> 2;
 #pragma unroll
-          for (int j = 0; j < nq; ++j)
-            o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < nq; ++j) {
+              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (chain > 0) {
+                const float4 a = o4[j];
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              }
+              o4[j] = o;
+            }
+          }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[set]);
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -1216,7 +1268,9 @@ int launch_tc_bn(int BN, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const
   }
 }
 
-inline int chunk_for(int C) { return C % 64 == 0 ? 64 : (C == 32 ? 32 : (C == 16 ? 16 : 0)); }
+// channels per K chunk (= TMA box width and swizzle span): multiples of 64, then multiples of 32
+// (32 itself and the stem's 160-wide patch matrix), then 16
+inline int chunk_for(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : (C == 16 ? 16 : 0)); }
 inline int bn_for(int Cout) {
   return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout == 32 ? 32 : (Cout == 16 ? 16 : 0)));
 }
@@ -1273,7 +1327,10 @@ static int tc_launch(const TcParams& p0, const void* x_hi, const void* x_lo, int
   p.kchunks = p.Cin / p.kc;
   p.fmt = fmt;
   const int tiles_n = cdiv(p.N, p.bn);
-  const int BN = bn_for(p.Cout);
+  int BN = bn_for(p.Cout);
+  // Few pixel tiles (the per-time-step ConvRNN gate convolutions have 3): narrower output-channel
+  // tiles put more SMs on the layer; each CTA's serial chain of MMAs shrinks by the same factor.
+  while (BN > 16 && (long long)p.tiles_h * tiles_n * (p.Cout / BN) < kNumSMs / 2) BN >>= 1;
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   EVE_TRY(make_map_nhwc(&a_hi, x_hi, inN, inH, inW, p.Cin, p.kc, p.bw, p.bh, p.bn, p.stride, fmt));
   EVE_TRY(make_map_2d(&b_hi, w_hi, wrows, wcols, p.kc, BN, fmt));
@@ -1292,11 +1349,11 @@ static int tc_launch(const TcParams& p0, const void* x_hi, const void* x_lo, int
 
 // ---- halo-row kernels: planning and launch
 static bool row_geometry_ok(const ConvGeom& g) {
-  if (g.KH != 3 || g.KW != 3 || g.stride != 1 || g.pad != 1) return false;
+  if (g.KH != g.KW || (g.KH != 3 && g.KH != 1) || g.stride != 1 || g.pad != g.KH / 2) return false;
   if (g.W != kTileM || g.OW != kTileM || g.OH != g.H || g.N < 1) return false;
   if (g.Cin != 16 && g.Cin != 32 && g.Cin != 64) return false;
   if (g.Cout != 16 && g.Cout != 32 && g.Cout != 64) return false;
-  if (g.Cin == 64 && g.Cout == 64) return false;    // nine resident 64x64 taps leave < 4 row slots
+  if (g.KH == 3 && g.Cin == 64 && g.Cout == 64) return false;   // nine resident 64x64 taps leave < 4 row slots
   return true;
 }
 
@@ -1324,44 +1381,47 @@ bool conv_tc_row_supported(const ConvGeom& g) {
   return get_option(OPT_TC_ROW_KERNEL) != 0 && row_geometry_ok(g);
 }
 
-template <int BN, int NPASS, int KC>
+template <int BN, int NPASS, int KC, int KS>
 static int launch_row(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                       const CUtensorMap& b_lo, TcRowParams p, cudaStream_t s) {
-  using Cfg = RowCfg<BN, NPASS, KC>;
+  using Cfg = RowCfg<BN, NPASS, KC, KS>;
   if (Cfg::kSlots < 4) {
     EVE_REQUIRE(false, EVE_ERR_SHAPE, "conv_tc_row: %d -> %d channels do not fit", KC, BN);
     return EVE_ERR_SHAPE;
   }
   static bool configured = false;
   if (!configured) {
-    EVE_CUDA(cudaFuncSetAttribute(conv_tc_row_kernel<BN, NPASS, KC>,
+    EVE_CUDA(cudaFuncSetAttribute(conv_tc_row_kernel<BN, NPASS, KC, KS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   p.slots = Cfg::kSlots;
   const int smem_bytes = Cfg::kFixedBytes + Cfg::kSlots * Cfg::kSlotBytes;
   const int grid = p.items < kNumSMs ? p.items : kNumSMs;
-  conv_tc_row_kernel<BN, NPASS, KC><<<grid, kThreads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+  conv_tc_row_kernel<BN, NPASS, KC, KS><<<grid, kThreads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }
 
 template <int BN, int KC>
-static int launch_row_np(int npass, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+static int launch_row_np(int ks, int npass, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                          const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcRowParams& p,
                          cudaStream_t s) {
-  return npass == 3 ? launch_row<BN, 3, KC>(a_hi, a_lo, b_hi, b_lo, p, s)
-                    : launch_row<BN, 1, KC>(a_hi, a_lo, b_hi, b_lo, p, s);
+  if (ks == 3)
+    return npass == 3 ? launch_row<BN, 3, KC, 3>(a_hi, a_lo, b_hi, b_lo, p, s)
+                      : launch_row<BN, 1, KC, 3>(a_hi, a_lo, b_hi, b_lo, p, s);
+  return npass == 3 ? launch_row<BN, 3, KC, 1>(a_hi, a_lo, b_hi, b_lo, p, s)
+                    : launch_row<BN, 1, KC, 1>(a_hi, a_lo, b_hi, b_lo, p, s);
 }
 
 template <int BN>
-static int launch_row_kc(int kc, int npass, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+static int launch_row_kc(int kc, int ks, int npass, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                          const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcRowParams& p,
                          cudaStream_t s) {
   switch (kc) {
-    case 16: return launch_row_np<BN, 16>(npass, a_hi, a_lo, b_hi, b_lo, p, s);
-    case 32: return launch_row_np<BN, 32>(npass, a_hi, a_lo, b_hi, b_lo, p, s);
-    default: return launch_row_np<BN, 64>(npass, a_hi, a_lo, b_hi, b_lo, p, s);
+    case 16: return launch_row_np<BN, 16>(ks, npass, a_hi, a_lo, b_hi, b_lo, p, s);
+    case 32: return launch_row_np<BN, 32>(ks, npass, a_hi, a_lo, b_hi, b_lo, p, s);
+    default: return launch_row_np<BN, 64>(ks, npass, a_hi, a_lo, b_hi, b_lo, p, s);
   }
 }
 
@@ -1379,18 +1439,18 @@ static int conv_tc_row_run(const ConvGeom& g, const void* x_hi, const void* x_lo
   p.bias = bias; p.addend = addend; p.out = y;
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   EVE_TRY(make_map_nhwc(&a_hi, x_hi, g.N, g.H, g.W, g.Cin, g.Cin, kRowBox, 1, 1, 1, fmt));
-  EVE_TRY(make_map_2d(&b_hi, w_hi, g.Cout, 9 * g.Cin, g.Cin, g.Cout, fmt));
+  EVE_TRY(make_map_2d(&b_hi, w_hi, g.Cout, g.KH * g.KW * g.Cin, g.Cin, g.Cout, fmt));
   if (npass == 3) {
     EVE_TRY(make_map_nhwc(&a_lo, x_lo, g.N, g.H, g.W, g.Cin, g.Cin, kRowBox, 1, 1, 1, fmt));
-    EVE_TRY(make_map_2d(&b_lo, w_lo, g.Cout, 9 * g.Cin, g.Cin, g.Cout, fmt));
+    EVE_TRY(make_map_2d(&b_lo, w_lo, g.Cout, g.KH * g.KW * g.Cin, g.Cin, g.Cout, fmt));
   } else {
     a_lo = a_hi;
     b_lo = b_hi;
   }
   switch (g.Cout) {
-    case 16: return launch_row_kc<16>(g.Cin, npass, a_hi, a_lo, b_hi, b_lo, p, s);
-    case 32: return launch_row_kc<32>(g.Cin, npass, a_hi, a_lo, b_hi, b_lo, p, s);
-    default: return launch_row_kc<64>(g.Cin, npass, a_hi, a_lo, b_hi, b_lo, p, s);
+    case 16: return launch_row_kc<16>(g.Cin, g.KH, npass, a_hi, a_lo, b_hi, b_lo, p, s);
+    case 32: return launch_row_kc<32>(g.Cin, g.KH, npass, a_hi, a_lo, b_hi, b_lo, p, s);
+    default: return launch_row_kc<64>(g.Cin, g.KH, npass, a_hi, a_lo, b_hi, b_lo, p, s);
   }
 }
 
@@ -1508,7 +1568,7 @@ static int wgrad_stage_bytes(const TcWgradParams& p, int npass) {
 }
 
 static void wgrad_plan(const ConvGeom& g, TcWgradParams& p, int& mblocks, int& nblocks,
-                       int& splits, int npass) {
+                       int& splits, int npass, int waves = 0) {
   p.N = g.N; p.H = g.OH; p.W = g.OW; p.Cin = g.Cin; p.Cout = g.Cout;   // tiles walk the dy grid
   p.KH = g.KH; p.KW = g.KW; p.pad = g.pad;
   p.swap = g.stride == 2 ? 1 : 0;
@@ -1530,7 +1590,20 @@ static void wgrad_plan(const ConvGeom& g, TcWgradParams& p, int& mblocks, int& n
   nblocks = Cn / p.nblk;
   p.stages = (220 * 1024) / wgrad_stage_bytes(p, npass);
   if (p.stages > 6) p.stages = 6;
-  int want = cdiv(3 * kNumSMs, mblocks * nblocks);
+  // one CTA per SM (the ring takes the whole shared memory): the grid must not spill one CTA into
+  // an extra wave, so the split count is rounded DOWN to fill `waves` full waves
+  // Fewer splits are faster (less partial traffic), more splits keep each fp32 accumulation chain
+  // in TMEM short (the tensor core's accumulate rounds toward zero: the error of a chain grows
+  // linearly with its length).  Take the smallest number of full waves whose chains stay below
+  // kWgradChainPixels, at most "tc_wgrad_waves".
+  const bool sizing = waves > 0;
+  if (!sizing) waves = get_option(OPT_TC_WGRAD_WAVES);
+  int want = 1;
+  for (int wv = sizing ? waves : 1; wv <= waves; ++wv) {
+    want = (wv * kNumSMs) / (mblocks * nblocks);
+    if (want < 1) want = 1;
+    if ((long long)p.tiles_total * p.rows <= (long long)want * kWgradChainPixels) break;
+  }
   int max_splits = cdiv(p.tiles_total, 4);          // at least 4 pixel tiles per CTA
   splits = want < max_splits ? want : max_splits;
   if (splits < 1) splits = 1;
@@ -1545,30 +1618,33 @@ bool conv_tc_wgrad_row_supported(const ConvGeom& g) {
   return g.Cout == 16 || g.Cout == 32;
 }
 
-template <int NPASS, int CIN, int COUT>
+template <int NPASS, int CIN, int COUT, int KS>
 static int launch_wgrad_row(const CUtensorMap& d_hi, const CUtensorMap& d_lo, const CUtensorMap& x_hi,
                             const CUtensorMap& x_lo, TcWgRowParams p, int grid, cudaStream_t s) {
-  using Cfg = WgRowCfg<NPASS, CIN, COUT>;
+  using Cfg = WgRowCfg<NPASS, CIN, COUT, KS>;
   static_assert(Cfg::kSlots >= 4, "halo-row wgrad: ring too shallow");
   static bool configured = false;
   if (!configured) {
-    EVE_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_row_kernel<NPASS, CIN, COUT>,
+    EVE_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_row_kernel<NPASS, CIN, COUT, KS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   p.slots = Cfg::kSlots;
   const int smem_bytes = Cfg::kSlots * Cfg::kSlotBytes + 1024 + kBarrierBytes;
-  conv_tc_wgrad_row_kernel<NPASS, CIN, COUT><<<grid, kThreads, smem_bytes, s>>>(d_hi, d_lo, x_hi, x_lo, p);
+  conv_tc_wgrad_row_kernel<NPASS, CIN, COUT, KS><<<grid, kThreads, smem_bytes, s>>>(d_hi, d_lo, x_hi, x_lo, p);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }
 
 template <int CIN, int COUT>
-static int launch_wgrad_row_np(int npass, const CUtensorMap& d_hi, const CUtensorMap& d_lo,
+static int launch_wgrad_row_np(int ks, int npass, const CUtensorMap& d_hi, const CUtensorMap& d_lo,
                                const CUtensorMap& x_hi, const CUtensorMap& x_lo,
                                const TcWgRowParams& p, int grid, cudaStream_t s) {
-  return npass == 3 ? launch_wgrad_row<3, CIN, COUT>(d_hi, d_lo, x_hi, x_lo, p, grid, s)
-                    : launch_wgrad_row<1, CIN, COUT>(d_hi, d_lo, x_hi, x_lo, p, grid, s);
+  if (ks == 3)
+    return npass == 3 ? launch_wgrad_row<3, CIN, COUT, 3>(d_hi, d_lo, x_hi, x_lo, p, grid, s)
+                      : launch_wgrad_row<1, CIN, COUT, 3>(d_hi, d_lo, x_hi, x_lo, p, grid, s);
+  return npass == 3 ? launch_wgrad_row<3, CIN, COUT, 1>(d_hi, d_lo, x_hi, x_lo, p, grid, s)
+                    : launch_wgrad_row<1, CIN, COUT, 1>(d_hi, d_lo, x_hi, x_lo, p, grid, s);
 }
 
 static int conv_tc_wgrad_row_run(const ConvGeom& g, const void* d_hi, const void* d_lo,
@@ -1594,12 +1670,12 @@ static int conv_tc_wgrad_row_run(const ConvGeom& g, const void* d_hi, const void
   *splits_out = grid;
   const int key = g.Cin * 100 + g.Cout;
   switch (key) {
-    case 1616: return launch_wgrad_row_np<16, 16>(npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
-    case 1632: return launch_wgrad_row_np<16, 32>(npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
-    case 3216: return launch_wgrad_row_np<32, 16>(npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
-    case 3232: return launch_wgrad_row_np<32, 32>(npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
-    case 6416: return launch_wgrad_row_np<64, 16>(npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
-    case 6432: return launch_wgrad_row_np<64, 32>(npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
+    case 1616: return launch_wgrad_row_np<16, 16>(g.KH, npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
+    case 1632: return launch_wgrad_row_np<16, 32>(g.KH, npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
+    case 3216: return launch_wgrad_row_np<32, 16>(g.KH, npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
+    case 3232: return launch_wgrad_row_np<32, 32>(g.KH, npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
+    case 6416: return launch_wgrad_row_np<64, 16>(g.KH, npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
+    case 6432: return launch_wgrad_row_np<64, 32>(g.KH, npass, md_hi, md_lo, mx_hi, mx_lo, p, grid, s);
   }
   EVE_REQUIRE(false, EVE_ERR_SHAPE, "conv_tc_wgrad_row: %d -> %d channels", g.Cin, g.Cout);
   return EVE_ERR_SHAPE;
@@ -1609,7 +1685,7 @@ size_t conv_tc_wgrad_partial_floats(const ConvGeom& g) {
   if (!conv_tc_wgrad_supported(g)) return 0;
   TcWgradParams p;
   int mb, nb, sp;
-  wgrad_plan(g, p, mb, nb, sp, 3);
+  wgrad_plan(g, p, mb, nb, sp, 3, 8);   // sized for the largest "tc_wgrad_waves" setting
   // the halo-row kernel writes one partial per CTA
   if (row_geometry_ok(g) && (g.Cout == 16 || g.Cout == 32)) sp = std::max(sp, kNumSMs);
   return (size_t)sp * g.Cout * g.K();

@@ -212,9 +212,10 @@ extern "C" int eve_eyenet_cnn_fwd(const eve_eyenet_cnn_params* p, const float* x
     const int C = k.g1.Cout, HW = k.g1.OH * k.g1.OW;
     EVE_TRY(conv_fwd(k.g1, k.in, w[slot], nullptr, nullptr, k.a, cs, s));
     EVE_TRY(in_stats(k.a, N, HW, C, k.am, k.ar, s));
-    EVE_TRY(in_apply(k.a, N, HW, C, k.am, k.ar, nullptr, nullptr, nullptr, nullptr, nullptr,
-                     ACT_RELU, k.y, s));
-    EVE_TRY(conv_fwd(k.g2, k.y, w[slot + 1], nullptr, nullptr, k.b, cs, s));
+    bool fused = false;
+    EVE_TRY(norm_act_into_conv(k.g2, false, k.a, N, HW, C, k.am, k.ar, nullptr, nullptr, ACT_RELU,
+                               k.y, cs, &fused, s));
+    EVE_TRY(conv_fwd(k.g2, fused ? nullptr : k.y, w[slot + 1], nullptr, nullptr, k.b, cs, s));
     EVE_TRY(in_stats(k.b, N, HW, C, k.bm, k.br, s));
     if (k.down) {
       EVE_TRY(conv_fwd(k.gd, k.in, w[slot + 2], nullptr, nullptr, k.d, cs, s));
@@ -271,7 +272,11 @@ extern "C" int eve_eyenet_cnn_bwd(const eve_eyenet_cnn_params* p, const float* d
                         gskip, nullptr, nullptr, sc.inb, false, s));
     // conv2: weight gradient + data gradient from one split of db
     float* dy = sc.t2;
-    EVE_TRY(conv_bwd(k.g2, k.y, db, w[slot + 1], gr[slot + 1], nullptr, acc, nullptr, dy, sc.cs, s));
+    bool fused = false;
+    EVE_TRY(norm_act_into_conv(k.g2, true, k.a, N, HW, C, k.am, k.ar, nullptr, nullptr, ACT_RELU,
+                               nullptr, sc.cs, &fused, s));
+    EVE_TRY(conv_bwd(k.g2, fused ? nullptr : k.y, db, w[slot + 1], gr[slot + 1], nullptr, acc,
+                     nullptr, dy, sc.cs, s));
     // y = relu(IN(a))
     float* da = sc.t0;
     EVE_TRY(in_backward(dy, nullptr, k.a, N, HW, C, k.am, k.ar, nullptr, nullptr, ACT_RELU, nullptr, da,

@@ -5,6 +5,9 @@
 // (refine_net.py:46,50,59,215); biased variance, eps = 1e-5, never running statistics.
 // HBM-bound: every kernel reads NHWC rows with 128-byte coalesced warps
 // (a warp = 32 consecutive channels of one pixel) and reduces with shuffles / smem.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace eve {
@@ -70,12 +73,18 @@ __global__ void __launch_bounds__(256) in_stats_kernel(const float* __restrict__
   s1[threadIdx.x] = a;
   s2[threadIdx.x] = b;
   __syncthreads();
-  if (lane == 0 && q < C4) {
-    for (int l = 1; l < L; ++l) {
-      float4 t = s1[l * CQ + ql], u = s2[l * CQ + ql];
+  // pairwise tree over the L pixel lanes (L is a power of two): log2(L) steps, fixed order
+  for (int half = L >> 1; half >= 1; half >>= 1) {
+    if (lane < half) {
+      const float4 t = s1[(lane + half) * CQ + ql], u = s2[(lane + half) * CQ + ql];
       a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
       b.x += u.x; b.y += u.y; b.z += u.z; b.w += u.w;
+      s1[threadIdx.x] = a;
+      s2[threadIdx.x] = b;
     }
+    __syncthreads();
+  }
+  if (lane == 0 && q < C4) {
     const float inv = 1.f / (float)HW;
     float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
     float sv[4] = {sh.x, sh.y, sh.z, sh.w};
@@ -128,6 +137,51 @@ in_apply_kernel(const float* __restrict__ x, long long total4, int HW, int C,
   float4 out = make_float4(act_fwd(o[0], act), act_fwd(o[1], act), act_fwd(o[2], act),
                            act_fwd(o[3], act));
   reinterpret_cast<float4*>(y)[i] = out;
+}
+
+// in_apply_kernel without a residual, emitting the result as the 16-bit hi/lo operand planes of
+// the convolution that consumes it (x = hi + lo; fp16 planes forward, bf16 planes backward) and,
+// optionally, as fp32.  Saves the separate split pass (one read + one launch per convolution) and
+// lets the forward pass skip the fp32 activation altogether.
+template <int FMT>
+__global__ void __launch_bounds__(256)
+in_apply_planes_kernel(const float* __restrict__ x, long long total4, int HW, int C,
+                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                       float* __restrict__ y, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int C4 = C >> 2;
+  int c = (int)(i % C4) * 4;
+  long long pix = i / C4;
+  int n = (int)(pix / HW);
+  float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+  float4 m = *reinterpret_cast<const float4*>(mean + (size_t)n * C + c);
+  float4 r = *reinterpret_cast<const float4*>(rstd + (size_t)n * C + c);
+  float o[4] = {(v.x - m.x) * r.x, (v.y - m.y) * r.y, (v.z - m.z) * r.z, (v.w - m.w) * r.w};
+  if (gamma) {
+    float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    float4 b = *reinterpret_cast<const float4*>(beta + c);
+    o[0] = fmaf(o[0], g.x, b.x); o[1] = fmaf(o[1], g.y, b.y);
+    o[2] = fmaf(o[2], g.z, b.z); o[3] = fmaf(o[3], g.w, b.w);
+  }
+  uint16_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    o[j] = act_fwd(o[j], act);
+    if (FMT == TC_BF16) {
+      __nv_bfloat16 hb = __float2bfloat16_rn(o[j]);
+      h[j] = __bfloat16_as_ushort(hb);
+      l[j] = __bfloat16_as_ushort(__float2bfloat16_rn(o[j] - __bfloat162float(hb)));
+    } else {
+      __half hh = __float2half_rn(o[j]);
+      h[j] = __half_as_ushort(hh);
+      l[j] = __half_as_ushort(__float2half_rn(o[j] - __half2float(hh)));
+    }
+  }
+  if (y) reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+  reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
 }
 
 // Backward reductions per (n,c): sum g and sum g*xhat with g = dy*act'(y).
@@ -201,13 +255,19 @@ in_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ yma
     s2[threadIdx.x * 4 + j] = b[j];
   }
   __syncthreads();
-  if (lane == 0 && q < C4) {
-    for (int l = 1; l < L; ++l)
+  for (int half = L >> 1; half >= 1; half >>= 1) {
+    if (lane < half) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        a[j] += s1[(l * CQ + ql) * 4 + j];
-        b[j] += s2[(l * CQ + ql) * 4 + j];
+        a[j] += s1[((lane + half) * CQ + ql) * 4 + j];
+        b[j] += s2[((lane + half) * CQ + ql) * 4 + j];
+        s1[threadIdx.x * 4 + j] = a[j];
+        s2[threadIdx.x * 4 + j] = b[j];
       }
+    }
+    __syncthreads();
+  }
+  if (lane == 0 && q < C4) {
     reinterpret_cast<float4*>(sum_g + (size_t)n * C)[q] =
         make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
     reinterpret_cast<float4*>(sum_gx + (size_t)n * C)[q] =
@@ -283,14 +343,30 @@ in_affine_grad_kernel(const float* __restrict__ sum_g, const float* __restrict__
   }
 }
 
-// channel quads per block: up to 16 (64 channels), never more than the tensor has
-inline int quad_block(int C) { int q = C >> 2; return q >= 16 ? 16 : (q >= 8 ? 8 : (q >= 4 ? 4 : (q >= 2 ? 2 : 1))); }
+// channel quads per block: up to 16 (64 channels), never more than the tensor has.  Wide maps get
+// narrow channel groups (down to 2 quads = one 32-byte sector per pixel) so that the grid
+// (one block per image and channel group) covers the SMs several times over and each of the
+// 256 / CQ pixel lanes still walks >= 32 pixels (shorter walks
+// are dominated by the block prologue and the cross-lane tree).  The choice depends on (C, HW) only -- never on
+// N -- so a frame's statistics are bit-identical whatever batch it is processed in.
+// in_bwd_reduce (three streams, fp64 accumulators) measured fastest with the widest groups: up to
+// 16 quads, i.e. whole 256-byte pixel rows per warp
+inline int quad_block_wide(int C) {
+  const int q = C >> 2;
+  return q >= 16 ? 16 : (q >= 8 ? 8 : (q >= 4 ? 4 : (q >= 2 ? 2 : 1)));
+}
+inline int quad_block(int C, int HW) {
+  const int q = C >> 2;
+  int cq = q >= 2 ? 2 : 1;
+  while (cq < 16 && cq < q && 8192 / cq > HW) cq <<= 1;    // every lane walks >= 32 pixels
+  return cq;
+}
 
 }  // namespace
 
 int in_stats(const float* x, int N, int HW, int C, float* mean, float* rstd, cudaStream_t s) {
   EVE_REQUIRE(C % 4 == 0, EVE_ERR_SHAPE, "in_stats: C=%d must be a multiple of 4", C);
-  int CQ = quad_block(C);
+  int CQ = quad_block(C, HW);
   dim3 grid(N, cdiv(C >> 2, CQ));
   in_stats_kernel<<<grid, 256, 0, s>>>(x, HW, C, CQ, mean, rstd);
   EVE_LAUNCH_CHECK();
@@ -308,6 +384,23 @@ int in_apply(const float* x, int N, int HW, int C, const float* mean, const floa
   return EVE_OK;
 }
 
+int in_apply_planes(const float* x, int N, int HW, int C, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, int act, int fmt, float* y, void* hi,
+                    void* lo, cudaStream_t s) {
+  EVE_REQUIRE(C % 4 == 0, EVE_ERR_SHAPE, "in_apply_planes: C=%d must be a multiple of 4", C);
+  EVE_REQUIRE(hi && lo, EVE_ERR_NULL, "in_apply_planes: plane pointers are NULL");
+  long long total4 = (long long)N * HW * C / 4;
+  if (total4 == 0) return EVE_OK;
+  if (fmt == TC_BF16)
+    in_apply_planes_kernel<TC_BF16><<<cdiv(total4, 256), 256, 0, s>>>(
+        x, total4, HW, C, mean, rstd, gamma, beta, act, y, (uint16_t*)hi, (uint16_t*)lo);
+  else
+    in_apply_planes_kernel<TC_F16><<<cdiv(total4, 256), 256, 0, s>>>(
+        x, total4, HW, C, mean, rstd, gamma, beta, act, y, (uint16_t*)hi, (uint16_t*)lo);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
 size_t in_backward_scratch_floats(int N, int C) { return (size_t)2 * N * C; }
 
 int in_backward(const float* dy, const float* y_for_mask, const float* x, int N, int HW, int C,
@@ -315,7 +408,7 @@ int in_backward(const float* dy, const float* y_for_mask, const float* x, int N,
                 int act, const float* addend, float* dx, float* g_out, float* dgamma,
                 float* dbeta, float* scratch, bool accumulate_affine, cudaStream_t s) {
   EVE_REQUIRE(C % 4 == 0, EVE_ERR_SHAPE, "in_backward: C=%d must be a multiple of 4", C);
-  int CQ = quad_block(C);
+  int CQ = quad_block_wide(C);
   float* sum_g = scratch;
   float* sum_gx = scratch + (size_t)N * C;
   dim3 grid(N, cdiv(C >> 2, CQ));

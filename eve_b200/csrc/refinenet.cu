@@ -487,21 +487,22 @@ int block_fwd(const RBlock& k, int N, const float* const* w, const ConvScratch& 
               cudaStream_t s) {
   const float* const* bw = w + k.slot;
   const int HW = k.H * k.W;
+  bool fused = false;
   EVE_TRY(in_stats(k.x, N, HW, k.ic, k.m0, k.r0, s));
-  EVE_TRY(in_apply(k.x, N, HW, k.ic, k.m0, k.r0, bw[0], bw[1], nullptr, nullptr, nullptr, k.act,
-                   k.y1, s));
-  EVE_TRY(conv_fwd(k.g1, k.y1, bw[2], bw[3], nullptr, k.c1, cs, s));
+  EVE_TRY(norm_act_into_conv(k.g1, false, k.x, N, HW, k.ic, k.m0, k.r0, bw[0], bw[1], k.act, k.y1,
+                             cs, &fused, s));
+  EVE_TRY(conv_fwd(k.g1, fused ? nullptr : k.y1, bw[2], bw[3], nullptr, k.c1, cs, s));
   EVE_TRY(in_stats(k.c1, N, HW, k.oc, k.m1, k.r1, s));
-  EVE_TRY(in_apply(k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], nullptr, nullptr, nullptr, k.act,
-                   k.y2, s));
   const float* addend = k.x;
   if (k.skipconv) {
-    EVE_TRY(in_apply(k.x, N, HW, k.ic, k.m0, k.r0, bw[8], bw[9], nullptr, nullptr, nullptr, k.act,
-                     k.s, s));
-    EVE_TRY(conv_fwd(k.gs, k.s, bw[10], bw[11], nullptr, k.out, cs, s));
+    EVE_TRY(norm_act_into_conv(k.gs, false, k.x, N, HW, k.ic, k.m0, k.r0, bw[8], bw[9], k.act, k.s,
+                               cs, &fused, s));
+    EVE_TRY(conv_fwd(k.gs, fused ? nullptr : k.s, bw[10], bw[11], nullptr, k.out, cs, s));
     addend = k.out;
   }
-  EVE_TRY(conv_fwd(k.g2, k.y2, bw[6], bw[7], addend, k.out, cs, s));
+  EVE_TRY(norm_act_into_conv(k.g2, false, k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], k.act, k.y2,
+                             cs, &fused, s));
+  EVE_TRY(conv_fwd(k.g2, fused ? nullptr : k.y2, bw[6], bw[7], addend, k.out, cs, s));
   return EVE_OK;
 }
 
@@ -521,16 +522,28 @@ int block_bwd(const RBlock& k, int N, const float* const* w, float* const* gr, b
   const float* const* bw = w + k.slot;
   float* const* bg = gr + k.slot;
   const int HW = k.H * k.W;
-  EVE_TRY(conv_bwd(k.g2, k.y2, dout, bw[6], bg[6], bg[7], acc, nullptr, sc.t0, sc.cs, s));
+  bool fused = false;
+  // the convolutions' x operands (y2, y1, s) are re-derived from the saved pre-norm tensors as bf16
+  // planes when the forward pass did not keep them (conv_x_fusable)
+  EVE_TRY(norm_act_into_conv(k.g2, true, k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], k.act, nullptr,
+                             sc.cs, &fused, s));
+  EVE_TRY(conv_bwd(k.g2, fused ? nullptr : k.y2, dout, bw[6], bg[6], bg[7], acc, nullptr, sc.t0,
+                   sc.cs, s));
   // activation masks are recomputed from (x, mean, rstd, gamma, beta) -- the same arithmetic as
   // in_apply -- instead of being read back from the saved activations (4 bytes/element less in
   // both backward passes of every normalisation)
   EVE_TRY(in_backward(sc.t0, nullptr, k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], k.act, nullptr,
                       sc.t1, nullptr, bg[4], bg[5], sc.inb, acc, s));
-  EVE_TRY(conv_bwd(k.g1, k.y1, sc.t1, bw[2], bg[2], bg[3], acc, nullptr, sc.t0, sc.cs, s));
+  EVE_TRY(norm_act_into_conv(k.g1, true, k.x, N, HW, k.ic, k.m0, k.r0, bw[0], bw[1], k.act, nullptr,
+                             sc.cs, &fused, s));
+  EVE_TRY(conv_bwd(k.g1, fused ? nullptr : k.y1, sc.t1, bw[2], bg[2], bg[3], acc, nullptr, sc.t0,
+                   sc.cs, s));
   const float* addend = dout;
   if (k.skipconv) {
-    EVE_TRY(conv_bwd(k.gs, k.s, dout, bw[10], bg[10], bg[11], acc, nullptr, sc.t2, sc.cs, s));
+    EVE_TRY(norm_act_into_conv(k.gs, true, k.x, N, HW, k.ic, k.m0, k.r0, bw[8], bw[9], k.act,
+                               nullptr, sc.cs, &fused, s));
+    EVE_TRY(conv_bwd(k.gs, fused ? nullptr : k.s, dout, bw[10], bg[10], bg[11], acc, nullptr, sc.t2,
+                     sc.cs, s));
     EVE_TRY(in_backward(sc.t2, nullptr, k.x, N, HW, k.ic, k.m0, k.r0, bw[8], bw[9], k.act, nullptr,
                         sc.t1, nullptr, bg[8], bg[9], sc.inb, acc, s));
     addend = sc.t1;
@@ -689,9 +702,10 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
   LAUNCH1D(pad_cin_kernel, 16 * kInitC * 9, w[0], 16, p->in_channels, kInitC, w0p);
   EVE_TRY(conv_fwd(n.gi0, n.x0, w0p, w[1], nullptr, n.i0, cs, s));
   EVE_TRY(in_stats(n.i0, N, HW0, 16, n.im, n.ir, s));
-  EVE_TRY(in_apply(n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], nullptr, nullptr, nullptr, ACT_RELU,
-                   n.i1, s));
-  EVE_TRY(conv_fwd(n.gi3, n.i1, w[4], w[5], nullptr, n.i2, cs, s));
+  bool i1_fused = false;
+  EVE_TRY(norm_act_into_conv(n.gi3, false, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU, n.i1,
+                             cs, &i1_fused, s));
+  EVE_TRY(conv_fwd(n.gi3, i1_fused ? nullptr : n.i1, w[4], w[5], nullptr, n.i2, cs, s));
   // ---- encoder
   for (int l = 0; l < kLevels; ++l) {
     for (auto& k : n.enc[l]) EVE_TRY(block_fwd(k, N, w, cs, s));
@@ -738,6 +752,13 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
       for (int i = 0; i < nc; ++i)
         EVE_CUDA(cudaMemcpyAsync(n.cell[i].h0, h0n + (size_t)i * B * E, (size_t)B * E * sizeof(float),
                                  cudaMemcpyDeviceToDevice, s));
+      // the gate weights do not change over the T steps: lay them out for the tensor cores once
+      size_t top_used = 0;
+      for (int i = 0; i < nc; ++i) {
+        const float* const* cw = w + n.slot_rnn + wpc * i;
+        EVE_TRY(conv_prepare_weights(g1, cw[0], false, cs, &top_used, s));
+        if (gru) EVE_TRY(conv_prepare_weights(g2, cw[2], false, cs, &top_used, s));
+      }
       for (int t = 0; t < T; ++t) {
         const float* xt = n.bx + (size_t)t * B * E;
         for (int i = 0; i < nc; ++i) {
@@ -765,6 +786,7 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
         EVE_CUDA(cudaMemcpyAsync(n.by + (size_t)t * B * E, xt, (size_t)B * E * sizeof(float),
                                  cudaMemcpyDeviceToDevice, s));
       }
+      conv_prepared_clear();
       bout = n.by;
       for (int i = 0; i < nc; ++i)
         EVE_CUDA(cudaMemcpyAsync(h0n + (size_t)i * B * E, n.cell[i].h + (size_t)(T - 1) * B * E,
@@ -900,6 +922,12 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
     float* dxh = ex.cb[3];
     float* dxa = ex.cb[4];
     float* dxb = ex.cb[5];
+    size_t top_used = 0;
+    for (int i = 0; i < nc; ++i) {
+      const float* const* cw = w + n.slot_rnn + wpc * i;
+      EVE_TRY(conv_prepare_weights(g1, cw[0], true, sc.cs, &top_used, s));
+      if (gru) EVE_TRY(conv_prepare_weights(g2, cw[2], true, sc.cs, &top_used, s));
+    }
     for (int t = T - 1; t >= 0; --t) {
       const float* dcur = ex.dby + (size_t)t * B * E;
       for (int i = nc - 1; i >= 0; --i) {
@@ -927,6 +955,7 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
         dcur = dxo;
       }
     }
+    conv_prepared_clear();
     dbx = ex.dbx;
     // weight gradients: one batched wgrad over all T*B bottleneck images per conv
     ConvGeom G1 = make_conv(N, kLevelH[4], kLevelW[4], 2 * nf, g1.Cout, 3, 1, 1);
@@ -959,7 +988,11 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
     }
   }
   // ---- initial
-  EVE_TRY(conv_bwd(n.gi3, n.i1, cur, w[4], gr[4], gr[5], acc, nullptr, sc.t0, sc.cs, s));
+  bool i1_fused = false;
+  EVE_TRY(norm_act_into_conv(n.gi3, true, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU, nullptr,
+                             sc.cs, &i1_fused, s));
+  EVE_TRY(conv_bwd(n.gi3, i1_fused ? nullptr : n.i1, cur, w[4], gr[4], gr[5], acc, nullptr, sc.t0,
+                   sc.cs, s));
   EVE_TRY(in_backward(sc.t0, nullptr, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU, nullptr,
                       sc.t1, nullptr, gr[2], gr[3], sc.inb, acc, s));
   {

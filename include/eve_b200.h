@@ -73,6 +73,10 @@ int eve_get_conv_mode(void);
  *                                shifted shared-memory descriptors) for 3x3 stride-1, W == 128
  *   "tc_row_strips"       0..128 row strips per image (0 = automatic)
  *   "tc_row_wgrad"        0/1    halo-row weight-gradient kernel
+ *   "tc_wgrad_waves"      1..8   full waves of CTAs the split-K weight gradient fills
+ *   "fused_planes"        0/1    normalise+activate kernels write the consuming convolution's
+ *                                16-bit operand planes directly (no fp32 activation, no split pass);
+ *                                must not change between a forward and its backward
  * Unknown names / out-of-range values return EVE_ERR_CONFIG. */
 int eve_set_option(const char* name, int value);
 int eve_get_option(const char* name, int* value);

@@ -129,3 +129,21 @@ def test_integration_shim_routes_reference_imports(tmp_path, monkeypatch):
     assert RefPathEVE is M.EVE and RefPathEyeNet is M.EyeNet
     for k in [k for k in sys.modules if k == 'models' or k.startswith('models.')]:
         monkeypatch.delitem(sys.modules, k)
+
+
+def test_tuning_options_round_trip_without_a_gpu():
+    """eve_set_option / eve_get_option are plain host state: defaults, range checks and unknown
+    names behave as include/eve_b200.h documents (no CUDA call involved)."""
+    from eve_b200 import lib as L
+    lib = L.load()
+    for name, lo, hi in [('tc_stage_cap', 2, 24), ('tc_row_kernel', 0, 1), ('tc_row_strips', 0, 128),
+                         ('tc_row_wgrad', 0, 1), ('tc_wgrad_waves', 1, 8), ('fused_planes', 0, 1)]:
+        prev = L.get_option(name)
+        assert lo <= prev <= hi
+        L.set_option(name, lo)
+        assert L.get_option(name) == lo
+        assert lib.eve_set_option(name.encode(), hi + 1) != 0
+        assert L.get_option(name) == lo
+        L.set_option(name, prev)
+    assert lib.eve_set_option(b'bogus', 0) != 0
+    assert 'unknown option' in L.last_error()

@@ -1,0 +1,136 @@
+"""The tensor-core path's tuning switches (include/eve_b200.h: eve_set_option) select between
+kernels that must compute the same thing: every variant is checked against fp64 arithmetic at
+the op level and against the default configuration on a whole EVE training step."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from eve_b200 import lib as L            # noqa: E402
+from tests import gpu_util as G          # noqa: E402
+
+OPTIONS = ('tc_stage_cap', 'tc_row_kernel', 'tc_row_strips', 'tc_row_wgrad', 'tc_wgrad_waves',
+           'fused_planes')
+
+
+@pytest.fixture()
+def options():
+    L.load()
+    saved = {k: L.get_option(k) for k in OPTIONS}
+    yield L.set_option
+    for k, v in saved.items():
+        L.set_option(k, v)
+
+
+# halo-row kernels: W == 128, 3x3, stride 1 (RefineNet level 0)
+ROW_CASES = [(16, 16, 3), (16, 32, 3), (32, 32, 3), (64, 16, 3), (32, 16, 3), (16, 64, 3), (64, 32, 3),
+             (16, 32, 1), (64, 16, 1), (32, 16, 1), (16, 64, 1), (64, 64, 1)]
+
+
+@pytest.mark.parametrize('cin,cout,k', ROW_CASES)
+@pytest.mark.parametrize('strips', [0, 1, 3, 72])
+def test_halo_row_kernels_match_fp64(cin, cout, k, strips, options):
+    """strips = 1: one work item per image (rows h0-1 and H are pure TMA zero fill); 72: one output
+    row per item (every staged row is a strip boundary); 3: the bench decomposition."""
+    n, h, w = 3, 72, 128
+    g = torch.Generator().manual_seed(1000 * cin + cout + k)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    xd = x.double().requires_grad_(True)
+    wd = wt.double().requires_grad_(True)
+    y = F.conv2d(xd, wd, b.double(), padding=k // 2)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy.double())
+    L.load().eve_set_conv_mode(1)
+    options('tc_row_kernel', 1)
+    options('tc_row_wgrad', 1)
+    options('tc_row_strips', strips)
+    got = G.conv_fwd(x.cuda(), wt.cuda(), b.cuda(), 1, k // 2)
+    dx = G.conv_dgrad(dy.cuda(), wt.cuda(), (h, w), 1, k // 2)
+    dw, db = G.conv_wgrad(x.cuda(), dy.cuda(), k, 1, k // 2)
+    torch.cuda.synchronize()
+    assert G.rel(got, y) < 3e-5
+    assert G.rel(dx, xd.grad) < 3e-5
+    assert G.rel(dw, wd.grad) < 3e-5
+    assert G.rel(db, dy.double().sum(dim=(0, 2, 3))) < 2e-5
+
+
+@pytest.mark.parametrize('waves', [1, 2, 4])
+def test_split_k_wave_count_does_not_change_weight_gradients(waves, options):
+    n, cin, h, w, cout = 6, 64, 32, 32, 64
+    g = torch.Generator().manual_seed(waves)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wd = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).double().requires_grad_(True)
+    y = F.conv2d(x.double(), wd, None, padding=1)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy.double())
+    L.load().eve_set_conv_mode(1)
+    options('tc_wgrad_waves', waves)
+    dw, _ = G.conv_wgrad(x.cuda(), dy.cuda(), 3, 1, 1)
+    torch.cuda.synchronize()
+    assert G.rel(dw, wd.grad) < 3e-5
+
+
+def _eve_step(cfg, seed=5, B=2, T=3):
+    from eve_b200 import synth
+    from eve_b200.models import EVE
+    cfg.override('refine_net_enabled', True)
+    cfg.override('load_screen_content', True)
+    sd = synth.make_state_dict(synth.eye_net_param_shapes(cfg), seed, 'eye_net.')
+    sd.update(synth.make_state_dict(synth.refine_net_param_shapes(cfg), seed + 1000, 'refine_net.'))
+    model = EVE(output_predictions=True)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    inputs = {k: v.cuda() for k, v in synth.make_clip_batch(B, T, seed=seed).items()}
+    np.random.seed(seed)
+    out = model({'x': inputs}, current_epoch=0.0)
+    out['full_loss'].backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    keep = {k: v.detach().clone() for k, v in out.items()
+            if torch.is_tensor(v) and v.is_floating_point()}
+    assert 'full_loss' in keep and 'PoG_px_final' in keep
+    return keep, grads
+
+
+VARIANTS = [
+    dict(fused_planes=0),
+    dict(tc_row_kernel=0, tc_row_wgrad=0),
+    dict(tc_row_strips=1, tc_wgrad_waves=1, tc_stage_cap=3),
+    dict(fused_planes=0, tc_row_kernel=0, tc_row_wgrad=0, tc_wgrad_waves=2),
+]
+
+
+@pytest.mark.parametrize('variant', VARIANTS, ids=lambda v: ','.join('%s=%d' % kv for kv in v.items()))
+def test_option_variants_agree_on_a_full_training_step(variant, cfg, options):
+    """Same seeded EVE step (EyeNet x2 + GazeRefineNet, forward + backward) under the default
+    switches and under a variant: the kernels differ only in operand staging and summation order,
+    so outputs agree to fp32 summation noise (forward 1e-4 on the refined PoG at random
+    weights, L2 2e-3 on gradients: the bars test_gpu_models.py documents for one configuration
+    against the oracle, tightened)."""
+    L.load().eve_set_conv_mode(1)
+    base_out, base_grads = _eve_step(cfg)
+    for k, v in variant.items():
+        options(k, v)
+    out, grads = _eve_step(cfg)
+    for k in base_out:
+        a, b = out[k].double(), base_out[k].double()
+        assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-7, k
+    assert grads.keys() == base_grads.keys()
+    for k in grads:
+        a, b = grads[k].double(), base_grads[k].double()
+        den = float(b.norm())
+        if den == 0.0:
+            assert float(a.norm()) == 0.0, k
+        else:
+            assert float((a - b).norm()) <= 2e-3 * den + 1e-9, k
+
+
+def test_unknown_option_is_rejected():
+    lib = L.load()
+    assert lib.eve_set_option(b'no_such_switch', 1) != 0
+    assert 'unknown option' in L.last_error()
+    assert lib.eve_set_option(b'tc_stage_cap', 1000) != 0

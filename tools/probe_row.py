@@ -121,3 +121,26 @@ for cin, cout in CASES[:4]:
             except Exception as e:  # noqa: BLE001
                 print('  %2d->%2d %-12s ERROR %s' % (cin, cout, name, e), flush=True)
     del x, y, ws
+
+print('== generic split-K wgrad vs number of CTA waves, ms (kernel + reduce)')
+for (n, cin, h, w, cout, k, st) in [(480, 64, 32, 32, 64, 3, 1), (480, 128, 16, 16, 128, 3, 1),
+                                    (480, 256, 8, 8, 256, 3, 1), (480, 512, 4, 4, 512, 3, 1),
+                                    (240, 64, 36, 64, 64, 3, 1), (240, 128, 18, 32, 128, 3, 1),
+                                    (480, 64, 32, 32, 128, 3, 2), (240, 16, 72, 128, 32, 1, 1)]:
+    x = torch.randn(n, h, w, cin, device='cuda')
+    oh, ow = h // st, w // st
+    dy = torch.randn(n, oh, ow, cout, device='cuda')
+    dw = torch.empty(cout, cin, k, k, device='cuda')
+    p = L.ConvParams(n, h, w, cin, cout, k, st, k // 2)
+    ws = torch.empty(lib.eve_conv2d_workspace_bytes(C.byref(p)), dtype=torch.uint8, device='cuda')
+
+    def runw():
+        L.check(lib.eve_conv2d_wgrad(C.byref(p), L.ptr(x), L.ptr(dy), L.ptr(dw), None, L.ptr(ws),
+                                     ws.numel(), L.stream_ptr()), 'wgrad')
+    line = '  n%d %d->%d %dx%d k%d s%d :' % (n, cin, cout, h, w, k, st)
+    for waves in (1, 2, 3, 4, 6):
+        L.set_option('tc_wgrad_waves', waves)
+        line += '  w%d %.3f' % (waves, prof_ms(2, runw))
+    print(line, flush=True)
+    del x, dy, ws
+L.set_option('tc_wgrad_waves', 3)
