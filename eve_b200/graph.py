@@ -7,7 +7,9 @@ costs one ``cudaGraphLaunch``.  Everything data-dependent stays outside the capt
     caller's pinned tensors);
   * the per-clip kappa augmentation draws (np.random, eve.py:468-469) are made on the host in
     the reference's order and copied into static [B, 2] buffers;
-  * the Adam step count lives on the device (eve_adam_params.step_dev).
+  * the Adam step count lives on the device (eve_adam_params.step_dev);
+  * ``prefetch()`` stages the NEXT batch host->device on a second stream while the current replay
+    computes; the step then starts with a device-to-device copy into the static buffers.
 The math is the eager path's, kernel for kernel -- tests/test_gpu_graph.py holds the two
 bit-identical.
 """
@@ -33,6 +35,11 @@ class GraphedTrainStep(object):
         self.batch = B
         self.loss = None
         self.graph = None
+        # input prefetch: staging buffers filled on a copy stream (see prefetch())
+        self.stage_in = None
+        self.copy_stream = None
+        self.stage_ready = None
+        self.stage_free = None
         self._load(example_inputs)
         # warm-up on a side stream (allocator pools, lazy kernel attributes, NCCL channels)
         side = torch.cuda.Stream(device=dev)
@@ -63,10 +70,36 @@ class GraphedTrainStep(object):
         for s in ('left', 'right'):
             self.model.kappa_buffers[s].copy_(self.kappa_host[s], non_blocking=True)
 
-    def __call__(self, inputs):
+    def prefetch(self, inputs):
+        """Start copying the NEXT step's inputs (pinned host tensors) into device staging buffers
+        on a second stream; it overlaps whatever the main stream is computing.  The following
+        ``__call__(None)`` consumes the staged batch."""
+        dev = self.trainer.device
+        if self.stage_in is None:
+            self.stage_in = {k: torch.empty_like(v) for k, v in self.static_in.items()}
+            self.copy_stream = torch.cuda.Stream(device=dev)
+            self.stage_ready = torch.cuda.Event()
+            self.stage_free = torch.cuda.Event()
+            self.stage_free.record(torch.cuda.current_stream(dev))
+        self.copy_stream.wait_event(self.stage_free)       # the previous staged batch was consumed
+        with torch.cuda.stream(self.copy_stream):
+            for k, v in inputs.items():
+                self.stage_in[k].copy_(v, non_blocking=True)
+            self.stage_ready.record(self.copy_stream)
+
+    def __call__(self, inputs=None):
         """Run one optimisation step on ``inputs`` (host or device tensors with the example's
-        shapes); returns the loss as a 0-dim device tensor (valid until the next call)."""
-        self._load(inputs)
+        shapes; None = the batch staged by ``prefetch()``); returns the loss as a 0-dim device
+        tensor (valid until the next call)."""
+        if inputs is None:
+            assert self.stage_in is not None, 'GraphedTrainStep: nothing was prefetched'
+            main = torch.cuda.current_stream(self.trainer.device)
+            main.wait_event(self.stage_ready)
+            inputs = self.stage_in
+            self._load(inputs)
+            self.stage_free.record(main)
+        else:
+            self._load(inputs)
         if self.graph is None:          # capture=False: same data path, eager launches
             self.loss = self._eager()
             return self.loss

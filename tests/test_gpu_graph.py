@@ -39,3 +39,30 @@ def test_graph_replay_equals_eager_steps(cfg):
     assert all(np.isfinite(la))
     ga.close()
     gb.close()
+
+
+def test_prefetched_inputs_give_the_same_steps(cfg):
+    """GraphedTrainStep.prefetch() (next batch staged H2D on a second stream, consumed by
+    __call__(None)) is only a different route for the same bytes: losses and parameters equal the
+    direct path's bit for bit."""
+    from eve_b200 import synth
+    cfg.override('refine_net_enabled', True)
+    cfg.override('load_screen_content', True)
+    B, T = 2, 3
+    xs = [{k: v.pin_memory() for k, v in synth.make_clip_batch(B, T, seed=60 + i).items()}
+          for i in range(4)]
+    ma, ta, ga = _make(cfg, 9, True, xs[0])
+    la = [float(ga(x)) for x in xs[1:]]
+    pa = ta.flat.clone()
+    mb, tb, gb = _make(cfg, 9, True, xs[0])
+    lb = []
+    gb.prefetch(xs[1])
+    for i in (1, 2, 3):
+        loss = gb(None)
+        if i < 3:
+            gb.prefetch(xs[i + 1])
+        lb.append(float(loss))
+    assert la == lb, (la, lb)
+    assert torch.equal(pa, tb.flat)
+    ga.close()
+    gb.close()

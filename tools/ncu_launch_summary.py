@@ -7,9 +7,10 @@ rows = list(csv.reader(open(path, errors='replace')))
 hi = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
 hdr = rows[hi]
 ik, ig, iv, iu = hdr.index('Kernel Name'), hdr.index('Grid Size'), hdr.index('Metric Value'), hdr.index('Metric Unit')
+imn = hdr.index('Metric Name')
 agg = collections.OrderedDict()
 for r in rows[hi + 1:]:
-    if len(r) <= iv:
+    if len(r) <= iv or r[imn] != 'gpu__time_duration.sum':
         continue
     name = re.sub(r'\(anonymous namespace\)::|<unnamed>::', '', r[ik])
     name = name.split('(')[0][:90]
