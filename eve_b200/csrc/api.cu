@@ -143,6 +143,7 @@ static Opt g_opts[OPT_COUNT] = {
     {"tc_row_wgrad", 1, 0, 1, "EVE_B200_TC_ROW_WGRAD", false},
     {"tc_wgrad_waves", 3, 1, 8, "EVE_B200_TC_WGRAD_WAVES", false},
     {"fused_planes", 1, 0, 1, "EVE_B200_FUSED_PLANES", false},
+    {"fused_norm", 1, 0, 1, "EVE_B200_FUSED_NORM", false},
 };
 int get_option(int key) {
   if (key < 0 || key >= OPT_COUNT) return 0;
@@ -267,6 +268,44 @@ extern "C" int eve_instnorm_act_bwd(const float* dy, const float* y, const float
   }
   return in_backward(dy, y, x, n, hw, c, mean, rstd, gamma, nullptr, act, nullptr, dx, nullptr, dgamma,
                      dbeta, (float*)workspace, false, s);
+}
+
+extern "C" size_t eve_instnorm_fused_workspace_bytes(int n, int hw, int c) {
+  return (in_bwd_fused_scratch_floats(n, hw, c) + 64) * sizeof(float);
+}
+
+extern "C" int eve_instnorm_fused_fwd(const float* x, const float* x2, int x2_mode, int n, int hw,
+                                      int c, const float* gamma, const float* beta,
+                                      const float* gamma_b, const float* beta_b, int act, int fmt,
+                                      float* mean, float* rstd, float* mean2, float* rstd2,
+                                      float* y, void* hi_a, void* lo_a, void* hi_b, void* lo_b,
+                                      eve_stream_t stream) {
+  EVE_REQUIRE(n >= 0 && hw > 0 && c > 0 && c % 4 == 0 && act >= 0 && act <= 2 && x2_mode >= 0 &&
+                  x2_mode <= 2 && (fmt == TC_F16 || fmt == TC_BF16),
+              EVE_ERR_SHAPE, "instnorm_fused_fwd: bad arguments n=%d hw=%d c=%d act=%d", n, hw, c, act);
+  EVE_REQUIRE(in_fused_supported(hw, c, x2_mode == 2 ? 2 : 1), EVE_ERR_SHAPE,
+              "instnorm_fused_fwd: hw=%d c=%d does not fit the cluster kernel", hw, c);
+  return in_fwd_fused(x, n, hw, c, x2, x2_mode, gamma, beta, gamma_b, beta_b, act, fmt, mean, rstd,
+                      mean2, rstd2, y, hi_a, lo_a, hi_b, lo_b, as_stream(stream));
+}
+
+extern "C" int eve_instnorm_fused_bwd(const float* dy, const float* dy2, const float* ymask,
+                                      const float* x, int n, int hw, int c, const float* mean,
+                                      const float* rstd, const float* gamma, const float* beta,
+                                      const float* gamma2, const float* beta2, int act,
+                                      const float* addend, float* dx, void* dx_hi, void* dx_lo,
+                                      float* g_out, float* dgamma, float* dbeta, float* dgamma2,
+                                      float* dbeta2, float* dbias, void* workspace,
+                                      size_t workspace_bytes, eve_stream_t stream) {
+  EVE_REQUIRE(n >= 0 && hw > 0 && c > 0 && c % 4 == 0 && act >= 0 && act <= 2, EVE_ERR_SHAPE,
+              "instnorm_fused_bwd: bad arguments n=%d hw=%d c=%d act=%d", n, hw, c, act);
+  EVE_REQUIRE(in_fused_supported(hw, c, 2), EVE_ERR_SHAPE,
+              "instnorm_fused_bwd: hw=%d c=%d does not fit the cluster kernel", hw, c);
+  EVE_REQUIRE(workspace && workspace_bytes >= eve_instnorm_fused_workspace_bytes(n, hw, c),
+              EVE_ERR_WORKSPACE, "instnorm_fused_bwd: workspace too small");
+  return in_bwd_fused(dy, dy2, ymask, x, n, hw, c, mean, rstd, gamma, beta, gamma2, beta2, act,
+                      addend, dx, dx_hi, dx_lo, g_out, dgamma, dbeta, dgamma2, dbeta2, dbias, nullptr,
+                      false, (float*)workspace, as_stream(stream));
 }
 
 extern "C" int eve_adaptive_maxpool_fwd(const float* x, int n, int h, int w, int c, int oh, int ow,

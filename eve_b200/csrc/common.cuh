@@ -159,6 +159,7 @@ enum OptKey {
   OPT_TC_ROW_WGRAD,          // halo-row weight-gradient kernel (W == 128)
   OPT_TC_WGRAD_WAVES,        // full waves of CTAs the split-K weight gradient is sized for
   OPT_FUSED_PLANES,          // InstanceNorm kernels emit the consuming convolution's operand planes
+  OPT_FUSED_NORM,            // one-pass cluster InstanceNorm kernels + plane-to-plane block pipelines
   OPT_COUNT
 };
 int get_option(int key);
@@ -189,6 +190,15 @@ int conv_dgrad(const ConvGeom& g, const float* dy, const float* w_oihw, const fl
                float* dx, const ConvScratch& sc, cudaStream_t s);
 int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw_oihw, float* dbias,
                bool accumulate, const ConvScratch& sc, cudaStream_t s);
+// Plane-to-plane entry points (split tensor-core path only; conv_x_fusable(g) must hold): the
+// producers of x / dy have already written the 16-bit hi/lo NHWC planes (x: fp16 for the forward
+// pass, bf16 for the backward pass; dy: bf16).  Bias gradients come from the producer of dy.
+int conv_fwd_planes(const ConvGeom& g, const void* x_hi, const void* x_lo, const float* w_oihw,
+                    const float* bias, const float* addend, float* y, const ConvScratch& sc,
+                    cudaStream_t s);
+int conv_bwd_planes(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* d_hi,
+                    const void* d_lo, const float* w_oihw, float* dw, bool accumulate,
+                    const float* addend, float* dx, const ConvScratch& sc, cudaStream_t s);
 // Weights of a convolution that is applied many times in a row (ConvRNN cells): prepared once into
 // the top of the scratch slice; conv_fwd / stride-1 conv_dgrad calls with the same weight pointer
 // then skip their own preparation until conv_prepared_clear().  *top_used accumulates the bytes
@@ -225,6 +235,36 @@ int in_apply_planes(const float* x, int N, int HW, int C, const float* mean, con
 int norm_act_into_conv(const ConvGeom& g, bool backward, const float* x, int N, int HW, int C,
                        const float* mean, const float* rstd, const float* gamma, const float* beta,
                        int act, float* y, const ConvScratch& cs, bool* fused, cudaStream_t s);
+// in_apply_planes with two affine sets from one read of x (RefineNet blocks with a skip
+// convolution normalise the same tensor twice, refine_net.py:45-62); set B optional
+int in_apply_planes2(const float* x, int N, int HW, int C, const float* mean, const float* rstd,
+                     const float* gamma, const float* beta, const float* gammaB,
+                     const float* betaB, int act, int fmt, void* hiA, void* loA, void* hiB,
+                     void* loB, cudaStream_t s);
+// ---- one-pass cluster kernels (in_fused.cu)
+bool in_fused_supported(int HW, int C, int tensors);
+// statistics + normalisation from ONE read of x: mean/rstd out, y = act(IN(x)*gamma+beta (+x2)) as
+// fp32 (y, optional) and as operand planes A (optional); planes B = act(IN(x)*gammaB+betaB)
+// (optional).  x2_mode: 0 none, 1 x2 is a residual added before the activation, 2 x2 is itself
+// instance-normalised (non-affine; mean2/rstd2 out) and added.
+int in_fwd_fused(const float* x, int N, int HW, int C, const float* x2, int x2_mode,
+                 const float* gamma, const float* beta, const float* gammaB, const float* betaB,
+                 int act, int fmt, float* mean, float* rstd, float* mean2, float* rstd2, float* y,
+                 void* hiA, void* loA, void* hiB, void* loB, cudaStream_t s);
+// reductions + dx from ONE read of (dy, x); see in_fused.cu.  Outputs (each optional): dx fp32,
+// dx as bf16 planes, g_out = dy*act', dgamma/dbeta (and the second affine set's), dbias = column
+// sums of dx (the bias gradient of the convolution that produced x).
+size_t in_bwd_fused_scratch_floats(int N, int HW, int C);
+int in_bwd_fused(const float* dy, const float* dy2, const float* ymask, const float* x, int N,
+                 int HW, int C, const float* mean, const float* rstd, const float* gamma,
+                 const float* beta, const float* gamma2, const float* beta2, int act,
+                 const float* addend, float* dx, void* dx_hi, void* dx_lo, float* g_out,
+                 float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, float* dbias,
+                 float* dbias2, bool accumulate, float* scratch, cudaStream_t s);
+// dy -> bf16 hi/lo planes and (dbias != null) dbias (+)= column sums, one read of dy
+size_t split_colsum_scratch_floats(long long rows, int C);
+int split_colsum(const float* dy, long long rows, int C, void* hi, void* lo, float* dbias,
+                 float* dbias2, bool accumulate, float* scratch, cudaStream_t s);
 // Backward of y = act(IN(x)*gamma+beta + res):
 //   g   = dy * act'(y)                          (written to g_out if non-null: grad wrt res)
 //   dx  = rstd*gamma*( g - mean_hw(g) - xhat*mean_hw(g*xhat) )  (+ addend, optional)

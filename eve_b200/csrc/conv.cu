@@ -490,6 +490,77 @@ int conv_bwd(const ConvGeom& g, const float* x, const float* dy, const float* w,
   return conv_tc_dgrad_s2_run(g, b.d_hi, b.d_lo, b.w_hi, b.w_lo, addend, dx, npass, s);
 }
 
+// ---- plane-to-plane entry points: only the weight planes (and the split-K partials) come out of
+// the scratch slice; the activations' planes belong to the caller
+int conv_fwd_planes(const ConvGeom& g, const void* x_hi, const void* x_lo, const float* w,
+                    const float* bias, const float* addend, float* y, const ConvScratch& sc,
+                    cudaStream_t s) {
+  EVE_REQUIRE(conv_x_fusable(g), EVE_ERR_CONFIG,
+              "conv_fwd_planes: the convolution does not take the split tensor-core path");
+  EVE_REQUIRE(x_hi && x_lo && w && y, EVE_ERR_NULL, "conv_fwd_planes: NULL pointer");
+  Carve c{sc.base, sc.base + sc.bytes};
+  const size_t wel = (size_t)g.Cout * g.K();
+  uint16_t* w_hi = c.get<uint16_t>(wel);
+  uint16_t* w_lo = c.get<uint16_t>(wel);
+  EVE_REQUIRE(w_lo, EVE_ERR_WORKSPACE, "conv_fwd_planes: scratch too small");
+  const float wscale = 64.f;
+  if (const PreparedW* pw = find_prepared(w, false, 3)) {
+    w_hi = const_cast<uint16_t*>(pw->hi);
+    w_lo = const_cast<uint16_t*>(pw->lo);
+  } else {
+    EVE_TRY(conv_tc_prep_weights(g, w, false, w_hi, w_lo, TC_F16, wscale, s));
+  }
+  ProfScope prof(PROF_CONV_FWD, 2.0 * g.out_elems() * (double)g.K(),
+                 4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
+  return conv_tc_run(g, x_hi, x_lo, w_hi, w_lo, bias, addend, y, 3, TC_F16, 1.f / wscale, s);
+}
+
+int conv_bwd_planes(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* d_hi,
+                    const void* d_lo, const float* w, float* dw, bool accumulate,
+                    const float* addend, float* dx, const ConvScratch& sc, cudaStream_t s) {
+  EVE_REQUIRE(conv_x_fusable(g), EVE_ERR_CONFIG,
+              "conv_bwd_planes: the convolution does not take the split tensor-core path");
+  EVE_REQUIRE(d_hi && d_lo && (!dw || (x_hi && x_lo)) && (!dx || w), EVE_ERR_NULL,
+              "conv_bwd_planes: NULL pointer");
+  Carve c{sc.base, sc.base + sc.bytes};
+  const size_t wel = (size_t)g.Cout * g.K();
+  float* part = c.get<float>(conv_tc_wgrad_partial_floats(g));
+  uint16_t* w_hi = c.get<uint16_t>(wel);
+  uint16_t* w_lo = c.get<uint16_t>(wel);
+  EVE_REQUIRE(w_lo, EVE_ERR_WORKSPACE, "conv_bwd_planes: scratch too small");
+  const double flops = 2.0 * g.out_elems() * (double)g.K();
+  const double bytes = 4.0 * (g.in_elems() + g.out_elems() + (double)wel);
+  if (dw) {
+    int splits = 0;
+    ProfScope prof(PROF_CONV_WGRAD, flops, bytes, s);
+    EVE_TRY(conv_tc_wgrad_run(g, d_hi, d_lo, x_hi, x_lo, part, 3, &splits, s));
+    EVE_TRY(wgrad_reduce(part, splits, g, dw, accumulate, s));
+  }
+  if (!dx) return EVE_OK;
+  const bool s1 = bwd_dgrad_s1(g);
+  if (const PreparedW* pw = s1 ? find_prepared(w, true, 3) : nullptr) {
+    w_hi = const_cast<uint16_t*>(pw->hi);
+    w_lo = const_cast<uint16_t*>(pw->lo);
+  } else {
+    EVE_TRY(conv_tc_prep_weights(g, w, true, w_hi, w_lo, TC_BF16, 1.f, s));
+  }
+  if (!s1 && g.KH == 1) {
+    // stride-2 1x1: only even/even pixels receive data, the rest is the addend (or zero)
+    if (addend) {
+      if (addend != dx)
+        EVE_CUDA(cudaMemcpyAsync(dx, addend, (size_t)g.in_elems() * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
+    } else {
+      EVE_TRY(fill_zero(dx, g.in_elems(), s));
+    }
+  }
+  ProfScope prof(PROF_CONV_DGRAD, flops, bytes, s);
+  if (s1)
+    return conv_tc_run(dgrad_as_fwd(g), d_hi, d_lo, w_hi, w_lo, nullptr, addend, dx, 3, TC_BF16, 1.f,
+                       s);
+  return conv_tc_dgrad_s2_run(g, d_hi, d_lo, w_hi, w_lo, addend, dx, 3, s);
+}
+
 void conv_prepared_clear() { g_nprepared = 0; }
 
 // Prepare the weights of `g` for repeated conv_fwd (dgrad = false) or stride-1 conv_dgrad

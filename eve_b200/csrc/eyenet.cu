@@ -123,7 +123,31 @@ size_t cnn_conv_scratch_bytes(const CnnTape& t) {
 
 size_t cnn_fwd_scratch(const CnnTape& t) {
   return align_up(cnn_conv_scratch_bytes(t), 256) +
-         align_up((size_t)512 * t.nf * sizeof(float), 256) + 1024;
+         align_up((size_t)512 * t.nf * sizeof(float), 256) +
+         4 * align_up(t.max_act * sizeof(uint16_t), 256) + 1024;   // operand planes IN, Y
+}
+
+struct Planes {
+  uint16_t *hi, *lo;
+};
+Planes get_planes(Arena& ws, size_t elems) {
+  Planes p;
+  p.hi = ws.get<uint16_t>(elems);
+  p.lo = ws.get<uint16_t>(elems);
+  return p;
+}
+
+// plane-to-plane pipeline (one-pass normalisations, in_fused.cu): every 3x3 / 1x1 convolution of
+// the eight blocks takes the split tensor-core path and every map fits the cluster kernels
+bool cnn_fused(const CnnTape& t) {
+  if (!get_option(OPT_FUSED_NORM)) return false;
+  for (int i = 0; i < 8; ++i) {
+    const BlockTape& k = t.blk[i];
+    if (!conv_x_fusable(k.g1) || !conv_x_fusable(k.g2)) return false;
+    if (k.down && !conv_x_fusable(k.gd)) return false;
+    if (!in_fused_supported(k.g1.OH * k.g1.OW, k.g1.Cout, 2)) return false;
+  }
+  return true;
 }
 
 }  // namespace
@@ -147,6 +171,8 @@ namespace {
 struct CnnBwdScratch {
   float *wg, *inb, *ga, *gb, *t0, *t1, *t2, *t3, *stem_g, *stem_d, *dpooled;
   ConvScratch cs;
+  Planes XP, XI, DB, DA;   // fused pipeline: x planes (y / block input), dy planes
+  float* col;
 };
 
 bool build_cnn_bwd_scratch(const CnnTape& t, Arena& ws, CnnBwdScratch& s) {
@@ -163,6 +189,11 @@ bool build_cnn_bwd_scratch(const CnnTape& t, Arena& ws, CnnBwdScratch& s) {
   s.stem_g = ws.get<float>((size_t)t.stem.out_elems());
   s.stem_d = ws.get<float>((size_t)t.stem.out_elems());
   s.dpooled = ws.get<float>((size_t)t.N * 512);
+  s.XP = get_planes(ws, t.max_act);
+  s.XI = get_planes(ws, t.max_act);
+  s.DB = get_planes(ws, t.max_act);
+  s.DA = get_planes(ws, t.max_act);
+  s.col = ws.get<float>((size_t)12 * t.N * 512);
   return ws.ok();
 }
 
@@ -206,6 +237,31 @@ extern "C" int eve_eyenet_cnn_fwd(const eve_eyenet_cnn_params* p, const float* x
   EVE_TRY(conv_fwd(t.stem, t.x, w[0], nullptr, nullptr, t.c1, cs, s));
   EVE_TRY(in_stats(t.c1, N, t.stem.OH * t.stem.OW, 64, t.c1m, t.c1r, s));
   EVE_TRY(in_relu_maxpool(t.c1, N, t.stem.OH, t.stem.OW, 64, t.c1m, t.c1r, t.p, t.pidx, s));
+  if (cnn_fused(t)) {
+    const Planes PI = get_planes(ws, t.max_act), PY = get_planes(ws, t.max_act);
+    EVE_REQUIRE(ws.ok(), EVE_ERR_WORKSPACE, "eyenet_cnn_fwd: workspace too small");
+    // PI always holds the fp16 planes of the current block input: written here for the first block,
+    // afterwards by the kernel that finishes the previous block
+    EVE_TRY(split_planes(t.p, (long long)t.blk[0].g1.in_elems(), PI.hi, PI.lo, TC_F16, s));
+    for (int i = 0; i < 8; ++i) {
+      BlockTape& k = t.blk[i];
+      const int slot = block_slot(i);
+      const int C = k.g1.Cout, HW = k.g1.OH * k.g1.OW;
+      EVE_TRY(conv_fwd_planes(k.g1, PI.hi, PI.lo, w[slot], nullptr, nullptr, k.a, cs, s));
+      EVE_TRY(in_fwd_fused(k.a, N, HW, C, nullptr, 0, nullptr, nullptr, nullptr, nullptr, ACT_RELU,
+                           TC_F16, k.am, k.ar, nullptr, nullptr, nullptr, PY.hi, PY.lo, nullptr,
+                           nullptr, s));
+      EVE_TRY(conv_fwd_planes(k.g2, PY.hi, PY.lo, w[slot + 1], nullptr, nullptr, k.b, cs, s));
+      if (k.down)
+        EVE_TRY(conv_fwd_planes(k.gd, PI.hi, PI.lo, w[slot + 2], nullptr, nullptr, k.d, cs, s));
+      // out = relu(IN(b) + (x | IN(d))): statistics of b (and d), the fp32 output (residual of the
+      // next block, mask of the backward pass) and the next block's operand planes in one pass
+      const bool last = i == 7;
+      EVE_TRY(in_fwd_fused(k.b, N, HW, C, k.down ? k.d : k.in, k.down ? 2 : 1, nullptr, nullptr,
+                           nullptr, nullptr, ACT_RELU, TC_F16, k.bm, k.br, k.dm, k.dr, k.out,
+                           last ? nullptr : PI.hi, last ? nullptr : PI.lo, nullptr, nullptr, s));
+    }
+  } else
   for (int i = 0; i < 8; ++i) {
     BlockTape& k = t.blk[i];
     const int slot = block_slot(i);
@@ -261,6 +317,42 @@ extern "C" int eve_eyenet_cnn_bwd(const eve_eyenet_cnn_params* p, const float* d
   float* dnext = sc.gb;
   EVE_TRY(avgpool_bwd(sc.dpooled, N, last.g1.OH * last.g1.OW, 512, dout, s));
 
+  if (cnn_fused(t)) {
+    for (int i = 7; i >= 0; --i) {
+      const BlockTape& k = t.blk[i];
+      const int slot = block_slot(i);
+      const int C = k.g1.Cout, HW = k.g1.OH * k.g1.OW;
+      float* gskip = sc.t1;
+      // out = relu(IN(b) + skip): db as the bf16 dy planes of conv2, gskip = dout * relu'(out)
+      EVE_TRY(in_bwd_fused(dout, nullptr, k.out, k.b, N, HW, C, k.bm, k.br, nullptr, nullptr, nullptr,
+                           nullptr, ACT_RELU, nullptr, nullptr, sc.DB.hi, sc.DB.lo, gskip, nullptr,
+                           nullptr, nullptr, nullptr, nullptr, nullptr, false, sc.col, s));
+      EVE_TRY(in_apply_planes2(k.a, N, HW, C, k.am, k.ar, nullptr, nullptr, nullptr, nullptr, ACT_RELU,
+                               TC_BF16, sc.XP.hi, sc.XP.lo, nullptr, nullptr, s));
+      EVE_TRY(conv_bwd_planes(k.g2, sc.XP.hi, sc.XP.lo, sc.DB.hi, sc.DB.lo, w[slot + 1], gr[slot + 1],
+                              acc, nullptr, sc.t2, sc.cs, s));
+      // y = relu(IN(a)): da as the dy planes of conv1
+      EVE_TRY(in_bwd_fused(sc.t2, nullptr, nullptr, k.a, N, HW, C, k.am, k.ar, nullptr, nullptr,
+                           nullptr, nullptr, ACT_RELU, nullptr, nullptr, sc.DA.hi, sc.DA.lo, nullptr,
+                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false, sc.col, s));
+      // the block input feeds conv1 and the downsample convolution: one bf16 split for both
+      EVE_TRY(split_planes(k.in, (long long)k.g1.in_elems(), sc.XI.hi, sc.XI.lo, TC_BF16, s));
+      const float* addend = gskip;
+      if (k.down) {
+        EVE_TRY(in_bwd_fused(gskip, nullptr, nullptr, k.d, N, HW, C, k.dm, k.dr, nullptr, nullptr,
+                             nullptr, nullptr, ACT_NONE, nullptr, nullptr, sc.DB.hi, sc.DB.lo, nullptr,
+                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false, sc.col, s));
+        EVE_TRY(conv_bwd_planes(k.gd, sc.XI.hi, sc.XI.lo, sc.DB.hi, sc.DB.lo, w[slot + 2],
+                                gr[slot + 2], acc, nullptr, sc.t3, sc.cs, s));
+        addend = sc.t3;
+      }
+      EVE_TRY(conv_bwd_planes(k.g1, sc.XI.hi, sc.XI.lo, sc.DA.hi, sc.DA.lo, w[slot], gr[slot], acc,
+                              addend, dnext, sc.cs, s));
+      float* tmp = dout;
+      dout = dnext;
+      dnext = tmp;
+    }
+  } else
   for (int i = 7; i >= 0; --i) {
     const BlockTape& k = t.blk[i];
     const int slot = block_slot(i);

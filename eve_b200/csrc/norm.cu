@@ -184,6 +184,58 @@ in_apply_planes_kernel(const float* __restrict__ x, long long total4, int HW, in
   reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
 }
 
+// Two affine sets from one read of x (planes only).
+template <int FMT>
+__global__ void __launch_bounds__(256)
+in_apply_planes2_kernel(const float* __restrict__ x, long long total4, int HW, int C,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                        const float* __restrict__ gammaB, const float* __restrict__ betaB, int act,
+                        uint16_t* __restrict__ hiA, uint16_t* __restrict__ loA,
+                        uint16_t* __restrict__ hiB, uint16_t* __restrict__ loB) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int C4 = C >> 2;
+  int c = (int)(i % C4) * 4;
+  long long pix = i / C4;
+  int n = (int)(pix / HW);
+  float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+  float4 m = *reinterpret_cast<const float4*>(mean + (size_t)n * C + c);
+  float4 r = *reinterpret_cast<const float4*>(rstd + (size_t)n * C + c);
+  const float xh[4] = {(v.x - m.x) * r.x, (v.y - m.y) * r.y, (v.z - m.z) * r.z, (v.w - m.w) * r.w};
+#pragma unroll
+  for (int set = 0; set < 2; ++set) {
+    const float* gp = set == 0 ? gamma : gammaB;
+    const float* bp = set == 0 ? beta : betaB;
+    uint16_t* hi = set == 0 ? hiA : hiB;
+    uint16_t* lo = set == 0 ? loA : loB;
+    if (!hi) continue;
+    float o[4] = {xh[0], xh[1], xh[2], xh[3]};
+    if (gp) {
+      float4 g = *reinterpret_cast<const float4*>(gp + c);
+      float4 b = *reinterpret_cast<const float4*>(bp + c);
+      o[0] = fmaf(o[0], g.x, b.x); o[1] = fmaf(o[1], g.y, b.y);
+      o[2] = fmaf(o[2], g.z, b.z); o[3] = fmaf(o[3], g.w, b.w);
+    }
+    uint16_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[j] = act_fwd(o[j], act);
+      if (FMT == TC_BF16) {
+        __nv_bfloat16 hb = __float2bfloat16_rn(o[j]);
+        h[j] = __bfloat16_as_ushort(hb);
+        l[j] = __bfloat16_as_ushort(__float2bfloat16_rn(o[j] - __bfloat162float(hb)));
+      } else {
+        __half hh = __float2half_rn(o[j]);
+        h[j] = __half_as_ushort(hh);
+        l[j] = __half_as_ushort(__float2half_rn(o[j] - __half2float(hh)));
+      }
+    }
+    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+    reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+  }
+}
+
 // Backward reductions per (n,c): sum g and sum g*xhat with g = dy*act'(y).
 // grid (N, C/CB); same thread layout as in_stats_kernel.
 __global__ void __launch_bounds__(256)
@@ -397,6 +449,26 @@ int in_apply_planes(const float* x, int N, int HW, int C, const float* mean, con
   else
     in_apply_planes_kernel<TC_F16><<<cdiv(total4, 256), 256, 0, s>>>(
         x, total4, HW, C, mean, rstd, gamma, beta, act, y, (uint16_t*)hi, (uint16_t*)lo);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+int in_apply_planes2(const float* x, int N, int HW, int C, const float* mean, const float* rstd,
+                     const float* gamma, const float* beta, const float* gammaB,
+                     const float* betaB, int act, int fmt, void* hiA, void* loA, void* hiB,
+                     void* loB, cudaStream_t s) {
+  EVE_REQUIRE(C % 4 == 0, EVE_ERR_SHAPE, "in_apply_planes2: C=%d must be a multiple of 4", C);
+  EVE_REQUIRE(hiA && loA && (!hiB || loB), EVE_ERR_NULL, "in_apply_planes2: plane pointers");
+  long long total4 = (long long)N * HW * C / 4;
+  if (total4 == 0) return EVE_OK;
+  if (fmt == TC_BF16)
+    in_apply_planes2_kernel<TC_BF16><<<cdiv(total4, 256), 256, 0, s>>>(
+        x, total4, HW, C, mean, rstd, gamma, beta, gammaB, betaB, act, (uint16_t*)hiA,
+        (uint16_t*)loA, (uint16_t*)hiB, (uint16_t*)loB);
+  else
+    in_apply_planes2_kernel<TC_F16><<<cdiv(total4, 256), 256, 0, s>>>(
+        x, total4, HW, C, mean, rstd, gamma, beta, gammaB, betaB, act, (uint16_t*)hiA,
+        (uint16_t*)loA, (uint16_t*)hiB, (uint16_t*)loB);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }

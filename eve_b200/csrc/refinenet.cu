@@ -553,6 +553,105 @@ int block_bwd(const RBlock& k, int N, const float* const* w, float* const* gr, b
   return EVE_OK;
 }
 
+// ------------------------------------------------- plane-to-plane block pipeline (fused_norm) --
+// Every normalisation is ONE pass (in_fused.cu) that writes the consuming convolution's operand
+// planes; backward normalisations emit the bf16 dy planes and the bias-gradient column sums of the
+// convolution in front of them, so no fp32 activation, split or colsum pass remains inside a block.
+struct Planes {
+  uint16_t *hi, *lo;
+};
+
+bool block_fusable(const RBlock& k) {
+  if (!conv_x_fusable(k.g1) || !conv_x_fusable(k.g2)) return false;
+  if (k.skipconv && !conv_x_fusable(k.gs)) return false;
+  const int HW = k.H * k.W;
+  return in_fused_supported(HW, k.ic, 2) && in_fused_supported(HW, k.oc, 2);
+}
+
+bool rnet_fused(const RNet& n) {
+  if (!get_option(OPT_FUSED_NORM)) return false;
+  if (!conv_x_fusable(n.gi3) || !in_fused_supported(kLevelH[0] * kLevelW[0], 16, 2)) return false;
+  for (int l = 0; l < kLevels; ++l) {
+    for (auto& k : n.enc[l])
+      if (!block_fusable(k)) return false;
+    if (!block_fusable(n.dec[l])) return false;
+  }
+  return true;
+}
+
+int block_fwd_fused(const RBlock& k, int N, const float* const* w, const ConvScratch& cs,
+                    const Planes& PA, const Planes& PB, cudaStream_t s) {
+  const float* const* bw = w + k.slot;
+  const int HW = k.H * k.W;
+  const bool sk = k.skipconv;
+  // one read of x: statistics, the main path's planes and (skip convolution) the skip path's
+  EVE_TRY(in_fwd_fused(k.x, N, HW, k.ic, nullptr, 0, bw[0], bw[1], sk ? bw[8] : nullptr,
+                       sk ? bw[9] : nullptr, k.act, TC_F16, k.m0, k.r0, nullptr, nullptr, nullptr,
+                       PA.hi, PA.lo, sk ? PB.hi : nullptr, sk ? PB.lo : nullptr, s));
+  EVE_TRY(conv_fwd_planes(k.g1, PA.hi, PA.lo, bw[2], bw[3], nullptr, k.c1, cs, s));
+  const float* addend = k.x;
+  if (sk) {
+    EVE_TRY(conv_fwd_planes(k.gs, PB.hi, PB.lo, bw[10], bw[11], nullptr, k.out, cs, s));
+    addend = k.out;
+  }
+  EVE_TRY(in_fwd_fused(k.c1, N, HW, k.oc, nullptr, 0, bw[4], bw[5], nullptr, nullptr, k.act, TC_F16,
+                       k.m1, k.r1, nullptr, nullptr, nullptr, PA.hi, PA.lo, nullptr, nullptr, s));
+  return conv_fwd_planes(k.g2, PA.hi, PA.lo, bw[6], bw[7], addend, k.out, cs, s);
+}
+
+struct FusedBwd {
+  Planes DA, DB, D2, XP, XP2;   // dout planes (ping-pong), dy planes of conv1, x planes
+  float* col;                   // reduction scratch of in_bwd_fused / split_colsum
+};
+
+size_t fused_col_floats(int N) {
+  return (size_t)12 * N * 512 + (size_t)2049 * 512;
+}
+
+// dout -> dx.  `din`: the planes of dout (already written, together with the bias gradients of
+// conv2 / the skip convolution, by whoever produced dout) or null (derived here).  `dnext`: where
+// to write the planes of dx (null: fp32 only); nb_a / nb_b: bias gradients fed by dx's column sums.
+int block_bwd_fused(const RBlock& k, int N, const float* const* w, float* const* gr, bool acc,
+                    const float* dout, const Planes* din, float* dx, const Planes* dnext,
+                    float* nb_a, float* nb_b, const BwdScratch& sc, const FusedBwd& f,
+                    cudaStream_t s) {
+  const float* const* bw = w + k.slot;
+  float* const* bg = gr + k.slot;
+  const int HW = k.H * k.W;
+  const bool sk = k.skipconv;
+  Planes D = f.DA;
+  if (din) {
+    D = *din;
+  } else {
+    EVE_TRY(split_colsum(dout, (long long)N * HW, k.oc, D.hi, D.lo, bg[7], sk ? bg[11] : nullptr,
+                         acc, f.col, s));
+  }
+  // conv2: x operand re-derived from the saved pre-norm tensor
+  EVE_TRY(in_apply_planes2(k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], nullptr, nullptr, k.act,
+                           TC_BF16, f.XP.hi, f.XP.lo, nullptr, nullptr, s));
+  EVE_TRY(conv_bwd_planes(k.g2, f.XP.hi, f.XP.lo, D.hi, D.lo, bw[6], bg[6], acc, nullptr, sc.t0,
+                          sc.cs, s));
+  // norm 1: dy planes of conv1, its bias gradient, the affine gradients -- one pass
+  EVE_TRY(in_bwd_fused(sc.t0, nullptr, nullptr, k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], nullptr,
+                       nullptr, k.act, nullptr, nullptr, f.D2.hi, f.D2.lo, nullptr, bg[4], bg[5],
+                       nullptr, nullptr, bg[3], nullptr, acc, f.col, s));
+  EVE_TRY(in_apply_planes2(k.x, N, HW, k.ic, k.m0, k.r0, bw[0], bw[1], sk ? bw[8] : nullptr,
+                           sk ? bw[9] : nullptr, k.act, TC_BF16, f.XP.hi, f.XP.lo,
+                           sk ? f.XP2.hi : nullptr, sk ? f.XP2.lo : nullptr, s));
+  EVE_TRY(conv_bwd_planes(k.g1, f.XP.hi, f.XP.lo, f.D2.hi, f.D2.lo, bw[2], bg[2], acc, nullptr,
+                          sc.t0, sc.cs, s));
+  if (sk)
+    EVE_TRY(conv_bwd_planes(k.gs, f.XP2.hi, f.XP2.lo, D.hi, D.lo, bw[10], bg[10], acc, nullptr,
+                            sc.t2, sc.cs, s));
+  // norm 0 (both affine sets of the same statistics when there is a skip convolution); the
+  // identity residual passes dout straight through when there is none
+  return in_bwd_fused(sc.t0, sk ? sc.t2 : nullptr, nullptr, k.x, N, HW, k.ic, k.m0, k.r0, bw[0],
+                      bw[1], sk ? bw[8] : nullptr, sk ? bw[9] : nullptr, k.act,
+                      sk ? nullptr : dout, dx,
+                      dnext ? dnext->hi : nullptr, dnext ? dnext->lo : nullptr, nullptr, bg[0],
+                      bg[1], sk ? bg[8] : nullptr, sk ? bg[9] : nullptr, nb_a, nb_b, acc, f.col, s);
+}
+
 size_t rnet_conv_scratch_bytes(const RNet& n) {
   size_t mi = 0, mo = 0, mw = 0, mp = 0;
   auto upd = [&](const ConvGeom& g) {
@@ -579,6 +678,23 @@ bool build_bwd_scratch(const RNet& n, Arena& ws, BwdScratch& sc) {
   sc.t2 = ws.get<float>(n.max_act);
   sc.ga = ws.get<float>(n.max_act);
   sc.gb = ws.get<float>(n.max_act);
+  return ws.ok();
+}
+
+Planes get_planes(Arena& ws, size_t elems) {
+  Planes p;
+  p.hi = ws.get<uint16_t>(elems);
+  p.lo = ws.get<uint16_t>(elems);
+  return p;
+}
+
+bool build_fused_bwd(const RNet& n, Arena& ws, FusedBwd& f) {
+  f.DA = get_planes(ws, n.max_act);
+  f.DB = get_planes(ws, n.max_act);
+  f.D2 = get_planes(ws, n.max_act);
+  f.XP = get_planes(ws, n.max_act);
+  f.XP2 = get_planes(ws, n.max_act);
+  f.col = ws.get<float>(fused_col_floats(n.N));
   return ws.ok();
 }
 
@@ -615,6 +731,7 @@ bool build_bwd_extra(const RNet& n, Arena& ws, BwdExtra& e) {
 size_t rnet_fwd_scratch_bytes(const RNet& n) {
   const int P = kLevelH[4] * kLevelW[4];
   return align_up(rnet_conv_scratch_bytes(n), 256) +
+         4 * align_up(n.max_act * sizeof(uint16_t), 256) +      // operand planes A, B (hi + lo)
          4 * align_up((size_t)n.B * P * 4 * n.nf * sizeof(float), 256) +
          2 * align_up((size_t)kMaxRCells * n.B * P * n.nf * sizeof(float), 256) + 4096 + 16384;
 }
@@ -659,8 +776,10 @@ extern "C" size_t eve_refinenet_workspace_bytes(const eve_refinenet_params* p) {
   Arena ws(nullptr, 0);
   BwdScratch sc;
   BwdExtra ex;
+  FusedBwd fb;
   build_bwd_scratch(n, ws, sc);
   build_bwd_extra(n, ws, ex);
+  build_fused_bwd(n, ws, fb);
   size_t f = rnet_fwd_scratch_bytes(n);
   return (ws.off > f ? ws.off : f) + 256;
 }
@@ -692,6 +811,8 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
   for (int i = 0; i < 4; ++i) cb[i] = ws.get<float>((size_t)B * P * 4 * nf);
   float* h0n = ws.get<float>((size_t)kMaxRCells * B * P * nf);
   float* c0n = ws.get<float>((size_t)kMaxRCells * B * P * nf);
+  const Planes PA = get_planes(ws, n.max_act), PB = get_planes(ws, n.max_act);
+  const bool fusedn = rnet_fused(n);
   const int HW0 = kLevelH[0] * kLevelW[0];
 
   // ---- input + initial
@@ -701,14 +822,23 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
   EVE_REQUIRE(w0p, EVE_ERR_WORKSPACE, "refinenet_fwd: workspace too small");
   LAUNCH1D(pad_cin_kernel, 16 * kInitC * 9, w[0], 16, p->in_channels, kInitC, w0p);
   EVE_TRY(conv_fwd(n.gi0, n.x0, w0p, w[1], nullptr, n.i0, cs, s));
-  EVE_TRY(in_stats(n.i0, N, HW0, 16, n.im, n.ir, s));
-  bool i1_fused = false;
-  EVE_TRY(norm_act_into_conv(n.gi3, false, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU, n.i1,
-                             cs, &i1_fused, s));
-  EVE_TRY(conv_fwd(n.gi3, i1_fused ? nullptr : n.i1, w[4], w[5], nullptr, n.i2, cs, s));
+  if (fusedn) {
+    EVE_TRY(in_fwd_fused(n.i0, N, HW0, 16, nullptr, 0, w[2], w[3], nullptr, nullptr, ACT_RELU, TC_F16,
+                         n.im, n.ir, nullptr, nullptr, nullptr, PA.hi, PA.lo, nullptr, nullptr, s));
+    EVE_TRY(conv_fwd_planes(n.gi3, PA.hi, PA.lo, w[4], w[5], nullptr, n.i2, cs, s));
+  } else {
+    EVE_TRY(in_stats(n.i0, N, HW0, 16, n.im, n.ir, s));
+    bool i1_fused = false;
+    EVE_TRY(norm_act_into_conv(n.gi3, false, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU,
+                               n.i1, cs, &i1_fused, s));
+    EVE_TRY(conv_fwd(n.gi3, i1_fused ? nullptr : n.i1, w[4], w[5], nullptr, n.i2, cs, s));
+  }
+  auto run_block = [&](const RBlock& k) -> int {
+    return fusedn ? block_fwd_fused(k, N, w, cs, PA, PB, s) : block_fwd(k, N, w, cs, s);
+  };
   // ---- encoder
   for (int l = 0; l < kLevels; ++l) {
-    for (auto& k : n.enc[l]) EVE_TRY(block_fwd(k, N, w, cs, s));
+    for (auto& k : n.enc[l]) EVE_TRY(run_block(k));
     if (l + 1 < kLevels) {
       const RBlock& k = n.enc[l].back();
       EVE_TRY(adaptive_maxpool_fwd(k.out, N, k.H, k.W, k.oc, kLevelH[l + 1], kLevelW[l + 1],
@@ -805,7 +935,7 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
     if (p->use_skip)
       EVE_TRY(copy_channels(n.enc[4].back().out, (long long)N * P, nf, nf, 0, n.cat[4], k.ic, nf,
                             false, s));
-    EVE_TRY(block_fwd(k, N, w, cs, s));
+    EVE_TRY(run_block(k));
   }
   for (int l = 3; l >= 0; --l) {
     const RBlock& k = n.dec[l];
@@ -816,7 +946,7 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
     if (p->use_skip)
       EVE_TRY(copy_channels(e.out, (long long)N * k.H * k.W, e.oc, e.oc, 0, n.cat[l], k.ic,
                             inner.oc, false, s));
-    EVE_TRY(block_fwd(k, N, w, cs, s));
+    EVE_TRY(run_block(k));
   }
   // ---- final: conv3x3 -> LeakyReLU -> conv1x1 -> sigmoid
   const float* const* fw = w + n.slot_final;
@@ -845,8 +975,11 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
   Arena ws(workspace, workspace_bytes);
   BwdScratch sc;
   BwdExtra ex;
+  FusedBwd fb;
   bool ok = build_bwd_scratch(n, ws, sc);
   ok = build_bwd_extra(n, ws, ex) && ok;
+  ok = build_fused_bwd(n, ws, fb) && ok;
+  const bool fusedn = rnet_fused(n);
   EVE_REQUIRE(ok, EVE_ERR_WORKSPACE, "refinenet_bwd: workspace too small (%zu < %zu)",
               workspace_bytes, ws.off);
   const int N = n.N, B = n.B, T = n.T, nf = n.nf;
@@ -876,7 +1009,11 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
     const RBlock& k = n.dec[l];
     const RBlock& inner = n.dec[l + 1];
     const RBlock& e = n.enc[l].back();
-    EVE_TRY(block_bwd(k, N, w, gr, acc, cur, other, sc, s));
+    if (fusedn)
+      EVE_TRY(block_bwd_fused(k, N, w, gr, acc, cur, nullptr, other, nullptr, nullptr, nullptr, sc,
+                              fb, s));
+    else
+      EVE_TRY(block_bwd(k, N, w, gr, acc, cur, other, sc, s));
     if (p->use_skip)
       EVE_TRY(copy_channels(other, (long long)N * k.H * k.W, e.oc, k.ic, inner.oc, ex.dskip[l],
                             e.oc, 0, false, s));
@@ -884,7 +1021,11 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
   }
   {
     const RBlock& k = n.dec[4];
-    EVE_TRY(block_bwd(k, N, w, gr, acc, cur, other, sc, s));
+    if (fusedn)
+      EVE_TRY(block_bwd_fused(k, N, w, gr, acc, cur, nullptr, other, nullptr, nullptr, nullptr, sc,
+                              fb, s));
+    else
+      EVE_TRY(block_bwd(k, N, w, gr, acc, cur, other, sc, s));
     if (p->use_skip)
       EVE_TRY(copy_channels(other, (long long)N * P, nf, k.ic, nf, ex.dskip[4], nf, 0, false, s));
     // batch-major [B][T][P][ic] -> time-major [T][B][P][nf]
@@ -973,9 +1114,30 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
   // ---- encoder, innermost first.  `cur` <- grad w.r.t. the encoder output of level 4
   LAUNCH1D(swap_bt_kernel, (long long)N * E, dbx, (long long)N * E, T, B, P, nf, nf, cur, nf);
   if (p->use_skip) EVE_TRY(ew_add(cur, ex.dskip[4], (long long)N * E, cur, s));
+  // In the fused pipeline a block hands the bf16 planes of its dx (and the bias-gradient column
+  // sums) straight to the block in front of it; `have` tells whether `cur` comes with planes.
+  Planes pcur = fb.DA, pnext = fb.DB;
+  bool have = false;
   for (int l = kLevels - 1; l >= 0; --l) {
     for (int j = (int)n.enc[l].size() - 1; j >= 0; --j) {
-      EVE_TRY(block_bwd(n.enc[l][j], N, w, gr, acc, cur, other, sc, s));
+      const RBlock& k = n.enc[l][j];
+      if (fusedn) {
+        // consumer of this block's dx: the previous block of the level, or initial.3 at the very end
+        const bool to_block = j > 0;
+        const bool to_initial = l == 0 && j == 0;
+        float* const* ng = to_block ? gr + n.enc[l][j - 1].slot : nullptr;
+        float* nb_a = to_block ? ng[7] : (to_initial ? gr[5] : nullptr);
+        float* nb_b = to_block && n.enc[l][j - 1].skipconv ? ng[11] : nullptr;
+        const bool emit = to_block || to_initial;
+        FusedBwd fl = fb;
+        fl.DA = pcur;          // where split_colsum puts the planes when `cur` came without them
+        EVE_TRY(block_bwd_fused(k, N, w, gr, acc, cur, have ? &pcur : nullptr, other,
+                                emit ? &pnext : nullptr, nb_a, nb_b, sc, fl, s));
+        have = emit;
+        Planes tp = pcur; pcur = pnext; pnext = tp;
+      } else {
+        EVE_TRY(block_bwd(k, N, w, gr, acc, cur, other, sc, s));
+      }
       float* tmp = cur; cur = other; other = tmp;
     }
     if (l > 0) {
@@ -985,16 +1147,28 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
       if (p->use_skip)
         EVE_TRY(ew_add(other, ex.dskip[l - 1], (long long)N * e.H * e.W * e.oc, other, s));
       float* tmp = cur; cur = other; other = tmp;
+      have = false;
     }
   }
   // ---- initial
-  bool i1_fused = false;
-  EVE_TRY(norm_act_into_conv(n.gi3, true, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU, nullptr,
-                             sc.cs, &i1_fused, s));
-  EVE_TRY(conv_bwd(n.gi3, i1_fused ? nullptr : n.i1, cur, w[4], gr[4], gr[5], acc, nullptr, sc.t0,
-                   sc.cs, s));
-  EVE_TRY(in_backward(sc.t0, nullptr, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU, nullptr,
-                      sc.t1, nullptr, gr[2], gr[3], sc.inb, acc, s));
+  if (fusedn) {
+    // `cur` arrives with its bf16 planes in pcur and initial.3's bias gradient already reduced
+    EVE_TRY(in_apply_planes2(n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], nullptr, nullptr, ACT_RELU,
+                             TC_BF16, fb.XP.hi, fb.XP.lo, nullptr, nullptr, s));
+    EVE_TRY(conv_bwd_planes(n.gi3, fb.XP.hi, fb.XP.lo, pcur.hi, pcur.lo, w[4], gr[4], acc, nullptr,
+                            sc.t0, sc.cs, s));
+    EVE_TRY(in_bwd_fused(sc.t0, nullptr, nullptr, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], nullptr,
+                         nullptr, ACT_RELU, nullptr, sc.t1, nullptr, nullptr, nullptr, gr[2], gr[3],
+                         nullptr, nullptr, gr[1], nullptr, acc, fb.col, s));
+  } else {
+    bool i1_fused = false;
+    EVE_TRY(norm_act_into_conv(n.gi3, true, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU,
+                               nullptr, sc.cs, &i1_fused, s));
+    EVE_TRY(conv_bwd(n.gi3, i1_fused ? nullptr : n.i1, cur, w[4], gr[4], gr[5], acc, nullptr, sc.t0,
+                     sc.cs, s));
+    EVE_TRY(in_backward(sc.t0, nullptr, n.i0, N, HW0, 16, n.im, n.ir, w[2], w[3], ACT_RELU, nullptr,
+                        sc.t1, nullptr, gr[2], gr[3], sc.inb, acc, s));
+  }
   {
     // zero-padded weights (and their gradient) live at the head of t2, which is free here
     float* w0p = sc.t2;
@@ -1002,7 +1176,7 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
     LAUNCH1D(pad_cin_kernel, 16 * kInitC * 9, w[0], 16, p->in_channels, kInitC, w0p);
     EVE_TRY(conv_bwd(n.gi0, n.x0, sc.t1, w0p, gr[0] ? dw0p : nullptr, nullptr, false, nullptr,
                      dheatmap ? sc.t0 : nullptr, sc.cs, s));
-    if (gr[1])
+    if (gr[1] && !fusedn)
       EVE_TRY(colsum(sc.t1, (long long)N * HW0, 16, 16, gr[1], sc.t2 + 2 * 16 * kInitC * 9, acc, s));
     if (gr[0])
       LAUNCH1D(unpad_cin_kernel, 16 * p->in_channels * 9, dw0p, 16, p->in_channels, kInitC, gr[0],

@@ -68,6 +68,11 @@ SIGNATURES = {
     'eve_conv2d_wgrad': (_I, [_P, _P, _P, _P, _P, _P, _Z, _P]),
     'eve_instnorm_act_fwd': (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
     'eve_instnorm_act_bwd': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    'eve_instnorm_fused_workspace_bytes': (_Z, [_I, _I, _I]),
+    'eve_instnorm_fused_fwd': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P,
+                                    _P, _P, _P, _P, _P, _P]),
+    'eve_instnorm_fused_bwd': (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P,
+                                    _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'eve_adaptive_maxpool_fwd': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'eve_adaptive_maxpool_bwd': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     'eve_upsample_bilinear_fwd': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -77,6 +77,10 @@ int eve_get_conv_mode(void);
  *   "fused_planes"        0/1    normalise+activate kernels write the consuming convolution's
  *                                16-bit operand planes directly (no fp32 activation, no split pass);
  *                                must not change between a forward and its backward
+ *   "fused_norm"          0/1    one-pass cluster InstanceNorm kernels (statistics + normalisation
+ *                                from a single read; backward emits dy planes and bias-gradient
+ *                                sums) and plane-to-plane residual blocks; 0 = the separate
+ *                                stats / apply / reduce / split passes of round 1
  * Unknown names / out-of-range values return EVE_ERR_CONFIG. */
 int eve_set_option(const char* name, int value);
 int eve_get_option(const char* name, int* value);
@@ -100,6 +104,33 @@ int eve_instnorm_act_bwd(const float* dy, const float* y, const float* x, int n,
                          const float* mean, const float* rstd, const float* gamma, int act,
                          float* dx, float* dgamma, float* dbeta, void* workspace,
                          size_t workspace_bytes, eve_stream_t stream);
+
+/* The same normalisation as ONE pass over the tensor (csrc/in_fused.cu): a thread-block cluster
+ * per (image, channel group) stages its pixels in shared memory, reduces the statistics through
+ * distributed shared memory and normalises from there.  These are the kernels the networks use;
+ * exposed so that they can be parity-tested alone.
+ *  fwd: y = act(IN(x)*gamma+beta (+ x2)) with x2_mode 0 none / 1 residual / 2 x2 is itself
+ *       instance-normalised (non-affine; mean2/rstd2 out).  Outputs, each optional: fp32 y, the
+ *       16-bit hi/lo operand planes of y (fmt 0 = fp16, 1 = bf16; y ~ hi + lo) and planes B of
+ *       act(IN(x)*gamma_b+beta_b) (a second affine set over the same statistics,
+ *       refine_net.py:45-62 layers.0 / skip_layer.0).
+ *  bwd: given dy (and dy2 for the second affine set) produces dx = d/dx (+ addend) as fp32 and/or
+ *       bf16 hi/lo planes, g_out = dy*act'(.), the affine gradients and dbias[c] = sum of dx
+ *       (the bias gradient of the convolution that produced x).  ymask: saved forward output
+ *       when a residual was added (its sign gives act'), else NULL (recomputed). */
+size_t eve_instnorm_fused_workspace_bytes(int n, int hw, int c);
+int eve_instnorm_fused_fwd(const float* x, const float* x2, int x2_mode, int n, int hw, int c,
+                           const float* gamma, const float* beta, const float* gamma_b,
+                           const float* beta_b, int act, int fmt, float* mean, float* rstd,
+                           float* mean2, float* rstd2, float* y, void* hi_a, void* lo_a,
+                           void* hi_b, void* lo_b, eve_stream_t stream);
+int eve_instnorm_fused_bwd(const float* dy, const float* dy2, const float* ymask, const float* x,
+                           int n, int hw, int c, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, const float* gamma2,
+                           const float* beta2, int act, const float* addend, float* dx,
+                           void* dx_hi, void* dx_lo, float* g_out, float* dgamma, float* dbeta,
+                           float* dgamma2, float* dbeta2, float* dbias, void* workspace,
+                           size_t workspace_bytes, eve_stream_t stream);
 
 /* nn.AdaptiveMaxPool2d (refine_net.py:93,121): idx = int32 flat h*W+w of the first maximum. */
 int eve_adaptive_maxpool_fwd(const float* x, int n, int h, int w, int c, int oh, int ow, float* y,
