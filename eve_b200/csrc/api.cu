@@ -4,7 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -18,6 +20,21 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
+}
+
+int ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;
+  if (bytes <= 48 * 1024) return EVE_OK;
+  int dev = 0;
+  EVE_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& cur = done[std::make_pair(kernel, dev)];
+  if (bytes > cur) {
+    EVE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+  }
+  return EVE_OK;
 }
 
 static std::atomic<long long> g_launches{0};

@@ -43,6 +43,9 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 void count_launch();
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): sets it once per pair
+// (and again if a larger value is asked for)
+int ensure_dynamic_smem(const void* kernel, size_t bytes);
 
 // Optional per-kernel-family device timing (eve_profile_*): CUDA events recorded on the
 // launching stream around a launch, summed on read.  Costs nothing when disabled.

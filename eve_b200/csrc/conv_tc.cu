@@ -1233,12 +1233,7 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
               const CUtensorMap& b_lo, const TcParams& p0, int tiles_m, int tiles_co,
               cudaStream_t s) {
   using Cfg = TcCfg<BN, NPASS>;
-  static bool configured = false;
-  if (!configured) {
-    EVE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, NPASS>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_kernel<BN, NPASS>, 227 * 1024));
   TcParams p = p0;
   p.tiles_m = tiles_m;
   p.tiles_co = tiles_co;
@@ -1389,12 +1384,7 @@ static int launch_row(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
     EVE_REQUIRE(false, EVE_ERR_SHAPE, "conv_tc_row: %d -> %d channels do not fit", KC, BN);
     return EVE_ERR_SHAPE;
   }
-  static bool configured = false;
-  if (!configured) {
-    EVE_CUDA(cudaFuncSetAttribute(conv_tc_row_kernel<BN, NPASS, KC, KS>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_row_kernel<BN, NPASS, KC, KS>, 227 * 1024));
   p.slots = Cfg::kSlots;
   const int smem_bytes = Cfg::kFixedBytes + Cfg::kSlots * Cfg::kSlotBytes;
   const int grid = p.items < kNumSMs ? p.items : kNumSMs;
@@ -1623,12 +1613,8 @@ static int launch_wgrad_row(const CUtensorMap& d_hi, const CUtensorMap& d_lo, co
                             const CUtensorMap& x_lo, TcWgRowParams p, int grid, cudaStream_t s) {
   using Cfg = WgRowCfg<NPASS, CIN, COUT, KS>;
   static_assert(Cfg::kSlots >= 4, "halo-row wgrad: ring too shallow");
-  static bool configured = false;
-  if (!configured) {
-    EVE_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_row_kernel<NPASS, CIN, COUT, KS>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_wgrad_row_kernel<NPASS, CIN, COUT, KS>,
+                              227 * 1024));
   p.slots = Cfg::kSlots;
   const int smem_bytes = Cfg::kSlots * Cfg::kSlotBytes + 1024 + kBarrierBytes;
   conv_tc_wgrad_row_kernel<NPASS, CIN, COUT, KS><<<grid, kThreads, smem_bytes, s>>>(d_hi, d_lo, x_hi, x_lo, p);
@@ -1727,17 +1713,8 @@ int conv_tc_wgrad_run(const ConvGeom& g, const void* d_hi, const void* d_lo, con
     mx_lo = mx_hi;
   }
   const int smem = p.stages * wgrad_stage_bytes(p, npass) + 1024 + 256;
-  static bool cfg3 = false, cfg1 = false;
-  if (npass == 3 && !cfg3) {
-    EVE_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel<3>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    cfg3 = true;
-  }
-  if (npass == 1 && !cfg1) {
-    EVE_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel<1>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    cfg1 = true;
-  }
+  if (npass == 3) EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_wgrad_kernel<3>, 227 * 1024));
+  else EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_wgrad_kernel<1>, 227 * 1024));
   dim3 grid(mb, nb, sp);
   if (npass == 3)
     conv_tc_wgrad_kernel<3><<<grid, kThreads, smem, s>>>(md_hi, md_lo, mx_hi, mx_lo, p);

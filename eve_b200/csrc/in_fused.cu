@@ -642,27 +642,10 @@ size_t bwd_smem(const FusedPlan& p) {
          2 * kThr * sizeof(float);
 }
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): remember the largest
-// value set so far for each pair
-int ensure_smem(const void* fn, size_t bytes) {
-  static std::mutex mu;
-  static std::map<std::pair<const void*, int>, size_t> done;
-  if (bytes <= 48 * 1024) return EVE_OK;
-  int dev = 0;
-  EVE_CUDA(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lk(mu);
-  size_t& cur = done[std::make_pair(fn, dev)];
-  if (bytes > cur) {
-    EVE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    cur = bytes;
-  }
-  return EVE_OK;
-}
-
 // Persistent launch: as many clusters as the device keeps resident (at most one per work item).
 template <typename K, typename A>
 int launch_persistent(K kernel, int items, int cs, size_t smem, const A& args, cudaStream_t s) {
-  EVE_TRY(ensure_smem((const void*)kernel, smem));
+  EVE_TRY(ensure_dynamic_smem((const void*)kernel, smem));
   int dev = 0;
   EVE_CUDA(cudaGetDevice(&dev));
   cudaLaunchConfig_t cfg = {};

@@ -46,7 +46,7 @@ sqnorm_partial_kernel(const float* __restrict__ g, long long n, float scale,
 __global__ void norm_final_kernel(const float* __restrict__ part, int nparts, float max_norm,
                                   float* __restrict__ stat, float* __restrict__ norm_out,
                                   int* __restrict__ step_dev, int step_host, float beta1,
-                                  float beta2) {
+                                  float beta2, const float* __restrict__ lr_dev, float lr_host) {
   __shared__ double sm[256];
   double a = 0.0;
   for (int i = threadIdx.x; i < nparts; i += blockDim.x) a += (double)part[i];
@@ -74,15 +74,17 @@ __global__ void norm_final_kernel(const float* __restrict__ part, int nparts, fl
     }
     stat[2] = (float)(1.0 - pow((double)beta1, (double)step));
     stat[3] = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    // learning rate of this step: a device scalar when a scheduler drives a captured graph
+    stat[4] = lr_dev ? *lr_dev : lr_host;
   }
 }
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, long long n, const float* __restrict__ stat, float scale,
-            float lr, float b1, float b2, float eps, float wd) {
+            float b1, float b2, float eps, float wd) {
   const float coef = stat[1] * scale;
-  const float bc1 = stat[2], bc2_sqrt = stat[3];
+  const float bc1 = stat[2], bc2_sqrt = stat[3], lr = stat[4];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float pv = p[i];
@@ -123,10 +125,10 @@ extern "C" int eve_adam_clip_step(const eve_adam_params* p, float* params, const
   sqnorm_partial_kernel<<<kNormBlocks, 256, 0, s>>>(grads, p->count, p->grad_scale, part);
   EVE_LAUNCH_CHECK();
   norm_final_kernel<<<1, 256, 0, s>>>(part, kNormBlocks, p->max_norm, stat, norm_out, p->step_dev,
-                                      p->step, p->beta1, p->beta2);
+                                      p->step, p->beta1, p->beta2, p->lr_dev, p->lr);
   EVE_LAUNCH_CHECK();
   adam_kernel<<<kNormBlocks * 2, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, p->count, stat,
-                                              p->grad_scale, p->lr, p->beta1, p->beta2, p->eps,
+                                              p->grad_scale, p->beta1, p->beta2, p->eps,
                                               p->weight_decay);
   EVE_LAUNCH_CHECK();
   return EVE_OK;

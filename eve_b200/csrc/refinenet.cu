@@ -794,6 +794,7 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
   EVE_REQUIRE(heatmap && w && out && saved && workspace, EVE_ERR_NULL,
               "refinenet_fwd: NULL pointer");
   EVE_REQUIRE(p->in_channels == 1 || screen, EVE_ERR_NULL, "refinenet_fwd: screen is NULL");
+  conv_prepared_clear();     // an earlier call that failed half-way must not leave entries behind
   cudaStream_t s = as_stream(stream);
   Arena sv(saved, saved_bytes);
   RNet n;
@@ -968,6 +969,7 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
   EVE_REQUIRE(!(p->rnn_type == EVE_CRNN_CLSTM && (dhT || dcT)), EVE_ERR_CONFIG,
               "refinenet_bwd: gradients into CLSTM states are not supported (the CLSTM state "
               "never reaches the heatmap, refine_net.py:168-174)");
+  conv_prepared_clear();
   cudaStream_t s = as_stream(stream);
   Arena sv(const_cast<void*>(saved), saved_bytes);
   RNet n;

@@ -17,8 +17,12 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import lib as L
+
 
 class GraphedTrainStep(object):
+    KAPPA_RING = 4
+
     def __init__(self, model, trainer, example_inputs, current_epoch=0.0, warmup=3,
                  tag='train', capture=True):
         self.model = model
@@ -28,13 +32,21 @@ class GraphedTrainStep(object):
         dev = trainer.device
         self.static_in = {k: torch.empty_like(v, device=dev) for k, v in example_inputs.items()}
         B = next(iter(example_inputs.values())).shape[0]
-        self.kappa_host = {s: torch.empty((B, 2), dtype=torch.float32).pin_memory()
-                           for s in ('left', 'right')}
+        # ring of pinned kappa buffers: the H2D copy of step i is asynchronous, so the host may not
+        # rewrite a buffer before the copy that reads it has run (event per slot)
+        self.kappa_host = [{s: torch.empty((B, 2), dtype=torch.float32).pin_memory()
+                            for s in ('left', 'right')} for _ in range(self.KAPPA_RING)]
+        self.kappa_done = [None] * self.KAPPA_RING
+        self.kappa_slot = 0
+        # recorded after the batch has been copied into the static buffers: callers that reuse
+        # their pinned input tensors wait on it (inputs_consumed.synchronize()) before rewriting them
+        self.inputs_consumed = torch.cuda.Event()
         model.kappa_buffers = {s: torch.zeros((B, 2), dtype=torch.float32, device=dev)
                                for s in ('left', 'right')}
         self.batch = B
         self.loss = None
         self.graph = None
+        self._pinned = False
         # input prefetch: staging buffers filled on a copy stream (see prefetch())
         self.stage_in = None
         self.copy_stream = None
@@ -54,6 +66,14 @@ class GraphedTrainStep(object):
             with torch.cuda.graph(self.graph):
                 self.loss = self._eager()
             torch.cuda.synchronize(dev)
+            # capturing ran the host side of one step without executing it: the device-side
+            # counter is the truth
+            if trainer.step_dev is not None:
+                trainer.steps = int(trainer.step_dev)
+            # the graph's kernels hold pointers into the shared scratch buffers (lib.workspace):
+            # from now on an outgrown buffer must stay allocated
+            L.pin_workspaces()
+            self._pinned = True
 
     def _eager(self):
         out = self.model({self.tag: dict(self.static_in)}, current_epoch=self.epoch)
@@ -64,11 +84,20 @@ class GraphedTrainStep(object):
     def _load(self, inputs):
         for k, v in inputs.items():
             self.static_in[k].copy_(v, non_blocking=True)
+        self.inputs_consumed.record(torch.cuda.current_stream(self.trainer.device))
         left, right = self.model.draw_kappas(self.batch)
-        self.kappa_host['left'].copy_(torch.from_numpy(left.astype(np.float32)))
-        self.kappa_host['right'].copy_(torch.from_numpy(right.astype(np.float32)))
+        slot = self.kappa_slot
+        self.kappa_slot = (slot + 1) % self.KAPPA_RING
+        if self.kappa_done[slot] is not None:
+            self.kappa_done[slot].synchronize()     # the copy that last read this slot has run
+        host = self.kappa_host[slot]
+        host['left'].copy_(torch.from_numpy(left.astype(np.float32)))
+        host['right'].copy_(torch.from_numpy(right.astype(np.float32)))
         for s in ('left', 'right'):
-            self.model.kappa_buffers[s].copy_(self.kappa_host[s], non_blocking=True)
+            self.model.kappa_buffers[s].copy_(host[s], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.trainer.device))
+        self.kappa_done[slot] = ev
 
     def prefetch(self, inputs):
         """Start copying the NEXT step's inputs (pinned host tensors) into device staging buffers
@@ -90,7 +119,8 @@ class GraphedTrainStep(object):
     def __call__(self, inputs=None):
         """Run one optimisation step on ``inputs`` (host or device tensors with the example's
         shapes; None = the batch staged by ``prefetch()``); returns the loss as a 0-dim device
-        tensor (valid until the next call)."""
+        tensor (valid until the next call).  Host inputs are copied asynchronously: do not rewrite
+        pinned input tensors before ``self.inputs_consumed`` has completed."""
         if inputs is None:
             assert self.stage_in is not None, 'GraphedTrainStep: nothing was prefetched'
             main = torch.cuda.current_stream(self.trainer.device)
@@ -109,3 +139,6 @@ class GraphedTrainStep(object):
 
     def close(self):
         self.model.kappa_buffers = None
+        if self._pinned:
+            L.unpin_workspaces()
+            self._pinned = False

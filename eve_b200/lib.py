@@ -43,7 +43,7 @@ class AdamParams(C.Structure):
     _fields_ = [('count', C.c_longlong), ('lr', C.c_float), ('beta1', C.c_float),
                 ('beta2', C.c_float), ('eps', C.c_float), ('weight_decay', C.c_float),
                 ('max_norm', C.c_float), ('grad_scale', C.c_float), ('step', C.c_int),
-                ('step_dev', C.c_void_p)]
+                ('step_dev', C.c_void_p), ('lr_dev', C.c_void_p)]
 
 
 EYE_RNN_TYPES = {None: 0, 'RNN': 1, 'LSTM': 2, 'GRU': 3}
@@ -170,13 +170,34 @@ def require_cuda(t, what):
 
 
 _workspaces = {}
+_pins = 0          # captured CUDA graphs that have workspace pointers baked into their kernels
+_retired = []      # outgrown buffers kept alive while any such graph exists
 
 
 def workspace(nbytes, device, tag='ws'):
-    """A per-(device, tag) scratch buffer that only ever grows (stream-ordered reuse)."""
+    """A per-(device, tag) scratch buffer that only ever grows (stream-ordered reuse).
+
+    While a captured graph is registered (pin_workspaces) an outgrown buffer is NOT freed: the
+    graph's kernels keep writing into it on replay, so handing its memory back to the caching
+    allocator would corrupt whatever tensor receives it next."""
     key = (str(device), tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None and _pins > 0:
+            _retired.append(buf)
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
+
+
+def pin_workspaces():
+    """Called when a CUDA graph that uses the shared scratch buffers has been captured."""
+    global _pins
+    _pins += 1
+
+
+def unpin_workspaces():
+    global _pins
+    _pins = max(_pins - 1, 0)
+    if _pins == 0:
+        del _retired[:]

@@ -12,6 +12,21 @@ import torch
 from . import lib as L
 
 
+def _on_tensor_device(fn):
+    """Run an autograd.Function static method with the CUDA device of its first CUDA tensor
+    argument current (the library launches on the current device / its current stream)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(ctx, *args):
+        for a in args:
+            if torch.is_tensor(a) and a.is_cuda:
+                with torch.cuda.device(a.device):
+                    return fn(ctx, *args)
+        return fn(ctx, *args)
+    return wrapped
+
+
 def _f32c(t):
     if t is None:
         return None
@@ -32,6 +47,7 @@ class Conv2dFn(torch.autograd.Function):
     ConvRNN cell modules of models/common.py; the networks call the fused entries instead)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, weight, bias, stride, padding):
         L.require_cuda(x, 'conv2d')
         lib = L.load()
@@ -55,6 +71,7 @@ class Conv2dFn(torch.autograd.Function):
         return yh.permute(0, 3, 1, 2)
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dy):
         lib = L.load()
         xh, weight = ctx.saved_tensors
@@ -86,6 +103,7 @@ class EyeNetCnnFn(torch.autograd.Function):
     x [N,3,H,W] -> feat [N,nf]; weights in the order of include/eve_b200.h."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, nf, *weights):
         L.require_cuda(x, 'EyeNet CNN')
         lib = L.load()
@@ -108,6 +126,7 @@ class EyeNetCnnFn(torch.autograd.Function):
         return feat
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dfeat):
         lib = L.load()
         weights = ctx.saved_tensors
@@ -133,6 +152,7 @@ class EyeNetTailFn(torch.autograd.Function):
     g [S,T,2], pupil [S,T], hT, cT ([cells,S,nf] or None)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, feat, head_pose, h0, c0, cfg, *weights):
         L.require_cuda(feat, 'EyeNet tail')
         lib = L.load()
@@ -171,6 +191,7 @@ class EyeNetTailFn(torch.autograd.Function):
         return g, pupil, hT, cT
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dg, dpupil, dhT, dcT):
         lib = L.load()
         weights = ctx.saved_tensors
@@ -214,6 +235,7 @@ class RefineNetFn(torch.autograd.Function):
     out [B,T,1,72,128], hT, cT."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, screen, heatmap, h0, c0, cfg, *weights):
         L.require_cuda(heatmap, 'RefineNet')
         lib = L.load()
@@ -252,6 +274,7 @@ class RefineNetFn(torch.autograd.Function):
         return out, hT, cT
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dout, dhT, dcT):
         lib = L.load()
         weights = ctx.saved_tensors
@@ -281,6 +304,7 @@ class HeatmapFn(torch.autograd.Function):
     """batch_make_heatmaps (common.py:226-243): centres [n,2] px -> [n,1,H,W]."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, centres, sigma, size_wh, screen_wh):
         L.require_cuda(centres, 'make_heatmap')
         lib = L.load()
@@ -297,6 +321,7 @@ class HeatmapFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dout):
         lib = L.load()
         centres, = ctx.saved_tensors
@@ -311,6 +336,7 @@ class SoftArgmaxFn(torch.autograd.Function):
     """soft_argmax (common.py:294-323): heatmaps [n,1,H,W] -> PoG [n,2] px."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, heatmaps, screen_wh):
         L.require_cuda(heatmaps, 'soft_argmax')
         lib = L.load()
@@ -325,6 +351,7 @@ class SoftArgmaxFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dpog):
         lib = L.load()
         heatmaps, = ctx.saved_tensors
@@ -340,6 +367,7 @@ class PogFn(torch.autograd.Function):
     (origin, rotation and calibration are data)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, origin, g, rot, inv_cam, ppm, screen_wh):
         L.require_cuda(g, 'to_screen_coordinates')
         lib = L.load()
@@ -356,6 +384,7 @@ class PogFn(torch.autograd.Function):
         return mm, px
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dmm, dpx):
         lib = L.load()
         origin, g, rot, inv_cam, ppm = ctx.saved_tensors
@@ -371,14 +400,17 @@ class PogFn(torch.autograd.Function):
 
 # ------------------------------------------------------------------- fused optimiser --
 def adam_clip_step(params, grads, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8,
-                   weight_decay=0.0, max_norm=0.0, grad_scale=1.0, step_dev=None):
+                   weight_decay=0.0, max_norm=0.0, grad_scale=1.0, step_dev=None, lr_dev=None):
     """clip_grad_norm_ + Adam on flat fp32 buffers (training.py:492-502).  Returns the
     pre-clip gradient norm as a 1-element device tensor.  ``step_dev`` (int32 device tensor)
-    makes the kernel keep the step count itself, so the call can live in a CUDA graph."""
+    makes the kernel keep the step count itself, so the call can live in a CUDA graph;
+    ``lr_dev`` (1-element fp32 device tensor) overrides ``lr`` the same way, so that a
+    learning-rate schedule keeps working across replays."""
     lib = L.load()
     L.require_cuda(params, 'adam_clip_step')
     p = L.AdamParams(params.numel(), lr, betas[0], betas[1], eps, weight_decay, max_norm,
-                     grad_scale, int(step), None if step_dev is None else step_dev.data_ptr())
+                     grad_scale, int(step), None if step_dev is None else step_dev.data_ptr(),
+                     None if lr_dev is None else lr_dev.data_ptr())
     ws = L.workspace(lib.eve_adam_clip_workspace_bytes(C.byref(p)), params.device, 'adam')
     norm = torch.empty(1, dtype=torch.float32, device=params.device)
     L.check(lib.eve_adam_clip_step(C.byref(p), L.ptr(params), L.ptr(grads), L.ptr(exp_avg),

@@ -47,7 +47,11 @@ class FlatAdamTrainer(object):
                            for p, o, n in zip(self.params, self.offsets, self.sizes)]
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
-        self.lr = float(cfg.learning_rate if lr is None else lr)
+        self._lr = float(cfg.learning_rate if lr is None else lr)
+        # the kernel reads the rate from this device scalar: a scheduler (training.py:382-440)
+        # may change `trainer.lr` between replays of a captured step
+        self.lr_dev = torch.full((1,), self._lr, dtype=torch.float32, device=dev) \
+            if dev.type == 'cuda' else None
         self.weight_decay = float(cfg.weight_decay if weight_decay is None else weight_decay)
         self.betas, self.eps = betas, eps
         if max_norm is None:
@@ -63,6 +67,50 @@ class FlatAdamTrainer(object):
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev) if dev.type == 'cuda' else None
         self.device = dev
         self.last_grad_norm = None
+        # every rank must start from the same parameters (what DDP's constructor enforces)
+        if self.world > 1:
+            dist.broadcast(self.flat, src=0, group=self.group)
+
+    @property
+    def lr(self):
+        return self._lr
+
+    @lr.setter
+    def lr(self, value):
+        self._lr = float(value)
+        if self.lr_dev is not None:
+            self.lr_dev.fill_(self._lr)      # stream-ordered: takes effect for the next step
+
+    @property
+    def param_groups(self):
+        """Minimal torch.optim view for LR schedulers that write ``group['lr']``."""
+        trainer = self
+
+        class _Group(dict):
+            def __setitem__(self, key, value):
+                dict.__setitem__(self, key, value)
+                if key == 'lr':
+                    trainer.lr = value
+
+        return [_Group(lr=self._lr, weight_decay=self.weight_decay, betas=self.betas, eps=self.eps,
+                       params=self.params)]
+
+    def state_dict(self):
+        """Adam moments and step count (what CheckpointManager stores as optimizer_N.pt,
+        checkpoint_manager.py:70-72), keyed by position like torch.optim."""
+        return {'flat_exp_avg': self.exp_avg.detach().clone(),
+                'flat_exp_avg_sq': self.exp_avg_sq.detach().clone(),
+                'steps': int(self.steps), 'lr': self._lr, 'sizes': list(self.sizes)}
+
+    def load_state_dict(self, state):
+        if list(state['sizes']) != list(self.sizes):
+            raise ValueError('FlatAdamTrainer.load_state_dict: parameter layout mismatch')
+        self.exp_avg.copy_(state['flat_exp_avg'])
+        self.exp_avg_sq.copy_(state['flat_exp_avg_sq'])
+        self.steps = int(state['steps'])
+        if self.step_dev is not None:
+            self.step_dev.fill_(self.steps)
+        self.lr = state.get('lr', self._lr)
 
     def gather_grads(self):
         """Pack p.grad of every trainable parameter into the flat gradient buffer (one fused
@@ -89,9 +137,9 @@ class FlatAdamTrainer(object):
             self.last_grad_norm = update(self)
             return
         self.last_grad_norm = ops.adam_clip_step(
-            self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.steps, self.lr,
+            self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.steps, self._lr,
             self.betas, self.eps, self.weight_decay, self.max_norm, 1.0 / self.world,
-            step_dev=self.step_dev)
+            step_dev=self.step_dev, lr_dev=self.lr_dev)
 
     def step(self, loss, update=None):
         loss.backward()

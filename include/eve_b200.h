@@ -279,6 +279,8 @@ typedef struct {
   int step;         /* 1-based Adam step for bias correction (ignored when step_dev is set) */
   int* step_dev;    /* optional DEVICE counter: the kernel increments it and uses the new value as
                        the step -- lets one captured CUDA graph be replayed for every step */
+  const float* lr_dev; /* optional DEVICE scalar overriding `lr`: a learning-rate schedule
+                          (training.py:382-440,576) can update it between replays of one graph */
 } eve_adam_params;
 size_t eve_adam_clip_workspace_bytes(const eve_adam_params* p);
 int eve_adam_clip_step(const eve_adam_params* p, float* params, const float* grads, float* exp_avg,

@@ -55,6 +55,31 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def _worker_diverged(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from eve_b200.parallel import FlatAdamTrainer
+    model = Toy()
+    with torch.no_grad():           # ranks built under different seeds / checkpoints
+        for p in model.parameters():
+            p.add_(float(rank))
+    FlatAdamTrainer(model, lr=1e-2)
+    ret[rank] = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+    dist.destroy_process_group()
+
+
+def test_trainer_broadcasts_rank0_parameters():
+    """Replicas that start from different parameters would silently train diverged models: the
+    trainer broadcasts rank 0's flat buffer at construction (what DDP does)."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_diverged, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert torch.equal(ret[0], ret[1])
+    want = torch.cat([p.detach().reshape(-1) for p in Toy().parameters()])
+    assert torch.equal(ret[0], want)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))

@@ -37,6 +37,11 @@ def u16(n):
     return torch.empty(n, dtype=torch.int16, device='cuda')
 
 
+import os
+if os.environ.get('BENCH_IN_SHAPES'):
+    SHAPES = [tuple(int(v) for v in t.split('x')) for t in os.environ['BENCH_IN_SHAPES'].split(',')]
+
+
 def main(which):
     s = L.stream_ptr()
     print('%-18s %10s %10s %10s %10s' % ('shape', 'fused ms', 'GB/s', 'legacy ms', 'GB/s'))
