@@ -51,8 +51,8 @@ FLOP_SCREEN_FRAME = 9629761536.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=60)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='eve_refine', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=8, help='clips per GPU')
@@ -154,55 +154,63 @@ def run_reference_step(cfg, sd, B, T, seed, threads):
     return 2 * B * T, time.perf_counter() - t0
 
 
-def cpu_baseline(cfg, sd, budget_clips=(4, 15), iters=5):
-    import torch
-    threads = os.cpu_count() or 1
-    run_reference_step(cfg, sd, 1, 2, 1, threads)               # warm-up (oneDNN primitives)
-    B, T = budget_clips
+REF_BUDGET_S = 150.0     # timed CPU work of the reference arm (seconds)
+
+
+def _timed_reference_steps(cfg, sd, B, T, threads, want_steps, budget_s, min_steps):
+    """Warm-up (one tiny step for the oneDNN primitive caches, one full-size step that also sizes
+    the budget), then full-size fwd+bwd steps of the SAME B x T workload the B200 arm runs."""
+    run_reference_step(cfg, sd, 1, 2, 10, threads)
+    _, s0 = run_reference_step(cfg, sd, B, T, 11, threads)
+    k = max(min_steps, min(want_steps, int(budget_s / max(s0, 1e-3))))
     frames, sec = 0, 0.0
-    for i in range(iters):
-        f, s = run_reference_step(cfg, sd, B, T, 2 + i, threads)
+    for i in range(k):
+        f, s = run_reference_step(cfg, sd, B, T, 100 + i, threads)
         frames += f
         sec += s
+    return k, frames, sec
+
+
+def _reference_sample_text(B, T, threads, k, frames, sec):
+    import torch
+    return ('oracle/eve_oracle.py = CPU restatement of the reference PyTorch path (fp32, torch %s, '
+            '%d threads; the reference itself is pure Python without a build system and is not '
+            'present on the GPU box): warm-up (B=1,T=2 then one B=%d,T=%d step), then %d x fwd+bwd of '
+            'the full B=%d clips x T=%d frames workload = %d eye-frames in %.1f s'
+            % (torch.__version__, threads, B, T, k, B, T, frames, sec))
+
+
+def cpu_baseline(cfg, sd, B, T, budget_s=30.0):
+    threads = os.cpu_count() or 1
+    k, frames, sec = _timed_reference_steps(cfg, sd, B, T, threads, 2, budget_s, 1)
     return {'value': frames / sec, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-            'sample': 'oracle/eve_oracle.py (CPU restatement of the reference PyTorch path, fp32, '
-                      'torch %s, %d threads): 1 warm-up (B=1,T=2) then %d x fwd+bwd of B=%d clips x '
-                      'T=%d frames = %d eye-frames in %.1f s' % (torch.__version__, threads, iters,
-                                                                  B, T, frames, sec)}
+            'sample': _reference_sample_text(B, T, threads, k, frames, sec)}
 
 
 def reference_arm(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference
     is pure Python/PyTorch and is not present on the GPU box, so this is the oracle port
-    (kind "port"), on all host threads, same workload config, a bounded sample per step."""
+    (kind "port"), on all host threads, on the SAME config as the B200 arm (B x T per step);
+    the number of timed steps is bounded by REF_BUDGET_S of CPU work (at least 3)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    import torch
     cfg = configure(args.workload)
     sd = build_state_dict(cfg)
     threads = os.cpu_count() or 1
-    B, T = 2, 6                                                 # 24 eye-frames per step
-    for i in range(max(args.warmup, 1)):
-        run_reference_step(cfg, sd, 1 if i else B, 2 if i else T, 10 + i, threads)
-    frames = 0
-    sec = 0.0
-    for i in range(args.steps):
-        f, s = run_reference_step(cfg, sd, B, T, 100 + i, threads)
-        frames += f
-        sec += s
+    B, T = args.batch, args.seq_len
+    k, frames, sec = _timed_reference_steps(cfg, sd, B, T, threads, args.steps, REF_BUDGET_S, 3)
     value = frames / sec
-    sample = ('oracle port of the reference PyTorch CPU path (fp32, torch %s), %d threads; each '
-              'step = fwd+bwd of B=%d clips x T=%d frames (%d eye-frames), a bounded sample of '
-              'the B=%d x T=%d workload' % (torch.__version__, threads, B, T, 2 * B * T,
-                                            args.batch, args.seq_len))
+    sample = _reference_sample_text(B, T, threads, k, frames, sec)
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sec / args.steps,
+        'steps': k, 'steps_requested': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * sec / k,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
         'config': {'workload': WORKLOADS[args.workload]['desc'], 'global_batch': args.batch,
-                   'seq_len': args.seq_len, 'sample_per_step': 'B=%d,T=%d' % (B, T)},
+                   'seq_len': args.seq_len, 'eye_frames_per_step': 2 * B * T,
+                   'sample_per_step': 'B=%d,T=%d (the full workload)' % (B, T)},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                          'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -313,6 +321,141 @@ def profiled_eager_run(model, trainer, inputs_fn, steps, world, device):
     return ms, prof
 
 
+# ---------------------------------------------------------------- secondary measurements --
+def _event_ms(fn, reps, device, flush=None):
+    import torch
+    ms = 0.0
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize(device)
+        ms += a.elapsed_time(b)
+    return ms / reps
+
+
+def leg_t60(args, device):
+    """BASELINE configs[3] per-GPU shape: full EVE, seq_len=60, batch=8 (graph-replayed step)."""
+    import numpy as np
+    from eve_b200.graph import GraphedTrainStep
+    from eve_b200.models import EVE
+    from eve_b200.parallel import FlatAdamTrainer
+    cfg = configure('eve_refine')
+    np.random.seed(77)
+    model = EVE()
+    model.load_state_dict(build_state_dict(cfg), strict=True)
+    model = model.to(device).train()
+    trainer = FlatAdamTrainer(model)
+    B, T = args.batch, 60
+    dev = [{k: v.to(device) for k, v in make_batch(B, T, cfg, seed=500 + i, pinned=False).items()}
+           for i in range(2)]
+    step_fn = GraphedTrainStep(model, trainer, dev[0], warmup=3, tag='bench')
+    steps = 10
+    ms, _ = timed_graph_run(step_fn, lambda i: dev[i % 2], steps, 1, 1, device, False)
+    step_fn.close()
+    return {'workload': 'full EVE (EyeNet x2 + GazeRefineNet CGRU), seq_len=60, batch=%d clips '
+                        '(BASELINE configs[3], per-GPU shape)' % B,
+            'value': 2 * B * T * steps / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / steps,
+            'steps': steps}
+
+
+def leg_stream900(args, device):
+    """BASELINE configs[4]: inference-only RefineNet stream, seq_len=900, batch=1 (heatmap raster
+    + RefineNet with the ConvGRU state carried across all 900 frames + soft-argmax), screen
+    frames/s, next to the CPU oracle on a bounded sample of the same stream."""
+    import torch
+    from eve_b200 import synth
+    from eve_b200.models import RefineNet
+    from eve_b200.models.common import batch_make_heatmaps, soft_argmax
+    from oracle import eve_oracle as O      # CPU baseline of this leg only
+    cfg = configure('eve_refine')
+    T = 900
+    sd = synth.make_state_dict(synth.refine_net_param_shapes(cfg), 1000)
+    net = RefineNet()
+    net.load_state_dict(sd)
+    net = net.to(device).eval()
+    g = torch.Generator().manual_seed(0)
+    px = torch.stack([torch.rand(1, T, generator=g) * 1920, torch.rand(1, T, generator=g) * 1080], -1)
+    screen = torch.rand(1, T, 3, 72, 128, generator=g)
+    pxd, scd = px.to(device), screen.to(device)
+
+    def run():
+        with torch.no_grad():
+            hm = batch_make_heatmaps(pxd, cfg.gaze_heatmap_sigma_initial)
+            out, _, _ = net.sequence(scd, hm)
+            return soft_argmax(out.reshape(T, 1, 72, 128))
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize(device)
+    ms = _event_ms(run, 5, device)
+    n = 45
+    osd = {'refine_net.' + k: v for k, v in sd.items()}
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        hm = O.make_heatmaps(px[:, :n], cfg.gaze_heatmap_sigma_initial)
+        O.refine_net_sequence(osd, cfg, screen[:, :4], hm[:, :4])
+        t0 = time.perf_counter()
+        O.soft_argmax(O.refine_net_sequence(osd, cfg, screen[:, :n], hm).reshape(n, 1, 72, 128))
+        dt = time.perf_counter() - t0
+    return {'workload': 'inference-only RefineNet stream, seq_len=900, batch=1 (BASELINE configs[4])',
+            'value': T / (ms * 1e-3), 'unit': 'screen frames/s', 'ms_per_stream': ms,
+            'cpu_baseline': {'value': n / dt, 'unit': 'screen frames/s', 'cores': threads,
+                             'kind': 'port', 'sample': 'first %d frames of the stream, %.2f s' % (n, dt)}}
+
+
+def leg_stock_torch(args, device):
+    """The "existing Blackwell library path" (BASELINE.md section 3): the same training step written
+    in plain PyTorch ops (the oracle's time-batched restatement of the reference modules) running
+    on the B200 through stock cuDNN / cuBLAS, fp32 and TF32.  A baseline beside the product."""
+    import numpy as np
+    import torch
+    from eve_b200 import synth
+    from oracle import eve_oracle as O      # baseline leg only
+    cfg = configure(args.workload)
+    B, T = args.batch, args.seq_len
+    sd = {k: v.to(device).requires_grad_(True) for k, v in build_state_dict(cfg).items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=cfg.learning_rate, weight_decay=cfg.weight_decay)
+    inputs = {k: v.to(device) for k, v in synth.make_clip_batch(
+        B, T, seed=7, with_screen=bool(cfg.load_screen_content)).items()}
+    std = np.radians(cfg.refine_net_offset_augmentation_sigma)
+    kap = {s_: torch.from_numpy(np.random.normal(size=(B, 2), scale=std).astype(np.float32)).to(device)
+           for s_ in ('left', 'right')}
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out, _ = O.eve_forward(sd, cfg, inputs, True, kap)
+        out['full_loss'].backward()
+        torch.nn.utils.clip_grad_norm_(list(sd.values()), cfg.gradient_clip_amount)
+        opt.step()
+
+    res = {'workload': WORKLOADS[args.workload]['desc'],
+           'what': 'plain PyTorch ops (torch %s, cuDNN %s) on the same B200, same B=%d x T=%d step '
+                   '(fwd + bwd + clip + Adam), time-batched like the product'
+                   % (torch.__version__, torch.backends.cudnn.version(), B, T), 'unit': UNIT}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32,
+           torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=device)
+    try:
+        for name, tf32 in (('fp32', False), ('tf32', True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize(device)
+            ms = _event_ms(step, 5, device, flush)
+            res[name] = {'value': 2 * B * T / (ms * 1e-3), 'ms_per_step': ms}
+    finally:
+        (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32,
+         torch.backends.cudnn.benchmark) = old
+    return res
+
+
 def b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -397,9 +540,19 @@ def b200_arm(args):
     if not args.no_extra:
         other = 'eyenet_static' if args.workload == 'eve_refine' else 'eve_refine'
         torch.cuda.empty_cache()
-        ex = measure(other, args.steps, args.warmup, False, False)
-        extra = {'workload': WORKLOADS[other]['desc'], 'value': ex['value'], 'unit': UNIT,
-                 'ms_per_step': ex['ms'] / args.steps}
+        ex_steps = min(args.steps, 20)
+        ex = measure(other, ex_steps, args.warmup, False, False)
+        extra = {'other_workload': {'workload': WORKLOADS[other]['desc'], 'value': ex['value'],
+                                    'unit': UNIT, 'ms_per_step': ex['ms'] / ex_steps}}
+        torch.cuda.empty_cache()
+        if world == 1 and rank == 0:
+            for name, fn in (('t60', leg_t60), ('stream900', leg_stream900),
+                             ('stock_torch_b200', leg_stock_torch)):
+                try:
+                    extra[name] = fn(args, device)
+                except Exception as e:      # a baseline leg must never take the headline down
+                    extra[name] = {'error': '%s: %s' % (type(e).__name__, e)}
+                torch.cuda.empty_cache()
     cfg = configure(args.workload)
 
     if rank != 0:
@@ -472,7 +625,7 @@ def b200_arm(args):
     if extra is not None:
         out['also'] = extra
     if world == 1 and not args.no_cpu_baseline:
-        out['cpu_baseline'] = cpu_baseline(cfg, build_state_dict(cfg))
+        out['cpu_baseline'] = cpu_baseline(cfg, build_state_dict(cfg), args.batch, args.seq_len)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

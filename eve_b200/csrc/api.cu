@@ -325,6 +325,17 @@ extern "C" int eve_instnorm_fused_bwd(const float* dy, const float* dy2, const f
                       false, (float*)workspace, as_stream(stream));
 }
 
+extern "C" int eve_in_relu_maxpool_fwd(const float* x, int n, int h, int w, int c, float* mean,
+                                       float* rstd, float* y, int32_t* idx, eve_stream_t stream) {
+  EVE_REQUIRE(x && mean && rstd && y && idx, EVE_ERR_NULL, "in_relu_maxpool_fwd: NULL pointer");
+  EVE_REQUIRE(n >= 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0, EVE_ERR_SHAPE,
+              "in_relu_maxpool_fwd: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
+  if (n == 0) return EVE_OK;
+  cudaStream_t s = as_stream(stream);
+  EVE_TRY(in_stats(x, n, h * w, c, mean, rstd, s));
+  return in_relu_maxpool(x, n, h, w, c, mean, rstd, y, idx, s);
+}
+
 extern "C" int eve_adaptive_maxpool_fwd(const float* x, int n, int h, int w, int c, int oh, int ow,
                                         float* y, int32_t* idx, eve_stream_t stream) {
   EVE_REQUIRE(x && y && idx, EVE_ERR_NULL, "adaptive_maxpool_fwd: NULL pointer");

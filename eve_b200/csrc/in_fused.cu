@@ -9,9 +9,9 @@
 // one (image, channel group): its CTAs stage disjoint pixel ranges of the group in shared memory
 // with cp.async, reduce the per-channel sums across the cluster through distributed shared memory
 // in a fixed order (deterministic, independent of the batch size) and then normalise straight out
-// of shared memory.  The clusters are PERSISTENT and the staging is double buffered: while item i
-// is reduced, synchronised and written back, the cp.async loads of item i+1 are already in flight,
-// so the HBM read stream never waits for the cluster barriers.  Outputs
+// of shared memory.  (A persistent, double-buffered variant was measured slower: the kernels are
+// bound by instruction issue and occupancy, not by exposed load latency -- profiles/README.)
+// Outputs
 //   forward : the consuming convolution's 16-bit hi/lo operand planes (two affine sets from one
 //             read when a block has a skip convolution), optionally the fp32 tensor;
 //   backward: dx as fp32 and/or as the bf16 hi/lo planes the preceding convolution's gradients
@@ -37,7 +37,8 @@ namespace eve {
 namespace {
 
 constexpr float kEps = 1e-5f;
-constexpr int kThr = 256;
+constexpr int kThr = 512;                    // 16 warps per CTA
+constexpr int kWarps = kThr / 32;
 constexpr int kMaxQ = 64;                    // channel quads per CTA (<= 256 channels)
 constexpr size_t kSmemTwo = 100 * 1024;      // staging bytes per CTA that still allow two CTAs per SM
 constexpr size_t kSmemOne = 200 * 1024;      // ... one CTA per SM
@@ -46,47 +47,41 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() {
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-// wait until at most `pending` of this thread's most recent groups are still in flight
-__device__ __forceinline__ void cp_async_wait(int pending) {
-  if (pending > 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
-  else asm volatile("cp.async.wait_group 0;" ::: "memory");
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-__device__ __forceinline__ float act_fwd(float v, int act) {
-  if (act == ACT_RELU) return v > 0.f ? v : 0.f;
-  if (act == ACT_LEAKY) return v > 0.f ? v : 0.01f * v;
-  return v;
+// activations as one select: slope = 0 (ReLU), 0.01 (LeakyReLU), 1 (none)
+__host__ __device__ __forceinline__ float act_slope(int act) {
+  return act == ACT_RELU ? 0.f : (act == ACT_LEAKY ? 0.01f : 1.f);
 }
-__device__ __forceinline__ float act_grad(float y, int act) {
-  if (act == ACT_RELU) return y > 0.f ? 1.f : 0.f;
-  if (act == ACT_LEAKY) return y > 0.f ? 1.f : 0.01f;
-  return 1.f;
-}
+__device__ __forceinline__ float act_apply(float v, float slope) { return v > 0.f ? v : v * slope; }
+__device__ __forceinline__ float act_deriv(float y, float slope) { return y > 0.f ? 1.f : slope; }
 
+// x ~ hi + lo as two 16-bit values each; four elements at a time with the packed converts
 template <int FMT>
 __device__ __forceinline__ void split4(const float* o, uint2& hi, uint2& lo) {
-  uint16_t h[4], l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (FMT == TC_BF16) {
-      __nv_bfloat16 hb = __float2bfloat16_rn(o[j]);
-      h[j] = __bfloat16_as_ushort(hb);
-      l[j] = __bfloat16_as_ushort(__float2bfloat16_rn(o[j] - __bfloat162float(hb)));
-    } else {
-      __half hh = __float2half_rn(o[j]);
-      h[j] = __half_as_ushort(hh);
-      l[j] = __half_as_ushort(__float2half_rn(o[j] - __half2float(hh)));
-    }
+  if (FMT == TC_BF16) {
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(o[0], o[1]);
+    const __nv_bfloat162 h23 = __floats2bfloat162_rn(o[2], o[3]);
+    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+    const __nv_bfloat162 l01 = __floats2bfloat162_rn(o[0] - f01.x, o[1] - f01.y);
+    const __nv_bfloat162 l23 = __floats2bfloat162_rn(o[2] - f23.x, o[3] - f23.y);
+    hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+  } else {
+    const __half2 h01 = __floats2half2_rn(o[0], o[1]);
+    const __half2 h23 = __floats2half2_rn(o[2], o[3]);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(o[0] - f01.x, o[1] - f01.y);
+    const __half2 l23 = __floats2half2_rn(o[2] - f23.x, o[3] - f23.y);
+    hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
   }
-  hi = *reinterpret_cast<uint2*>(h);
-  lo = *reinterpret_cast<uint2*>(l);
 }
 
 // ------------------------------------------------------------------------- decomposition --
-// Depends on (C, HW, staging buffers) only -- never on N -- so that a frame's statistics are
+// Depends on (C, HW, staged tensors) only -- never on N -- so that a frame's statistics are
 // bit-identical whatever batch it is processed in.
 struct FusedPlan {
   int CG, Q, CS, ppc;
@@ -95,8 +90,8 @@ int max_cluster() {           // tuning knob (environment, read once)
   static int v = 0;
   if (!v) {
     const char* e = getenv("EVE_B200_IN_MAXCS");
-    v = e ? atoi(e) : 16;
-    if (v != 1 && v != 2 && v != 4 && v != 8 && v != 16) v = 16;
+    v = e ? atoi(e) : 8;
+    if (v != 1 && v != 2 && v != 4 && v != 8 && v != 16) v = 8;
   }
   return v;
 }
@@ -109,14 +104,14 @@ size_t smem_two() {
   }
   return v;
 }
-// bufs: slice-sized staging buffers the kernel keeps (forward 2 x tensors, backward 4)
-bool plan_fused(int C, int HW, int bufs, FusedPlan& p) {
+// tensors: fp32 slices the kernel stages (forward 1 or 2, backward 2)
+bool plan_fused(int C, int HW, int tensors, FusedPlan& p) {
   if (C % 4 != 0 || C < 4 || HW < 1) return false;
-  auto bytes = [&](int cg_, int cs_) { return (size_t)cdiv(HW, cs_) * cg_ * 4 * bufs; };
+  auto bytes = [&](int cg_, int cs_) { return (size_t)cdiv(HW, cs_) * cg_ * 4 * tensors; };
   const int maxcs = max_cluster();
   const int top = C < 4 * kMaxQ ? C : 4 * kMaxQ;
   // 1) groups of >= 16 channels (64-byte pieces), two CTAs per SM; 2) the same with one CTA per
-  // SM; 3) 8-channel groups (one 32-byte sector per pixel: measurably worse DRAM efficiency)
+  // SM; 3) / 4) 8-channel groups (one 32-byte sector per pixel: measurably worse DRAM efficiency)
   for (int stage = 0; stage < 4; ++stage) {
     const size_t budget = (stage & 1) ? kSmemOne : smem_two();
     const int min_cg = stage < 2 ? (C < 16 ? C : 16) : (C < 8 ? C : 8);
@@ -133,8 +128,8 @@ bool plan_fused(int C, int HW, int bufs, FusedPlan& p) {
 }
 
 // Sum v[0..3] over all threads that own the same channel quad q (thread t: q = t % Q, pixel lane
-// t / Q).  The totals land in out[q*4 + j], valid after the call (ends with __syncthreads()).
-// Fixed order -> deterministic.  wred: kThr*4 elements of scratch.
+// t / Q).  The totals land in out[q*4 + j] (t < 4Q), valid after the call (ends with
+// __syncthreads()).  Fixed order -> deterministic.  wred: kThr*4 elements of scratch.
 template <typename T>
 __device__ __forceinline__ void quad_reduce(T* v, int Q, int L, T* wred, T* out) {
   const int t = threadIdx.x, warp = t >> 5, ln = t & 31;
@@ -153,7 +148,7 @@ __device__ __forceinline__ void quad_reduce(T* v, int Q, int L, T* wred, T* out)
       const int q = t >> 2, j = t & 3;
       T s = (T)0;
 #pragma unroll
-      for (int w = 0; w < kThr / 32; ++w) s += wred[(w * 32 + q) * 4 + j];
+      for (int w = 0; w < kWarps; ++w) s += wred[(w * 32 + q) * 4 + j];
       out[t] = s;
     }
   } else {
@@ -173,192 +168,171 @@ __device__ __forceinline__ void quad_reduce(T* v, int Q, int L, T* wred, T* out)
 // ================================================================================ forward ==
 struct InFwdArgs {
   const float* x;
-  const float* x2;       // x2_mode 1: residual added after the affine; 2: second normalised input
-  int x2_mode;
-  int N, HW, C, Q, CS, ppc;
+  const float* x2;       // MODE 1: residual added after the affine; 2: second normalised input
+  int HW, C, Q, CS, ppc;
   const float *gamma, *beta, *gammaB, *betaB;
-  int act;
+  float slope;                          // activation
   float *mean, *rstd, *mean2, *rstd2;   // [N, C]
   float* y;                             // fp32 result (optional)
   uint16_t *hiA, *loA, *hiB, *loB;      // operand planes (A optional, B optional)
 };
 
-// grid CS * clusters (1-D), cluster (CS, 1, 1), block 256.  Cluster k walks the work items
-// k, k + clusters, ... (item = image * groups + channel group).  Thread t owns channel quad
-// q = t % Q of the pixels lane, lane + L, ... (lane = t / Q, L = 256 / Q) of its CTA's pixel range
-// in every phase.
-template <int FMT>
-__global__ void __launch_bounds__(kThr, 2)
+// grid (CS, C/CG, N), cluster (CS, 1, 1), block 512.  Thread t owns channel quad q = t % Q of the
+// pixels lane, lane + L, ... (lane = t / Q, L = 512 / Q) of its CTA's pixel range in every phase.
+template <int FMT, int MODE>
+__global__ void __launch_bounds__(kThr)
 in_fwd_fused_kernel(const InFwdArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
-  const int cid = blockIdx.x / a.CS, ncl = gridDim.x / a.CS;
+  const int rank = blockIdx.x, cgi = blockIdx.y, n = blockIdx.z;
   const int Q = a.Q, C4 = a.C >> 2;
-  const int ncg = C4 / Q;
-  const int total = a.N * ncg;
-  const int two = a.x2_mode == 2 ? 1 : 0;
+  constexpr bool two = MODE == 2;
   const int p0 = rank * a.ppc;
   const int np = max(0, min(a.HW, p0 + a.ppc) - p0);
-  const size_t slice = (size_t)a.ppc * Q;
-  float4* sbuf = reinterpret_cast<float4*>(smraw);            // [2 buffers][1 + two][slice]
-  float* wred = reinterpret_cast<float*>(sbuf + 2 * (1 + two) * slice);   // [kThr*4]
-  float* cpart = wred + kThr * 4;        // [2 passes][2 tensors][kThr]
-  float* stat = cpart + 4 * kThr;        // mean, rstd, mean2, rstd2: [4][kThr] (index q*4+j)
+  const int slice = a.ppc * Q;
+  float4* sx = reinterpret_cast<float4*>(smraw);
+  float4* sx2 = sx + slice;
+  float* wred = reinterpret_cast<float*>(sx2 + (two ? slice : 0));   // [kThr*4]
+  float* cpart = wred + kThr * 4;        // [2 passes][2 tensors][4*kMaxQ]
+  float* stat = cpart + 4 * 4 * kMaxQ;   // mean, rstd, mean2, rstd2: [4][4*kMaxQ] (index q*4+j)
+  constexpr int kS = 4 * kMaxQ;
 
   const int L = kThr / Q;
   const int q = threadIdx.x % Q, lane = threadIdx.x / Q;
   const bool active = lane < L;
+  const int step_s = L * Q;                       // smem stride (float4) between a thread's pixels
+  const size_t step_g = (size_t)L * C4;           // global stride
+  const size_t goff = ((size_t)n * a.HW + p0 + lane) * C4 + (size_t)cgi * Q + q;
+  const int s0 = lane * Q + q;
+  if (active) {
+    const float4* gx = reinterpret_cast<const float4*>(a.x) + goff;
+    float4* d = sx + s0;
+    for (int p = lane; p < np; p += L, gx += step_g, d += step_s) cp_async16(d, gx);
+    if (two) {
+      const float4* gx2 = reinterpret_cast<const float4*>(a.x2) + goff;
+      float4* d2 = sx2 + s0;
+      for (int p = lane; p < np; p += L, gx2 += step_g, d2 += step_s) cp_async16(d2, gx2);
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
   const float inv = 1.f / (float)a.HW;
-
-  auto item_off = [&](int item) -> size_t {     // float4 offset of this thread's first element
-    const int n = item / ncg, cgi = item - n * ncg;
-    return ((size_t)n * a.HW + p0) * C4 + (size_t)cgi * Q + q;
-  };
-  auto issue = [&](int item, int b) {
+  // ---- pass 0: mean; pass 1: variance about the mean (exact two-pass: the data sits in smem)
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     if (active) {
-      const size_t go = item_off(item);
-      float4* d = sbuf + (size_t)b * (1 + two) * slice;
-      const float4* gx = reinterpret_cast<const float4*>(a.x) + go;
-      for (int p = lane; p < np; p += L) cp_async16(&d[p * Q + q], gx + (size_t)p * C4);
-      if (two) {
-        const float4* gx2 = reinterpret_cast<const float4*>(a.x2) + go;
-        for (int p = lane; p < np; p += L) cp_async16(&d[slice + p * Q + q], gx2 + (size_t)p * C4);
+      const float4* d = sx + s0;
+      const float4* d2 = sx2 + s0;
+      if (pass == 0) {
+        for (int p = lane; p < np; p += L, d += step_s, d2 += step_s) {
+          const float4 v = *d;
+          s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+          if (two) {
+            const float4 u = *d2;
+            s2[0] += u.x; s2[1] += u.y; s2[2] += u.z; s2[3] += u.w;
+          }
+        }
+      } else {
+        const float4 m = reinterpret_cast<const float4*>(stat)[q];
+        const float4 m2 = reinterpret_cast<const float4*>(stat + 2 * kS)[q];
+        for (int p = lane; p < np; p += L, d += step_s, d2 += step_s) {
+          float4 v = *d;
+          v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
+          s[0] = fmaf(v.x, v.x, s[0]); s[1] = fmaf(v.y, v.y, s[1]);
+          s[2] = fmaf(v.z, v.z, s[2]); s[3] = fmaf(v.w, v.w, s[3]);
+          if (two) {
+            float4 u = *d2;
+            u.x -= m2.x; u.y -= m2.y; u.z -= m2.z; u.w -= m2.w;
+            s2[0] = fmaf(u.x, u.x, s2[0]); s2[1] = fmaf(u.y, u.y, s2[1]);
+            s2[2] = fmaf(u.z, u.z, s2[2]); s2[3] = fmaf(u.w, u.w, s2[3]);
+          }
+        }
       }
     }
-    cp_async_commit();
-  };
-
-  int b = 0;
-  if (cid < total) issue(cid, 0);
-  for (int item = cid; item < total; item += ncl, b ^= 1) {
-    const int nxt = item + ncl;
-    if (nxt < total) issue(nxt, b ^ 1);          // prefetch the next item behind this one
-    cp_async_wait(nxt < total ? 1 : 0);
+    quad_reduce<float>(s, Q, L, wred, cpart + (pass * 2 + 0) * kS);
+    if (two) quad_reduce<float>(s2, Q, L, wred, cpart + (pass * 2 + 1) * kS);
+    cluster.sync();
+    if (threadIdx.x < Q * 4) {      // fixed order over the cluster ranks: same result in every CTA
+      float t = 0.f, t2 = 0.f;
+      for (int r = 0; r < a.CS; ++r) {
+        const float* rp = cluster.map_shared_rank(cpart, r);
+        t += rp[(pass * 2 + 0) * kS + threadIdx.x];
+        if (two) t2 += rp[(pass * 2 + 1) * kS + threadIdx.x];
+      }
+      if (pass == 0) {
+        stat[threadIdx.x] = t * inv;
+        stat[2 * kS + threadIdx.x] = t2 * inv;
+      } else {
+        stat[kS + threadIdx.x] = rsqrtf(t * inv + kEps);
+        stat[3 * kS + threadIdx.x] = rsqrtf(t2 * inv + kEps);
+      }
+    }
     __syncthreads();
-    const float4* sx = sbuf + (size_t)b * (1 + two) * slice;
-    const float4* sx2 = sx + slice;
-    const int n = item / ncg, cgi = item - n * ncg;
-    // ---- pass 0: mean; pass 1: variance about the mean (exact two-pass: the data sits in smem)
-    for (int pass = 0; pass < 2; ++pass) {
-      float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-      if (active) {
-        if (pass == 0) {
-          for (int p = lane; p < np; p += L) {
-            const float4 v = sx[p * Q + q];
-            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-            if (two) {
-              const float4 u = sx2[p * Q + q];
-              s2[0] += u.x; s2[1] += u.y; s2[2] += u.z; s2[3] += u.w;
-            }
-          }
-        } else {
-          const float4 m = reinterpret_cast<const float4*>(stat)[q];
-          const float4 m2 = reinterpret_cast<const float4*>(stat + 2 * kThr)[q];
-          for (int p = lane; p < np; p += L) {
-            float4 v = sx[p * Q + q];
-            v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
-            s[0] = fmaf(v.x, v.x, s[0]); s[1] = fmaf(v.y, v.y, s[1]);
-            s[2] = fmaf(v.z, v.z, s[2]); s[3] = fmaf(v.w, v.w, s[3]);
-            if (two) {
-              float4 u = sx2[p * Q + q];
-              u.x -= m2.x; u.y -= m2.y; u.z -= m2.z; u.w -= m2.w;
-              s2[0] = fmaf(u.x, u.x, s2[0]); s2[1] = fmaf(u.y, u.y, s2[1]);
-              s2[2] = fmaf(u.z, u.z, s2[2]); s2[3] = fmaf(u.w, u.w, s2[3]);
-            }
-          }
-        }
-      }
-      quad_reduce<float>(s, Q, L, wred, cpart + (pass * 2 + 0) * kThr);
-      if (two) quad_reduce<float>(s2, Q, L, wred, cpart + (pass * 2 + 1) * kThr);
-      // The pass-p partials of item i are rewritten for item i+1 only after the OTHER pass's
-      // barrier of item i / i+1, by which every peer has finished reading them.
-      cluster.sync();
-      if (threadIdx.x < Q * 4) {    // fixed order over the cluster ranks: same result in every CTA
-        float t = 0.f, t2 = 0.f;
-        for (int r = 0; r < a.CS; ++r) {
-          const float* rp = cluster.map_shared_rank(cpart, r);
-          t += rp[(pass * 2 + 0) * kThr + threadIdx.x];
-          if (two) t2 += rp[(pass * 2 + 1) * kThr + threadIdx.x];
-        }
-        if (pass == 0) {
-          stat[threadIdx.x] = t * inv;
-          stat[2 * kThr + threadIdx.x] = t2 * inv;
-        } else {
-          stat[kThr + threadIdx.x] = rsqrtf(t * inv + kEps);
-          stat[3 * kThr + threadIdx.x] = rsqrtf(t2 * inv + kEps);
-        }
-      }
-      __syncthreads();
+  }
+  if (rank == 0 && threadIdx.x < Q * 4) {
+    const size_t so = (size_t)n * a.C + (size_t)cgi * Q * 4 + threadIdx.x;
+    a.mean[so] = stat[threadIdx.x];
+    a.rstd[so] = stat[kS + threadIdx.x];
+    if (two) {
+      a.mean2[so] = stat[2 * kS + threadIdx.x];
+      a.rstd2[so] = stat[3 * kS + threadIdx.x];
     }
-    if (rank == 0 && threadIdx.x < Q * 4) {
-      const size_t so = (size_t)n * a.C + (size_t)cgi * Q * 4 + threadIdx.x;
-      a.mean[so] = stat[threadIdx.x];
-      a.rstd[so] = stat[kThr + threadIdx.x];
-      if (two) {
-        a.mean2[so] = stat[2 * kThr + threadIdx.x];
-        a.rstd2[so] = stat[3 * kThr + threadIdx.x];
-      }
-    }
+  }
 
-    // ---- normalise out of shared memory
-    if (active) {
-      const int c = (cgi * Q + q) * 4;
-      const size_t goff = item_off(item);
-      const float4 m = reinterpret_cast<const float4*>(stat)[q];
-      const float4 r = reinterpret_cast<const float4*>(stat + kThr)[q];
-      const float4 m2 = reinterpret_cast<const float4*>(stat + 2 * kThr)[q];
-      const float4 r2 = reinterpret_cast<const float4*>(stat + 3 * kThr)[q];
-      float4 gA = make_float4(1.f, 1.f, 1.f, 1.f), bA = make_float4(0.f, 0.f, 0.f, 0.f), gB = gA, bB = bA;
-      if (a.gamma) {
-        gA = *reinterpret_cast<const float4*>(a.gamma + c);
-        bA = *reinterpret_cast<const float4*>(a.beta + c);
+  // ---- normalise out of shared memory
+  if (active) {
+    const int c = (cgi * Q + q) * 4;
+    const float4 m = reinterpret_cast<const float4*>(stat)[q];
+    const float4 r = reinterpret_cast<const float4*>(stat + kS)[q];
+    const float4 m2 = reinterpret_cast<const float4*>(stat + 2 * kS)[q];
+    const float4 r2 = reinterpret_cast<const float4*>(stat + 3 * kS)[q];
+    float4 gA = make_float4(1.f, 1.f, 1.f, 1.f), bA = make_float4(0.f, 0.f, 0.f, 0.f), gB = gA, bB = bA;
+    if (a.gamma) {
+      gA = *reinterpret_cast<const float4*>(a.gamma + c);
+      bA = *reinterpret_cast<const float4*>(a.beta + c);
+    }
+    const bool hasB = a.hiB != nullptr;
+    if (hasB) {
+      gB = *reinterpret_cast<const float4*>(a.gammaB + c);
+      bB = *reinterpret_cast<const float4*>(a.betaB + c);
+    }
+    const float slope = a.slope;
+    const float4* d = sx + s0;
+    const float4* d2 = sx2 + s0;
+    size_t go = goff;
+    for (int p = lane; p < np; p += L, d += step_s, d2 += step_s, go += step_g) {
+      const float4 v = *d;
+      const float xh[4] = {(v.x - m.x) * r.x, (v.y - m.y) * r.y, (v.z - m.z) * r.z, (v.w - m.w) * r.w};
+      float o[4] = {fmaf(xh[0], gA.x, bA.x), fmaf(xh[1], gA.y, bA.y), fmaf(xh[2], gA.z, bA.z),
+                    fmaf(xh[3], gA.w, bA.w)};
+      if (MODE == 2) {
+        const float4 u = *d2;
+        o[0] += (u.x - m2.x) * r2.x; o[1] += (u.y - m2.y) * r2.y;
+        o[2] += (u.z - m2.z) * r2.z; o[3] += (u.w - m2.w) * r2.w;
+      } else if (MODE == 1) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(a.x2) + go);
+        o[0] += u.x; o[1] += u.y; o[2] += u.z; o[3] += u.w;
       }
-      if (a.hiB) {
-        gB = *reinterpret_cast<const float4*>(a.gammaB + c);
-        bB = *reinterpret_cast<const float4*>(a.betaB + c);
-      }
-      const float4* gres = a.x2_mode == 1 ? reinterpret_cast<const float4*>(a.x2) + goff : nullptr;
-      for (int p = lane; p < np; p += L) {
-        const float4 v = sx[p * Q + q];
-        const float xh[4] = {(v.x - m.x) * r.x, (v.y - m.y) * r.y, (v.z - m.z) * r.z, (v.w - m.w) * r.w};
-        float add[4] = {0.f, 0.f, 0.f, 0.f};
-        const size_t go = goff + (size_t)p * C4;
-        if (two) {
-          const float4 u = sx2[p * Q + q];
-          add[0] = (u.x - m2.x) * r2.x; add[1] = (u.y - m2.y) * r2.y;
-          add[2] = (u.z - m2.z) * r2.z; add[3] = (u.w - m2.w) * r2.w;
-        } else if (gres) {
-          const float4 u = __ldg(gres + (size_t)p * C4);
-          add[0] = u.x; add[1] = u.y; add[2] = u.z; add[3] = u.w;
-        }
-        float o[4];
-        if (a.gamma) {
-          o[0] = fmaf(xh[0], gA.x, bA.x); o[1] = fmaf(xh[1], gA.y, bA.y);
-          o[2] = fmaf(xh[2], gA.z, bA.z); o[3] = fmaf(xh[3], gA.w, bA.w);
-        } else {
-          o[0] = xh[0]; o[1] = xh[1]; o[2] = xh[2]; o[3] = xh[3];
-        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = act_fwd(o[j] + add[j], a.act);
-        if (a.y) reinterpret_cast<float4*>(a.y)[go] = make_float4(o[0], o[1], o[2], o[3]);
-        if (a.hiA) {
-          uint2 h, l;
-          split4<FMT>(o, h, l);
-          reinterpret_cast<uint2*>(a.hiA)[go] = h;
-          reinterpret_cast<uint2*>(a.loA)[go] = l;
-        }
-        if (a.hiB) {
-          const float ob[4] = {act_fwd(fmaf(xh[0], gB.x, bB.x), a.act), act_fwd(fmaf(xh[1], gB.y, bB.y), a.act),
-                               act_fwd(fmaf(xh[2], gB.z, bB.z), a.act), act_fwd(fmaf(xh[3], gB.w, bB.w), a.act)};
-          uint2 h, l;
-          split4<FMT>(ob, h, l);
-          reinterpret_cast<uint2*>(a.hiB)[go] = h;
-          reinterpret_cast<uint2*>(a.loB)[go] = l;
-        }
+      for (int j = 0; j < 4; ++j) o[j] = act_apply(o[j], slope);
+      if (a.y) reinterpret_cast<float4*>(a.y)[go] = make_float4(o[0], o[1], o[2], o[3]);
+      if (a.hiA) {
+        uint2 h, l;
+        split4<FMT>(o, h, l);
+        reinterpret_cast<uint2*>(a.hiA)[go] = h;
+        reinterpret_cast<uint2*>(a.loA)[go] = l;
+      }
+      if (hasB) {
+        const float ob[4] = {act_apply(fmaf(xh[0], gB.x, bB.x), slope), act_apply(fmaf(xh[1], gB.y, bB.y), slope),
+                             act_apply(fmaf(xh[2], gB.z, bB.z), slope), act_apply(fmaf(xh[3], gB.w, bB.w), slope)};
+        uint2 h, l;
+        split4<FMT>(ob, h, l);
+        reinterpret_cast<uint2*>(a.hiB)[go] = h;
+        reinterpret_cast<uint2*>(a.loB)[go] = l;
       }
     }
-    __syncthreads();    // this staging buffer is refilled by the prefetch of the next iteration
   }
   cluster.sync();     // nobody leaves while a peer may still read its partial sums
 }
@@ -374,9 +348,9 @@ struct InBwdArgs {
   const float* dy2;
   const float* ymask;     // saved forward output (residual case); null: recompute xhat*gamma+beta
   const float* x;
-  int N, HW, C, Q, CS, ppc;
+  int HW, C, Q, CS, ppc;
   const float *mean, *rstd, *gamma, *beta, *gamma2, *beta2;
-  int act;
+  float slope;
   const float* addend;
   float* dx;
   uint16_t *dx_hi, *dx_lo;
@@ -385,194 +359,190 @@ struct InBwdArgs {
   float* colpart;                              // [N * CS][C] column sums of dx (optional)
 };
 
-__global__ void __launch_bounds__(kThr, 2)
+template <bool DUAL>
+__global__ void __launch_bounds__(kThr)
 in_bwd_fused_kernel(const InBwdArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
-  const int cid = blockIdx.x / a.CS, ncl = gridDim.x / a.CS;
+  const int rank = blockIdx.x, cgi = blockIdx.y, n = blockIdx.z;
   const int Q = a.Q, C4 = a.C >> 2;
-  const int ncg = C4 / Q;
-  const int total = a.N * ncg;
-  const int dual = a.dy2 != nullptr;
   const int p0 = rank * a.ppc;
   const int np = max(0, min(a.HW, p0 + a.ppc) - p0);
-  const size_t slice = (size_t)a.ppc * Q;
-  float4* sbuf = reinterpret_cast<float4*>(smraw);                 // [2 buffers][dy/G, x/xhat][slice]
-  double* wred = reinterpret_cast<double*>(sbuf + 4 * slice);      // [kThr*4]
-  double* cpart = wred + kThr * 4;                                 // [2 parities][4 sums][kThr]
-  float* tot = reinterpret_cast<float*>(cpart + 8 * kThr);         // A, B: [2][kThr]
+  const int slice = a.ppc * Q;
+  float4* sg = reinterpret_cast<float4*>(smraw);                  // dy, then G
+  float4* sx = sg + slice;                                        // x, then xhat
+  double* wred = reinterpret_cast<double*>(sx + slice);           // [kThr*4]
+  double* cpart = wred + kThr * 4;                                // [4 sums][4*kMaxQ] (index q*4+j)
+  float* tot = reinterpret_cast<float*>(cpart + 4 * 4 * kMaxQ);   // A, B: [2][4*kMaxQ]
+  constexpr int kS = 4 * kMaxQ;
 
   const int L = kThr / Q;
   const int q = threadIdx.x % Q, lane = threadIdx.x / Q;
   const bool active = lane < L;
-
-  auto item_off = [&](int item) -> size_t {
-    const int n = item / ncg, cgi = item - n * ncg;
-    return ((size_t)n * a.HW + p0) * C4 + (size_t)cgi * Q + q;
-  };
-  auto issue = [&](int item, int b) {
-    if (active) {
-      const size_t go = item_off(item);
-      float4* d = sbuf + (size_t)b * 2 * slice;
-      const float4* gd = reinterpret_cast<const float4*>(a.dy) + go;
-      const float4* gx = reinterpret_cast<const float4*>(a.x) + go;
-      for (int p = lane; p < np; p += L) {
-        cp_async16(&d[p * Q + q], gd + (size_t)p * C4);
-        cp_async16(&d[slice + p * Q + q], gx + (size_t)p * C4);
-      }
+  const int step_s = L * Q;
+  const size_t step_g = (size_t)L * C4;
+  const size_t goff = ((size_t)n * a.HW + p0 + lane) * C4 + (size_t)cgi * Q + q;
+  const int s0 = lane * Q + q;
+  if (active) {
+    const float4* gd = reinterpret_cast<const float4*>(a.dy) + goff;
+    const float4* gx = reinterpret_cast<const float4*>(a.x) + goff;
+    float4 *d = sg + s0, *e = sx + s0;
+    for (int p = lane; p < np; p += L, gd += step_g, gx += step_g, d += step_s, e += step_s) {
+      cp_async16(d, gd);
+      cp_async16(e, gx);
     }
-    cp_async_commit();
-  };
+  }
+  cp_async_wait_all();
+  __syncthreads();
 
-  int b = 0;
-  if (cid < total) issue(cid, 0);
-  for (int item = cid; item < total; item += ncl, b ^= 1) {
-    const int nxt = item + ncl;
-    if (nxt < total) issue(nxt, b ^ 1);
-    cp_async_wait(nxt < total ? 1 : 0);
-    __syncthreads();
-    float4* sg = sbuf + (size_t)b * 2 * slice;     // dy, then G
-    float4* sx = sg + slice;                       // x, then xhat
-    double* cp_ = cpart + (size_t)b * 4 * kThr;    // partial sums of this parity
-    const int n = item / ncg, cgi = item - n * ncg;
-    const size_t goff = item_off(item);
-    const int c = (cgi * Q + q) * 4;
+  const int c = (cgi * Q + q) * 4;
+  const float slope = a.slope;
+  float m[4] = {0, 0, 0, 0}, r[4] = {0, 0, 0, 0};
+  float ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+  float ga2[4] = {0.f, 0.f, 0.f, 0.f}, be2[4] = {0.f, 0.f, 0.f, 0.f};
+  // ---- phase 1: g, G and the sums.  Each thread sums its few pixels in fp32; everything across
+  // threads, CTAs and (later) images is accumulated in fp64: sum(g*xhat) is a covariance and
+  // cancels heavily.
+  float f_g[4] = {0, 0, 0, 0}, f_gx[4] = {0, 0, 0, 0}, f_g2[4] = {0, 0, 0, 0}, f_gx2[4] = {0, 0, 0, 0};
+  if (active) {
     const size_t so = (size_t)n * a.C + c;
-    float m[4] = {0, 0, 0, 0}, r[4] = {0, 0, 0, 0};
-    float ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
-    float ga2[4] = {0.f, 0.f, 0.f, 0.f}, be2[4] = {0.f, 0.f, 0.f, 0.f};
-    // ---- phase 1: g, G and the four sums.  fp64 accumulators: sum(g*xhat) is a covariance and
-    // cancels heavily; the affine gradients are sums of these over the whole batch.
-    double s_g[4] = {0, 0, 0, 0}, s_gx[4] = {0, 0, 0, 0}, s_g2[4] = {0, 0, 0, 0}, s_gx2[4] = {0, 0, 0, 0};
-    if (active) {
-      const float4 m4 = *reinterpret_cast<const float4*>(a.mean + so);
-      const float4 r4 = *reinterpret_cast<const float4*>(a.rstd + so);
-      m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
-      r[0] = r4.x; r[1] = r4.y; r[2] = r4.z; r[3] = r4.w;
-      if (a.gamma) {
-        const float4 g4 = *reinterpret_cast<const float4*>(a.gamma + c);
-        const float4 b4 = *reinterpret_cast<const float4*>(a.beta + c);
-        ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w;
-        be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
-      }
-      if (dual) {
-        const float4 g4 = *reinterpret_cast<const float4*>(a.gamma2 + c);
-        const float4 b4 = *reinterpret_cast<const float4*>(a.beta2 + c);
-        ga2[0] = g4.x; ga2[1] = g4.y; ga2[2] = g4.z; ga2[3] = g4.w;
-        be2[0] = b4.x; be2[1] = b4.y; be2[2] = b4.z; be2[3] = b4.w;
-      }
-      const float4* gy = a.ymask ? reinterpret_cast<const float4*>(a.ymask) + goff : nullptr;
-      const float4* gd2 = dual ? reinterpret_cast<const float4*>(a.dy2) + goff : nullptr;
-      float4* go_ = a.g_out ? reinterpret_cast<float4*>(a.g_out) + goff : nullptr;
-      for (int p = lane; p < np; p += L) {
-        const int i = p * Q + q;
-        const float4 d4 = sg[i], x4 = sx[i];
-        const float d[4] = {d4.x, d4.y, d4.z, d4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
-        float ym[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
-        if (gy) {
-          const float4 t = __ldg(gy + (size_t)p * C4);
-          ym[0] = t.x; ym[1] = t.y; ym[2] = t.z; ym[3] = t.w;
-        }
-        if (dual) {
-          const float4 t = __ldg(gd2 + (size_t)p * C4);
-          d2[0] = t.x; d2[1] = t.y; d2[2] = t.z; d2[3] = t.w;
-        }
-        float xh[4], g[4], G[4];
+    const float4 m4 = *reinterpret_cast<const float4*>(a.mean + so);
+    const float4 r4 = *reinterpret_cast<const float4*>(a.rstd + so);
+    m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
+    r[0] = r4.x; r[1] = r4.y; r[2] = r4.z; r[3] = r4.w;
+    if (a.gamma) {
+      const float4 g4 = *reinterpret_cast<const float4*>(a.gamma + c);
+      const float4 b4 = *reinterpret_cast<const float4*>(a.beta + c);
+      ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w;
+      be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
+    }
+    if (DUAL) {
+      const float4 g4 = *reinterpret_cast<const float4*>(a.gamma2 + c);
+      const float4 b4 = *reinterpret_cast<const float4*>(a.beta2 + c);
+      ga2[0] = g4.x; ga2[1] = g4.y; ga2[2] = g4.z; ga2[3] = g4.w;
+      be2[0] = b4.x; be2[1] = b4.y; be2[2] = b4.z; be2[3] = b4.w;
+    }
+    const bool has_mask = a.ymask != nullptr;
+    const bool has_gout = a.g_out != nullptr;
+    float4 *d = sg + s0, *e = sx + s0;
+    size_t go = goff;
+    for (int p = lane; p < np; p += L, d += step_s, e += step_s, go += step_g) {
+      const float4 d4 = *d, x4 = *e;
+      const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+      float pre[4], d2[4] = {0.f, 0.f, 0.f, 0.f};
+      float xh[4], g[4], G[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          xh[j] = (xv[j] - m[j]) * r[j];
-          g[j] = d[j];
-          if (a.act != ACT_NONE) g[j] *= act_grad(gy ? ym[j] : fmaf(xh[j], ga[j], be[j]), a.act);
-          s_g[j] += (double)g[j];
-          s_gx[j] += (double)g[j] * (double)xh[j];
-          G[j] = ga[j] * g[j];
-          if (dual) {
-            float g2 = d2[j];
-            if (a.act != ACT_NONE) g2 *= act_grad(fmaf(xh[j], ga2[j], be2[j]), a.act);
-            s_g2[j] += (double)g2;
-            s_gx2[j] += (double)g2 * (double)xh[j];
-            G[j] = fmaf(ga2[j], g2, G[j]);
-          }
-        }
-        if (go_) go_[(size_t)p * C4] = make_float4(g[0], g[1], g[2], g[3]);
-        sg[i] = make_float4(G[0], G[1], G[2], G[3]);
-        sx[i] = make_float4(xh[0], xh[1], xh[2], xh[3]);
+      for (int j = 0; j < 4; ++j) {
+        xh[j] = (xv[j] - m[j]) * r[j];
+        pre[j] = fmaf(xh[j], ga[j], be[j]);
       }
-    }
-    quad_reduce<double>(s_g, Q, L, wred, cp_);
-    quad_reduce<double>(s_gx, Q, L, wred, cp_ + kThr);
-    if (dual) {
-      quad_reduce<double>(s_g2, Q, L, wred, cp_ + 2 * kThr);
-      quad_reduce<double>(s_gx2, Q, L, wred, cp_ + 3 * kThr);
-    }
-    // one barrier per item: the partials alternate between two buffers, so a CTA that runs ahead
-    // writes parity b^1 while slower peers may still read parity b
-    cluster.sync();
-    if (threadIdx.x < Q * 4) {
-      // thread t < 4Q totals channel cgi*CG + t
-      double t[4] = {0.0, 0.0, 0.0, 0.0};
-      const int nsum = dual ? 4 : 2;
-      for (int rk = 0; rk < a.CS; ++rk) {
-        const double* rp = cluster.map_shared_rank(cp_, rk);
-        for (int k = 0; k < nsum; ++k) t[k] += rp[k * kThr + threadIdx.x];
+      if (has_mask) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(a.ymask) + go);
+        pre[0] = t.x; pre[1] = t.y; pre[2] = t.z; pre[3] = t.w;
       }
-      const int ch = cgi * Q * 4 + threadIdx.x;
-      const double g1 = a.gamma ? (double)a.gamma[ch] : 1.0;
-      const double g2 = dual ? (double)a.gamma2[ch] : 0.0;
-      const double inv = 1.0 / (double)a.HW;
-      tot[threadIdx.x] = (float)((g1 * t[0] + g2 * t[2]) * inv);
-      tot[kThr + threadIdx.x] = (float)((g1 * t[1] + g2 * t[3]) * inv);
-      if (rank == 0 && a.sum_g) {
-        const size_t o = (size_t)n * a.C + ch;
-        a.sum_g[o] = (float)t[0];
-        a.sum_gx[o] = (float)t[1];
-        if (dual && a.sum_g2) {
-          a.sum_g2[o] = (float)t[2];
-          a.sum_gx2[o] = (float)t[3];
+      if (DUAL) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(a.dy2) + go);
+        d2[0] = t.x; d2[1] = t.y; d2[2] = t.z; d2[3] = t.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        g[j] = dv[j] * act_deriv(pre[j], slope);
+        f_g[j] += g[j];
+        f_gx[j] = fmaf(g[j], xh[j], f_gx[j]);
+        G[j] = ga[j] * g[j];
+        if (DUAL) {
+          const float g2 = d2[j] * act_deriv(fmaf(xh[j], ga2[j], be2[j]), slope);
+          f_g2[j] += g2;
+          f_gx2[j] = fmaf(g2, xh[j], f_gx2[j]);
+          G[j] = fmaf(ga2[j], g2, G[j]);
         }
       }
+      if (has_gout) reinterpret_cast<float4*>(a.g_out)[go] = make_float4(g[0], g[1], g[2], g[3]);
+      *d = make_float4(G[0], G[1], G[2], G[3]);
+      *e = make_float4(xh[0], xh[1], xh[2], xh[3]);
     }
-    __syncthreads();
+  }
+  {
+    double t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = (double)f_g[j];
+    quad_reduce<double>(t, Q, L, wred, cpart);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = (double)f_gx[j];
+    quad_reduce<double>(t, Q, L, wred, cpart + kS);
+    if (DUAL) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = (double)f_g2[j];
+      quad_reduce<double>(t, Q, L, wred, cpart + 2 * kS);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = (double)f_gx2[j];
+      quad_reduce<double>(t, Q, L, wred, cpart + 3 * kS);
+    }
+  }
+  cluster.sync();
+  if (threadIdx.x < Q * 4) {
+    // thread t < 4Q totals channel cgi*CG + t
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    constexpr int nsum = DUAL ? 4 : 2;
+    for (int rk = 0; rk < a.CS; ++rk) {
+      const double* rp = cluster.map_shared_rank(cpart, rk);
+#pragma unroll
+      for (int k = 0; k < nsum; ++k) t[k] += rp[k * kS + threadIdx.x];
+    }
+    const int ch = cgi * Q * 4 + threadIdx.x;
+    const double g1 = a.gamma ? (double)a.gamma[ch] : 1.0;
+    const double g2 = DUAL ? (double)a.gamma2[ch] : 0.0;
+    const double inv = 1.0 / (double)a.HW;
+    tot[threadIdx.x] = (float)((g1 * t[0] + g2 * t[2]) * inv);
+    tot[kS + threadIdx.x] = (float)((g1 * t[1] + g2 * t[3]) * inv);
+    if (rank == 0 && a.sum_g) {
+      const size_t o = (size_t)n * a.C + ch;
+      a.sum_g[o] = (float)t[0];
+      a.sum_gx[o] = (float)t[1];
+      if (DUAL && a.sum_g2) {
+        a.sum_g2[o] = (float)t[2];
+        a.sum_gx2[o] = (float)t[3];
+      }
+    }
+  }
+  __syncthreads();
 
-    // ---- phase 2: dx out of shared memory
-    float cs[4] = {0.f, 0.f, 0.f, 0.f};
-    if (active) {
-      const float4 A4 = reinterpret_cast<const float4*>(tot)[q];
-      const float4 B4 = reinterpret_cast<const float4*>(tot + kThr)[q];
-      const float A[4] = {A4.x, A4.y, A4.z, A4.w}, B[4] = {B4.x, B4.y, B4.z, B4.w};
-      const float4* gadd = a.addend ? reinterpret_cast<const float4*>(a.addend) + goff : nullptr;
-      for (int p = lane; p < np; p += L) {
-        const int i = p * Q + q;
-        const float4 G4 = sg[i], h4 = sx[i];
-        const float G[4] = {G4.x, G4.y, G4.z, G4.w}, xh[4] = {h4.x, h4.y, h4.z, h4.w};
-        float o[4];
+  // ---- phase 2: dx out of shared memory
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    const float4 A4 = reinterpret_cast<const float4*>(tot)[q];
+    const float4 B4 = reinterpret_cast<const float4*>(tot + kS)[q];
+    const float A[4] = {A4.x, A4.y, A4.z, A4.w}, B[4] = {B4.x, B4.y, B4.z, B4.w};
+    const bool has_add = a.addend != nullptr, has_dx = a.dx != nullptr, has_pl = a.dx_hi != nullptr;
+    const float4 *d = sg + s0, *e = sx + s0;
+    size_t go = goff;
+    for (int p = lane; p < np; p += L, d += step_s, e += step_s, go += step_g) {
+      const float4 G4 = *d, h4 = *e;
+      const float G[4] = {G4.x, G4.y, G4.z, G4.w}, xh[4] = {h4.x, h4.y, h4.z, h4.w};
+      float o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = r[j] * (G[j] - A[j] - xh[j] * B[j]);
-        const size_t go = goff + (size_t)p * C4;
-        if (gadd) {
-          const float4 t = __ldg(gadd + (size_t)p * C4);
-          o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
-        }
+      for (int j = 0; j < 4; ++j) o[j] = r[j] * (G[j] - A[j] - xh[j] * B[j]);
+      if (has_add) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(a.addend) + go);
+        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cs[j] += o[j];
-        if (a.dx) reinterpret_cast<float4*>(a.dx)[go] = make_float4(o[0], o[1], o[2], o[3]);
-        if (a.dx_hi) {
-          uint2 h, l;
-          split4<TC_BF16>(o, h, l);
-          reinterpret_cast<uint2*>(a.dx_hi)[go] = h;
-          reinterpret_cast<uint2*>(a.dx_lo)[go] = l;
-        }
+      for (int j = 0; j < 4; ++j) cs[j] += o[j];
+      if (has_dx) reinterpret_cast<float4*>(a.dx)[go] = make_float4(o[0], o[1], o[2], o[3]);
+      if (has_pl) {
+        uint2 h, l;
+        split4<TC_BF16>(o, h, l);
+        reinterpret_cast<uint2*>(a.dx_hi)[go] = h;
+        reinterpret_cast<uint2*>(a.dx_lo)[go] = l;
       }
     }
-    if (a.colpart) {
-      float* fred = reinterpret_cast<float*>(wred);
-      float* fout = fred + kThr * 4;
-      quad_reduce<float>(cs, Q, L, fred, fout);
-      if (threadIdx.x < Q * 4)
-        a.colpart[((size_t)n * a.CS + rank) * a.C + cgi * Q * 4 + threadIdx.x] = fout[threadIdx.x];
-    }
-    __syncthreads();    // staging buffer b and wred are reused by the next iterations
+  }
+  if (a.colpart) {
+    float* fred = reinterpret_cast<float*>(wred);
+    float* fout = fred + kThr * 4;
+    quad_reduce<float>(cs, Q, L, fred, fout);
+    if (threadIdx.x < Q * 4)
+      a.colpart[((size_t)n * a.CS + rank) * a.C + cgi * Q * 4 + threadIdx.x] = fout[threadIdx.x];
   }
   cluster.sync();
 }
@@ -635,20 +605,19 @@ rowsum_kernel(const float* __restrict__ part, int rows, int C, float* __restrict
 }
 
 size_t fwd_smem(const FusedPlan& p, int tensors) {
-  return (size_t)p.ppc * p.Q * 16 * 2 * tensors + (size_t)(4 + 4 + 4) * kThr * sizeof(float);
+  return (size_t)p.ppc * p.Q * 16 * tensors +
+         (size_t)(kThr * 4 + 4 * 4 * kMaxQ + 4 * 4 * kMaxQ) * sizeof(float);
 }
 size_t bwd_smem(const FusedPlan& p) {
-  return (size_t)p.ppc * p.Q * 16 * 4 + (size_t)(4 + 8) * kThr * sizeof(double) +
-         2 * kThr * sizeof(float);
+  return (size_t)p.ppc * p.Q * 16 * 2 + (size_t)(kThr * 4 + 4 * 4 * kMaxQ) * sizeof(double) +
+         2 * 4 * kMaxQ * sizeof(float);
 }
 
-// Persistent launch: as many clusters as the device keeps resident (at most one per work item).
 template <typename K, typename A>
-int launch_persistent(K kernel, int items, int cs, size_t smem, const A& args, cudaStream_t s) {
+int launch_cluster(K kernel, dim3 grid, int cs, size_t smem, const A& args, cudaStream_t s) {
   EVE_TRY(ensure_dynamic_smem((const void*)kernel, smem));
-  int dev = 0;
-  EVE_CUDA(cudaGetDevice(&dev));
   cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
   cfg.blockDim = dim3(kThr, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
@@ -659,41 +628,33 @@ int launch_persistent(K kernel, int items, int cs, size_t smem, const A& args, c
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  int resident = 0;
-  {
+  if (cs > 8) {
     static std::mutex mu;
-    static std::map<std::tuple<const void*, int, int, size_t>, int> cache;
     static std::map<const void*, bool> allowed;
     std::lock_guard<std::mutex> lk(mu);
-    if (cs > 8 && !allowed[(const void*)kernel]) {
+    if (!allowed[(const void*)kernel]) {
       EVE_CUDA(cudaFuncSetAttribute((const void*)kernel,
                                     cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       allowed[(const void*)kernel] = true;
     }
-    auto key = std::make_tuple((const void*)kernel, dev, cs, smem);
-    auto it = cache.find(key);
-    if (it == cache.end()) {
-      cfg.gridDim = dim3((unsigned)(cs * kNumSMs * 2), 1, 1);
-      int n = 0;
-      EVE_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
-      EVE_REQUIRE(n > 0, EVE_ERR_CUDA, "in_fused: a cluster of %d CTAs with %zu bytes of shared "
-                  "memory cannot be scheduled", cs, smem);
-      it = cache.emplace(key, n).first;
-    }
-    resident = it->second;
   }
-  const int clusters = items < resident ? items : resident;
-  cfg.gridDim = dim3((unsigned)(clusters * cs), 1, 1);
   EVE_CUDA(cudaLaunchKernelEx(&cfg, kernel, args));
   count_launch();
   return EVE_OK;
+}
+
+template <int FMT>
+int launch_fwd(int mode, dim3 grid, int cs, size_t smem, const InFwdArgs& a, cudaStream_t s) {
+  if (mode == 2) return launch_cluster(in_fwd_fused_kernel<FMT, 2>, grid, cs, smem, a, s);
+  if (mode == 1) return launch_cluster(in_fwd_fused_kernel<FMT, 1>, grid, cs, smem, a, s);
+  return launch_cluster(in_fwd_fused_kernel<FMT, 0>, grid, cs, smem, a, s);
 }
 
 }  // namespace
 
 bool in_fused_supported(int HW, int C, int tensors) {
   FusedPlan p;
-  return plan_fused(C, HW, 2 * tensors, p);
+  return plan_fused(C, HW, tensors, p);
 }
 
 int in_fwd_fused(const float* x, int N, int HW, int C, const float* x2, int x2_mode,
@@ -703,7 +664,7 @@ int in_fwd_fused(const float* x, int N, int HW, int C, const float* x2, int x2_m
   if (N == 0) return EVE_OK;
   const int tensors = x2_mode == 2 ? 2 : 1;
   FusedPlan p;
-  EVE_REQUIRE(plan_fused(C, HW, 2 * tensors, p), EVE_ERR_SHAPE,
+  EVE_REQUIRE(plan_fused(C, HW, tensors, p), EVE_ERR_SHAPE,
               "in_fwd_fused: unsupported shape HW=%d C=%d", HW, C);
   EVE_REQUIRE(x && mean && rstd, EVE_ERR_NULL, "in_fwd_fused: NULL pointer");
   EVE_REQUIRE(x2_mode == 0 || x2, EVE_ERR_NULL, "in_fwd_fused: x2 is NULL");
@@ -711,23 +672,22 @@ int in_fwd_fused(const float* x, int N, int HW, int C, const float* x2, int x2_m
   EVE_REQUIRE((gamma == nullptr) == (beta == nullptr), EVE_ERR_NULL, "in_fwd_fused: gamma/beta");
   EVE_REQUIRE(!hiB || (gammaB && betaB && loB), EVE_ERR_NULL, "in_fwd_fused: second affine set");
   InFwdArgs a;
-  a.x = x; a.x2 = x2; a.x2_mode = x2_mode;
-  a.N = N; a.HW = HW; a.C = C; a.Q = p.Q; a.CS = p.CS; a.ppc = p.ppc;
+  a.x = x; a.x2 = x2;
+  a.HW = HW; a.C = C; a.Q = p.Q; a.CS = p.CS; a.ppc = p.ppc;
   a.gamma = gamma; a.beta = beta; a.gammaB = gammaB; a.betaB = betaB;
-  a.act = act;
+  a.slope = act_slope(act);
   a.mean = mean; a.rstd = rstd; a.mean2 = mean2; a.rstd2 = rstd2;
   a.y = y;
   a.hiA = (uint16_t*)hiA; a.loA = (uint16_t*)loA; a.hiB = (uint16_t*)hiB; a.loB = (uint16_t*)loB;
   const size_t smem = fwd_smem(p, tensors);
-  const int items = N * (C / p.CG);
-  if (fmt == TC_BF16)
-    return launch_persistent(in_fwd_fused_kernel<TC_BF16>, items, p.CS, smem, a, s);
-  return launch_persistent(in_fwd_fused_kernel<TC_F16>, items, p.CS, smem, a, s);
+  dim3 grid(p.CS, C / p.CG, N);
+  if (fmt == TC_BF16) return launch_fwd<TC_BF16>(x2_mode, grid, p.CS, smem, a, s);
+  return launch_fwd<TC_F16>(x2_mode, grid, p.CS, smem, a, s);
 }
 
 size_t in_bwd_fused_scratch_floats(int N, int HW, int C) {
   FusedPlan p;
-  if (!plan_fused(C, HW, 4, p)) return 0;
+  if (!plan_fused(C, HW, 2, p)) return 0;
   return (size_t)4 * N * C + (size_t)N * p.CS * C;
 }
 
@@ -739,16 +699,16 @@ int in_bwd_fused(const float* dy, const float* dy2, const float* ymask, const fl
                  float* dbias2, bool accumulate, float* scratch, cudaStream_t s) {
   if (N == 0) return EVE_OK;
   FusedPlan p;
-  EVE_REQUIRE(plan_fused(C, HW, 4, p), EVE_ERR_SHAPE,
+  EVE_REQUIRE(plan_fused(C, HW, 2, p), EVE_ERR_SHAPE,
               "in_bwd_fused: unsupported shape HW=%d C=%d", HW, C);
   EVE_REQUIRE(dy && x && mean && rstd && scratch, EVE_ERR_NULL, "in_bwd_fused: NULL pointer");
   EVE_REQUIRE(!dy2 || (gamma2 && beta2 && gamma), EVE_ERR_NULL, "in_bwd_fused: second affine set");
   EVE_REQUIRE(!dx_hi || dx_lo, EVE_ERR_NULL, "in_bwd_fused: dx_lo is NULL");
   InBwdArgs a;
   a.dy = dy; a.dy2 = dy2; a.ymask = ymask; a.x = x;
-  a.N = N; a.HW = HW; a.C = C; a.Q = p.Q; a.CS = p.CS; a.ppc = p.ppc;
+  a.HW = HW; a.C = C; a.Q = p.Q; a.CS = p.CS; a.ppc = p.ppc;
   a.mean = mean; a.rstd = rstd; a.gamma = gamma; a.beta = beta; a.gamma2 = gamma2; a.beta2 = beta2;
-  a.act = act;
+  a.slope = act_slope(act);
   a.addend = addend; a.dx = dx; a.dx_hi = (uint16_t*)dx_hi; a.dx_lo = (uint16_t*)dx_lo;
   a.g_out = g_out;
   const size_t nc = (size_t)N * C;
@@ -758,7 +718,9 @@ int in_bwd_fused(const float* dy, const float* dy2, const float* ymask, const fl
   a.sum_g2 = affine && dy2 ? scratch + 2 * nc : nullptr;
   a.sum_gx2 = affine && dy2 ? scratch + 3 * nc : nullptr;
   a.colpart = (dbias || dbias2) ? scratch + 4 * nc : nullptr;
-  EVE_TRY(launch_persistent(in_bwd_fused_kernel, N * (C / p.CG), p.CS, bwd_smem(p), a, s));
+  dim3 grid(p.CS, C / p.CG, N);
+  if (dy2) EVE_TRY(launch_cluster(in_bwd_fused_kernel<true>, grid, p.CS, bwd_smem(p), a, s));
+  else EVE_TRY(launch_cluster(in_bwd_fused_kernel<false>, grid, p.CS, bwd_smem(p), a, s));
   const int acc = accumulate ? 1 : 0;
   if (affine) {
     rowsum_kernel<<<cdiv(C, 8), 256, 0, s>>>(a.sum_gx, N, C, dgamma, nullptr, acc);

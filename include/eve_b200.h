@@ -132,6 +132,13 @@ int eve_instnorm_fused_bwd(const float* dy, const float* dy2, const float* ymask
                            float* dgamma2, float* dbeta2, float* dbias, void* workspace,
                            size_t workspace_bytes, eve_stream_t stream);
 
+/* The ResNet stem tail as one kernel: maxpool3x3 s2 p1 (relu (InstanceNorm(x))) (torchvision
+ * ResNet.bn1 / relu / maxpool behind eye_net.py:48-50,106).  x[n,h,w,c] NHWC -> y[n,oh,ow,c] with
+ * oh = (h+2-3)/2+1; idx = int32 flat ih*w+iw of the first maximum in row-major window order
+ * (what ATen returns; padding never wins).  mean/rstd [n,c] are outputs. */
+int eve_in_relu_maxpool_fwd(const float* x, int n, int h, int w, int c, float* mean, float* rstd,
+                            float* y, int32_t* idx, eve_stream_t stream);
+
 /* nn.AdaptiveMaxPool2d (refine_net.py:93,121): idx = int32 flat h*W+w of the first maximum. */
 int eve_adaptive_maxpool_fwd(const float* x, int n, int h, int w, int c, int oh, int ow, float* y,
                              int32_t* idx, eve_stream_t stream);

@@ -3,8 +3,11 @@
 A plain-PyTorch (fp32 or fp64, CPU) functional restatement of the arithmetic the
 reference performs in ``src/models/{eye_net,refine_net,common,eve}.py`` and
 ``src/losses/*.py``.  It exists only to check the CUDA path: nothing under
-``eve_b200/`` imports it; only ``tests/``, ``__graft_entry__.smoke()`` and the
-``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` do.
+``eve_b200/`` imports it; only ``tests/``, ``__graft_entry__.smoke()`` and the baseline
+legs of ``bench.py`` do (``cpu_baseline`` / ``--impl reference`` on the host cores, and
+``also.stock_torch_b200``: the same plain-PyTorch arithmetic timed on the GPU through
+cuDNN/cuBLAS as the "existing library path" baseline -- measured beside the product, never
+part of it).
 
 Parity status: **pinned against the reference itself.**  The reference ships no tests
 or golden vectors, so ``oracle/gen_golden.py`` imports the
@@ -325,8 +328,8 @@ def offset_augmentation(g, head_R, kappa):
 def make_heatmaps(centres_px, sigma, size_wh=(128, 72), screen_wh=(1920.0, 1080.0)):
     """common.py:226-243 for [..., 2] pixel centres -> [..., 1, H, W]."""
     w, h = size_wh
-    xs = torch.arange(w, dtype=centres_px.dtype).view(1, w)
-    ys = torch.arange(h, dtype=centres_px.dtype).view(h, 1)
+    xs = torch.arange(w, dtype=centres_px.dtype, device=centres_px.device).view(1, w)
+    ys = torch.arange(h, dtype=centres_px.dtype, device=centres_px.device).view(h, 1)
     cx = ((w / screen_wh[0]) * centres_px[..., 0])[..., None, None]
     cy = ((h / screen_wh[1]) * centres_px[..., 1])[..., None, None]
     alpha = -0.5 / (sigma ** 2)
@@ -337,8 +340,8 @@ def make_heatmaps(centres_px, sigma, size_wh=(128, 72), screen_wh=(1920.0, 1080.
 def soft_argmax(heatmaps, size_wh=(128, 72), screen_wh=(1920.0, 1080.0)):
     """common.py:294-323: [N,1,H,W] -> [N,2] pixels."""
     w, h = size_wh
-    xs = torch.linspace(0, 1.0, w, dtype=torch.float64).to(heatmaps.dtype)
-    ys = torch.linspace(0, 1.0, h, dtype=torch.float64).to(heatmaps.dtype)
+    xs = torch.linspace(0, 1.0, w, dtype=torch.float64).to(heatmaps.dtype).to(heatmaps.device)
+    ys = torch.linspace(0, 1.0, h, dtype=torch.float64).to(heatmaps.dtype).to(heatmaps.device)
     p = F.softmax(1e2 * heatmaps.reshape(-1, h * w), dim=-1).reshape(-1, h, w)
     lx = (p * xs.view(1, 1, w)).sum(dim=(1, 2))
     ly = (p * ys.view(1, h, 1)).sum(dim=(1, 2))
@@ -357,10 +360,10 @@ def gaze_history_maps(timestamps, heatmaps, validity, decay):
         ts = timestamps[:, :t + 1]
         nz = ts != 0
         # last non-zero timestamp of the prefix
-        idx = (nz.long() * torch.arange(1, t + 2).view(1, -1)).argmax(dim=1)
+        idx = (nz.long() * torch.arange(1, t + 2, device=ts.device).view(1, -1)).argmax(dim=1)
         target = ts.gather(1, idx.view(-1, 1))
         diff = ((target - ts) * 1e-6).to(heatmaps.dtype)
-        wgt = torch.pow(torch.tensor(decay, dtype=heatmaps.dtype), diff)
+        wgt = torch.pow(torch.tensor(decay, dtype=heatmaps.dtype, device=heatmaps.device), diff)
         wgt = wgt * nz.to(heatmaps.dtype) * validity[:, :t + 1].to(heatmaps.dtype)
         out.append((wgt.view(B, t + 1, 1, 1, 1) * heatmaps[:, :t + 1]).sum(1))
     return torch.stack(out, 1)
@@ -567,7 +570,7 @@ def eve_losses(d, mid, out, cfg, training):
         if 'g_' + stage in mid and 'g' in d:
             out['metric_ang_g_' + stage] = apply(angular_error, 'g_' + stage, 'g')
 
-    total = torch.zeros((), dtype=mid['left_g_initial'].dtype)
+    total = torch.zeros((), dtype=mid['left_g_initial'].dtype, device=mid['left_g_initial'].device)
     if 'loss_ang_left_g_initial' in out:
         total = total + cfg.loss_coeff_g_ang_initial * (
             out['loss_ang_left_g_initial'] + out['loss_ang_right_g_initial'])

@@ -80,6 +80,7 @@ def test_replay_survives_workspace_growth(cfg):
     B, T = 1, 2
     xs = [synth.make_clip_batch(B, T, seed=80 + i) for i in range(4)]
     dev = torch.device('cuda', torch.cuda.current_device())
+    L._workspaces.clear()      # earlier tests may have left buffers big enough for anything
     ma, ta, ga = _make(cfg, 11, True, xs[0])
     la = [float(ga(xs[1]))]
     before = L.workspace(1, dev).data_ptr()

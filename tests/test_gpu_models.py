@@ -134,6 +134,22 @@ def test_eve_forward_backward_matches_reference(name, cfg, conv_mode):
     assert checked >= 20, checked
     for must in ('full_loss', 'left_pupil_size', 'g_initial', 'PoG_px_initial'):
         assert must in out
+    # derived labels (EVE.calculate_additional_labels, eve.py:441-543) against the reference's
+    labels = 0
+    for k, ref in gold.items():
+        if not k.startswith('label/'):
+            continue
+        key = k[len('label/'):]
+        assert key in inputs, key
+        got = inputs[key].detach().cpu().numpy()
+        if ref.dtype == np.bool_ or np.issubdtype(ref.dtype, np.integer):
+            assert np.array_equal(got.astype(ref.dtype), ref), k     # validity masks: bit-exact
+        else:
+            assert got.shape == ref.shape, (k, got.shape, ref.shape)
+            assert H.rel_err(got, ref) < 2e-6, (k, H.rel_err(got, ref))
+        labels += 1
+    if any(k.startswith('label/') for k in gold):
+        assert labels >= 5, labels
 
     if training:
         out['full_loss'].backward()

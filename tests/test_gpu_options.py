@@ -127,13 +127,16 @@ def test_option_variants_agree_on_a_full_training_step(variant, cfg, options):
     # that 1e-7 difference to ~1e-2 on the last gradients of the chain (initial.0), the same
     # amplification the fp32 reference shows against fp64 (test_gpu_models.py)
     gtol = 2e-2 if ('fused_norm' in variant or 'fused_planes' in variant) else 2e-3
+    # biases in front of an InstanceNorm have an exactly zero gradient (the norm removes the
+    # mean): what is computed there is cancellation noise ~1e-6 of the real gradients
+    floor = 1e-6 * max(float(v.double().norm()) for v in base_grads.values())
     for k in grads:
         a, b = grads[k].double(), base_grads[k].double()
         den = float(b.norm())
         if den == 0.0:
             assert float(a.norm()) == 0.0, k
         else:
-            assert float((a - b).norm()) <= gtol * den + 1e-9, k
+            assert float((a - b).norm()) <= gtol * den + floor, k
 
 
 def test_unknown_option_is_rejected():
