@@ -51,7 +51,7 @@ FLOP_SCREEN_FRAME = 9629761536.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=60)
+    ap.add_argument('--steps', type=int, default=80)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='eve_refine', choices=sorted(WORKLOADS))
@@ -60,6 +60,9 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary workload line')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-input leg (profiling runs)')
+    ap.add_argument('--leg', default=None, choices=['t60', 'stream900', 'stock_torch_b200'],
+                    help='run ONE secondary measurement in this process and print its JSON '
+                         '(bench.py runs each of them in a child process of its own)')
     return ap.parse_args()
 
 
@@ -419,7 +422,10 @@ def leg_stock_torch(args, device):
     cfg = configure(args.workload)
     B, T = args.batch, args.seq_len
     sd = {k: v.to(device).requires_grad_(True) for k, v in build_state_dict(cfg).items()}
-    opt = torch.optim.Adam(list(sd.values()), lr=cfg.learning_rate, weight_decay=cfg.weight_decay)
+    # lr = 0: the same work per step with the parameters staying at their seeded values (sixteen
+    # steps at the reference's learning rate from random weights can leave the sigmoid output
+    # non-finite, which trips a device-side assert inside F.binary_cross_entropy)
+    opt = torch.optim.Adam(list(sd.values()), lr=0.0, weight_decay=0.0)
     inputs = {k: v.to(device) for k, v in synth.make_clip_batch(
         B, T, seed=7, with_screen=bool(cfg.load_screen_content)).items()}
     std = np.radians(cfg.refine_net_offset_augmentation_sigma)
@@ -454,6 +460,35 @@ def leg_stock_torch(args, device):
         (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32,
          torch.backends.cudnn.benchmark) = old
     return res
+
+
+LEGS = {'t60': leg_t60, 'stream900': leg_stream900, 'stock_torch_b200': leg_stock_torch}
+
+
+def run_leg_in_child(name, args, timeout=900):
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), '--leg', name, '--workload', args.workload,
+           '--batch', str(args.batch), '--seq-len', str(args.seq_len)]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout,
+                           cwd=REPO, text=True)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+        if r.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {'error': 'rc=%d: %s' % (r.returncode, r.stderr.strip().splitlines()[-1][:300]
+                                        if r.stderr.strip() else 'no output')}
+    except Exception as e:
+        return {'error': '%s: %s' % (type(e).__name__, e)}
+
+
+def leg_main(args):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the B200 path has no CPU fallback')
+    torch.cuda.set_device(0)
+    from eve_b200 import lib as L
+    L.load()
+    print(json.dumps(LEGS[args.leg](args, torch.device('cuda', 0))))
 
 
 def b200_arm(args):
@@ -546,13 +581,11 @@ def b200_arm(args):
                                     'unit': UNIT, 'ms_per_step': ex['ms'] / ex_steps}}
         torch.cuda.empty_cache()
         if world == 1 and rank == 0:
-            for name, fn in (('t60', leg_t60), ('stream900', leg_stream900),
-                             ('stock_torch_b200', leg_stock_torch)):
-                try:
-                    extra[name] = fn(args, device)
-                except Exception as e:      # a baseline leg must never take the headline down
-                    extra[name] = {'error': '%s: %s' % (type(e).__name__, e)}
-                torch.cuda.empty_cache()
+            # each secondary leg in a child process: a failure there (even a device-side assert,
+            # which poisons the CUDA context) must never take the headline down
+            torch.cuda.synchronize(device)
+            for name in LEGS:
+                extra[name] = run_leg_in_child(name, args)
     cfg = configure(args.workload)
 
     if rank != 0:
@@ -635,6 +668,8 @@ def main():
     args = parse()
     if args.impl == 'reference':
         reference_arm(args)
+    elif args.leg:
+        leg_main(args)
     else:
         b200_arm(args)
 

@@ -45,6 +45,7 @@ struct ProfRec {
   int kind;
   double flops, bytes;
   cudaEvent_t a, b;
+  int geom[8];        // N, H, W, Cin, Cout, k, stride, tagged (0 when the caller gave no geometry)
 };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
@@ -62,11 +63,15 @@ static cudaEvent_t prof_event() {
   return e;
 }
 
-ProfScope::ProfScope(int kind, double flops, double bytes, cudaStream_t stream)
+ProfScope::ProfScope(int kind, double flops, double bytes, cudaStream_t stream, const ConvGeom* g)
     : slot(-1), s(stream) {
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  ProfRec r{kind, flops, bytes, prof_event(), prof_event()};
+  ProfRec r{kind, flops, bytes, prof_event(), prof_event(), {0, 0, 0, 0, 0, 0, 0, 0}};
+  if (g) {
+    const int t[8] = {g->N, g->H, g->W, g->Cin, g->Cout, g->KH, g->stride, 1};
+    for (int i = 0; i < 8; ++i) r.geom[i] = t[i];
+  }
   if (!r.a || !r.b) return;
   cudaEventRecord(r.a, s);
   g_prof_recs.push_back(r);
@@ -136,6 +141,25 @@ extern "C" int eve_profile_read(int kind, double* ms, double* flops, double* byt
   if (bytes) *bytes = b;
   if (launches) *launches = n;
   return EVE_OK;
+}
+// One text line per recorded launch: "kind N H W Cin Cout k stride ms flops bytes"; returns the
+// number of bytes the full listing needs (call with cap = 0 to size the buffer).
+extern "C" long long eve_profile_dump(char* buf, long long cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  long long off = 0;
+  for (auto& r : g_prof_recs) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+    float e = 0.f;
+    if (cudaEventElapsedTime(&e, r.a, r.b) != cudaSuccess) continue;
+    char line[192];
+    int n = snprintf(line, sizeof(line), "%d %d %d %d %d %d %d %d %.6f %.0f %.0f\n", r.kind,
+                     r.geom[0], r.geom[1], r.geom[2], r.geom[3], r.geom[4], r.geom[5], r.geom[6],
+                     (double)e, r.flops, r.bytes);
+    if (buf && off + n < cap) memcpy(buf + off, line, (size_t)n);
+    off += n;
+  }
+  if (buf && cap > 0) buf[off < cap ? off : cap - 1] = 0;
+  return off + 1;
 }
 extern "C" const char* eve_last_error(void) { return g_error; }
 

@@ -50,10 +50,12 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes);
 // Optional per-kernel-family device timing (eve_profile_*): CUDA events recorded on the
 // launching stream around a launch, summed on read.  Costs nothing when disabled.
 enum ProfKind { PROF_CONV_FWD = 0, PROF_CONV_DGRAD = 1, PROF_CONV_WGRAD = 2, PROF_KINDS = 3 };
+struct ConvGeom;
 struct ProfScope {
   int slot;
   cudaStream_t s;
-  ProfScope(int kind, double flops, double bytes, cudaStream_t stream);
+  // `g` (optional) tags the record with the convolution's geometry for eve_profile_dump()
+  ProfScope(int kind, double flops, double bytes, cudaStream_t stream, const ConvGeom* g = nullptr);
   ~ProfScope();
 };
 

@@ -275,7 +275,7 @@ int conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* bia
     }
     if (x) EVE_TRY(split_planes(x, g.in_elems(), f.x_hi, npass == 3 ? f.x_lo : nullptr, fmt, s));
     ProfScope prof(PROF_CONV_FWD, 2.0 * g.out_elems() * (double)g.K(),
-                   4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
+                   4.0 * (g.in_elems() + g.out_elems() + (double)wel), s, &g);
     return conv_tc_run(g, f.x_hi, f.x_lo, f.w_hi, f.w_lo, bias, addend, y, npass, fmt,
                        1.f / wscale, s);
   }
@@ -296,7 +296,7 @@ int conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* bia
         x, g.H, g.W, g.OH, g.OW, fmt, x_hi, npass == 3 ? x_lo : nullptr);
     EVE_LAUNCH_CHECK();
     ProfScope prof(PROF_CONV_FWD, 2.0 * g.out_elems() * (double)g.K(),
-                   4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
+                   4.0 * (g.in_elems() + g.out_elems() + (double)wel), s, &g);
     return conv_tc_run(gg, x_hi, x_lo, w_hi, w_lo, bias, addend, y, npass, fmt, 1.f / wscale, s);
   }
   float* wf = c.get<float>(wel);
@@ -327,7 +327,7 @@ int conv_dgrad(const ConvGeom& g, const float* dy, const float* w, const float* 
       }
       EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
       ProfScope prof(PROF_CONV_DGRAD, 2.0 * g.out_elems() * (double)g.K(),
-                     4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
+                     4.0 * (g.in_elems() + g.out_elems() + (double)wel), s, &g);
       return conv_tc_run(f, d_hi, d_lo, w_hi, w_lo, nullptr, addend, dx, npass, TC_BF16, 1.f, s);
     }
   }
@@ -351,7 +351,7 @@ int conv_dgrad(const ConvGeom& g, const float* dy, const float* w, const float* 
       }
     }
     ProfScope prof(PROF_CONV_DGRAD, 2.0 * g.out_elems() * (double)g.K(),
-                   4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
+                   4.0 * (g.in_elems() + g.out_elems() + (double)wel), s, &g);
     return conv_tc_dgrad_s2_run(g, d_hi, d_lo, w_hi, w_lo, addend, dx, npass, s);
   }
   float* wd = c.get<float>(wel);
@@ -382,7 +382,7 @@ int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, fl
     int splits = 0;
     {
       ProfScope prof(PROF_CONV_WGRAD, 2.0 * g.out_elems() * (double)g.K(),
-                     4.0 * (g.in_elems() + g.out_elems() + (double)g.Cout * g.K()), s);
+                     4.0 * (g.in_elems() + g.out_elems() + (double)g.Cout * g.K()), s, &g);
       EVE_TRY(conv_tc_wgrad_run(g, d_hi, d_lo, x_hi, x_lo, part, npass, &splits, s, xfmt));
       EVE_TRY(wgrad_reduce(part, splits, g, dw, accumulate, s));
     }
@@ -408,7 +408,7 @@ int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, fl
     int splits = 0;
     {
       ProfScope prof(PROF_CONV_WGRAD, 2.0 * g.out_elems() * (double)g.K(),
-                     4.0 * (g.in_elems() + g.out_elems() + (double)g.Cout * g.K()), s);
+                     4.0 * (g.in_elems() + g.out_elems() + (double)g.Cout * g.K()), s, &g);
       EVE_TRY(conv_tc_wgrad_run(gg, d_hi, d_lo, x_hi, x_lo, part, npass, &splits, s));
       stem_wgrad_reduce_kernel<<<cdiv(g.Cout * 147, 256), 256, 0, s>>>(part, splits, g.Cout, dw,
                                                                       accumulate ? 1 : 0);
@@ -467,7 +467,7 @@ int conv_bwd(const ConvGeom& g, const float* x, const float* dy, const float* w,
   const double bytes = 4.0 * (g.in_elems() + g.out_elems() + (double)wel);
   {
     int splits = 0;
-    ProfScope prof(PROF_CONV_WGRAD, flops, bytes, s);
+    ProfScope prof(PROF_CONV_WGRAD, flops, bytes, s, &g);
     EVE_TRY(conv_tc_wgrad_run(g, b.d_hi, b.d_lo, b.x_hi, b.x_lo, part, npass, &splits, s));
     EVE_TRY(wgrad_reduce(part, splits, g, dw, accumulate, s));
   }
@@ -483,7 +483,7 @@ int conv_bwd(const ConvGeom& g, const float* x, const float* dy, const float* w,
       EVE_TRY(fill_zero(dx, g.in_elems(), s));
     }
   }
-  ProfScope prof(PROF_CONV_DGRAD, flops, bytes, s);
+  ProfScope prof(PROF_CONV_DGRAD, flops, bytes, s, &g);
   if (s1)
     return conv_tc_run(dgrad_as_fwd(g), b.d_hi, b.d_lo, b.w_hi, b.w_lo, nullptr, addend, dx, npass,
                        TC_BF16, 1.f, s);
@@ -511,7 +511,7 @@ int conv_fwd_planes(const ConvGeom& g, const void* x_hi, const void* x_lo, const
     EVE_TRY(conv_tc_prep_weights(g, w, false, w_hi, w_lo, TC_F16, wscale, s));
   }
   ProfScope prof(PROF_CONV_FWD, 2.0 * g.out_elems() * (double)g.K(),
-                 4.0 * (g.in_elems() + g.out_elems() + (double)wel), s);
+                 4.0 * (g.in_elems() + g.out_elems() + (double)wel), s, &g);
   return conv_tc_run(g, x_hi, x_lo, w_hi, w_lo, bias, addend, y, 3, TC_F16, 1.f / wscale, s);
 }
 
@@ -532,7 +532,7 @@ int conv_bwd_planes(const ConvGeom& g, const void* x_hi, const void* x_lo, const
   const double bytes = 4.0 * (g.in_elems() + g.out_elems() + (double)wel);
   if (dw) {
     int splits = 0;
-    ProfScope prof(PROF_CONV_WGRAD, flops, bytes, s);
+    ProfScope prof(PROF_CONV_WGRAD, flops, bytes, s, &g);
     EVE_TRY(conv_tc_wgrad_run(g, d_hi, d_lo, x_hi, x_lo, part, 3, &splits, s));
     EVE_TRY(wgrad_reduce(part, splits, g, dw, accumulate, s));
   }
@@ -554,7 +554,7 @@ int conv_bwd_planes(const ConvGeom& g, const void* x_hi, const void* x_lo, const
       EVE_TRY(fill_zero(dx, g.in_elems(), s));
     }
   }
-  ProfScope prof(PROF_CONV_DGRAD, flops, bytes, s);
+  ProfScope prof(PROF_CONV_DGRAD, flops, bytes, s, &g);
   if (s1)
     return conv_tc_run(dgrad_as_fwd(g), d_hi, d_lo, w_hi, w_lo, nullptr, addend, dx, 3, TC_BF16, 1.f,
                        s);

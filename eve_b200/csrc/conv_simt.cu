@@ -418,7 +418,7 @@ int conv_fwd_simt(const ConvGeom& g, const float* x, const float* wf, const floa
   a.Ho = g.OH; a.Wo = g.OW; a.Nn = g.Cout; a.KH = g.KH; a.KW = g.KW;
   a.num = g.stride; a.den = 1; a.dr = 1; a.base = -g.pad;
   a.M = g.N * g.OH * g.OW; a.K = g.K(); a.ldo = ldo;
-  ProfScope prof(PROF_CONV_FWD, conv_flops(g), conv_bytes(g), s);
+  ProfScope prof(PROF_CONV_FWD, conv_flops(g), conv_bytes(g), s, &g);
   return dispatch_gather(a, s);
 }
 
@@ -430,7 +430,7 @@ int conv_dgrad_simt(const ConvGeom& g, const float* dy, int lddy, const float* w
   a.Ho = g.H; a.Wo = g.W; a.Nn = g.Cin; a.KH = g.KH; a.KW = g.KW;
   a.num = 1; a.den = g.stride; a.dr = -1; a.base = g.pad;
   a.M = g.N * g.H * g.W; a.K = g.KH * g.KW * g.Cout; a.ldo = g.Cin;
-  ProfScope prof(PROF_CONV_DGRAD, conv_flops(g), conv_bytes(g), s);
+  ProfScope prof(PROF_CONV_DGRAD, conv_flops(g), conv_bytes(g), s, &g);
   return dispatch_gather(a, s);
 }
 
@@ -449,7 +449,7 @@ int conv_wgrad_simt(const ConvGeom& g, const float* x, const float* dy, int lddy
   a.chunk = cdiv(cdiv(a.P, S), BK) * BK;
   S = cdiv(a.P, a.chunk);
   dim3 grid(cdiv(g.Cout, 64), cdiv(a.KK, 64), S);
-  ProfScope prof(PROF_CONV_WGRAD, conv_flops(g), conv_bytes(g), s);
+  ProfScope prof(PROF_CONV_WGRAD, conv_flops(g), conv_bytes(g), s, &g);
   igemm_wgrad_kernel<<<grid, NT, 0, s>>>(a);
   EVE_LAUNCH_CHECK();
   size_t total = (size_t)g.Cout * g.K();

@@ -39,6 +39,21 @@ class HeatmapParams(C.Structure):
                 ('screen_h', C.c_float), ('sigma', C.c_float)]
 
 
+class LabelArgs(C.Structure):
+    _fields_ = [('n', C.c_int)] + [(k, C.c_void_p) for k in (
+        'left_pog_px', 'right_pog_px', 'left_valid', 'right_valid', 'mm_per_px', 'left_o', 'right_o',
+        'left_R', 'cam', 'left_pog_cm', 'right_pog_cm', 'o', 'pog_px', 'pog_cm', 'valid', 'g')]
+
+
+LOSS_OPS = {'angular': 0, 'mse': 1, 'l1': 2, 'euclidean': 3, 'identity': 4}
+LOSS_MAX_TERMS = 40
+
+
+class LossTerm(C.Structure):
+    _fields_ = [('op', C.c_int), ('dim', C.c_int), ('pred', C.c_void_p), ('gt', C.c_void_p),
+                ('valid', C.c_void_p), ('valid2', C.c_void_p), ('dpred', C.c_void_p)]
+
+
 class AdamParams(C.Structure):
     _fields_ = [('count', C.c_longlong), ('lr', C.c_float), ('beta1', C.c_float),
                 ('beta2', C.c_float), ('eps', C.c_float), ('weight_decay', C.c_float),
@@ -58,6 +73,8 @@ SIGNATURES = {
     'eve_profile_enable': (None, [_I]),
     'eve_profile_reset': (None, []),
     'eve_profile_read': (_I, [_I, _P, _P, _P, _P]),
+    'eve_profile_dump': (C.c_longlong, [_P, C.c_longlong]),
+    'eve_probe_mma_rate': (_I, [_I, _I, _I, _I, _I, _I, _P, _P]),
     'eve_set_conv_mode': (None, [_I]),
     'eve_get_conv_mode': (_I, []),
     'eve_set_option': (_I, [C.c_char_p, _I]),
@@ -101,6 +118,19 @@ SIGNATURES = {
     'eve_soft_argmax_bwd': (_I, [_P, _P, _P, _P, _P]),
     'eve_pog_fwd': (_I, [_I, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P]),
     'eve_pog_bwd': (_I, [_I, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P]),
+    'eve_combined_gaze_fwd': (_I, [_I, _P, _P, _P, _P, _P, _P]),
+    'eve_combined_gaze_bwd': (_I, [_I, _P, _P, _P, _P, _P, _P, _P]),
+    'eve_offset_augmentation_fwd': (_I, [_I, _I, _P, _P, _P, _I, _P, _P]),
+    'eve_offset_augmentation_bwd': (_I, [_I, _I, _P, _P, _P, _I, _P, _P, _P]),
+    'eve_labels_fwd': (_I, [_P, _P]),
+    'eve_heatmap_labels_fwd': (_I, [_P, _P, _P, _I, _P, _P, _P]),
+    'eve_gaze_history_scratch_bytes': (_Z, [_I, _I]),
+    'eve_gaze_history_fwd': (_I, [_I, _I, _I, _P, _P, _F, _P, _P, _P, _Z, _P]),
+    'eve_gaze_history_bwd': (_I, [_I, _I, _I, _P, _P, _F, _P, _P, _P, _Z, _P]),
+    'eve_masked_losses_fwd': (_I, [_I, _P, _I, _I, _P, _P]),
+    'eve_masked_losses_bwd': (_I, [_I, _P, _I, _I, _P, _P]),
+    'eve_heatmap_frame_losses_fwd': (_I, [_I, _I, _P, _P, _P, _P, _P]),
+    'eve_heatmap_frame_losses_bwd': (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
     'eve_adam_clip_workspace_bytes': (_Z, [_P]),
     'eve_adam_clip_step': (_I, [_P, _P, _P, _P, _P, _P, _P, _Z, _P]),
 }

@@ -1,10 +1,12 @@
 """Gaze geometry, heatmaps, soft-argmax and gaze-history maps of the EVE hot path.
 
 Same names, argument meaning and results as the reference's ``src/models/common.py``; the
-three memory-bound pieces -- ``to_screen_coordinates`` (:149-179), ``batch_make_heatmaps``
-(:226-243) and ``soft_argmax`` (:294-323) -- run as hand-written CUDA kernels through the
-C ABI (eve_b200/ops.py), the remaining per-sample 3x3 algebra is batched torch arithmetic on
-the GPU (no Python loop over the batch, unlike :243, :276-287).
+per-frame pieces EVE.forward calls -- ``to_screen_coordinates`` (:149-179),
+``calculate_combined_gaze_direction`` (:129-146), ``apply_offset_augmentation`` (:182-218),
+``batch_make_heatmaps`` (:226-243), ``soft_argmax`` (:294-323) and the gaze-history maps
+(:249-287, as an O(T) recurrence) -- run as hand-written CUDA kernels through the C ABI
+(eve_b200/ops.py).  The small angle / rotation helpers stay torch arithmetic; the ``_*_torch``
+functions are the formulas the kernels are checked against (tests only).
 """
 import math
 
@@ -12,6 +14,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .. import lib as L
 from .. import ops
 from ..config import get_config
 
@@ -88,12 +91,23 @@ def get_intersect_with_zero(o, g):
     return o[..., :2] + t.unsqueeze(-1) * g[..., :2]
 
 
-def calculate_combined_gaze_direction(avg_origin, avg_PoG, head_rotation, camera_transformation):
-    """common.py:129-146."""
+def _combined_gaze_torch(avg_origin, avg_PoG, head_rotation, camera_transformation):
+    """common.py:129-146 in torch arithmetic: the formula the kernel (and its hand-derived VJP in
+    csrc/gaze_math.cuh) is checked against on the CPU; not on the product path."""
     p3 = F.pad(avg_PoG, (0, 1))
     p3 = apply_transformation(camera_transformation, p3)
     d = torch.matmul(head_rotation, (p3 - avg_origin).unsqueeze(-1)).squeeze(-1)
     return vector_to_pitchyaw(-d)
+
+
+def calculate_combined_gaze_direction(avg_origin, avg_PoG, head_rotation, camera_transformation):
+    """common.py:129-146 as one CUDA kernel (one thread per frame; leading dimensions free)."""
+    L.require_cuda(avg_PoG, 'calculate_combined_gaze_direction')
+    lead = avg_PoG.shape[:-1]
+    g = ops.CombinedGazeFn.apply(avg_origin.reshape(-1, 3), avg_PoG.reshape(-1, 2),
+                                 head_rotation.reshape(-1, 3, 3),
+                                 camera_transformation.reshape(-1, 4, 4))
+    return g.reshape(*lead, 2)
 
 
 def to_screen_coordinates(origin, direction, rotation, reference_dict):
@@ -110,7 +124,23 @@ def to_screen_coordinates(origin, direction, rotation, reference_dict):
 
 
 def apply_offset_augmentation(gaze_direction, head_rotation, kappa, inverse_kappa=False):
-    """common.py:182-218."""
+    """common.py:182-218 as one CUDA kernel (one thread per frame).  A kappa that is one draw per
+    clip expanded over time (eve.py:466-477) is read through its [B, 2] base, not copied."""
+    L.require_cuda(gaze_direction, 'apply_offset_augmentation')
+    lead = gaze_direction.shape[:-1]
+    fpk = 1
+    if kappa.ndim == 3 and kappa.shape[1] > 1 and kappa.stride(1) == 0:
+        fpk = kappa.shape[1]
+        kappa = kappa[:, 0]
+    out = ops.OffsetAugmentationFn.apply(gaze_direction.reshape(-1, 2),
+                                         head_rotation.reshape(-1, 3, 3), kappa.reshape(-1, 2),
+                                         fpk, bool(inverse_kappa))
+    return out.reshape(*lead, 2)
+
+
+def _offset_augmentation_torch(gaze_direction, head_rotation, kappa, inverse_kappa=False):
+    """common.py:182-218 in torch arithmetic: checker of the kernel math (tests/test_host_math.py,
+    oracle/check_host_logic.py); not on the product path."""
     d = -pitchyaw_to_vector(gaze_direction)
     d = -torch.matmul(head_rotation.transpose(-1, -2), d.unsqueeze(-1)).squeeze(-1)
     kv = pitchyaw_to_vector(kappa)
@@ -170,6 +200,14 @@ def batch_make_gaze_history_maps(history_timestamps, heatmaps, validity):
     if isinstance(heatmaps, (list, tuple)):
         heatmaps = torch.stack(list(heatmaps), dim=1)
     t = heatmaps.shape[1]
+    return all_gaze_history_maps(history_timestamps[:, :t], heatmaps, validity[:, :t])[:, -1]
+
+
+def _batch_make_gaze_history_maps_torch(history_timestamps, heatmaps, validity):
+    """common.py:276-287 from the explicit weights (torch arithmetic; checker only)."""
+    if isinstance(heatmaps, (list, tuple)):
+        heatmaps = torch.stack(list(heatmaps), dim=1)
+    t = heatmaps.shape[1]
     wgt = gaze_history_weights(history_timestamps[:, :t], validity[:, :t])[:, t - 1]   # [B, t]
     return (wgt.view(wgt.shape[0], t, 1, 1, 1).detach() * heatmaps).sum(dim=1)
 
@@ -184,7 +222,16 @@ def make_gaze_history_map(history_timestamps, heatmaps, validities):
 
 def all_gaze_history_maps(history_timestamps, heatmaps, validity):
     """Every prefix at once: heatmaps [B, T, 1, H, W] -> [B, T, 1, H, W] where slice t is what
-    the reference computes after step t (the O(T^2) Python loop of eve.py:596-601)."""
+    the reference computes after step t (the O(T^2) Python loop of eve.py:596-601).  On the GPU
+    this is the O(T) recurrence kernel eve_gaze_history_fwd (one pass over the heatmaps)."""
+    L.require_cuda(heatmaps, 'gaze history maps')
+    return ops.GazeHistoryFn.apply(heatmaps, history_timestamps, validity,
+                                   float(config.gaze_history_map_decay_per_ms))
+
+
+def _all_gaze_history_maps_torch(history_timestamps, heatmaps, validity):
+    """The same maps from the explicit [T x T] weights (torch arithmetic): checker of the
+    recurrence kernel against the reference's loops; not on the product path."""
     B, T = heatmaps.shape[:2]
     wgt = gaze_history_weights(history_timestamps, validity)            # [B, T, T]
     flat = heatmaps.reshape(B, T, -1)

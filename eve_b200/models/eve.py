@@ -14,6 +14,7 @@ from torch import nn
 
 from ..config import get_config
 from .. import losses as LS
+from .. import ops
 from .common import (all_gaze_history_maps, apply_offset_augmentation, batch_make_heatmaps,
                      calculate_combined_gaze_direction, soft_argmax, to_screen_coordinates)
 from .eye_net import EyeNet
@@ -187,44 +188,47 @@ class EVE(nn.Module):
 
     # ------------------------------------------------------------ losses / metrics --
     def calculate_losses_and_metrics(self, input_dict, intermediate_dict, output_dict):
-        """eve.py:286-439 with the per-clip Python loops of losses/*.py vectorised."""
+        """eve.py:286-439: the same terms under the same keys, collected into ONE table and
+        evaluated by the fused masked-loss kernels (losses.evaluate_terms) instead of ~30 loss
+        objects looping over the batch in Python."""
         d, mid, out = input_dict, intermediate_dict, output_dict
         augment = self.training and config.refine_net_do_offset_augmentation
+        names, terms = [], []
 
-        def term(fn, pred_key, gt_key, ref=None):
+        def term(name, loss, pred_key, gt_key, ref=None, valid2=None):
             ref = d if ref is None else ref
-            return fn(mid[pred_key], gt_key, ref)
+            names.append(name)
+            terms.append((loss, mid[pred_key], ref[gt_key], ref[gt_key + '_validity'], valid2))
 
         for side in ('left', 'right'):
             src = side + ('_g_initial_unaugmented' if augment else '_g_initial')
             if src in mid and side + '_g_tobii' in d:
-                out['loss_ang_%s_g_initial' % side] = term(LS.angular_loss, src, side + '_g_tobii')
+                term('loss_ang_%s_g_initial' % side, LS.angular_loss, src, side + '_g_tobii')
             src = side + ('_PoG_cm_initial_unaugmented' if augment else '_PoG_cm_initial')
             if src in mid and side + '_PoG_cm_tobii' in d:
-                out['loss_mse_%s_PoG_cm_initial' % side] = term(LS.mse_loss, src,
-                                                                side + '_PoG_cm_tobii')
-                out['metric_euc_%s_PoG_cm_initial' % side] = term(LS.euclidean_loss, src,
-                                                                  side + '_PoG_cm_tobii')
+                term('loss_mse_%s_PoG_cm_initial' % side, LS.mse_loss, src, side + '_PoG_cm_tobii')
+                term('metric_euc_%s_PoG_cm_initial' % side, LS.euclidean_loss, src,
+                     side + '_PoG_cm_tobii')
             if side + '_PoG_px_initial' in mid and side + '_PoG_tobii' in d:
-                out['metric_euc_%s_PoG_px_initial' % side] = term(
-                    LS.euclidean_loss, side + '_PoG_px_initial', side + '_PoG_tobii')
+                term('metric_euc_%s_PoG_px_initial' % side, LS.euclidean_loss,
+                     side + '_PoG_px_initial', side + '_PoG_tobii')
             if side + '_pupil_size' in mid and side + '_p' in d:
-                out['loss_l1_%s_pupil_size' % side] = term(LS.l1_loss, side + '_pupil_size',
-                                                           side + '_p')
+                term('loss_l1_%s_pupil_size' % side, LS.l1_loss, side + '_pupil_size', side + '_p')
         if 'left_PoG_tobii' in d and 'right_PoG_tobii' in d:
-            mid['right_PoG_cm_initial_validity'] = (d['left_PoG_tobii_validity']
-                                                    & d['right_PoG_tobii_validity'])
-            out['loss_mse_lr_consistency'] = term(LS.mse_loss, 'left_PoG_cm_initial',
-                                                  'right_PoG_cm_initial', mid)
-            out['metric_euc_lr_consistency'] = term(LS.euclidean_loss, 'left_PoG_cm_initial',
-                                                    'right_PoG_cm_initial', mid)
+            # eve.py:330-341: validity of the left/right consistency terms = left AND right
+            mid['right_PoG_cm_initial_validity'] = d['PoG_px_tobii_validity'] \
+                if 'PoG_px_tobii_validity' in d else (d['left_PoG_tobii_validity']
+                                                      & d['right_PoG_tobii_validity'])
+            term('loss_mse_lr_consistency', LS.mse_loss, 'left_PoG_cm_initial',
+                 'right_PoG_cm_initial', mid)
+            term('metric_euc_lr_consistency', LS.euclidean_loss, 'left_PoG_cm_initial',
+                 'right_PoG_cm_initial', mid)
         src = 'heatmap_initial_unaugmented' if augment else 'heatmap_initial'
         if src in mid and 'heatmap_initial' in d:
-            out['loss_ce_heatmap_initial'] = term(LS.cross_entropy_loss, src, 'heatmap_initial')
+            term('loss_ce_heatmap_initial', LS.cross_entropy_loss, src, 'heatmap_initial')
         if 'heatmap_final' in mid and 'heatmap_final' in d:
-            out['loss_ce_heatmap_final'] = term(LS.cross_entropy_loss, 'heatmap_final',
-                                                'heatmap_final')
-            out['loss_mse_heatmap_final'] = term(LS.mse_loss, 'heatmap_final', 'heatmap_final')
+            term('loss_ce_heatmap_final', LS.cross_entropy_loss, 'heatmap_final', 'heatmap_final')
+            term('loss_mse_heatmap_final', LS.mse_loss, 'heatmap_final', 'heatmap_final')
         stages = ['initial', 'final']
         if config.refine_net_do_offset_augmentation:
             stages.insert(0, 'initial_unaugmented')
@@ -233,10 +237,12 @@ class EVE(nn.Module):
                 k = 'PoG_%s_%s' % (unit, stage)
                 if k in mid and 'PoG_%s_tobii' % unit in d:
                     if stage != 'initial_unaugmented':
-                        out['loss_mse_' + k] = term(LS.mse_loss, k, 'PoG_%s_tobii' % unit)
-                    out['metric_euc_' + k] = term(LS.euclidean_loss, k, 'PoG_%s_tobii' % unit)
+                        term('loss_mse_' + k, LS.mse_loss, k, 'PoG_%s_tobii' % unit)
+                    term('metric_euc_' + k, LS.euclidean_loss, k, 'PoG_%s_tobii' % unit)
             if 'g_' + stage in mid and 'g' in d:
-                out['metric_ang_g_' + stage] = term(LS.angular_loss, 'g_' + stage, 'g')
+                term('metric_ang_g_' + stage, LS.angular_loss, 'g_' + stage, 'g')
+        for name, value in zip(names, LS.evaluate_terms(terms)):
+            out[name] = value
 
     # ---------------------------------------------------------------------- labels --
     @staticmethod
@@ -249,16 +255,13 @@ class EVE(nn.Module):
         return left, right
 
     def calculate_additional_labels(self, full_input_dict, current_epoch=None):
-        """eve.py:441-543 without the Python loops over the batch."""
+        """eve.py:441-543: one kernel for the per-frame label block (PoG in cm, averaged origin
+        and PoG, validity AND, ground-truth combined gaze) and one for the three validity-scaled
+        label heatmaps, instead of Python loops over the batch."""
         d = full_input_dict
         sample_entry = next(iter(d.values()))
         batch_size, sequence_len = sample_entry.shape[0], sample_entry.shape[1]
         dev = sample_entry.device
-        for side in ('left', 'right'):
-            if (side + '_PoG_tobii') in d:
-                d[side + '_PoG_cm_tobii'] = (d[side + '_PoG_tobii']
-                                             * (0.1 * d['millimeters_per_pixel'])).detach()
-                d[side + '_PoG_cm_tobii_validity'] = d[side + '_PoG_tobii_validity']
         if self.training and config.refine_net_do_offset_augmentation:
             assert current_epoch is not None
             assert isinstance(current_epoch, float)
@@ -271,28 +274,55 @@ class EVE(nn.Module):
             else:
                 left_kappas, right_kappas = self.draw_kappas(batch_size)
                 for side, k in (('left', left_kappas), ('right', right_kappas)):
-                    k = np.repeat(np.expand_dims(k, axis=1), sequence_len, axis=1)
-                    d[side + '_kappa_fake'] = torch.tensor(k.astype(np.float32)).to(dev)
+                    k = torch.tensor(k.astype(np.float32)).to(dev)
+                    d[side + '_kappa_fake'] = k.unsqueeze(1).expand(batch_size, sequence_len, 2)
+        full = all(k in d for k in ('left_PoG_tobii', 'right_PoG_tobii', 'left_o', 'right_o',
+                                    'left_R', 'camera_transformation', 'millimeters_per_pixel'))
+        if full:
+            d.update(ops.frame_labels(d))
+            for side in ('left', 'right'):
+                d[side + '_PoG_cm_tobii_validity'] = d[side + '_PoG_tobii_validity']
+            d['o_validity'] = d['left_o_validity']
+            v = d['PoG_px_tobii_validity']
+            d['PoG_cm_tobii_validity'] = v
+            d['g_validity'] = v
+            if config.refine_net_enabled:
+                names = ('initial', 'history', 'final')
+                maps = ops.heatmap_labels(
+                    d['PoG_px_tobii'], v,
+                    [config.gaze_heatmap_sigma_initial, config.gaze_heatmap_sigma_history,
+                     config.gaze_heatmap_sigma_final], config.gaze_heatmap_size,
+                    config.actual_screen_size)
+                for name, hm in zip(names, maps):
+                    d['heatmap_' + name] = hm
+                    d['heatmap_' + name + '_validity'] = v
+            return
+        # partial inputs (inference without labels, eve.py:449-543 guards each block): the same
+        # per-block conditions in small torch expressions
+        for side in ('left', 'right'):
+            if (side + '_PoG_tobii') in d:
+                d[side + '_PoG_cm_tobii'] = (d[side + '_PoG_tobii']
+                                             * (0.1 * d['millimeters_per_pixel'])).detach()
+                d[side + '_PoG_cm_tobii_validity'] = d[side + '_PoG_tobii_validity']
         if 'left_o' in d:
-            d['o'] = torch.stack([d['left_o'], d['right_o']], dim=-1).mean(dim=-1).detach()
+            d['o'] = ((d['left_o'] + d['right_o']) / 2.0).detach()
             d['o_validity'] = d['left_o_validity']
         if 'left_PoG_tobii' in d:
-            d['PoG_px_tobii'] = torch.stack([d['left_PoG_tobii'], d['right_PoG_tobii']],
-                                            dim=-1).mean(dim=-1).detach()
-            d['PoG_cm_tobii'] = torch.stack([d['left_PoG_cm_tobii'], d['right_PoG_cm_tobii']],
-                                            dim=-1).mean(dim=-1).detach()
+            d['PoG_px_tobii'] = ((d['left_PoG_tobii'] + d['right_PoG_tobii']) / 2.0).detach()
+            d['PoG_cm_tobii'] = ((d['left_PoG_cm_tobii'] + d['right_PoG_cm_tobii']) / 2.0).detach()
             v = (d['left_PoG_tobii_validity'].bool() & d['right_PoG_tobii_validity'].bool()).detach()
             d['PoG_px_tobii_validity'] = v
             d['PoG_cm_tobii_validity'] = v
             if config.refine_net_enabled:
-                vf = v.float().view(batch_size, sequence_len, 1, 1, 1)
-                with torch.no_grad():
-                    for name, sigma in (('initial', config.gaze_heatmap_sigma_initial),
-                                        ('history', config.gaze_heatmap_sigma_history),
-                                        ('final', config.gaze_heatmap_sigma_final)):
-                        d['heatmap_' + name] = batch_make_heatmaps(d['PoG_px_tobii'], sigma) * vf
-                        d['heatmap_' + name + '_validity'] = v
-        if 'PoG_cm_tobii' in d:
+                maps = ops.heatmap_labels(
+                    d['PoG_px_tobii'], v,
+                    [config.gaze_heatmap_sigma_initial, config.gaze_heatmap_sigma_history,
+                     config.gaze_heatmap_sigma_final], config.gaze_heatmap_size,
+                    config.actual_screen_size)
+                for name, hm in zip(('initial', 'history', 'final'), maps):
+                    d['heatmap_' + name] = hm
+                    d['heatmap_' + name + '_validity'] = v
+        if 'PoG_cm_tobii' in d and 'o' in d:
             d['g'] = calculate_combined_gaze_direction(
                 d['o'], 10.0 * d['PoG_cm_tobii'], d['left_R'], d['camera_transformation'])
             d['g_validity'] = d['PoG_cm_tobii_validity']
@@ -311,9 +341,10 @@ class EVE(nn.Module):
             mid[side + '_PoG_cm_' + output_suffix] = 0.1 * mm
             mid[side + '_PoG_px_' + output_suffix] = px
         for unit in ('px', 'cm'):
-            mid['PoG_%s_%s' % (unit, output_suffix)] = torch.stack(
-                [mid['left_PoG_%s_%s' % (unit, output_suffix)],
-                 mid['right_PoG_%s_%s' % (unit, output_suffix)]], dim=-1).mean(dim=-1)
+            # torch.stack([l, r], -1).mean(-1) (eve.py:571-578) == (l + r) / 2 exactly in fp32
+            mid['PoG_%s_%s' % (unit, output_suffix)] = (
+                mid['left_PoG_%s_%s' % (unit, output_suffix)]
+                + mid['right_PoG_%s_%s' % (unit, output_suffix)]) / 2.0
         mid['PoG_mm_' + output_suffix] = 10.0 * mid['PoG_cm_' + output_suffix]
         mid['g_' + output_suffix] = calculate_combined_gaze_direction(
             d['o'], mid['PoG_mm_' + output_suffix], d['left_R'], d['camera_transformation'])

@@ -398,6 +398,262 @@ class PogFn(torch.autograd.Function):
         return None, dg, None, None, None, None
 
 
+class CombinedGazeFn(torch.autograd.Function):
+    """calculate_combined_gaze_direction (common.py:129-146): one kernel, one thread per frame.
+    Gradient flows to the averaged PoG only (origin, rotation and calibration are data)."""
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, origin, pog_mm, head_rot, cam):
+        L.require_cuda(pog_mm, 'calculate_combined_gaze_direction')
+        lib = L.load()
+        origin, pog_mm, head_rot, cam = (_f32c(t) for t in (origin, pog_mm, head_rot, cam))
+        n = pog_mm.shape[0]
+        g = torch.empty((n, 2), dtype=torch.float32, device=pog_mm.device)
+        L.check(lib.eve_combined_gaze_fwd(n, L.ptr(origin), L.ptr(pog_mm), L.ptr(head_rot),
+                                          L.ptr(cam), L.ptr(g), L.stream_ptr()),
+                'eve_combined_gaze_fwd')
+        ctx.save_for_backward(origin, pog_mm, head_rot, cam)
+        return g
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, dg):
+        lib = L.load()
+        origin, pog_mm, head_rot, cam = ctx.saved_tensors
+        dg = _f32c(dg)
+        dp = torch.empty_like(pog_mm)
+        L.check(lib.eve_combined_gaze_bwd(pog_mm.shape[0], L.ptr(origin), L.ptr(pog_mm),
+                                          L.ptr(head_rot), L.ptr(cam), L.ptr(dg), L.ptr(dp),
+                                          L.stream_ptr()), 'eve_combined_gaze_bwd')
+        return None, dp, None, None
+
+
+class OffsetAugmentationFn(torch.autograd.Function):
+    """apply_offset_augmentation (common.py:182-218).  ``kappa`` is [n / frames_per_kappa, 2]: one
+    kappa per clip repeated over time (eve.py:466-477) needs no expanded copy."""
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, g, head_rot, kappa, frames_per_kappa, inverse):
+        L.require_cuda(g, 'apply_offset_augmentation')
+        lib = L.load()
+        g, head_rot, kappa = _f32c(g), _f32c(head_rot), _f32c(kappa)
+        n = g.shape[0]
+        assert kappa.shape[0] * int(frames_per_kappa) == n
+        out = torch.empty_like(g)
+        L.check(lib.eve_offset_augmentation_fwd(n, int(frames_per_kappa), L.ptr(g), L.ptr(head_rot),
+                                                L.ptr(kappa), int(bool(inverse)), L.ptr(out),
+                                                L.stream_ptr()), 'eve_offset_augmentation_fwd')
+        ctx.args = (int(frames_per_kappa), int(bool(inverse)))
+        ctx.save_for_backward(g, head_rot, kappa)
+        return out
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, dout):
+        lib = L.load()
+        g, head_rot, kappa = ctx.saved_tensors
+        dout = _f32c(dout)
+        dg = torch.empty_like(g)
+        L.check(lib.eve_offset_augmentation_bwd(g.shape[0], ctx.args[0], L.ptr(g), L.ptr(head_rot),
+                                                L.ptr(kappa), ctx.args[1], L.ptr(dout), L.ptr(dg),
+                                                L.stream_ptr()), 'eve_offset_augmentation_bwd')
+        return dg, None, None, None, None
+
+
+def _u8(t):
+    """Validity flags as a contiguous byte tensor (torch.bool is one byte per element)."""
+    if t.dtype == torch.bool:
+        return t.contiguous().view(torch.uint8)
+    return (t != 0).contiguous().view(torch.uint8)
+
+
+def frame_labels(d):
+    """The per-frame block of EVE.calculate_additional_labels (eve.py:449-456, 498-517, 534-543)
+    as one kernel; returns the dict entries it derives (no gradients: labels)."""
+    lib = L.load()
+    lp = _f32c(d['left_PoG_tobii'])
+    L.require_cuda(lp, 'calculate_additional_labels')
+    lead = lp.shape[:-1]
+    n = lp.numel() // 2
+    dev = lp.device
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    out = {'left_PoG_cm_tobii': f(*lead, 2), 'right_PoG_cm_tobii': f(*lead, 2), 'o': f(*lead, 3),
+           'PoG_px_tobii': f(*lead, 2), 'PoG_cm_tobii': f(*lead, 2), 'g': f(*lead, 2)}
+    valid = torch.empty(lead, dtype=torch.bool, device=dev)
+    keep = [_f32c(d[k]) for k in ('right_PoG_tobii', 'millimeters_per_pixel', 'left_o', 'right_o',
+                                  'left_R', 'camera_transformation')]
+    lv, rv = _u8(d['left_PoG_tobii_validity']), _u8(d['right_PoG_tobii_validity'])
+    a = L.LabelArgs(n, L.ptr(lp), L.ptr(keep[0]), L.ptr(lv), L.ptr(rv), L.ptr(keep[1]),
+                    L.ptr(keep[2]), L.ptr(keep[3]), L.ptr(keep[4]), L.ptr(keep[5]),
+                    L.ptr(out['left_PoG_cm_tobii']), L.ptr(out['right_PoG_cm_tobii']),
+                    L.ptr(out['o']), L.ptr(out['PoG_px_tobii']), L.ptr(out['PoG_cm_tobii']),
+                    valid.data_ptr(), L.ptr(out['g']))
+    with torch.cuda.device(dev):
+        L.check(lib.eve_labels_fwd(C.byref(a), L.stream_ptr()), 'eve_labels_fwd')
+    out['PoG_px_tobii_validity'] = valid
+    return out
+
+
+def heatmap_labels(centres, valid, sigmas, size_wh, screen_wh):
+    """eve.py:519-531: the validity-scaled label heatmaps for up to three sigmas, one launch.
+    centres [..., 2] px, valid [...] bool -> list of [..., 1, H, W]."""
+    lib = L.load()
+    centres = _f32c(centres)
+    L.require_cuda(centres, 'label heatmaps')
+    lead = centres.shape[:-1]
+    n = centres.numel() // 2
+    w, h = int(size_wh[0]), int(size_wh[1])
+    outs = [torch.empty((*lead, 1, h, w), dtype=torch.float32, device=centres.device)
+            for _ in sigmas]
+    v = _u8(valid)
+    p = L.HeatmapParams(n, w, h, float(screen_wh[0]), float(screen_wh[1]), 1.0)
+    sg = (C.c_float * len(sigmas))(*[float(s_) for s_ in sigmas])
+    with torch.cuda.device(centres.device):
+        L.check(lib.eve_heatmap_labels_fwd(C.byref(p), L.ptr(centres), L.ptr(v), len(sigmas), sg,
+                                           L.ptr_table(outs), L.stream_ptr()),
+                'eve_heatmap_labels_fwd')
+    return outs
+
+
+class GazeHistoryFn(torch.autograd.Function):
+    """Gaze-history maps of every prefix (common.py:249-287 evaluated after each step as in
+    eve.py:596-601) by the O(T) recurrence of eve_gaze_history_fwd.
+    heatmaps [B,T,1,H,W], timestamps [B,T] int64, validity [B,T] -> [B,T,1,H,W]."""
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, heatmaps, timestamps, validity, decay):
+        L.require_cuda(heatmaps, 'gaze history maps')
+        lib = L.load()
+        heatmaps = _f32c(heatmaps)
+        B, T = heatmaps.shape[:2]
+        hw = heatmaps[0, 0].numel()
+        ts = timestamps.to(torch.int64).contiguous()
+        v = _u8(validity)
+        out = torch.empty_like(heatmaps)
+        ws = L.workspace(lib.eve_gaze_history_scratch_bytes(B, T), heatmaps.device, 'hist')
+        L.check(lib.eve_gaze_history_fwd(B, T, hw, L.ptr(ts), L.ptr(v), float(decay),
+                                         L.ptr(heatmaps), L.ptr(out), L.ptr(ws), ws.numel(),
+                                         L.stream_ptr()), 'eve_gaze_history_fwd')
+        ctx.args = (B, T, hw, float(decay))
+        ctx.save_for_backward(ts, v)
+        return out
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, dout):
+        lib = L.load()
+        ts, v = ctx.saved_tensors
+        B, T, hw, decay = ctx.args
+        dout = _f32c(dout)
+        dh = torch.empty_like(dout)
+        ws = L.workspace(lib.eve_gaze_history_scratch_bytes(B, T), dout.device, 'hist')
+        L.check(lib.eve_gaze_history_bwd(B, T, hw, L.ptr(ts), L.ptr(v), decay, L.ptr(dout),
+                                         L.ptr(dh), L.ptr(ws), ws.numel(), L.stream_ptr()),
+                'eve_gaze_history_bwd')
+        return dh, None, None, None
+
+
+# --------------------------------------------------------------------------- losses --
+class HeatmapFrameLossFn(torch.autograd.Function):
+    """Per-frame BCE and MSE of heatmap pairs (cross_entropy.py:29-35, mse.py) from one read:
+    pred / gt [B,T,1,H,W] -> (bce [B,T], mse [B,T])."""
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, pred, gt):
+        L.require_cuda(pred, 'heatmap losses')
+        lib = L.load()
+        pred, gt = _f32c(pred), _f32c(gt)
+        lead = pred.shape[:2]
+        n = lead[0] * lead[1]
+        hw = pred.numel() // max(n, 1)
+        bce = torch.empty(lead, dtype=torch.float32, device=pred.device)
+        mse = torch.empty(lead, dtype=torch.float32, device=pred.device)
+        L.check(lib.eve_heatmap_frame_losses_fwd(n, hw, L.ptr(pred), L.ptr(gt), L.ptr(bce),
+                                                 L.ptr(mse), L.stream_ptr()),
+                'eve_heatmap_frame_losses_fwd')
+        ctx.args = (n, hw)
+        ctx.save_for_backward(pred, gt)
+        ctx.set_materialize_grads(False)
+        return bce, mse
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, dbce, dmse):
+        if dbce is None and dmse is None:
+            return None, None
+        lib = L.load()
+        pred, gt = ctx.saved_tensors
+        n, hw = ctx.args
+        dbce, dmse = _f32c(dbce), _f32c(dmse)
+        dp = torch.empty_like(pred)
+        L.check(lib.eve_heatmap_frame_losses_bwd(n, hw, L.ptr(pred), L.ptr(gt), L.ptr(dbce),
+                                                 L.ptr(dmse), L.ptr(dp), L.stream_ptr()),
+                'eve_heatmap_frame_losses_bwd')
+        return dp, None
+
+
+class MaskedLossesFn(torch.autograd.Function):
+    """A table of validity-masked sequence losses (base_loss_with_validity.py:32-73) in one
+    launch.  ``spec`` is a list of (op, pred_index, gt, valid, valid2); ``preds`` the distinct
+    prediction tensors [B,T,dim] / [B,T].  Returns a [len(spec)] vector of scalars."""
+
+    @staticmethod
+    def _table(spec, preds, dpreds):
+        terms = (L.LossTerm * len(spec))()
+        for i, (op, pi, gt, valid, valid2) in enumerate(spec):
+            pr = preds[pi]
+            dim = 1 if pr.ndim == 2 else pr.shape[-1]
+            terms[i] = L.LossTerm(L.LOSS_OPS[op], dim, L.ptr(pr), L.ptr(gt), L.ptr(valid),
+                                  L.ptr(valid2), None if dpreds is None or dpreds[pi] is None
+                                  else dpreds[pi].data_ptr())
+        return terms
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, spec, *preds):
+        lib = L.load()
+        assert 0 < len(spec) <= L.LOSS_MAX_TERMS
+        preds = [_f32c(p) for p in preds]
+        L.require_cuda(preds[0], 'losses')
+        B, T = preds[0].shape[:2]
+        spec = [(op, pi, None if gt is None else _f32c(gt), _u8(v), None if v2 is None else _u8(v2))
+                for op, pi, gt, v, v2 in spec]
+        for op, pi, gt, v, v2 in spec:
+            assert preds[pi].shape[:2] == (B, T) and v.shape == (B, T)
+            assert gt is None or gt.shape == preds[pi].shape, (op, gt.shape, preds[pi].shape)
+        out = torch.empty(len(spec), dtype=torch.float32, device=preds[0].device)
+        terms = MaskedLossesFn._table(spec, preds, None)
+        L.check(lib.eve_masked_losses_fwd(len(spec), terms, B, T, L.ptr(out), L.stream_ptr()),
+                'eve_masked_losses_fwd')
+        ctx.spec, ctx.bt = spec, (B, T)
+        ctx.save_for_backward(*preds)
+        return out
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, dout):
+        lib = L.load()
+        preds = ctx.saved_tensors
+        B, T = ctx.bt
+        dout = _f32c(dout)
+        need = [ctx.needs_input_grad[1 + i] for i in range(len(preds))]
+        # one zeroed flat buffer for every gradient, sliced per prediction tensor
+        sizes = [p.numel() if nd else 0 for p, nd in zip(preds, need)]
+        flat = torch.zeros(max(sum(sizes), 1), dtype=torch.float32, device=dout.device)
+        dpreds, off = [], 0
+        for p, nd, sz in zip(preds, need, sizes):
+            dpreds.append(flat[off:off + sz].view(p.shape) if nd else None)
+            off += sz
+        terms = MaskedLossesFn._table(ctx.spec, preds, dpreds)
+        L.check(lib.eve_masked_losses_bwd(len(ctx.spec), terms, B, T, L.ptr(dout), L.stream_ptr()),
+                'eve_masked_losses_bwd')
+        return (None,) + tuple(dpreds)
+
+
 # ------------------------------------------------------------------- fused optimiser --
 def adam_clip_step(params, grads, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8,
                    weight_decay=0.0, max_norm=0.0, grad_scale=1.0, step_dev=None, lr_dev=None):

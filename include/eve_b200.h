@@ -48,6 +48,15 @@ long long eve_launch_count(void);
 void eve_profile_enable(int on);
 void eve_profile_reset(void);
 int eve_profile_read(int kind, double* ms, double* flops, double* bytes, long long* launches);
+/* Per-launch listing of the recorded convolution passes, one text line each:
+ * "kind N H W Cin Cout ksize stride ms flops bytes".  Returns the bytes the listing needs
+ * (including the terminating NUL); call with buf = NULL to size the buffer. */
+long long eve_profile_dump(char* buf, long long cap);
+/* Hardware probe (measurement aid): `grid` CTAs each issue reps x nmma
+ * tcgen05.mma (M=128, N=n, K=16, both operands in shared memory, A start shifted by
+ * a_shift_bytes) and report their clock64 span in cycles_out[grid] (device memory). */
+int eve_probe_mma_rate(int n, int nmma, int reps, int a_shift_bytes, int distinct_a, int grid,
+                       long long* cycles_out, eve_stream_t stream);
 
 /* ------------------------------------------------------------------ building blocks --
  * Exposed so that each kernel family can be parity-tested on its own.  NHWC fp32. */
@@ -271,6 +280,94 @@ int eve_pog_fwd(int n, const float* origin, const float* g, const float* rot,
 int eve_pog_bwd(int n, const float* origin, const float* g, const float* rot,
                 const float* inv_cam, const float* ppm, float screen_w, float screen_h,
                 const float* dpog_mm, const float* dpog_px, float* dg, eve_stream_t stream);
+
+/* common.py:129-146 calculate_combined_gaze_direction: per frame origin[n,3] (averaged eye origin),
+ * pog_mm[n,2], head_rot[n,3,3], cam[n,4,4] (camera_transformation) -> g[n,2] (pitch, yaw).
+ * bwd: gradient w.r.t. pog_mm only. */
+int eve_combined_gaze_fwd(int n, const float* origin, const float* pog_mm, const float* head_rot,
+                          const float* cam, float* g, eve_stream_t stream);
+int eve_combined_gaze_bwd(int n, const float* origin, const float* pog_mm, const float* head_rot,
+                          const float* cam, const float* dg, float* dpog_mm, eve_stream_t stream);
+/* common.py:182-218 apply_offset_augmentation: g[n,2], head_rot[n,3,3], kappa[n/frames_per_kappa,2]
+ * (eve.py:466-477 draws one kappa per clip and repeats it over time: frames_per_kappa = T; pass 1
+ * for a per-frame kappa) -> out[n,2].  bwd: gradient w.r.t. g only (kappa is data). */
+int eve_offset_augmentation_fwd(int n, int frames_per_kappa, const float* g, const float* head_rot,
+                                const float* kappa, int inverse_kappa, float* out,
+                                eve_stream_t stream);
+int eve_offset_augmentation_bwd(int n, int frames_per_kappa, const float* g, const float* head_rot,
+                                const float* kappa, int inverse_kappa, const float* dout, float* dg,
+                                eve_stream_t stream);
+/* eve.py:441-543 EVE.calculate_additional_labels, the per-frame block: PoG labels in cm
+ * (:449-456), averaged origin / PoG and the left&right validity (:498-517), ground-truth combined
+ * gaze g (:534-543).  All arrays [n, .]; validity arrays are bytes (torch.bool). */
+typedef struct {
+  int n;
+  const float *left_pog_px, *right_pog_px;          /* [n,2] left/right_PoG_tobii */
+  const unsigned char *left_valid, *right_valid;    /* [n] */
+  const float* mm_per_px;                           /* [n,2] millimeters_per_pixel */
+  const float *left_o, *right_o;                    /* [n,3] */
+  const float* left_R;                              /* [n,3,3] */
+  const float* cam;                                 /* [n,4,4] camera_transformation */
+  float *left_pog_cm, *right_pog_cm;                /* out [n,2] */
+  float* o;                                         /* out [n,3] */
+  float *pog_px, *pog_cm;                           /* out [n,2] */
+  unsigned char* valid;                             /* out [n] */
+  float* g;                                         /* out [n,2] */
+} eve_label_args;
+int eve_labels_fwd(const eve_label_args* a, eve_stream_t stream);
+/* eve.py:519-531: nsig (<= 3) label heatmaps per frame from one launch,
+ * outs[s][n,1,hm_h,hm_w] = make_heatmap(centres_px[n], sigmas[s]) * valid[n]
+ * (sigmas and outs are HOST arrays; p->sigma is ignored). */
+int eve_heatmap_labels_fwd(const eve_heatmap_params* p, const float* centres_px,
+                           const unsigned char* valid, int nsig, const float* sigmas,
+                           float* const* outs, eve_stream_t stream);
+/* common.py:249-287 gaze-history maps for every prefix of a clip as an O(T) recurrence (the
+ * reference re-sums the history at every step, eve.py:596-601): timestamps[batch,steps] int64
+ * (0 = padded frame), valid[batch,steps] bytes, heatmaps / out [batch,steps,hw].
+ * bwd: gradient w.r.t. heatmaps.  scratch: eve_gaze_history_scratch_bytes(). */
+size_t eve_gaze_history_scratch_bytes(int batch, int steps);
+int eve_gaze_history_fwd(int batch, int steps, int hw, const long long* timestamps,
+                         const unsigned char* valid, float decay, const float* heatmaps, float* out,
+                         void* scratch, size_t scratch_bytes, eve_stream_t stream);
+int eve_gaze_history_bwd(int batch, int steps, int hw, const long long* timestamps,
+                         const unsigned char* valid, float decay, const float* dout,
+                         float* dheatmaps, void* scratch, size_t scratch_bytes,
+                         eve_stream_t stream);
+
+/* ------------------------------------------------------------- losses and metrics --
+ * eve.py:286-439 + losses/base_loss_with_validity.py:32-73: a table of validity-masked sequence
+ * losses, each  mean_b( sum_t(valid * l) / n_valid_b  [divided only if n_valid_b > 1] ),
+ * evaluated by ONE launch; pred/gt are [batch,steps,dim], valid [batch,steps] bytes. */
+enum {
+  EVE_LOSS_ANGULAR = 0,   /* losses/angular.py: angle between two pitch/yaw pairs, degrees (dim 2) */
+  EVE_LOSS_MSE = 1,       /* mean over dim of (a-b)^2 */
+  EVE_LOSS_L1 = 2,        /* mean over dim of |a-b| */
+  EVE_LOSS_EUCLIDEAN = 3, /* sqrt(sum over dim of (a-b)^2) */
+  EVE_LOSS_IDENTITY = 4   /* pred[batch,steps] already holds the per-frame loss (heatmap terms) */
+};
+#define EVE_LOSS_MAX_TERMS 40
+typedef struct {
+  int op, dim;
+  const float* pred;
+  const float* gt;              /* NULL for EVE_LOSS_IDENTITY */
+  const unsigned char* valid;
+  const unsigned char* valid2;  /* optional second mask, ANDed (lr-consistency terms) */
+  float* dpred;                 /* bwd only: gradient buffer of pred, ACCUMULATED into (terms that
+                                   share a prediction share it; zero it first); NULL = no gradient */
+} eve_loss_term;
+/* out[nterms] / dout[nterms] are DEVICE arrays; `terms` is a HOST array (copied into the launch) */
+int eve_masked_losses_fwd(int nterms, const eve_loss_term* terms, int batch, int steps, float* out,
+                          eve_stream_t stream);
+int eve_masked_losses_bwd(int nterms, const eve_loss_term* terms, int batch, int steps,
+                          const float* dout, eve_stream_t stream);
+/* cross_entropy.py:29-35 / mse.py on heatmaps: per frame f, bce[f] = mean over hw of
+ * F.binary_cross_entropy(pred, gt) (logs clamped at -100) and mse[f] = mean (pred-gt)^2; either
+ * output may be NULL.  bwd: dpred = dbce[f] * dBCE + dmse[f] * dMSE (either may be NULL). */
+int eve_heatmap_frame_losses_fwd(int n, int hw, const float* pred, const float* gt, float* bce,
+                                 float* mse, eve_stream_t stream);
+int eve_heatmap_frame_losses_bwd(int n, int hw, const float* pred, const float* gt,
+                                 const float* dbce, const float* dmse, float* dpred,
+                                 eve_stream_t stream);
 
 /* ------------------------------------------------------------------ optimiser step --
  * training.py:492-502 + train.py:49-55: clip_grad_norm_(max_norm) then Adam with L2

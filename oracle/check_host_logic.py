@@ -77,12 +77,12 @@ def main():
                                          RC.get_intersect_with_zero(o3, g3))
     pog = torch.randn(n, 2, generator=g) * 150.0
     out['calculate_combined_gaze_direction'] = err(
-        PC.calculate_combined_gaze_direction(o3, pog, R, T),
+        PC._combined_gaze_torch(o3, pog, R, T),
         RC.calculate_combined_gaze_direction(o3, pog, R, T))
     kappa = torch.randn(n, 2, generator=g) * 0.05
     for inv in (False, True):
         out['apply_offset_augmentation/inverse=%d' % inv] = err(
-            PC.apply_offset_augmentation(py, R, kappa, inverse_kappa=inv),
+            PC._offset_augmentation_torch(py, R, kappa, inverse_kappa=inv),
             RC.apply_offset_augmentation(py, R, kappa, inverse_kappa=inv))
 
     # gaze history maps: the reference's O(T^2) Python loops against the batched weights
@@ -93,19 +93,19 @@ def main():
     val = torch.rand(B, Tn, generator=g) > 0.25
     hms = torch.rand(B, Tn, 1, H, W, generator=g)
     worst_b, worst_all = 0.0, 0.0
-    allmaps = PC.all_gaze_history_maps(ts, hms, val)
+    allmaps = PC._all_gaze_history_maps_torch(ts, hms, val)
     for t in range(1, Tn + 1):
         if bool((ts[:, :t] == 0).all(dim=1).any()):
             continue                                 # the reference cannot index an all-zero prefix
         lst = [hms[:, i] for i in range(t)]
         want = RC.batch_make_gaze_history_maps(ts, lst, val)
-        worst_b = max(worst_b, err(PC.batch_make_gaze_history_maps(ts, lst, val), want))
+        worst_b = max(worst_b, err(PC._batch_make_gaze_history_maps_torch(ts, lst, val), want))
         worst_all = max(worst_all, err(allmaps[:, t - 1], want))
     out['batch_make_gaze_history_maps'] = worst_b
     out['all_gaze_history_maps'] = worst_all
     one = RC.make_gaze_history_map(ts[1], [hms[1, i] for i in range(Tn)], val[1])
-    out['make_gaze_history_map'] = err(PC.make_gaze_history_map(ts[1], [hms[1, i] for i in range(Tn)],
-                                                                val[1]), one)
+    out['make_gaze_history_map'] = err(PC._batch_make_gaze_history_maps_torch(
+        ts[1:2], [hms[1:2, i] for i in range(Tn)], val[1:2])[0], one)
 
     # validity-masked sequence losses (loop over the batch in the reference, one expression here)
     B, Tn = 5, 9
@@ -116,20 +116,20 @@ def main():
     ref = {'g_validity': valid, 'p_validity': valid, 'h_validity': valid, 's_validity': valid}
     a2, b2 = (torch.rand(B, Tn, 2, generator=g) - 0.5), (torch.rand(B, Tn, 2, generator=g) - 0.5)
     ref['g'] = b2
-    out['loss/angular'] = err(PL.angular_loss(a2, 'g', ref), RAng()(a2, 'g', ref))
+    out['loss/angular'] = err(PL.angular_loss.torch_formula(a2, 'g', ref), RAng()(a2, 'g', ref))
     ref['p'] = b2 * 300.0
-    out['loss/euclidean'] = err(PL.euclidean_loss(a2 * 300.0, 'p', ref), REuc()(a2 * 300.0, 'p', ref))
-    out['loss/mse'] = err(PL.mse_loss(a2, 'g', ref), RMse()(a2, 'g', ref))
-    out['loss/l1'] = err(PL.l1_loss(a2, 'g', ref), RL1()(a2, 'g', ref))
+    out['loss/euclidean'] = err(PL.euclidean_loss.torch_formula(a2 * 300.0, 'p', ref), REuc()(a2 * 300.0, 'p', ref))
+    out['loss/mse'] = err(PL.mse_loss.torch_formula(a2, 'g', ref), RMse()(a2, 'g', ref))
+    out['loss/l1'] = err(PL.l1_loss.torch_formula(a2, 'g', ref), RL1()(a2, 'g', ref))
     s1, s2 = torch.rand(B, Tn, generator=g), torch.rand(B, Tn, generator=g)
     ref['s'] = s2
-    out['loss/mse_scalar'] = err(PL.mse_loss(s1, 's', ref), RMse()(s1, 's', ref))
-    out['loss/l1_scalar'] = err(PL.l1_loss(s1, 's', ref), RL1()(s1, 's', ref))
+    out['loss/mse_scalar'] = err(PL.mse_loss.torch_formula(s1, 's', ref), RMse()(s1, 's', ref))
+    out['loss/l1_scalar'] = err(PL.l1_loss.torch_formula(s1, 's', ref), RL1()(s1, 's', ref))
     h1 = torch.rand(B, Tn, 1, 6, 8, generator=g).clamp(1e-4, 1 - 1e-4)
     h2 = torch.rand(B, Tn, 1, 6, 8, generator=g)
     ref['h'] = h2
-    out['loss/cross_entropy'] = err(PL.cross_entropy_loss(h1, 'h', ref), RCe()(h1, 'h', ref))
-    out['loss/mse_heatmap'] = err(PL.mse_loss(h1, 'h', ref), RMse()(h1, 'h', ref))
+    out['loss/cross_entropy'] = err(PL.cross_entropy_loss.torch_formula(h1, 'h', ref), RCe()(h1, 'h', ref))
+    out['loss/mse_heatmap'] = err(PL.mse_loss.torch_formula(h1, 'h', ref), RMse()(h1, 'h', ref))
     print(json.dumps(out))
 
 

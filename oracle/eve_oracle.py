@@ -406,7 +406,14 @@ def euclidean_per_frame(a, b):
 
 def bce_per_frame(a, b):
     """cross_entropy.py:29-35: F.binary_cross_entropy per frame (the reference's own call;
-    its backward stays finite when a saturates to exactly 0 or 1)."""
+    its backward stays finite when a saturates to exactly 0 or 1).
+
+    fp64 evaluations only (the yardstick the parity tests measure fp32 noise against): the
+    reference's heatmaps are 1e-8 + exp(.) (common.py:243), which rounds to <= 1 in fp32 but is
+    1 + 1e-8 in fp64 at a pixel centre, where F.binary_cross_entropy raises; clamp there."""
+    if a.dtype == torch.float64:
+        a = a.clamp(max=1.0)
+        b = b.clamp(max=1.0)
     return F.binary_cross_entropy(a, b, reduction='none').mean(dim=_feature_dims(a))
 
 

@@ -1,0 +1,96 @@
+"""The device math of the geometry / loss kernels, checked on the CPU.
+
+eve_b200/csrc/gaze_math.cuh holds the value and the hand-derived vector-Jacobian products of the
+gaze geometry (common.py:32-218) and of the angular loss (losses/angular.py) as scalar-templated
+host/device functions.  Here the header is compiled for the host in double precision (g++) and
+every function and VJP is compared with torch autograd over the product's torch formulas, which
+tests/test_host_logic.py pins to the unmodified reference functions."""
+import ctypes as C
+import math
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def hm():
+    src = os.path.join(REPO, 'tests', 'host_math', 'gaze_math_host.cpp')
+    out = os.path.join(tempfile.mkdtemp(prefix='eve_hm_'), 'libgm.so')
+    subprocess.check_call(['g++', '-O1', '-shared', '-fPIC', '-o', out, src])
+    return C.CDLL(out)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _rot(n, g):
+    from eve_b200.models.common import pitchyaw_to_rotation
+    return pitchyaw_to_rotation(torch.rand(n, 2, generator=g, dtype=torch.float64) - 0.5)
+
+
+def test_combined_gaze_and_its_vjp(hm):
+    from eve_b200.models.common import _combined_gaze_torch as calculate_combined_gaze_direction
+    g = torch.Generator().manual_seed(0)
+    n = 64
+    o = torch.randn(n, 3, generator=g, dtype=torch.float64) * 5 + torch.tensor([0.0, 0.0, 600.0])
+    pog = (torch.rand(n, 2, generator=g, dtype=torch.float64) * 500).requires_grad_(True)
+    R = _rot(n, g)
+    cam = torch.eye(4, dtype=torch.float64).repeat(n, 1, 1)
+    cam[:, :3, :3] = _rot(n, g)
+    cam[:, :3, 3] = torch.randn(n, 3, generator=g, dtype=torch.float64) * 20
+    want = calculate_combined_gaze_direction(o, pog, R, cam)
+    gg = torch.randn(n, 2, generator=g, dtype=torch.float64)
+    want.backward(gg)
+    got, dpog = np.zeros((n, 2)), np.zeros((n, 2))
+    args = [np.ascontiguousarray(t.detach().numpy()) for t in (o, pog, R, cam)]
+    hm.hm_combined_gaze(n, *map(_p, args), _p(got))
+    hm.hm_combined_gaze_vjp(n, *map(_p, args), _p(np.ascontiguousarray(gg.numpy())), _p(dpog))
+    assert np.abs(got - want.detach().numpy()).max() < 1e-12
+    assert np.abs(dpog - pog.grad.numpy()).max() < 1e-12 * max(1.0, np.abs(dpog).max())
+
+
+@pytest.mark.parametrize('inverse', [False, True])
+def test_offset_augmentation_and_its_vjp(hm, inverse):
+    from eve_b200.models.common import _offset_augmentation_torch as apply_offset_augmentation
+    g = torch.Generator().manual_seed(1)
+    n = 64
+    gz = ((torch.rand(n, 2, generator=g, dtype=torch.float64) - 0.5) * 0.8).requires_grad_(True)
+    R = _rot(n, g)
+    kappa = torch.randn(n, 2, generator=g, dtype=torch.float64) * math.radians(3.0)
+    want = apply_offset_augmentation(gz, R, kappa, inverse_kappa=inverse)
+    gout = torch.randn(n, 2, generator=g, dtype=torch.float64)
+    want.backward(gout)
+    got, dg = np.zeros((n, 2)), np.zeros((n, 2))
+    args = [np.ascontiguousarray(t.detach().numpy()) for t in (gz, R, kappa)]
+    hm.hm_offset_aug(n, *map(_p, args), int(inverse), _p(got))
+    hm.hm_offset_aug_vjp(n, *map(_p, args), int(inverse), _p(np.ascontiguousarray(gout.numpy())), _p(dg))
+    assert np.abs(got - want.detach().numpy()).max() < 1e-12
+    assert np.abs(dg - gz.grad.numpy()).max() < 1e-11
+
+
+def test_angular_error_and_its_vjp(hm):
+    from eve_b200.losses import angular_loss
+    g = torch.Generator().manual_seed(2)
+    n = 64
+    a = ((torch.rand(n, 2, generator=g, dtype=torch.float64) - 0.5)).requires_grad_(True)
+    b = (torch.rand(n, 2, generator=g, dtype=torch.float64) - 0.5)
+    want = angular_loss.per_frame(a, b)
+    gl = torch.randn(n, generator=g, dtype=torch.float64)
+    want.backward(gl)
+    got, da = np.zeros(n), np.zeros((n, 2))
+    an, bn = np.ascontiguousarray(a.detach().numpy()), np.ascontiguousarray(b.numpy())
+    hm.hm_angular.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+    hm.hm_angular_vjp.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                  C.c_void_p, C.c_void_p]
+    hm.hm_angular(n, _p(an), _p(bn), -1.0 + 1e-8, 1.0 - 1e-8, _p(got))
+    hm.hm_angular_vjp(n, _p(an), _p(bn), -1.0 + 1e-8, 1.0 - 1e-8,
+                      _p(np.ascontiguousarray(gl.numpy())), _p(da))
+    assert np.abs(got - want.detach().numpy()).max() < 1e-9
+    assert np.abs(da - a.grad.numpy()).max() < 1e-8 * max(1.0, np.abs(da).max())

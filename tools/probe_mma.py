@@ -1,0 +1,22 @@
+"""tcgen05.mma issue rate from shared-memory operands (M=128, K=16, bf16): cycles per MMA as a
+function of N, with one CTA per SM (all 148 busy) and with a single CTA; aligned and pixel-shifted
+A start addresses.  Usage: python tools/probe_mma.py"""
+import sys
+
+import torch
+
+sys.path.insert(0, '.')
+from eve_b200 import lib as L   # noqa: E402
+
+lib = L.load()
+out = torch.zeros(148, dtype=torch.int64, device='cuda')
+print('%4s %5s %6s %8s %10s %10s' % ('N', 'grid', 'shift', 'distinct', 'cyc/mma', 'floor N/2'))
+for grid in (148, 1):
+    for n in (16, 32, 64, 128, 256):
+        for shift, distinct in ((0, 0), (0, 1), (128 * 35, 1)):
+            nmma, reps = 96, 50
+            L.check(lib.eve_probe_mma_rate(n, nmma, reps, shift, distinct, grid, L.ptr(out), L.stream_ptr()),
+                    'probe')
+            torch.cuda.synchronize()
+            cyc = out[:grid].double().mean().item() / (nmma * reps)
+            print('%4d %5d %6d %8d %10.2f %10.1f' % (n, grid, shift, distinct, cyc, n / 2))

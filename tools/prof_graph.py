@@ -37,14 +37,21 @@ busy = collections.defaultdict(float)
 gap = collections.defaultdict(float)
 cnt = collections.Counter()
 prev_end = None
+prev_name = None
+pairs = collections.defaultdict(lambda: [0, 0.0])
 for e in ks:
     name = e.name.replace('(anonymous namespace)::', '').replace('void ', '').split('(')[0][:70]
     d = e.time_range.end - e.time_range.start
     busy[name] += d
     cnt[name] += 1
     if prev_end is not None:
-        gap[name] += max(0.0, e.time_range.start - prev_end)
+        gp = max(0.0, e.time_range.start - prev_end)
+        gap[name] += gp
+        pr = pairs[(prev_name, name)]
+        pr[0] += 1
+        pr[1] += gp
     prev_end = max(prev_end or 0, e.time_range.end)
+    prev_name = name
 span = ks[-1].time_range.end - ks[0].time_range.start
 tb, tg = sum(busy.values()), sum(gap.values())
 print('kernels %d  span %.3f ms  busy %.3f ms  gaps %.3f ms' % (len(ks), span / 1e3, tb / 1e3, tg / 1e3))
@@ -52,3 +59,7 @@ print('%-72s %6s %9s %9s %8s' % ('kernel', 'count', 'busy ms', 'gap ms', 'gap/k 
 for name in sorted(busy, key=lambda n: -(busy[n] + gap[n]))[:45]:
     print('%-72s %6d %9.3f %9.3f %8.2f' % (name, cnt[name], busy[name] / 1e3, gap[name] / 1e3,
                                             gap[name] / cnt[name]))
+print()
+print('largest idle gaps by (previous kernel -> next kernel)')
+for (a, b), (c, gsum) in sorted(pairs.items(), key=lambda kv: -kv[1][1])[:25]:
+    print('%9.3f ms %5d x %7.1f us   %s -> %s' % (gsum / 1e3, c, gsum / c, a[:48], b[:48]))
