@@ -163,6 +163,14 @@ extern "C" long long eve_profile_dump(char* buf, long long cap) {
 }
 extern "C" const char* eve_last_error(void) { return g_error; }
 
+extern "C" int eve_conv2d_describe(const eve_conv_params* p, char* buf, size_t cap) {
+  ConvGeom g;
+  EVE_TRY(check_conv(p, g));
+  EVE_REQUIRE(buf && cap > 0, EVE_ERR_NULL, "conv2d_describe: NULL buffer");
+  conv_tc_describe(g, buf, cap);
+  return EVE_OK;
+}
+
 extern "C" size_t eve_conv2d_workspace_bytes(const eve_conv_params* p) {
   ConvGeom g;
   if (check_conv(p, g) != EVE_OK) return 0;
@@ -185,6 +193,7 @@ static Opt g_opts[OPT_COUNT] = {
     {"tc_wgrad_waves", 3, 1, 8, "EVE_B200_TC_WGRAD_WAVES", false},
     {"fused_planes", 1, 0, 1, "EVE_B200_FUSED_PLANES", false},
     {"fused_norm", 1, 0, 1, "EVE_B200_FUSED_NORM", false},
+    {"tc_strip", 1, 0, 2, "EVE_B200_TC_STRIP", false},
 };
 int get_option(int key) {
   if (key < 0 || key >= OPT_COUNT) return 0;

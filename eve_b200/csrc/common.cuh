@@ -135,6 +135,7 @@ int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const voi
                 const void* w_lo, const float* bias, const float* addend, float* y, int npass,
                 int fmt, float out_scale, cudaStream_t s);
 
+int conv_tc_describe(const ConvGeom& g, char* buf, size_t cap);
 bool conv_tc_dgrad_s2_supported(const ConvGeom& g);
 int conv_tc_dgrad_s2_run(const ConvGeom& g, const void* d_hi, const void* d_lo, const void* w_hi,
                          const void* w_lo, const float* addend, float* dx, int npass,
@@ -165,6 +166,7 @@ enum OptKey {
   OPT_TC_WGRAD_WAVES,        // full waves of CTAs the split-K weight gradient is sized for
   OPT_FUSED_PLANES,          // InstanceNorm kernels emit the consuming convolution's operand planes
   OPT_FUSED_NORM,            // one-pass cluster InstanceNorm kernels + plane-to-plane block pipelines
+  OPT_TC_STRIP,              // padded-strip tcgen05 kernel for 3x3 stride-1 layers: 0 off, 1 auto, 2 whenever it fits
   OPT_COUNT
 };
 int get_option(int key);

@@ -17,6 +17,7 @@
 //  * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 =
 //    epilogue (TMEM -> registers -> +bias/+addend -> fp32 NHWC global).
 #include <algorithm>
+#include <cstdio>
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -198,10 +199,20 @@ constexpr int kMaxStages = 24;
 constexpr int kSmemBudget = 224 * 1024;
 constexpr int kBarrierBytes = 512;     // (2 * kMaxStages + 4) mbarriers + the TMEM slot
 
+// Stacked-B issue (split operands, BN <= 64).  Measured on B200 (tools/probe_mma.py): with both
+// operands in shared memory one tcgen05.mma M=128 x N x K=16 costs max(N / 2, ~(4096 + 32 N) / 120)
+// cycles -- 43 / 44 / 51 / 68 / 132 for N = 16 / 32 / 64 / 128 / 256: below N = 128 the 4 KB A-tile
+// read, not the tensor pipe, sets the pace.  The three products of a split K step read A_hi twice;
+// since the lo weight plane sits directly behind the hi plane at the same row pitch, ONE MMA with
+// N = 2 BN over [B_hi ; B_lo] yields A_hi B_hi in accumulator columns [0, BN) and A_hi B_lo in
+// [BN, 2 BN), a second MMA adds A_lo B_hi to [0, BN), and the epilogue sums the two halves in fp32:
+// 51 + 68 instead of 3 x 51 cycles at BN = 64, 43 + 44 instead of 3 x 43 at BN = 16.
 template <int BN, int NPASS>
 struct TcCfg {
   static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
-  static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;   // per accumulator buffer (x2)
+  static constexpr bool kStack = NPASS == 3 && BN <= 64;
+  static constexpr int kAccCols = kStack ? 2 * BN : BN;       // accumulator columns of one tile
+  static constexpr uint32_t kTmemCols = kAccCols < 32 ? 32 : kAccCols;   // per accumulator buffer (x2)
 };
 
 template <int BN, int NPASS>
@@ -288,6 +299,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // M = 128, N = BN
     const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
+                            ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const int ksteps = p.kc >> 4;
     uint32_t g = 0, local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
@@ -310,7 +323,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint64_t db_lo = kmajor_desc(b_hi + p.b_bytes, p.kc);
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t adv = (uint64_t)(k * 2);  // 16 elements = 32 bytes >> 4
-            if (NPASS == 3) {
+            if (Cfg::kStack) {
+              // [A_hi B_hi | A_hi B_lo] from one N = 2 BN instruction, then A_lo B_hi
+              umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc2, (it | k) != 0);
+              umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);
+            } else if (NPASS == 3) {
               // small terms first so they are not absorbed by a large partial sum
               umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, (it | k) != 0);
               umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
@@ -352,6 +369,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_d + (uint32_t)c0, v);
+        if (Cfg::kStack) {
+          if (BN < 32) {
+#pragma unroll
+            for (int j = 0; j < BN; ++j) v[j] += v[BN + j];      // both halves came with one load
+          } else {
+            float u[32];
+            tmem_ld32(tmem_d + (uint32_t)(BN + c0), u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += u[j];
+          }
+        }
         if (valid) {
           if (p.out_scale != 1.f) {
 #pragma unroll
@@ -419,14 +447,17 @@ struct RowCfg {
   static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
   static constexpr int kRowBytes = (kRowBox * KC * 2 + 1023) / 1024 * 1024;   // one plane of one row
   static constexpr int kSlotBytes = kRowBytes * kPlanes;
-  static constexpr int kTapBytes = BN * KC * 2 < 1024 ? 1024 : BN * KC * 2;    // one tap, one plane
+  static constexpr bool kStack = NPASS == 3 && BN <= 64;       // see TcCfg
+  // one tap, one plane; with the stacked-B issue the lo plane must follow the hi plane directly
+  static constexpr int kTapBytes = (kStack || BN * KC * 2 >= 1024) ? BN * KC * 2 : 1024;
   static constexpr int kTaps = KS * KS;                 // 3x3 or 1x1
   static constexpr int kHalo = KS / 2;
-  static constexpr int kWeightBytes = kTaps * kPlanes * kTapBytes;
+  static constexpr int kWeightBytes = (kTaps * kPlanes * kTapBytes + 1023) / 1024 * 1024;
   static constexpr int kFixedBytes = kWeightBytes + 1024 + kBarrierBytes;
   static constexpr int kSlotsRaw = (227 * 1024 - kFixedBytes) / kSlotBytes;
   static constexpr int kSlots = kSlotsRaw > kMaxStages ? kMaxStages : kSlotsRaw;
-  static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kAccCols = kStack ? 2 * BN : BN;
+  static constexpr uint32_t kTmemCols = kAccCols < 32 ? 32 : kAccCols;
 };
 
 template <int BN, int NPASS, int KC, int KS>
@@ -509,6 +540,8 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     // ===================== MMA issuer =====================
     const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
+                            ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     constexpr int kSteps = KC / 16;
     constexpr uint32_t kPix16 = (uint32_t)(KC * 2) >> 4;        // one pixel, in 16-byte units
     constexpr uint32_t kRow16 = (uint32_t)Cfg::kRowBytes >> 4;
@@ -548,7 +581,10 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 const uint64_t da_lo = da_hi + kRow16;
                 const uint64_t db_hi = b_base + (uint64_t)((r * KS + q) * kPlanes * kTap16 + k * two);
                 const uint64_t db_lo = db_hi + kTap16;
-                if (NPASS == 3) {
+                if (Cfg::kStack) {
+                  umma_bf16(tmem_d, da_hi, db_hi, idesc2, (r | q | k) != 0);
+                  umma_bf16(tmem_d, da_lo, db_hi, idesc, 1);
+                } else if (NPASS == 3) {
                   umma_bf16(tmem_d, da_lo, db_hi, idesc, (r | q | k) != 0);
                   umma_bf16(tmem_d, da_hi, db_lo, idesc, 1);
                   umma_bf16(tmem_d, da_hi, db_hi, idesc, 1);
@@ -596,6 +632,17 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         for (int c0 = 0; c0 < BN; c0 += 32) {
           float v[32];
           tmem_ld32(tmem_d + (uint32_t)c0, v);
+          if (Cfg::kStack) {
+            if (BN < 32) {
+#pragma unroll
+              for (int j = 0; j < BN; ++j) v[j] += v[BN + j];
+            } else {
+              float u[32];
+              tmem_ld32(tmem_d + (uint32_t)(BN + c0), u);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += u[j];
+            }
+          }
           if (p.out_scale != 1.f) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) v[j] *= p.out_scale;
@@ -627,6 +674,269 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * kTmemCols);
+  }
+}
+
+// ================================================================ padded-strip kernel ==
+// 3x3 stride-1 "same" convolutions whose maps are narrower than 128 pixels (EyeNet layer1,
+// RefineNet levels 1-3: eye_net.py:48-50, refine_net.py:45-62).  The generic kernel above loads one
+// A box per filter tap, i.e. every input pixel crosses L2 -> shared memory nine times; at 64
+// channels that stream (125 B/clk/SM needed, ~42 available) and not the tensor pipe sets the pace.
+// Here a work item stages its input ONCE per K chunk as a zero-padded strip: a TMA box
+// [bn images][R + 2 rows][W + 2 pixels][KC channels] starting at (w, h) = (-1, h0 - 1) lands in
+// shared memory as consecutive pixel rows of KC channels, row-major in a space padded to W + 2
+// columns.  An M tile is 128 CONSECUTIVE positions of that padded space, and filter tap (r, q) of
+// all of them is the same staged strip read through a descriptor whose start address is shifted by
+// r * (W + 2) + q pixels (the swizzle is a function of the absolute shared-memory address, DESIGN
+// 3b).  The two pad positions per row (and the halo rows between images when bn > 1) produce junk
+// accumulator rows that the epilogue skips.  Each weight tile [BN][KC] of a (tap, chunk) is
+// streamed once per item through a small ring and used by all T tiles of the item (T accumulators
+// in TMEM), so operand traffic per item is  A * (R + 2) / R  +  9 taps * B  instead of 9 * (A + B)
+// per tile.  Five roles: A producer, B producer, MMA issuer, four epilogue warps.
+struct TcStripParams {
+  int N, H, W, Cout, Wp;
+  int R, bn;                 // output rows per strip; images per item (bn > 1 only when R == H)
+  int strips, groups;        // ceil(H / R), ceil(N / bn)
+  int S;                     // (R + 2) * Wp: staged pixel rows per image
+  int tiles_co, items;       // Cout / BN; groups * strips * tiles_co
+  int kchunks;               // Cin / KC
+  int Tmax, nsets;           // accumulators per set, sets in TMEM (2 = epilogue overlaps the next item)
+  int a_plane_bytes;         // one plane of one A buffer
+  int b_stages;
+  int fmt;
+  float out_scale;
+  const float* bias;
+  const float* addend;
+  float* out;
+};
+
+constexpr int kStripThreads = 224;      // 7 warps
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(kStripThreads, 1)
+conv_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                     const TcStripParams p) {
+  constexpr int kBPlane = BN * KC * 2 < 1024 ? 1024 : BN * KC * 2;    // one weight plane of a stage
+  constexpr bool kStack = BN <= 64;                                   // stacked-B issue, see TcCfg
+  static_assert(!kStack || kBPlane == BN * KC * 2, "stacked B needs the lo plane right behind hi");
+  constexpr int kAcc = kStack ? 2 * BN : BN;                          // accumulator columns per tile
+  constexpr uint32_t kPix16 = (uint32_t)(KC * 2) >> 4;                // one pixel row, 16-byte units
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* a_buf = smem;                                         // [2 buffers][2 planes][a_plane_bytes]
+  uint8_t* b_ring = smem + 4 * (size_t)p.a_plane_bytes;          // [b_stages][2 planes][kBPlane]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.b_stages * 2 * kBPlane);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* b_full = a_empty + 2;
+  uint64_t* b_empty = b_full + p.b_stages;
+  uint64_t* tmem_full = b_empty + p.b_stages;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(p.nsets * p.Tmax * kAcc)) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tmap_prefetch(&tmA_hi);
+    tmap_prefetch(&tmA_lo);
+    tmap_prefetch(&tmB_hi);
+    tmap_prefetch(&tmB_lo);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    for (int i = 0; i < p.b_stages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== A producer: one padded strip per (item, K chunk) =====================
+    if (elect_one()) {
+      const uint32_t tx = (uint32_t)(p.bn * p.S) * (uint32_t)(KC * 2) * 2u;
+      uint32_t ga = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int si = item / p.tiles_co;
+        const int h0 = (si % p.strips) * p.R;
+        const int n0 = (si / p.strips) * p.bn;
+        for (int c = 0; c < p.kchunks; ++c, ++ga) {
+          const uint32_t buf = ga & 1;
+          mbar_wait(&a_empty[buf], ((ga >> 1) & 1) ^ 1);
+          uint8_t* dst = a_buf + (size_t)buf * 2 * p.a_plane_bytes;
+          mbar_expect_tx(&a_full[buf], tx);
+          tma_load_4d(dst, &tmA_hi, &a_full[buf], c * KC, -1, h0 - 1, n0);
+          tma_load_4d(dst + p.a_plane_bytes, &tmA_lo, &a_full[buf], c * KC, -1, h0 - 1, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== B producer: one weight tile per (item, K chunk, tap) =====================
+    if (elect_one()) {
+      constexpr uint32_t tx = (uint32_t)(BN * KC * 2) * 2u;
+      const int Cin = p.kchunks * KC;
+      uint32_t gb = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int co0 = (item % p.tiles_co) * BN;
+        for (int c = 0; c < p.kchunks; ++c) {
+          for (int tap = 0; tap < 9; ++tap, ++gb) {
+            const uint32_t s = gb % (uint32_t)p.b_stages;
+            mbar_wait(&b_empty[s], ((gb / (uint32_t)p.b_stages) & 1) ^ 1);
+            uint8_t* dst = b_ring + (size_t)s * 2 * kBPlane;
+            mbar_expect_tx(&b_full[s], tx);
+            tma_load_2d(dst, &tmB_hi, &b_full[s], tap * Cin + c * KC, co0);
+            tma_load_2d(dst + kBPlane, &tmB_lo, &b_full[s], tap * Cin + c * KC, co0);
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
+                            ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    constexpr int kSteps = KC / 16;
+    const uint64_t desc0 = kmajor_desc(0u, KC);
+    const uint32_t a16 = smem_u32(a_buf) >> 4, b16 = smem_u32(b_ring) >> 4;
+    const uint32_t aplane16 = (uint32_t)p.a_plane_bytes >> 4;
+    constexpr uint32_t bplane16 = (uint32_t)kBPlane >> 4;
+    uint32_t ga = 0, gb = 0, local = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++local) {
+      const int si = item / p.tiles_co;
+      const int h0 = (si % p.strips) * p.R;
+      const int n0 = (si / p.strips) * p.bn;
+      const int rows = min(p.R, p.H - h0), imgs = min(p.bn, p.N - n0);
+      const int T = ((imgs - 1) * p.S + rows * p.Wp + kTileM - 1) / kTileM;
+      const uint32_t set = p.nsets == 2 ? (local & 1) : 0u;
+      const uint32_t use = p.nsets == 2 ? (local >> 1) : local;
+      mbar_wait(&tmem_empty[set], (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_set = tmem_base + set * (uint32_t)(p.Tmax * kAcc);
+      for (int c = 0; c < p.kchunks; ++c, ++ga) {
+        const uint32_t buf = ga & 1;
+        mbar_wait(&a_full[buf], (ga >> 1) & 1);
+        const uint64_t a_desc = desc0 + (uint64_t)(a16 + buf * 2 * aplane16);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap, ++gb) {
+          const uint32_t s = gb % (uint32_t)p.b_stages;
+          mbar_wait(&b_full[s], (gb / (uint32_t)p.b_stages) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const int r = tap / 3, q = tap - 3 * r;
+            const uint64_t a_tap = a_desc + (uint64_t)((uint32_t)(r * p.Wp + q) * kPix16);
+            const uint64_t b_tap = desc0 + (uint64_t)(b16 + s * 2 * bplane16);
+            for (int t = 0; t < T; ++t) {
+              const uint64_t a_t = a_tap + (uint64_t)((uint32_t)t * (uint32_t)kTileM * kPix16);
+              const uint32_t tmem_d = tmem_set + (uint32_t)(t * kAcc);
+#pragma unroll
+              for (int k = 0; k < kSteps; ++k) {
+                const uint64_t da_hi = a_t + (uint64_t)(k * 2);
+                const uint64_t da_lo = da_hi + aplane16;
+                const uint64_t db_hi = b_tap + (uint64_t)(k * 2);
+                const uint64_t db_lo = db_hi + bplane16;
+                if (kStack) {
+                  umma_bf16(tmem_d, da_hi, db_hi, idesc2, (c | tap | k) != 0);
+                  umma_bf16(tmem_d, da_lo, db_hi, idesc, 1);
+                } else {
+                  // small terms first so they are not absorbed by a large partial sum
+                  umma_bf16(tmem_d, da_lo, db_hi, idesc, (c | tap | k) != 0);
+                  umma_bf16(tmem_d, da_hi, db_lo, idesc, 1);
+                  umma_bf16(tmem_d, da_hi, db_hi, idesc, 1);
+                }
+              }
+            }
+            umma_commit(&b_empty[s]);
+            if (tap == 8) {
+              umma_commit(&a_empty[buf]);
+              if (c == p.kchunks - 1) umma_commit(&tmem_full[set]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 3..6: TMEM lane quadrant = warp & 3) =====================
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    uint32_t local = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++local) {
+      const int tco = item % p.tiles_co;
+      const int si = item / p.tiles_co;
+      const int h0 = (si % p.strips) * p.R;
+      const int n0 = (si / p.strips) * p.bn;
+      const int rows = min(p.R, p.H - h0), imgs = min(p.bn, p.N - n0);
+      const int T = ((imgs - 1) * p.S + rows * p.Wp + kTileM - 1) / kTileM;
+      const int co0 = tco * BN;
+      const uint32_t set = p.nsets == 2 ? (local & 1) : 0u;
+      const uint32_t use = p.nsets == 2 ? (local >> 1) : local;
+      mbar_wait(&tmem_full[set], use & 1);
+      tc_fence_after();
+      const uint32_t tmem_set = tmem_base + set * (uint32_t)(p.Tmax * kAcc) + ((uint32_t)(quad * 32) << 16);
+      for (int t = 0; t < T; ++t) {
+        const int j = t * kTileM + m;            // position in the padded space of the item
+        const int i = j / p.S;
+        const int rem = j - i * p.S;
+        const int hh = rem / p.Wp;
+        const int ww = rem - hh * p.Wp;
+        const bool valid = i < imgs && hh < rows && ww < p.W;
+        const size_t row = (((size_t)(n0 + i) * p.H + (h0 + hh)) * p.W + ww) * p.Cout + co0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_set + (uint32_t)(t * kAcc + c0), v);
+          if (kStack) {
+            float u[32];
+            tmem_ld32(tmem_set + (uint32_t)(t * kAcc + BN + c0), u);
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) v[jj] += u[jj];
+          }
+          if (valid) {
+            if (p.out_scale != 1.f) {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) v[jj] *= p.out_scale;
+            }
+            if (p.bias) {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) v[jj] += __ldg(p.bias + co0 + c0 + jj);
+            }
+            if (p.addend) {
+              const float4* a4 = reinterpret_cast<const float4*>(p.addend + row + c0);
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const float4 a = __ldg(a4 + jj);
+                v[4 * jj] += a.x; v[4 * jj + 1] += a.y; v[4 * jj + 2] += a.z; v[4 * jj + 3] += a.w;
+              }
+            }
+            float4* o4 = reinterpret_cast<float4*>(p.out + row + c0);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              o4[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[set]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -679,8 +989,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
   const int a_block = kWgRows * p.uw * 2;          // bytes reserved per dy unit
   const int b_block = kWgRows * p.xw * 2;          // bytes reserved per x block
   const int a_bytes = kTileM * kWgRows * 2;        // upb * a_block == 128 * 64 * 2 always
-  const int plane_bytes = a_bytes + nbB * b_block;
-  const int stage_bytes = ((plane_bytes * kPlanes) + 1023) & ~1023;
+  const int bplane_bytes = nbB * b_block;          // one plane of the N-side blocks
+  // stage = [M hi][M lo][N hi blocks][N lo blocks]: the lo N blocks follow the hi ones at the
+  // block pitch, so ONE MN-major descriptor with N = 2 nblk reads [hi ; lo] (stacked-B issue)
+  const int stage_bytes = (((a_bytes + bplane_bytes) * kPlanes) + 1023) & ~1023;
+  const bool stack = NPASS == 3 && p.nblk <= 128;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;
@@ -695,7 +1008,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
   const int t_end = min(p.tiles_total, t_begin + p.tiles_per_split);
   const int iters = max(t_end - t_begin, 0);
   uint32_t tmem_cols = 32;                 // allocation granularity: powers of two >= 32
-  while (tmem_cols < (uint32_t)p.nblk) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(stack ? 2 * p.nblk : p.nblk)) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     tmap_prefetch(&tmD_hi);
@@ -734,7 +1047,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
         mbar_expect_tx(&full[s], tx);
 #pragma unroll
         for (int pl = 0; pl < kPlanes; ++pl) {
-          uint8_t* base = st + pl * plane_bytes;
+          uint8_t* abase = st + pl * a_bytes;
+          uint8_t* bbase = st + kPlanes * a_bytes + pl * bplane_bytes;
           const CUtensorMap* md = pl == 0 ? &tmD_hi : &tmD_lo;
           const CUtensorMap* mx = pl == 0 ? &tmX_hi : &tmX_lo;
           for (int b = 0; b < p.upb; ++b) {
@@ -744,12 +1058,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
             const int r = tap / p.KW, q = tap - r * p.KW;
             const int dw = p.swap ? q - p.pad : p.pad - q;
             const int dh = p.swap ? r - p.pad : p.pad - r;
-            tma_load_4d(base + b * a_block, md, &full[s], cb * p.uw, w0 * p.mstride + dw,
+            tma_load_4d(abase + b * a_block, md, &full[s], cb * p.uw, w0 * p.mstride + dw,
                         h0 * p.mstride + dh, n0);
           }
           for (int b = 0; b < nbB; ++b)
-            tma_load_4d(base + a_bytes + b * b_block, mx, &full[s], nb * p.nblk + b * p.xw, w0, h0,
-                        n0);
+            tma_load_4d(bbase + b * b_block, mx, &full[s], nb * p.nblk + b * p.xw, w0, h0, n0);
         }
       }
     }
@@ -758,6 +1071,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
     const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt_m << 7) | ((uint32_t)p.fmt_n << 10) |
                            (1u << 15) | (1u << 16) |
                            ((uint32_t)(p.nblk >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * p.nblk) >> 3) << 17);
     const int ksteps = p.rows >> 4;
     for (int it = 0; it < iters; ++it) {
       const int s = it % p.stages;
@@ -766,15 +1080,20 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
-        const uint32_t b_hi = a_hi + a_bytes;
-        const uint32_t a_lo = a_hi + plane_bytes;
-        const uint32_t b_lo = b_hi + plane_bytes;
+        const uint32_t a_lo = a_hi + a_bytes;
+        const uint32_t b_hi = a_hi + kPlanes * a_bytes;
+        const uint32_t b_lo = b_hi + bplane_bytes;
         for (int k = 0; k < ksteps; ++k) {
           const uint32_t adva = (uint32_t)k * 16u * (uint32_t)(p.uw * 2);   // 16 pixel rows
           const uint32_t advb = (uint32_t)k * 16u * (uint32_t)(p.xw * 2);
           const uint64_t dah = mnmajor_desc(a_hi + adva, a_block, p.uw);
           const uint64_t dbh = mnmajor_desc(b_hi + advb, b_block, p.xw);
-          if (NPASS == 3) {
+          if (stack) {
+            // [M_hi N_hi | M_hi N_lo] from one N = 2 nblk instruction, then M_lo N_hi
+            const uint64_t dal = mnmajor_desc(a_lo + adva, a_block, p.uw);
+            umma_bf16(tmem_base, dah, dbh, idesc2, (it | k) != 0);
+            umma_bf16(tmem_base, dal, dbh, idesc, 1);
+          } else if (NPASS == 3) {
             const uint64_t dal = mnmajor_desc(a_lo + adva, a_block, p.uw);
             const uint64_t dbl = mnmajor_desc(b_lo + advb, b_block, p.xw);
             umma_bf16(tmem_base, dal, dbh, idesc, (it | k) != 0);
@@ -810,6 +1129,16 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
       float v[32];
       if (iters > 0) {
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+        if (stack) {
+          if (p.nblk < 32) {
+            for (int j = 0; j < p.nblk; ++j) v[j] += v[p.nblk + j];
+          } else {
+            float u[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.nblk + c0), u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += u[j];
+          }
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -863,8 +1192,12 @@ struct WgRowCfg {
   static constexpr int kSlots = kSlotsRaw > kMaxStages ? kMaxStages : kSlotsRaw;
   // two accumulator sets (three filter rows x CIN columns each), flushed alternately
   static constexpr int kHalo = KS / 2;
-  static constexpr uint32_t kSetCols = KS * CIN;
-  static constexpr uint32_t kTmemCols = CIN == 16 ? 128u : (CIN == 32 ? 256u : 512u);   // >= 2 * 3 * CIN
+  // stacked-B issue (see TcCfg): the x lo plane sits exactly one leading-dimension offset behind
+  // the hi plane, so N = 2 CIN reads [x_hi ; x_lo]; 2 sets x 3 filter rows x 2 CIN columns must fit
+  static constexpr bool kStack = NPASS == 3 && CIN <= 32;
+  static constexpr uint32_t kAcc = kStack ? 2 * CIN : CIN;       // accumulator columns per filter row
+  static constexpr uint32_t kSetCols = KS * kAcc;
+  static constexpr uint32_t kTmemCols = 2 * kSetCols <= 128 ? 128u : (2 * kSetCols <= 256 ? 256u : 512u);
 };
 constexpr int kWgFlushRows = kWgradChainPixels / kTileM;   // image rows per accumulation chain
 
@@ -950,6 +1283,8 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
     // D fp32, A/B bf16, both MN-major, M = 128, N = CIN
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(CIN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                ((uint32_t)((2 * CIN) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     // per 16-pixel K step the operands advance by 16 pixel rows; everything in 16-byte units
     constexpr uint32_t kDStep16 = (uint32_t)(16 * COUT * 2) >> 4;
     constexpr uint32_t kXStep16 = (uint32_t)(16 * CIN * 2) >> 4;
@@ -993,12 +1328,16 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
             // staged box starts at pixel -1, so a 1x1 filter reads it one pixel in
             const uint64_t db = d_desc0 + (uint64_t)(ring16 + sl[2 * kHalo - r] * kSlot16 +
                                                      (1 - kHalo) * ((uint32_t)(COUT * 2) >> 4));
-            const uint32_t tmem_d = tmem_base + set * Cfg::kSetCols + (uint32_t)(r * CIN);
+            const uint32_t tmem_d = tmem_base + set * Cfg::kSetCols + (uint32_t)r * Cfg::kAcc;
 #pragma unroll
             for (int ks = 0; ks < kTileM / 16; ++ks) {
               const uint64_t dah = db + (uint64_t)(ks * kDStep16);
               const uint64_t dbh = xb + (uint64_t)(ks * kXStep16);
-              if (NPASS == 3) {
+              if (Cfg::kStack) {
+                const uint64_t dal = dah + kDRow16;
+                umma_bf16(tmem_d, dah, dbh, idesc2, ks == 0 ? acc0 : 1u);
+                umma_bf16(tmem_d, dal, dbh, idesc, 1);
+              } else if (NPASS == 3) {
                 const uint64_t dal = dah + kDRow16;
                 const uint64_t dbl = dbh + kXRow16;
                 umma_bf16(tmem_d, dal, dbh, idesc, ks == 0 ? acc0 : 1u);
@@ -1045,7 +1384,19 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
         for (int c0 = 0; c0 < CIN; c0 += 32) {
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + set * Cfg::kSetCols +
-                        (uint32_t)(r * CIN + c0), v);
+                        (uint32_t)r * Cfg::kAcc + (uint32_t)c0, v);
+          if (Cfg::kStack) {
+            if (CIN < 32) {
+#pragma unroll
+              for (int j = 0; j < CIN; ++j) v[j] += v[CIN + j];
+            } else {
+              float u[32];
+              tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + set * Cfg::kSetCols +
+                            (uint32_t)r * Cfg::kAcc + (uint32_t)(CIN + c0), u);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += u[j];
+            }
+          }
           if (valid) {
             float4* o4 = reinterpret_cast<float4*>(dst + c0);
             constexpr int nq = (CIN < 32 ? CIN : 32) >> 2;
@@ -1239,7 +1590,9 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
   p.tiles_co = tiles_co;
   // ring slots sized for this layer's chunk width (swizzle atoms need 1024-byte alignment)
   p.a_bytes = kTileM * p.kc * 2;
-  p.b_bytes = BN * p.kc * 2 < 1024 ? 1024 : BN * p.kc * 2;
+  // stacked-B issue reads [B_hi ; B_lo] through one descriptor: the lo plane follows the hi plane
+  // without padding (BN * kc * 2 is a multiple of every swizzle atom; a stage stays 1024-aligned)
+  p.b_bytes = (Cfg::kStack || BN * p.kc * 2 >= 1024) ? BN * p.kc * 2 : 1024;
   p.stage_bytes = (p.a_bytes + p.b_bytes) * Cfg::kPlanes;
   p.stages = (kSmemBudget - 1024 - kBarrierBytes) / p.stage_bytes;
   const int cap = tc_stage_cap();
@@ -1444,6 +1797,157 @@ static int conv_tc_row_run(const ConvGeom& g, const void* x_hi, const void* x_lo
   }
 }
 
+// ---- padded-strip kernel: planning and launch
+struct StripPlan {
+  int BN, KC, R, bn, Tmax, nsets, a_plane_bytes, b_stages;
+  double score;      // useful fraction of the issued MMA rows x wave balance
+};
+
+static int strip_bn_for(int Cout) { return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout == 32 ? 32 : 0)); }
+
+// efficiency of the generic kernel's pixel boxes on the same geometry (for the auto switch)
+static double generic_box_efficiency(const ConvGeom& g) {
+  int bw, bh, bn;
+  pick_box(g.N, g.OH, g.OW, bw, bh, bn);
+  return ((double)g.OH / (double)(cdiv(g.OH, bh) * bh)) * ((double)(bw * bh * bn) / kTileM) *
+         ((double)g.N / (double)(cdiv(g.N, bn) * bn));
+}
+
+static bool strip_plan(const ConvGeom& g, StripPlan& best) {
+  if (g.KH != 3 || g.KW != 3 || g.stride != 1 || g.pad != 1 || g.OH != g.H || g.OW != g.W) return false;
+  if (g.W + 2 > 256 || g.W >= kTileM || g.N < 1) return false;
+  const int BN = strip_bn_for(g.Cout);
+  if (BN == 0) return false;
+  const int Wp = g.W + 2;
+  const int usable = 227 * 1024 - 1024 - kBarrierBytes;
+  best.score = -1.0;
+  const int kcs[3] = {64, 32, 16};
+  for (int ki = 0; ki < 3; ++ki) {
+    const int KC = kcs[ki];
+    if (g.Cin % KC != 0) continue;
+    const int bsz = 2 * (BN * KC * 2 < 1024 ? 1024 : BN * KC * 2);
+    for (int bn = 1; bn <= 16 && bn <= g.N; ++bn) {
+      for (int R = (bn == 1 ? 1 : g.H); R <= g.H; ++R) {
+        const int S = (R + 2) * Wp;
+        const int Tmax = cdiv((long long)(bn - 1) * S + (long long)R * Wp, kTileM);
+        const int acc = BN <= 64 ? 2 * BN : BN;        // stacked-B accumulators are twice as wide
+        if (Tmax * acc > 512) break;                   // grows with R
+        const int arows = Tmax * kTileM + 2 * Wp + 2;
+        const int a_plane = (int)align_up((size_t)arows * KC * 2, 1024);
+        int stages = (usable - 4 * a_plane) / bsz;
+        if (stages < 3) break;
+        if (stages > 12) stages = 12;
+        const int strips = cdiv(g.H, R), groups = cdiv(g.N, bn);
+        const int last_rows = g.H - (strips - 1) * R;
+        // tiles over all items of one output-channel tile (the tail image group counts as full)
+        const long long t_full = cdiv((long long)(bn - 1) * S + (long long)R * Wp, kTileM);
+        const long long t_last = cdiv((long long)(bn - 1) * S + (long long)last_rows * Wp, kTileM);
+        const long long tiles = (long long)groups * ((strips - 1) * t_full + t_last);
+        const double eff = (double)g.N * g.H * g.W / ((double)tiles * kTileM);
+        const long long items = (long long)groups * strips * (g.Cout / BN);
+        const double bal = (double)items / (double)((long long)cdiv(items, kNumSMs) * kNumSMs);
+        const int nsets = 2 * Tmax * acc <= 512 ? 2 : 1;
+        const double score = eff * bal * (KC == 64 ? 1.0 : (KC == 32 ? 0.97 : 0.9)) *
+                             (nsets == 2 ? 1.0 : 0.95) * ((double)R / (R + 2) * 0.1 + 0.9);
+        if (score > best.score + 1e-9) {
+          best = StripPlan{BN, KC, R, bn, Tmax, nsets, a_plane, stages, score};
+        }
+      }
+    }
+  }
+  return best.score > 0.0;
+}
+
+bool conv_tc_strip_supported(const ConvGeom& g) {
+  const int opt = get_option(OPT_TC_STRIP);
+  if (opt == 0) return false;
+  StripPlan pl;
+  if (!strip_plan(g, pl)) return false;
+  if (opt == 2) return true;
+  // auto (calibrated with tools/probe_strip.py at the bench geometries, profiles/r2_probe_strip.txt):
+  // the strip kernel issues junk rows (pad columns, halo rows, partial tiles) but moves 3-7x fewer
+  // operand bytes and amortises each weight tile over all tiles of an item.  It wins where the box
+  // kernel's own pixel boxes are inefficient (9x16 maps: 56 % useful rows, 1.07-1.42x) and on
+  // 32-channel outputs (1.02-1.36x); at 64 channels it needs both accumulator sets (18x32: 1.07-
+  // 1.16x, while 32x32 / 36x64 plans only fit one set and lose 15-30 %); on the well-filled
+  // 128-channel maps the box kernel already runs at 70-78 % of the split-operand peak.
+  const double ge = generic_box_efficiency(g);
+  if (pl.BN == 32) return true;
+  if (pl.BN == 64) return pl.nsets == 2 && pl.score >= 0.78 * ge;
+  return pl.score >= 0.9 * ge;
+}
+
+template <int BN, int KC>
+static int launch_strip(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                        const CUtensorMap& b_lo, const TcStripParams& p, cudaStream_t s) {
+  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_strip_kernel<BN, KC>, 227 * 1024));
+  constexpr int kBPlane = BN * KC * 2 < 1024 ? 1024 : BN * KC * 2;
+  const int smem_bytes = 4 * p.a_plane_bytes + p.b_stages * 2 * kBPlane + 1024 + kBarrierBytes;
+  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  conv_tc_strip_kernel<BN, KC><<<grid, kStripThreads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+template <int BN>
+static int launch_strip_kc(int kc, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                           const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcStripParams& p,
+                           cudaStream_t s) {
+  switch (kc) {
+    case 64: return launch_strip<BN, 64>(a_hi, a_lo, b_hi, b_lo, p, s);
+    case 32: return launch_strip<BN, 32>(a_hi, a_lo, b_hi, b_lo, p, s);
+    default: return launch_strip<BN, 16>(a_hi, a_lo, b_hi, b_lo, p, s);
+  }
+}
+
+static int conv_tc_strip_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* w_hi,
+                             const void* w_lo, const float* bias, const float* addend, float* y,
+                             int fmt, float out_scale, cudaStream_t s) {
+  StripPlan pl;
+  EVE_REQUIRE(strip_plan(g, pl), EVE_ERR_SHAPE, "conv_tc_strip: unsupported geometry");
+  TcStripParams p;
+  p.N = g.N; p.H = g.H; p.W = g.W; p.Cout = g.Cout; p.Wp = g.W + 2;
+  p.R = pl.R; p.bn = pl.bn;
+  p.strips = cdiv(g.H, pl.R);
+  p.groups = cdiv(g.N, pl.bn);
+  p.S = (pl.R + 2) * p.Wp;
+  p.tiles_co = g.Cout / pl.BN;
+  p.items = p.groups * p.strips * p.tiles_co;
+  p.kchunks = g.Cin / pl.KC;
+  p.Tmax = pl.Tmax; p.nsets = pl.nsets;
+  p.a_plane_bytes = pl.a_plane_bytes;
+  p.b_stages = pl.b_stages;
+  p.fmt = fmt;
+  p.out_scale = out_scale;
+  p.bias = bias; p.addend = addend; p.out = y;
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  EVE_TRY(make_map_nhwc(&a_hi, x_hi, g.N, g.H, g.W, g.Cin, pl.KC, p.Wp, pl.R + 2, pl.bn, 1, fmt));
+  EVE_TRY(make_map_nhwc(&a_lo, x_lo, g.N, g.H, g.W, g.Cin, pl.KC, p.Wp, pl.R + 2, pl.bn, 1, fmt));
+  EVE_TRY(make_map_2d(&b_hi, w_hi, g.Cout, 9 * g.Cin, pl.KC, pl.BN, fmt));
+  EVE_TRY(make_map_2d(&b_lo, w_lo, g.Cout, 9 * g.Cin, pl.KC, pl.BN, fmt));
+  switch (pl.BN) {
+    case 128: return launch_strip_kc<128>(pl.KC, a_hi, a_lo, b_hi, b_lo, p, s);
+    case 64: return launch_strip_kc<64>(pl.KC, a_hi, a_lo, b_hi, b_lo, p, s);
+    default: return launch_strip_kc<32>(pl.KC, a_hi, a_lo, b_hi, b_lo, p, s);
+  }
+}
+
+// which forward-style kernel conv_tc_run() picks for `g`, and with what plan (debugging / docs)
+int conv_tc_describe(const ConvGeom& g, char* buf, size_t cap) {
+  if (!conv_tc_supported(g)) return snprintf(buf, cap, "not on the tensor-core path");
+  if (conv_tc_row_supported(g)) return snprintf(buf, cap, "halo-row kernel");
+  StripPlan pl;
+  const bool have = strip_plan(g, pl);
+  const double ge = generic_box_efficiency(g);
+  if (have && conv_tc_strip_supported(g))
+    return snprintf(buf, cap, "strip kernel BN=%d KC=%d R=%d bn=%d T=%d sets=%d stages=%d score=%.3f (box kernel %.3f)",
+                    pl.BN, pl.KC, pl.R, pl.bn, pl.Tmax, pl.nsets, pl.b_stages, pl.score, ge);
+  if (have)
+    return snprintf(buf, cap, "box kernel eff=%.3f (strip plan BN=%d KC=%d R=%d bn=%d T=%d sets=%d score=%.3f)", ge,
+                    pl.BN, pl.KC, pl.R, pl.bn, pl.Tmax, pl.nsets, pl.score);
+  return snprintf(buf, cap, "box kernel eff=%.3f", ge);
+}
+
 // y[N,OH,OW,Cout] = conv(x) (+bias) (+addend).  x_hi/x_lo: 16-bit NHWC planes of the input;
 // w_hi/w_lo: K-major weights [Cout][KH*KW*Cin].  npass: 3 (split operands) or 1 (plain bf16).
 int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* w_hi,
@@ -1453,6 +1957,8 @@ int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const voi
   EVE_REQUIRE(npass == 1 || npass == 3, EVE_ERR_CONFIG, "conv_tc: npass must be 1 or 3");
   if (conv_tc_row_supported(g))
     return conv_tc_row_run(g, x_hi, x_lo, w_hi, w_lo, bias, addend, y, npass, fmt, out_scale, s);
+  if (npass == 3 && conv_tc_strip_supported(g))
+    return conv_tc_strip_run(g, x_hi, x_lo, w_hi, w_lo, bias, addend, y, fmt, out_scale, s);
   TcParams p;
   p.N = g.N; p.OH = g.OH; p.OW = g.OW; p.Cin = g.Cin; p.Cout = g.Cout; p.stride = g.stride;
   p.ntaps = g.KH * g.KW;
@@ -1554,7 +2060,7 @@ bool conv_tc_wgrad_supported(const ConvGeom& g) {
 static int wgrad_stage_bytes(const TcWgradParams& p, int npass) {
   const int planes = npass == 3 ? 2 : 1;
   const int plane = kTileM * kWgRows * 2 + (p.nblk / p.xw) * kWgRows * p.xw * 2;
-  return ((plane * planes) + 1023) & ~1023;
+  return ((plane * planes) + 1023) & ~1023;      // [M hi][M lo][N hi blocks][N lo blocks]
 }
 
 static void wgrad_plan(const ConvGeom& g, TcWgradParams& p, int& mblocks, int& nblocks,

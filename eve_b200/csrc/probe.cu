@@ -37,7 +37,16 @@ mma_rate_kernel(int n, int nmma, int reps, int a_shift_bytes, int distinct_a, lo
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = slot;
-  if (threadIdx.x == 0) {
+  // one elected lane of a converged warp issues (the idiom of the product kernels: a plain
+  // `threadIdx.x == 0` branch makes ptxas wrap every UTCHMMA in a BRA.U.ANY convergence loop,
+  // which costs ~50 cycles per MMA)
+  bool leader = false;
+  if (warp == 1) {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    leader = pred != 0;
+  }
+  if (leader) {
     // K-major SWIZZLE_128B descriptors: 64 channels per row, 8-row atoms of 1024 bytes
     const uint64_t hi = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
     const uint32_t a0 = p_smem_u32(smem) + (uint32_t)a_shift_bytes;

@@ -8,6 +8,9 @@ costs one ``cudaGraphLaunch``.  Everything data-dependent stays outside the capt
   * the per-clip kappa augmentation draws (np.random, eve.py:468-469) are made on the host in
     the reference's order and copied into static [B, 2] buffers;
   * the Adam step count lives on the device (eve_adam_params.step_dev);
+  * batches may carry their frames undecoded-to-float ('eyes_frames' / 'screen_frames' uint8 in the
+    decoder's layout, eve_b200/input_pipeline.py): they cross PCIe as bytes and one kernel per
+    stream converts them straight into the static float buffers;
   * ``prefetch()`` stages the NEXT batch host->device on a second stream while the current replay
     computes; the step then starts with a device-to-device copy into the static buffers.
 The math is the eager path's, kernel for kernel -- tests/test_gpu_graph.py holds the two
@@ -17,6 +20,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import input_pipeline as IP
 from . import lib as L
 
 
@@ -30,7 +34,8 @@ class GraphedTrainStep(object):
         self.tag = tag
         self.epoch = float(current_epoch)
         dev = trainer.device
-        self.static_in = {k: torch.empty_like(v, device=dev) for k, v in example_inputs.items()}
+        self.static_in = {k: torch.empty(v.shape, dtype=v.dtype, device=dev)
+                          for k, v in example_inputs.items()}
         B = next(iter(example_inputs.values())).shape[0]
         # ring of pinned kappa buffers: the H2D copy of step i is asynchronous, so the host may not
         # rewrite a buffer before the copy that reads it has run (event per slot)
@@ -49,6 +54,7 @@ class GraphedTrainStep(object):
         self._pinned = False
         # input prefetch: staging buffers filled on a copy stream (see prefetch())
         self.stage_in = None
+        self.raw_dev = {}               # device copies of uint8 frame tensors handed over on the host
         self.copy_stream = None
         self.stage_ready = None
         self.stage_free = None
@@ -81,9 +87,29 @@ class GraphedTrainStep(object):
         self.trainer.step(loss)
         return loss.detach()
 
+    def _raw_on_device(self, k, v):
+        if v.is_cuda:
+            return v
+        buf = self.raw_dev.get(k)
+        if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+            buf = self.raw_dev[k] = torch.empty(v.shape, dtype=v.dtype, device=self.trainer.device)
+        buf.copy_(v, non_blocking=True)
+        return buf
+
     def _load(self, inputs):
+        fpc = inputs.get('frames_per_clip')
+        if fpc is not None:
+            fpc = self._raw_on_device('frames_per_clip', fpc)
         for k, v in inputs.items():
-            self.static_in[k].copy_(v, non_blocking=True)
+            if k == 'eyes_frames':      # uint8 [B,T,H,2*ew,3] -> both static eye-patch buffers
+                IP.preprocess_eye_frames(self._raw_on_device(k, v), fpc,
+                                         out=(self.static_in['left_eye_patch'],
+                                              self.static_in['right_eye_patch']))
+            elif k == 'screen_frames':  # uint8 [B,T,72,128,3] -> the static screen_frame buffer
+                IP.preprocess_screen_frames(self._raw_on_device(k, v), fpc,
+                                            out=self.static_in['screen_frame'])
+            elif k != 'frames_per_clip':
+                self.static_in[k].copy_(v, non_blocking=True)
         self.inputs_consumed.record(torch.cuda.current_stream(self.trainer.device))
         left, right = self.model.draw_kappas(self.batch)
         slot = self.kappa_slot
@@ -105,15 +131,20 @@ class GraphedTrainStep(object):
         ``__call__(None)`` consumes the staged batch."""
         dev = self.trainer.device
         if self.stage_in is None:
-            self.stage_in = {k: torch.empty_like(v) for k, v in self.static_in.items()}
+            self.stage_in = {}
             self.copy_stream = torch.cuda.Stream(device=dev)
             self.stage_ready = torch.cuda.Event()
             self.stage_free = torch.cuda.Event()
             self.stage_free.record(torch.cuda.current_stream(dev))
         self.copy_stream.wait_event(self.stage_free)       # the previous staged batch was consumed
+        for k in [k for k in self.stage_in if k not in inputs]:
+            del self.stage_in[k]
         with torch.cuda.stream(self.copy_stream):
             for k, v in inputs.items():
-                self.stage_in[k].copy_(v, non_blocking=True)
+                buf = self.stage_in.get(k)
+                if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                    buf = self.stage_in[k] = torch.empty(v.shape, dtype=v.dtype, device=dev)
+                buf.copy_(v, non_blocking=True)
             self.stage_ready.record(self.copy_stream)
 
     def __call__(self, inputs=None):

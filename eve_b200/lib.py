@@ -80,6 +80,7 @@ SIGNATURES = {
     'eve_set_option': (_I, [C.c_char_p, _I]),
     'eve_get_option': (_I, [C.c_char_p, _P]),
     'eve_conv2d_workspace_bytes': (_Z, [_P]),
+    'eve_conv2d_describe': (_I, [_P, _P, _Z]),
     'eve_conv2d_fwd': (_I, [_P, _P, _P, _P, _P, _P, _Z, _P]),
     'eve_conv2d_dgrad': (_I, [_P, _P, _P, _P, _P, _Z, _P]),
     'eve_conv2d_wgrad': (_I, [_P, _P, _P, _P, _P, _P, _Z, _P]),
@@ -131,6 +132,7 @@ SIGNATURES = {
     'eve_masked_losses_bwd': (_I, [_I, _P, _I, _I, _P, _P]),
     'eve_heatmap_frame_losses_fwd': (_I, [_I, _I, _P, _P, _P, _P, _P]),
     'eve_heatmap_frame_losses_bwd': (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
+    'eve_preprocess_frames': (_I, [_P, _I, _I, _I, _I, _I, _I, _F, _F, _P, _I, _P, _P]),
     'eve_adam_clip_workspace_bytes': (_Z, [_P]),
     'eve_adam_clip_step': (_I, [_P, _P, _P, _P, _P, _P, _P, _Z, _P]),
 }

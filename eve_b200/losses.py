@@ -33,12 +33,13 @@ def _feature_dims(a):
     return tuple(range(2, a.ndim))
 
 
-def evaluate_terms(terms):
+def evaluate_terms(terms, return_vector=False):
     """``terms``: list of (loss object, predictions [B,T,...], ground truth, validity [B,T],
     optional second validity).  Returns one scalar tensor per term (views of one [n] vector that
-    a single kernel launch produced; gradients flow to the predictions through one more launch)."""
+    a single kernel launch produced; gradients flow to the predictions through one more launch).
+    ``return_vector``: also return that [n] vector (None when the table needed several launches)."""
     if not terms:
-        return []
+        return ([], None) if return_vector else []
     preds, index, spec = [], {}, []
 
     def slot(t):
@@ -62,14 +63,17 @@ def evaluate_terms(terms):
             spec.append(('identity', slot(bce if loss.op == 'bce' else mse), None, valid, valid2))
         else:
             spec.append((loss.op, slot(pred), gt.detach(), valid, valid2))
-    out = []
+    out, vecs = [], []
     for at in range(0, len(spec), L.LOSS_MAX_TERMS):
         chunk = spec[at:at + L.LOSS_MAX_TERMS]
         used = sorted({pi for _, pi, _, _, _ in chunk})
         remap = {pi: i for i, pi in enumerate(used)}
         chunk = [(op, remap[pi], gt, v, v2) for op, pi, gt, v, v2 in chunk]
         vec = ops.MaskedLossesFn.apply(chunk, *[preds[pi] for pi in used])
+        vecs.append(vec)
         out.extend(vec.unbind(0))
+    if return_vector:
+        return out, (vecs[0] if len(vecs) == 1 else None)
     return out
 
 

@@ -235,7 +235,7 @@ def _all_gaze_history_maps_torch(history_timestamps, heatmaps, validity):
     B, T = heatmaps.shape[:2]
     wgt = gaze_history_weights(history_timestamps, validity)            # [B, T, T]
     flat = heatmaps.reshape(B, T, -1)
-    return torch.bmm(wgt.detach(), flat).reshape(heatmaps.shape)
+    return torch.bmm(wgt.detach().to(flat.dtype), flat).reshape(heatmaps.shape)
 
 
 # ------------------------------------------------------------------- ConvRNN cells --

@@ -143,28 +143,31 @@ class EVE(nn.Module):
 
         self.calculate_losses_and_metrics(d, mid, out)
 
-        # ---- weighted sum (eve.py:234-265)
-        full_loss = torch.zeros((), device=first.device)
-        if 'loss_ang_left_g_initial' in out:
-            full_loss = full_loss + config.loss_coeff_g_ang_initial * (
-                out['loss_ang_left_g_initial'] + out['loss_ang_right_g_initial'])
-        if 'loss_mse_left_PoG_cm_initial' in out and config.loss_coeff_PoG_cm_initial > 0.0:
-            full_loss = full_loss + config.loss_coeff_PoG_cm_initial * (
-                out['loss_mse_left_PoG_cm_initial'] + out['loss_mse_right_PoG_cm_initial'])
-        if 'loss_l1_left_pupil_size' in out:
-            full_loss = full_loss + config.loss_coeff_pupil_size * (
-                out['loss_l1_left_pupil_size'] + out['loss_l1_right_pupil_size'])
-        if 'loss_mse_PoG_cm_final' in out:
-            full_loss = full_loss + config.loss_coeff_PoG_cm_final * out['loss_mse_PoG_cm_final']
-        if 'loss_ce_heatmap_initial' in out:
-            full_loss = full_loss + config.loss_coeff_heatmap_ce_initial * \
-                out['loss_ce_heatmap_initial']
-        if 'loss_ce_heatmap_final' in out:
-            full_loss = full_loss + config.loss_coeff_heatmap_ce_final * \
-                out['loss_ce_heatmap_final']
-        if 'loss_mse_heatmap_final' in out:
-            full_loss = full_loss + config.loss_coeff_heatmap_mse_final * \
-                out['loss_mse_heatmap_final']
+        # ---- weighted sum (eve.py:234-265): one dot product over the loss vector the fused
+        # kernel produced (coefficient 0 for every metric), instead of a chain of scalar kernels
+        coeff = {}
+        for side in ('left', 'right'):
+            coeff['loss_ang_%s_g_initial' % side] = config.loss_coeff_g_ang_initial
+            if config.loss_coeff_PoG_cm_initial > 0.0:
+                coeff['loss_mse_%s_PoG_cm_initial' % side] = config.loss_coeff_PoG_cm_initial
+            coeff['loss_l1_%s_pupil_size' % side] = config.loss_coeff_pupil_size
+        coeff['loss_mse_PoG_cm_final'] = config.loss_coeff_PoG_cm_final
+        coeff['loss_ce_heatmap_initial'] = config.loss_coeff_heatmap_ce_initial
+        coeff['loss_ce_heatmap_final'] = config.loss_coeff_heatmap_ce_final
+        coeff['loss_mse_heatmap_final'] = config.loss_coeff_heatmap_mse_final
+        names, vec = self._loss_table
+        if vec is not None:
+            wkey = (tuple(names), tuple(sorted(coeff.items())), str(vec.device))
+            if getattr(self, '_loss_weights_key', None) != wkey:
+                self._loss_weights = torch.tensor([float(coeff.get(k, 0.0)) for k in names],
+                                                  dtype=torch.float32, device=vec.device)
+                self._loss_weights_key = wkey
+            full_loss = torch.dot(vec, self._loss_weights)
+        else:
+            full_loss = torch.zeros((), device=first.device)
+            for k, c in coeff.items():
+                if k in out:
+                    full_loss = full_loss + c * out[k]
         out['full_loss'] = full_loss
 
         # ---- tensors for visualisation (eve.py:268-283)
@@ -241,8 +244,10 @@ class EVE(nn.Module):
                     term('metric_euc_' + k, LS.euclidean_loss, k, 'PoG_%s_tobii' % unit)
             if 'g_' + stage in mid and 'g' in d:
                 term('metric_ang_g_' + stage, LS.angular_loss, 'g_' + stage, 'g')
-        for name, value in zip(names, LS.evaluate_terms(terms)):
+        values, vec = LS.evaluate_terms(terms, return_vector=True)
+        for name, value in zip(names, values):
             out[name] = value
+        self._loss_table = (names, vec)
 
     # ---------------------------------------------------------------------- labels --
     @staticmethod

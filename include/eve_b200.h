@@ -90,10 +90,18 @@ int eve_get_conv_mode(void);
  *                                from a single read; backward emits dy planes and bias-gradient
  *                                sums) and plane-to-plane residual blocks; 0 = the separate
  *                                stats / apply / reduce / split passes of round 1
+ *   "tc_strip"            0..2   padded-strip kernel for 3x3 stride-1 layers narrower than 128
+ *                                pixels (input staged once per K chunk as a zero-padded strip, the
+ *                                nine taps taken as descriptor shifts, weight tiles shared by all
+ *                                tiles of the strip): 0 off, 1 where its plan wastes at most a
+ *                                seventh more MMA rows than the per-tap box kernel, 2 wherever it fits
  * Unknown names / out-of-range values return EVE_ERR_CONFIG. */
 int eve_set_option(const char* name, int value);
 int eve_get_option(const char* name, int* value);
 size_t eve_conv2d_workspace_bytes(const eve_conv_params* p);
+/* Text description of the kernel (and tiling plan) eve_conv2d_fwd picks for this geometry in
+ * conv mode 1 (diagnostics, docs). */
+int eve_conv2d_describe(const eve_conv_params* p, char* buf, size_t cap);
 int eve_conv2d_fwd(const eve_conv_params* p, const float* x, const float* w, const float* bias,
                    float* y, void* workspace, size_t workspace_bytes, eve_stream_t stream);
 /* dx = d(loss)/dx given dy */
@@ -368,6 +376,17 @@ int eve_heatmap_frame_losses_fwd(int n, int hw, const float* pred, const float* 
 int eve_heatmap_frame_losses_bwd(int n, int hw, const float* pred, const float* gt,
                                  const float* dbce, const float* dmse, float* dpred,
                                  eve_stream_t stream);
+
+/* ------------------------------------------------------------------ input pipeline --
+ * datasources/eve_sequences.py:196-211 (preprocess_frames / preprocess_screen_frames) and the
+ * eye-patch split of :283-285 on the device: frames[n,h,w_in,c] uint8 (decoder layout) ->
+ * out[n,c,h,w_out] float32 = frames[:, :, x_offset : x_offset + w_out, :] * scale + bias, rounded
+ * like numpy's two in-place float32 ops (bit-identical to the reference's arrays).
+ * frames_per_clip (optional, DEVICE int[n / steps]): frames t >= frames_per_clip[clip] are written
+ * as zeros (the reference zero-pads short clips after preprocessing, :287-299). */
+int eve_preprocess_frames(const unsigned char* frames, int n, int h, int w_in, int c, int x_offset,
+                          int w_out, float scale, float bias, const int* frames_per_clip, int steps,
+                          float* out, eve_stream_t stream);
 
 /* ------------------------------------------------------------------ optimiser step --
  * training.py:492-502 + train.py:49-55: clip_grad_norm_(max_norm) then Adam with L2

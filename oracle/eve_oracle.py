@@ -417,6 +417,32 @@ def bce_per_frame(a, b):
     return F.binary_cross_entropy(a, b, reduction='none').mean(dim=_feature_dims(a))
 
 
+# -------------------------------------------------------------------- input pipeline --
+def preprocess_frames(frames):
+    """datasources/eve_sequences.py:196-203: N x H x W x C uint8 -> N x C x H x W float32 in [-1, 1]
+    (numpy, in-place float32 ops exactly as the reference writes them)."""
+    import numpy as np
+    frames = np.transpose(frames, [0, 3, 1, 2])
+    frames = frames.astype(np.float32)
+    frames *= 2.0 / 255.0
+    frames -= 1.0
+    return frames
+
+
+def preprocess_screen_frames(frames):
+    """datasources/eve_sequences.py:205-211."""
+    import numpy as np
+    frames = np.transpose(frames, [0, 3, 1, 2])
+    frames = frames.astype(np.float32)
+    frames *= 1.0 / 255.0
+    return frames
+
+
+def split_eye_patches(frames, ew):
+    """eve_sequences.py:283-285 on preprocessed "eyes" frames: (left, right)."""
+    return frames[:, :, :, ew:], frames[:, :, :, :ew]
+
+
 # ------------------------------------------------------------------------------- EVE --
 def derive_labels(inp, cfg, training, kappas=None):
     """EVE.calculate_additional_labels (eve.py:441-543), vectorised over B and T.

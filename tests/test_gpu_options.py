@@ -12,7 +12,7 @@ from eve_b200 import lib as L            # noqa: E402
 from tests import gpu_util as G          # noqa: E402
 
 OPTIONS = ('tc_stage_cap', 'tc_row_kernel', 'tc_row_strips', 'tc_row_wgrad', 'tc_wgrad_waves',
-           'fused_planes', 'fused_norm')
+           'fused_planes', 'fused_norm', 'tc_strip')
 
 
 @pytest.fixture()
@@ -58,6 +58,45 @@ def test_halo_row_kernels_match_fp64(cin, cout, k, strips, options):
     assert G.rel(db, dy.double().sum(dim=(0, 2, 3))) < 2e-5
 
 
+# padded-strip kernel (n, cin, cout, h, w): one image per item with several strips (ragged last
+# strip), several whole images per item (halo rows between images are junk accumulator rows), a
+# ragged tail group (n not a multiple of the images per item), every BN / K-chunk template
+STRIP_CASES = [(5, 64, 64, 32, 32), (3, 64, 64, 36, 64), (7, 256, 256, 9, 16), (4, 128, 128, 18, 32),
+               (9, 128, 128, 16, 16), (11, 256, 128, 8, 8), (13, 512, 128, 4, 4), (3, 128, 32, 36, 64),
+               (3, 32, 64, 36, 64), (3, 32, 32, 36, 64), (5, 16, 32, 20, 24), (2, 64, 64, 7, 10),
+               (1, 32, 32, 5, 8), (17, 64, 128, 5, 8)]
+
+
+@pytest.mark.parametrize('case', STRIP_CASES, ids=lambda c: 'x'.join(map(str, c)))
+def test_padded_strip_kernel_matches_fp64(case, options):
+    """tc_strip = 2 takes the strip kernel wherever its plan fits (forward AND the stride-1 data
+    gradient, which is the same kernel on the flipped filter); 0 is the per-tap box kernel."""
+    import ctypes as C
+    n, cin, cout, h, w = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, generator=g)
+    xd = x.double().requires_grad_(True)
+    y = F.conv2d(xd, wt.double(), b.double(), padding=1)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy.double())
+    lib = L.load()
+    lib.eve_set_conv_mode(1)
+    options('tc_strip', 2)
+    buf = C.create_string_buffer(256)
+    L.check(lib.eve_conv2d_describe(C.byref(L.ConvParams(n, h, w, cin, cout, 3, 1, 1)), buf, 256), 'describe')
+    assert buf.value.decode().startswith('strip kernel'), buf.value
+    got = G.conv_fwd(x.cuda(), wt.cuda(), b.cuda(), 1, 1)
+    dx = G.conv_dgrad(dy.cuda(), wt.cuda(), (h, w), 1, 1)
+    options('tc_strip', 0)
+    got0 = G.conv_fwd(x.cuda(), wt.cuda(), b.cuda(), 1, 1)
+    torch.cuda.synchronize()
+    assert G.rel(got, y) < 3e-5
+    assert G.rel(dx, xd.grad) < 3e-5
+    assert G.rel(got0, y) < 3e-5
+
+
 @pytest.mark.parametrize('waves', [1, 2, 4])
 def test_split_k_wave_count_does_not_change_weight_gradients(waves, options):
     n, cin, h, w, cout = 6, 64, 32, 32, 64
@@ -97,6 +136,8 @@ def _eve_step(cfg, seed=5, B=2, T=3):
 
 
 VARIANTS = [
+    dict(tc_strip=2),
+    dict(tc_strip=0),
     dict(fused_norm=0),
     dict(fused_norm=0, fused_planes=0),
     dict(fused_planes=0),
@@ -126,7 +167,9 @@ def test_option_variants_agree_on_a_full_training_step(variant, cfg, options):
     # (two-pass cluster reduction vs shifted single pass); RefineNet at random weights amplifies
     # that 1e-7 difference to ~1e-2 on the last gradients of the chain (initial.0), the same
     # amplification the fp32 reference shows against fp64 (test_gpu_models.py)
-    gtol = 2e-2 if ('fused_norm' in variant or 'fused_planes' in variant) else 2e-3
+    # (the strip kernel likewise sums the taps of a K chunk in a different order)
+    gtol = 2e-2 if ('fused_norm' in variant or 'fused_planes' in variant or 'tc_strip' in variant) \
+        else 2e-3
     # biases in front of an InstanceNorm have an exactly zero gradient (the norm removes the
     # mean): what is computed there is cancellation noise ~1e-6 of the real gradients
     floor = 1e-6 * max(float(v.double().norm()) for v in base_grads.values())

@@ -59,6 +59,11 @@ print('%-72s %6s %9s %9s %8s' % ('kernel', 'count', 'busy ms', 'gap ms', 'gap/k 
 for name in sorted(busy, key=lambda n: -(busy[n] + gap[n]))[:45]:
     print('%-72s %6d %9.3f %9.3f %8.2f' % (name, cnt[name], busy[name] / 1e3, gap[name] / 1e3,
                                             gap[name] / cnt[name]))
+aten = [n for n in busy if not n.startswith('eve::') and not n.startswith('Memcpy') and not n.startswith('Memset')]
+print('ATen kernels in the step: %d launches, %.3f ms busy; library kernels: %d launches' % (
+    sum(cnt[n] for n in aten), sum(busy[n] for n in aten) / 1e3, sum(cnt[n] for n in busy if n not in aten)))
+for n in sorted(aten, key=lambda n: -cnt[n])[:12]:
+    print('   %5d x %s' % (cnt[n], n[:100]))
 print()
 print('largest idle gaps by (previous kernel -> next kernel)')
 for (a, b), (c, gsum) in sorted(pairs.items(), key=lambda kv: -kv[1][1])[:25]:
