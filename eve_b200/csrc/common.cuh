@@ -136,6 +136,12 @@ int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const voi
                 int fmt, float out_scale, cudaStream_t s);
 
 int conv_tc_describe(const ConvGeom& g, char* buf, size_t cap);
+// persistent ConvGRU forward (conv_tc.cu): one CTA per clip walks all T steps
+bool cgru_seq_supported(int nf, int H, int W);
+int cgru_seq_fwd(int B, int T, const void* w1h_hi, const void* w1h_lo, const void* w2h_hi,
+                 const void* w2h_lo, const float* gx1, const float* gx2, const float* h0, float* r,
+                 float* z, float* n, float* h, float* xh, float* cat2, float out_scale,
+                 cudaStream_t s);
 bool conv_tc_dgrad_s2_supported(const ConvGeom& g);
 int conv_tc_dgrad_s2_run(const ConvGeom& g, const void* d_hi, const void* d_lo, const void* w_hi,
                          const void* w_lo, const float* addend, float* dx, int npass,
@@ -167,6 +173,7 @@ enum OptKey {
   OPT_FUSED_PLANES,          // InstanceNorm kernels emit the consuming convolution's operand planes
   OPT_FUSED_NORM,            // one-pass cluster InstanceNorm kernels + plane-to-plane block pipelines
   OPT_TC_STRIP,              // padded-strip tcgen05 kernel for 3x3 stride-1 layers: 0 off, 1 auto, 2 whenever it fits
+  OPT_CGRU_PERSISTENT,       // ConvGRU (64 features, 5x8 maps): whole sequence in one persistent kernel
   OPT_COUNT
 };
 int get_option(int key);

@@ -207,15 +207,18 @@ constexpr int kBarrierBytes = 512;     // (2 * kMaxStages + 4) mbarriers + the T
 // N = 2 BN over [B_hi ; B_lo] yields A_hi B_hi in accumulator columns [0, BN) and A_hi B_lo in
 // [BN, 2 BN), a second MMA adds A_lo B_hi to [0, BN), and the epilogue sums the two halves in fp32:
 // 51 + 68 instead of 3 x 51 cycles at BN = 64, 43 + 44 instead of 3 x 43 at BN = 16.
-template <int BN, int NPASS>
+// STACK is a property of the LAYER (Cout <= 64 or not), not of the tile width a launch ends up
+// with: few-tile layers narrow BN to spread over more SMs, and a frame's result must not depend on
+// the batch it is processed in (the two issue orders round differently).
+template <int BN, int NPASS, bool STACK = false>
 struct TcCfg {
   static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
-  static constexpr bool kStack = NPASS == 3 && BN <= 64;
+  static constexpr bool kStack = NPASS == 3 && BN <= 64 && STACK;
   static constexpr int kAccCols = kStack ? 2 * BN : BN;       // accumulator columns of one tile
   static constexpr uint32_t kTmemCols = kAccCols < 32 ? 32 : kAccCols;   // per accumulator buffer (x2)
 };
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, bool STACK>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -223,7 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator
   // is double-buffered in TMEM so the epilogue of tile i overlaps the K loop of tile i+1; the
   // shared-memory ring simply keeps rolling across tile boundaries.
-  using Cfg = TcCfg<BN, NPASS>;
+  using Cfg = TcCfg<BN, NPASS, STACK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
@@ -940,6 +943,269 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   }
 }
 
+// ================================================================= persistent ConvGRU ==
+// CGRUCell (common.py:388-415) over a whole sequence in ONE kernel, for the 64-feature 5x8
+// bottleneck of GazeRefineNet (refine_net.py:151-176):
+//     r, z = sigmoid(conv3x3(cat[x, h]; W1) + b1)        n = tanh(conv3x3(cat[r * h, x]; W2) + b2)
+//     h'   = (1 - z) n + z h
+// The x halves of both convolutions do not depend on the recurrence: the caller evaluates them for
+// all T steps at once (gx1 = conv(x; W1[:, :nf]) + b1, gx2 = conv(x; W2[:, nf:]) + b2, two batched
+// launches).  What is left per step -- conv(h; W1[:, nf:]) and conv(r * h; W2[:, :nf]) on a 5x8 map
+// -- is 0.3 GFLOP but strictly sequential; as separate launches it cost ~40 us per step.  Here one
+// CTA owns one clip and walks its T steps:
+//   * the hidden state lives in shared memory as the fp16 hi/lo operand planes of a zero-padded
+//     7x10 strip (so the nine taps are descriptor shifts, as in the strip kernel) and in registers
+//     as fp32;
+//   * D^T[out channel][position] = W[out channel][K] . act[position][K]: the weights are the M = 128
+//     operand (streamed tap by tap from L2 through a TMA ring, they never change), the 48 padded
+//     positions the N operand, so every TMEM lane is an output channel and the gate math runs on
+//     all 128 epilogue threads with coalesced channel-major global accesses;
+//   * the epilogue threads write r * h and h' straight back into the operand planes (manual
+//     128-byte swizzle) and hand over to the MMA warp through mbarriers: no global round trip and
+//     no launch inside the time loop.
+// The per-step tape the BPTT kernels read (r, z, n, h and the h-halves of xh / cat2) is written
+// from the same registers.
+struct CgruSeqParams {
+  int B, T;
+  const float* gx1;     // [T][B][40][128]  x-half of the gate convolution + bias
+  const float* gx2;     // [T][B][40][64]   x-half of the candidate convolution + bias
+  const float* h0;      // [B][40][64]
+  float *r, *z, *n, *h; // [T][B][40][64]
+  float* xh;            // [T][B][40][128]: this kernel fills channels [64, 128) with h_{t-1}
+  float* cat2;          // [T][B][40][128]: this kernel fills channels [0, 64) with r * h_{t-1}
+  float out_scale;      // undoes the 2^6 pre-scale of the fp16 weight planes
+};
+
+constexpr int kCgNf = 64, kCgH = 5, kCgW = 8, kCgWp = kCgW + 2, kCgPix = kCgH * kCgW;
+constexpr int kCgPos = 48;                       // padded positions covered (last valid one is 47)
+constexpr int kCgActRows = 88;                   // staged rows one operand plane may be read at
+constexpr int kCgActPlane = kCgActRows * 128;    // bytes (1024-aligned)
+constexpr int kCgStageBytes = 2 * 128 * kCgNf * 2;   // [hi][lo] x 128 out channels x 64 in channels
+constexpr int kCgStages = 5;
+constexpr int kCgSmem = kCgStages * kCgStageBytes + 4 * kCgActPlane + kCgPix * kCgNf * 4 + 1024 + 512;
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// value v of channel c at padded row p of an operand plane pair (K-major, SWIZZLE_128B)
+__device__ __forceinline__ void cg_store_act(uint8_t* plane_hi, int p, int c, float v) {
+  const __half hh = __float2half_rn(v);
+  const __half ll = __float2half_rn(v - __half2float(hh));
+  const uint32_t off = (uint32_t)p * 128u + ((((uint32_t)c >> 3) ^ ((uint32_t)p & 7u)) << 4) +
+                       ((uint32_t)c & 7u) * 2u;
+  *reinterpret_cast<__half*>(plane_hi + off) = hh;
+  *reinterpret_cast<__half*>(plane_hi + kCgActPlane + off) = ll;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+cgru_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_constant__ CUtensorMap tmW1_lo,
+                    const __grid_constant__ CUtensorMap tmW2_hi, const __grid_constant__ CUtensorMap tmW2_lo,
+                    const CgruSeqParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* ring = smem;                                        // [stages][hi | lo][128 x 64 fp16]
+  uint8_t* act1 = ring + kCgStages * kCgStageBytes;            // h planes      [hi | lo][88 rows]
+  uint8_t* act2 = act1 + 2 * kCgActPlane;                      // r * h planes
+  float* zbuf = reinterpret_cast<float*>(act2 + 2 * kCgActPlane);   // [40][64]
+  uint64_t* full = reinterpret_cast<uint64_t*>(zbuf + kCgPix * kCgNf);
+  uint64_t* empty = full + kCgStages;
+  uint64_t* d_full = empty + kCgStages;      // [2]: gate / candidate accumulators complete
+  uint64_t* act_ready = d_full + 2;          // [2]: h planes / r*h planes written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const int B = p.B, T = p.T;
+
+  if (warp == 0 && lane == 0) {
+    tmap_prefetch(&tmW1_hi);
+    tmap_prefetch(&tmW1_lo);
+    tmap_prefetch(&tmW2_hi);
+    tmap_prefetch(&tmW2_lo);
+    for (int i = 0; i < kCgStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d_full[i], 1);
+      mbar_init(&act_ready[i], 128);
+    }
+    fence_barrier_init();
+  }
+  // pad rows / columns of the operand planes stay zero for the whole kernel
+  for (int i = threadIdx.x; i < 4 * kCgActPlane / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(act1)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== weight producer: 18 tap tiles per step, forever the same =====================
+    if (elect_one()) {
+      uint32_t g = 0;
+      for (int t = 0; t < T; ++t) {
+        for (int conv = 0; conv < 2; ++conv) {
+          const CUtensorMap* mh = conv == 0 ? &tmW1_hi : &tmW2_hi;
+          const CUtensorMap* ml = conv == 0 ? &tmW1_lo : &tmW2_lo;
+          const uint32_t tx = conv == 0 ? 2u * 128u * kCgNf * 2u : 2u * 64u * kCgNf * 2u;
+          for (int tap = 0; tap < 9; ++tap, ++g) {
+            const uint32_t s = g % kCgStages;
+            mbar_wait(&empty[s], ((g / kCgStages) & 1) ^ 1);
+            uint8_t* dst = ring + (size_t)s * kCgStageBytes;
+            mbar_expect_tx(&full[s], tx);
+            tma_load_2d(dst, mh, &full[s], tap * kCgNf, 0);
+            tma_load_2d(dst + kCgStageBytes / 2, ml, &full[s], tap * kCgNf, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // D fp32, A = weights (fp16, K-major, M = 128), B = activations (fp16, K-major, N = 48)
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(kCgPos >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint64_t desc0 = kmajor_desc(0u, 64);
+    const uint32_t ring16 = smem_u32(ring) >> 4;
+    const uint32_t act16[2] = {smem_u32(act1) >> 4, smem_u32(act2) >> 4};
+    constexpr uint32_t kLo16W = (uint32_t)(kCgStageBytes / 2) >> 4;
+    constexpr uint32_t kLo16A = (uint32_t)kCgActPlane >> 4;
+    uint32_t g = 0;
+    for (int t = 0; t < T; ++t) {
+      for (int conv = 0; conv < 2; ++conv) {
+        mbar_wait(&act_ready[conv], (uint32_t)t & 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(conv * 64);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap, ++g) {
+          const uint32_t s = g % kCgStages;
+          mbar_wait(&full[s], (g / kCgStages) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const int rr = tap / 3, qq = tap - 3 * rr;
+            const uint64_t w_hi = desc0 + (uint64_t)(ring16 + s * ((uint32_t)kCgStageBytes >> 4));
+            const uint64_t a_hi = desc0 + (uint64_t)(act16[conv] + (uint32_t)(rr * kCgWp + qq) * 8u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t dw_hi = w_hi + (uint64_t)(k * 2), dw_lo = dw_hi + kLo16W;
+              const uint64_t da_hi = a_hi + (uint64_t)(k * 2), da_lo = da_hi + kLo16A;
+              umma_bf16(tmem_d, dw_lo, da_hi, idesc, (tap | k) != 0);
+              umma_bf16(tmem_d, dw_hi, da_lo, idesc, 1);
+              umma_bf16(tmem_d, dw_hi, da_hi, idesc, 1);
+            }
+            umma_commit(&empty[s]);
+            if (tap == 8) umma_commit(&d_full[conv]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================== gates (128 threads: TMEM lane = output channel) =====================
+    const int quad = warp & 3;
+    const int co = quad * 32 + lane;           // gate convolution: r for co < 64, z for co >= 64
+    const int c = co & 63;
+    const bool is_r = co < 64;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float h[kCgPix];
+    // initial state -> registers, operand planes and the h-half of xh[0]
+    if (is_r) {
+#pragma unroll
+      for (int pix = 0; pix < kCgPix; ++pix) {
+        const float v = __ldg(p.h0 + ((size_t)b * kCgPix + pix) * kCgNf + c);
+        h[pix] = v;
+        cg_store_act(act1, (pix / kCgW + 1) * kCgWp + (pix % kCgW) + 1, c, v);
+        p.xh[((size_t)b * kCgPix + pix) * (2 * kCgNf) + kCgNf + c] = v;
+      }
+    }
+    fence_proxy_async();
+    mbar_arrive(&act_ready[0]);
+    for (int t = 0; t < T; ++t) {
+      const size_t frame = (size_t)t * B + b;
+      // ---- r, z
+      float gx[kCgPix];
+#pragma unroll
+      for (int pix = 0; pix < kCgPix; ++pix)
+        gx[pix] = __ldg(p.gx1 + (frame * kCgPix + pix) * (2 * kCgNf) + co);
+      mbar_wait(&d_full[0], (uint32_t)t & 1);
+      tc_fence_after();
+      float v[kCgPos];
+      tmem_ld32(tlane, v);
+      tmem_ld16(tlane + 32u, v + 32);
+#pragma unroll
+      for (int j = 0; j < kCgPos; ++j) {
+        if (j % kCgWp < kCgW) {
+          const int pix = (j / kCgWp) * kCgW + j % kCgWp;
+          const float s = 1.f / (1.f + expf(-(v[j] * p.out_scale + gx[pix])));
+          const size_t o = (frame * kCgPix + pix) * kCgNf + c;
+          if (is_r) {
+            p.r[o] = s;
+            const float rh = s * h[pix];
+            p.cat2[(frame * kCgPix + pix) * (2 * kCgNf) + c] = rh;
+            cg_store_act(act2, j + kCgWp + 1, c, rh);
+          } else {
+            p.z[o] = s;
+            zbuf[pix * kCgNf + c] = s;
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&act_ready[1]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // z (threads 64..127) -> zbuf -> threads 0..63
+      // ---- candidate and the new state (threads 0..63)
+      if (is_r) {
+#pragma unroll
+        for (int pix = 0; pix < kCgPix; ++pix)
+          gx[pix] = __ldg(p.gx2 + (frame * kCgPix + pix) * kCgNf + c);
+      }
+      mbar_wait(&d_full[1], (uint32_t)t & 1);
+      tc_fence_after();
+      if (is_r) {
+        tmem_ld32(tlane + 64u, v);
+        tmem_ld16(tlane + 96u, v + 32);
+#pragma unroll
+        for (int j = 0; j < kCgPos; ++j) {
+          if (j % kCgWp < kCgW) {
+            const int pix = (j / kCgWp) * kCgW + j % kCgWp;
+            const float nv = tanhf(v[j] * p.out_scale + gx[pix]);
+            const float zv = zbuf[pix * kCgNf + c];
+            const float hn = (1.f - zv) * nv + zv * h[pix];
+            const size_t o = (frame * kCgPix + pix) * kCgNf + c;
+            p.n[o] = nv;
+            p.h[o] = hn;
+            if (t + 1 < T)
+              p.xh[(((size_t)(t + 1) * B + b) * kCgPix + pix) * (2 * kCgNf) + kCgNf + c] = hn;
+            h[pix] = hn;
+            cg_store_act(act1, j + kCgWp + 1, c, hn);
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&act_ready[0]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
 // =============================================================== weight gradient ====
 // dW[co][(r,q)][ci] = sum over pixels p=(n,h,w) of dy[n, h-r+pad, w-q+pad, co] * x[n,h,w,ci]
 // as a GEMM whose K dimension is the pixel index.  Both operands come straight from the NHWC
@@ -1579,12 +1845,12 @@ void pick_box(int N, int H, int W, int& bw, int& bh, int& bn) {
   }
 }
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, bool STACK>
 int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
               const CUtensorMap& b_lo, const TcParams& p0, int tiles_m, int tiles_co,
               cudaStream_t s) {
-  using Cfg = TcCfg<BN, NPASS>;
-  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_kernel<BN, NPASS>, 227 * 1024));
+  using Cfg = TcCfg<BN, NPASS, STACK>;
+  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_kernel<BN, NPASS, STACK>, 227 * 1024));
   TcParams p = p0;
   p.tiles_m = tiles_m;
   p.tiles_co = tiles_co;
@@ -1600,19 +1866,27 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
   const int smem_bytes = p.stages * p.stage_bytes + 1024 /*align*/ + kBarrierBytes;
   const long long total = (long long)tiles_m * tiles_co;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);   // one persistent CTA per SM
-  conv_tc_kernel<BN, NPASS><<<grid, kThreads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+  conv_tc_kernel<BN, NPASS, STACK><<<grid, kThreads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }
 
 template <int NPASS>
-int launch_tc_bn(int BN, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                 const CUtensorMap& b_lo, const TcParams& p, int gx, int gy, cudaStream_t s) {
+int launch_tc_bn(int BN, bool stack, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                 const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcParams& p, int gx, int gy,
+                 cudaStream_t s) {
+  if (NPASS == 3 && stack) {
+    switch (BN) {
+      case 64: return launch_tc<64, NPASS, true>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+      case 32: return launch_tc<32, NPASS, true>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+      default: return launch_tc<16, NPASS, true>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+    }
+  }
   switch (BN) {
-    case 128: return launch_tc<128, NPASS>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
-    case 64: return launch_tc<64, NPASS>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
-    case 32: return launch_tc<32, NPASS>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
-    default: return launch_tc<16, NPASS>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+    case 128: return launch_tc<128, NPASS, false>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+    case 64: return launch_tc<64, NPASS, false>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+    case 32: return launch_tc<32, NPASS, false>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+    default: return launch_tc<16, NPASS, false>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
   }
 }
 
@@ -1676,6 +1950,7 @@ static int tc_launch(const TcParams& p0, const void* x_hi, const void* x_lo, int
   p.fmt = fmt;
   const int tiles_n = cdiv(p.N, p.bn);
   int BN = bn_for(p.Cout);
+  const bool stack = BN <= 64;          // decided by the layer, before any narrowing (see TcCfg)
   // Few pixel tiles (the per-time-step ConvRNN gate convolutions have 3): narrower output-channel
   // tiles put more SMs on the layer; each CTA's serial chain of MMAs shrinks by the same factor.
   while (BN > 16 && (long long)p.tiles_h * tiles_n * (p.Cout / BN) < kNumSMs / 2) BN >>= 1;
@@ -1691,8 +1966,8 @@ static int tc_launch(const TcParams& p0, const void* x_hi, const void* x_lo, int
     b_lo = b_hi;
   }
   const int gx = p.tiles_h * tiles_n, gy = p.Cout / BN;
-  return npass == 3 ? launch_tc_bn<3>(BN, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s)
-                    : launch_tc_bn<1>(BN, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+  return npass == 3 ? launch_tc_bn<3>(BN, stack, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s)
+                    : launch_tc_bn<1>(BN, false, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
 }
 
 // ---- halo-row kernels: planning and launch
@@ -1813,7 +2088,7 @@ static double generic_box_efficiency(const ConvGeom& g) {
          ((double)g.N / (double)(cdiv(g.N, bn) * bn));
 }
 
-static bool strip_plan(const ConvGeom& g, StripPlan& best) {
+static bool strip_plan(const ConvGeom& g, StripPlan& best, int force_kc = 0) {
   if (g.KH != 3 || g.KW != 3 || g.stride != 1 || g.pad != 1 || g.OH != g.H || g.OW != g.W) return false;
   if (g.W + 2 > 256 || g.W >= kTileM || g.N < 1) return false;
   const int BN = strip_bn_for(g.Cout);
@@ -1824,7 +2099,7 @@ static bool strip_plan(const ConvGeom& g, StripPlan& best) {
   const int kcs[3] = {64, 32, 16};
   for (int ki = 0; ki < 3; ++ki) {
     const int KC = kcs[ki];
-    if (g.Cin % KC != 0) continue;
+    if (g.Cin % KC != 0 || (force_kc && KC != force_kc)) continue;
     const int bsz = 2 * (BN * KC * 2 < 1024 ? 1024 : BN * KC * 2);
     for (int bn = 1; bn <= 16 && bn <= g.N; ++bn) {
       for (int R = (bn == 1 ? 1 : g.H); R <= g.H; ++R) {
@@ -1858,11 +2133,22 @@ static bool strip_plan(const ConvGeom& g, StripPlan& best) {
   return best.score > 0.0;
 }
 
-bool conv_tc_strip_supported(const ConvGeom& g) {
+// The strip and the box kernel sum a pixel's products in different orders (as do two K chunk
+// widths), and a frame's result must not depend on the batch it is processed in
+// (test_inference_stream_900_frames_in_chunks): the kernel choice and the chunk width are therefore
+// decided for a canonical batch (one full wave of images per SM), i.e. from (H, W, Cin, Cout) alone;
+// only the strip height / images per item -- which do not change any output bit -- follow the real N.
+static ConvGeom canonical_batch(const ConvGeom& g) {
+  ConvGeom c = g;
+  c.N = 64 * kNumSMs;
+  return c;
+}
+
+static bool strip_decision(const ConvGeom& g, StripPlan& canon) {
   const int opt = get_option(OPT_TC_STRIP);
   if (opt == 0) return false;
-  StripPlan pl;
-  if (!strip_plan(g, pl)) return false;
+  const ConvGeom c = canonical_batch(g);
+  if (!strip_plan(c, canon)) return false;
   if (opt == 2) return true;
   // auto (calibrated with tools/probe_strip.py at the bench geometries, profiles/r2_probe_strip.txt):
   // the strip kernel issues junk rows (pad columns, halo rows, partial tiles) but moves 3-7x fewer
@@ -1871,10 +2157,15 @@ bool conv_tc_strip_supported(const ConvGeom& g) {
   // 32-channel outputs (1.02-1.36x); at 64 channels it needs both accumulator sets (18x32: 1.07-
   // 1.16x, while 32x32 / 36x64 plans only fit one set and lose 15-30 %); on the well-filled
   // 128-channel maps the box kernel already runs at 70-78 % of the split-operand peak.
-  const double ge = generic_box_efficiency(g);
-  if (pl.BN == 32) return true;
-  if (pl.BN == 64) return pl.nsets == 2 && pl.score >= 0.78 * ge;
-  return pl.score >= 0.9 * ge;
+  const double ge = generic_box_efficiency(c);
+  if (canon.BN == 32) return true;
+  if (canon.BN == 64) return canon.nsets == 2 && canon.score >= 0.78 * ge;
+  return canon.score >= 0.9 * ge;
+}
+
+bool conv_tc_strip_supported(const ConvGeom& g) {
+  StripPlan canon, pl;
+  return strip_decision(g, canon) && strip_plan(g, pl, canon.KC);
 }
 
 template <int BN, int KC>
@@ -1903,8 +2194,9 @@ static int launch_strip_kc(int kc, const CUtensorMap& a_hi, const CUtensorMap& a
 static int conv_tc_strip_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const void* w_hi,
                              const void* w_lo, const float* bias, const float* addend, float* y,
                              int fmt, float out_scale, cudaStream_t s) {
-  StripPlan pl;
-  EVE_REQUIRE(strip_plan(g, pl), EVE_ERR_SHAPE, "conv_tc_strip: unsupported geometry");
+  StripPlan canon, pl;
+  EVE_REQUIRE(strip_decision(g, canon) && strip_plan(g, pl, canon.KC), EVE_ERR_SHAPE,
+              "conv_tc_strip: unsupported geometry");
   TcStripParams p;
   p.N = g.N; p.H = g.H; p.W = g.W; p.Cout = g.Cout; p.Wp = g.W + 2;
   p.R = pl.R; p.bn = pl.bn;
@@ -1936,16 +2228,45 @@ static int conv_tc_strip_run(const ConvGeom& g, const void* x_hi, const void* x_
 int conv_tc_describe(const ConvGeom& g, char* buf, size_t cap) {
   if (!conv_tc_supported(g)) return snprintf(buf, cap, "not on the tensor-core path");
   if (conv_tc_row_supported(g)) return snprintf(buf, cap, "halo-row kernel");
-  StripPlan pl;
-  const bool have = strip_plan(g, pl);
+  StripPlan canon, pl;
+  const bool take = strip_decision(g, canon);
+  const bool have = take ? strip_plan(g, pl, canon.KC) : strip_plan(g, pl);
   const double ge = generic_box_efficiency(g);
-  if (have && conv_tc_strip_supported(g))
+  if (have && take)
     return snprintf(buf, cap, "strip kernel BN=%d KC=%d R=%d bn=%d T=%d sets=%d stages=%d score=%.3f (box kernel %.3f)",
                     pl.BN, pl.KC, pl.R, pl.bn, pl.Tmax, pl.nsets, pl.b_stages, pl.score, ge);
   if (have)
     return snprintf(buf, cap, "box kernel eff=%.3f (strip plan BN=%d KC=%d R=%d bn=%d T=%d sets=%d score=%.3f)", ge,
                     pl.BN, pl.KC, pl.R, pl.bn, pl.Tmax, pl.nsets, pl.score);
   return snprintf(buf, cap, "box kernel eff=%.3f", ge);
+}
+
+// ---- persistent ConvGRU sequence kernel
+bool cgru_seq_supported(int nf, int H, int W) {
+  return get_option(OPT_CGRU_PERSISTENT) != 0 && conv_mode() == 1 && nf == kCgNf && H == kCgH && W == kCgW;
+}
+
+// w1h_*: fp16 hi/lo K-major planes [128][9 * 64] of gates_1.weight[:, nf:2nf] (pre-scaled by
+// 1 / out_scale), w2h_*: [64][9 * 64] of gate_2.weight[:, 0:nf]
+int cgru_seq_fwd(int B, int T, const void* w1h_hi, const void* w1h_lo, const void* w2h_hi,
+                 const void* w2h_lo, const float* gx1, const float* gx2, const float* h0, float* r,
+                 float* z, float* n, float* h, float* xh, float* cat2, float out_scale,
+                 cudaStream_t s) {
+  EVE_REQUIRE(B > 0 && T > 0, EVE_ERR_SHAPE, "cgru_seq_fwd: B=%d T=%d", B, T);
+  CgruSeqParams p;
+  p.B = B; p.T = T;
+  p.gx1 = gx1; p.gx2 = gx2; p.h0 = h0;
+  p.r = r; p.z = z; p.n = n; p.h = h; p.xh = xh; p.cat2 = cat2;
+  p.out_scale = out_scale;
+  CUtensorMap m1h, m1l, m2h, m2l;
+  EVE_TRY(make_map_2d(&m1h, w1h_hi, 2 * kCgNf, 9 * kCgNf, 64, 2 * kCgNf, TC_F16));
+  EVE_TRY(make_map_2d(&m1l, w1h_lo, 2 * kCgNf, 9 * kCgNf, 64, 2 * kCgNf, TC_F16));
+  EVE_TRY(make_map_2d(&m2h, w2h_hi, kCgNf, 9 * kCgNf, 64, kCgNf, TC_F16));
+  EVE_TRY(make_map_2d(&m2l, w2h_lo, kCgNf, 9 * kCgNf, 64, kCgNf, TC_F16));
+  EVE_TRY(ensure_dynamic_smem((const void*)cgru_seq_fwd_kernel, kCgSmem));
+  cgru_seq_fwd_kernel<<<B, kThreads, kCgSmem, s>>>(m1h, m1l, m2h, m2l, p);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
 }
 
 // y[N,OH,OW,Cout] = conv(x) (+bias) (+addend).  x_hi/x_lo: 16-bit NHWC planes of the input;

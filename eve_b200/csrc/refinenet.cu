@@ -359,6 +359,18 @@ swap_bt_kernel(const float* __restrict__ x, long long total, int A, int Bd, int 
   y[(((size_t)b * A + a) * P + p) * ldy + c] = x[(((size_t)a * Bd + b) * P + p) * ldx + c];
 }
 
+// OIHW slice along the input channels: out[co][ci][3][3] = w[co][c0 + ci][3][3]
+__global__ void __launch_bounds__(256)
+slice_cin_kernel(const float* __restrict__ w, int cout, int cin_total, int c0, int cin,
+                 float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * cin * 9) return;
+  int t = i % 9;
+  int ci = (i / 9) % cin;
+  int co = i / (9 * cin);
+  out[i] = w[((size_t)co * cin_total + c0 + ci) * 9 + t];
+}
+
 // xh[row, 0:nf] = x[row], xh[row, nf:2nf] = h[row]
 __global__ void __launch_bounds__(256)
 cat2_kernel(const float* __restrict__ a, const float* __restrict__ b, long long rows, int nf,
@@ -883,14 +895,56 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
       for (int i = 0; i < nc; ++i)
         EVE_CUDA(cudaMemcpyAsync(n.cell[i].h0, h0n + (size_t)i * B * E, (size_t)B * E * sizeof(float),
                                  cudaMemcpyDeviceToDevice, s));
+      const bool persistent = gru && cgru_seq_supported(nf, kLevelH[4], kLevelW[4]) &&
+                              (size_t)N * P * 2 * nf * sizeof(float) <= n.max_act * sizeof(uint16_t);
+      if (persistent) {
+        // ---- persistent ConvGRU (conv_tc.cu: cgru_seq_fwd_kernel), cell by cell: the x halves of
+        // both gate convolutions for all T steps at once, then ONE kernel walks the recurrence.
+        // Scratch: the block pipelines' operand-plane buffers are idle during the bottleneck.
+        float* gx1 = reinterpret_cast<float*>(PA.hi);           // [T*B][P][2nf]
+        float* gx2 = reinterpret_cast<float*>(PA.lo);           // [T*B][P][nf]
+        const size_t w1s = (size_t)2 * nf * nf * 9, w2s = (size_t)nf * nf * 9;
+        float* W1x = reinterpret_cast<float*>(PB.hi);
+        float* W1h = W1x + w1s;
+        float* W2h = W1h + w1s;
+        float* W2x = W2h + w2s;
+        uint16_t* p1h = PB.lo;                                   // K-major fp16 planes of W1h, W2h
+        uint16_t* p1l = p1h + w1s;
+        uint16_t* p2h = p1l + w1s;
+        uint16_t* p2l = p2h + w2s;
+        EVE_REQUIRE((2 * w1s + 2 * w2s) * sizeof(float) <= n.max_act * sizeof(uint16_t), EVE_ERR_WORKSPACE,
+                    "refinenet_fwd: operand-plane scratch too small for the ConvGRU weights");
+        const ConvGeom gx1g = make_conv(N, kLevelH[4], kLevelW[4], nf, 2 * nf, 3, 1, 1);
+        const ConvGeom gx2g = make_conv(N, kLevelH[4], kLevelW[4], nf, nf, 3, 1, 1);
+        for (int i = 0; i < nc; ++i) {
+          CellTape& c = n.cell[i];
+          const float* const* cw = w + n.slot_rnn + wpc * i;
+          const float* xseq = i == 0 ? n.bx : n.cell[i - 1].h;   // [T][B][P][nf], time-major
+          LAUNCH1D(slice_cin_kernel, (long long)w1s, cw[0], 2 * nf, 2 * nf, 0, nf, W1x);
+          LAUNCH1D(slice_cin_kernel, (long long)w1s, cw[0], 2 * nf, 2 * nf, nf, nf, W1h);
+          LAUNCH1D(slice_cin_kernel, (long long)w2s, cw[2], nf, 2 * nf, 0, nf, W2h);
+          LAUNCH1D(slice_cin_kernel, (long long)w2s, cw[2], nf, 2 * nf, nf, nf, W2x);
+          EVE_TRY(conv_fwd(gx1g, xseq, W1x, cw[1], nullptr, gx1, cs, s));
+          EVE_TRY(conv_fwd(gx2g, xseq, W2x, cw[3], nullptr, gx2, cs, s));
+          // x halves of the two concatenated inputs the weight gradients read (xh = [x, h], cat2 = [r*h, x])
+          EVE_TRY(copy_channels(xseq, (long long)N * P, nf, nf, 0, c.xh, 2 * nf, 0, false, s));
+          EVE_TRY(copy_channels(xseq, (long long)N * P, nf, nf, 0, c.cat2, 2 * nf, nf, false, s));
+          EVE_TRY(conv_tc_prep_weights(gx1g, W1h, false, p1h, p1l, TC_F16, 64.f, s));
+          EVE_TRY(conv_tc_prep_weights(gx2g, W2h, false, p2h, p2l, TC_F16, 64.f, s));
+          EVE_TRY(cgru_seq_fwd(B, T, p1h, p1l, p2h, p2l, gx1, gx2, c.h0, c.r, c.z, c.n, c.h, c.xh,
+                               c.cat2, 1.f / 64.f, s));
+        }
+        EVE_CUDA(cudaMemcpyAsync(n.by, n.cell[nc - 1].h, (size_t)N * E * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
+      }
       // the gate weights do not change over the T steps: lay them out for the tensor cores once
       size_t top_used = 0;
-      for (int i = 0; i < nc; ++i) {
+      for (int i = 0; i < nc && !persistent; ++i) {
         const float* const* cw = w + n.slot_rnn + wpc * i;
         EVE_TRY(conv_prepare_weights(g1, cw[0], false, cs, &top_used, s));
         if (gru) EVE_TRY(conv_prepare_weights(g2, cw[2], false, cs, &top_used, s));
       }
-      for (int t = 0; t < T; ++t) {
+      for (int t = 0; t < T && !persistent; ++t) {
         const float* xt = n.bx + (size_t)t * B * E;
         for (int i = 0; i < nc; ++i) {
           CellTape& c = n.cell[i];

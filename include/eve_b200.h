@@ -95,6 +95,10 @@ int eve_get_conv_mode(void);
  *                                nine taps taken as descriptor shifts, weight tiles shared by all
  *                                tiles of the strip): 0 off, 1 where its plan wastes at most a
  *                                seventh more MMA rows than the per-tap box kernel, 2 wherever it fits
+ *   "cgru_persistent"     0/1    ConvGRU bottleneck (64 features, 5x8 maps) as ONE persistent kernel
+ *                                per sequence (x halves of the gate convolutions batched over
+ *                                time, recurrence in shared memory / TMEM); 0 = one convolution
+ *                                launch pair per time step
  * Unknown names / out-of-range values return EVE_ERR_CONFIG. */
 int eve_set_option(const char* name, int value);
 int eve_get_option(const char* name, int* value);

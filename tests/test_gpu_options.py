@@ -12,7 +12,7 @@ from eve_b200 import lib as L            # noqa: E402
 from tests import gpu_util as G          # noqa: E402
 
 OPTIONS = ('tc_stage_cap', 'tc_row_kernel', 'tc_row_strips', 'tc_row_wgrad', 'tc_wgrad_waves',
-           'fused_planes', 'fused_norm', 'tc_strip')
+           'fused_planes', 'fused_norm', 'tc_strip', 'cgru_persistent')
 
 
 @pytest.fixture()
@@ -137,6 +137,7 @@ def _eve_step(cfg, seed=5, B=2, T=3):
 
 VARIANTS = [
     dict(tc_strip=2),
+    dict(cgru_persistent=0),
     dict(tc_strip=0),
     dict(fused_norm=0),
     dict(fused_norm=0, fused_planes=0),
@@ -165,10 +166,11 @@ def test_option_variants_agree_on_a_full_training_step(variant, cfg, options):
     assert grads.keys() == base_grads.keys()
     # variants that swap the InstanceNorm kernels compute the statistics in a different order
     # (two-pass cluster reduction vs shifted single pass); RefineNet at random weights amplifies
-    # that 1e-7 difference to ~1e-2 on the last gradients of the chain (initial.0), the same
+    # that 1e-7 difference to 1e-2 .. 2e-2 on the last gradients of the chain (initial.0), the same
     # amplification the fp32 reference shows against fp64 (test_gpu_models.py)
     # (the strip kernel likewise sums the taps of a K chunk in a different order)
-    gtol = 2e-2 if ('fused_norm' in variant or 'fused_planes' in variant or 'tc_strip' in variant) \
+    gtol = 3e-2 if ('fused_norm' in variant or 'fused_planes' in variant or 'tc_strip' in variant
+                    or 'cgru_persistent' in variant) \
         else 2e-3
     # biases in front of an InstanceNorm have an exactly zero gradient (the norm removes the
     # mean): what is computed there is cancellation noise ~1e-6 of the real gradients
