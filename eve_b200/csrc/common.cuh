@@ -142,6 +142,10 @@ int cgru_seq_fwd(int B, int T, const void* w1h_hi, const void* w1h_lo, const voi
                  const void* w2h_lo, const float* gx1, const float* gx2, const float* h0, float* r,
                  float* z, float* n, float* h, float* xh, float* cat2, float out_scale,
                  cudaStream_t s);
+int cgru_seq_bwd(int B, int T, const void* wd2_hi, const void* wd2_lo, const void* wd1_hi,
+                 const void* wd1_lo, const float* dout, float* dcarry, const float* r, const float* z,
+                 const float* n, const float* h, const float* h0, float* dg1, float* dg2,
+                 cudaStream_t s);
 bool conv_tc_dgrad_s2_supported(const ConvGeom& g);
 int conv_tc_dgrad_s2_run(const ConvGeom& g, const void* d_hi, const void* d_lo, const void* w_hi,
                          const void* w_lo, const float* addend, float* dx, int npass,

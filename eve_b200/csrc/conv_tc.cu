@@ -1144,27 +1144,35 @@ cgru_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_co
       float v[kCgPos];
       tmem_ld32(tlane, v);
       tmem_ld16(tlane + 32u, v + 32);
+      // critical path first: the values the next convolution needs go to shared memory and the
+      // MMA warp is released; the tape stores to global memory follow while it is already issuing
 #pragma unroll
       for (int j = 0; j < kCgPos; ++j) {
         if (j % kCgWp < kCgW) {
           const int pix = (j / kCgWp) * kCgW + j % kCgWp;
           const float s = 1.f / (1.f + expf(-(v[j] * p.out_scale + gx[pix])));
-          const size_t o = (frame * kCgPix + pix) * kCgNf + c;
-          if (is_r) {
-            p.r[o] = s;
-            const float rh = s * h[pix];
-            p.cat2[(frame * kCgPix + pix) * (2 * kCgNf) + c] = rh;
-            cg_store_act(act2, j + kCgWp + 1, c, rh);
-          } else {
-            p.z[o] = s;
-            zbuf[pix * kCgNf + c] = s;
-          }
+          v[j] = s;
+          if (is_r) cg_store_act(act2, j + kCgWp + 1, c, s * h[pix]);
+          else zbuf[pix * kCgNf + c] = s;
         }
       }
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&act_ready[1]);
       asm volatile("bar.sync 1, 128;" ::: "memory");      // z (threads 64..127) -> zbuf -> threads 0..63
+#pragma unroll
+      for (int j = 0; j < kCgPos; ++j) {
+        if (j % kCgWp < kCgW) {
+          const int pix = (j / kCgWp) * kCgW + j % kCgWp;
+          const size_t o = (frame * kCgPix + pix) * kCgNf + c;
+          if (is_r) {
+            p.r[o] = v[j];
+            p.cat2[(frame * kCgPix + pix) * (2 * kCgNf) + c] = v[j] * h[pix];
+          } else {
+            p.z[o] = v[j];
+          }
+        }
+      }
       // ---- candidate and the new state (threads 0..63)
       if (is_r) {
 #pragma unroll
@@ -1183,11 +1191,7 @@ cgru_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_co
             const float nv = tanhf(v[j] * p.out_scale + gx[pix]);
             const float zv = zbuf[pix * kCgNf + c];
             const float hn = (1.f - zv) * nv + zv * h[pix];
-            const size_t o = (frame * kCgPix + pix) * kCgNf + c;
-            p.n[o] = nv;
-            p.h[o] = hn;
-            if (t + 1 < T)
-              p.xh[(((size_t)(t + 1) * B + b) * kCgPix + pix) * (2 * kCgNf) + kCgNf + c] = hn;
+            v[j] = nv;
             h[pix] = hn;
             cg_store_act(act1, j + kCgWp + 1, c, hn);
           }
@@ -1196,6 +1200,273 @@ cgru_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_co
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&act_ready[0]);
+      if (is_r) {
+#pragma unroll
+        for (int j = 0; j < kCgPos; ++j) {
+          if (j % kCgWp < kCgW) {
+            const int pix = (j / kCgWp) * kCgW + j % kCgWp;
+            const size_t o = (frame * kCgPix + pix) * kCgNf + c;
+            p.n[o] = v[j];
+            p.h[o] = h[pix];
+            if (t + 1 < T)
+              p.xh[(((size_t)(t + 1) * B + b) * kCgPix + pix) * (2 * kCgNf) + kCgNf + c] = h[pix];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// ---- backward through time of the same cell (BPTT), again one CTA per clip.  Per step t (T-1..0):
+//     d    = dL/dh_t (from the decoder) + carry
+//     dg2  = d (1 - z)(1 - n^2)        dz' = d (h_{t-1} - n) z (1 - z)        carry' = d z
+//     drh  = dgrad(conv2 | r*h half)(dg2)      dr' = drh h_{t-1} r (1 - r)     carry' += drh r
+//     carry' += dgrad(conv1 | h half)([dr', dz'])
+// Only the h halves of the two data gradients sit in the recurrence; the x halves (the gradient
+// handed to the encoder) and both weight gradients are evaluated afterwards, batched over all T
+// steps, from the dg1 / dg2 sequences this kernel stores.  D^T[in channel][position] =
+// Wd[in channel][(tap, out channel)] . dg[position + tap][out channel]: the flipped, transposed
+// filters are the M operand (64 real rows), the gate gradients -- written by the epilogue threads
+// as bf16 hi/lo operand planes of a zero-padded 7x10 strip -- the N operand.
+struct CgruSeqBwdParams {
+  int B, T;
+  const float* dout;                   // [T][B][40][64]
+  float* dcarry;                       // [B][40][64]: in dL/dh_T, out dL/dh_0
+  const float *r, *z, *n, *h, *h0;     // forward tape
+  float* dg1;                          // [T][B][40][128] = [dr', dz']
+  float* dg2;                          // [T][B][40][64]
+};
+
+constexpr int kCgBStage = 2 * 64 * kCgNf * 2;          // [hi | lo] x 64 in channels x 64 (tap, co) columns
+constexpr int kCgBStages = 8;
+// one extra half stage behind the ring: the M = 128 read of the last stage's lo plane runs 8 KB past it
+constexpr int kCgBSmem = kCgBStages * kCgBStage + kCgBStage + 6 * kCgActPlane + 1024 + 512;
+
+__device__ __forceinline__ void cg_store_grad(uint8_t* plane_hi, int p, int c, float v) {
+  const __nv_bfloat16 hh = __float2bfloat16_rn(v);
+  const __nv_bfloat16 ll = __float2bfloat16_rn(v - __bfloat162float(hh));
+  const uint32_t off = (uint32_t)p * 128u + ((((uint32_t)c >> 3) ^ ((uint32_t)p & 7u)) << 4) +
+                       ((uint32_t)c & 7u) * 2u;
+  *reinterpret_cast<__nv_bfloat16*>(plane_hi + off) = hh;
+  *reinterpret_cast<__nv_bfloat16*>(plane_hi + kCgActPlane + off) = ll;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+cgru_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW2_hi, const __grid_constant__ CUtensorMap tmW2_lo,
+                    const __grid_constant__ CUtensorMap tmW1_hi, const __grid_constant__ CUtensorMap tmW1_lo,
+                    const CgruSeqBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* ring = smem;                                          // [stages][hi 8 KB | lo 8 KB] (+ pad)
+  uint8_t* g2p = ring + (kCgBStages + 1) * kCgBStage;            // dg2 planes  [hi | lo][88 rows]
+  uint8_t* g1p = g2p + 2 * kCgActPlane;                          // dg1 planes  [chunk][hi | lo][88 rows]
+  uint64_t* full = reinterpret_cast<uint64_t*>(g1p + 4 * kCgActPlane);
+  uint64_t* empty = full + kCgBStages;
+  uint64_t* d_full = empty + kCgBStages;     // [2]
+  uint64_t* act_ready = d_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const int B = p.B, T = p.T;
+
+  if (warp == 0 && lane == 0) {
+    tmap_prefetch(&tmW1_hi);
+    tmap_prefetch(&tmW1_lo);
+    tmap_prefetch(&tmW2_hi);
+    tmap_prefetch(&tmW2_lo);
+    for (int i = 0; i < kCgBStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d_full[i], 1);
+      mbar_init(&act_ready[i], 128);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 6 * kCgActPlane / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(g2p)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // the half stage behind the ring is only ever read into junk accumulator rows: keep it finite
+  for (int i = threadIdx.x; i < kCgBStage / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(ring + kCgBStages * kCgBStage)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== filter producer: 9 + 18 tiles per step =====================
+    if (elect_one()) {
+      constexpr uint32_t tx = 2u * 64u * kCgNf * 2u;
+      uint32_t g = 0;
+      for (int t = 0; t < T; ++t) {
+        for (int conv = 0; conv < 2; ++conv) {
+          const CUtensorMap* mh = conv == 0 ? &tmW2_hi : &tmW1_hi;
+          const CUtensorMap* ml = conv == 0 ? &tmW2_lo : &tmW1_lo;
+          const int tiles = conv == 0 ? 9 : 18;          // (tap, 64-wide out-channel chunk)
+          for (int i = 0; i < tiles; ++i, ++g) {
+            const uint32_t s = g % kCgBStages;
+            mbar_wait(&empty[s], ((g / kCgBStages) & 1) ^ 1);
+            uint8_t* dst = ring + (size_t)s * kCgBStage;
+            mbar_expect_tx(&full[s], tx);
+            tma_load_2d(dst, mh, &full[s], i * kCgNf, 0);
+            tma_load_2d(dst + kCgBStage / 2, ml, &full[s], i * kCgNf, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // D fp32, A = flipped filters (bf16, K-major, M = 128 with 64 real rows), B = gate gradients (bf16)
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kCgPos >> 3) << 17) |
+                               ((uint32_t)(kTileM >> 4) << 24);
+    const uint64_t desc0 = kmajor_desc(0u, 64);
+    const uint32_t ring16 = smem_u32(ring) >> 4;
+    const uint32_t g2_16 = smem_u32(g2p) >> 4, g1_16 = smem_u32(g1p) >> 4;
+    constexpr uint32_t kLo16W = (uint32_t)(kCgBStage / 2) >> 4;
+    constexpr uint32_t kLo16A = (uint32_t)kCgActPlane >> 4;
+    uint32_t g = 0;
+    for (int t = 0; t < T; ++t) {
+      for (int conv = 0; conv < 2; ++conv) {
+        mbar_wait(&act_ready[conv], (uint32_t)t & 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(conv * 64);
+        const int tiles = conv == 0 ? 9 : 18;
+#pragma unroll 1
+        for (int i = 0; i < tiles; ++i, ++g) {
+          const uint32_t s = g % kCgBStages;
+          mbar_wait(&full[s], (g / kCgBStages) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const int tap = conv == 0 ? i : (i >> 1);
+            const int chunk = conv == 0 ? 0 : (i & 1);
+            const int rr = tap / 3, qq = tap - 3 * rr;
+            const uint64_t w_hi = desc0 + (uint64_t)(ring16 + s * ((uint32_t)kCgBStage >> 4));
+            const uint32_t planes16 = conv == 0 ? g2_16 : g1_16 + (uint32_t)chunk * 2u * kLo16A;
+            const uint64_t a_hi = desc0 + (uint64_t)(planes16 + (uint32_t)(rr * kCgWp + qq) * 8u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t dw_hi = w_hi + (uint64_t)(k * 2), dw_lo = dw_hi + kLo16W;
+              const uint64_t da_hi = a_hi + (uint64_t)(k * 2), da_lo = da_hi + kLo16A;
+              umma_bf16(tmem_d, dw_lo, da_hi, idesc, (i | k) != 0);
+              umma_bf16(tmem_d, dw_hi, da_lo, idesc, 1);
+              umma_bf16(tmem_d, dw_hi, da_hi, idesc, 1);
+            }
+            umma_commit(&empty[s]);
+            if (i == tiles - 1) umma_commit(&d_full[conv]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================== gate gradients (TMEM lane = input channel; lanes 0..63 are real) =====================
+    const int quad = warp & 3;
+    const int c = quad * 32 + lane;
+    const bool live = c < kCgNf;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float dc[kCgPix];
+    if (live) {
+#pragma unroll
+      for (int pix = 0; pix < kCgPix; ++pix) dc[pix] = p.dcarry[((size_t)b * kCgPix + pix) * kCgNf + c];
+    }
+    for (int step = 0; step < T; ++step) {
+      const int t = T - 1 - step;
+      const size_t frame = (size_t)t * B + b;
+      const float* hprev = t == 0 ? p.h0 + (size_t)b * kCgPix * kCgNf
+                                  : p.h + ((size_t)(t - 1) * B + b) * kCgPix * kCgNf;
+      float v[kCgPos];
+      // ---- dg2, dz', direct carry
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < kCgPos; ++j) {
+          if (j % kCgWp < kCgW) {
+            const int pix = (j / kCgWp) * kCgW + j % kCgWp;
+            const size_t o = (frame * kCgPix + pix) * kCgNf + c;
+            const float d = __ldg(p.dout + o) + dc[pix];
+            const float zv = __ldg(p.z + o), nv = __ldg(p.n + o);
+            const float hp = __ldg(hprev + (size_t)pix * kCgNf + c);
+            const float g2 = d * (1.f - zv) * (1.f - nv * nv);
+            const float dz = d * (hp - nv) * zv * (1.f - zv);
+            dc[pix] = d * zv;
+            v[j] = dz;
+            cg_store_grad(g2p, j + kCgWp + 1, c, g2);
+            cg_store_grad(g1p + 2 * kCgActPlane, j + kCgWp + 1, c, dz);       // chunk 1 = dz'
+            p.dg2[o] = g2;
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&act_ready[0]);
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < kCgPos; ++j) {
+          if (j % kCgWp < kCgW) {
+            const int pix = (j / kCgWp) * kCgW + j % kCgWp;
+            p.dg1[(frame * kCgPix + pix) * (2 * kCgNf) + kCgNf + c] = v[j];
+          }
+        }
+      }
+      // ---- d(r*h) -> dr', carry += d(r*h) r
+      mbar_wait(&d_full[0], (uint32_t)step & 1);
+      tc_fence_after();
+      if (live) {
+        tmem_ld32(tlane, v);
+        tmem_ld16(tlane + 32u, v + 32);
+#pragma unroll
+        for (int j = 0; j < kCgPos; ++j) {
+          if (j % kCgWp < kCgW) {
+            const int pix = (j / kCgWp) * kCgW + j % kCgWp;
+            const size_t o = (frame * kCgPix + pix) * kCgNf + c;
+            const float rv = __ldg(p.r + o);
+            const float hp = __ldg(hprev + (size_t)pix * kCgNf + c);
+            const float dr = v[j] * hp * rv * (1.f - rv);
+            dc[pix] += v[j] * rv;
+            v[j] = dr;
+            cg_store_grad(g1p, j + kCgWp + 1, c, dr);                           // chunk 0 = dr'
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&act_ready[1]);
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < kCgPos; ++j) {
+          if (j % kCgWp < kCgW) {
+            const int pix = (j / kCgWp) * kCgW + j % kCgWp;
+            p.dg1[(frame * kCgPix + pix) * (2 * kCgNf) + c] = v[j];
+          }
+        }
+      }
+      // ---- carry += dgrad(conv1 | h half)
+      mbar_wait(&d_full[1], (uint32_t)step & 1);
+      tc_fence_after();
+      if (live) {
+        tmem_ld32(tlane + 64u, v);
+        tmem_ld16(tlane + 96u, v + 32);
+#pragma unroll
+        for (int j = 0; j < kCgPos; ++j) {
+          if (j % kCgWp < kCgW) dc[(j / kCgWp) * kCgW + j % kCgWp] += v[j];
+        }
+      }
+      tc_fence_before();
+    }
+    if (live) {
+#pragma unroll
+      for (int pix = 0; pix < kCgPix; ++pix) p.dcarry[((size_t)b * kCgPix + pix) * kCgNf + c] = dc[pix];
     }
   }
   tc_fence_before();
@@ -2265,6 +2536,29 @@ int cgru_seq_fwd(int B, int T, const void* w1h_hi, const void* w1h_lo, const voi
   EVE_TRY(make_map_2d(&m2l, w2h_lo, kCgNf, 9 * kCgNf, 64, kCgNf, TC_F16));
   EVE_TRY(ensure_dynamic_smem((const void*)cgru_seq_fwd_kernel, kCgSmem));
   cgru_seq_fwd_kernel<<<B, kThreads, kCgSmem, s>>>(m1h, m1l, m2h, m2l, p);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+// wd2_*: bf16 hi/lo planes [64][9 * 64] of the data-gradient layout of gate_2.weight[:, 0:nf],
+// wd1_*: [64][9 * 128] of gates_1.weight[:, nf:2nf] (conv_tc_prep_weights(dgrad = true))
+int cgru_seq_bwd(int B, int T, const void* wd2_hi, const void* wd2_lo, const void* wd1_hi,
+                 const void* wd1_lo, const float* dout, float* dcarry, const float* r, const float* z,
+                 const float* n, const float* h, const float* h0, float* dg1, float* dg2,
+                 cudaStream_t s) {
+  EVE_REQUIRE(B > 0 && T > 0, EVE_ERR_SHAPE, "cgru_seq_bwd: B=%d T=%d", B, T);
+  CgruSeqBwdParams p;
+  p.B = B; p.T = T;
+  p.dout = dout; p.dcarry = dcarry;
+  p.r = r; p.z = z; p.n = n; p.h = h; p.h0 = h0;
+  p.dg1 = dg1; p.dg2 = dg2;
+  CUtensorMap m2h, m2l, m1h, m1l;
+  EVE_TRY(make_map_2d(&m2h, wd2_hi, kCgNf, 9 * kCgNf, 64, kCgNf, TC_BF16));
+  EVE_TRY(make_map_2d(&m2l, wd2_lo, kCgNf, 9 * kCgNf, 64, kCgNf, TC_BF16));
+  EVE_TRY(make_map_2d(&m1h, wd1_hi, kCgNf, 9 * 2 * kCgNf, 64, kCgNf, TC_BF16));
+  EVE_TRY(make_map_2d(&m1l, wd1_lo, kCgNf, 9 * 2 * kCgNf, 64, kCgNf, TC_BF16));
+  EVE_TRY(ensure_dynamic_smem((const void*)cgru_seq_bwd_kernel, kCgBSmem));
+  cgru_seq_bwd_kernel<<<B, kThreads, kCgBSmem, s>>>(m2h, m2l, m1h, m1l, p);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }

@@ -1119,13 +1119,55 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
     float* dxh = ex.cb[3];
     float* dxa = ex.cb[4];
     float* dxb = ex.cb[5];
+    const bool persistent = gru && cgru_seq_supported(nf, kLevelH[4], kLevelW[4]) &&
+                            (size_t)N * E * sizeof(float) <= n.max_act * sizeof(uint16_t);
+    if (persistent) {
+      // ---- persistent BPTT (conv_tc.cu: cgru_seq_bwd_kernel), top cell first: ONE kernel walks the
+      // recurrence and stores the gate-gradient sequences; the x halves of the data gradients (what
+      // the cell below / the encoder receives) follow as two convolutions batched over all T steps.
+      // Scratch: the fused block pipeline's plane buffers are idle between decoder and encoder.
+      const size_t w1s = (size_t)2 * nf * nf * 9, w2s = (size_t)nf * nf * 9;
+      EVE_REQUIRE((2 * w1s + 2 * w2s) * sizeof(float) <= n.max_act * sizeof(uint16_t), EVE_ERR_WORKSPACE,
+                  "refinenet_bwd: operand-plane scratch too small for the ConvGRU weights");
+      float* W1x = reinterpret_cast<float*>(fb.XP.hi);
+      float* W1h = W1x + w1s;
+      float* W2h = W1h + w1s;
+      float* W2x = W2h + w2s;
+      uint16_t* d1h = fb.XP.lo;                // data-gradient planes of W1h [nf][9 * 2nf], W2h [nf][9 * nf]
+      uint16_t* d1l = d1h + w1s;
+      uint16_t* d2h = d1l + w1s;
+      uint16_t* d2l = d2h + w2s;
+      float* dxa = reinterpret_cast<float*>(fb.XP2.hi);      // [T][B][P][nf] sequences
+      float* dxb = reinterpret_cast<float*>(fb.XP2.lo);
+      const ConvGeom gx1g = make_conv(N, kLevelH[4], kLevelW[4], nf, 2 * nf, 3, 1, 1);
+      const ConvGeom gx2g = make_conv(N, kLevelH[4], kLevelW[4], nf, nf, 3, 1, 1);
+      const float* dcur = ex.dby;
+      for (int i = nc - 1; i >= 0; --i) {
+        const CellTape& c = n.cell[i];
+        const float* const* cw = w + n.slot_rnn + wpc * i;
+        LAUNCH1D(slice_cin_kernel, (long long)w1s, cw[0], 2 * nf, 2 * nf, 0, nf, W1x);
+        LAUNCH1D(slice_cin_kernel, (long long)w1s, cw[0], 2 * nf, 2 * nf, nf, nf, W1h);
+        LAUNCH1D(slice_cin_kernel, (long long)w2s, cw[2], nf, 2 * nf, 0, nf, W2h);
+        LAUNCH1D(slice_cin_kernel, (long long)w2s, cw[2], nf, 2 * nf, nf, nf, W2x);
+        EVE_TRY(conv_tc_prep_weights(gx1g, W1h, true, d1h, d1l, TC_BF16, 1.f, s));
+        EVE_TRY(conv_tc_prep_weights(gx2g, W2h, true, d2h, d2l, TC_BF16, 1.f, s));
+        EVE_TRY(cgru_seq_bwd(B, T, d2h, d2l, d1h, d1l, dcur, ex.dcarry[i], c.r, c.z, c.n, c.h, c.h0,
+                             ex.dg1all[i], ex.dg2all[i], s));
+        float* dxo = (i == 0) ? ex.dbx : (dcur == dxa ? dxb : dxa);
+        float* tmp = (dxo == dxa || dcur == dxa) ? dxb : dxa;
+        if (tmp == dxo || tmp == dcur) tmp = ex.dbx;          // (i > 0 with both sequences busy)
+        EVE_TRY(conv_dgrad(gx1g, ex.dg1all[i], W1x, nullptr, tmp, sc.cs, s));
+        EVE_TRY(conv_dgrad(gx2g, ex.dg2all[i], W2x, tmp, dxo, sc.cs, s));
+        dcur = dxo;
+      }
+    }
     size_t top_used = 0;
-    for (int i = 0; i < nc; ++i) {
+    for (int i = 0; i < nc && !persistent; ++i) {
       const float* const* cw = w + n.slot_rnn + wpc * i;
       EVE_TRY(conv_prepare_weights(g1, cw[0], true, sc.cs, &top_used, s));
       if (gru) EVE_TRY(conv_prepare_weights(g2, cw[2], true, sc.cs, &top_used, s));
     }
-    for (int t = T - 1; t >= 0; --t) {
+    for (int t = T - 1; t >= 0 && !persistent; --t) {
       const float* dcur = ex.dby + (size_t)t * B * E;
       for (int i = nc - 1; i >= 0; --i) {
         const CellTape& c = n.cell[i];

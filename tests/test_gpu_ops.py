@@ -134,6 +134,11 @@ def test_layout_round_trip():
     L.check(lib.eve_nhwc_to_nchw(L.ptr(y), 3, 5, 7, 9, L.ptr(z), L.stream_ptr()), 'b')
     assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
     assert torch.equal(z, x)
+    # three-channel images take the plane-interleaving kernel
+    x = torch.randn(5, 3, 12, 20).cuda()
+    y = torch.empty(5, 12, 20, 3, device='cuda')
+    L.check(lib.eve_nchw_to_nhwc(L.ptr(x), 5, 3, 12, 20, L.ptr(y), L.stream_ptr()), 'c')
+    assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
 
 
 def test_adam_clip_matches_torch():

@@ -174,7 +174,10 @@ def test_option_variants_agree_on_a_full_training_step(variant, cfg, options):
         else 2e-3
     # biases in front of an InstanceNorm have an exactly zero gradient (the norm removes the
     # mean): what is computed there is cancellation noise ~1e-6 of the real gradients
-    floor = 1e-6 * max(float(v.double().norm()) for v in base_grads.values())
+    # (1e-6 of the largest gradient norm; 1e-4 for the variants that reorder sums, whose amplified
+    # differences reach a few percent of the SMALL gradients' own norms: affine terms of the first
+    # RefineNet blocks sit 1000x below the EyeNet stem's gradient)
+    floor = (1e-4 if gtol > 2e-3 else 1e-6) * max(float(v.double().norm()) for v in base_grads.values())
     for k in grads:
         a, b = grads[k].double(), base_grads[k].double()
         den = float(b.norm())
