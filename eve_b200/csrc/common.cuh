@@ -224,6 +224,17 @@ int conv_bwd_planes(const ConvGeom& g, const void* x_hi, const void* x_lo, const
 int conv_prepare_weights(const ConvGeom& g, const float* w_oihw, bool dgrad, const ConvScratch& sc,
                          size_t* top_used, cudaStream_t s);
 void conv_prepared_clear();
+int conv_prepared_mark();
+void conv_prepared_truncate(int mark);
+// All tensor-core weight layouts of a network pass from one launch (forward layouts, or the
+// flipped data-gradient layouts); `region` must stay untouched until conv_prepared_clear().
+struct ConvPrepReq {
+  ConvGeom g;
+  const float* w;
+};
+size_t conv_prepare_batch_bytes(const ConvPrepReq* reqs, int n);
+int conv_prepare_batch(const ConvPrepReq* reqs, int n, bool dgrad, void* region, size_t bytes,
+                       cudaStream_t s);
 // both gradients of one convolution (dw/dbias and dx, each optional) from one split of dy
 int conv_bwd(const ConvGeom& g, const float* x, const float* dy, const float* w_oihw, float* dw,
              float* dbias, bool accumulate, const float* addend, float* dx, const ConvScratch& sc,
@@ -310,8 +321,9 @@ int avgpool_bwd(const float* dy, int N, int HW, int C, float* dx, cudaStream_t s
 // torch AdaptiveMaxPool2d semantics: window [floor(i*L/O), ceil((i+1)*L/O))
 int adaptive_maxpool_fwd(const float* x, int N, int H, int W, int C, int OH, int OW, float* y,
                          int32_t* idx, cudaStream_t s);
+// dx = scatter(dy) (+ addend, dx's layout: the skip-connection gradient)
 int adaptive_maxpool_bwd(const float* dy, const int32_t* idx, int N, int H, int W, int C, int OH,
-                         int OW, float* dx, cudaStream_t s);
+                         int OW, float* dx, cudaStream_t s, const float* addend = nullptr);
 // bilinear (align_corners=False) upsample of x[N,H,W,C] to [OH,OW], written into
 // y[N,OH,OW,ldy] at channel offset coff (the concat of refine_net.py:123-126)
 int upsample_bilinear_fwd(const float* x, int N, int H, int W, int C, int OH, int OW, float* y,

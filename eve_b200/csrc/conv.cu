@@ -186,7 +186,8 @@ struct PreparedW {
   int dgrad, npass;
   const uint16_t *hi, *lo;
 };
-static thread_local PreparedW g_prepared[8];
+constexpr int kMaxPrepared = 192;
+static thread_local PreparedW g_prepared[kMaxPrepared];
 static thread_local int g_nprepared = 0;
 
 static const PreparedW* find_prepared(const float* w, bool dgrad, int npass) {
@@ -338,7 +339,12 @@ int conv_dgrad(const ConvGeom& g, const float* dy, const float* w, const float* 
     uint16_t* d_hi = c.get<uint16_t>((size_t)g.out_elems());
     uint16_t* d_lo = c.get<uint16_t>((size_t)g.out_elems());
     EVE_REQUIRE(d_lo, EVE_ERR_WORKSPACE, "conv_dgrad: scratch too small");
-    EVE_TRY(conv_tc_prep_weights(g, w, true, w_hi, npass == 3 ? w_lo : nullptr, TC_BF16, 1.f, s));
+    if (const PreparedW* pw = find_prepared(w, true, npass)) {
+      w_hi = const_cast<uint16_t*>(pw->hi);
+      w_lo = const_cast<uint16_t*>(pw->lo);
+    } else {
+      EVE_TRY(conv_tc_prep_weights(g, w, true, w_hi, npass == 3 ? w_lo : nullptr, TC_BF16, 1.f, s));
+    }
     EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
     if (g.KH == 1) {
       // only even/even pixels receive data: the rest is the addend (or zero)
@@ -461,8 +467,14 @@ int conv_bwd(const ConvGeom& g, const float* x, const float* dy, const float* w,
   // descriptor is an illegal instruction on sm_100a), so x is split as bf16 next to dy
   EVE_TRY(split_planes(dy, g.out_elems(), b.d_hi, npass == 3 ? b.d_lo : nullptr, TC_BF16, s));
   if (x) EVE_TRY(split_planes(x, g.in_elems(), b.x_hi, npass == 3 ? b.x_lo : nullptr, TC_BF16, s));
-  if (dx)
-    EVE_TRY(conv_tc_prep_weights(g, w, true, b.w_hi, npass == 3 ? b.w_lo : nullptr, TC_BF16, 1.f, s));
+  if (dx) {
+    if (const PreparedW* pw = find_prepared(w, true, npass)) {
+      b.w_hi = const_cast<uint16_t*>(pw->hi);
+      b.w_lo = const_cast<uint16_t*>(pw->lo);
+    } else {
+      EVE_TRY(conv_tc_prep_weights(g, w, true, b.w_hi, npass == 3 ? b.w_lo : nullptr, TC_BF16, 1.f, s));
+    }
+  }
   const double flops = 2.0 * g.out_elems() * (double)g.K();
   const double bytes = 4.0 * (g.in_elems() + g.out_elems() + (double)wel);
   {
@@ -538,7 +550,7 @@ int conv_bwd_planes(const ConvGeom& g, const void* x_hi, const void* x_lo, const
   }
   if (!dx) return EVE_OK;
   const bool s1 = bwd_dgrad_s1(g);
-  if (const PreparedW* pw = s1 ? find_prepared(w, true, 3) : nullptr) {
+  if (const PreparedW* pw = find_prepared(w, true, 3)) {      // same layout for stride 1 and 2
     w_hi = const_cast<uint16_t*>(pw->hi);
     w_lo = const_cast<uint16_t*>(pw->lo);
   } else {
@@ -562,6 +574,10 @@ int conv_bwd_planes(const ConvGeom& g, const void* x_hi, const void* x_lo, const
 }
 
 void conv_prepared_clear() { g_nprepared = 0; }
+int conv_prepared_mark() { return g_nprepared; }
+void conv_prepared_truncate(int mark) {
+  if (mark >= 0 && mark < g_nprepared) g_nprepared = mark;
+}
 
 // Prepare the weights of `g` for repeated conv_fwd (dgrad = false) or stride-1 conv_dgrad
 // (dgrad = true) calls.  Storage is taken from the top of the scratch slice, below `*top_used`
@@ -571,7 +587,7 @@ void conv_prepared_clear() { g_nprepared = 0; }
 int conv_prepare_weights(const ConvGeom& g, const float* w, bool dgrad, const ConvScratch& sc,
                          size_t* top_used, cudaStream_t s) {
   const int mode = conv_mode();
-  if (mode == 0 || g_nprepared >= 8) return EVE_OK;
+  if (mode == 0 || g_nprepared >= kMaxPrepared) return EVE_OK;
   const int npass = mode == 1 ? 3 : 1;
   if (!dgrad && !((tc_mask() & 1) && conv_tc_supported(g))) return EVE_OK;
   if (dgrad && !((tc_mask() & 2) && g.stride == 1 && conv_tc_supported(dgrad_as_fwd(g)))) return EVE_OK;
@@ -590,6 +606,113 @@ int conv_prepare_weights(const ConvGeom& g, const float* w, bool dgrad, const Co
   EVE_TRY(conv_tc_prep_weights(g, w, dgrad, hi, npass == 3 ? lo : nullptr, fmt, wscale, s));
   g_prepared[g_nprepared++] = PreparedW{w, dgrad ? 1 : 0, npass, hi, lo};
   return EVE_OK;
+}
+
+// ---- batched weight preparation: the tensor-core layouts of ALL convolutions of a network pass
+// from ONE launch (they only change at the optimizer step; preparing them per call cost ~125 tiny
+// launches per training step).  Entries are registered like conv_prepare_weights() does.
+namespace {
+struct PrepEntry {
+  const float* w;
+  uint16_t *hi, *lo;
+  int Cout, Cin, KH, KW;
+  int flip, fmt;
+  float scale;
+  long long start, count;      // element range of this entry in the launch (start is 256-aligned)
+};
+constexpr int kPrepBatch = 56;
+struct PrepTable {
+  int n;
+  PrepEntry e[kPrepBatch];
+};
+
+__global__ void __launch_bounds__(256)
+prep_weights_batch_kernel(const PrepTable tab) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // block-uniform search (entry starts are multiples of the block size)
+  int k = 0;
+  while (k + 1 < tab.n && tab.e[k + 1].start <= (long long)blockIdx.x * blockDim.x) ++k;
+  const PrepEntry& e = tab.e[k];
+  const long long o = i - e.start;      // OUTPUT element: consecutive threads write consecutive bytes
+  if (o >= e.count) return;
+  const int taps = e.KH * e.KW;
+  int co, ci, tap;
+  if (!e.flip) {                         // [co][tap][ci]
+    ci = (int)(o % e.Cin);
+    const long long t = o / e.Cin;
+    tap = (int)(t % taps);
+    co = (int)(t / taps);
+  } else {                               // [ci][flipped tap][co]
+    co = (int)(o % e.Cout);
+    const long long t = o / e.Cout;
+    tap = taps - 1 - (int)(t % taps);
+    ci = (int)(t / taps);
+  }
+  float v = __ldg(e.w + ((size_t)co * e.Cin + ci) * taps + tap) * e.scale;
+  uint16_t h, l;
+  split16(v, e.fmt, h, l);
+  e.hi[o] = h;
+  if (e.lo) e.lo[o] = l;
+}
+}  // namespace
+
+static bool prep_wanted(const ConvGeom& g, bool dgrad) {
+  const int mode = conv_mode();
+  if (mode == 0) return false;
+  if (!dgrad) return (tc_mask() & 1) && conv_tc_supported(g);
+  if (!(tc_mask() & 2)) return false;
+  return bwd_dgrad_s1(g) || conv_tc_dgrad_s2_supported(g);
+}
+
+size_t conv_prepare_batch_bytes(const ConvPrepReq* reqs, int n) {
+  size_t bytes = 0;
+  for (int i = 0; i < n; ++i)
+    bytes += 2 * align_up((size_t)reqs[i].g.Cout * reqs[i].g.K() * sizeof(uint16_t), 1024);
+  return bytes + 1024;
+}
+
+int conv_prepare_batch(const ConvPrepReq* reqs, int n, bool dgrad, void* region, size_t bytes,
+                       cudaStream_t s) {
+  const int mode = conv_mode();
+  if (mode == 0 || !region) return EVE_OK;
+  const int npass = mode == 1 ? 3 : 1;
+  char* p = (char*)align_up((size_t)region, 1024);
+  char* end = (char*)region + bytes;
+  PrepTable tab;
+  tab.n = 0;
+  long long total = 0;
+  auto flush = [&]() -> int {
+    if (tab.n == 0) return EVE_OK;
+    prep_weights_batch_kernel<<<cdiv(total, 256), 256, 0, s>>>(tab);
+    EVE_LAUNCH_CHECK();
+    tab.n = 0;
+    total = 0;
+    return EVE_OK;
+  };
+  for (int i = 0; i < n; ++i) {
+    const ConvGeom& g = reqs[i].g;
+    if (!reqs[i].w || !prep_wanted(g, dgrad) || g_nprepared >= kMaxPrepared) continue;
+    if (find_prepared(reqs[i].w, dgrad, npass)) continue;          // shared weights
+    const size_t wel = (size_t)g.Cout * g.K();
+    const size_t plane = align_up(wel * sizeof(uint16_t), 1024);
+    if (p + 2 * plane > end) break;                                  // the rest is prepared per call
+    PrepEntry e;
+    e.w = reqs[i].w;
+    e.hi = (uint16_t*)p;
+    e.lo = npass == 3 ? (uint16_t*)(p + plane) : nullptr;
+    p += 2 * plane;
+    e.Cout = g.Cout; e.Cin = g.Cin; e.KH = g.KH; e.KW = g.KW;
+    e.flip = dgrad ? 1 : 0;
+    e.fmt = (!dgrad && npass == 3) ? TC_F16 : TC_BF16;
+    e.scale = (!dgrad && npass == 3) ? 64.f : 1.f;
+    e.start = total;
+    e.count = (long long)wel;
+    total += (long long)align_up(wel, 256);
+    tab.e[tab.n++] = e;
+    g_prepared[g_nprepared++] = PreparedW{e.w, dgrad ? 1 : 0, npass, e.hi, e.lo ? e.lo : e.hi};
+    if (tab.n == kPrepBatch) EVE_TRY(flush());
+  }
+  return flush();
 }
 
 // act(IN(x)) feeding convolution `g`: either as fp32 `y` (then conv_* split it themselves) or,

@@ -4,6 +4,7 @@
 // as instantiated at eye_net.py:48-50.  The CNN runs for all patches of a step at once
 // (norms are per sample); only the RNN cell walks over time.
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -121,10 +122,28 @@ size_t cnn_conv_scratch_bytes(const CnnTape& t) {
   return conv_scratch_bytes(mi, mo, mw, mp);
 }
 
+// the sixteen 3x3 + three 1x1 block convolutions (the stem has its own patch-matrix layout)
+std::vector<ConvPrepReq> cnn_prep_list(const CnnTape& t, const float* const* w) {
+  std::vector<ConvPrepReq> v;
+  for (int i = 0; i < 8; ++i) {
+    const BlockTape& k = t.blk[i];
+    const int slot = block_slot(i);
+    v.push_back(ConvPrepReq{k.g1, w ? w[slot] : nullptr});
+    v.push_back(ConvPrepReq{k.g2, w ? w[slot + 1] : nullptr});
+    if (k.down) v.push_back(ConvPrepReq{k.gd, w ? w[slot + 2] : nullptr});
+  }
+  return v;
+}
+size_t cnn_prep_bytes(const CnnTape& t) {
+  const std::vector<ConvPrepReq> v = cnn_prep_list(t, nullptr);
+  return conv_prepare_batch_bytes(v.data(), (int)v.size());
+}
+
 size_t cnn_fwd_scratch(const CnnTape& t) {
   return align_up(cnn_conv_scratch_bytes(t), 256) +
          align_up((size_t)512 * t.nf * sizeof(float), 256) +
-         4 * align_up(t.max_act * sizeof(uint16_t), 256) + 1024;   // operand planes IN, Y
+         4 * align_up(t.max_act * sizeof(uint16_t), 256) +         // operand planes IN, Y
+         align_up(cnn_prep_bytes(t), 256) + 1024;
 }
 
 struct Planes {
@@ -173,6 +192,8 @@ struct CnnBwdScratch {
   ConvScratch cs;
   Planes XP, XI, DB, DA;   // fused pipeline: x planes (y / block input), dy planes
   float* col;
+  char* prep;              // batched weight layouts (conv_prepare_batch)
+  size_t prep_bytes;
 };
 
 bool build_cnn_bwd_scratch(const CnnTape& t, Arena& ws, CnnBwdScratch& s) {
@@ -194,6 +215,8 @@ bool build_cnn_bwd_scratch(const CnnTape& t, Arena& ws, CnnBwdScratch& s) {
   s.DB = get_planes(ws, t.max_act);
   s.DA = get_planes(ws, t.max_act);
   s.col = ws.get<float>((size_t)12 * t.N * 512);
+  s.prep_bytes = cnn_prep_bytes(t);
+  s.prep = ws.get<char>(s.prep_bytes);
   return ws.ok();
 }
 
@@ -232,6 +255,15 @@ extern "C" int eve_eyenet_cnn_fwd(const eve_eyenet_cnn_params* p, const float* x
   cs.base = ws.get<char>(cs.bytes);
   float* wfc = ws.get<float>((size_t)512 * t.nf);
   const int N = t.N;
+  conv_prepared_clear();
+  {
+    // forward tensor-core layouts of the 19 block convolutions: one launch
+    const size_t pb = cnn_prep_bytes(t);
+    char* region = ws.get<char>(pb);
+    EVE_REQUIRE(region, EVE_ERR_WORKSPACE, "eyenet_cnn_fwd: workspace too small");
+    const std::vector<ConvPrepReq> reqs = cnn_prep_list(t, w);
+    EVE_TRY(conv_prepare_batch(reqs.data(), (int)reqs.size(), false, region, pb, s));
+  }
 
   EVE_TRY(nchw_to_nhwc(x, N, 3, p->h, p->w, t.x, s));
   EVE_TRY(conv_fwd(t.stem, t.x, w[0], nullptr, nullptr, t.c1, cs, s));
@@ -286,6 +318,7 @@ extern "C" int eve_eyenet_cnn_fwd(const eve_eyenet_cnn_params* p, const float* x
   const BlockTape& last = t.blk[7];
   EVE_TRY(avgpool_fwd(last.out, N, last.g1.OH * last.g1.OW, 512, t.pooled, s));
   EVE_TRY(linear_fwd(t.pooled, N, 512, w[20], w[21], t.nf, feat, wfc, s));
+  conv_prepared_clear();
   return EVE_OK;
 }
 
@@ -308,6 +341,12 @@ extern "C" int eve_eyenet_cnn_bwd(const eve_eyenet_cnn_params* p, const float* d
               "eyenet_cnn_bwd: workspace too small (%zu < %zu)", workspace_bytes, ws.off);
   const int N = t.N;
   const bool acc = accumulate != 0;
+  conv_prepared_clear();
+  {
+    // flipped data-gradient layouts of the block convolutions: one launch
+    const std::vector<ConvPrepReq> reqs = cnn_prep_list(t, w);
+    EVE_TRY(conv_prepare_batch(reqs.data(), (int)reqs.size(), true, sc.prep, sc.prep_bytes, s));
+  }
 
   // fc
   EVE_TRY(linear_wgrad(t.pooled, dfeat, N, 512, t.nf, gr[20], gr[21], sc.wg, acc, s));
@@ -396,6 +435,7 @@ extern "C" int eve_eyenet_cnn_bwd(const eve_eyenet_cnn_params* p, const float* d
                         ACT_RELU, nullptr, sc.stem_d, nullptr, nullptr, nullptr, sc.inb, false, s));
     EVE_TRY(conv_wgrad(t.stem, t.x, sc.stem_d, gr[0], nullptr, acc, sc.cs, s));
   }
+  conv_prepared_clear();
   return EVE_OK;
 }
 

@@ -187,10 +187,54 @@ adaptive_maxpool_fwd_kernel(const float* __restrict__ x, long long total4, int H
   *reinterpret_cast<int4*>(idx + i * 4) = make_int4(bi[0], bi[1], bi[2], bi[3]);
 }
 
+// Windows that tile the input exactly (H = kh * OH, W = kw * OW: every level of GazeRefineNet but the
+// 9 -> 5 rows of the last one): one thread per OUTPUT element quad reads (dy, idx) once and writes
+// its kh x kw window -- no window search, no re-reads.  `addend` (optional, dx's layout) is the
+// gradient arriving through the skip connection (refine_net.py:123-126), fused instead of a
+// separate read-modify-write pass over dx.
+template <int KH, int KW>
+__global__ void __launch_bounds__(256)
+adaptive_maxpool_bwd_exact_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx,
+                                  long long total4, int W, int C, int OH, int OW,
+                                  const float* __restrict__ addend, float* __restrict__ dx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int C4 = C >> 2;
+  const int c = (int)(i % C4) * 4;
+  long long t = i / C4;
+  const int ox = (int)(t % OW);
+  t /= OW;
+  const int oy = (int)(t % OH);
+  const long long n = t / OH;
+  const int4 id = __ldg(reinterpret_cast<const int4*>(idx) + i);
+  const F4 d = ld4(dy + i * 4);
+  const int H = OH * KH;
+#pragma unroll
+  for (int r = 0; r < KH; ++r) {
+#pragma unroll
+    for (int q = 0; q < KW; ++q) {
+      const int h = oy * KH + r, w = ox * KW + q;
+      const int me = h * W + w;
+      const size_t o = (((size_t)n * H + h) * W + w) * C + c;
+      F4 v;
+      v.v[0] = id.x == me ? d.v[0] : 0.f;
+      v.v[1] = id.y == me ? d.v[1] : 0.f;
+      v.v[2] = id.z == me ? d.v[2] : 0.f;
+      v.v[3] = id.w == me ? d.v[3] : 0.f;
+      if (addend) {
+        const F4 a = ld4(addend + o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.v[j] += a.v[j];
+      }
+      st4(dx + o, v);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 adaptive_maxpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx,
                             long long total4, int H, int W, int C, int OH, int OW,
-                            float* __restrict__ dx) {
+                            const float* __restrict__ addend, float* __restrict__ dx) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int C4 = C >> 2;
@@ -216,6 +260,11 @@ adaptive_maxpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restr
       if (id.z == me) s[2] += d.v[2];
       if (id.w == me) s[3] += d.v[3];
     }
+  }
+  if (addend) {
+    const F4 a = ld4(addend + i * 4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] += a.v[j];
   }
   *reinterpret_cast<float4*>(dx + i * 4) = make_float4(s[0], s[1], s[2], s[3]);
 }
@@ -400,11 +449,18 @@ int adaptive_maxpool_fwd(const float* x, int N, int H, int W, int C, int OH, int
 }
 
 int adaptive_maxpool_bwd(const float* dy, const int32_t* idx, int N, int H, int W, int C, int OH,
-                         int OW, float* dx, cudaStream_t s) {
+                         int OW, float* dx, cudaStream_t s, const float* addend) {
   EVE_REQUIRE(C % 4 == 0, EVE_ERR_SHAPE, "adaptive_maxpool: C must be a multiple of 4");
+  if (H == 2 * OH && W == 2 * OW) {
+    long long total = (long long)N * OH * OW * (C / 4);
+    adaptive_maxpool_bwd_exact_kernel<2, 2><<<cdiv(total, 256), 256, 0, s>>>(dy, idx, total, W, C, OH, OW,
+                                                                             addend, dx);
+    EVE_LAUNCH_CHECK();
+    return EVE_OK;
+  }
   long long total = (long long)N * H * W * (C / 4);
   adaptive_maxpool_bwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(dy, idx, total, H, W, C, OH, OW,
-                                                               dx);
+                                                               addend, dx);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }

@@ -681,6 +681,29 @@ size_t rnet_conv_scratch_bytes(const RNet& n) {
   return conv_scratch_bytes(mi, mo, mw, mp);
 }
 
+// every convolution whose tensor-core weight layout can be prepared ahead of the pass (w == null:
+// geometry only, for sizing); initial.0 runs on a zero-padded scratch copy and is prepared per call
+std::vector<ConvPrepReq> rnet_prep_list(const RNet& n, const float* const* w) {
+  std::vector<ConvPrepReq> v;
+  auto add = [&](const ConvGeom& g, int slot) { v.push_back(ConvPrepReq{g, w ? w[slot] : nullptr}); };
+  add(n.gi3, 4);
+  auto block = [&](const RBlock& k) {
+    add(k.g1, k.slot + 2);
+    add(k.g2, k.slot + 6);
+    if (k.skipconv) add(k.gs, k.slot + 10);
+  };
+  for (int l = 0; l < kLevels; ++l) {
+    for (auto& k : n.enc[l]) block(k);
+    block(n.dec[l]);
+  }
+  add(n.gf0, n.slot_final);
+  return v;
+}
+size_t rnet_prep_bytes(const RNet& n) {
+  const std::vector<ConvPrepReq> v = rnet_prep_list(n, nullptr);
+  return conv_prepare_batch_bytes(v.data(), (int)v.size());
+}
+
 bool build_bwd_scratch(const RNet& n, Arena& ws, BwdScratch& sc) {
   sc.cs.bytes = rnet_conv_scratch_bytes(n);
   sc.cs.base = ws.get<char>(sc.cs.bytes);
@@ -745,7 +768,8 @@ size_t rnet_fwd_scratch_bytes(const RNet& n) {
   return align_up(rnet_conv_scratch_bytes(n), 256) +
          4 * align_up(n.max_act * sizeof(uint16_t), 256) +      // operand planes A, B (hi + lo)
          4 * align_up((size_t)n.B * P * 4 * n.nf * sizeof(float), 256) +
-         2 * align_up((size_t)kMaxRCells * n.B * P * n.nf * sizeof(float), 256) + 4096 + 16384;
+         2 * align_up((size_t)kMaxRCells * n.B * P * n.nf * sizeof(float), 256) +
+         align_up(rnet_prep_bytes(n), 256) + 4096 + 16384;
 }
 
 }  // namespace
@@ -792,6 +816,7 @@ extern "C" size_t eve_refinenet_workspace_bytes(const eve_refinenet_params* p) {
   build_bwd_scratch(n, ws, sc);
   build_bwd_extra(n, ws, ex);
   build_fused_bwd(n, ws, fb);
+  ws.get<char>(rnet_prep_bytes(n));
   size_t f = rnet_fwd_scratch_bytes(n);
   return (ws.off > f ? ws.off : f) + 256;
 }
@@ -833,6 +858,14 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
            (long long)N * HW0, HW0, n.x0);
   float* w0p = ws.get<float>((size_t)16 * kInitC * 9);
   EVE_REQUIRE(w0p, EVE_ERR_WORKSPACE, "refinenet_fwd: workspace too small");
+  {
+    // forward tensor-core layouts of all convolution weights: one launch
+    const size_t pb = rnet_prep_bytes(n);
+    char* region = ws.get<char>(pb);
+    EVE_REQUIRE(region, EVE_ERR_WORKSPACE, "refinenet_fwd: workspace too small");
+    const std::vector<ConvPrepReq> reqs = rnet_prep_list(n, w);
+    EVE_TRY(conv_prepare_batch(reqs.data(), (int)reqs.size(), false, region, pb, s));
+  }
   LAUNCH1D(pad_cin_kernel, 16 * kInitC * 9, w[0], 16, p->in_channels, kInitC, w0p);
   EVE_TRY(conv_fwd(n.gi0, n.x0, w0p, w[1], nullptr, n.i0, cs, s));
   if (fusedn) {
@@ -938,6 +971,7 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
                                  cudaMemcpyDeviceToDevice, s));
       }
       // the gate weights do not change over the T steps: lay them out for the tensor cores once
+      const int prep_mark = conv_prepared_mark();
       size_t top_used = 0;
       for (int i = 0; i < nc && !persistent; ++i) {
         const float* const* cw = w + n.slot_rnn + wpc * i;
@@ -971,7 +1005,7 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
         EVE_CUDA(cudaMemcpyAsync(n.by + (size_t)t * B * E, xt, (size_t)B * E * sizeof(float),
                                  cudaMemcpyDeviceToDevice, s));
       }
-      conv_prepared_clear();
+      conv_prepared_truncate(prep_mark);
       bout = n.by;
       for (int i = 0; i < nc; ++i)
         EVE_CUDA(cudaMemcpyAsync(h0n + (size_t)i * B * E, n.cell[i].h + (size_t)(T - 1) * B * E,
@@ -1008,6 +1042,7 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
   EVE_TRY(conv_fwd(n.gf0, n.dec[0].out, fw[0], fw[1], nullptr, n.f0, cs, s));
   LAUNCH1D(final_head_fwd_kernel, (long long)N * HW0, n.f0, fw[2], fw[3], (long long)N * HW0, out,
            n.sig);
+  conv_prepared_clear();
   return EVE_OK;
 }
 
@@ -1035,9 +1070,17 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
   bool ok = build_bwd_scratch(n, ws, sc);
   ok = build_bwd_extra(n, ws, ex) && ok;
   ok = build_fused_bwd(n, ws, fb) && ok;
+  const size_t prep_bytes = rnet_prep_bytes(n);
+  char* prep_region = ws.get<char>(prep_bytes);
+  ok = ok && prep_region != nullptr;
   const bool fusedn = rnet_fused(n);
   EVE_REQUIRE(ok, EVE_ERR_WORKSPACE, "refinenet_bwd: workspace too small (%zu < %zu)",
               workspace_bytes, ws.off);
+  {
+    // flipped data-gradient layouts of all convolution weights: one launch
+    const std::vector<ConvPrepReq> reqs = rnet_prep_list(n, w);
+    EVE_TRY(conv_prepare_batch(reqs.data(), (int)reqs.size(), true, prep_region, prep_bytes, s));
+  }
   const int N = n.N, B = n.B, T = n.T, nf = n.nf;
   const int P = kLevelH[4] * kLevelW[4];
   const int HW0 = kLevelH[0] * kLevelW[0];
@@ -1161,6 +1204,7 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
         dcur = dxo;
       }
     }
+    const int prep_mark = conv_prepared_mark();
     size_t top_used = 0;
     for (int i = 0; i < nc && !persistent; ++i) {
       const float* const* cw = w + n.slot_rnn + wpc * i;
@@ -1194,7 +1238,7 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
         dcur = dxo;
       }
     }
-    conv_prepared_clear();
+    conv_prepared_truncate(prep_mark);
     dbx = ex.dbx;
     // weight gradients: one batched wgrad over all T*B bottleneck images per conv
     ConvGeom G1 = make_conv(N, kLevelH[4], kLevelW[4], 2 * nf, g1.Cout, 3, 1, 1);
@@ -1240,10 +1284,9 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
     }
     if (l > 0) {
       const RBlock& e = n.enc[l - 1].back();
+      // + the gradient that reached this encoder output through the skip connection
       EVE_TRY(adaptive_maxpool_bwd(cur, n.pidx[l - 1], N, e.H, e.W, e.oc, kLevelH[l], kLevelW[l],
-                                   other, s));
-      if (p->use_skip)
-        EVE_TRY(ew_add(other, ex.dskip[l - 1], (long long)N * e.H * e.W * e.oc, other, s));
+                                   other, s, p->use_skip ? ex.dskip[l - 1] : nullptr));
       float* tmp = cur; cur = other; other = tmp;
       have = false;
     }
@@ -1283,5 +1326,6 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
       EVE_TRY(copy_channels(sc.t0, (long long)N * HW0, 1, kInitC, p->in_channels - 1, dheatmap, 1, 0,
                             false, s));
   }
+  conv_prepared_clear();
   return EVE_OK;
 }
