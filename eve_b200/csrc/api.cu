@@ -194,6 +194,7 @@ static Opt g_opts[OPT_COUNT] = {
     {"fused_planes", 1, 0, 1, "EVE_B200_FUSED_PLANES", false},
     {"fused_norm", 1, 0, 1, "EVE_B200_FUSED_NORM", false},
     {"tc_strip", 1, 0, 2, "EVE_B200_TC_STRIP", false},
+    {"tc_wgrad_strip", 1, 0, 1, "EVE_B200_TC_WGRAD_STRIP", false},
     {"cgru_persistent", 1, 0, 1, "EVE_B200_CGRU_PERSISTENT", false},
 };
 int get_option(int key) {

@@ -1961,6 +1961,219 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
   }
 }
 
+// ====================================================== padded-strip weight gradient ==
+// dW of 3x3 stride-1 convolutions with 64 output channels on maps narrower than 128 pixels (EyeNet
+// layer1, RefineNet levels 1-2: the split-K kernel above re-loads the dy box once per filter tap and
+// the x box once per M block -- 48 KB of operands per 8 MMAs, 2.4x what L2 -> shared memory
+// delivers, 120 TFLOP/s).  As in conv_tc_wgrad_row_kernel the K dimension runs over pixels, but of a
+// zero-padded STRIP: a work item stages R rows of x and R + 2 rows of dy ONCE, both as boxes that
+// start at w = -1 and are W + 2 pixels wide, so that pixel p of the x strip meets pixel
+// p + (2 - r)(W + 2) + (1 - q) of the dy strip for filter tap (r, q): nine descriptor start
+// addresses into one staged strip.  The pad pixels of x are TMA zero fill and contribute nothing.
+// One M = 128 instruction covers two taps (64 output channels each) whose strip offsets differ by
+// the descriptor's leading-dimension offset; five instructions per 16-pixel K step cover the nine
+// taps.  Each CTA accumulates all its items in TMEM (five accumulators) and flushes into ONE partial
+// gradient (deterministic second stage: wgrad_reduce) at least every kWgradChainPixels pixels.
+struct TcWgStripParams {
+  int N, H, W, Wp;
+  int R, strips, items;           // rows per strip, strips per image, N * strips
+  int ksteps;                     // ceil(R * Wp / 16)
+  int dy_plane, x_plane;          // bytes of one plane inside a stage (1024-aligned)
+  int flush_items;                // items per accumulation chain
+  float* part;                    // [gridDim.x][64][9 * CIN]
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
+                           const __grid_constant__ CUtensorMap tmD_lo,
+                           const __grid_constant__ CUtensorMap tmX_hi,
+                           const __grid_constant__ CUtensorMap tmX_lo, const TcWgStripParams p) {
+  constexpr int COUT = 64;
+  constexpr bool kStack = CIN <= 32;                       // 5 x 2 CIN accumulator columns must fit
+  constexpr uint32_t kAcc = kStack ? 2 * CIN : CIN;
+  constexpr uint32_t kTmemCols = 5 * kAcc <= 256 ? 256u : 512u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  const int stage_bytes = 2 * (p.dy_plane + p.x_plane);      // [dy hi][dy lo][x hi][x lo]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + 2 * (size_t)stage_bytes);
+  uint64_t* empty = full + 2;
+  uint64_t* tmem_full = empty + 2;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tmap_prefetch(&tmD_hi);
+    tmap_prefetch(&tmD_lo);
+    tmap_prefetch(&tmX_hi);
+    tmap_prefetch(&tmX_lo);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 128);
+    fence_barrier_init();
+  }
+  // everything a descriptor may touch outside the TMA boxes (the pixel in front of the dy strip,
+  // the tails behind both strips) must be finite: x is zero there, and 0 * NaN would poison dW
+  for (int i = threadIdx.x; i < 2 * stage_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int my_items = 0;
+  for (int item = blockIdx.x; item < p.items; item += gridDim.x) ++my_items;
+  const int chains = (my_items + p.flush_items - 1) / p.flush_items;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t tx = (uint32_t)((p.R + 2) * p.Wp * COUT * 2 + p.R * p.Wp * CIN * 2) * 2u;
+      uint32_t g = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++g) {
+        const int n = item / p.strips;
+        const int h0 = (item - n * p.strips) * p.R;
+        const uint32_t s = g & 1;
+        mbar_wait(&empty[s], ((g >> 1) & 1) ^ 1);
+        uint8_t* st = ring + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full[s], tx);
+        tma_load_4d(st, &tmD_hi, &full[s], 0, -1, h0 - 1, n);
+        tma_load_4d(st + p.dy_plane, &tmD_lo, &full[s], 0, -1, h0 - 1, n);
+        tma_load_4d(st + 2 * p.dy_plane, &tmX_hi, &full[s], 0, -1, h0, n);
+        tma_load_4d(st + 2 * p.dy_plane + p.x_plane, &tmX_lo, &full[s], 0, -1, h0, n);
+      }
+    }
+  } else if (warp == 1) {
+    // D fp32, A/B bf16, both MN-major, M = 128 (two taps x 64 output channels), N = CIN (or 2 CIN)
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(CIN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                ((uint32_t)((2 * CIN) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    constexpr uint32_t kDStep16 = (uint32_t)(16 * COUT * 2) >> 4;   // 16 pixels of the dy strip
+    constexpr uint32_t kXStep16 = (uint32_t)(16 * CIN * 2) >> 4;
+    const uint32_t ring16 = smem_u32(ring) >> 4;
+    const uint32_t dylo16 = (uint32_t)p.dy_plane >> 4, xlo16 = (uint32_t)p.x_plane >> 4;
+    // M blocks: (first tap's dy-strip offset in pixels, pixel distance to the second tap).  Tap
+    // (r, q) pairs x pixel p with dy pixel p + (2 - r) Wp + (1 - q); the one negative offset (tap
+    // (2, 2): -1) is taken on the x side instead -- block 0 reads x one pixel in, dy from 0; the x
+    // pixel it skips is a pad column (zero), the one it gains lies in the zero tail.
+    const int Wp = p.Wp;
+    const uint32_t boff[5] = {0u, 1u, (uint32_t)Wp, 2u * Wp - 1u, 2u * Wp + 1u};
+    const uint32_t blbo[5] = {1u, (uint32_t)Wp - 2u, 1u, 1u, 1u};
+    uint64_t ddesc[5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b)
+      ddesc[b] = mnmajor_desc(0u, blbo[b] * 128u, COUT) + (uint64_t)(boff[b] * 8u);
+    const uint64_t xdesc = mnmajor_desc(0u, (uint32_t)p.x_plane, CIN);
+    constexpr uint32_t kXPix16 = (uint32_t)(CIN * 2) >> 4;
+    uint32_t g = 0;
+    int in_chain = 0, chain = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++g) {
+      const uint32_t s = g & 1;
+      if (in_chain == 0) {
+        mbar_wait(tmem_empty, ((uint32_t)chain & 1) ^ 1);       // the epilogue drained the accumulators
+        tc_fence_after();
+      }
+      mbar_wait(&full[s], (g >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t st16 = ring16 + s * ((uint32_t)stage_bytes >> 4);
+        const uint32_t x16 = st16 + 2 * dylo16;
+        for (int ks = 0; ks < p.ksteps; ++ks) {
+          const uint32_t acc = (in_chain | ks) != 0 ? 1u : 0u;
+          const uint64_t dbh0 = xdesc + (uint64_t)(x16 + (uint32_t)ks * kXStep16);
+#pragma unroll
+          for (int b = 0; b < 5; ++b) {
+            const uint64_t dbh = b == 0 ? dbh0 + kXPix16 : dbh0;
+            const uint64_t dah = ddesc[b] + (uint64_t)(st16 + (uint32_t)ks * kDStep16);
+            const uint64_t dal = dah + dylo16;
+            const uint32_t tmem_d = tmem_base + (uint32_t)b * kAcc;
+            if (kStack) {
+              umma_bf16(tmem_d, dah, dbh, idesc2, acc);
+              umma_bf16(tmem_d, dal, dbh, idesc, 1);
+            } else {
+              const uint64_t dbl = dbh + xlo16;
+              umma_bf16(tmem_d, dal, dbh, idesc, acc);
+              umma_bf16(tmem_d, dah, dbl, idesc, 1);
+              umma_bf16(tmem_d, dah, dbh, idesc, 1);
+            }
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      __syncwarp();
+      ++in_chain;
+      const bool last = item + (int)gridDim.x >= p.items;
+      if (in_chain == p.flush_items || last) {
+        if (elect_one()) umma_commit(tmem_full);
+        __syncwarp();
+        in_chain = 0;
+        ++chain;
+      }
+    }
+  } else {
+    // epilogue: drain every finished chain into this CTA's partial gradient (same thread, same
+    // address, fixed order: deterministic round-to-nearest additions)
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int sub = m >> 6, co = m & 63;
+    constexpr size_t KK = (size_t)9 * CIN;
+    // (r * 3 + q) of the tap in M sub-block `sub` of block b; -1: the junk half of the last block
+    const int tapmap[5][2] = {{8, 7}, {6, 5}, {4, 3}, {2, 1}, {0, -1}};
+    for (int chain = 0; chain < chains; ++chain) {
+      mbar_wait(tmem_full, (uint32_t)chain & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int b = 0; b < 5; ++b) {
+        const int tap = tapmap[b][sub];
+        float* dst = p.part + ((size_t)blockIdx.x * COUT + co) * KK + (size_t)(tap < 0 ? 0 : tap) * CIN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < CIN; c0 += 32) {
+          float v[32];
+          const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)b * kAcc + (uint32_t)c0;
+          tmem_ld32(ta, v);
+          if (kStack) {
+            float u[32];
+            tmem_ld32(ta + (uint32_t)CIN, u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += u[j];
+          }
+          if (tap >= 0) {
+            float4* o4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (chain > 0) {
+                const float4 a = o4[j];
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              }
+              o4[j] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty);
+    }
+    if (chains == 0) {      // a CTA without items still owns a partial: it must read as zero
+      for (int i = m; i < COUT * (int)KK; i += 128) p.part[(size_t)blockIdx.x * COUT * KK + i] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------ operand preparation --
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float* __restrict__ x, long long n4, __nv_bfloat16* __restrict__ hi,
@@ -2788,6 +3001,80 @@ static int conv_tc_wgrad_row_run(const ConvGeom& g, const void* d_hi, const void
   return EVE_ERR_SHAPE;
 }
 
+// ---- padded-strip weight gradient: 3x3 stride 1, 64 output channels, 32 or 64 input channels
+static bool wgrad_strip_geometry_ok(const ConvGeom& g) {
+  if (g.KH != 3 || g.KW != 3 || g.stride != 1 || g.pad != 1 || g.OH != g.H || g.OW != g.W) return false;
+  if (g.Cout != 64 || (g.Cin != 32 && g.Cin != 64) || g.N < 1) return false;
+  return g.W + 2 <= 256 && g.W < kTileM;        // (128-pixel rows: the halo-row kernels)
+}
+
+struct WgStripPlan {
+  int R, strips, ksteps, dy_plane, x_plane, smem;
+};
+static bool wgrad_strip_plan(const ConvGeom& g, WgStripPlan& pl) {
+  const int Wp = g.W + 2;
+  auto fit = [&](int R, WgStripPlan& q) {
+    q.R = R;
+    q.ksteps = cdiv((long long)R * Wp, 16);
+    const int kpad = q.ksteps * 16;
+    q.dy_plane = (int)align_up((size_t)(1 + kpad + 2 * Wp + 4) * 128, 1024);
+    q.x_plane = (int)align_up((size_t)kpad * g.Cin * 2, 1024);
+    q.smem = 2 * 2 * (q.dy_plane + q.x_plane) + 1024 + 256;
+    return q.smem <= 227 * 1024 && R + 2 <= 256;
+  };
+  int rmax = 0;
+  WgStripPlan q;
+  for (int R = 1; R <= g.H; ++R)
+    if (fit(R, q)) rmax = R; else break;
+  if (rmax == 0) return false;
+  pl.strips = cdiv(g.H, rmax);
+  fit(cdiv(g.H, pl.strips), pl);
+  pl.strips = cdiv(g.H, pl.R);
+  return true;
+}
+
+bool conv_tc_wgrad_strip_supported(const ConvGeom& g) {
+  WgStripPlan pl;
+  return get_option(OPT_TC_WGRAD_STRIP) != 0 && wgrad_strip_geometry_ok(g) && wgrad_strip_plan(g, pl);
+}
+
+template <int CIN>
+static int launch_wgrad_strip(const CUtensorMap& d_hi, const CUtensorMap& d_lo, const CUtensorMap& x_hi,
+                              const CUtensorMap& x_lo, const TcWgStripParams& p, int grid, int smem,
+                              cudaStream_t s) {
+  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_wgrad_strip_kernel<CIN>, 227 * 1024));
+  conv_tc_wgrad_strip_kernel<CIN><<<grid, kThreads, smem, s>>>(d_hi, d_lo, x_hi, x_lo, p);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
+static int conv_tc_wgrad_strip_run(const ConvGeom& g, const void* d_hi, const void* d_lo,
+                                   const void* x_hi, const void* x_lo, float* part, int* splits_out,
+                                   cudaStream_t s) {
+  WgStripPlan pl;
+  EVE_REQUIRE(wgrad_strip_geometry_ok(g) && wgrad_strip_plan(g, pl), EVE_ERR_SHAPE,
+              "conv_tc_wgrad_strip: unsupported geometry");
+  TcWgStripParams p;
+  p.N = g.N; p.H = g.H; p.W = g.W; p.Wp = g.W + 2;
+  p.R = pl.R; p.strips = pl.strips;
+  p.items = g.N * pl.strips;
+  p.ksteps = pl.ksteps;
+  p.dy_plane = pl.dy_plane; p.x_plane = pl.x_plane;
+  // every fp32 accumulation chain in TMEM stays below kWgradChainPixels pixels (round-toward-zero
+  // accumulation: the error of a chain grows with its length)
+  p.flush_items = std::max(1, kWgradChainPixels / (pl.R * g.W));
+  p.part = part;
+  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  CUtensorMap md_hi, md_lo, mx_hi, mx_lo;
+  EVE_TRY(make_map_nhwc(&md_hi, d_hi, g.N, g.H, g.W, 64, 64, p.Wp, pl.R + 2, 1));
+  EVE_TRY(make_map_nhwc(&md_lo, d_lo, g.N, g.H, g.W, 64, 64, p.Wp, pl.R + 2, 1));
+  EVE_TRY(make_map_nhwc(&mx_hi, x_hi, g.N, g.H, g.W, g.Cin, g.Cin, p.Wp, pl.R, 1));
+  EVE_TRY(make_map_nhwc(&mx_lo, x_lo, g.N, g.H, g.W, g.Cin, g.Cin, p.Wp, pl.R, 1));
+  *splits_out = grid;
+  return g.Cin == 64 ? launch_wgrad_strip<64>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s)
+                     : launch_wgrad_strip<32>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s);
+}
+
 size_t conv_tc_wgrad_partial_floats(const ConvGeom& g) {
   if (!conv_tc_wgrad_supported(g)) return 0;
   TcWgradParams p;
@@ -2795,6 +3082,7 @@ size_t conv_tc_wgrad_partial_floats(const ConvGeom& g) {
   wgrad_plan(g, p, mb, nb, sp, 3, 8);   // sized for the largest "tc_wgrad_waves" setting
   // the halo-row kernel writes one partial per CTA
   if (row_geometry_ok(g) && (g.Cout == 16 || g.Cout == 32)) sp = std::max(sp, kNumSMs);
+  if (wgrad_strip_geometry_ok(g)) sp = std::max(sp, kNumSMs);      // one partial per CTA as well
   return (size_t)sp * g.Cout * g.K();
 }
 
@@ -2805,6 +3093,8 @@ int conv_tc_wgrad_run(const ConvGeom& g, const void* d_hi, const void* d_lo, con
   EVE_REQUIRE(conv_tc_wgrad_supported(g), EVE_ERR_SHAPE, "conv_tc_wgrad: unsupported geometry");
   if (conv_tc_wgrad_row_supported(g) && x_fmt == TC_BF16)
     return conv_tc_wgrad_row_run(g, d_hi, d_lo, x_hi, x_lo, part, npass, splits_out, s);
+  if (npass == 3 && x_fmt == TC_BF16 && conv_tc_wgrad_strip_supported(g))
+    return conv_tc_wgrad_strip_run(g, d_hi, d_lo, x_hi, x_lo, part, splits_out, s);
   TcWgradParams p;
   int mb, nb, sp;
   wgrad_plan(g, p, mb, nb, sp, npass);

@@ -95,6 +95,9 @@ int eve_get_conv_mode(void);
  *                                nine taps taken as descriptor shifts, weight tiles shared by all
  *                                tiles of the strip): 0 off, 1 where its plan wastes at most a
  *                                seventh more MMA rows than the per-tap box kernel, 2 wherever it fits
+ *   "tc_wgrad_strip"      0/1    padded-strip weight-gradient kernel (3x3 stride 1, 64 output
+ *                                channels, maps narrower than 128 pixels): x and dy strips staged
+ *                                once per item, the nine taps as descriptor shifts
  *   "cgru_persistent"     0/1    ConvGRU bottleneck (64 features, 5x8 maps) as ONE persistent kernel
  *                                per sequence (x halves of the gate convolutions batched over
  *                                time, recurrence in shared memory / TMEM); 0 = one convolution

@@ -12,7 +12,7 @@ from eve_b200 import lib as L            # noqa: E402
 from tests import gpu_util as G          # noqa: E402
 
 OPTIONS = ('tc_stage_cap', 'tc_row_kernel', 'tc_row_strips', 'tc_row_wgrad', 'tc_wgrad_waves',
-           'fused_planes', 'fused_norm', 'tc_strip', 'cgru_persistent')
+           'fused_planes', 'fused_norm', 'tc_strip', 'cgru_persistent', 'tc_wgrad_strip')
 
 
 @pytest.fixture()
@@ -97,6 +97,33 @@ def test_padded_strip_kernel_matches_fp64(case, options):
     assert G.rel(got0, y) < 3e-5
 
 
+# padded-strip weight gradient (n, cin, h, w): Cout = 64; several strips per image with a ragged
+# last strip, one strip per image, more CTAs than items and many items per CTA (several flushes)
+WGRAD_STRIP_CASES = [(5, 64, 32, 32), (3, 64, 36, 64), (7, 32, 36, 64), (9, 64, 18, 32), (40, 64, 5, 8),
+                     (2, 32, 7, 10), (200, 64, 8, 8), (330, 64, 32, 32)]
+
+
+@pytest.mark.parametrize('case', WGRAD_STRIP_CASES, ids=lambda c: 'x'.join(map(str, c)))
+def test_padded_strip_weight_gradient_matches_fp64(case, options):
+    n, cin, h, w = case
+    cout = 64
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(n, cin, h, w, generator=g)
+    wd = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).double().requires_grad_(True)
+    y = F.conv2d(x.double(), wd, None, padding=1)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy.double())
+    L.load().eve_set_conv_mode(1)
+    options('tc_wgrad_strip', 1)
+    dw, db = G.conv_wgrad(x.cuda(), dy.cuda(), 3, 1, 1)
+    options('tc_wgrad_strip', 0)
+    dw0, _ = G.conv_wgrad(x.cuda(), dy.cuda(), 3, 1, 1)
+    torch.cuda.synchronize()
+    assert G.rel(dw, wd.grad) < 5e-5
+    assert G.rel(dw0, wd.grad) < 5e-5
+    assert G.rel(db, dy.double().sum(dim=(0, 2, 3))) < 2e-5
+
+
 @pytest.mark.parametrize('waves', [1, 2, 4])
 def test_split_k_wave_count_does_not_change_weight_gradients(waves, options):
     n, cin, h, w, cout = 6, 64, 32, 32, 64
@@ -138,6 +165,7 @@ def _eve_step(cfg, seed=5, B=2, T=3):
 VARIANTS = [
     dict(tc_strip=2),
     dict(cgru_persistent=0),
+    dict(tc_wgrad_strip=0),
     dict(tc_strip=0),
     dict(fused_norm=0),
     dict(fused_norm=0, fused_planes=0),
