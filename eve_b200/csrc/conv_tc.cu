@@ -3018,7 +3018,8 @@ static bool wgrad_strip_plan(const ConvGeom& g, WgStripPlan& pl) {
     q.ksteps = cdiv((long long)R * Wp, 16);
     const int kpad = q.ksteps * 16;
     q.dy_plane = (int)align_up((size_t)(1 + kpad + 2 * Wp + 4) * 128, 1024);
-    q.x_plane = (int)align_up((size_t)kpad * g.Cin * 2, 1024);
+    // + 1 pixel: block 0 reads the x strip one pixel in, so its last K step ends one pixel later
+    q.x_plane = (int)align_up((size_t)(kpad + 1) * g.Cin * 2, 1024);
     q.smem = 2 * 2 * (q.dy_plane + q.x_plane) + 1024 + 256;
     return q.smem <= 227 * 1024 && R + 2 <= 256;
   };

@@ -44,7 +44,9 @@ if os.environ.get('BENCH_IN_SHAPES'):
 
 def main(which):
     s = L.stream_ptr()
-    print('%-18s %10s %10s %10s %10s' % ('shape', 'fused ms', 'GB/s', 'legacy ms', 'GB/s'))
+    chunk_mb = float(os.environ.get('BENCH_IN_CHUNK_MB', '0'))
+    print('%-18s %10s %10s %10s %10s %12s %8s' % ('shape', 'fused ms', 'GB/s', 'legacy ms', 'GB/s',
+                                                   'chunked ms', 'GB/s'))
     tot_f = tot_l = 0.0
     for n, hw, c in SHAPES:
         e = n * hw * c
@@ -66,10 +68,22 @@ def main(which):
             def legacy():
                 L.check(lib.eve_instnorm_act_fwd(L.ptr(x), n, hw, c, L.ptr(g), L.ptr(b), 1, L.ptr(y),
                                                  L.ptr(mean), L.ptr(rstd), s), 'l')
+            # the separate stats / apply passes over chunks of images small enough that the second
+            # pass finds its input in L2 (BENCH_IN_CHUNK_MB of x per chunk)
+            per = max(1, int(chunk_mb * 1e6 / (hw * c * 4))) if chunk_mb > 0 else n
+
+            def chunked():
+                for i0 in range(0, n, per):
+                    m = min(per, n - i0)
+                    o, so = i0 * hw * c, i0 * c
+                    L.check(lib.eve_instnorm_act_fwd(x[o:].data_ptr(), m, hw, c, L.ptr(g), L.ptr(b), 1,
+                                                     y[o:].data_ptr(), mean[so:].data_ptr(),
+                                                     rstd[so:].data_ptr(), s), 'c')
             tf, tl = timeit(fused), timeit(legacy)
+            tc = timeit(chunked) if chunk_mb > 0 else float('nan')
             bytes_ = 8.0 * e
-            print('fwd %-14s %10.3f %10.0f %10.3f %10.0f' % ('%dx%dx%d' % (n, hw, c), tf,
-                  bytes_ / tf / 1e6, tl, bytes_ / tl / 1e6))
+            print('fwd %-14s %10.3f %10.0f %10.3f %10.0f %12.3f %8.0f' % ('%dx%dx%d' % (n, hw, c), tf,
+                  bytes_ / tf / 1e6, tl, bytes_ / tl / 1e6, tc, bytes_ / tc / 1e6))
             tot_f += tf
             tot_l += tl
         if which in ('bwd', 'all'):
@@ -84,10 +98,21 @@ def main(which):
                 L.check(lib.eve_instnorm_act_bwd(L.ptr(dy), L.ptr(x), L.ptr(x), n, hw, c, L.ptr(mean),
                                                  L.ptr(rstd), L.ptr(g), 1, L.ptr(y), L.ptr(dg),
                                                  L.ptr(db), L.ptr(ws), ws.numel(), s), 'lb')
+            per = max(1, int(chunk_mb * 1e6 / (hw * c * 8))) if chunk_mb > 0 else n
+
+            def chunkedb():
+                for i0 in range(0, n, per):
+                    m = min(per, n - i0)
+                    o, so = i0 * hw * c, i0 * c
+                    L.check(lib.eve_instnorm_act_bwd(dy[o:].data_ptr(), x[o:].data_ptr(), x[o:].data_ptr(),
+                                                     m, hw, c, mean[so:].data_ptr(), rstd[so:].data_ptr(),
+                                                     L.ptr(g), 1, y[o:].data_ptr(), L.ptr(dg), L.ptr(db),
+                                                     L.ptr(ws), ws.numel(), s), 'cb')
             tf, tl = timeit(fusedb), timeit(legacyb)
+            tc = timeit(chunkedb) if chunk_mb > 0 else float('nan')
             bytes_ = 12.0 * e
-            print('bwd %-14s %10.3f %10.0f %10.3f %10.0f' % ('%dx%dx%d' % (n, hw, c), tf,
-                  bytes_ / tf / 1e6, tl, bytes_ / tl / 1e6))
+            print('bwd %-14s %10.3f %10.0f %10.3f %10.0f %12.3f %8.0f' % ('%dx%dx%d' % (n, hw, c), tf,
+                  bytes_ / tf / 1e6, tl, bytes_ / tl / 1e6, tc, bytes_ / tc / 1e6))
             tot_f += tf
             tot_l += tl
     print('total fused %.3f ms, legacy %.3f ms' % (tot_f, tot_l))
