@@ -1962,41 +1962,58 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
 }
 
 // ====================================================== padded-strip weight gradient ==
-// dW of 3x3 stride-1 convolutions with 64 output channels on maps narrower than 128 pixels (EyeNet
-// layer1, RefineNet levels 1-2: the split-K kernel above re-loads the dy box once per filter tap and
-// the x box once per M block -- 48 KB of operands per 8 MMAs, 2.4x what L2 -> shared memory
-// delivers, 120 TFLOP/s).  As in conv_tc_wgrad_row_kernel the K dimension runs over pixels, but of a
-// zero-padded STRIP: a work item stages R rows of x and R + 2 rows of dy ONCE, both as boxes that
-// start at w = -1 and are W + 2 pixels wide, so that pixel p of the x strip meets pixel
-// p + (2 - r)(W + 2) + (1 - q) of the dy strip for filter tap (r, q): nine descriptor start
-// addresses into one staged strip.  The pad pixels of x are TMA zero fill and contribute nothing.
-// One M = 128 instruction covers two taps (64 output channels each) whose strip offsets differ by
-// the descriptor's leading-dimension offset; five instructions per 16-pixel K step cover the nine
-// taps.  Each CTA accumulates all its items in TMEM (five accumulators) and flushes into ONE partial
+// dW of 3x3 stride-1 convolutions on maps narrower than 128 pixels (EyeNet layers 1-2, RefineNet
+// levels 1-2: the split-K kernel above re-loads the dy box once per filter tap and the x box once per
+// M block -- 48..64 KB of operands per 8..12 MMAs, about twice what L2 -> shared memory delivers).
+// As in conv_tc_wgrad_row_kernel the K dimension runs over pixels, but of a zero-padded STRIP: a work
+// item stages R rows of x and R + 2 rows of dy ONCE, both as boxes that start at w = -1 and are
+// W + 2 pixels wide, so that pixel p of the x strip meets pixel p + (2 - r)(W + 2) + (1 - q) of the dy
+// strip for filter tap (r, q): nine descriptor start addresses into one staged strip (the single
+// negative offset, tap (2, 2), is taken on the x side).  The pad pixels of x are TMA zero fill and
+// contribute nothing.  One M = 128 MN-major instruction covers 128 / SUBW taps of SUBW output
+// channels whose strip offsets differ by the descriptor's leading-dimension offset:
+//   SUBW = 64: tap pairs, five M blocks cover the nine taps of a 64-channel output block;
+//   SUBW = 32: the three horizontal taps of a filter row (+ one junk sub-block), three M blocks.
+// A JOB = (output-channel block, group of M blocks) owns as many accumulators as TMEM holds
+// (128-channel inputs: the taps of a block split into two jobs); the CTAs are dealt round-robin to
+// the jobs and each walks its job's strips, accumulating in TMEM and flushing into ONE partial
 // gradient (deterministic second stage: wgrad_reduce) at least every kWgradChainPixels pixels.
+struct WgStripJob {
+  int co0;                 // first output channel of the job's block
+  int nblk;                // M blocks (accumulators)
+  int boff[5], blbo[5];    // dy-strip offset of the first tap of a block, pixel distance between its taps
+  int xoff[5];             // x-strip offset (1 for the block that holds tap (2, 2))
+  int tap[5][4];           // r * 3 + q of every M sub-block, -1 = junk
+};
+constexpr int kWgMaxJobs = 4;
 struct TcWgStripParams {
-  int N, H, W, Wp;
-  int R, strips, items;           // rows per strip, strips per image, N * strips
+  int N, H, W, Wp, Cin, Cout;
+  int R, strips, items;           // rows per strip, strips per image, N * strips (per job)
   int ksteps;                     // ceil(R * Wp / 16)
-  int dy_plane, x_plane;          // bytes of one plane inside a stage (1024-aligned)
+  int dy_plane, x_chunk;          // bytes of one dy plane / of one 64-channel x chunk plane (1024-aligned)
   int flush_items;                // items per accumulation chain
-  float* part;                    // [gridDim.x][64][9 * CIN]
+  int njobs;
+  int period, slotjob[12];        // CTA c works on job slotjob[c % period]
+  WgStripJob job[kWgMaxJobs];
+  float* part;                    // [gridDim.x][Cout][9 * Cin]  (zero-filled by the host when njobs > 1)
 };
 
-template <int CIN>
+template <int CIN, int SUBW>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
                            const __grid_constant__ CUtensorMap tmD_lo,
                            const __grid_constant__ CUtensorMap tmX_hi,
                            const __grid_constant__ CUtensorMap tmX_lo, const TcWgStripParams p) {
-  constexpr int COUT = 64;
-  constexpr bool kStack = CIN <= 32;                       // 5 x 2 CIN accumulator columns must fit
-  constexpr uint32_t kAcc = kStack ? 2 * CIN : CIN;
-  constexpr uint32_t kTmemCols = 5 * kAcc <= 256 ? 256u : 512u;
+  constexpr int XW = CIN > 64 ? 64 : CIN;                  // channels of one x chunk (swizzle span)
+  constexpr int XCH = CIN / XW;                            // x chunks: N = CIN spans XCH descriptor blocks
+  constexpr bool kStack = CIN <= 32;                       // see TcCfg: N = 2 CIN over [x_hi ; x_lo]
+  constexpr uint32_t kAcc = kStack ? 2 * CIN : CIN;        // accumulator columns of one M block
+  constexpr int SUBS = kTileM / SUBW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
-  const int stage_bytes = 2 * (p.dy_plane + p.x_plane);      // [dy hi][dy lo][x hi][x lo]
+  const int x_plane = XCH * p.x_chunk;
+  const int stage_bytes = 2 * (p.dy_plane + x_plane);      // [dy hi][dy lo][x hi chunks][x lo chunks]
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + 2 * (size_t)stage_bytes);
   uint64_t* empty = full + 2;
   uint64_t* tmem_full = empty + 2;
@@ -2005,6 +2022,23 @@ conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // this CTA's job (dealt by a short repeating pattern, jobs with more M blocks get more CTAs) and
+  // its share of the job's items
+  const int jb = p.slotjob[blockIdx.x % p.period];
+  int cta_in_job = 0, ctas_in_job = 0;
+  for (int c = 0; c < (int)gridDim.x; ++c) {
+    if (p.slotjob[c % p.period] == jb) {
+      if (c < (int)blockIdx.x) ++cta_in_job;
+      ++ctas_in_job;
+    }
+  }
+  const WgStripJob& job = p.job[jb];
+  uint32_t tmem_cols = 32;
+  {
+    int mx = 0;
+    for (int j = 0; j < p.njobs; ++j) mx = max(mx, p.job[j].nblk);
+    while (tmem_cols < (uint32_t)mx * kAcc) tmem_cols <<= 1;
+  }
   if (warp == 0 && lane == 0) {
     tmap_prefetch(&tmD_hi);
     tmap_prefetch(&tmD_lo);
@@ -2018,11 +2052,11 @@ conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
     mbar_init(tmem_empty, 128);
     fence_barrier_init();
   }
-  // everything a descriptor may touch outside the TMA boxes (the pixel in front of the dy strip,
-  // the tails behind both strips) must be finite: x is zero there, and 0 * NaN would poison dW
+  // everything a descriptor may touch outside the TMA boxes (the tails behind both strips) must be
+  // finite: x is zero there, and 0 * NaN would poison dW
   for (int i = threadIdx.x; i < 2 * stage_bytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -2030,52 +2064,54 @@ conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
   const uint32_t tmem_base = *tmem_slot;
 
   int my_items = 0;
-  for (int item = blockIdx.x; item < p.items; item += gridDim.x) ++my_items;
+  for (int item = cta_in_job; item < p.items; item += ctas_in_job) ++my_items;
   const int chains = (my_items + p.flush_items - 1) / p.flush_items;
 
   if (warp == 0) {
     if (elect_one()) {
-      const uint32_t tx = (uint32_t)((p.R + 2) * p.Wp * COUT * 2 + p.R * p.Wp * CIN * 2) * 2u;
+      const uint32_t tx = (uint32_t)((p.R + 2) * p.Wp * SUBW * 2 + p.R * p.Wp * CIN * 2) * 2u;
       uint32_t g = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++g) {
+      for (int item = cta_in_job; item < p.items; item += ctas_in_job, ++g) {
         const int n = item / p.strips;
         const int h0 = (item - n * p.strips) * p.R;
         const uint32_t s = g & 1;
         mbar_wait(&empty[s], ((g >> 1) & 1) ^ 1);
         uint8_t* st = ring + (size_t)s * stage_bytes;
         mbar_expect_tx(&full[s], tx);
-        tma_load_4d(st, &tmD_hi, &full[s], 0, -1, h0 - 1, n);
-        tma_load_4d(st + p.dy_plane, &tmD_lo, &full[s], 0, -1, h0 - 1, n);
-        tma_load_4d(st + 2 * p.dy_plane, &tmX_hi, &full[s], 0, -1, h0, n);
-        tma_load_4d(st + 2 * p.dy_plane + p.x_plane, &tmX_lo, &full[s], 0, -1, h0, n);
+        tma_load_4d(st, &tmD_hi, &full[s], job.co0, -1, h0 - 1, n);
+        tma_load_4d(st + p.dy_plane, &tmD_lo, &full[s], job.co0, -1, h0 - 1, n);
+#pragma unroll
+        for (int c = 0; c < XCH; ++c) {
+          tma_load_4d(st + 2 * p.dy_plane + c * p.x_chunk, &tmX_hi, &full[s], c * XW, -1, h0, n);
+          tma_load_4d(st + 2 * p.dy_plane + x_plane + c * p.x_chunk, &tmX_lo, &full[s], c * XW, -1, h0, n);
+        }
       }
     }
   } else if (warp == 1) {
-    // D fp32, A/B bf16, both MN-major, M = 128 (two taps x 64 output channels), N = CIN (or 2 CIN)
+    // D fp32, A/B bf16, both MN-major, M = 128 (SUBS taps x SUBW output channels), N = CIN (or 2 CIN)
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(CIN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                 ((uint32_t)((2 * CIN) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-    constexpr uint32_t kDStep16 = (uint32_t)(16 * COUT * 2) >> 4;   // 16 pixels of the dy strip
-    constexpr uint32_t kXStep16 = (uint32_t)(16 * CIN * 2) >> 4;
+    constexpr uint32_t kDPix16 = (uint32_t)(SUBW * 2) >> 4;         // one pixel of the dy strip
+    constexpr uint32_t kXPix16 = (uint32_t)(XW * 2) >> 4;
+    constexpr uint32_t kDStep16 = 16u * kDPix16, kXStep16 = 16u * kXPix16;
     const uint32_t ring16 = smem_u32(ring) >> 4;
-    const uint32_t dylo16 = (uint32_t)p.dy_plane >> 4, xlo16 = (uint32_t)p.x_plane >> 4;
-    // M blocks: (first tap's dy-strip offset in pixels, pixel distance to the second tap).  Tap
-    // (r, q) pairs x pixel p with dy pixel p + (2 - r) Wp + (1 - q); the one negative offset (tap
-    // (2, 2): -1) is taken on the x side instead -- block 0 reads x one pixel in, dy from 0; the x
-    // pixel it skips is a pad column (zero), the one it gains lies in the zero tail.
-    const int Wp = p.Wp;
-    const uint32_t boff[5] = {0u, 1u, (uint32_t)Wp, 2u * Wp - 1u, 2u * Wp + 1u};
-    const uint32_t blbo[5] = {1u, (uint32_t)Wp - 2u, 1u, 1u, 1u};
-    uint64_t ddesc[5];
+    const uint32_t dylo16 = (uint32_t)p.dy_plane >> 4, xlo16 = (uint32_t)x_plane >> 4;
+    uint64_t ddesc[5], xdesc[5];
+    // x: N spans XCH 64-channel chunks (leading-dimension offset = one chunk); with the stacked
+    // issue the second block is the lo plane instead
+    const uint32_t x_lbo = kStack ? (uint32_t)x_plane : (uint32_t)p.x_chunk;
 #pragma unroll
-    for (int b = 0; b < 5; ++b)
-      ddesc[b] = mnmajor_desc(0u, blbo[b] * 128u, COUT) + (uint64_t)(boff[b] * 8u);
-    const uint64_t xdesc = mnmajor_desc(0u, (uint32_t)p.x_plane, CIN);
-    constexpr uint32_t kXPix16 = (uint32_t)(CIN * 2) >> 4;
+    for (int b = 0; b < 5; ++b) {
+      ddesc[b] = mnmajor_desc(0u, (uint32_t)job.blbo[b] * (uint32_t)(SUBW * 2), SUBW) +
+                 (uint64_t)((uint32_t)job.boff[b] * kDPix16);
+      xdesc[b] = mnmajor_desc(0u, x_lbo, XW) + (uint64_t)((uint32_t)job.xoff[b] * kXPix16);
+    }
+    const int nblk = job.nblk;
     uint32_t g = 0;
-    int in_chain = 0, chain = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++g) {
+    int in_chain = 0, chain = 0, done = 0;
+    for (int item = cta_in_job; item < p.items; item += ctas_in_job, ++g) {
       const uint32_t s = g & 1;
       if (in_chain == 0) {
         mbar_wait(tmem_empty, ((uint32_t)chain & 1) ^ 1);       // the epilogue drained the accumulators
@@ -2088,21 +2124,22 @@ conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
         const uint32_t x16 = st16 + 2 * dylo16;
         for (int ks = 0; ks < p.ksteps; ++ks) {
           const uint32_t acc = (in_chain | ks) != 0 ? 1u : 0u;
-          const uint64_t dbh0 = xdesc + (uint64_t)(x16 + (uint32_t)ks * kXStep16);
 #pragma unroll
           for (int b = 0; b < 5; ++b) {
-            const uint64_t dbh = b == 0 ? dbh0 + kXPix16 : dbh0;
-            const uint64_t dah = ddesc[b] + (uint64_t)(st16 + (uint32_t)ks * kDStep16);
-            const uint64_t dal = dah + dylo16;
-            const uint32_t tmem_d = tmem_base + (uint32_t)b * kAcc;
-            if (kStack) {
-              umma_bf16(tmem_d, dah, dbh, idesc2, acc);
-              umma_bf16(tmem_d, dal, dbh, idesc, 1);
-            } else {
-              const uint64_t dbl = dbh + xlo16;
-              umma_bf16(tmem_d, dal, dbh, idesc, acc);
-              umma_bf16(tmem_d, dah, dbl, idesc, 1);
-              umma_bf16(tmem_d, dah, dbh, idesc, 1);
+            if (b < nblk) {
+              const uint64_t dbh = xdesc[b] + (uint64_t)(x16 + (uint32_t)ks * kXStep16);
+              const uint64_t dah = ddesc[b] + (uint64_t)(st16 + (uint32_t)ks * kDStep16);
+              const uint64_t dal = dah + dylo16;
+              const uint32_t tmem_d = tmem_base + (uint32_t)b * kAcc;
+              if (kStack) {
+                umma_bf16(tmem_d, dah, dbh, idesc2, acc);
+                umma_bf16(tmem_d, dal, dbh, idesc, 1);
+              } else {
+                const uint64_t dbl = dbh + xlo16;
+                umma_bf16(tmem_d, dal, dbh, idesc, acc);
+                umma_bf16(tmem_d, dah, dbl, idesc, 1);
+                umma_bf16(tmem_d, dah, dbh, idesc, 1);
+              }
             }
           }
         }
@@ -2110,8 +2147,8 @@ conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
       }
       __syncwarp();
       ++in_chain;
-      const bool last = item + (int)gridDim.x >= p.items;
-      if (in_chain == p.flush_items || last) {
+      ++done;
+      if (in_chain == p.flush_items || done == my_items) {
         if (elect_one()) umma_commit(tmem_full);
         __syncwarp();
         in_chain = 0;
@@ -2123,17 +2160,15 @@ conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
     // address, fixed order: deterministic round-to-nearest additions)
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
-    const int sub = m >> 6, co = m & 63;
-    constexpr size_t KK = (size_t)9 * CIN;
-    // (r * 3 + q) of the tap in M sub-block `sub` of block b; -1: the junk half of the last block
-    const int tapmap[5][2] = {{8, 7}, {6, 5}, {4, 3}, {2, 1}, {0, -1}};
+    const int sub = m / SUBW, co = job.co0 + m % SUBW;
+    const size_t KK = (size_t)9 * CIN;
     for (int chain = 0; chain < chains; ++chain) {
       mbar_wait(tmem_full, (uint32_t)chain & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int b = 0; b < 5; ++b) {
-        const int tap = tapmap[b][sub];
-        float* dst = p.part + ((size_t)blockIdx.x * COUT + co) * KK + (size_t)(tap < 0 ? 0 : tap) * CIN;
+      for (int b = 0; b < job.nblk; ++b) {
+        const int tap = sub < SUBS ? job.tap[b][sub] : -1;
+        float* dst = p.part + ((size_t)blockIdx.x * p.Cout + co) * KK + (size_t)(tap < 0 ? 0 : tap) * CIN;
 #pragma unroll 1
         for (int c0 = 0; c0 < CIN; c0 += 32) {
           float v[32];
@@ -2162,15 +2197,12 @@ conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
       tc_fence_before();
       mbar_arrive(tmem_empty);
     }
-    if (chains == 0) {      // a CTA without items still owns a partial: it must read as zero
-      for (int i = m; i < COUT * (int)KK; i += 128) p.part[(size_t)blockIdx.x * COUT * KK + i] = 0.f;
-    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -3001,26 +3033,32 @@ static int conv_tc_wgrad_row_run(const ConvGeom& g, const void* d_hi, const void
   return EVE_ERR_SHAPE;
 }
 
-// ---- padded-strip weight gradient: 3x3 stride 1, 64 output channels, 32 or 64 input channels
+// ---- padded-strip weight gradient: 3x3 stride 1; (Cout, Cin) in {64} x {32, 64, 128},
+// {128} x {64, 128}, {32} x {32, 128}
 static bool wgrad_strip_geometry_ok(const ConvGeom& g) {
   if (g.KH != 3 || g.KW != 3 || g.stride != 1 || g.pad != 1 || g.OH != g.H || g.OW != g.W) return false;
-  if (g.Cout != 64 || (g.Cin != 32 && g.Cin != 64) || g.N < 1) return false;
-  return g.W + 2 <= 256 && g.W < kTileM;        // (128-pixel rows: the halo-row kernels)
+  if (g.N < 1 || g.W + 2 > 256 || g.W >= kTileM) return false;      // (128-pixel rows: the halo-row kernels)
+  if (g.Cout == 64) return g.Cin == 32 || g.Cin == 64 || g.Cin == 128;
+  if (g.Cout == 128) return g.Cin == 64 || g.Cin == 128;
+  if (g.Cout == 32) return g.Cin == 32 || g.Cin == 128;
+  return false;
 }
 
 struct WgStripPlan {
-  int R, strips, ksteps, dy_plane, x_plane, smem;
+  int R, strips, ksteps, dy_plane, x_chunk, smem;
 };
 static bool wgrad_strip_plan(const ConvGeom& g, WgStripPlan& pl) {
   const int Wp = g.W + 2;
+  const int subw = g.Cout == 32 ? 32 : 64;
+  const int xw = g.Cin > 64 ? 64 : g.Cin, xch = g.Cin / xw;
   auto fit = [&](int R, WgStripPlan& q) {
     q.R = R;
     q.ksteps = cdiv((long long)R * Wp, 16);
     const int kpad = q.ksteps * 16;
-    q.dy_plane = (int)align_up((size_t)(1 + kpad + 2 * Wp + 4) * 128, 1024);
-    // + 1 pixel: block 0 reads the x strip one pixel in, so its last K step ends one pixel later
-    q.x_plane = (int)align_up((size_t)(kpad + 1) * g.Cin * 2, 1024);
-    q.smem = 2 * 2 * (q.dy_plane + q.x_plane) + 1024 + 256;
+    q.dy_plane = (int)align_up((size_t)(kpad + 2 * Wp + 8) * subw * 2, 1024);
+    // + 1 pixel: the block that holds tap (2, 2) reads the x strip one pixel in
+    q.x_chunk = (int)align_up((size_t)(kpad + 1) * xw * 2, 1024);
+    q.smem = 2 * 2 * (q.dy_plane + xch * q.x_chunk) + 1024 + 256;
     return q.smem <= 227 * 1024 && R + 2 <= 256;
   };
   int rmax = 0;
@@ -3039,12 +3077,44 @@ bool conv_tc_wgrad_strip_supported(const ConvGeom& g) {
   return get_option(OPT_TC_WGRAD_STRIP) != 0 && wgrad_strip_geometry_ok(g) && wgrad_strip_plan(g, pl);
 }
 
-template <int CIN>
+// M blocks of one output-channel block: dy-strip offset of the first tap, pixel distance between the
+// taps of the block, x-strip offset, (r * 3 + q) per sub-block.  Tap (r, q) pairs x pixel p with dy
+// pixel p + (2 - r) Wp + (1 - q).
+static void wgrad_strip_blocks(int Wp, int subw, int boff[5], int blbo[5], int xoff[5], int tap[5][4],
+                               int& nblk) {
+  for (int b = 0; b < 5; ++b) {
+    xoff[b] = 0;
+    for (int j = 0; j < 4; ++j) tap[b][j] = -1;
+  }
+  if (subw == 64) {       // tap pairs in order of increasing strip offset
+    nblk = 5;
+    const int o[5] = {0, 1, Wp, 2 * Wp - 1, 2 * Wp + 1};
+    const int l[5] = {1, Wp - 2, 1, 1, 1};
+    const int t[5][2] = {{8, 7}, {6, 5}, {4, 3}, {2, 1}, {0, -1}};
+    for (int b = 0; b < 5; ++b) {
+      boff[b] = o[b]; blbo[b] = l[b];
+      tap[b][0] = t[b][0]; tap[b][1] = t[b][1];
+    }
+    xoff[0] = 1;          // tap (2, 2): offset -1, taken on the x side
+  } else {                // one filter row per block: q = 2, 1, 0 one pixel apart (+ a junk sub-block)
+    nblk = 3;
+    for (int b = 0; b < 3; ++b) {
+      const int r = 2 - b;
+      boff[b] = (2 - r) * Wp - 1 + (b == 0 ? 1 : 0);
+      blbo[b] = 1;
+      tap[b][0] = r * 3 + 2; tap[b][1] = r * 3 + 1; tap[b][2] = r * 3 + 0;
+    }
+    xoff[0] = 1;
+    boff[3] = boff[4] = 0; blbo[3] = blbo[4] = 1;
+  }
+}
+
+template <int CIN, int SUBW>
 static int launch_wgrad_strip(const CUtensorMap& d_hi, const CUtensorMap& d_lo, const CUtensorMap& x_hi,
                               const CUtensorMap& x_lo, const TcWgStripParams& p, int grid, int smem,
                               cudaStream_t s) {
-  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_wgrad_strip_kernel<CIN>, 227 * 1024));
-  conv_tc_wgrad_strip_kernel<CIN><<<grid, kThreads, smem, s>>>(d_hi, d_lo, x_hi, x_lo, p);
+  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_wgrad_strip_kernel<CIN, SUBW>, 227 * 1024));
+  conv_tc_wgrad_strip_kernel<CIN, SUBW><<<grid, kThreads, smem, s>>>(d_hi, d_lo, x_hi, x_lo, p);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }
@@ -3055,25 +3125,65 @@ static int conv_tc_wgrad_strip_run(const ConvGeom& g, const void* d_hi, const vo
   WgStripPlan pl;
   EVE_REQUIRE(wgrad_strip_geometry_ok(g) && wgrad_strip_plan(g, pl), EVE_ERR_SHAPE,
               "conv_tc_wgrad_strip: unsupported geometry");
+  const int subw = g.Cout == 32 ? 32 : 64;
+  const int xw = g.Cin > 64 ? 64 : g.Cin;
   TcWgStripParams p;
-  p.N = g.N; p.H = g.H; p.W = g.W; p.Wp = g.W + 2;
+  p.N = g.N; p.H = g.H; p.W = g.W; p.Wp = g.W + 2; p.Cin = g.Cin; p.Cout = g.Cout;
   p.R = pl.R; p.strips = pl.strips;
   p.items = g.N * pl.strips;
   p.ksteps = pl.ksteps;
-  p.dy_plane = pl.dy_plane; p.x_plane = pl.x_plane;
+  p.dy_plane = pl.dy_plane; p.x_chunk = pl.x_chunk;
   // every fp32 accumulation chain in TMEM stays below kWgradChainPixels pixels (round-toward-zero
   // accumulation: the error of a chain grows with its length)
   p.flush_items = std::max(1, kWgradChainPixels / (pl.R * g.W));
   p.part = part;
-  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  // jobs: per output-channel block, the M blocks in groups that fit TMEM (512 columns)
+  int boff[5], blbo[5], xoff[5], tap[5][4], nblk;
+  wgrad_strip_blocks(p.Wp, subw, boff, blbo, xoff, tap, nblk);
+  const int acc_cols = g.Cin <= 32 ? 2 * g.Cin : g.Cin;
+  const int per_job = std::min(nblk, 512 / acc_cols);
+  const int groups = cdiv(nblk, per_job);
+  p.njobs = 0;
+  p.period = 0;
+  for (int cb = 0; cb < g.Cout / subw; ++cb) {
+    for (int gr = 0; gr < groups; ++gr) {
+      // split as evenly as the block count allows, the larger groups last
+      const int lo = gr * nblk / groups, hi = (gr + 1) * nblk / groups;
+      WgStripJob& j = p.job[p.njobs];
+      j.co0 = cb * subw;
+      j.nblk = hi - lo;
+      for (int b = 0; b < 5; ++b) {
+        const int src = lo + b < hi ? lo + b : lo;
+        j.boff[b] = boff[src]; j.blbo[b] = blbo[src]; j.xoff[b] = xoff[src];
+        for (int q = 0; q < 4; ++q) j.tap[b][q] = lo + b < hi ? tap[src][q] : -1;
+      }
+      // CTAs in proportion to the M blocks of the job
+      for (int k = 0; k < j.nblk && p.period < 12; ++k) p.slotjob[p.period++] = p.njobs;
+      ++p.njobs;
+    }
+  }
+  EVE_REQUIRE(p.njobs >= 1 && p.njobs <= kWgMaxJobs && p.period >= 1, EVE_ERR_SHAPE,
+              "conv_tc_wgrad_strip: %d jobs", p.njobs);
+  const long long want = (long long)p.items * p.njobs;
+  const int grid = want < kNumSMs ? (int)want : kNumSMs;
+  if (p.njobs > 1)      // a CTA only writes its own job's region of its partial gradient
+    EVE_TRY(fill_zero(part, (long long)grid * g.Cout * g.K(), s));
   CUtensorMap md_hi, md_lo, mx_hi, mx_lo;
-  EVE_TRY(make_map_nhwc(&md_hi, d_hi, g.N, g.H, g.W, 64, 64, p.Wp, pl.R + 2, 1));
-  EVE_TRY(make_map_nhwc(&md_lo, d_lo, g.N, g.H, g.W, 64, 64, p.Wp, pl.R + 2, 1));
-  EVE_TRY(make_map_nhwc(&mx_hi, x_hi, g.N, g.H, g.W, g.Cin, g.Cin, p.Wp, pl.R, 1));
-  EVE_TRY(make_map_nhwc(&mx_lo, x_lo, g.N, g.H, g.W, g.Cin, g.Cin, p.Wp, pl.R, 1));
+  EVE_TRY(make_map_nhwc(&md_hi, d_hi, g.N, g.H, g.W, g.Cout, subw, p.Wp, pl.R + 2, 1));
+  EVE_TRY(make_map_nhwc(&md_lo, d_lo, g.N, g.H, g.W, g.Cout, subw, p.Wp, pl.R + 2, 1));
+  EVE_TRY(make_map_nhwc(&mx_hi, x_hi, g.N, g.H, g.W, g.Cin, xw, p.Wp, pl.R, 1));
+  EVE_TRY(make_map_nhwc(&mx_lo, x_lo, g.N, g.H, g.W, g.Cin, xw, p.Wp, pl.R, 1));
   *splits_out = grid;
-  return g.Cin == 64 ? launch_wgrad_strip<64>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s)
-                     : launch_wgrad_strip<32>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s);
+  const int key = g.Cin * 100 + subw;
+  switch (key) {
+    case 3264: return launch_wgrad_strip<32, 64>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s);
+    case 6464: return launch_wgrad_strip<64, 64>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s);
+    case 12864: return launch_wgrad_strip<128, 64>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s);
+    case 3232: return launch_wgrad_strip<32, 32>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s);
+    case 12832: return launch_wgrad_strip<128, 32>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s);
+  }
+  EVE_REQUIRE(false, EVE_ERR_SHAPE, "conv_tc_wgrad_strip: %d -> %d channels", g.Cin, g.Cout);
+  return EVE_ERR_SHAPE;
 }
 
 size_t conv_tc_wgrad_partial_floats(const ConvGeom& g) {

@@ -604,6 +604,35 @@ rowsum_kernel(const float* __restrict__ part, int rows, int C, float* __restrict
   }
 }
 
+// up to five such reductions (dgamma, dbeta, the second affine set's, the bias column sums) that
+// follow one in_bwd_fused launch, as ONE launch: blockIdx.y = job
+struct RowsumJobs {
+  int n;
+  const float* part[5];
+  int rows[5];
+  float* out[5];
+  float* out2[5];
+};
+__global__ void __launch_bounds__(256)
+rowsum_multi_kernel(const RowsumJobs jobs, int C, int accumulate) {
+  const int j = blockIdx.y;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  const float* part = jobs.part[j];
+  const int rows = jobs.rows[j];
+  double s = 0.0;
+  for (int rr = lane; rr < rows; rr += 32) s += (double)part[(size_t)rr * C + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    float* out = jobs.out[j];
+    float* out2 = jobs.out2[j];
+    if (out) out[c] = accumulate ? out[c] + (float)s : (float)s;
+    if (out2) out2[c] = accumulate ? out2[c] + (float)s : (float)s;
+  }
+}
+
 size_t fwd_smem(const FusedPlan& p, int tensors) {
   return (size_t)p.ppc * p.Q * 16 * tensors +
          (size_t)(kThr * 4 + 4 * 4 * kMaxQ + 4 * 4 * kMaxQ) * sizeof(float);
@@ -722,20 +751,23 @@ int in_bwd_fused(const float* dy, const float* dy2, const float* ymask, const fl
   if (dy2) EVE_TRY(launch_cluster(in_bwd_fused_kernel<true>, grid, p.CS, bwd_smem(p), a, s));
   else EVE_TRY(launch_cluster(in_bwd_fused_kernel<false>, grid, p.CS, bwd_smem(p), a, s));
   const int acc = accumulate ? 1 : 0;
+  RowsumJobs jobs;
+  jobs.n = 0;
+  auto add = [&](const float* part, int rows, float* out, float* out2) {
+    jobs.part[jobs.n] = part; jobs.rows[jobs.n] = rows; jobs.out[jobs.n] = out; jobs.out2[jobs.n] = out2;
+    ++jobs.n;
+  };
   if (affine) {
-    rowsum_kernel<<<cdiv(C, 8), 256, 0, s>>>(a.sum_gx, N, C, dgamma, nullptr, acc);
-    EVE_LAUNCH_CHECK();
-    rowsum_kernel<<<cdiv(C, 8), 256, 0, s>>>(a.sum_g, N, C, dbeta, nullptr, acc);
-    EVE_LAUNCH_CHECK();
+    add(a.sum_gx, N, dgamma, nullptr);
+    add(a.sum_g, N, dbeta, nullptr);
     if (dy2 && dgamma2) {
-      rowsum_kernel<<<cdiv(C, 8), 256, 0, s>>>(a.sum_gx2, N, C, dgamma2, nullptr, acc);
-      EVE_LAUNCH_CHECK();
-      rowsum_kernel<<<cdiv(C, 8), 256, 0, s>>>(a.sum_g2, N, C, dbeta2, nullptr, acc);
-      EVE_LAUNCH_CHECK();
+      add(a.sum_gx2, N, dgamma2, nullptr);
+      add(a.sum_g2, N, dbeta2, nullptr);
     }
   }
-  if (a.colpart) {
-    rowsum_kernel<<<cdiv(C, 8), 256, 0, s>>>(a.colpart, N * p.CS, C, dbias, dbias2, acc);
+  if (a.colpart) add(a.colpart, N * p.CS, dbias, dbias2);
+  if (jobs.n > 0) {
+    rowsum_multi_kernel<<<dim3(cdiv(C, 8), jobs.n), 256, 0, s>>>(jobs, C, acc);
     EVE_LAUNCH_CHECK();
   }
   return EVE_OK;

@@ -327,22 +327,38 @@ upsample_bwd_kernel(const float* __restrict__ dy, int lddy, int coff, long long 
   int ox_lo = max(0, (int)floorf(((float)w - 0.5f) / sw - 1.5f));
   int ox_hi = min(OW - 1, (int)ceilf(((float)w + 1.5f) / sw + 0.5f));
   float s[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-    int y0, y1;
-    float ly0, ly1;
-    bilinear_src(oy, sh, H, y0, y1, ly0, ly1);
-    float wy = (y0 == h ? ly0 : 0.f) + (y1 == h ? ly1 : 0.f);
-    if (wy == 0.f) continue;
-    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-      int x0, x1;
-      float lx0, lx1;
-      bilinear_src(ox, sw, W, x0, x1, lx0, lx1);
-      float wx = (x0 == w ? lx0 : 0.f) + (x1 == w ? lx1 : 0.f);
-      if (wx == 0.f) continue;
-      F4 d = ld4(dy + (((size_t)n * OH + oy) * OW + ox) * lddy + coff + c);
-      const float wt = wy * wx;
+  // horizontal weights of the candidate columns once per thread (not once per candidate pair);
+  // in chunks of kMaxCand columns (one chunk for every upscale factor below 5)
+  constexpr int kMaxCand = 12;
+  for (int xb = ox_lo; xb <= ox_hi; xb += kMaxCand) {
+    float wxs[kMaxCand];
+    const int nx = min(ox_hi - xb + 1, kMaxCand);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) s[j] = fmaf(wt, d.v[j], s[j]);
+    for (int k = 0; k < kMaxCand; ++k) {
+      wxs[k] = 0.f;
+      if (k < nx) {
+        int x0, x1;
+        float lx0, lx1;
+        bilinear_src(xb + k, sw, W, x0, x1, lx0, lx1);
+        wxs[k] = (x0 == w ? lx0 : 0.f) + (x1 == w ? lx1 : 0.f);
+      }
+    }
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      int y0, y1;
+      float ly0, ly1;
+      bilinear_src(oy, sh, H, y0, y1, ly0, ly1);
+      float wy = (y0 == h ? ly0 : 0.f) + (y1 == h ? ly1 : 0.f);
+      if (wy == 0.f) continue;
+      const float* row = dy + (((size_t)n * OH + oy) * OW + xb) * lddy + coff + c;
+#pragma unroll
+      for (int k = 0; k < kMaxCand; ++k) {
+        if (k < nx && wxs[k] != 0.f) {
+          F4 d = ld4(row + (size_t)k * lddy);
+          const float wt = wy * wxs[k];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s[j] = fmaf(wt, d.v[j], s[j]);
+        }
+      }
     }
   }
   *reinterpret_cast<float4*>(dx + i * 4) = make_float4(s[0], s[1], s[2], s[3]);

@@ -97,16 +97,20 @@ def test_padded_strip_kernel_matches_fp64(case, options):
     assert G.rel(got0, y) < 3e-5
 
 
-# padded-strip weight gradient (n, cin, h, w): Cout = 64; several strips per image with a ragged
-# last strip, one strip per image, more CTAs than items and many items per CTA (several flushes)
-WGRAD_STRIP_CASES = [(5, 64, 32, 32), (3, 64, 36, 64), (7, 32, 36, 64), (9, 64, 18, 32), (40, 64, 5, 8),
-                     (2, 32, 7, 10), (200, 64, 8, 8), (330, 64, 32, 32)]
+# padded-strip weight gradient (n, cin, cout, h, w): several strips per image with a ragged last
+# strip, one strip per image, more CTAs than items and many items per CTA (several flushes), every
+# template (64-wide tap pairs / 32-wide filter rows, stacked and 128-channel inputs) and multi-job
+# launches (128 output channels, 128 input channels)
+WGRAD_STRIP_CASES = [(5, 64, 64, 32, 32), (3, 64, 64, 36, 64), (7, 32, 64, 36, 64), (9, 64, 64, 18, 32),
+                     (40, 64, 64, 5, 8), (2, 32, 64, 7, 10), (200, 64, 64, 8, 8), (330, 64, 64, 32, 32),
+                     (6, 128, 128, 18, 32), (11, 128, 128, 16, 16), (5, 64, 128, 18, 32),
+                     (4, 128, 64, 9, 16), (3, 128, 32, 36, 64), (5, 32, 32, 36, 64), (150, 128, 128, 16, 16),
+                     (1, 128, 128, 5, 8)]
 
 
 @pytest.mark.parametrize('case', WGRAD_STRIP_CASES, ids=lambda c: 'x'.join(map(str, c)))
 def test_padded_strip_weight_gradient_matches_fp64(case, options):
-    n, cin, h, w = case
-    cout = 64
+    n, cin, cout, h, w = case
     g = torch.Generator().manual_seed(sum(case))
     x = torch.randn(n, cin, h, w, generator=g)
     wd = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).double().requires_grad_(True)
