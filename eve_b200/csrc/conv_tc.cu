@@ -555,23 +555,34 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const uint64_t desc0 = kmajor_desc(0u, KC);
     const uint64_t b_base = desc0 + (uint64_t)(smem_u32(wsm) >> 4);
     const uint32_t ring16 = smem_u32(ring) >> 4;
-    uint32_t g = 0, local = 0;
+    // ring position of entry g kept incrementally (slot, phase): no runtime division in the issue
+    // loop, and a staged row is waited for once, not by each of the three output rows that read it
+    uint32_t local = 0, sg = 0, pg = 0;
+    int confirmed = 0;              // entries g .. g + confirmed - 1 are known to have landed
+    auto advance = [&](uint32_t& sl, uint32_t& ph) {
+      if (++sl == (uint32_t)slots) {
+        sl = 0;
+        ph ^= 1u;
+      }
+    };
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int n = item / p.strips;
       const int h0 = (item - n * p.strips) * p.rows_per_strip;
       const int h1 = min(p.H, h0 + p.rows_per_strip);
-      for (int h = h0; h < h1; ++h, ++g, ++local) {
+      for (int h = h0; h < h1; ++h, ++local) {
         const uint32_t buf = local & 1;
         const uint32_t use = local >> 1;
         mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * kTmemCols;
+        uint32_t se = sg, pe = pg;
 #pragma unroll
         for (int r = 0; r < KS; ++r) {
-          const uint32_t e = g + (uint32_t)r;          // staged row h + r - halo
-          const uint32_t s = e % (uint32_t)slots;
-          mbar_wait(&full[s], (e / (uint32_t)slots) & 1);
-          tc_fence_after();
+          const uint32_t s = se;                       // staged row h + r - halo
+          if (r >= confirmed) {
+            mbar_wait(&full[s], pe);
+            tc_fence_after();
+          }
           if (elect_one()) {
             const uint64_t a_base = desc0 + (uint64_t)(ring16 + s * ((uint32_t)Cfg::kSlotBytes >> 4));
 #pragma unroll
@@ -597,22 +608,29 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               }
             }
             if (r == KS - 1) {
-              umma_commit(&empty[g % (uint32_t)slots]);     // row h - halo is not needed any more
+              umma_commit(&empty[sg]);                  // row h - halo is not needed any more
               umma_commit(&tmem_full[buf]);
             }
           }
           __syncwarp();
+          advance(se, pe);
         }
+        advance(sg, pg);
+        confirmed = KS - 1;
       }
       // end of the strip: the trailing halo rows (h1 - 1, h1) are released as well
       if (KS == 3) {
         if (elect_one()) {
-          umma_commit(&empty[g % (uint32_t)slots]);
-          umma_commit(&empty[(g + 1) % (uint32_t)slots]);
+          uint32_t s1 = sg, p1 = pg;
+          umma_commit(&empty[s1]);
+          advance(s1, p1);
+          umma_commit(&empty[s1]);
         }
         __syncwarp();
-        g += 2;
+        advance(sg, pg);
+        advance(sg, pg);
       }
+      confirmed = 0;
     }
   } else {
     // ===================== epilogue =====================
@@ -1832,13 +1850,22 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
     const uint64_t d_desc0 = mnmajor_desc(0u, (uint32_t)(COUT * 2), COUT);
     const uint64_t x_desc0 = mnmajor_desc(0u, (uint32_t)Cfg::kXRowBytes, CIN);
     const uint32_t ring16 = smem_u32(ring) >> 4;
-    uint32_t g = 0;
+    // ring position of entry g kept incrementally (no runtime division in the issue loop); a staged
+    // row is waited for once, not by each of the three x rows that read it
+    uint32_t sg = 0, pg = 0;
+    int confirmed = 0;
+    auto advance = [&](uint32_t& sl_, uint32_t& ph_) {
+      if (++sl_ == (uint32_t)slots) {
+        sl_ = 0;
+        ph_ ^= 1u;
+      }
+    };
     int row = 0;                 // rows accumulated so far by this CTA
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int n = item / p.strips;
       const int h0 = (item - n * p.strips) * p.rows_per_strip;
       const int h1 = min(p.H, h0 + p.rows_per_strip);
-      for (int h = h0; h < h1; ++h, ++g, ++row) {
+      for (int h = h0; h < h1; ++h, ++row) {
         // accumulation chains of kWgFlushRows rows alternate between the two accumulator sets
         const uint32_t chain = (uint32_t)(row / kWgFlushRows);
         const uint32_t set = chain & 1;
@@ -1849,11 +1876,14 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
           tc_fence_after();
         }
         uint32_t sl[KS];
+        {
+          uint32_t se = sg, pe = pg;
 #pragma unroll
-        for (int j = 0; j < KS; ++j) {
-          const uint32_t e = g + (uint32_t)j;
-          sl[j] = e % (uint32_t)slots;
-          mbar_wait(&full[sl[j]], (e / (uint32_t)slots) & 1);
+          for (int j = 0; j < KS; ++j) {
+            sl[j] = se;
+            if (j >= confirmed) mbar_wait(&full[se], pe);
+            advance(se, pe);
+          }
         }
         tc_fence_after();
         if (elect_one()) {
@@ -1889,15 +1919,21 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
           if (chain_end) umma_commit(&tmem_full[set]);
         }
         __syncwarp();
+        advance(sg, pg);
+        confirmed = KS - 1;
       }
       if (KS == 3) {
         if (elect_one()) {
-          umma_commit(&empty[g % (uint32_t)slots]);
-          umma_commit(&empty[(g + 1) % (uint32_t)slots]);
+          uint32_t s1 = sg, p1 = pg;
+          umma_commit(&empty[s1]);
+          advance(s1, p1);
+          umma_commit(&empty[s1]);
         }
         __syncwarp();
-        g += 2;
+        advance(sg, pg);
+        advance(sg, pg);
       }
+      confirmed = 0;
     }
   } else {
     // epilogue: drain each finished chain into this CTA's partial gradient (same thread, same
@@ -2204,6 +2240,32 @@ conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+}
+
+// multi-job launches: each CTA's partial only holds its job's (output block, taps) region.  Sum
+// every element over the CTAs of ITS job, in CTA order (deterministic), into one compact partial.
+struct WgCompactArgs {
+  int grid, period, slotjob[12];
+  int items;                 // CTAs of a job beyond its item count had nothing to do and wrote nothing
+  int subw, Cin;
+  int tapjob[4][9];          // job that owns (output-channel block, tap)
+};
+__global__ void __launch_bounds__(256)
+wgrad_strip_compact_kernel(const float* __restrict__ parts, float* __restrict__ out, long long full,
+                           const WgCompactArgs a) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= full) return;
+  const int co = (int)(e / (9 * a.Cin));
+  const int tap = (int)((e / a.Cin) % 9);
+  const int job = a.tapjob[co / a.subw][tap];
+  float acc = 0.f;
+  int rank = 0;
+  for (int z = 0; z < a.grid; ++z)
+    if (a.slotjob[z % a.period] == job) {
+      if (rank < a.items) acc += parts[(size_t)z * full + e];
+      ++rank;
+    }
+  out[e] = acc;
 }
 
 // ------------------------------------------------------------ operand preparation --
@@ -3166,24 +3228,46 @@ static int conv_tc_wgrad_strip_run(const ConvGeom& g, const void* d_hi, const vo
               "conv_tc_wgrad_strip: %d jobs", p.njobs);
   const long long want = (long long)p.items * p.njobs;
   const int grid = want < kNumSMs ? (int)want : kNumSMs;
-  if (p.njobs > 1)      // a CTA only writes its own job's region of its partial gradient
-    EVE_TRY(fill_zero(part, (long long)grid * g.Cout * g.K(), s));
+  if (grid < p.period) {       // few items: one CTA per job and item, dealt plainly round-robin
+    p.period = p.njobs;
+    for (int j = 0; j < p.njobs; ++j) p.slotjob[j] = j;
+  }
+  const size_t full = (size_t)g.Cout * g.K();
+  // multi-job launches: the CTAs' partials live behind slot 0, which receives the compacted sum
+  if (p.njobs > 1) p.part = part + full;
   CUtensorMap md_hi, md_lo, mx_hi, mx_lo;
   EVE_TRY(make_map_nhwc(&md_hi, d_hi, g.N, g.H, g.W, g.Cout, subw, p.Wp, pl.R + 2, 1));
   EVE_TRY(make_map_nhwc(&md_lo, d_lo, g.N, g.H, g.W, g.Cout, subw, p.Wp, pl.R + 2, 1));
   EVE_TRY(make_map_nhwc(&mx_hi, x_hi, g.N, g.H, g.W, g.Cin, xw, p.Wp, pl.R, 1));
   EVE_TRY(make_map_nhwc(&mx_lo, x_lo, g.N, g.H, g.W, g.Cin, xw, p.Wp, pl.R, 1));
-  *splits_out = grid;
+  *splits_out = p.njobs > 1 ? 1 : grid;
   const int key = g.Cin * 100 + subw;
+  int rc = EVE_ERR_SHAPE;
   switch (key) {
-    case 3264: return launch_wgrad_strip<32, 64>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s);
-    case 6464: return launch_wgrad_strip<64, 64>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s);
-    case 12864: return launch_wgrad_strip<128, 64>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s);
-    case 3232: return launch_wgrad_strip<32, 32>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s);
-    case 12832: return launch_wgrad_strip<128, 32>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s);
+    case 3264: rc = launch_wgrad_strip<32, 64>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s); break;
+    case 6464: rc = launch_wgrad_strip<64, 64>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s); break;
+    case 12864: rc = launch_wgrad_strip<128, 64>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s); break;
+    case 3232: rc = launch_wgrad_strip<32, 32>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s); break;
+    case 12832: rc = launch_wgrad_strip<128, 32>(md_hi, md_lo, mx_hi, mx_lo, p, grid, pl.smem, s); break;
+    default:
+      EVE_REQUIRE(false, EVE_ERR_SHAPE, "conv_tc_wgrad_strip: %d -> %d channels", g.Cin, g.Cout);
   }
-  EVE_REQUIRE(false, EVE_ERR_SHAPE, "conv_tc_wgrad_strip: %d -> %d channels", g.Cin, g.Cout);
-  return EVE_ERR_SHAPE;
+  EVE_TRY(rc);
+  if (p.njobs > 1) {
+    WgCompactArgs a;
+    a.grid = grid; a.period = p.period; a.items = p.items;
+    for (int i = 0; i < 12; ++i) a.slotjob[i] = i < p.period ? p.slotjob[i] : 0;
+    a.subw = subw; a.Cin = g.Cin;
+    for (int cb = 0; cb < 4; ++cb)
+      for (int t = 0; t < 9; ++t) a.tapjob[cb][t] = 0;
+    for (int j = 0; j < p.njobs; ++j)
+      for (int b = 0; b < p.job[j].nblk; ++b)
+        for (int q = 0; q < 4; ++q)
+          if (p.job[j].tap[b][q] >= 0) a.tapjob[p.job[j].co0 / subw][p.job[j].tap[b][q]] = j;
+    wgrad_strip_compact_kernel<<<cdiv((long long)full, 256), 256, 0, s>>>(p.part, part, (long long)full, a);
+    EVE_LAUNCH_CHECK();
+  }
+  return EVE_OK;
 }
 
 size_t conv_tc_wgrad_partial_floats(const ConvGeom& g) {
@@ -3193,7 +3277,7 @@ size_t conv_tc_wgrad_partial_floats(const ConvGeom& g) {
   wgrad_plan(g, p, mb, nb, sp, 3, 8);   // sized for the largest "tc_wgrad_waves" setting
   // the halo-row kernel writes one partial per CTA
   if (row_geometry_ok(g) && (g.Cout == 16 || g.Cout == 32)) sp = std::max(sp, kNumSMs);
-  if (wgrad_strip_geometry_ok(g)) sp = std::max(sp, kNumSMs);      // one partial per CTA as well
+  if (wgrad_strip_geometry_ok(g)) sp = std::max(sp, kNumSMs + 1);  // one partial per CTA (+ the compacted one)
   return (size_t)sp * g.Cout * g.K();
 }
 
