@@ -2245,10 +2245,10 @@ conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
 // multi-job launches: each CTA's partial only holds its job's (output block, taps) region.  Sum
 // every element over the CTAs of ITS job, in CTA order (deterministic), into one compact partial.
 struct WgCompactArgs {
-  int grid, period, slotjob[12];
-  int items;                 // CTAs of a job beyond its item count had nothing to do and wrote nothing
   int subw, Cin;
-  int tapjob[4][9];          // job that owns (output-channel block, tap)
+  int tapjob[4][9];                     // job that owns (output-channel block, tap)
+  int count[kWgMaxJobs];                // CTAs of each job that had items
+  unsigned char cta[kWgMaxJobs][160];   // their indices, ascending (the summation order)
 };
 __global__ void __launch_bounds__(256)
 wgrad_strip_compact_kernel(const float* __restrict__ parts, float* __restrict__ out, long long full,
@@ -2258,13 +2258,17 @@ wgrad_strip_compact_kernel(const float* __restrict__ parts, float* __restrict__ 
   const int co = (int)(e / (9 * a.Cin));
   const int tap = (int)((e / a.Cin) % 9);
   const int job = a.tapjob[co / a.subw][tap];
+  const int n = a.count[job];
   float acc = 0.f;
-  int rank = 0;
-  for (int z = 0; z < a.grid; ++z)
-    if (a.slotjob[z % a.period] == job) {
-      if (rank < a.items) acc += parts[(size_t)z * full + e];
-      ++rank;
-    }
+  int i = 0;
+  for (; i + 4 <= n; i += 4) {           // four independent loads in flight, fixed addition order
+    const float v0 = __ldg(parts + (size_t)a.cta[job][i] * full + e);
+    const float v1 = __ldg(parts + (size_t)a.cta[job][i + 1] * full + e);
+    const float v2 = __ldg(parts + (size_t)a.cta[job][i + 2] * full + e);
+    const float v3 = __ldg(parts + (size_t)a.cta[job][i + 3] * full + e);
+    acc = (((acc + v0) + v1) + v2) + v3;
+  }
+  for (; i < n; ++i) acc += __ldg(parts + (size_t)a.cta[job][i] * full + e);
   out[e] = acc;
 }
 
@@ -3255,15 +3259,21 @@ static int conv_tc_wgrad_strip_run(const ConvGeom& g, const void* d_hi, const vo
   EVE_TRY(rc);
   if (p.njobs > 1) {
     WgCompactArgs a;
-    a.grid = grid; a.period = p.period; a.items = p.items;
-    for (int i = 0; i < 12; ++i) a.slotjob[i] = i < p.period ? p.slotjob[i] : 0;
     a.subw = subw; a.Cin = g.Cin;
     for (int cb = 0; cb < 4; ++cb)
       for (int t = 0; t < 9; ++t) a.tapjob[cb][t] = 0;
+    for (int j = 0; j < kWgMaxJobs; ++j) a.count[j] = 0;
     for (int j = 0; j < p.njobs; ++j)
       for (int b = 0; b < p.job[j].nblk; ++b)
         for (int q = 0; q < 4; ++q)
           if (p.job[j].tap[b][q] >= 0) a.tapjob[p.job[j].co0 / subw][p.job[j].tap[b][q]] = j;
+    // CTAs of a job beyond its item count had nothing to do and wrote nothing
+    int rank[kWgMaxJobs] = {0, 0, 0, 0};
+    for (int z = 0; z < grid; ++z) {
+      const int j = p.slotjob[z % p.period];
+      if (rank[j] < p.items && a.count[j] < 160) a.cta[j][a.count[j]++] = (unsigned char)z;
+      ++rank[j];
+    }
     wgrad_strip_compact_kernel<<<cdiv((long long)full, 256), 256, 0, s>>>(p.part, part, (long long)full, a);
     EVE_LAUNCH_CHECK();
   }

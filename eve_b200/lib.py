@@ -75,6 +75,8 @@ SIGNATURES = {
     'eve_profile_read': (_I, [_I, _P, _P, _P, _P]),
     'eve_profile_dump': (C.c_longlong, [_P, C.c_longlong]),
     'eve_probe_mma_rate': (_I, [_I, _I, _I, _I, _I, _I, _P, _P]),
+    'eve_probe_mma_rate_swizzle': (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'eve_probe_mma_rate_issuers': (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'eve_set_conv_mode': (None, [_I]),
     'eve_get_conv_mode': (_I, []),
     'eve_set_option': (_I, [C.c_char_p, _I]),

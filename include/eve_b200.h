@@ -57,6 +57,16 @@ long long eve_profile_dump(char* buf, long long cap);
  * a_shift_bytes) and report their clock64 span in cycles_out[grid] (device memory). */
 int eve_probe_mma_rate(int n, int nmma, int reps, int a_shift_bytes, int distinct_a, int grid,
                        long long* cycles_out, eve_stream_t stream);
+/* the same with row_bytes = 128 / 64 / 32: SWIZZLE_128B / 64B / 32B operand rows (64 / 32 / 16
+ * channels per pixel row) */
+int eve_probe_mma_rate_swizzle(int n, int nmma, int reps, int a_shift_bytes, int distinct_a,
+                               int row_bytes, int grid, long long* cycles_out, eve_stream_t stream);
+/* the same with 1..4 warps issuing independent chains concurrently (each into its own accumulator
+ * columns); cycles_out is the span of warp 0, i.e. divide by nmma * reps for cycles per MMA of ONE
+ * chain while `issuers` chains run */
+int eve_probe_mma_rate_issuers(int n, int nmma, int reps, int a_shift_bytes, int distinct_a,
+                               int row_bytes, int issuers, int grid, long long* cycles_out,
+                               eve_stream_t stream);
 
 /* ------------------------------------------------------------------ building blocks --
  * Exposed so that each kernel family can be parity-tested on its own.  NHWC fp32. */

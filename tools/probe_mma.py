@@ -20,3 +20,22 @@ for grid in (148, 1):
             torch.cuda.synchronize()
             cyc = out[:grid].double().mean().item() / (nmma * reps)
             print('%4d %5d %6d %8d %10.2f %10.1f' % (n, grid, shift, distinct, cyc, n / 2))
+print()
+print('operand row width (swizzle mode), 148 CTAs, aligned start')
+print('%4s %10s %10s' % ('N', 'row bytes', 'cyc/mma'))
+for n in (16, 32, 64, 128):
+    for rb in (128, 64, 32):
+        nmma, reps = 96, 50
+        L.check(lib.eve_probe_mma_rate_swizzle(n, nmma, reps, 0, 1, rb, 148, L.ptr(out), L.stream_ptr()), 'probe')
+        torch.cuda.synchronize()
+        print('%4d %10d %10.2f' % (n, rb, out.double().mean().item() / (nmma * reps)))
+print()
+print('concurrent issuing warps (independent chains), 148 CTAs: cycles per MMA of one chain / aggregate')
+print('%4s %8s %10s %10s' % ('N', 'issuers', 'per chain', 'aggregate'))
+for n in (16, 32, 64, 128):
+    for iss in (1, 2, 4):
+        nmma, reps = 96, 50
+        L.check(lib.eve_probe_mma_rate_issuers(n, nmma, reps, 0, 1, 128, iss, 148, L.ptr(out), L.stream_ptr()), 'probe')
+        torch.cuda.synchronize()
+        c = out.double().mean().item() / (nmma * reps)
+        print('%4d %8d %10.2f %10.2f' % (n, iss, c, c / iss))
