@@ -43,6 +43,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrival that publishes nothing but "this thread's tcgen05.ld results are in registers": the
+// default .release form makes the thread wait until its earlier global stores are acknowledged
+// (measured on the halo-row kernel: ~500 cycles per output row between the last STG and the next
+// instruction), which the accumulator hand-back does not need.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -408,7 +415,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
       // all of this thread's TMEM reads have completed (tcgen05.wait::ld): release the buffer
       tc_fence_before();
-      mbar_arrive(&tmem_empty[buf]);
+      mbar_arrive_relaxed(&tmem_empty[buf]);
     }
   }
   tc_fence_before();
@@ -456,7 +463,8 @@ struct RowCfg {
   static constexpr int kTaps = KS * KS;                 // 3x3 or 1x1
   static constexpr int kHalo = KS / 2;
   static constexpr int kWeightBytes = (kTaps * kPlanes * kTapBytes + 1023) / 1024 * 1024;
-  static constexpr int kFixedBytes = kWeightBytes + 1024 + kBarrierBytes;
+  static constexpr int kStageBytes = 4 * 32 * BN * 4;   // epilogue transpose tiles: 4 warps x 32 pixels x BN floats
+  static constexpr int kFixedBytes = kWeightBytes + kStageBytes + 1024 + kBarrierBytes;
   static constexpr int kSlotsRaw = (227 * 1024 - kFixedBytes) / kSlotBytes;
   static constexpr int kSlots = kSlotsRaw > kMaxStages ? kMaxStages : kSlotsRaw;
   static constexpr int kAccCols = kStack ? 2 * BN : BN;
@@ -476,7 +484,8 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   uint8_t* wsm = smem;                                        // [taps][planes][kTapBytes]
-  uint8_t* ring = smem + Cfg::kWeightBytes;                   // [slots][planes][kRowBytes]
+  uint8_t* stage = smem + Cfg::kWeightBytes;                  // [4 epilogue warps][32 pixels][BN] fp32
+  uint8_t* ring = stage + Cfg::kStageBytes;                   // [slots][planes][kRowBytes]
   const int slots = p.slots;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)slots * Cfg::kSlotBytes);
   uint64_t* empty = full + slots;
@@ -557,33 +566,35 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const uint32_t ring16 = smem_u32(ring) >> 4;
     // ring position of entry g kept incrementally (slot, phase): no runtime division in the issue
     // loop, and a staged row is waited for once, not by each of the three output rows that read it
-    uint32_t local = 0, sg = 0, pg = 0;
-    int confirmed = 0;              // entries g .. g + confirmed - 1 are known to have landed
-    auto advance = [&](uint32_t& sl, uint32_t& ph) {
-      if (++sl == (uint32_t)slots) {
-        sl = 0;
-        ph ^= 1u;
-      }
-    };
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      const int n = item / p.strips;
-      const int h0 = (item - n * p.strips) * p.rows_per_strip;
-      const int h1 = min(p.H, h0 + p.rows_per_strip);
-      for (int h = h0; h < h1; ++h, ++local) {
-        const uint32_t buf = local & 1;
-        const uint32_t use = local >> 1;
-        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * kTmemCols;
-        uint32_t se = sg, pe = pg;
+    // One elected lane runs the whole loop (waits included): a per-row elect / reconverge pair
+    // around each batch of MMAs costs more issue slots than the MMAs themselves at 16 channels.
+    if (elect_one()) {
+      uint32_t local = 0, sg = 0, pg = 0;
+      int confirmed = 0;              // entries g .. g + confirmed - 1 are known to have landed
+      auto advance = [&](uint32_t& sl, uint32_t& ph) {
+        if (++sl == (uint32_t)slots) {
+          sl = 0;
+          ph ^= 1u;
+        }
+      };
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int n = item / p.strips;
+        const int h0 = (item - n * p.strips) * p.rows_per_strip;
+        const int h1 = min(p.H, h0 + p.rows_per_strip);
+        for (int h = h0; h < h1; ++h, ++local) {
+          const uint32_t buf = local & 1;
+          const uint32_t use = local >> 1;
+          mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * kTmemCols;
+          uint32_t se = sg, pe = pg;
 #pragma unroll
-        for (int r = 0; r < KS; ++r) {
-          const uint32_t s = se;                       // staged row h + r - halo
-          if (r >= confirmed) {
-            mbar_wait(&full[s], pe);
-            tc_fence_after();
-          }
-          if (elect_one()) {
+          for (int r = 0; r < KS; ++r) {
+            const uint32_t s = se;                       // staged row h + r - halo
+            if (r >= confirmed) {
+              mbar_wait(&full[s], pe);
+              tc_fence_after();
+            }
             const uint64_t a_base = desc0 + (uint64_t)(ring16 + s * ((uint32_t)Cfg::kSlotBytes >> 4));
 #pragma unroll
             for (int q = 0; q < KS; ++q) {
@@ -611,32 +622,45 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               umma_commit(&empty[sg]);                  // row h - halo is not needed any more
               umma_commit(&tmem_full[buf]);
             }
+            advance(se, pe);
           }
-          __syncwarp();
-          advance(se, pe);
+          advance(sg, pg);
+          confirmed = KS - 1;
         }
-        advance(sg, pg);
-        confirmed = KS - 1;
-      }
-      // end of the strip: the trailing halo rows (h1 - 1, h1) are released as well
-      if (KS == 3) {
-        if (elect_one()) {
-          uint32_t s1 = sg, p1 = pg;
-          umma_commit(&empty[s1]);
-          advance(s1, p1);
-          umma_commit(&empty[s1]);
+        // end of the strip: the trailing halo rows (h1 - 1, h1) are released as well
+        if (KS == 3) {
+          umma_commit(&empty[sg]);
+          advance(sg, pg);
+          umma_commit(&empty[sg]);
+          advance(sg, pg);
         }
-        __syncwarp();
-        advance(sg, pg);
-        advance(sg, pg);
+        confirmed = 0;
       }
-      confirmed = 0;
     }
   } else {
     // ===================== epilogue =====================
     const int quad = warp & 3;
     const int m = quad * 32 + lane;         // output pixel w = TMEM lane
-    constexpr int CW = BN < 32 ? BN : 32;
+    // A TMEM lane is one output pixel, so the accumulator registers of a thread are BN consecutive
+    // floats of ITS pixel: stored directly, every STG.128 of a warp touches 32 different sectors and
+    // half-fills each (measured: the L1 -> crossbar request path was the busiest unit of the kernel and
+    // the next row's instructions waited ~500 cycles for the store queue to read its registers).  The
+    // warp therefore transposes through a private shared-memory tile -- raw accumulators in, XOR-
+    // swizzled by pixel so that both sides are bank-conflict free -- and does bias / scale / residual
+    // and the store with lane-contiguous 16-byte pieces: 512 contiguous bytes per instruction.  The
+    // accumulator is handed back to the MMA warp as soon as it is in registers.
+    constexpr int RB = BN * 4;                    // bytes of one output pixel
+    constexpr int NCH = BN / 4;                   // 16-byte pieces per pixel == 512-byte passes per warp tile
+    uint8_t* tile = stage + (size_t)quad * (32 * RB);
+    auto swz = [](int px) { return BN == 16 ? ((px >> 1) & 3) : (px & 7); };
+    // coalesced side: pass i, lane l holds piece c_l of pixel px0 + i * ppi
+    constexpr int ppi = 512 / RB;                 // pixels per pass
+    const int c_l = lane % NCH;
+    const int px0 = lane / NCH;
+    float bias4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bias4[j] = p.bias ? __ldg(p.bias + c_l * 4 + j) : 0.f;
+    const float scale = p.out_scale;              // a power of two: fma(v, scale, bias) rounds once, as v * scale + bias did
     uint32_t local = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int n = item / p.strips;
@@ -645,12 +669,21 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       for (int h = h0; h < h1; ++h, ++local) {
         const uint32_t buf = local & 1;
         const uint32_t use = local >> 1;
-        const size_t row = ((size_t)(n * p.H + h) * kTileM + m) * BN;
+        // this warp's 32 pixels x BN floats are contiguous in NHWC
+        const size_t base = ((size_t)(n * p.H + h) * kTileM + quad * 32) * BN + (size_t)lane * 4;
+        // the residual addend does not depend on the accumulator: fetch it before waiting
+        float4 add4[NCH];
+        if (p.addend) {
+          const float4* a4 = reinterpret_cast<const float4*>(p.addend + base);
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) add4[i] = __ldg(a4 + i * 32);
+        }
         mbar_wait(&tmem_full[buf], use & 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * kTmemCols + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
+#pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
+          constexpr int CW = BN < 32 ? BN : 32;
           float v[32];
           tmem_ld32(tmem_d + (uint32_t)c0, v);
           if (Cfg::kStack) {
@@ -664,29 +697,33 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               for (int j = 0; j < 32; ++j) v[j] += u[j];
             }
           }
-          if (p.out_scale != 1.f) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] *= p.out_scale;
+          if (c0 + 32 >= BN) {
+            tc_fence_before();
+            mbar_arrive_relaxed(&tmem_empty[buf]);
           }
-          if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] += __ldg(p.bias + c0 + j);
+          for (int j = 0; j < CW / 4; ++j) {
+            const int c = c0 / 4 + j;
+            *reinterpret_cast<float4*>(tile + lane * RB + ((c ^ swz(lane)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
-          if (p.addend) {
-            const float4* a4 = reinterpret_cast<const float4*>(p.addend + row + c0);
-#pragma unroll
-            for (int j = 0; j < CW / 4; ++j) {
-              float4 a = __ldg(a4 + j);
-              v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
-            }
-          }
-          float4* o4 = reinterpret_cast<float4*>(p.out + row + c0);
-#pragma unroll
-          for (int j = 0; j < CW / 4; ++j)
-            o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        tc_fence_before();
-        mbar_arrive(&tmem_empty[buf]);
+        __syncwarp();
+        float4* o4 = reinterpret_cast<float4*>(p.out + base);
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const int px = px0 + i * ppi;
+          float4 a = *reinterpret_cast<const float4*>(tile + px * RB + ((c_l ^ swz(px)) << 4));
+          a.x = fmaf(a.x, scale, bias4[0]);
+          a.y = fmaf(a.y, scale, bias4[1]);
+          a.z = fmaf(a.z, scale, bias4[2]);
+          a.w = fmaf(a.w, scale, bias4[3]);
+          if (p.addend) {
+            a.x += add4[i].x; a.y += add4[i].y; a.z += add4[i].z; a.w += add4[i].w;
+          }
+          o4[i * 32] = a;
+        }
+        __syncwarp();          // the tile is rewritten by the next row
       }
     }
   }
@@ -950,7 +987,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[set]);
+      mbar_arrive_relaxed(&tmem_empty[set]);
     }
   }
   tc_fence_before();
@@ -1986,7 +2023,7 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[set]);
+      mbar_arrive_relaxed(&tmem_empty[set]);
     }
   }
   tc_fence_before();
@@ -2231,7 +2268,7 @@ conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
         }
       }
       tc_fence_before();
-      mbar_arrive(tmem_empty);
+      mbar_arrive_relaxed(tmem_empty);
     }
   }
   tc_fence_before();
