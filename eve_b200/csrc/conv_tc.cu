@@ -67,6 +67,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// explicit shared-space vector accesses (a pointer derived from the dynamic shared-memory base
+// compiles to generic LD / ST, which queue behind the global stores of the epilogue)
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -651,7 +666,7 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     // accumulator is handed back to the MMA warp as soon as it is in registers.
     constexpr int RB = BN * 4;                    // bytes of one output pixel
     constexpr int NCH = BN / 4;                   // 16-byte pieces per pixel == 512-byte passes per warp tile
-    uint8_t* tile = stage + (size_t)quad * (32 * RB);
+    const uint32_t tile = smem_u32(stage) + (uint32_t)quad * (32 * RB);
     auto swz = [](int px) { return BN == 16 ? ((px >> 1) & 3) : (px & 7); };
     // coalesced side: pass i, lane l holds piece c_l of pixel px0 + i * ppi
     constexpr int ppi = 512 / RB;                 // pixels per pass
@@ -704,8 +719,8 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 #pragma unroll
           for (int j = 0; j < CW / 4; ++j) {
             const int c = c0 / 4 + j;
-            *reinterpret_cast<float4*>(tile + lane * RB + ((c ^ swz(lane)) << 4)) =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            sts128(tile + (uint32_t)(lane * RB + ((c ^ swz(lane)) << 4)),
+                   make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
           }
         }
         __syncwarp();
@@ -713,7 +728,7 @@ conv_tc_row_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
           const int px = px0 + i * ppi;
-          float4 a = *reinterpret_cast<const float4*>(tile + px * RB + ((c_l ^ swz(px)) << 4));
+          float4 a = lds128(tile + (uint32_t)(px * RB + ((c_l ^ swz(px)) << 4)));
           a.x = fmaf(a.x, scale, bias4[0]);
           a.y = fmaf(a.y, scale, bias4[1]);
           a.z = fmaf(a.z, scale, bias4[2]);
@@ -1889,41 +1904,42 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
     const uint32_t ring16 = smem_u32(ring) >> 4;
     // ring position of entry g kept incrementally (no runtime division in the issue loop); a staged
     // row is waited for once, not by each of the three x rows that read it
-    uint32_t sg = 0, pg = 0;
-    int confirmed = 0;
-    auto advance = [&](uint32_t& sl_, uint32_t& ph_) {
-      if (++sl_ == (uint32_t)slots) {
-        sl_ = 0;
-        ph_ ^= 1u;
-      }
-    };
-    int row = 0;                 // rows accumulated so far by this CTA
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      const int n = item / p.strips;
-      const int h0 = (item - n * p.strips) * p.rows_per_strip;
-      const int h1 = min(p.H, h0 + p.rows_per_strip);
-      for (int h = h0; h < h1; ++h, ++row) {
-        // accumulation chains of kWgFlushRows rows alternate between the two accumulator sets
-        const uint32_t chain = (uint32_t)(row / kWgFlushRows);
-        const uint32_t set = chain & 1;
-        const bool chain_start = row % kWgFlushRows == 0;
-        const bool chain_end = row % kWgFlushRows == kWgFlushRows - 1 || row == total_rows - 1;
-        if (chain_start) {
-          mbar_wait(&tmem_empty[set], ((chain >> 1) & 1) ^ 1);   // the epilogue drained this set
-          tc_fence_after();
+    // one elected lane runs the whole loop, waits included (see conv_tc_row_kernel)
+    if (elect_one()) {
+      uint32_t sg = 0, pg = 0;
+      int confirmed = 0;
+      auto advance = [&](uint32_t& sl_, uint32_t& ph_) {
+        if (++sl_ == (uint32_t)slots) {
+          sl_ = 0;
+          ph_ ^= 1u;
         }
-        uint32_t sl[KS];
-        {
-          uint32_t se = sg, pe = pg;
-#pragma unroll
-          for (int j = 0; j < KS; ++j) {
-            sl[j] = se;
-            if (j >= confirmed) mbar_wait(&full[se], pe);
-            advance(se, pe);
+      };
+      int row = 0;                 // rows accumulated so far by this CTA
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int n = item / p.strips;
+        const int h0 = (item - n * p.strips) * p.rows_per_strip;
+        const int h1 = min(p.H, h0 + p.rows_per_strip);
+        for (int h = h0; h < h1; ++h, ++row) {
+          // accumulation chains of kWgFlushRows rows alternate between the two accumulator sets
+          const uint32_t chain = (uint32_t)(row / kWgFlushRows);
+          const uint32_t set = chain & 1;
+          const bool chain_start = row % kWgFlushRows == 0;
+          const bool chain_end = row % kWgFlushRows == kWgFlushRows - 1 || row == total_rows - 1;
+          if (chain_start) {
+            mbar_wait(&tmem_empty[set], ((chain >> 1) & 1) ^ 1);   // the epilogue drained this set
+            tc_fence_after();
           }
-        }
-        tc_fence_after();
-        if (elect_one()) {
+          uint32_t sl[KS];
+          {
+            uint32_t se = sg, pe = pg;
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+              sl[j] = se;
+              if (j >= confirmed) mbar_wait(&full[se], pe);
+              advance(se, pe);
+            }
+          }
+          tc_fence_after();
           const uint32_t acc0 = chain_start ? 0u : 1u;
           const uint64_t xb = x_desc0 + (uint64_t)(ring16 + sl[kHalo] * kSlot16 + kPlanes * kDRow16);
 #pragma unroll
@@ -1954,23 +1970,17 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
           }
           umma_commit(&empty[sl[0]]);
           if (chain_end) umma_commit(&tmem_full[set]);
+          advance(sg, pg);
+          confirmed = KS - 1;
         }
-        __syncwarp();
-        advance(sg, pg);
-        confirmed = KS - 1;
-      }
-      if (KS == 3) {
-        if (elect_one()) {
-          uint32_t s1 = sg, p1 = pg;
-          umma_commit(&empty[s1]);
-          advance(s1, p1);
-          umma_commit(&empty[s1]);
+        if (KS == 3) {
+          umma_commit(&empty[sg]);
+          advance(sg, pg);
+          umma_commit(&empty[sg]);
+          advance(sg, pg);
         }
-        __syncwarp();
-        advance(sg, pg);
-        advance(sg, pg);
+        confirmed = 0;
       }
-      confirmed = 0;
     }
   } else {
     // epilogue: drain each finished chain into this CTA's partial gradient (same thread, same
