@@ -85,6 +85,7 @@ __device__ __forceinline__ void split4(const float* o, uint2& hi, uint2& lo) {
 // bit-identical whatever batch it is processed in.
 struct FusedPlan {
   int CG, Q, CS, ppc;
+  bool one_cta;        // the staged form takes more than half an SM's shared memory
 };
 int max_cluster() {           // tuning knob (environment, read once)
   static int v = 0;
@@ -120,6 +121,7 @@ bool plan_fused(int C, int HW, int tensors, FusedPlan& p) {
       for (int CS = 1; CS <= maxcs && CS <= HW; CS <<= 1)
         if (bytes(CG, CS) <= budget) {
           p.CG = CG; p.Q = CG / 4; p.CS = CS; p.ppc = cdiv(HW, CS);
+          p.one_cta = (stage & 1) != 0;
           return true;
         }
     }
@@ -547,6 +549,204 @@ in_bwd_fused_kernel(const InBwdArgs a) {
   cluster.sync();
 }
 
+// ---- streaming variant ---------------------------------------------------------------------
+// Large maps (RefineNet level 0 / 1: 9216 and 2304 pixels) do not fit a cluster's shared memory
+// unless every CTA takes ~150 KB, i.e. ONE CTA per SM whose load, reduce, cluster-sync and store
+// phases run back to back with nothing else to hide them (measured: 28 % of the DRAM peak).  This
+// variant keeps the work split (cluster = one image x channel group, fixed-order DSMEM reduction,
+// same arithmetic per element) but stages nothing: phase 1 streams dy and x from HBM through
+// registers, phase 2 reads them AGAIN -- the cluster touched them microseconds ago and the ~20
+// clusters in flight hold ~25 MB, so the second read is served by the 126 MB L2 -- and recomputes
+// g / xhat instead of loading them from shared memory.  With ~27 KB of reduction scratch per CTA
+// two CTAs share an SM and one cluster's stores overlap another's loads.
+template <bool DUAL>
+struct BwdElem {
+  float xh[4], g[4], G[4];
+};
+
+template <bool DUAL>
+__device__ __forceinline__ void bwd_elem(const float4 d4, const float4 x4, const float4 y4,
+                                         const bool has_mask, const float4 e4, const float* m,
+                                         const float* r, const float* ga, const float* be,
+                                         const float* ga2, const float* be2, const float slope,
+                                         BwdElem<DUAL>& o, float* g2) {
+  const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+  const float yv[4] = {y4.x, y4.y, y4.z, y4.w}, ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    o.xh[j] = (xv[j] - m[j]) * r[j];
+    const float pre = has_mask ? yv[j] : fmaf(o.xh[j], ga[j], be[j]);
+    o.g[j] = dv[j] * act_deriv(pre, slope);
+    o.G[j] = ga[j] * o.g[j];
+    if (DUAL) {
+      g2[j] = ev[j] * act_deriv(fmaf(o.xh[j], ga2[j], be2[j]), slope);
+      o.G[j] = fmaf(ga2[j], g2[j], o.G[j]);
+    }
+  }
+}
+
+template <bool DUAL>
+__global__ void __launch_bounds__(kThr, 2)
+in_bwd_stream_kernel(const InBwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = blockIdx.x, cgi = blockIdx.y, n = blockIdx.z;
+  const int Q = a.Q, C4 = a.C >> 2;
+  const int p0 = rank * a.ppc;
+  const int np = max(0, min(a.HW, p0 + a.ppc) - p0);
+  double* wred = reinterpret_cast<double*>(smraw);                // [kThr*4]
+  double* cpart = wred + kThr * 4;                                // [4 sums][4*kMaxQ]
+  float* tot = reinterpret_cast<float*>(cpart + 4 * 4 * kMaxQ);   // A, B: [2][4*kMaxQ]
+  constexpr int kS = 4 * kMaxQ;
+
+  const int L = kThr / Q;
+  const int q = threadIdx.x % Q, lane = threadIdx.x / Q;
+  const bool active = lane < L;
+  const size_t step_g = (size_t)L * C4;
+  const size_t goff = ((size_t)n * a.HW + p0 + lane) * C4 + (size_t)cgi * Q + q;
+  const int c = (cgi * Q + q) * 4;
+  const float slope = a.slope;
+  const float4* gd = reinterpret_cast<const float4*>(a.dy);
+  const float4* gx = reinterpret_cast<const float4*>(a.x);
+  const float4* gy = reinterpret_cast<const float4*>(a.ymask);
+  const float4* ge = reinterpret_cast<const float4*>(a.dy2);
+  const bool has_mask = a.ymask != nullptr;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float m[4] = {0, 0, 0, 0}, r[4] = {0, 0, 0, 0};
+  float ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+  float ga2[4] = {0.f, 0.f, 0.f, 0.f}, be2[4] = {0.f, 0.f, 0.f, 0.f};
+  float f_g[4] = {0, 0, 0, 0}, f_gx[4] = {0, 0, 0, 0}, f_g2[4] = {0, 0, 0, 0}, f_gx2[4] = {0, 0, 0, 0};
+  if (active) {
+    const size_t so = (size_t)n * a.C + c;
+    const float4 m4 = *reinterpret_cast<const float4*>(a.mean + so);
+    const float4 r4 = *reinterpret_cast<const float4*>(a.rstd + so);
+    m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
+    r[0] = r4.x; r[1] = r4.y; r[2] = r4.z; r[3] = r4.w;
+    if (a.gamma) {
+      const float4 g4 = *reinterpret_cast<const float4*>(a.gamma + c);
+      const float4 b4 = *reinterpret_cast<const float4*>(a.beta + c);
+      ga[0] = g4.x; ga[1] = g4.y; ga[2] = g4.z; ga[3] = g4.w;
+      be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
+    }
+    if (DUAL) {
+      const float4 g4 = *reinterpret_cast<const float4*>(a.gamma2 + c);
+      const float4 b4 = *reinterpret_cast<const float4*>(a.beta2 + c);
+      ga2[0] = g4.x; ga2[1] = g4.y; ga2[2] = g4.z; ga2[3] = g4.w;
+      be2[0] = b4.x; be2[1] = b4.y; be2[2] = b4.z; be2[3] = b4.w;
+    }
+    // ---- phase 1: the sums (fp32 per thread over its few pixels, fp64 across threads and CTAs,
+    // exactly as the staged kernel)
+    const bool has_gout = a.g_out != nullptr;
+    size_t go = goff;
+#pragma unroll (DUAL ? 1 : 4)
+    for (int p = lane; p < np; p += L, go += step_g) {
+      const float4 d4 = __ldg(gd + go), x4 = __ldg(gx + go);
+      const float4 y4 = has_mask ? __ldg(gy + go) : z4;
+      const float4 e4 = DUAL ? __ldg(ge + go) : z4;
+      BwdElem<DUAL> o;
+      float g2[4] = {0.f, 0.f, 0.f, 0.f};
+      bwd_elem<DUAL>(d4, x4, y4, has_mask, e4, m, r, ga, be, ga2, be2, slope, o, g2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f_g[j] += o.g[j];
+        f_gx[j] = fmaf(o.g[j], o.xh[j], f_gx[j]);
+        if (DUAL) {
+          f_g2[j] += g2[j];
+          f_gx2[j] = fmaf(g2[j], o.xh[j], f_gx2[j]);
+        }
+      }
+      if (has_gout)
+        reinterpret_cast<float4*>(a.g_out)[go] = make_float4(o.g[0], o.g[1], o.g[2], o.g[3]);
+    }
+  }
+  {
+    double t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = (double)f_g[j];
+    quad_reduce<double>(t, Q, L, wred, cpart);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = (double)f_gx[j];
+    quad_reduce<double>(t, Q, L, wred, cpart + kS);
+    if (DUAL) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = (double)f_g2[j];
+      quad_reduce<double>(t, Q, L, wred, cpart + 2 * kS);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = (double)f_gx2[j];
+      quad_reduce<double>(t, Q, L, wred, cpart + 3 * kS);
+    }
+  }
+  cluster.sync();
+  if (threadIdx.x < Q * 4) {
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    constexpr int nsum = DUAL ? 4 : 2;
+    for (int rk = 0; rk < a.CS; ++rk) {
+      const double* rp = cluster.map_shared_rank(cpart, rk);
+#pragma unroll
+      for (int k = 0; k < nsum; ++k) t[k] += rp[k * kS + threadIdx.x];
+    }
+    const int ch = cgi * Q * 4 + threadIdx.x;
+    const double g1 = a.gamma ? (double)a.gamma[ch] : 1.0;
+    const double g2 = DUAL ? (double)a.gamma2[ch] : 0.0;
+    const double inv = 1.0 / (double)a.HW;
+    tot[threadIdx.x] = (float)((g1 * t[0] + g2 * t[2]) * inv);
+    tot[kS + threadIdx.x] = (float)((g1 * t[1] + g2 * t[3]) * inv);
+    if (rank == 0 && a.sum_g) {
+      const size_t o = (size_t)n * a.C + ch;
+      a.sum_g[o] = (float)t[0];
+      a.sum_gx[o] = (float)t[1];
+      if (DUAL && a.sum_g2) {
+        a.sum_g2[o] = (float)t[2];
+        a.sum_gx2[o] = (float)t[3];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: dx from a second read of dy / x (L2)
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    const float4 A4 = reinterpret_cast<const float4*>(tot)[q];
+    const float4 B4 = reinterpret_cast<const float4*>(tot + kS)[q];
+    const float A[4] = {A4.x, A4.y, A4.z, A4.w}, B[4] = {B4.x, B4.y, B4.z, B4.w};
+    const bool has_add = a.addend != nullptr, has_dx = a.dx != nullptr, has_pl = a.dx_hi != nullptr;
+    size_t go = goff;
+#pragma unroll (DUAL ? 1 : 4)
+    for (int p = lane; p < np; p += L, go += step_g) {
+      const float4 d4 = __ldg(gd + go), x4 = __ldg(gx + go);
+      const float4 y4 = has_mask ? __ldg(gy + go) : z4;
+      const float4 e4 = DUAL ? __ldg(ge + go) : z4;
+      const float4 t4 = has_add ? __ldg(reinterpret_cast<const float4*>(a.addend) + go) : z4;
+      BwdElem<DUAL> e;
+      float g2[4];
+      bwd_elem<DUAL>(d4, x4, y4, has_mask, e4, m, r, ga, be, ga2, be2, slope, e, g2);
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = r[j] * (e.G[j] - A[j] - e.xh[j] * B[j]);
+      if (has_add) {
+        o[0] += t4.x; o[1] += t4.y; o[2] += t4.z; o[3] += t4.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cs[j] += o[j];
+      if (has_dx) reinterpret_cast<float4*>(a.dx)[go] = make_float4(o[0], o[1], o[2], o[3]);
+      if (has_pl) {
+        uint2 h, l;
+        split4<TC_BF16>(o, h, l);
+        reinterpret_cast<uint2*>(a.dx_hi)[go] = h;
+        reinterpret_cast<uint2*>(a.dx_lo)[go] = l;
+      }
+    }
+  }
+  if (a.colpart) {
+    float* fred = reinterpret_cast<float*>(wred);
+    float* fout = fred + kThr * 4;
+    quad_reduce<float>(cs, Q, L, fred, fout);
+    if (threadIdx.x < Q * 4)
+      a.colpart[((size_t)n * a.CS + rank) * a.C + cgi * Q * 4 + threadIdx.x] = fout[threadIdx.x];
+  }
+  cluster.sync();
+}
+
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
@@ -748,8 +948,18 @@ int in_bwd_fused(const float* dy, const float* dy2, const float* ymask, const fl
   a.sum_gx2 = affine && dy2 ? scratch + 3 * nc : nullptr;
   a.colpart = (dbias || dbias2) ? scratch + 4 * nc : nullptr;
   dim3 grid(p.CS, C / p.CG, N);
-  if (dy2) EVE_TRY(launch_cluster(in_bwd_fused_kernel<true>, grid, p.CS, bwd_smem(p), a, s));
-  else EVE_TRY(launch_cluster(in_bwd_fused_kernel<false>, grid, p.CS, bwd_smem(p), a, s));
+  // the streaming form reads dy / x / ymask / dy2 twice: not when g_out overwrites one of them
+  const bool inplace = g_out && (g_out == dy || g_out == dy2 || g_out == ymask || g_out == x);
+  const int sopt = get_option(OPT_IN_STREAM);
+  if (!inplace && (sopt == 2 || (sopt == 1 && p.one_cta))) {
+    const size_t smem = (size_t)(kThr * 4 + 4 * 4 * kMaxQ) * sizeof(double) + 2 * 4 * kMaxQ * sizeof(float);
+    if (dy2) EVE_TRY(launch_cluster(in_bwd_stream_kernel<true>, grid, p.CS, smem, a, s));
+    else EVE_TRY(launch_cluster(in_bwd_stream_kernel<false>, grid, p.CS, smem, a, s));
+  } else if (dy2) {
+    EVE_TRY(launch_cluster(in_bwd_fused_kernel<true>, grid, p.CS, bwd_smem(p), a, s));
+  } else {
+    EVE_TRY(launch_cluster(in_bwd_fused_kernel<false>, grid, p.CS, bwd_smem(p), a, s));
+  }
   const int acc = accumulate ? 1 : 0;
   RowsumJobs jobs;
   jobs.n = 0;

@@ -112,6 +112,10 @@ int eve_get_conv_mode(void);
  *                                per sequence (x halves of the gate convolutions batched over
  *                                time, recurrence in shared memory / TMEM); 0 = one convolution
  *                                launch pair per time step
+ *   "in_stream"           0..2   InstanceNorm backward without shared-memory staging (second read of
+ *                                dy / x served by L2, two CTAs per SM): 0 = never, 1 = for maps whose
+ *                                staged form needs one CTA per SM, 2 = always (default: measured
+ *                                fastest inside the training step, where dy is usually still in L2)
  * Unknown names / out-of-range values return EVE_ERR_CONFIG. */
 int eve_set_option(const char* name, int value);
 int eve_get_option(const char* name, int* value);

@@ -94,11 +94,24 @@ def test_forward_block_end_with_residual(shape, mode):
         assert G.rel(st[2], r.double().mean(dim=(2, 3))) < 1e-6
 
 
+@pytest.fixture()
+def in_stream():
+    """Sets the `in_stream` switch (0 staged in shared memory, 1 automatic, 2 streaming: second read
+    of dy / x from L2) for one test and restores it."""
+    L.load()
+    saved = L.get_option('in_stream')
+    yield lambda v: L.set_option('in_stream', v)
+    L.set_option('in_stream', saved)
+
+
 @pytest.mark.parametrize('shape', SHAPES, ids=lambda s: 'x'.join(map(str, s)))
 @pytest.mark.parametrize('dual', [False, True])
-def test_backward_all_outputs(shape, dual):
-    """dx (+ addend) in fp32 and as bf16 planes, affine gradients of both sets, bias gradient."""
+@pytest.mark.parametrize('stream', [0, 1, 2])
+def test_backward_all_outputs(shape, dual, stream, in_stream):
+    """dx (+ addend) in fp32 and as bf16 planes, affine gradients of both sets, bias gradient;
+    the staged and the streaming kernel both against fp64."""
     lib = L.load()
+    in_stream(stream)
     n, c, h, w = shape
     act = 2
     g = torch.Generator().manual_seed(23 + c + h)
@@ -143,11 +156,14 @@ def test_backward_all_outputs(shape, dual):
     assert G.rel(dbias, want_dx.sum(dim=(0, 2, 3))) < 2e-5
 
 
-@pytest.mark.parametrize('shape', [(3, 64, 32, 32), (5, 512, 4, 4)], ids=lambda s: 'x'.join(map(str, s)))
-def test_backward_block_end_mask_from_saved_output(shape):
+@pytest.mark.parametrize('shape', [(3, 64, 32, 32), (5, 512, 4, 4), (1, 64, 72, 128)],
+                         ids=lambda s: 'x'.join(map(str, s)))
+@pytest.mark.parametrize('stream', [0, 2])
+def test_backward_block_end_mask_from_saved_output(shape, stream, in_stream):
     """out = relu(IN(b) + skip): act' from the saved output, g_out = dy * relu'(out) (the
     gradient of the skip branch), dx through the non-affine norm as bf16 planes only."""
     lib = L.load()
+    in_stream(stream)
     n, c, h, w = shape
     g = torch.Generator().manual_seed(31 + c)
     b = torch.randn(shape, generator=g)
@@ -194,3 +210,42 @@ def test_statistics_do_not_depend_on_the_batch():
     torch.cuda.synchronize()
     assert torch.equal(outs[0][0][2:3], outs[1][0])
     assert torch.equal(outs[0][1][2:3], outs[1][1]) and torch.equal(outs[0][2][2:3], outs[1][2])
+
+
+@pytest.mark.parametrize('dual', [False, True])
+def test_streaming_backward_agrees_with_the_staged_kernel(dual, in_stream):
+    """The streaming kernel performs the same arithmetic per element and the same fixed-order
+    reductions as the staged one; only where the second read comes from differs (and how the
+    compiler contracts multiply-adds: agreement to a few ulp, not bit-identity)."""
+    lib = L.load()
+    n, c, h, w = 3, 32, 72, 128
+    g = torch.Generator().manual_seed(5)
+    x = G.nhwc((torch.randn(n, c, h, w, generator=g) * 1.5 + 0.5).cuda())
+    dy, dy2 = (G.nhwc(torch.randn(n, c, h, w, generator=g).cuda()) for _ in range(2))
+    add = G.nhwc(torch.randn(n, c, h, w, generator=g).cuda())
+    ga, ba, gb, bb = (torch.randn(c, generator=g).cuda() for _ in range(4))
+    mean = x.mean(dim=(1, 2)).contiguous()
+    rstd = (1.0 / torch.sqrt(x.var(dim=(1, 2), unbiased=False) + 1e-5)).contiguous()
+    res = []
+    for mode in (0, 2):
+        in_stream(mode)
+        dx = torch.empty_like(x)
+        hi, lo = _u16(x.shape), _u16(x.shape)
+        outs = [torch.empty(c, device='cuda') for _ in range(5)]
+        ws = torch.empty(lib.eve_instnorm_fused_workspace_bytes(n, h * w, c), dtype=torch.uint8,
+                         device='cuda')
+        L.check(lib.eve_instnorm_fused_bwd(
+            L.ptr(dy), L.ptr(dy2) if dual else None, None, L.ptr(x), n, h * w, c, L.ptr(mean),
+            L.ptr(rstd), L.ptr(ga), L.ptr(ba), L.ptr(gb) if dual else None,
+            L.ptr(bb) if dual else None, 2, L.ptr(add), L.ptr(dx), L.ptr(hi), L.ptr(lo), None,
+            L.ptr(outs[0]), L.ptr(outs[1]), L.ptr(outs[2]) if dual else None,
+            L.ptr(outs[3]) if dual else None, L.ptr(outs[4]), L.ptr(ws), ws.numel(),
+            L.stream_ptr()), 'fused_bwd')
+        torch.cuda.synchronize()
+        res.append([dx, hi, lo, outs[0], outs[1], outs[4]] + (outs[2:4] if dual else []))
+    for a, b in zip(*res):
+        if a.dtype == torch.int16:      # bf16 planes: identical up to the rounding of a last-ulp difference
+            a, b = a.view(torch.bfloat16).float(), b.view(torch.bfloat16).float()
+            assert float((a - b).abs().max()) <= 2.0 ** -7 * float(b.abs().max())
+        else:
+            assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max())

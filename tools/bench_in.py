@@ -44,6 +44,8 @@ if os.environ.get('BENCH_IN_SHAPES'):
 
 def main(which):
     s = L.stream_ptr()
+    if os.environ.get('BENCH_IN_STREAM'):
+        L.set_option('in_stream', int(os.environ['BENCH_IN_STREAM']))
     chunk_mb = float(os.environ.get('BENCH_IN_CHUNK_MB', '0'))
     print('%-18s %10s %10s %10s %10s %12s %8s' % ('shape', 'fused ms', 'GB/s', 'legacy ms', 'GB/s',
                                                    'chunked ms', 'GB/s'))
