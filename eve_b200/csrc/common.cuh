@@ -291,7 +291,9 @@ int in_bwd_fused(const float* dy, const float* dy2, const float* ymask, const fl
                  const float* beta, const float* gamma2, const float* beta2, int act,
                  const float* addend, float* dx, void* dx_hi, void* dx_lo, float* g_out,
                  float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, float* dbias,
-                 float* dbias2, bool accumulate, float* scratch, cudaStream_t s);
+                 float* dbias2, bool accumulate, float* scratch, cudaStream_t s,
+                 void* ya_hi = nullptr, void* ya_lo = nullptr, void* yb_hi = nullptr,
+                 void* yb_lo = nullptr);
 // dy -> bf16 hi/lo planes and (dbias != null) dbias (+)= column sums, one read of dy
 size_t split_colsum_scratch_floats(long long rows, int C);
 int split_colsum(const float* dy, long long rows, int C, void* hi, void* lo, float* dbias,

@@ -366,14 +366,17 @@ extern "C" int eve_eyenet_cnn_bwd(const eve_eyenet_cnn_params* p, const float* d
       EVE_TRY(in_bwd_fused(dout, nullptr, k.out, k.b, N, HW, C, k.bm, k.br, nullptr, nullptr, nullptr,
                            nullptr, ACT_RELU, nullptr, nullptr, sc.DB.hi, sc.DB.lo, gskip, nullptr,
                            nullptr, nullptr, nullptr, nullptr, nullptr, false, sc.col, s));
-      EVE_TRY(in_apply_planes2(k.a, N, HW, C, k.am, k.ar, nullptr, nullptr, nullptr, nullptr, ACT_RELU,
-                               TC_BF16, sc.XP.hi, sc.XP.lo, nullptr, nullptr, s));
-      EVE_TRY(conv_bwd_planes(k.g2, sc.XP.hi, sc.XP.lo, sc.DB.hi, sc.DB.lo, w[slot + 1], gr[slot + 1],
-                              acc, nullptr, sc.t2, sc.cs, s));
-      // y = relu(IN(a)): da as the dy planes of conv1
+      // conv2: data gradient first; the weight gradient's x operand relu(IN(a)) comes out of the
+      // norm's backward kernel (it computes xhat anyway), not out of a separate pass over a
+      EVE_TRY(conv_bwd_planes(k.g2, nullptr, nullptr, sc.DB.hi, sc.DB.lo, w[slot + 1], nullptr, acc,
+                              nullptr, sc.t2, sc.cs, s));
+      // y = relu(IN(a)): da as the dy planes of conv1, y as the x planes of conv2's weight gradient
       EVE_TRY(in_bwd_fused(sc.t2, nullptr, nullptr, k.a, N, HW, C, k.am, k.ar, nullptr, nullptr,
                            nullptr, nullptr, ACT_RELU, nullptr, nullptr, sc.DA.hi, sc.DA.lo, nullptr,
-                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false, sc.col, s));
+                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false, sc.col, s,
+                           sc.XP.hi, sc.XP.lo));
+      EVE_TRY(conv_bwd_planes(k.g2, sc.XP.hi, sc.XP.lo, sc.DB.hi, sc.DB.lo, w[slot + 1], gr[slot + 1],
+                              acc, nullptr, nullptr, sc.cs, s));
       // the block input feeds conv1 and the downsample convolution: one bf16 split for both
       EVE_TRY(split_planes(k.in, (long long)k.g1.in_elems(), sc.XI.hi, sc.XI.lo, TC_BF16, s));
       const float* addend = gskip;

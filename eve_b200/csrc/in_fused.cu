@@ -359,6 +359,10 @@ struct InBwdArgs {
   float* g_out;
   float *sum_g, *sum_gx, *sum_g2, *sum_gx2;    // [N, C] (optional, for the affine gradients)
   float* colpart;                              // [N * CS][C] column sums of dx (optional)
+  // optional: the forward activation act(xhat * gamma + beta) of this norm as bf16 hi/lo planes (and
+  // of the second affine set) -- the x operand of the weight gradient of the convolution(s) the norm
+  // feeds, re-derived here from the xhat this kernel computes anyway instead of by a separate pass
+  uint16_t *ya_hi, *ya_lo, *yb_hi, *yb_lo;
 };
 
 template <bool DUAL>
@@ -516,6 +520,7 @@ in_bwd_fused_kernel(const InBwdArgs a) {
     const float4 B4 = reinterpret_cast<const float4*>(tot + kS)[q];
     const float A[4] = {A4.x, A4.y, A4.z, A4.w}, B[4] = {B4.x, B4.y, B4.z, B4.w};
     const bool has_add = a.addend != nullptr, has_dx = a.dx != nullptr, has_pl = a.dx_hi != nullptr;
+    const bool has_ya = a.ya_hi != nullptr;
     const float4 *d = sg + s0, *e = sx + s0;
     size_t go = goff;
     for (int p = lane; p < np; p += L, d += step_s, e += step_s, go += step_g) {
@@ -536,6 +541,22 @@ in_bwd_fused_kernel(const InBwdArgs a) {
         split4<TC_BF16>(o, h, l);
         reinterpret_cast<uint2*>(a.dx_hi)[go] = h;
         reinterpret_cast<uint2*>(a.dx_lo)[go] = l;
+      }
+      if (has_ya) {
+        float y[4];
+        uint2 h, l;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = act_apply(fmaf(xh[j], ga[j], be[j]), slope);
+        split4<TC_BF16>(y, h, l);
+        reinterpret_cast<uint2*>(a.ya_hi)[go] = h;
+        reinterpret_cast<uint2*>(a.ya_lo)[go] = l;
+        if (DUAL && a.yb_hi) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) y[j] = act_apply(fmaf(xh[j], ga2[j], be2[j]), slope);
+          split4<TC_BF16>(y, h, l);
+          reinterpret_cast<uint2*>(a.yb_hi)[go] = h;
+          reinterpret_cast<uint2*>(a.yb_lo)[go] = l;
+        }
       }
     }
   }
@@ -710,6 +731,7 @@ in_bwd_stream_kernel(const InBwdArgs a) {
     const float4 B4 = reinterpret_cast<const float4*>(tot + kS)[q];
     const float A[4] = {A4.x, A4.y, A4.z, A4.w}, B[4] = {B4.x, B4.y, B4.z, B4.w};
     const bool has_add = a.addend != nullptr, has_dx = a.dx != nullptr, has_pl = a.dx_hi != nullptr;
+    const bool has_ya = a.ya_hi != nullptr;
     size_t go = goff;
 #pragma unroll (DUAL ? 1 : 4)
     for (int p = lane; p < np; p += L, go += step_g) {
@@ -734,6 +756,22 @@ in_bwd_stream_kernel(const InBwdArgs a) {
         split4<TC_BF16>(o, h, l);
         reinterpret_cast<uint2*>(a.dx_hi)[go] = h;
         reinterpret_cast<uint2*>(a.dx_lo)[go] = l;
+      }
+      if (has_ya) {
+        float y[4];
+        uint2 h, l;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = act_apply(fmaf(e.xh[j], ga[j], be[j]), slope);
+        split4<TC_BF16>(y, h, l);
+        reinterpret_cast<uint2*>(a.ya_hi)[go] = h;
+        reinterpret_cast<uint2*>(a.ya_lo)[go] = l;
+        if (DUAL && a.yb_hi) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) y[j] = act_apply(fmaf(e.xh[j], ga2[j], be2[j]), slope);
+          split4<TC_BF16>(y, h, l);
+          reinterpret_cast<uint2*>(a.yb_hi)[go] = h;
+          reinterpret_cast<uint2*>(a.yb_lo)[go] = l;
+        }
       }
     }
   }
@@ -925,11 +963,15 @@ int in_bwd_fused(const float* dy, const float* dy2, const float* ymask, const fl
                  const float* beta, const float* gamma2, const float* beta2, int act,
                  const float* addend, float* dx, void* dx_hi, void* dx_lo, float* g_out,
                  float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, float* dbias,
-                 float* dbias2, bool accumulate, float* scratch, cudaStream_t s) {
+                 float* dbias2, bool accumulate, float* scratch, cudaStream_t s, void* ya_hi,
+                 void* ya_lo, void* yb_hi, void* yb_lo) {
   if (N == 0) return EVE_OK;
   FusedPlan p;
   EVE_REQUIRE(plan_fused(C, HW, 2, p), EVE_ERR_SHAPE,
               "in_bwd_fused: unsupported shape HW=%d C=%d", HW, C);
+  EVE_REQUIRE(!ya_hi || (ya_lo && !ymask), EVE_ERR_NULL,
+              "in_bwd_fused: activation planes need ya_lo and the recomputed pre-activation");
+  EVE_REQUIRE(!yb_hi || (yb_lo && ya_hi && dy2), EVE_ERR_NULL, "in_bwd_fused: second plane set");
   EVE_REQUIRE(dy && x && mean && rstd && scratch, EVE_ERR_NULL, "in_bwd_fused: NULL pointer");
   EVE_REQUIRE(!dy2 || (gamma2 && beta2 && gamma), EVE_ERR_NULL, "in_bwd_fused: second affine set");
   EVE_REQUIRE(!dx_hi || dx_lo, EVE_ERR_NULL, "in_bwd_fused: dx_lo is NULL");
@@ -940,6 +982,8 @@ int in_bwd_fused(const float* dy, const float* dy2, const float* ymask, const fl
   a.slope = act_slope(act);
   a.addend = addend; a.dx = dx; a.dx_hi = (uint16_t*)dx_hi; a.dx_lo = (uint16_t*)dx_lo;
   a.g_out = g_out;
+  a.ya_hi = (uint16_t*)ya_hi; a.ya_lo = (uint16_t*)ya_lo;
+  a.yb_hi = (uint16_t*)yb_hi; a.yb_lo = (uint16_t*)yb_lo;
   const size_t nc = (size_t)N * C;
   const bool affine = gamma && dgamma;
   a.sum_g = affine ? scratch : nullptr;

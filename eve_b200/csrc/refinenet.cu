@@ -638,30 +638,36 @@ int block_bwd_fused(const RBlock& k, int N, const float* const* w, float* const*
     EVE_TRY(split_colsum(dout, (long long)N * HW, k.oc, D.hi, D.lo, bg[7], sk ? bg[11] : nullptr,
                          acc, f.col, s));
   }
-  // conv2: x operand re-derived from the saved pre-norm tensor
-  EVE_TRY(in_apply_planes2(k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], nullptr, nullptr, k.act,
-                           TC_BF16, f.XP.hi, f.XP.lo, nullptr, nullptr, s));
-  EVE_TRY(conv_bwd_planes(k.g2, f.XP.hi, f.XP.lo, D.hi, D.lo, bw[6], bg[6], acc, nullptr, sc.t0,
+  // Data gradients first, weight gradients after the norm's backward kernel: that kernel computes
+  // xhat of the saved pre-norm tensor anyway and writes act(xhat * gamma + beta) -- the x operand
+  // of the weight gradient -- as bf16 planes next to dx (no separate re-derivation pass).
+  EVE_TRY(conv_bwd_planes(k.g2, nullptr, nullptr, D.hi, D.lo, bw[6], nullptr, acc, nullptr, sc.t0,
                           sc.cs, s));
-  // norm 1: dy planes of conv1, its bias gradient, the affine gradients -- one pass
+  // norm 1: dy planes of conv1, its bias gradient, the affine gradients, conv2's x planes
   EVE_TRY(in_bwd_fused(sc.t0, nullptr, nullptr, k.c1, N, HW, k.oc, k.m1, k.r1, bw[4], bw[5], nullptr,
                        nullptr, k.act, nullptr, nullptr, f.D2.hi, f.D2.lo, nullptr, bg[4], bg[5],
-                       nullptr, nullptr, bg[3], nullptr, acc, f.col, s));
-  EVE_TRY(in_apply_planes2(k.x, N, HW, k.ic, k.m0, k.r0, bw[0], bw[1], sk ? bw[8] : nullptr,
-                           sk ? bw[9] : nullptr, k.act, TC_BF16, f.XP.hi, f.XP.lo,
-                           sk ? f.XP2.hi : nullptr, sk ? f.XP2.lo : nullptr, s));
-  EVE_TRY(conv_bwd_planes(k.g1, f.XP.hi, f.XP.lo, f.D2.hi, f.D2.lo, bw[2], bg[2], acc, nullptr,
+                       nullptr, nullptr, bg[3], nullptr, acc, f.col, s, f.XP.hi, f.XP.lo));
+  EVE_TRY(conv_bwd_planes(k.g2, f.XP.hi, f.XP.lo, D.hi, D.lo, bw[6], bg[6], acc, nullptr, nullptr,
+                          sc.cs, s));
+  EVE_TRY(conv_bwd_planes(k.g1, nullptr, nullptr, f.D2.hi, f.D2.lo, bw[2], nullptr, acc, nullptr,
                           sc.t0, sc.cs, s));
   if (sk)
-    EVE_TRY(conv_bwd_planes(k.gs, f.XP2.hi, f.XP2.lo, D.hi, D.lo, bw[10], bg[10], acc, nullptr,
+    EVE_TRY(conv_bwd_planes(k.gs, nullptr, nullptr, D.hi, D.lo, bw[10], nullptr, acc, nullptr,
                             sc.t2, sc.cs, s));
   // norm 0 (both affine sets of the same statistics when there is a skip convolution); the
   // identity residual passes dout straight through when there is none
-  return in_bwd_fused(sc.t0, sk ? sc.t2 : nullptr, nullptr, k.x, N, HW, k.ic, k.m0, k.r0, bw[0],
-                      bw[1], sk ? bw[8] : nullptr, sk ? bw[9] : nullptr, k.act,
-                      sk ? nullptr : dout, dx,
-                      dnext ? dnext->hi : nullptr, dnext ? dnext->lo : nullptr, nullptr, bg[0],
-                      bg[1], sk ? bg[8] : nullptr, sk ? bg[9] : nullptr, nb_a, nb_b, acc, f.col, s);
+  EVE_TRY(in_bwd_fused(sc.t0, sk ? sc.t2 : nullptr, nullptr, k.x, N, HW, k.ic, k.m0, k.r0, bw[0],
+                       bw[1], sk ? bw[8] : nullptr, sk ? bw[9] : nullptr, k.act,
+                       sk ? nullptr : dout, dx,
+                       dnext ? dnext->hi : nullptr, dnext ? dnext->lo : nullptr, nullptr, bg[0],
+                       bg[1], sk ? bg[8] : nullptr, sk ? bg[9] : nullptr, nb_a, nb_b, acc, f.col, s,
+                       f.XP.hi, f.XP.lo, sk ? f.XP2.hi : nullptr, sk ? f.XP2.lo : nullptr));
+  EVE_TRY(conv_bwd_planes(k.g1, f.XP.hi, f.XP.lo, f.D2.hi, f.D2.lo, bw[2], bg[2], acc, nullptr,
+                          nullptr, sc.cs, s));
+  if (sk)
+    EVE_TRY(conv_bwd_planes(k.gs, f.XP2.hi, f.XP2.lo, D.hi, D.lo, bw[10], bg[10], acc, nullptr,
+                            nullptr, sc.cs, s));
+  return EVE_OK;
 }
 
 size_t rnet_conv_scratch_bytes(const RNet& n) {
