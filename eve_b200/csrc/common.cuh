@@ -150,6 +150,9 @@ bool conv_tc_dgrad_s2_supported(const ConvGeom& g);
 int conv_tc_dgrad_s2_run(const ConvGeom& g, const void* d_hi, const void* d_lo, const void* w_hi,
                          const void* w_lo, const float* addend, float* dx, int npass,
                          cudaStream_t s);
+int conv_tc_stem_run(int N, int H, int W, const void* x_hi, const void* x_lo, int win_bytes,
+                     int pitch_bytes, const void* w_hi, const void* w_lo, const float* bias, float* y,
+                     int npass, int fmt, float out_scale, cudaStream_t s);
 bool conv_tc_wgrad_supported(const ConvGeom& g);
 size_t conv_tc_wgrad_partial_floats(const ConvGeom& g);
 int conv_tc_wgrad_run(const ConvGeom& g, const void* d_hi, const void* d_lo, const void* x_hi,
@@ -179,6 +182,7 @@ enum OptKey {
   OPT_TC_STRIP,              // padded-strip tcgen05 kernel for 3x3 stride-1 layers: 0 off, 1 auto, 2 whenever it fits
   OPT_TC_WGRAD_STRIP,        // padded-strip weight-gradient kernel (3x3 stride 1, 64 output channels)
   OPT_CGRU_PERSISTENT,       // ConvGRU (64 features, 5x8 maps): whole sequence in one persistent kernel
+  OPT_STEM_WINDOWS,          // stem forward without an im2col matrix: 0 off, 1 one window per output column, 2 overlapping windows in the padded image
   OPT_IN_STREAM,             // InstanceNorm backward without shared-memory staging: 0 off, 1 maps that need one CTA per SM, 2 always (default)
   OPT_COUNT
 };

@@ -77,6 +77,64 @@ stem_im2col_kernel(const float* __restrict__ x, int H, int W, int OH, int OW, in
   }
 }
 
+// Stem windows (conv_tc_stem_run): 16-bit hi/lo planes of the zero-padded input, either
+//   mode 1: [N][H + 6][OW][32]: the window of output column ox (input pixels 2 ox - 3 .. 2 ox + 4,
+//           4 channels each, channel 3 and everything outside the image zero), or
+//   mode 2: [N][H + 6][W + 8][4]: the padded image itself (3 zero pixels left, 5 right); windows are
+//           read overlapping, 2 pixels apart.
+// One thread writes 8 values (two pixels) = one 16-byte store per plane.
+__global__ void __launch_bounds__(256)
+stem_windows_kernel(const float* __restrict__ x, int N, int H, int W, int mode, int fmt,
+                    uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  const int Hp = H + 6;
+  const int groups = mode == 1 ? (W / 2) * 4 : (W + 8) / 2;   // 16-byte groups per padded row
+  const long long total = (long long)N * Hp * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int gidx = (int)(i % groups);
+    const long long row = i / groups;
+    const int ihp = (int)(row % Hp);
+    const int n = (int)(row / Hp);
+    const int ih = ihp - 3;
+    int ix0;                                       // first of the two input pixels of this group
+    if (mode == 1) {
+      const int ox = gidx >> 2, pg = gidx & 3;
+      ix0 = 2 * ox - 3 + 2 * pg;
+    } else {
+      ix0 = 2 * gidx - 3;
+    }
+    uint16_t h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ix = ix0 + (j >> 2), c = j & 3;
+      float v = 0.f;
+      // mode 1: the 8th pixel of a window (pg == 3, second pixel) is outside the 7-tap filter; its
+      // weights are zero, the value is irrelevant but kept finite
+      if (c < 3 && ih >= 0 && ih < H && ix >= 0 && ix < W)
+        v = __ldg(x + (((size_t)n * H + ih) * W + ix) * 3 + c);
+      split16(v, fmt, h[j], l[j]);
+    }
+    reinterpret_cast<uint4*>(hi)[i] = *reinterpret_cast<uint4*>(h);
+    if (lo) reinterpret_cast<uint4*>(lo)[i] = *reinterpret_cast<uint4*>(l);
+  }
+}
+
+// OIHW [64][3][7][7] -> [64][7][32] (k = r*32 + q*4 + c; q == 7 and c == 3 zero)
+__global__ void stem_prep_weights_win_kernel(const float* __restrict__ w, int Cout, int fmt,
+                                             float scale, uint16_t* __restrict__ hi,
+                                             uint16_t* __restrict__ lo) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * 224) return;
+  const int k = i % 224, co = i / 224;
+  const int r = k >> 5, q = (k >> 2) & 7, c = k & 3;
+  float v = 0.f;
+  if (q < 7 && c < 3) v = w[((size_t)co * 3 + c) * 49 + r * 7 + q] * scale;
+  uint16_t h, l;
+  split16(v, fmt, h, l);
+  hi[i] = h;
+  if (lo) lo[i] = l;
+}
+
 // OIHW [64][3][7][7] -> [64][kStemK] (k = (r*7+q)*3 + c, zero padded)
 __global__ void stem_prep_weights_kernel(const float* __restrict__ w, int Cout, int fmt,
                                          float scale, uint16_t* __restrict__ hi,
@@ -285,6 +343,28 @@ int conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* bia
     const int fmt = npass == 3 ? TC_F16 : TC_BF16;
     const float wscale = npass == 3 ? 64.f : 1.f;
     const ConvGeom gg = stem_gemm(g);
+    const int win = get_option(OPT_STEM_WINDOWS);
+    if (win != 0 && g.H % 2 == 0 && g.W % 2 == 0 && g.W % 8 == 0 && !addend) {
+      // no im2col matrix: 32-value windows of the zero-padded planes, seven taps (conv_tc_stem_run)
+      const int Hp = g.H + 6;
+      const size_t row_el = win == 1 ? (size_t)(g.W / 2) * 32 : (size_t)(g.W + 8) * 4;
+      const size_t pel = (size_t)g.N * Hp * row_el;      // <= the im2col matrix the scratch is sized for
+      uint16_t* w_hi = c.get<uint16_t>((size_t)g.Cout * 224);
+      uint16_t* w_lo = c.get<uint16_t>((size_t)g.Cout * 224);
+      uint16_t* x_hi = c.get<uint16_t>(pel);
+      uint16_t* x_lo = c.get<uint16_t>(pel);
+      EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_fwd(stem windows): scratch too small");
+      stem_prep_weights_win_kernel<<<cdiv(g.Cout * 224, 256), 256, 0, s>>>(
+          w, g.Cout, fmt, wscale, w_hi, npass == 3 ? w_lo : nullptr);
+      EVE_LAUNCH_CHECK();
+      stem_windows_kernel<<<kNumSMs * 8, 256, 0, s>>>(x, g.N, g.H, g.W, win, fmt, x_hi,
+                                                     npass == 3 ? x_lo : nullptr);
+      EVE_LAUNCH_CHECK();
+      ProfScope prof(PROF_CONV_FWD, 2.0 * g.out_elems() * (double)g.K(),
+                     4.0 * (g.in_elems() + g.out_elems() + (double)wel), s, &g);
+      return conv_tc_stem_run(g.N, g.H, g.W, x_hi, x_lo, win == 1 ? 64 : 16, (int)(row_el * 2), w_hi,
+                              w_lo, bias, y, npass, fmt, 1.f / wscale, s);
+    }
     uint16_t* w_hi = c.get<uint16_t>((size_t)g.Cout * kStemK);
     uint16_t* w_lo = c.get<uint16_t>((size_t)g.Cout * kStemK);
     uint16_t* x_hi = c.get<uint16_t>((size_t)gg.in_elems());

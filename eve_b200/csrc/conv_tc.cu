@@ -2436,6 +2436,29 @@ int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, 
   return EVE_OK;
 }
 
+// Stem windows (conv_tc_stem_run): a rank-4 view [N][Hp][OW][32] whose rows of 32 elements start
+// every `win_bytes` bytes along OW (64: one materialised window per output column; 16: windows that
+// OVERLAP in a zero-padded 4-channel image, 2 pixels apart) and every `pitch_bytes` along Hp; the box
+// takes every second row (the convolution's vertical stride).
+int make_map_windows(CUtensorMap* m, const void* base, int N, int Hp, int OW, int win_bytes,
+                     int pitch_bytes, int bw, int bh, int bn, int fmt) {
+  EncodeTiledFn enc = encode_fn();
+  EVE_REQUIRE(enc, EVE_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled is not available");
+  cuuint64_t dims[4] = {32, (cuuint64_t)OW, (cuuint64_t)Hp, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)win_bytes, (cuuint64_t)pitch_bytes,
+                           (cuuint64_t)Hp * (cuuint64_t)pitch_bytes};
+  cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)(bh * 2), (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 2, 1};
+  CUresult r = enc(m, fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                   4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(32),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EVE_REQUIRE(r == CUDA_SUCCESS, EVE_ERR_CUDA,
+              "conv_tc: cuTensorMapEncodeTiled(stem windows %dx%dx%d, %d / %d bytes) failed: %d", N, Hp,
+              OW, win_bytes, pitch_bytes, (int)r);
+  return EVE_OK;
+}
+
 int make_map_2d(CUtensorMap* m, const void* base, int rows, int cols, int cw, int box_rows,
                 int fmt = 1) {
   EncodeTiledFn enc = encode_fn();
@@ -2570,7 +2593,7 @@ int conv_tc_prep_weights(const ConvGeom& g, const float* w_oihw, bool dgrad, voi
 
 static int tc_launch(const TcParams& p0, const void* x_hi, const void* x_lo, int inN, int inH,
                      int inW, const void* w_hi, const void* w_lo, int wrows, int wcols, int npass,
-                     int fmt, cudaStream_t s) {
+                     int fmt, cudaStream_t s, int win_bytes = 0, int pitch_bytes = 0) {
   TcParams p = p0;
   pick_box(p.N, p.OH, p.OW, p.bw, p.bh, p.bn);
   p.tiles_h = cdiv(p.OH, p.bh);
@@ -2584,11 +2607,18 @@ static int tc_launch(const TcParams& p0, const void* x_hi, const void* x_lo, int
   // tiles put more SMs on the layer; each CTA's serial chain of MMAs shrinks by the same factor.
   while (BN > 16 && (long long)p.tiles_h * tiles_n * (p.Cout / BN) < kNumSMs / 2) BN >>= 1;
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
-  EVE_TRY(make_map_nhwc(&a_hi, x_hi, inN, inH, inW, p.Cin, p.kc, p.bw, p.bh, p.bn, p.stride, fmt));
+  if (win_bytes)
+    EVE_TRY(make_map_windows(&a_hi, x_hi, inN, inH, inW, win_bytes, pitch_bytes, p.bw, p.bh, p.bn, fmt));
+  else
+    EVE_TRY(make_map_nhwc(&a_hi, x_hi, inN, inH, inW, p.Cin, p.kc, p.bw, p.bh, p.bn, p.stride, fmt));
   EVE_TRY(make_map_2d(&b_hi, w_hi, wrows, wcols, p.kc, BN, fmt));
   if (npass == 3) {
-    EVE_TRY(make_map_nhwc(&a_lo, x_lo, inN, inH, inW, p.Cin, p.kc, p.bw, p.bh, p.bn, p.stride,
-                          fmt));
+    if (win_bytes)
+      EVE_TRY(make_map_windows(&a_lo, x_lo, inN, inH, inW, win_bytes, pitch_bytes, p.bw, p.bh, p.bn,
+                               fmt));
+    else
+      EVE_TRY(make_map_nhwc(&a_lo, x_lo, inN, inH, inW, p.Cin, p.kc, p.bw, p.bh, p.bn, p.stride,
+                            fmt));
     EVE_TRY(make_map_2d(&b_lo, w_lo, wrows, wcols, p.kc, BN, fmt));
   } else {
     a_lo = a_hi;
@@ -2946,6 +2976,31 @@ int conv_tc_run(const ConvGeom& g, const void* x_hi, const void* x_lo, const voi
   p.bias = bias; p.addend = addend; p.out = y; p.out_scale = out_scale;
   return tc_launch(p, x_hi, x_lo, g.N, g.H, g.W, w_hi, w_lo, g.Cout, g.KH * g.KW * g.Cin, npass,
                    fmt, s);
+}
+
+// The 7x7 stride-2 stem (3 input channels, eye_net.py:48 via torchvision's ResNet-18 conv1) without
+// a materialised im2col matrix: a filter ROW of one output pixel is 7 pixels x 3 channels = 8 pixels
+// x 4 channels (zero padded) = 32 consecutive 16-bit values, so the convolution is a 7-tap "7x1"
+// convolution over 32-channel windows: tap r reads window row 2 oh + r of the zero-padded planes
+// (top pad 3: no negative coordinates), K = 7 x 32.  x_hi / x_lo: [N][H + 6][...] planes whose
+// window of output column ow starts at ow * win_bytes (see make_map_windows); w: [64][7 * 32].
+int conv_tc_stem_run(int N, int H, int W, const void* x_hi, const void* x_lo, int win_bytes,
+                     int pitch_bytes, const void* w_hi, const void* w_lo, const float* bias, float* y,
+                     int npass, int fmt, float out_scale, cudaStream_t s) {
+  EVE_REQUIRE(H % 2 == 0 && W % 2 == 0 && W / 2 <= kTileM && N >= 1, EVE_ERR_SHAPE,
+              "conv_tc_stem: unsupported geometry");
+  TcParams p;
+  p.N = N; p.OH = H / 2; p.OW = W / 2; p.Cin = 32; p.Cout = 64; p.stride = 2;
+  p.ntaps = 7;
+  for (int r = 0; r < 7; ++r) {
+    p.tap_dh[r] = r;
+    p.tap_dw[r] = 0;
+    p.tap_koff[r] = r * 32;
+  }
+  p.out_mul = 1; p.out_ah = 0; p.out_aw = 0; p.out_H = p.OH; p.out_W = p.OW;
+  p.bias = bias; p.addend = nullptr; p.out = y; p.out_scale = out_scale;
+  return tc_launch(p, x_hi, x_lo, N, H + 6, W / 2, w_hi, w_lo, 64, 7 * 32, npass, fmt, s, win_bytes,
+                   pitch_bytes);
 }
 
 // Data gradient of a stride-2 convolution (3x3 pad 1 or 1x1 pad 0) as four stride-1

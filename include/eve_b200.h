@@ -112,6 +112,12 @@ int eve_get_conv_mode(void);
  *                                per sequence (x halves of the gate convolutions batched over
  *                                time, recurrence in shared memory / TMEM); 0 = one convolution
  *                                launch pair per time step
+ *   "stem_windows"        0..2   EyeNet stem (7x7 stride 2, 3 channels) forward without an im2col
+ *                                matrix: a filter row of an output pixel is one 32-value window
+ *                                (8 pixels x 4 zero-padded channels) and the convolution a 7-tap
+ *                                tensor-core pass over window rows.  1 = one window per output
+ *                                column written once (default), 2 = windows overlapping inside the
+ *                                zero-padded image (TMA strides smaller than the box), 0 = im2col
  *   "in_stream"           0..2   InstanceNorm backward without shared-memory staging (second read of
  *                                dy / x served by L2, two CTAs per SM): 0 = never, 1 = for maps whose
  *                                staged form needs one CTA per SM, 2 = always (default: measured

@@ -56,6 +56,34 @@ def test_conv2d_forward_dgrad_wgrad(case):
     assert G.rel(db, bd.grad) < TOL
 
 
+@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('n,h,w', [(3, 128, 128), (2, 64, 96)])
+def test_stem_forward_window_modes(mode, n, h, w):
+    """EyeNet stem (7x7 stride 2 pad 3, 3 -> 64 channels; eye_net.py:48 via torchvision conv1) with
+    the im2col matrix (0), one 32-value window per output column (1) and windows overlapping inside
+    the zero-padded image (2): all three against fp64, image borders included."""
+    from eve_b200 import lib as L
+    L.load()
+    saved = L.get_option('stem_windows')
+    try:
+        L.set_option('stem_windows', mode)
+        g = torch.Generator().manual_seed(11 + mode)
+        x = torch.randn(n, 3, h, w, generator=g)
+        wt = torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5
+        b = torch.randn(64, generator=g)
+        want = F.conv2d(x.double(), wt.double(), b.double(), stride=2, padding=3)
+        got = G.conv_fwd(x.cuda(), wt.cuda(), b.cuda(), 2, 3)
+        assert got.shape == want.shape
+        assert G.rel(got, want) < TOL
+        # the border rows / columns on their own (zero padding of the windows)
+        for sl in ((slice(None), slice(None), slice(0, 2)), (slice(None), slice(None), slice(-2, None)),
+                   (slice(None), slice(None), slice(None), slice(0, 2)),
+                   (slice(None), slice(None), slice(None), slice(-2, None))):
+            assert G.rel(got[sl], want[sl]) < TOL
+    finally:
+        L.set_option('stem_windows', saved)
+
+
 def test_conv2d_empty_batch():
     wt = torch.randn(8, 4, 3, 3).cuda()
     y = G.conv_fwd(torch.zeros(0, 4, 8, 8).cuda(), wt, None, 1, 1)
