@@ -606,7 +606,18 @@ __device__ __forceinline__ void bwd_elem(const float4 d4, const float4 x4, const
   }
 }
 
-template <bool DUAL>
+template <int N>
+__device__ __forceinline__ void cp_async_wait_pending() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
+// D = depth of the per-thread cp.async ring the element loops read through: every thread keeps D
+// iterations (x up to five tensors) of ITS OWN 16-byte pieces in flight in shared memory -- loads
+// held in registers (an unrolled __ldg loop under the 64-register cap of two CTAs per SM) kept only
+// one or two iterations in flight and the kernel waited on the long scoreboard at 36 % of the DRAM
+// peak.  No thread reads another thread's pieces, so cp.async.wait_group is the only synchronisation.
+template <bool DUAL, int D>
 __global__ void __launch_bounds__(kThr, 2)
 in_bwd_stream_kernel(const InBwdArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -618,6 +629,7 @@ in_bwd_stream_kernel(const InBwdArgs a) {
   double* wred = reinterpret_cast<double*>(smraw);                // [kThr*4]
   double* cpart = wred + kThr * 4;                                // [4 sums][4*kMaxQ]
   float* tot = reinterpret_cast<float*>(cpart + 4 * 4 * kMaxQ);   // A, B: [2][4*kMaxQ]
+  float4* ring = reinterpret_cast<float4*>(tot + 2 * 4 * kMaxQ);  // [D][tensors][kThr]
   constexpr int kS = 4 * kMaxQ;
 
   const int L = kThr / Q;
@@ -631,13 +643,36 @@ in_bwd_stream_kernel(const InBwdArgs a) {
   const float4* gx = reinterpret_cast<const float4*>(a.x);
   const float4* gy = reinterpret_cast<const float4*>(a.ymask);
   const float4* ge = reinterpret_cast<const float4*>(a.dy2);
+  const float4* gt = reinterpret_cast<const float4*>(a.addend);
   const bool has_mask = a.ymask != nullptr;
+  const bool has_add = a.addend != nullptr;
+  // ring layout: tensor slots dy, x, [ymask], [dy2], [addend] (the last in phase 2 only)
+  const int i_mask = 2, i_e = 2 + (has_mask ? 1 : 0), i_add = i_e + (DUAL ? 1 : 0);
+  const int TT = i_add + (has_add ? 1 : 0);
+  float4* mine = ring + threadIdx.x;
+  auto issue = [&](int slot, size_t go, bool with_add) {
+    float4* d = mine + (size_t)slot * TT * kThr;
+    cp_async16(d, gd + go);
+    cp_async16(d + kThr, gx + go);
+    if (has_mask) cp_async16(d + i_mask * kThr, gy + go);
+    if (DUAL) cp_async16(d + i_e * kThr, ge + go);
+    if (with_add) cp_async16(d + i_add * kThr, gt + go);
+  };
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float m[4] = {0, 0, 0, 0}, r[4] = {0, 0, 0, 0};
   float ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
   float ga2[4] = {0.f, 0.f, 0.f, 0.f}, be2[4] = {0.f, 0.f, 0.f, 0.f};
   float f_g[4] = {0, 0, 0, 0}, f_gx[4] = {0, 0, 0, 0}, f_g2[4] = {0, 0, 0, 0}, f_gx2[4] = {0, 0, 0, 0};
   if (active) {
+    // ---- phase 1: the sums (fp32 per thread over its few pixels, fp64 across threads and CTAs,
+    // exactly as the staged kernel)
+    int pi = lane;
+    size_t gi = goff;
+#pragma unroll
+    for (int k = 0; k < D; ++k, pi += L, gi += step_g) {
+      if (pi < np) issue(k, gi, false);
+      cp_async_commit();
+    }
     const size_t so = (size_t)n * a.C + c;
     const float4 m4 = *reinterpret_cast<const float4*>(a.mean + so);
     const float4 r4 = *reinterpret_cast<const float4*>(a.rstd + so);
@@ -655,15 +690,19 @@ in_bwd_stream_kernel(const InBwdArgs a) {
       ga2[0] = g4.x; ga2[1] = g4.y; ga2[2] = g4.z; ga2[3] = g4.w;
       be2[0] = b4.x; be2[1] = b4.y; be2[2] = b4.z; be2[3] = b4.w;
     }
-    // ---- phase 1: the sums (fp32 per thread over its few pixels, fp64 across threads and CTAs,
-    // exactly as the staged kernel)
     const bool has_gout = a.g_out != nullptr;
     size_t go = goff;
-#pragma unroll (DUAL ? 1 : 4)
-    for (int p = lane; p < np; p += L, go += step_g) {
-      const float4 d4 = __ldg(gd + go), x4 = __ldg(gx + go);
-      const float4 y4 = has_mask ? __ldg(gy + go) : z4;
-      const float4 e4 = DUAL ? __ldg(ge + go) : z4;
+    int slot = 0;
+#pragma unroll 1
+    for (int p = lane; p < np; p += L, go += step_g, pi += L, gi += step_g) {
+      cp_async_wait_pending<D - 1>();
+      const float4* d = mine + (size_t)slot * TT * kThr;
+      const float4 d4 = d[0], x4 = d[kThr];
+      const float4 y4 = has_mask ? d[i_mask * kThr] : z4;
+      const float4 e4 = DUAL ? d[i_e * kThr] : z4;
+      if (pi < np) issue(slot, gi, false);       // refill the slot just read (iteration + D)
+      cp_async_commit();
+      slot = slot + 1 == D ? 0 : slot + 1;
       BwdElem<DUAL> o;
       float g2[4] = {0.f, 0.f, 0.f, 0.f};
       bwd_elem<DUAL>(d4, x4, y4, has_mask, e4, m, r, ga, be, ga2, be2, slope, o, g2);
@@ -678,6 +717,15 @@ in_bwd_stream_kernel(const InBwdArgs a) {
       }
       if (has_gout)
         reinterpret_cast<float4*>(a.g_out)[go] = make_float4(o.g[0], o.g[1], o.g[2], o.g[3]);
+    }
+    cp_async_wait_pending<0>();
+    // phase 2's first D iterations: on their way while the sums cross the cluster
+    pi = lane;
+    gi = goff;
+#pragma unroll
+    for (int k = 0; k < D; ++k, pi += L, gi += step_g) {
+      if (pi < np) issue(k, gi, has_add);
+      cp_async_commit();
     }
   }
   {
@@ -730,15 +778,23 @@ in_bwd_stream_kernel(const InBwdArgs a) {
     const float4 A4 = reinterpret_cast<const float4*>(tot)[q];
     const float4 B4 = reinterpret_cast<const float4*>(tot + kS)[q];
     const float A[4] = {A4.x, A4.y, A4.z, A4.w}, B[4] = {B4.x, B4.y, B4.z, B4.w};
-    const bool has_add = a.addend != nullptr, has_dx = a.dx != nullptr, has_pl = a.dx_hi != nullptr;
+    const bool has_dx = a.dx != nullptr, has_pl = a.dx_hi != nullptr;
     const bool has_ya = a.ya_hi != nullptr;
     size_t go = goff;
-#pragma unroll (DUAL ? 1 : 4)
-    for (int p = lane; p < np; p += L, go += step_g) {
-      const float4 d4 = __ldg(gd + go), x4 = __ldg(gx + go);
-      const float4 y4 = has_mask ? __ldg(gy + go) : z4;
-      const float4 e4 = DUAL ? __ldg(ge + go) : z4;
-      const float4 t4 = has_add ? __ldg(reinterpret_cast<const float4*>(a.addend) + go) : z4;
+    int pi = lane + D * L;
+    size_t gi = goff + (size_t)D * step_g;
+    int slot = 0;
+#pragma unroll 1
+    for (int p = lane; p < np; p += L, go += step_g, pi += L, gi += step_g) {
+      cp_async_wait_pending<D - 1>();
+      const float4* d = mine + (size_t)slot * TT * kThr;
+      const float4 d4 = d[0], x4 = d[kThr];
+      const float4 y4 = has_mask ? d[i_mask * kThr] : z4;
+      const float4 e4 = DUAL ? d[i_e * kThr] : z4;
+      const float4 t4 = has_add ? d[i_add * kThr] : z4;
+      if (pi < np) issue(slot, gi, has_add);
+      cp_async_commit();
+      slot = slot + 1 == D ? 0 : slot + 1;
       BwdElem<DUAL> e;
       float g2[4];
       bwd_elem<DUAL>(d4, x4, y4, has_mask, e4, m, r, ga, be, ga2, be2, slope, e, g2);
@@ -774,6 +830,7 @@ in_bwd_stream_kernel(const InBwdArgs a) {
         }
       }
     }
+    cp_async_wait_pending<0>();
   }
   if (a.colpart) {
     float* fred = reinterpret_cast<float*>(wred);
@@ -996,9 +1053,21 @@ int in_bwd_fused(const float* dy, const float* dy2, const float* ymask, const fl
   const bool inplace = g_out && (g_out == dy || g_out == dy2 || g_out == ymask || g_out == x);
   const int sopt = get_option(OPT_IN_STREAM);
   if (!inplace && (sopt == 2 || (sopt == 1 && p.one_cta))) {
-    const size_t smem = (size_t)(kThr * 4 + 4 * 4 * kMaxQ) * sizeof(double) + 2 * 4 * kMaxQ * sizeof(float);
-    if (dy2) EVE_TRY(launch_cluster(in_bwd_stream_kernel<true>, grid, p.CS, smem, a, s));
-    else EVE_TRY(launch_cluster(in_bwd_stream_kernel<false>, grid, p.CS, smem, a, s));
+    // ring depth: tensors x depth >= 8 sixteen-byte pieces per thread in flight, two CTAs per SM
+    const int tensors = 2 + (ymask ? 1 : 0) + (dy2 ? 1 : 0) + (addend ? 1 : 0);
+    const int depth = tensors <= 2 ? 4 : (tensors == 3 ? 3 : 2);
+    const size_t smem = (size_t)(kThr * 4 + 4 * 4 * kMaxQ) * sizeof(double) + 2 * 4 * kMaxQ * sizeof(float) +
+                        (size_t)depth * tensors * kThr * 16;
+    if (dy2) {
+      if (depth == 3) EVE_TRY(launch_cluster(in_bwd_stream_kernel<true, 3>, grid, p.CS, smem, a, s));
+      else EVE_TRY(launch_cluster(in_bwd_stream_kernel<true, 2>, grid, p.CS, smem, a, s));
+    } else if (depth == 4) {
+      EVE_TRY(launch_cluster(in_bwd_stream_kernel<false, 4>, grid, p.CS, smem, a, s));
+    } else if (depth == 3) {
+      EVE_TRY(launch_cluster(in_bwd_stream_kernel<false, 3>, grid, p.CS, smem, a, s));
+    } else {
+      EVE_TRY(launch_cluster(in_bwd_stream_kernel<false, 2>, grid, p.CS, smem, a, s));
+    }
   } else if (dy2) {
     EVE_TRY(launch_cluster(in_bwd_fused_kernel<true>, grid, p.CS, bwd_smem(p), a, s));
   } else {
