@@ -636,9 +636,10 @@ def b200_arm(args):
             traffic = tj.get('dram_bytes_per_conv_launch')
             traffic_src = tj.get('source')
     roofline = {
-        'bound': 'tensor', 'kernel': 'conv_tc_kernel / conv_tc_row_kernel / conv_tc_wgrad_kernel / '
+        'bound': 'tensor', 'kernel': 'conv_tc_kernel / conv_tc_strip_kernel / conv_tc_row_kernel / '
+                                     'conv_tc_wgrad_kernel / conv_tc_wgrad_strip_kernel / '
                                      'conv_tc_wgrad_row_kernel (tcgen05 implicit GEMM, split '
-                                     'fp16/bf16 operands = 3 MMAs per product) + the few CUDA-core '
+                                     'fp16/bf16 operands = 2-3 MMAs per product) + the few CUDA-core '
                                      'convs left; all conv fwd + dgrad + wgrad launches',
         'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
         'peak_source': peak_src, 'traffic': traffic, 'traffic_source': traffic_src,

@@ -205,8 +205,10 @@ def test_option_variants_agree_on_a_full_training_step(variant, cfg, options):
     # that 1e-7 difference to 1e-2 .. 2e-2 on the last gradients of the chain (initial.0), the same
     # amplification the fp32 reference shows against fp64 (test_gpu_models.py)
     # (the strip kernel likewise sums the taps of a K chunk in a different order)
+    # (... and the window form of the stem sums its 7 x 32 products in another order than the
+    # 160-wide patch matrix: 1e-7 on the EyeNet features, amplified the same way downstream)
     gtol = 3e-2 if ('fused_norm' in variant or 'fused_planes' in variant or 'tc_strip' in variant
-                    or 'cgru_persistent' in variant) \
+                    or 'cgru_persistent' in variant or 'stem_windows' in variant) \
         else 2e-3
     # biases in front of an InstanceNorm have an exactly zero gradient (the norm removes the
     # mean): what is computed there is cancellation noise ~1e-6 of the real gradients
