@@ -87,6 +87,15 @@ struct FusedPlan {
   int CG, Q, CS, ppc;
   bool one_cta;        // the staged form takes more than half an SM's shared memory
 };
+int stream_cluster() {        // tuning knob: cluster size of the streaming backward (0 = the staged plan's)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EVE_B200_IN_STREAM_CS");
+    v = e ? atoi(e) : 0;
+    if (v != 1 && v != 2 && v != 4 && v != 8) v = 0;
+  }
+  return v;
+}
 int max_cluster() {           // tuning knob (environment, read once)
   static int v = 0;
   if (!v) {
@@ -1032,6 +1041,23 @@ int in_bwd_fused(const float* dy, const float* dy2, const float* ymask, const fl
   EVE_REQUIRE(dy && x && mean && rstd && scratch, EVE_ERR_NULL, "in_bwd_fused: NULL pointer");
   EVE_REQUIRE(!dy2 || (gamma2 && beta2 && gamma), EVE_ERR_NULL, "in_bwd_fused: second affine set");
   EVE_REQUIRE(!dx_hi || dx_lo, EVE_ERR_NULL, "in_bwd_fused: dx_lo is NULL");
+  // the streaming form reads dy / x / ymask / dy2 twice: not when g_out overwrites one of them
+  const bool inplace = g_out && (g_out == dy || g_out == dy2 || g_out == ymask || g_out == x);
+  const int sopt = get_option(OPT_IN_STREAM);
+  const bool stream = !inplace && (sopt == 2 || (sopt == 1 && p.one_cta));
+  if (stream) {
+    // Nothing is staged, so the cluster need not be as large as the shared-memory plan wants, and
+    // smaller is faster (measured, tools/bench_in.py: 8 -> 2 CTAs +9-13 % at 9216 pixels, +30-45 % at
+    // 1024-2304 pixels; in the training step 34.52 -> 33.85 ms with 2 everywhere, 34.10 with 4, 34.13
+    // with 1): fewer cluster-wide barriers and per-CTA prologues, a longer steady state of the ring,
+    // and clusters that pack the GPCs' CTA slots without remainder.  Never a function of N.
+    int cs = stream_cluster();
+    if (!cs) cs = 2;
+    if (cs < p.CS) {
+      p.CS = cs;
+      p.ppc = cdiv(HW, p.CS);
+    }
+  }
   InBwdArgs a;
   a.dy = dy; a.dy2 = dy2; a.ymask = ymask; a.x = x;
   a.HW = HW; a.C = C; a.Q = p.Q; a.CS = p.CS; a.ppc = p.ppc;
@@ -1049,10 +1075,7 @@ int in_bwd_fused(const float* dy, const float* dy2, const float* ymask, const fl
   a.sum_gx2 = affine && dy2 ? scratch + 3 * nc : nullptr;
   a.colpart = (dbias || dbias2) ? scratch + 4 * nc : nullptr;
   dim3 grid(p.CS, C / p.CG, N);
-  // the streaming form reads dy / x / ymask / dy2 twice: not when g_out overwrites one of them
-  const bool inplace = g_out && (g_out == dy || g_out == dy2 || g_out == ymask || g_out == x);
-  const int sopt = get_option(OPT_IN_STREAM);
-  if (!inplace && (sopt == 2 || (sopt == 1 && p.one_cta))) {
+  if (stream) {
     // ring depth: tensors x depth >= 8 sixteen-byte pieces per thread in flight, two CTAs per SM
     const int tensors = 2 + (ymask ? 1 : 0) + (dy2 ? 1 : 0) + (addend ? 1 : 0);
     const int depth = tensors <= 2 ? 4 : (tensors == 3 ? 3 : 2);
