@@ -18,6 +18,7 @@
 //    epilogue (TMEM -> registers -> +bias/+addend -> fp32 NHWC global).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -104,6 +105,24 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same 2-D tile delivered to the same CTA-relative offset of every CTA in `mask` (and counted on
+// the mbarrier at the same offset in each of them)
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar,
+                                               int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmap_prefetch(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -141,6 +160,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+// ... on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)), "h"(mask)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -240,7 +266,20 @@ struct TcCfg {
   static constexpr uint32_t kTmemCols = kAccCols < 32 ? 32 : kAccCols;   // per accumulator buffer (x2)
 };
 
-template <int BN, int NPASS, bool STACK>
+// PAIR: launched as clusters of two CTAs that walk PAIRS of pixel tiles with the same output-channel
+// tile.  The weight tile of a stage is the same for both, so each CTA loads HALF of it (BN / 2 rows)
+// and TMA-multicasts that half into both CTAs' rings: the L2 -> shared-memory stream, which bounds
+// this kernel (one A box per tap: ~46 B/clk/SM measured against ~13 B/clk of DRAM), carries the
+// weights once per pair.  A stage may be refilled only when BOTH CTAs have consumed it, so every
+// MMA-done commit arrives on both CTAs' `empty` barriers (count 2).  Arithmetic per tile is
+// unchanged (bit-identical results).  MEASURED (tools/conv_table.py, EVE_B200_TC_PAIR=1): 2-8 %
+// slower on every 64- and 128-channel layer -- each SM still ingests the whole stage (its own A box,
+// its half of B and the peer's half), so what the multicast halves is L2 read traffic, not the bytes
+// through the SM's input port that actually pace the kernel, and the two rings advance in lockstep.
+// Kept behind `tc_pair` (default off) as the evidence.  cta_group::2 MMAs add nothing either:
+// measured (tools/probe_mma.py), an M = 256 pair instruction costs each SM the same 67 cycles at
+// N = 128 (46 vs 51 at N = 64): at N >= 128 the instruction already runs at the tensor pipe's rate.
+template <int BN, int NPASS, bool STACK, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -262,7 +301,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int iters = p.ntaps * p.kchunks;
-  const int total_tiles = p.tiles_m * p.tiles_co;
+  // work items: tiles (tm, tco), or for PAIR pair-rows (2 tm-tiles, tco) of which this CTA takes tile
+  // 2 * row + rank; all roles of both CTAs walk the same item sequence
+  const uint32_t rank = PAIR ? cluster_rank() : 0u;
+  const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total_tiles = (PAIR ? (p.tiles_m + 1) / 2 : p.tiles_m) * p.tiles_co;
 
   if (warp == 0 && lane == 0) {
     tmap_prefetch(&tmA_hi);
@@ -273,7 +317,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], PAIR ? 2 : 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
@@ -284,6 +328,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 1) tmem_alloc(tmem_slot, 2 * Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -291,11 +336,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===================== TMA producer =====================
     if (elect_one()) {
       const uint32_t rows = p.bw * p.bh * p.bn;
-      const uint32_t tx = (rows + (uint32_t)BN) * (uint32_t)(p.kc * 2) * Cfg::kPlanes;
+      const uint32_t tx_a = rows * (uint32_t)(p.kc * 2) * Cfg::kPlanes;
+      const uint32_t tx_b = (uint32_t)BN * (uint32_t)(p.kc * 2) * Cfg::kPlanes;
+      const uint32_t half_bytes = (uint32_t)(BN / 2) * (uint32_t)(p.kc * 2);
       uint32_t g = 0;   // global K-iteration counter: stage = g % kStages
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = item0; tile < total_tiles; tile += item_step) {
         const int tco = tile % p.tiles_co;
-        const int tm = tile / p.tiles_co;
+        const int tm = PAIR ? 2 * (tile / p.tiles_co) + (int)rank : tile / p.tiles_co;
+        const bool active = tm < p.tiles_m;
         const int h0 = (tm % p.tiles_h) * p.bh;
         const int n0 = (tm / p.tiles_h) * p.bn;
         const int co0 = tco * BN;
@@ -308,12 +356,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const int kc = it - tap * p.kchunks;
           const int wi = p.tap_dw[tap], hi = h0 * p.stride + p.tap_dh[tap];
           const int kb = p.tap_koff[tap] + kc * p.kc;
-          mbar_expect_tx(&full[s], tx);
-          tma_load_4d(st, &tmA_hi, &full[s], kc * p.kc, wi, hi, n0);
-          tma_load_2d(st + p.a_bytes * Cfg::kPlanes, &tmB_hi, &full[s], kb, co0);
-          if (NPASS == 3) {
-            tma_load_4d(st + p.a_bytes, &tmA_lo, &full[s], kc * p.kc, wi, hi, n0);
-            tma_load_2d(st + p.a_bytes * 2 + p.b_bytes, &tmB_lo, &full[s], kb, co0);
+          mbar_expect_tx(&full[s], (active ? tx_a : 0u) + tx_b);
+          if (active) {
+            tma_load_4d(st, &tmA_hi, &full[s], kc * p.kc, wi, hi, n0);
+            if (NPASS == 3) tma_load_4d(st + p.a_bytes, &tmA_lo, &full[s], kc * p.kc, wi, hi, n0);
+          }
+          if (PAIR) {
+            // this CTA's half of the weight tile, into both CTAs' stage s
+            const int cb = co0 + (int)rank * (BN / 2);
+            tma_load_2d_mc(st + p.a_bytes * Cfg::kPlanes + rank * half_bytes, &tmB_hi, &full[s], kb, cb, 3);
+            if (NPASS == 3)
+              tma_load_2d_mc(st + p.a_bytes * 2 + p.b_bytes + rank * half_bytes, &tmB_lo, &full[s], kb, cb, 3);
+          } else {
+            tma_load_2d(st + p.a_bytes * Cfg::kPlanes, &tmB_hi, &full[s], kb, co0);
+            if (NPASS == 3) tma_load_2d(st + p.a_bytes * 2 + p.b_bytes, &tmB_lo, &full[s], kb, co0);
           }
         }
       }
@@ -328,9 +384,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                             ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const int ksteps = p.kc >> 4;
     uint32_t g = 0, local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int tile = item0; tile < total_tiles; tile += item_step) {
+      if (PAIR && 2 * (tile / p.tiles_co) + (int)rank >= p.tiles_m) {
+        // no tile of its own in this pair-row: the CTA still receives (and supplies half of) the
+        // weight stages; release each one for both CTAs as soon as it has landed
+        for (int it = 0; it < iters; ++it, ++g) {
+          const int s = g % kStages;
+          mbar_wait(&full[s], (g / kStages) & 1);
+          if (elect_one()) umma_commit_mc(&empty[s], 3);
+          __syncwarp();
+        }
+        continue;
+      }
       const uint32_t buf = local & 1;
       const uint32_t use = local >> 1;
+      ++local;
       mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * Cfg::kTmemCols;
@@ -361,7 +429,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (it | k) != 0);
             }
           }
-          umma_commit(&empty[s]);
+          if (PAIR) umma_commit_mc(&empty[s], 3);
+          else umma_commit(&empty[s]);
           if (it == iters - 1) umma_commit(&tmem_full[buf]);
         }
         __syncwarp();
@@ -376,11 +445,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int in = m / (p.bw * p.bh);
     constexpr int CW = BN < 32 ? BN : 32;   // columns handled per TMEM load
     uint32_t local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int tile = item0; tile < total_tiles; tile += item_step) {
+      const int tco = tile % p.tiles_co;
+      const int tm = PAIR ? 2 * (tile / p.tiles_co) + (int)rank : tile / p.tiles_co;
+      if (PAIR && tm >= p.tiles_m) continue;
       const uint32_t buf = local & 1;
       const uint32_t use = local >> 1;
-      const int tco = tile % p.tiles_co;
-      const int tm = tile / p.tiles_co;
+      ++local;
       const int h = (tm % p.tiles_h) * p.bh + ih;
       const int n = (tm / p.tiles_h) * p.bn + in;
       const int co0 = tco * BN;
@@ -435,6 +506,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // nobody leaves while the peer may still write its ring / barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * Cfg::kTmemCols);
@@ -2497,12 +2569,40 @@ void pick_box(int N, int H, int W, int& bw, int& bh, int& bn) {
   }
 }
 
+template <int BN, int NPASS, bool STACK, bool PAIR>
+int launch_tc_kernel(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                     const CUtensorMap& b_lo, const TcParams& p, int grid, int smem_bytes,
+                     cudaStream_t s) {
+  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_kernel<BN, NPASS, STACK, PAIR>, 227 * 1024));
+  if (!PAIR) {
+    conv_tc_kernel<BN, NPASS, STACK, false><<<grid, kThreads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+    EVE_LAUNCH_CHECK();
+    return EVE_OK;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  EVE_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, NPASS, STACK, PAIR>, a_hi, a_lo, b_hi, b_lo, p));
+  count_launch();
+  return EVE_OK;
+}
+
+// pair: clusters of two CTAs sharing each weight stage (see conv_tc_kernel); the B maps then have
+// BN / 2-row boxes
 template <int BN, int NPASS, bool STACK>
 int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
               const CUtensorMap& b_lo, const TcParams& p0, int tiles_m, int tiles_co,
-              cudaStream_t s) {
+              cudaStream_t s, bool pair = false) {
   using Cfg = TcCfg<BN, NPASS, STACK>;
-  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_kernel<BN, NPASS, STACK>, 227 * 1024));
   TcParams p = p0;
   p.tiles_m = tiles_m;
   p.tiles_co = tiles_co;
@@ -2516,26 +2616,32 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
   const int cap = tc_stage_cap();
   if (p.stages > cap) p.stages = cap;
   const int smem_bytes = p.stages * p.stage_bytes + 1024 /*align*/ + kBarrierBytes;
+  if (pair) {
+    constexpr bool kHasPair = NPASS == 3 && ((BN == 128 && !STACK) || (BN == 64 && STACK));
+    if (kHasPair) {
+      const long long rows = (long long)((tiles_m + 1) / 2) * tiles_co;
+      const int pairs = (int)(rows < kNumSMs / 2 ? rows : kNumSMs / 2);
+      return launch_tc_kernel<BN, NPASS, STACK, kHasPair>(a_hi, a_lo, b_hi, b_lo, p, 2 * pairs, smem_bytes, s);
+    }
+  }
   const long long total = (long long)tiles_m * tiles_co;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);   // one persistent CTA per SM
-  conv_tc_kernel<BN, NPASS, STACK><<<grid, kThreads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
-  EVE_LAUNCH_CHECK();
-  return EVE_OK;
+  return launch_tc_kernel<BN, NPASS, STACK, false>(a_hi, a_lo, b_hi, b_lo, p, grid, smem_bytes, s);
 }
 
 template <int NPASS>
 int launch_tc_bn(int BN, bool stack, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                  const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcParams& p, int gx, int gy,
-                 cudaStream_t s) {
+                 cudaStream_t s, bool pair = false) {
   if (NPASS == 3 && stack) {
     switch (BN) {
-      case 64: return launch_tc<64, NPASS, true>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+      case 64: return launch_tc<64, NPASS, true>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s, pair);
       case 32: return launch_tc<32, NPASS, true>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
       default: return launch_tc<16, NPASS, true>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
     }
   }
   switch (BN) {
-    case 128: return launch_tc<128, NPASS, false>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
+    case 128: return launch_tc<128, NPASS, false>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s, pair);
     case 64: return launch_tc<64, NPASS, false>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
     case 32: return launch_tc<32, NPASS, false>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
     default: return launch_tc<16, NPASS, false>(a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
@@ -2606,12 +2712,20 @@ static int tc_launch(const TcParams& p0, const void* x_hi, const void* x_lo, int
   // Few pixel tiles (the per-time-step ConvRNN gate convolutions have 3): narrower output-channel
   // tiles put more SMs on the layer; each CTA's serial chain of MMAs shrinks by the same factor.
   while (BN > 16 && (long long)p.tiles_h * tiles_n * (p.Cout / BN) < kNumSMs / 2) BN >>= 1;
+  // CTA pairs sharing the weight stages: the split-operand kernels with 64 (stacked) or 128 output
+  // channels per tile, when every pair has at least one pair-row of tiles (a launch-shape decision
+  // only: the arithmetic per tile does not change, so it may depend on the batch)
+  const int popt = get_option(OPT_TC_PAIR);      // 2 = whenever there are two tiles (tests)
+  const long long pair_rows = (long long)((p.tiles_h * tiles_n + 1) / 2) * (p.Cout / BN);
+  const bool pair = popt != 0 && npass == 3 && ((BN == 128 && !stack) || (BN == 64 && stack)) &&
+                    p.tiles_h * tiles_n >= 2 && (popt == 2 || pair_rows >= kNumSMs / 2);
+  const int b_box = pair ? BN / 2 : BN;
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   if (win_bytes)
     EVE_TRY(make_map_windows(&a_hi, x_hi, inN, inH, inW, win_bytes, pitch_bytes, p.bw, p.bh, p.bn, fmt));
   else
     EVE_TRY(make_map_nhwc(&a_hi, x_hi, inN, inH, inW, p.Cin, p.kc, p.bw, p.bh, p.bn, p.stride, fmt));
-  EVE_TRY(make_map_2d(&b_hi, w_hi, wrows, wcols, p.kc, BN, fmt));
+  EVE_TRY(make_map_2d(&b_hi, w_hi, wrows, wcols, p.kc, b_box, fmt));
   if (npass == 3) {
     if (win_bytes)
       EVE_TRY(make_map_windows(&a_lo, x_lo, inN, inH, inW, win_bytes, pitch_bytes, p.bw, p.bh, p.bn,
@@ -2619,13 +2733,13 @@ static int tc_launch(const TcParams& p0, const void* x_hi, const void* x_lo, int
     else
       EVE_TRY(make_map_nhwc(&a_lo, x_lo, inN, inH, inW, p.Cin, p.kc, p.bw, p.bh, p.bn, p.stride,
                             fmt));
-    EVE_TRY(make_map_2d(&b_lo, w_lo, wrows, wcols, p.kc, BN, fmt));
+    EVE_TRY(make_map_2d(&b_lo, w_lo, wrows, wcols, p.kc, b_box, fmt));
   } else {
     a_lo = a_hi;
     b_lo = b_hi;
   }
   const int gx = p.tiles_h * tiles_n, gy = p.Cout / BN;
-  return npass == 3 ? launch_tc_bn<3>(BN, stack, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s)
+  return npass == 3 ? launch_tc_bn<3>(BN, stack, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s, pair)
                     : launch_tc_bn<1>(BN, false, a_hi, a_lo, b_hi, b_lo, p, gx, gy, s);
 }
 
@@ -2755,6 +2869,10 @@ static bool strip_plan(const ConvGeom& g, StripPlan& best, int force_kc = 0) {
   const int Wp = g.W + 2;
   const int usable = 227 * 1024 - 1024 - kBarrierBytes;
   best.score = -1.0;
+  // experiment switches (tools/probe_strip.py): force the strip height / chunk width
+  static const int env_r = [] { const char* e = getenv("EVE_B200_STRIP_R"); return e ? atoi(e) : 0; }();
+  static const int env_kc = [] { const char* e = getenv("EVE_B200_STRIP_KC"); return e ? atoi(e) : 0; }();
+  if (env_kc && !force_kc && g.Cin % env_kc == 0) force_kc = env_kc;
   const int kcs[3] = {64, 32, 16};
   for (int ki = 0; ki < 3; ++ki) {
     const int KC = kcs[ki];
@@ -2762,6 +2880,7 @@ static bool strip_plan(const ConvGeom& g, StripPlan& best, int force_kc = 0) {
     const int bsz = 2 * (BN * KC * 2 < 1024 ? 1024 : BN * KC * 2);
     for (int bn = 1; bn <= 16 && bn <= g.N; ++bn) {
       for (int R = (bn == 1 ? 1 : g.H); R <= g.H; ++R) {
+        if (env_r && bn == 1 && R != env_r && env_r <= g.H) continue;
         const int S = (R + 2) * Wp;
         const int Tmax = cdiv((long long)(bn - 1) * S + (long long)R * Wp, kTileM);
         const int acc = BN <= 64 ? 2 * BN : BN;        // stacked-B accumulators are twice as wide

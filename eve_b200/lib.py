@@ -77,6 +77,7 @@ SIGNATURES = {
     'eve_probe_mma_rate': (_I, [_I, _I, _I, _I, _I, _I, _P, _P]),
     'eve_probe_mma_rate_swizzle': (_I, [_I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'eve_probe_mma_rate_issuers': (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'eve_probe_mma_rate_pair': (_I, [_I, _I, _I, _I, _P, _P]),
     'eve_set_conv_mode': (None, [_I]),
     'eve_get_conv_mode': (_I, []),
     'eve_set_option': (_I, [C.c_char_p, _I]),

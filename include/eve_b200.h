@@ -68,6 +68,11 @@ int eve_probe_mma_rate_issuers(int n, int nmma, int reps, int a_shift_bytes, int
                                int row_bytes, int issuers, int grid, long long* cycles_out,
                                eve_stream_t stream);
 
+/* the same for CTA PAIRS (tcgen05.mma.cta_group::2, M = 256 over two SMs, B split in halves):
+ * `pairs` clusters of two CTAs; cycles_out[pairs] = span of each leader */
+int eve_probe_mma_rate_pair(int n, int nmma, int reps, int pairs, long long* cycles_out,
+                            eve_stream_t stream);
+
 /* ------------------------------------------------------------------ building blocks --
  * Exposed so that each kernel family can be parity-tested on its own.  NHWC fp32. */
 
@@ -112,6 +117,14 @@ int eve_get_conv_mode(void);
  *                                per sequence (x halves of the gate convolutions batched over
  *                                time, recurrence in shared memory / TMEM); 0 = one convolution
  *                                launch pair per time step
+ *   "tc_pair"             0..2   per-tap box kernel with 64 / 128 output channels per tile launched as
+ *                                clusters of two CTAs: each loads half of every weight stage and
+ *                                TMA-multicasts it to both (the kernel is bound by its L2 -> shared
+ *                                memory operand stream); bit-identical results.  0 = off (default:
+ *                                measured 2-8 % SLOWER per layer -- every SM still ingests the whole
+ *                                stage, so the multicast relieves L2 but not the SM's input port, and
+ *                                the two rings now advance in lockstep), 1 = when every pair has
+ *                                work, 2 = whenever a layer has two tiles
  *   "stem_windows"        0..2   EyeNet stem (7x7 stride 2, 3 channels) forward without an im2col
  *                                matrix: a filter row of an output pixel is one 32-value window
  *                                (8 pixels x 4 zero-padded channels) and the convolution a 7-tap

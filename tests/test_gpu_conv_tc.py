@@ -82,3 +82,54 @@ def test_mode_switch_is_visible():
     lib.eve_set_conv_mode(2)
     assert lib.eve_get_conv_mode() == 2
     lib.eve_set_conv_mode(prev)
+
+
+# (n, cin, h, w, cout, k[, stride]): geometries of the per-tap box kernel with 64 (stacked issue) or
+# 128 output channels per tile; odd tile counts leave one CTA of the last pair without a tile
+PAIR_CASES = [
+    (3, 64, 32, 32, 64, 3),      # 24 tiles
+    (5, 64, 32, 32, 64, 3),      # 40 tiles
+    (3, 128, 16, 16, 128, 3),    # 6 tiles
+    (5, 128, 16, 16, 128, 3),    # 10 tiles
+    (3, 256, 8, 8, 256, 3),      # two output-channel tiles, two images per pixel tile, ragged
+    (7, 512, 4, 4, 512, 3),      # four output-channel tiles, one ragged pixel tile
+    (3, 64, 32, 32, 128, 3, 2),  # stride 2
+    (3, 64, 32, 32, 128, 1, 2),  # 1x1 stride 2 (one K stage per tile)
+    (300, 64, 32, 32, 64, 3),    # 2400 tiles: every pair walks many pair-rows (the bench regime)
+]
+
+
+@pytest.mark.parametrize('case', PAIR_CASES)
+def test_weight_multicast_pairs_are_bit_identical(case, conv_mode):
+    """tc_pair: clusters of two CTAs that TMA-multicast each half of a weight stage to both rings.
+    Only the delivery of the B operand changes, so forward and data gradient must be bit-identical
+    to the single-CTA launch (and the single-CTA launch is held to fp64 by the tests above)."""
+    n, cin, h, w, cout, k = case[:6]
+    stride = case[6] if len(case) > 6 else 1
+    pad = k // 2
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(n, cin, h, w, generator=g).cuda()
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    dy = torch.randn(n, cout, oh, ow, generator=g).cuda()
+    conv_mode(1)
+    saved = L.get_option('tc_pair')
+    saved_strip = L.get_option('tc_strip')
+    try:
+        L.set_option('tc_strip', 0)          # keep these geometries on the box kernel
+        res = []
+        for mode in (0, 2):
+            L.set_option('tc_pair', mode)
+            y = G.conv_fwd(x, wt, b, stride, pad)
+            dx = G.conv_dgrad(dy, wt, (h, w), stride, pad)
+            torch.cuda.synchronize()
+            res.append((y, dx))
+        assert torch.equal(res[0][0], res[1][0])
+        assert torch.equal(res[0][1], res[1][1])
+        if n <= 8:
+            want = F.conv2d(x.double().cpu(), wt.double().cpu(), b.double().cpu(), stride=stride, padding=pad)
+            assert G.rel(res[1][0], want) < 3e-5
+    finally:
+        L.set_option('tc_pair', saved)
+        L.set_option('tc_strip', saved_strip)

@@ -12,7 +12,7 @@ from eve_b200 import lib as L            # noqa: E402
 from tests import gpu_util as G          # noqa: E402
 
 OPTIONS = ('tc_stage_cap', 'tc_row_kernel', 'tc_row_strips', 'tc_row_wgrad', 'tc_wgrad_waves',
-           'fused_planes', 'fused_norm', 'tc_strip', 'cgru_persistent', 'tc_wgrad_strip', 'in_stream', 'stem_windows')
+           'fused_planes', 'fused_norm', 'tc_strip', 'cgru_persistent', 'tc_wgrad_strip', 'in_stream', 'stem_windows', 'tc_pair')
 
 
 @pytest.fixture()
@@ -168,6 +168,7 @@ def _eve_step(cfg, seed=5, B=2, T=3):
 
 VARIANTS = [
     dict(in_stream=0),
+    dict(tc_pair=1),
     dict(stem_windows=0),
     dict(stem_windows=2),
     dict(in_stream=1),

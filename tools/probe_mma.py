@@ -39,3 +39,15 @@ for n in (16, 32, 64, 128):
         torch.cuda.synchronize()
         c = out.double().mean().item() / (nmma * reps)
         print('%4d %8d %10.2f %10.2f' % (n, iss, c, c / iss))
+
+print()
+print('CTA pairs (cta_group::2, M = 256 over two SMs, each CTA holds 128 rows of A and N/2 rows of B):')
+print('cycles per instruction = cycles each SM spends per M=128 x N x K=16 of work')
+print('%4s %6s %10s %14s' % ('N', 'pairs', 'cyc/mma', '1-CTA M=128'))
+single = {32: 43.7, 64: 51.4, 128: 68.3, 256: 132.2}
+for pairs in (74, 1):
+    for n in (32, 64, 128, 256):
+        nmma, reps = 96, 50
+        L.check(lib.eve_probe_mma_rate_pair(n, nmma, reps, pairs, L.ptr(out), L.stream_ptr()), 'probe')
+        torch.cuda.synchronize()
+        print('%4d %6d %10.2f %14.1f' % (n, pairs, out[:pairs].double().mean().item() / (nmma * reps), single[n]))

@@ -13,11 +13,14 @@ from tests import gpu_util as G      # noqa: E402
 
 lib = L.load()
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+import os
 GEOMS = [(480, 32, 32, 64, 64), (240, 36, 64, 64, 64), (240, 9, 16, 256, 256), (240, 18, 32, 128, 128),
          (480, 16, 16, 128, 128), (480, 8, 8, 256, 256), (480, 4, 4, 512, 512), (240, 36, 64, 128, 32),
          (240, 36, 64, 32, 64), (240, 36, 64, 32, 32), (240, 9, 16, 512, 128), (240, 18, 32, 256, 64),
          (240, 18, 32, 64, 128), (240, 9, 16, 128, 256), (240, 5, 8, 256, 256), (240, 18, 32, 64, 64),
          (240, 9, 16, 128, 128), (240, 5, 8, 128, 256), (3, 7, 10, 64, 64), (5, 9, 16, 32, 32)]
+if os.environ.get('PROBE_STRIP_GEOMS'):
+    GEOMS = [tuple(int(v) for v in t.split('x')) for t in os.environ['PROBE_STRIP_GEOMS'].split(',')]
 
 
 def timed(x, w, b, opt):
