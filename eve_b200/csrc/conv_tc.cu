@@ -339,7 +339,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const uint32_t tx_a = rows * (uint32_t)(p.kc * 2) * Cfg::kPlanes;
       const uint32_t tx_b = (uint32_t)BN * (uint32_t)(p.kc * 2) * Cfg::kPlanes;
       const uint32_t half_bytes = (uint32_t)(BN / 2) * (uint32_t)(p.kc * 2);
-      uint32_t g = 0;   // global K-iteration counter: stage = g % kStages
+      uint32_t s = 0, ph = 0;   // ring position, kept incrementally
       for (int tile = item0; tile < total_tiles; tile += item_step) {
         const int tco = tile % p.tiles_co;
         const int tm = PAIR ? 2 * (tile / p.tiles_co) + (int)rank : tile / p.tiles_co;
@@ -347,13 +347,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int h0 = (tm % p.tiles_h) * p.bh;
         const int n0 = (tm / p.tiles_h) * p.bn;
         const int co0 = tco * BN;
-        for (int it = 0; it < iters; ++it, ++g) {
-          const int s = g % kStages;
-          const uint32_t ph = (g / kStages) & 1;
+        int tap = 0, kc = 0;
+        for (int it = 0; it < iters; ++it) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * p.stage_bytes;
-          const int tap = it / p.kchunks;
-          const int kc = it - tap * p.kchunks;
           const int wi = p.tap_dw[tap], hi = h0 * p.stride + p.tap_dh[tap];
           const int kb = p.tap_koff[tap] + kc * p.kc;
           mbar_expect_tx(&full[s], (active ? tx_a : 0u) + tx_b);
@@ -371,6 +368,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             tma_load_2d(st + p.a_bytes * Cfg::kPlanes, &tmB_hi, &full[s], kb, co0);
             if (NPASS == 3) tma_load_2d(st + p.a_bytes * 2 + p.b_bytes, &tmB_lo, &full[s], kb, co0);
           }
+          if (++kc == p.kchunks) {
+            kc = 0;
+            ++tap;
+          }
+          if (++s == (uint32_t)kStages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
       }
     }
@@ -383,37 +388,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const uint32_t idesc2 = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
                             ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const int ksteps = p.kc >> 4;
-    uint32_t g = 0, local = 0;
-    for (int tile = item0; tile < total_tiles; tile += item_step) {
-      if (PAIR && 2 * (tile / p.tiles_co) + (int)rank >= p.tiles_m) {
-        // no tile of its own in this pair-row: the CTA still receives (and supplies half of) the
-        // weight stages; release each one for both CTAs as soon as it has landed
-        for (int it = 0; it < iters; ++it, ++g) {
-          const int s = g % kStages;
-          mbar_wait(&full[s], (g / kStages) & 1);
-          if (elect_one()) umma_commit_mc(&empty[s], 3);
-          __syncwarp();
+    // ONE elected lane runs the whole issue loop, waits included.  Measured (EVE_B200_TC_KC=32: twice
+    // the stages per tile made the 64-channel layers 1.44x slower): a ring stage cost ~370 cycles of
+    // issuer overhead next to ~480 cycles of MMAs -- an elect / reconverge pair, two runtime
+    // divisions, four descriptor encodings and the barrier round trip per stage, none of which
+    // overlaps the MMAs because the issuing thread does not run ahead of the tensor pipe.  Now: stage
+    // index and phase kept incrementally, descriptors = one hoisted constant + (address >> 4).
+    if (elect_one()) {
+      const uint64_t dconst = kmajor_desc(0u, p.kc);
+      const uint32_t smem16 = smem_u32(smem) >> 4;
+      const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
+      const uint32_t a16 = (uint32_t)p.a_bytes >> 4, b16 = (uint32_t)p.b_bytes >> 4;
+      uint32_t s = 0, ph = 0, local = 0;
+      for (int tile = item0; tile < total_tiles; tile += item_step) {
+        if (PAIR && 2 * (tile / p.tiles_co) + (int)rank >= p.tiles_m) {
+          // no tile of its own in this pair-row: the CTA still receives (and supplies half of) the
+          // weight stages; release each one for both CTAs as soon as it has landed
+          for (int it = 0; it < iters; ++it) {
+            mbar_wait(&full[s], ph);
+            umma_commit_mc(&empty[s], 3);
+            if (++s == (uint32_t)kStages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+          continue;
         }
-        continue;
-      }
-      const uint32_t buf = local & 1;
-      const uint32_t use = local >> 1;
-      ++local;
-      mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + buf * Cfg::kTmemCols;
-      for (int it = 0; it < iters; ++it, ++g) {
-        const int s = g % kStages;
-        const uint32_t ph = (g / kStages) & 1;
-        mbar_wait(&full[s], ph);
+        const uint32_t buf = local & 1;
+        const uint32_t use = local >> 1;
+        ++local;
+        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_hi = smem_u32(smem + s * p.stage_bytes);
-          const uint32_t b_hi = a_hi + p.a_bytes * Cfg::kPlanes;
-          const uint64_t da_hi = kmajor_desc(a_hi, p.kc);
-          const uint64_t db_hi = kmajor_desc(b_hi, p.kc);
-          const uint64_t da_lo = kmajor_desc(a_hi + p.a_bytes, p.kc);
-          const uint64_t db_lo = kmajor_desc(b_hi + p.b_bytes, p.kc);
+        const uint32_t tmem_d = tmem_base + buf * Cfg::kTmemCols;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t da_hi = dconst + (uint64_t)(smem16 + s * stage16);
+          const uint64_t da_lo = da_hi + a16;
+          const uint64_t db_hi = da_hi + a16 * Cfg::kPlanes;
+          const uint64_t db_lo = db_hi + b16;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t adv = (uint64_t)(k * 2);  // 16 elements = 32 bytes >> 4
             if (Cfg::kStack) {
@@ -432,8 +445,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (PAIR) umma_commit_mc(&empty[s], 3);
           else umma_commit(&empty[s]);
           if (it == iters - 1) umma_commit(&tmem_full[buf]);
+          if (++s == (uint32_t)kStages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
-        __syncwarp();
       }
     }
   } else {
@@ -2612,10 +2628,19 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
   // without padding (BN * kc * 2 is a multiple of every swizzle atom; a stage stays 1024-aligned)
   p.b_bytes = (Cfg::kStack || BN * p.kc * 2 >= 1024) ? BN * p.kc * 2 : 1024;
   p.stage_bytes = (p.a_bytes + p.b_bytes) * Cfg::kPlanes;
-  p.stages = (kSmemBudget - 1024 - kBarrierBytes) / p.stage_bytes;
+  // experiment switch: two persistent CTAs per SM, each with half the ring (two MMA issuers per SM)
+  static const int ctas = [] { const char* e = getenv("EVE_B200_TC_CTAS"); return e && atoi(e) == 2 ? 2 : 1; }();
+  const int per_sm = (ctas == 2 && !pair && 2 * 2 * (int)Cfg::kTmemCols <= 512 &&
+                      ((kSmemBudget / 2 - 1024 - kBarrierBytes) / p.stage_bytes) >= 3) ? 2 : 1;
+  p.stages = (kSmemBudget / per_sm - 1024 - kBarrierBytes) / p.stage_bytes;
   const int cap = tc_stage_cap();
   if (p.stages > cap) p.stages = cap;
   const int smem_bytes = p.stages * p.stage_bytes + 1024 /*align*/ + kBarrierBytes;
+  if (per_sm == 2) {
+    const long long total2 = (long long)tiles_m * tiles_co;
+    const int grid2 = (int)(total2 < 2 * kNumSMs ? total2 : 2 * kNumSMs);
+    return launch_tc_kernel<BN, NPASS, STACK, false>(a_hi, a_lo, b_hi, b_lo, p, grid2, smem_bytes, s);
+  }
   if (pair) {
     constexpr bool kHasPair = NPASS == 3 && ((BN == 128 && !STACK) || (BN == 64 && STACK));
     if (kHasPair) {
@@ -2704,6 +2729,11 @@ static int tc_launch(const TcParams& p0, const void* x_hi, const void* x_lo, int
   pick_box(p.N, p.OH, p.OW, p.bw, p.bh, p.bn);
   p.tiles_h = cdiv(p.OH, p.bh);
   p.kc = chunk_for(p.Cin);
+  {
+    // experiment switch: narrower K chunks (same sequence of K = 16 steps, smaller ring stages)
+    static const int env_kc = [] { const char* e = getenv("EVE_B200_TC_KC"); return e ? atoi(e) : 0; }();
+    if ((env_kc == 32 || env_kc == 16) && env_kc < p.kc && p.Cin % env_kc == 0) p.kc = env_kc;
+  }
   p.kchunks = p.Cin / p.kc;
   p.fmt = fmt;
   const int tiles_n = cdiv(p.N, p.bn);
