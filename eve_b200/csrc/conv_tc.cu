@@ -427,7 +427,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint64_t da_lo = da_hi + a16;
           const uint64_t db_hi = da_hi + a16 * Cfg::kPlanes;
           const uint64_t db_lo = db_hi + b16;
-          for (int k = 0; k < ksteps; ++k) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {              // kc <= 64: at most four K = 16 steps per stage
+            if (k >= ksteps) break;
             const uint64_t adv = (uint64_t)(k * 2);  // 16 elements = 32 bytes >> 4
             if (Cfg::kStack) {
               // [A_hi B_hi | A_hi B_lo] from one N = 2 BN instruction, then A_lo B_hi
@@ -974,31 +976,32 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     const uint32_t a16 = smem_u32(a_buf) >> 4, b16 = smem_u32(b_ring) >> 4;
     const uint32_t aplane16 = (uint32_t)p.a_plane_bytes >> 4;
     constexpr uint32_t bplane16 = (uint32_t)kBPlane >> 4;
-    uint32_t ga = 0, gb = 0, local = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++local) {
-      const int si = item / p.tiles_co;
-      const int h0 = (si % p.strips) * p.R;
-      const int n0 = (si / p.strips) * p.bn;
-      const int rows = min(p.R, p.H - h0), imgs = min(p.bn, p.N - n0);
-      const int T = ((imgs - 1) * p.S + rows * p.Wp + kTileM - 1) / kTileM;
-      const uint32_t set = p.nsets == 2 ? (local & 1) : 0u;
-      const uint32_t use = p.nsets == 2 ? (local >> 1) : local;
-      mbar_wait(&tmem_empty[set], (use & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_set = tmem_base + set * (uint32_t)(p.Tmax * kAcc);
-      for (int c = 0; c < p.kchunks; ++c, ++ga) {
-        const uint32_t buf = ga & 1;
-        mbar_wait(&a_full[buf], (ga >> 1) & 1);
-        const uint64_t a_desc = desc0 + (uint64_t)(a16 + buf * 2 * aplane16);
+    // one elected lane runs the whole loop, waits included; ring position kept incrementally (see
+    // conv_tc_kernel: per-stage issuer overhead does not overlap the MMAs)
+    if (elect_one()) {
+      uint32_t ga = 0, sb = 0, pb = 0, local = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++local) {
+        const int si = item / p.tiles_co;
+        const int h0 = (si % p.strips) * p.R;
+        const int n0 = (si / p.strips) * p.bn;
+        const int rows = min(p.R, p.H - h0), imgs = min(p.bn, p.N - n0);
+        const int T = ((imgs - 1) * p.S + rows * p.Wp + kTileM - 1) / kTileM;
+        const uint32_t set = p.nsets == 2 ? (local & 1) : 0u;
+        const uint32_t use = p.nsets == 2 ? (local >> 1) : local;
+        mbar_wait(&tmem_empty[set], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_set = tmem_base + set * (uint32_t)(p.Tmax * kAcc);
+        for (int c = 0; c < p.kchunks; ++c, ++ga) {
+          const uint32_t buf = ga & 1;
+          mbar_wait(&a_full[buf], (ga >> 1) & 1);
+          const uint64_t a_desc = desc0 + (uint64_t)(a16 + buf * 2 * aplane16);
+          uint32_t tap_off = 0;                     // (r * Wp + q) pixels
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap, ++gb) {
-          const uint32_t s = gb % (uint32_t)p.b_stages;
-          mbar_wait(&b_full[s], (gb / (uint32_t)p.b_stages) & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            const int r = tap / 3, q = tap - 3 * r;
-            const uint64_t a_tap = a_desc + (uint64_t)((uint32_t)(r * p.Wp + q) * kPix16);
-            const uint64_t b_tap = desc0 + (uint64_t)(b16 + s * 2 * bplane16);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint64_t a_tap = a_desc + (uint64_t)(tap_off * kPix16);
+            const uint64_t b_tap = desc0 + (uint64_t)(b16 + sb * 2 * bplane16);
             for (int t = 0; t < T; ++t) {
               const uint64_t a_t = a_tap + (uint64_t)((uint32_t)t * (uint32_t)kTileM * kPix16);
               const uint32_t tmem_d = tmem_set + (uint32_t)(t * kAcc);
@@ -1019,13 +1022,18 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
                 }
               }
             }
-            umma_commit(&b_empty[s]);
+            umma_commit(&b_empty[sb]);
             if (tap == 8) {
               umma_commit(&a_empty[buf]);
               if (c == p.kchunks - 1) umma_commit(&tmem_full[set]);
             }
+            if (++sb == (uint32_t)p.b_stages) {
+              sb = 0;
+              pb ^= 1u;
+            }
+            // next tap: one pixel to the right, or to the start of the next padded row
+            tap_off += (tap % 3 == 2) ? (uint32_t)(p.Wp - 2) : 1u;
           }
-          __syncwarp();
         }
       }
     }
@@ -1768,31 +1776,30 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
                            ((uint32_t)(p.nblk >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * p.nblk) >> 3) << 17);
     const int ksteps = p.rows >> 4;
-    for (int it = 0; it < iters; ++it) {
-      const int s = it % p.stages;
-      const uint32_t ph = (it / p.stages) & 1;
-      mbar_wait(&full[s], ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
-        const uint32_t a_lo = a_hi + a_bytes;
-        const uint32_t b_hi = a_hi + kPlanes * a_bytes;
-        const uint32_t b_lo = b_hi + bplane_bytes;
+    // one elected lane, ring position kept incrementally, descriptor constants hoisted (the issuer's
+    // per-stage and per-K-step overhead does not overlap the MMAs: see conv_tc_kernel)
+    if (elect_one()) {
+      const uint64_t dac = mnmajor_desc(0u, a_block, p.uw);
+      const uint64_t dbc = mnmajor_desc(0u, b_block, p.xw);
+      const uint32_t smem16 = smem_u32(smem) >> 4, stage16 = (uint32_t)stage_bytes >> 4;
+      const uint32_t a16 = (uint32_t)a_bytes >> 4, bp16 = (uint32_t)bplane_bytes >> 4;
+      const uint32_t ka16 = 2u * (uint32_t)p.uw, kb16 = 2u * (uint32_t)p.xw;   // 16 pixel rows, in 16-byte units
+      uint32_t s = 0, ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi16 = smem16 + s * stage16;
+        const uint32_t b_hi16 = a_hi16 + kPlanes * a16;
         for (int k = 0; k < ksteps; ++k) {
-          const uint32_t adva = (uint32_t)k * 16u * (uint32_t)(p.uw * 2);   // 16 pixel rows
-          const uint32_t advb = (uint32_t)k * 16u * (uint32_t)(p.xw * 2);
-          const uint64_t dah = mnmajor_desc(a_hi + adva, a_block, p.uw);
-          const uint64_t dbh = mnmajor_desc(b_hi + advb, b_block, p.xw);
+          const uint64_t dah = dac + (uint64_t)(a_hi16 + (uint32_t)k * ka16);
+          const uint64_t dbh = dbc + (uint64_t)(b_hi16 + (uint32_t)k * kb16);
           if (stack) {
             // [M_hi N_hi | M_hi N_lo] from one N = 2 nblk instruction, then M_lo N_hi
-            const uint64_t dal = mnmajor_desc(a_lo + adva, a_block, p.uw);
             umma_bf16(tmem_base, dah, dbh, idesc2, (it | k) != 0);
-            umma_bf16(tmem_base, dal, dbh, idesc, 1);
+            umma_bf16(tmem_base, dah + a16, dbh, idesc, 1);
           } else if (NPASS == 3) {
-            const uint64_t dal = mnmajor_desc(a_lo + adva, a_block, p.uw);
-            const uint64_t dbl = mnmajor_desc(b_lo + advb, b_block, p.xw);
-            umma_bf16(tmem_base, dal, dbh, idesc, (it | k) != 0);
-            umma_bf16(tmem_base, dah, dbl, idesc, 1);
+            umma_bf16(tmem_base, dah + a16, dbh, idesc, (it | k) != 0);
+            umma_bf16(tmem_base, dah, dbh + bp16, idesc, 1);
             umma_bf16(tmem_base, dah, dbh, idesc, 1);
           } else {
             umma_bf16(tmem_base, dah, dbh, idesc, (it | k) != 0);
@@ -1800,8 +1807,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmD_hi,
         }
         umma_commit(&empty[s]);
         if (it == iters - 1) umma_commit(tmem_full);
+        if (++s == (uint32_t)p.stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
-      __syncwarp();
     }
   } else {
     const int quad = warp & 3;
@@ -2280,17 +2290,17 @@ conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
       xdesc[b] = mnmajor_desc(0u, x_lbo, XW) + (uint64_t)((uint32_t)job.xoff[b] * kXPix16);
     }
     const int nblk = job.nblk;
-    uint32_t g = 0;
-    int in_chain = 0, chain = 0, done = 0;
-    for (int item = cta_in_job; item < p.items; item += ctas_in_job, ++g) {
-      const uint32_t s = g & 1;
-      if (in_chain == 0) {
-        mbar_wait(tmem_empty, ((uint32_t)chain & 1) ^ 1);       // the epilogue drained the accumulators
+    if (elect_one()) {                 // one lane runs the whole loop, waits included
+      uint32_t g = 0;
+      int in_chain = 0, chain = 0, done = 0;
+      for (int item = cta_in_job; item < p.items; item += ctas_in_job, ++g) {
+        const uint32_t s = g & 1;
+        if (in_chain == 0) {
+          mbar_wait(tmem_empty, ((uint32_t)chain & 1) ^ 1);       // the epilogue drained the accumulators
+          tc_fence_after();
+        }
+        mbar_wait(&full[s], (g >> 1) & 1);
         tc_fence_after();
-      }
-      mbar_wait(&full[s], (g >> 1) & 1);
-      tc_fence_after();
-      if (elect_one()) {
         const uint32_t st16 = ring16 + s * ((uint32_t)stage_bytes >> 4);
         const uint32_t x16 = st16 + 2 * dylo16;
         for (int ks = 0; ks < p.ksteps; ++ks) {
@@ -2315,15 +2325,13 @@ conv_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmD_hi,
           }
         }
         umma_commit(&empty[s]);
-      }
-      __syncwarp();
-      ++in_chain;
-      ++done;
-      if (in_chain == p.flush_items || done == my_items) {
-        if (elect_one()) umma_commit(tmem_full);
-        __syncwarp();
-        in_chain = 0;
-        ++chain;
+        ++in_chain;
+        ++done;
+        if (in_chain == p.flush_items || done == my_items) {
+          umma_commit(tmem_full);
+          in_chain = 0;
+          ++chain;
+        }
       }
     }
   } else {
