@@ -1248,21 +1248,20 @@ cgru_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_co
     const uint32_t act16[2] = {smem_u32(act1) >> 4, smem_u32(act2) >> 4};
     constexpr uint32_t kLo16W = (uint32_t)(kCgStageBytes / 2) >> 4;
     constexpr uint32_t kLo16A = (uint32_t)kCgActPlane >> 4;
-    uint32_t g = 0;
-    for (int t = 0; t < T; ++t) {
-      for (int conv = 0; conv < 2; ++conv) {
-        mbar_wait(&act_ready[conv], (uint32_t)t & 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(conv * 64);
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap, ++g) {
-          const uint32_t s = g % kCgStages;
-          mbar_wait(&full[s], (g / kCgStages) & 1);
+    if (elect_one()) {               // one lane runs the whole loop, waits included
+      uint32_t s = 0, ph = 0;
+      for (int t = 0; t < T; ++t) {
+        for (int conv = 0; conv < 2; ++conv) {
+          mbar_wait(&act_ready[conv], (uint32_t)t & 1);
           tc_fence_after();
-          if (elect_one()) {
-            const int rr = tap / 3, qq = tap - 3 * rr;
+          const uint32_t tmem_d = tmem_base + (uint32_t)(conv * 64);
+          uint32_t tap_off = 0;        // (r * Wp + q) padded positions
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
             const uint64_t w_hi = desc0 + (uint64_t)(ring16 + s * ((uint32_t)kCgStageBytes >> 4));
-            const uint64_t a_hi = desc0 + (uint64_t)(act16[conv] + (uint32_t)(rr * kCgWp + qq) * 8u);
+            const uint64_t a_hi = desc0 + (uint64_t)(act16[conv] + tap_off * 8u);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t dw_hi = w_hi + (uint64_t)(k * 2), dw_lo = dw_hi + kLo16W;
@@ -1273,8 +1272,12 @@ cgru_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_co
             }
             umma_commit(&empty[s]);
             if (tap == 8) umma_commit(&d_full[conv]);
+            if (++s == (uint32_t)kCgStages) {
+              s = 0;
+              ph ^= 1u;
+            }
+            tap_off += (tap % 3 == 2) ? (uint32_t)(kCgWp - 2) : 1u;
           }
-          __syncwarp();
         }
       }
     }
@@ -1502,19 +1505,18 @@ cgru_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW2_hi, const __grid_co
     const uint32_t g2_16 = smem_u32(g2p) >> 4, g1_16 = smem_u32(g1p) >> 4;
     constexpr uint32_t kLo16W = (uint32_t)(kCgBStage / 2) >> 4;
     constexpr uint32_t kLo16A = (uint32_t)kCgActPlane >> 4;
-    uint32_t g = 0;
-    for (int t = 0; t < T; ++t) {
-      for (int conv = 0; conv < 2; ++conv) {
-        mbar_wait(&act_ready[conv], (uint32_t)t & 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(conv * 64);
-        const int tiles = conv == 0 ? 9 : 18;
-#pragma unroll 1
-        for (int i = 0; i < tiles; ++i, ++g) {
-          const uint32_t s = g % kCgBStages;
-          mbar_wait(&full[s], (g / kCgBStages) & 1);
+    if (elect_one()) {               // one lane runs the whole loop, waits included
+      uint32_t s = 0, ph = 0;
+      for (int t = 0; t < T; ++t) {
+        for (int conv = 0; conv < 2; ++conv) {
+          mbar_wait(&act_ready[conv], (uint32_t)t & 1);
           tc_fence_after();
-          if (elect_one()) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)(conv * 64);
+          const int tiles = conv == 0 ? 9 : 18;
+#pragma unroll 1
+          for (int i = 0; i < tiles; ++i) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
             const int tap = conv == 0 ? i : (i >> 1);
             const int chunk = conv == 0 ? 0 : (i & 1);
             const int rr = tap / 3, qq = tap - 3 * rr;
@@ -1531,8 +1533,11 @@ cgru_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW2_hi, const __grid_co
             }
             umma_commit(&empty[s]);
             if (i == tiles - 1) umma_commit(&d_full[conv]);
+            if (++s == (uint32_t)kCgBStages) {
+              s = 0;
+              ph ^= 1u;
+            }
           }
-          __syncwarp();
         }
       }
     }
