@@ -246,6 +246,10 @@ constexpr int kThreads = 192;
 constexpr int kMaxStages = 24;
 constexpr int kSmemBudget = 224 * 1024;
 constexpr int kBarrierBytes = 512;     // (2 * kMaxStages + 4) mbarriers + the TMEM slot
+// box-kernel epilogue: per epilogue warp a 32 pixel x 32 channel fp32 transpose tile (4 KB) and the
+// 32 output row offsets of its pixels
+constexpr int kEpiTileBytes = 4 * 32 * 128;
+constexpr int kEpiBytes = kEpiTileBytes + 128 * 8;
 
 // Stacked-B issue (split operands, BN <= 64).  Measured on B200 (tools/probe_mma.py): with both
 // operands in shared memory one tcgen05.mma M=128 x N x K=16 costs max(N / 2, ~(4096 + 32 N) / 120)
@@ -297,6 +301,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* tmem_full = empty + kStages;          // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* epi = smem + kStages * p.stage_bytes + kBarrierBytes;   // transpose tiles + row offsets
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -462,6 +467,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int ih = (m / p.bw) % p.bh;
     const int in = m / (p.bw * p.bh);
     constexpr int CW = BN < 32 ? BN : 32;   // columns handled per TMEM load
+    // A TMEM lane is one output pixel: stored straight from the accumulator registers, every
+    // STG.128 of a warp touches 32 different 128-byte lines and half-fills a sector in each (ncu on
+    // the 64-channel layers: the epilogue warps were busy 77 % of the time, 42 % of that waiting for
+    // the store queue to read its registers, and handed accumulators back late).  Each warp now
+    // transposes a 32 pixel x CW channel chunk through a private XOR-swizzled shared-memory tile and
+    // does scale / bias / residual and the store with lane-contiguous 16-byte pieces (whole 64- or
+    // 128-byte runs per pixel, 512 bytes per instruction); the accumulator goes back to the MMA warp
+    // as soon as its last chunk is in registers.
+    constexpr int PP = CW / 4;              // 16-byte pieces per pixel and chunk
+    constexpr int PXP = 32 / PP;            // pixels per 512-byte pass
+    const uint32_t tile_s = smem_u32(epi) + (uint32_t)quad * (32 * 128);
+    unsigned long long* s_row = reinterpret_cast<unsigned long long*>(epi + kEpiTileBytes) + quad * 32;
+    auto swz = [](int px) { return PP == 4 ? ((px >> 1) & 3) : (px & 7); };
+    const int piece = lane % PP, prow = lane / PP;
+    const float scale = p.out_scale;        // a power of two: fma(v, scale, bias) rounds as v * scale + bias
     uint32_t local = 0;
     for (int tile = item0; tile < total_tiles; tile += item_step) {
       const int tco = tile % p.tiles_co;
@@ -476,11 +496,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const bool valid = in < p.bn && h < p.OH && n < p.N;
       const size_t row = ((size_t)(n * p.out_H + h * p.out_mul + p.out_ah) * p.out_W +
                           iw * p.out_mul + p.out_aw) * p.Cout + co0;
-      mbar_wait(&tmem_full[buf], use & 1);
-      tc_fence_after();
+      __syncwarp();                          // the previous tile's readers are done with s_row
+      s_row[lane] = valid ? (unsigned long long)row : ~0ull;
+      __syncwarp();
       const uint32_t tmem_d = tmem_base + buf * Cfg::kTmemCols + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        // everything the coalesced side needs from global memory is requested before the accumulator
+        // chunk is loaded (the shared-memory accesses below are ordering points for the compiler)
+        unsigned long long ro[PP];
+        float4 add4[PP];
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) {
+          const float* bp = p.bias + co0 + c0 + piece * 4;
+          b4 = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+        }
+#pragma unroll
+        for (int i = 0; i < PP; ++i) {
+          ro[i] = s_row[i * PXP + prow];
+          add4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.addend && ro[i] != ~0ull)
+            add4[i] = __ldg(reinterpret_cast<const float4*>(p.addend + (size_t)ro[i] + (size_t)(c0 + piece * 4)));
+        }
+        if (c0 == 0) {
+          mbar_wait(&tmem_full[buf], use & 1);
+          tc_fence_after();
+        }
         float v[32];
         tmem_ld32(tmem_d + (uint32_t)c0, v);
         if (Cfg::kStack) {
@@ -494,32 +535,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int j = 0; j < 32; ++j) v[j] += u[j];
           }
         }
-        if (valid) {
-          if (p.out_scale != 1.f) {
+        if (c0 + 32 >= BN) {
+          // all of this thread's TMEM reads have completed (tcgen05.wait::ld): release the buffer
+          tc_fence_before();
+          mbar_arrive_relaxed(&tmem_empty[buf]);
+        }
+        __syncwarp();                        // the previous chunk has been read out of the tile
 #pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] *= p.out_scale;
-          }
-          if (p.bias) {
+        for (int j = 0; j < PP; ++j)
+          sts128(tile_s + (uint32_t)(lane * (CW * 4) + ((j ^ swz(lane)) << 4)),
+                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        __syncwarp();
 #pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] += __ldg(p.bias + co0 + c0 + j);
-          }
-          if (p.addend) {
-            const float4* a4 = reinterpret_cast<const float4*>(p.addend + row + c0);
-#pragma unroll
-            for (int j = 0; j < CW / 4; ++j) {
-              float4 a = __ldg(a4 + j);
-              v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+        for (int i = 0; i < PP; ++i) {
+          const int px = i * PXP + prow;
+          float4 a = lds128(tile_s + (uint32_t)(px * (CW * 4) + ((piece ^ swz(px)) << 4)));
+          if (ro[i] != ~0ull) {
+            const size_t o = (size_t)ro[i] + (size_t)(c0 + piece * 4);
+            a.x = fmaf(a.x, scale, b4.x);
+            a.y = fmaf(a.y, scale, b4.y);
+            a.z = fmaf(a.z, scale, b4.z);
+            a.w = fmaf(a.w, scale, b4.w);
+            if (p.addend) {
+              a.x += add4[i].x; a.y += add4[i].y; a.z += add4[i].z; a.w += add4[i].w;
             }
+            *reinterpret_cast<float4*>(p.out + o) = a;
           }
-          float4* o4 = reinterpret_cast<float4*>(p.out + row + c0);
-#pragma unroll
-          for (int j = 0; j < CW / 4; ++j)
-            o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
       }
-      // all of this thread's TMEM reads have completed (tcgen05.wait::ld): release the buffer
-      tc_fence_before();
-      mbar_arrive_relaxed(&tmem_empty[buf]);
     }
   }
   tc_fence_before();
@@ -2644,11 +2687,11 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
   // experiment switch: two persistent CTAs per SM, each with half the ring (two MMA issuers per SM)
   static const int ctas = [] { const char* e = getenv("EVE_B200_TC_CTAS"); return e && atoi(e) == 2 ? 2 : 1; }();
   const int per_sm = (ctas == 2 && !pair && 2 * 2 * (int)Cfg::kTmemCols <= 512 &&
-                      ((kSmemBudget / 2 - 1024 - kBarrierBytes) / p.stage_bytes) >= 3) ? 2 : 1;
-  p.stages = (kSmemBudget / per_sm - 1024 - kBarrierBytes) / p.stage_bytes;
+                      ((kSmemBudget / 2 - 1024 - kBarrierBytes - kEpiBytes) / p.stage_bytes) >= 3) ? 2 : 1;
+  p.stages = (kSmemBudget / per_sm - 1024 - kBarrierBytes - kEpiBytes) / p.stage_bytes;
   const int cap = tc_stage_cap();
   if (p.stages > cap) p.stages = cap;
-  const int smem_bytes = p.stages * p.stage_bytes + 1024 /*align*/ + kBarrierBytes;
+  const int smem_bytes = p.stages * p.stage_bytes + 1024 /*align*/ + kBarrierBytes + kEpiBytes;
   if (per_sm == 2) {
     const long long total2 = (long long)tiles_m * tiles_co;
     const int grid2 = (int)(total2 < 2 * kNumSMs ? total2 : 2 * kNumSMs);
