@@ -940,6 +940,7 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   uint64_t* tmem_full = b_empty + p.b_stages;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* epi = reinterpret_cast<uint8_t*>(a_full) + kBarrierBytes;   // transpose tiles + row offsets
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1082,8 +1083,14 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     }
   } else {
     // ===================== epilogue (warps 3..6: TMEM lane quadrant = warp & 3) =====================
+    // as in conv_tc_kernel: 32-channel chunks transposed through a per-warp swizzled shared-memory
+    // tile, scale / bias / residual and the stores on lane-contiguous 16-byte pieces
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
+    const uint32_t tile_s = smem_u32(epi) + (uint32_t)quad * (32 * 128);
+    unsigned long long* s_row = reinterpret_cast<unsigned long long*>(epi + kEpiTileBytes) + quad * 32;
+    const int piece = lane & 7, prow = lane >> 3;
+    const float scale = p.out_scale;
     uint32_t local = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++local) {
       const int tco = item % p.tiles_co;
@@ -1095,8 +1102,6 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       const int co0 = tco * BN;
       const uint32_t set = p.nsets == 2 ? (local & 1) : 0u;
       const uint32_t use = p.nsets == 2 ? (local >> 1) : local;
-      mbar_wait(&tmem_full[set], use & 1);
-      tc_fence_after();
       const uint32_t tmem_set = tmem_base + set * (uint32_t)(p.Tmax * kAcc) + ((uint32_t)(quad * 32) << 16);
       for (int t = 0; t < T; ++t) {
         const int j = t * kTileM + m;            // position in the padded space of the item
@@ -1106,8 +1111,29 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         const int ww = rem - hh * p.Wp;
         const bool valid = i < imgs && hh < rows && ww < p.W;
         const size_t row = (((size_t)(n0 + i) * p.H + (h0 + hh)) * p.W + ww) * p.Cout + co0;
+        __syncwarp();                            // the previous tile's readers are done with s_row
+        s_row[lane] = valid ? (unsigned long long)row : ~0ull;
+        __syncwarp();
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
+          unsigned long long ro[8];
+          float4 add4[8];
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) {
+            const float* bp = p.bias + co0 + c0 + piece * 4;
+            b4 = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            ro[q] = s_row[q * 4 + prow];
+            add4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.addend && ro[q] != ~0ull)
+              add4[q] = __ldg(reinterpret_cast<const float4*>(p.addend + (size_t)ro[q] + (size_t)(c0 + piece * 4)));
+          }
+          if (t == 0 && c0 == 0) {
+            mbar_wait(&tmem_full[set], use & 1);
+            tc_fence_after();
+          }
           float v[32];
           tmem_ld32(tmem_set + (uint32_t)(t * kAcc + c0), v);
           if (kStack) {
@@ -1116,32 +1142,34 @@ conv_tc_strip_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) v[jj] += u[jj];
           }
-          if (valid) {
-            if (p.out_scale != 1.f) {
+          if (t == T - 1 && c0 + 32 >= BN) {
+            tc_fence_before();
+            mbar_arrive_relaxed(&tmem_empty[set]);   // the item's accumulators are all in registers
+          }
+          __syncwarp();                          // the previous chunk has been read out of the tile
 #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) v[jj] *= p.out_scale;
-            }
-            if (p.bias) {
+          for (int q = 0; q < 8; ++q)
+            sts128(tile_s + (uint32_t)(lane * 128 + ((q ^ (lane & 7)) << 4)),
+                   make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+          __syncwarp();
 #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) v[jj] += __ldg(p.bias + co0 + c0 + jj);
-            }
-            if (p.addend) {
-              const float4* a4 = reinterpret_cast<const float4*>(p.addend + row + c0);
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                const float4 a = __ldg(a4 + jj);
-                v[4 * jj] += a.x; v[4 * jj + 1] += a.y; v[4 * jj + 2] += a.z; v[4 * jj + 3] += a.w;
+          for (int q = 0; q < 8; ++q) {
+            const int px = q * 4 + prow;
+            float4 a = lds128(tile_s + (uint32_t)(px * 128 + ((piece ^ (px & 7)) << 4)));
+            if (ro[q] != ~0ull) {
+              const size_t o = (size_t)ro[q] + (size_t)(c0 + piece * 4);
+              a.x = fmaf(a.x, scale, b4.x);
+              a.y = fmaf(a.y, scale, b4.y);
+              a.z = fmaf(a.z, scale, b4.z);
+              a.w = fmaf(a.w, scale, b4.w);
+              if (p.addend) {
+                a.x += add4[q].x; a.y += add4[q].y; a.z += add4[q].z; a.w += add4[q].w;
               }
+              *reinterpret_cast<float4*>(p.out + o) = a;
             }
-            float4* o4 = reinterpret_cast<float4*>(p.out + row + c0);
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-              o4[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive_relaxed(&tmem_empty[set]);
     }
   }
   tc_fence_before();
@@ -2953,7 +2981,7 @@ static bool strip_plan(const ConvGeom& g, StripPlan& best, int force_kc = 0) {
   const int BN = strip_bn_for(g.Cout);
   if (BN == 0) return false;
   const int Wp = g.W + 2;
-  const int usable = 227 * 1024 - 1024 - kBarrierBytes;
+  const int usable = 227 * 1024 - 1024 - kBarrierBytes - kEpiBytes;
   best.score = -1.0;
   // experiment switches (tools/probe_strip.py): force the strip height / chunk width
   static const int env_r = [] { const char* e = getenv("EVE_B200_STRIP_R"); return e ? atoi(e) : 0; }();
@@ -3037,7 +3065,7 @@ static int launch_strip(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
                         const CUtensorMap& b_lo, const TcStripParams& p, cudaStream_t s) {
   EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_strip_kernel<BN, KC>, 227 * 1024));
   constexpr int kBPlane = BN * KC * 2 < 1024 ? 1024 : BN * KC * 2;
-  const int smem_bytes = 4 * p.a_plane_bytes + p.b_stages * 2 * kBPlane + 1024 + kBarrierBytes;
+  const int smem_bytes = 4 * p.a_plane_bytes + p.b_stages * 2 * kBPlane + 1024 + kBarrierBytes + kEpiBytes;
   const int grid = p.items < kNumSMs ? p.items : kNumSMs;
   conv_tc_strip_kernel<BN, KC><<<grid, kStripThreads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
   EVE_LAUNCH_CHECK();
