@@ -182,6 +182,7 @@ enum OptKey {
   OPT_TC_STRIP,              // padded-strip tcgen05 kernel for 3x3 stride-1 layers: 0 off, 1 auto, 2 whenever it fits
   OPT_TC_WGRAD_STRIP,        // padded-strip weight-gradient kernel (3x3 stride 1, 64 output channels)
   OPT_CGRU_PERSISTENT,       // ConvGRU (64 features, 5x8 maps): whole sequence in one persistent kernel
+  OPT_TC_DUAL,               // box kernel with two MMA-issuing warps (even / odd ring stages, two partial accumulators)
   OPT_TC_PAIR,               // box kernel as clusters of two CTAs that multicast the weight stages to each other
   OPT_STEM_WINDOWS,          // stem forward without an im2col matrix: 0 off, 1 one window per output column, 2 overlapping windows in the padded image
   OPT_IN_STREAM,             // InstanceNorm backward without shared-memory staging: 0 off, 1 maps that need one CTA per SM, 2 always (default)

@@ -283,11 +283,17 @@ struct TcCfg {
 // Kept behind `tc_pair` (default off) as the evidence.  cta_group::2 MMAs add nothing either:
 // measured (tools/probe_mma.py), an M = 256 pair instruction costs each SM the same 67 cycles at
 // N = 128 (46 vs 51 at N = 64): at N >= 128 the instruction already runs at the tensor pipe's rate.
-template <int BN, int NPASS, bool STACK, bool PAIR = false>
-__global__ void __launch_bounds__(kThreads, 1)
+// DUAL: TWO issuing warps (warp 1: even ring stages of a tile, warp 6: odd ones), each accumulating
+// into its own TMEM accumulator; the epilogue adds the two.  The issuing thread does not run ahead
+// of the tensor pipe, so one issuer's per-stage bookkeeping and barrier round trip now overlap the
+// other's MMAs (two issuers interleave at the pipe's rate: tools/probe_mma.py).
+template <int BN, int NPASS, bool STACK, bool PAIR = false, bool DUAL = false>
+__global__ void __launch_bounds__(DUAL ? kThreads + 32 : kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const TcParams p) {
+  static_assert(!(PAIR && DUAL), "the pair and the dual-issuer variants are not combined");
+  constexpr uint32_t kAccSets = DUAL ? 2u : 1u;      // partial accumulators per TMEM buffer
   // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator
   // is double-buffered in TMEM so the epilogue of tile i overlaps the K loop of tile i+1; the
   // shared-memory ring simply keeps rolling across tile boundaries.
@@ -325,12 +331,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(&empty[s], PAIR ? 2 : 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_full[b], DUAL ? 2 : 1);   // one commit per issuing warp
       mbar_init(&tmem_empty[b], 128);   // every epilogue thread arrives
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * Cfg::kTmemCols);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * kAccSets * Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();      // the peer's barriers exist before anything is multicast to them
@@ -384,8 +390,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (DUAL && warp == 6)) {
     // ===================== MMA issuer =====================
+    const int me = warp == 1 ? 0 : 1;     // DUAL: which half of a tile's stages this warp issues
     // instruction descriptor: D fp32, A/B fp16 or bf16 (format field 0 / 1), both K-major,
     // M = 128, N = BN
     const uint32_t idesc = (1u << 4) | ((uint32_t)p.fmt << 7) | ((uint32_t)p.fmt << 10) |
@@ -424,8 +431,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         ++local;
         mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * Cfg::kTmemCols;
+        const uint32_t tmem_d = tmem_base + (buf * kAccSets + (uint32_t)me) * Cfg::kTmemCols;
         for (int it = 0; it < iters; ++it) {
+          if (DUAL && (it & 1) != me) {      // the other issuer's stage
+            if (++s == (uint32_t)kStages) {
+              s = 0;
+              ph ^= 1u;
+            }
+            continue;
+          }
+          const int first = DUAL ? me : 0;   // this issuer's first stage of the tile starts its accumulator
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint64_t da_hi = dconst + (uint64_t)(smem16 + s * stage16);
@@ -438,25 +453,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const uint64_t adv = (uint64_t)(k * 2);  // 16 elements = 32 bytes >> 4
             if (Cfg::kStack) {
               // [A_hi B_hi | A_hi B_lo] from one N = 2 BN instruction, then A_lo B_hi
-              umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc2, (it | k) != 0);
+              umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc2, ((it - first) | k) != 0);
               umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);
             } else if (NPASS == 3) {
               // small terms first so they are not absorbed by a large partial sum
-              umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, (it | k) != 0);
+              umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, ((it - first) | k) != 0);
               umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
               umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, 1);
             } else {
-              umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (it | k) != 0);
+              umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, ((it - first) | k) != 0);
             }
           }
           if (PAIR) umma_commit_mc(&empty[s], 3);
           else umma_commit(&empty[s]);
-          if (it == iters - 1) umma_commit(&tmem_full[buf]);
+          if (!DUAL && it == iters - 1) umma_commit(&tmem_full[buf]);
           if (++s == (uint32_t)kStages) {
             s = 0;
             ph ^= 1u;
           }
         }
+        // DUAL: each issuer reports the end of ITS stages (an issuer without a stage -- a single-stage
+        // tile -- arrives at once and its accumulator is not read)
+        if (DUAL) umma_commit(&tmem_full[buf]);
       }
     }
   } else {
@@ -499,7 +517,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       __syncwarp();                          // the previous tile's readers are done with s_row
       s_row[lane] = valid ? (unsigned long long)row : ~0ull;
       __syncwarp();
-      const uint32_t tmem_d = tmem_base + buf * Cfg::kTmemCols + ((uint32_t)(quad * 32) << 16);
+      const uint32_t tmem_d = tmem_base + buf * kAccSets * Cfg::kTmemCols + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         // everything the coalesced side needs from global memory is requested before the accumulator
@@ -531,6 +549,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           } else {
             float u[32];
             tmem_ld32(tmem_d + (uint32_t)(BN + c0), u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += u[j];
+          }
+        }
+        if (DUAL && iters > 1) {             // the second issuer's partial sums
+          float u[32];
+          tmem_ld32(tmem_d + Cfg::kTmemCols + (uint32_t)c0, u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += u[j];
+          if (Cfg::kStack) {
+            tmem_ld32(tmem_d + Cfg::kTmemCols + (uint32_t)(BN + c0), u);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += u[j];
           }
@@ -570,7 +599,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (PAIR) cluster_sync_all();      // nobody leaves while the peer may still write its ring / barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * Cfg::kTmemCols);
+    tmem_dealloc(tmem_base, 2 * kAccSets * Cfg::kTmemCols);
   }
 }
 
@@ -2669,19 +2698,20 @@ void pick_box(int N, int H, int W, int& bw, int& bh, int& bn) {
   }
 }
 
-template <int BN, int NPASS, bool STACK, bool PAIR>
+template <int BN, int NPASS, bool STACK, bool PAIR, bool DUAL = false>
 int launch_tc_kernel(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                      const CUtensorMap& b_lo, const TcParams& p, int grid, int smem_bytes,
                      cudaStream_t s) {
-  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_kernel<BN, NPASS, STACK, PAIR>, 227 * 1024));
+  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_kernel<BN, NPASS, STACK, PAIR, DUAL>, 227 * 1024));
+  constexpr int threads = DUAL ? kThreads + 32 : kThreads;
   if (!PAIR) {
-    conv_tc_kernel<BN, NPASS, STACK, false><<<grid, kThreads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+    conv_tc_kernel<BN, NPASS, STACK, false, DUAL><<<grid, threads, smem_bytes, s>>>(a_hi, a_lo, b_hi, b_lo, p);
     EVE_LAUNCH_CHECK();
     return EVE_OK;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
@@ -2691,7 +2721,7 @@ int launch_tc_kernel(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  EVE_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, NPASS, STACK, PAIR>, a_hi, a_lo, b_hi, b_lo, p));
+  EVE_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, NPASS, STACK, PAIR, false>, a_hi, a_lo, b_hi, b_lo, p));
   count_launch();
   return EVE_OK;
 }
@@ -2735,6 +2765,11 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
   }
   const long long total = (long long)tiles_m * tiles_co;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);   // one persistent CTA per SM
+  // two issuing warps with one partial accumulator each (TMEM: 2 buffers x 2 x 128 columns); a property
+  // of the layer's tile shape only, never of the batch (the two partial sums round differently)
+  constexpr bool kHasDual = NPASS == 3 && ((BN == 128 && !STACK) || (BN == 64 && STACK));
+  if (kHasDual && get_option(OPT_TC_DUAL) != 0 && p.ntaps * p.kchunks >= 2)
+    return launch_tc_kernel<BN, NPASS, STACK, false, kHasDual>(a_hi, a_lo, b_hi, b_lo, p, grid, smem_bytes, s);
   return launch_tc_kernel<BN, NPASS, STACK, false>(a_hi, a_lo, b_hi, b_lo, p, grid, smem_bytes, s);
 }
 

@@ -116,8 +116,10 @@ def test_weight_multicast_pairs_are_bit_identical(case, conv_mode):
     conv_mode(1)
     saved = L.get_option('tc_pair')
     saved_strip = L.get_option('tc_strip')
+    saved_dual = L.get_option('tc_dual')
     try:
         L.set_option('tc_strip', 0)          # keep these geometries on the box kernel
+        L.set_option('tc_dual', 0)           # (the pair launch has one issuing warp: compare like with like)
         res = []
         for mode in (0, 2):
             L.set_option('tc_pair', mode)
@@ -133,3 +135,4 @@ def test_weight_multicast_pairs_are_bit_identical(case, conv_mode):
     finally:
         L.set_option('tc_pair', saved)
         L.set_option('tc_strip', saved_strip)
+        L.set_option('tc_dual', saved_dual)

@@ -12,7 +12,7 @@ from eve_b200 import lib as L            # noqa: E402
 from tests import gpu_util as G          # noqa: E402
 
 OPTIONS = ('tc_stage_cap', 'tc_row_kernel', 'tc_row_strips', 'tc_row_wgrad', 'tc_wgrad_waves',
-           'fused_planes', 'fused_norm', 'tc_strip', 'cgru_persistent', 'tc_wgrad_strip', 'in_stream', 'stem_windows', 'tc_pair')
+           'fused_planes', 'fused_norm', 'tc_strip', 'cgru_persistent', 'tc_wgrad_strip', 'in_stream', 'stem_windows', 'tc_pair', 'tc_dual')
 
 
 @pytest.fixture()
@@ -169,6 +169,7 @@ def _eve_step(cfg, seed=5, B=2, T=3):
 VARIANTS = [
     dict(in_stream=0),
     dict(tc_pair=1),
+    dict(tc_dual=0),
     dict(stem_windows=0),
     dict(stem_windows=2),
     dict(in_stream=1),
@@ -209,7 +210,7 @@ def test_option_variants_agree_on_a_full_training_step(variant, cfg, options):
     # (... and the window form of the stem sums its 7 x 32 products in another order than the
     # 160-wide patch matrix: 1e-7 on the EyeNet features, amplified the same way downstream)
     gtol = 3e-2 if ('fused_norm' in variant or 'fused_planes' in variant or 'tc_strip' in variant
-                    or 'cgru_persistent' in variant or 'stem_windows' in variant) \
+                    or 'cgru_persistent' in variant or 'stem_windows' in variant or 'tc_dual' in variant) \
         else 2e-3
     # biases in front of an InstanceNorm have an exactly zero gradient (the norm removes the
     # mean): what is computed there is cancellation noise ~1e-6 of the real gradients
