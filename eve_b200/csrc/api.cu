@@ -196,7 +196,7 @@ static Opt g_opts[OPT_COUNT] = {
     {"tc_strip", 1, 0, 2, "EVE_B200_TC_STRIP", false},
     {"tc_wgrad_strip", 1, 0, 1, "EVE_B200_TC_WGRAD_STRIP", false},
     {"cgru_persistent", 1, 0, 1, "EVE_B200_CGRU_PERSISTENT", false},
-    {"tc_dual", 1, 0, 1, "EVE_B200_TC_DUAL", false},
+    {"tc_dual", 0, 0, 1, "EVE_B200_TC_DUAL", false},
     {"tc_pair", 0, 0, 2, "EVE_B200_TC_PAIR", false},
     {"stem_windows", 1, 0, 2, "EVE_B200_STEM_WINDOWS", false},
     {"in_stream", 2, 0, 2, "EVE_B200_IN_STREAM", false},

@@ -65,8 +65,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef EVE_TC_DEBUG_SPIN
+  // debug builds: a protocol mistake reports the barrier instead of hanging the GPU
+  for (long long spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins > (1ll << 24)) {
+      printf("mbar_wait timeout: block %d warp %d bar+%u parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+             smem_u32(bar) & 0xFFFu, parity);
+      __trap();
+    }
+  }
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 // explicit shared-space vector accesses (a pointer derived from the dynamic shared-memory base
 // compiles to generic LD / ST, which queue behind the global stores of the epilogue)
@@ -284,9 +295,13 @@ struct TcCfg {
 // measured (tools/probe_mma.py), an M = 256 pair instruction costs each SM the same 67 cycles at
 // N = 128 (46 vs 51 at N = 64): at N >= 128 the instruction already runs at the tensor pipe's rate.
 // DUAL: TWO issuing warps (warp 1: even ring stages of a tile, warp 6: odd ones), each accumulating
-// into its own TMEM accumulator; the epilogue adds the two.  The issuing thread does not run ahead
-// of the tensor pipe, so one issuer's per-stage bookkeeping and barrier round trip now overlap the
-// other's MMAs (two issuers interleave at the pipe's rate: tools/probe_mma.py).
+// into its own TMEM accumulator; the epilogue adds the two.  The idea: the issuing thread does not
+// run ahead of the tensor pipe, so one issuer's per-stage bookkeeping and barrier round trip would
+// overlap the other's MMAs (two issuers interleave at the pipe's rate: tools/probe_mma.py).
+// MEASURED after the issue loop had been slimmed down: 4-11 % SLOWER on the 64-channel layers
+// (32.7 vs 32.3 ms per step) -- what is left between the MMAs is waiting for operands to enter the
+// SM, which a second issuer cannot hide, plus a second accumulator to drain.  Off by default
+// (`tc_dual`), kept with its test as the evidence.
 template <int BN, int NPASS, bool STACK, bool PAIR = false, bool DUAL = false>
 __global__ void __launch_bounds__(DUAL ? kThreads + 32 : kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -312,6 +327,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int iters = p.ntaps * p.kchunks;
+  // DUAL: a ring slot must always belong to the same issuer (an issuer that skipped a phase of a
+  // slot's barrier could not tell phase n from phase n - 2 by parity), so the ring depth is even and
+  // every tile occupies an EVEN number of ring positions: an odd stage count is padded with one
+  // empty position that the producer merely arrives on and its owner merely releases.  Then ring
+  // position parity == stage parity within the tile == issuer, for every tile, whatever the batch.
+  const int ring_iters = DUAL ? (iters + 1) & ~1 : iters;
   // work items: tiles (tm, tco), or for PAIR pair-rows (2 tm-tiles, tco) of which this CTA takes tile
   // 2 * row + rank; all roles of both CTAs walk the same item sequence
   const uint32_t rank = PAIR ? cluster_rank() : 0u;
@@ -359,8 +380,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int n0 = (tm / p.tiles_h) * p.bn;
         const int co0 = tco * BN;
         int tap = 0, kc = 0;
-        for (int it = 0; it < iters; ++it) {
+        for (int it = 0; it < ring_iters; ++it) {
           mbar_wait(&empty[s], ph ^ 1);
+          if (DUAL && it >= iters) {           // the pad position: no data, just complete the phase
+            mbar_arrive(&full[s]);
+            if (++s == (uint32_t)kStages) {
+              s = 0;
+              ph ^= 1u;
+            }
+            continue;
+          }
           uint8_t* st = smem + s * p.stage_bytes;
           const int wi = p.tap_dw[tap], hi = h0 * p.stride + p.tap_dh[tap];
           const int kb = p.tap_koff[tap] + kc * p.kc;
@@ -432,8 +461,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (buf * kAccSets + (uint32_t)me) * Cfg::kTmemCols;
-        for (int it = 0; it < iters; ++it) {
-          if (DUAL && (it & 1) != me) {      // the other issuer's stage
+        for (int it = 0; it < ring_iters; ++it) {
+          if (DUAL && (it & 1) != me) {      // the other issuer's ring position
             if (++s == (uint32_t)kStages) {
               s = 0;
               ph ^= 1u;
@@ -443,6 +472,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const int first = DUAL ? me : 0;   // this issuer's first stage of the tile starts its accumulator
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (DUAL && it >= iters) {         // the pad position: release it
+            umma_commit(&empty[s]);
+            if (++s == (uint32_t)kStages) {
+              s = 0;
+              ph ^= 1u;
+            }
+            continue;
+          }
           const uint64_t da_hi = dconst + (uint64_t)(smem16 + s * stage16);
           const uint64_t da_lo = da_hi + a16;
           const uint64_t db_hi = da_hi + a16 * Cfg::kPlanes;
@@ -2767,9 +2804,13 @@ int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMa
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);   // one persistent CTA per SM
   // two issuing warps with one partial accumulator each (TMEM: 2 buffers x 2 x 128 columns); a property
   // of the layer's tile shape only, never of the batch (the two partial sums round differently)
-  constexpr bool kHasDual = NPASS == 3 && ((BN == 128 && !STACK) || (BN == 64 && STACK));
-  if (kHasDual && get_option(OPT_TC_DUAL) != 0 && p.ntaps * p.kchunks >= 2)
+  // (64 stacked output channels: the ring is deep enough to be made even; the 128-channel tiles have
+  // three 64 KB stages)
+  constexpr bool kHasDual = NPASS == 3 && BN == 64 && STACK;
+  if (kHasDual && get_option(OPT_TC_DUAL) != 0 && p.ntaps * p.kchunks >= 2 && p.stages >= 4) {
+    p.stages &= ~1;
     return launch_tc_kernel<BN, NPASS, STACK, false, kHasDual>(a_hi, a_lo, b_hi, b_lo, p, grid, smem_bytes, s);
+  }
   return launch_tc_kernel<BN, NPASS, STACK, false>(a_hi, a_lo, b_hi, b_lo, p, grid, smem_bytes, s);
 }
 

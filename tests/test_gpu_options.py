@@ -169,7 +169,7 @@ def _eve_step(cfg, seed=5, B=2, T=3):
 VARIANTS = [
     dict(in_stream=0),
     dict(tc_pair=1),
-    dict(tc_dual=0),
+    dict(tc_dual=1),
     dict(stem_windows=0),
     dict(stem_windows=2),
     dict(in_stream=1),
