@@ -205,7 +205,7 @@ def reference_arm(args):
     k, frames, sec = _timed_reference_steps(cfg, sd, B, T, threads, args.steps, REF_BUDGET_S, 3)
     value = frames / sec
     sample = _reference_sample_text(B, T, threads, k, frames, sec)
-    print(json.dumps({
+    _emit({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': k, 'steps_requested': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * sec / k,
@@ -217,7 +217,7 @@ def reference_arm(args):
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                          'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------- B200 arm --
@@ -488,7 +488,7 @@ def leg_main(args):
     torch.cuda.set_device(0)
     from eve_b200 import lib as L
     L.load()
-    print(json.dumps(LEGS[args.leg](args, torch.device('cuda', 0))))
+    _emit(LEGS[args.leg](args, torch.device('cuda', 0)))
 
 
 def b200_arm(args):
@@ -681,13 +681,29 @@ def b200_arm(args):
         out['also'] = extra
     if world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(cfg, build_state_dict(cfg), args.batch, args.seq_len)
-    print(json.dumps(out))
+    _emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RECORD_OUT = None
+
+
+def _emit(record):
+    """The one JSON line of a run, on the process's original stdout."""
+    out = _RECORD_OUT if _RECORD_OUT is not None else sys.stdout
+    out.write(json.dumps(record) + '\n')
+    out.flush()
+
+
 def main():
     args = parse()
+    # stdout carries exactly ONE line, the JSON record: everything else a library writes to file
+    # descriptor 1 (the NCCL version banner under torchrun, for one) is sent to stderr instead
+    global _RECORD_OUT
+    sys.stdout.flush()
+    _RECORD_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
         reference_arm(args)
     elif args.leg:
