@@ -200,6 +200,7 @@ static Opt g_opts[OPT_COUNT] = {
     {"tc_pair", 0, 0, 2, "EVE_B200_TC_PAIR", false},
     {"stem_windows", 1, 0, 2, "EVE_B200_STEM_WINDOWS", false},
     {"in_stream", 2, 0, 2, "EVE_B200_IN_STREAM", false},
+    {"stem_fused_bwd", 1, 0, 1, "EVE_B200_STEM_FUSED_BWD", false},
 };
 int get_option(int key) {
   if (key < 0 || key >= OPT_COUNT) return 0;
@@ -373,6 +374,21 @@ extern "C" int eve_in_relu_maxpool_fwd(const float* x, int n, int h, int w, int 
   cudaStream_t s = as_stream(stream);
   EVE_TRY(in_stats(x, n, h * w, c, mean, rstd, s));
   return in_relu_maxpool(x, n, h, w, c, mean, rstd, y, idx, s);
+}
+
+extern "C" int eve_in_relu_maxpool_bwd(const float* dy, const float* y, const int32_t* idx,
+                                       const float* x, int n, int h, int w, int c,
+                                       const float* mean, const float* rstd, float* dx,
+                                       uint16_t* dx_hi, uint16_t* dx_lo, float* scratch,
+                                       eve_stream_t stream) {
+  EVE_REQUIRE(dy && y && idx && x && mean && rstd && scratch && (dx || dx_hi), EVE_ERR_NULL,
+              "in_relu_maxpool_bwd: NULL pointer");
+  EVE_REQUIRE(n >= 0 && h > 0 && w > 0 && c > 0 && c % 4 == 0 && h % 2 == 0 && w % 2 == 0,
+              EVE_ERR_SHAPE, "in_relu_maxpool_bwd: bad shape n=%d h=%d w=%d c=%d (h, w even)", n, h,
+              w, c);
+  if (n == 0) return EVE_OK;
+  return stem_pool_in_backward(dy, y, idx, x, n, h, w, c, mean, rstd, dx, dx_hi, dx_lo, scratch,
+                               as_stream(stream));
 }
 
 extern "C" int eve_adaptive_maxpool_fwd(const float* x, int n, int h, int w, int c, int oh, int ow,

@@ -186,6 +186,7 @@ enum OptKey {
   OPT_TC_PAIR,               // box kernel as clusters of two CTAs that multicast the weight stages to each other
   OPT_STEM_WINDOWS,          // stem forward without an im2col matrix: 0 off, 1 one window per output column, 2 overlapping windows in the padded image
   OPT_IN_STREAM,             // InstanceNorm backward without shared-memory staging: 0 off, 1 maps that need one CTA per SM, 2 always (default)
+  OPT_STEM_FUSED_BWD,        // EyeNet stem backward: max-pool gather inside the norm's backward, sums taken over pool windows, dy planes written directly
   OPT_COUNT
 };
 int get_option(int key);
@@ -216,6 +217,13 @@ int conv_dgrad(const ConvGeom& g, const float* dy, const float* w_oihw, const fl
                float* dx, const ConvScratch& sc, cudaStream_t s);
 int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw_oihw, float* dbias,
                bool accumulate, const ConvScratch& sc, cudaStream_t s);
+// The stem's weight gradient from dy planes its producer wrote (stem_pool_in_backward):
+// conv_wgrad_stem_planes() tells where they go inside `sc`, conv_wgrad_stem_run() consumes them.
+bool conv_wgrad_stem_takes_planes(const ConvGeom& g);
+int conv_wgrad_stem_planes(const ConvGeom& g, const ConvScratch& sc, uint16_t** d_hi,
+                           uint16_t** d_lo);
+int conv_wgrad_stem_run(const ConvGeom& g, const float* x, float* dw, bool accumulate,
+                        const ConvScratch& sc, cudaStream_t s);
 // Plane-to-plane entry points (split tensor-core path only; conv_x_fusable(g) must hold): the
 // producers of x / dy have already written the 16-bit hi/lo NHWC planes (x: fp16 for the forward
 // pass, bf16 for the backward pass; dy: bf16).  Bias gradients come from the producer of dy.
@@ -315,6 +323,16 @@ int in_backward(const float* dy, const float* y_for_mask, const float* x, int N,
                 int act, const float* addend, float* dx, float* g_out, float* dgamma,
                 float* dbeta, float* scratch, bool accumulate_affine, cudaStream_t s);
 size_t in_backward_scratch_floats(int N, int C);
+// Backward of  p = maxpool3x3s2p1(relu(IN(x)))  (non-affine norm; torchvision ResNet stem,
+// eye_net.py:48-50) in two kernels: the two per-(n, c) sums of the norm's backward are taken over
+// the POOL WINDOWS (only the argmax of a window carries gradient, and its normalised value is the
+// pooled output p itself), then one pass gathers the pooled gradient per pixel and writes the
+// norm's input gradient as fp32 (dx) and / or as the bf16 hi / lo planes the stem's weight
+// gradient reads (d_lo may be NULL).  H and W even.  scratch: in_backward_scratch_floats(N, C).
+int stem_pool_in_backward(const float* dpool, const float* pooled, const int32_t* idx,
+                          const float* x, int N, int H, int W, int C, const float* mean,
+                          const float* rstd, float* dx, uint16_t* d_hi, uint16_t* d_lo,
+                          float* scratch, cudaStream_t s);
 
 // ------------------------------------------------------------------------------ pools --
 int nchw_to_nhwc(const float* x, int N, int C, int H, int W, float* y, cudaStream_t s);

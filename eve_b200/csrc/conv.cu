@@ -446,6 +446,64 @@ int conv_dgrad(const ConvGeom& g, const float* dy, const float* w, const float* 
   return conv_dgrad_simt(g, dy, g.Cout, wd, addend, dx, s);
 }
 
+// ---- the stem's weight gradient on the tensor cores: bf16 hi/lo planes of dy (split here, or
+// written directly by the producer of dy: stem_pool_in_backward) x the bf16 patch matrix of x
+struct StemWgradCarve {
+  float* part;
+  uint16_t *d_hi, *d_lo, *x_hi, *x_lo;
+};
+
+bool conv_wgrad_stem_takes_planes(const ConvGeom& g) {
+  return conv_mode() != 0 && (tc_mask() & 4) && !conv_tc_wgrad_supported(g) && is_stem(g) &&
+         conv_tc_wgrad_supported(stem_gemm(g));
+}
+
+static bool carve_stem_wgrad(const ConvGeom& g, const ConvScratch& sc, StemWgradCarve& k) {
+  Carve c{sc.base, sc.base + sc.bytes};
+  const int npass = conv_mode() == 1 ? 3 : 1;
+  const ConvGeom gg = stem_gemm(g);
+  size_t pf = conv_tc_wgrad_partial_floats(gg);
+  size_t cs = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
+  k.part = c.get<float>(pf > cs ? pf : cs);
+  k.d_hi = c.get<uint16_t>((size_t)g.out_elems());
+  k.d_lo = c.get<uint16_t>((size_t)g.out_elems());
+  k.x_hi = c.get<uint16_t>((size_t)gg.in_elems());
+  k.x_lo = c.get<uint16_t>((size_t)gg.in_elems());
+  if (!k.x_lo) return false;
+  if (npass != 3) k.d_lo = k.x_lo = nullptr;
+  return true;
+}
+
+int conv_wgrad_stem_planes(const ConvGeom& g, const ConvScratch& sc, uint16_t** d_hi,
+                           uint16_t** d_lo) {
+  StemWgradCarve k;
+  EVE_REQUIRE(conv_wgrad_stem_takes_planes(g) && carve_stem_wgrad(g, sc, k), EVE_ERR_WORKSPACE,
+              "conv_wgrad_stem_planes: not the tensor-core stem path, or scratch too small");
+  *d_hi = k.d_hi;
+  *d_lo = k.d_lo;
+  return EVE_OK;
+}
+
+int conv_wgrad_stem_run(const ConvGeom& g, const float* x, float* dw, bool accumulate,
+                        const ConvScratch& sc, cudaStream_t s) {
+  StemWgradCarve k;
+  EVE_REQUIRE(conv_wgrad_stem_takes_planes(g) && carve_stem_wgrad(g, sc, k), EVE_ERR_WORKSPACE,
+              "conv_wgrad(stem): scratch too small");
+  const int npass = conv_mode() == 1 ? 3 : 1;
+  const ConvGeom gg = stem_gemm(g);
+  stem_im2col_kernel<<<g.N * g.OH, 256, 7 * g.W * 3 * sizeof(float), s>>>(
+      x, g.H, g.W, g.OH, g.OW, TC_BF16, k.x_hi, k.x_lo);
+  EVE_LAUNCH_CHECK();
+  int splits = 0;
+  ProfScope prof(PROF_CONV_WGRAD, 2.0 * g.out_elems() * (double)g.K(),
+                 4.0 * (g.in_elems() + g.out_elems() + (double)g.Cout * g.K()), s, &g);
+  EVE_TRY(conv_tc_wgrad_run(gg, k.d_hi, k.d_lo, k.x_hi, k.x_lo, k.part, npass, &splits, s));
+  stem_wgrad_reduce_kernel<<<cdiv(g.Cout * 147, 256), 256, 0, s>>>(k.part, splits, g.Cout, dw,
+                                                                  accumulate ? 1 : 0);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
 int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, float* dbias,
                bool accumulate, const ConvScratch& sc, cudaStream_t s) {
   Carve c{sc.base, sc.base + sc.bytes};
@@ -476,32 +534,13 @@ int conv_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, fl
       EVE_TRY(colsum(dy, (long long)g.N * g.OH * g.OW, g.Cout, g.Cout, dbias, part, accumulate, s));
     return EVE_OK;
   }
-  if (dw && mode != 0 && (tc_mask() & 4) && is_stem(g) && conv_tc_wgrad_supported(stem_gemm(g))) {
-    const int npass = mode == 1 ? 3 : 1;
-    const ConvGeom gg = stem_gemm(g);
-    size_t pf = conv_tc_wgrad_partial_floats(gg);
-    size_t cs = colsum_scratch_floats((long long)g.N * g.OH * g.OW, g.Cout);
-    float* part = c.get<float>(pf > cs ? pf : cs);
-    uint16_t* d_hi = c.get<uint16_t>((size_t)g.out_elems());
-    uint16_t* d_lo = c.get<uint16_t>((size_t)g.out_elems());
-    uint16_t* x_hi = c.get<uint16_t>((size_t)gg.in_elems());
-    uint16_t* x_lo = c.get<uint16_t>((size_t)gg.in_elems());
-    EVE_REQUIRE(x_lo, EVE_ERR_WORKSPACE, "conv_wgrad(stem): scratch too small");
-    EVE_TRY(split_planes(dy, g.out_elems(), d_hi, npass == 3 ? d_lo : nullptr, TC_BF16, s));
-    stem_im2col_kernel<<<g.N * g.OH, 256, 7 * g.W * 3 * sizeof(float), s>>>(
-        x, g.H, g.W, g.OH, g.OW, TC_BF16, x_hi, npass == 3 ? x_lo : nullptr);
-    EVE_LAUNCH_CHECK();
-    int splits = 0;
-    {
-      ProfScope prof(PROF_CONV_WGRAD, 2.0 * g.out_elems() * (double)g.K(),
-                     4.0 * (g.in_elems() + g.out_elems() + (double)g.Cout * g.K()), s, &g);
-      EVE_TRY(conv_tc_wgrad_run(gg, d_hi, d_lo, x_hi, x_lo, part, npass, &splits, s));
-      stem_wgrad_reduce_kernel<<<cdiv(g.Cout * 147, 256), 256, 0, s>>>(part, splits, g.Cout, dw,
-                                                                      accumulate ? 1 : 0);
-      EVE_LAUNCH_CHECK();
-    }
+  if (dw && conv_wgrad_stem_takes_planes(g)) {
+    StemWgradCarve k;
+    EVE_REQUIRE(carve_stem_wgrad(g, sc, k), EVE_ERR_WORKSPACE, "conv_wgrad(stem): scratch too small");
+    EVE_TRY(split_planes(dy, g.out_elems(), k.d_hi, k.d_lo, TC_BF16, s));
+    EVE_TRY(conv_wgrad_stem_run(g, x, dw, accumulate, sc, s));
     if (dbias)
-      EVE_TRY(colsum(dy, (long long)g.N * g.OH * g.OW, g.Cout, g.Cout, dbias, part, accumulate, s));
+      EVE_TRY(colsum(dy, (long long)g.N * g.OH * g.OW, g.Cout, g.Cout, dbias, k.part, accumulate, s));
     return EVE_OK;
   }
   size_t need = conv_wgrad_scratch_floats(g);

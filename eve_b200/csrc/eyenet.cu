@@ -433,10 +433,25 @@ extern "C" int eve_eyenet_cnn_bwd(const eve_eyenet_cnn_params* p, const float* d
   if (gr[0]) {
     const int OH = t.stem.OH, OW = t.stem.OW;
     const int PH = (OH + 2 - 3) / 2 + 1, PW = (OW + 2 - 3) / 2 + 1;
-    EVE_TRY(maxpool_bwd_scatter(dout, t.pidx, N, OH, OW, PH, PW, 64, sc.stem_g, s));
-    EVE_TRY(in_backward(sc.stem_g, nullptr, t.c1, N, OH * OW, 64, t.c1m, t.c1r, nullptr, nullptr,
-                        ACT_RELU, nullptr, sc.stem_d, nullptr, nullptr, nullptr, sc.inb, false, s));
-    EVE_TRY(conv_wgrad(t.stem, t.x, sc.stem_d, gr[0], nullptr, acc, sc.cs, s));
+    if (get_option(OPT_STEM_FUSED_BWD) && OH % 2 == 0 && OW % 2 == 0) {
+      // no dense un-pooled gradient: window sums + one gather pass (norm.cu)
+      if (conv_wgrad_stem_takes_planes(t.stem)) {
+        uint16_t *d_hi, *d_lo;
+        EVE_TRY(conv_wgrad_stem_planes(t.stem, sc.cs, &d_hi, &d_lo));
+        EVE_TRY(stem_pool_in_backward(dout, t.p, t.pidx, t.c1, N, OH, OW, 64, t.c1m, t.c1r, nullptr,
+                                      d_hi, d_lo, sc.inb, s));
+        EVE_TRY(conv_wgrad_stem_run(t.stem, t.x, gr[0], acc, sc.cs, s));
+      } else {
+        EVE_TRY(stem_pool_in_backward(dout, t.p, t.pidx, t.c1, N, OH, OW, 64, t.c1m, t.c1r,
+                                      sc.stem_d, nullptr, nullptr, sc.inb, s));
+        EVE_TRY(conv_wgrad(t.stem, t.x, sc.stem_d, gr[0], nullptr, acc, sc.cs, s));
+      }
+    } else {
+      EVE_TRY(maxpool_bwd_scatter(dout, t.pidx, N, OH, OW, PH, PW, 64, sc.stem_g, s));
+      EVE_TRY(in_backward(sc.stem_g, nullptr, t.c1, N, OH * OW, 64, t.c1m, t.c1r, nullptr, nullptr,
+                          ACT_RELU, nullptr, sc.stem_d, nullptr, nullptr, nullptr, sc.inb, false, s));
+      EVE_TRY(conv_wgrad(t.stem, t.x, sc.stem_d, gr[0], nullptr, acc, sc.cs, s));
+    }
   }
   conv_prepared_clear();
   return EVE_OK;

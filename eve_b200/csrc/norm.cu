@@ -395,6 +395,172 @@ in_affine_grad_kernel(const float* __restrict__ sum_g, const float* __restrict__
   }
 }
 
+// ---- backward of  p = maxpool3x3s2p1(relu(IN(x)))  without the dense un-pooled gradient map.
+// Only the argmax pixel of a pool window carries gradient, ReLU passes it iff the pooled value is
+// positive, and the normalised value at that pixel IS the pooled value (no affine terms), so
+//     sum_pixels g = sum_windows dp [p > 0]           sum_pixels g xhat = sum_windows dp p
+// : the reductions read the two pooled tensors (a quarter of the map each) instead of the map
+// and its gradient.  Same thread layout and fp64 accumulation as in_bwd_reduce_kernel.
+__global__ void __launch_bounds__(256)
+stem_pool_sums_kernel(const float* __restrict__ dp, const float* __restrict__ pooled, int OHW, int C,
+                      int CQ, float* __restrict__ sum_g, float* __restrict__ sum_gx) {
+  __shared__ double s1[256 * 4];
+  __shared__ double s2[256 * 4];
+  const int n = blockIdx.x;
+  const int ql = threadIdx.x % CQ;
+  const int q = blockIdx.y * CQ + ql;
+  const int lane = threadIdx.x / CQ;
+  const int L = 256 / CQ;
+  const int C4 = C >> 2;
+  const size_t base4 = (size_t)n * OHW * C4;
+  const float4* dq = reinterpret_cast<const float4*>(dp) + base4;
+  const float4* pq = reinterpret_cast<const float4*>(pooled) + base4;
+  double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+  if (q < C4) {
+    auto body = [&](const float4& d4, const float4& p4) {
+      const float d[4] = {d4.x, d4.y, d4.z, d4.w}, pv[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float g = pv[j] > 0.f ? d[j] : 0.f;
+        a[j] += (double)g;
+        b[j] += (double)g * (double)pv[j];
+      }
+    };
+    int w = lane;
+    for (; w + 3 * L < OHW; w += 4 * L) {
+      const size_t o = (size_t)w * C4 + q, st = (size_t)L * C4;
+      float4 d0 = __ldg(dq + o), d1 = __ldg(dq + o + st), d2 = __ldg(dq + o + 2 * st),
+             d3 = __ldg(dq + o + 3 * st);
+      float4 p0 = __ldg(pq + o), p1 = __ldg(pq + o + st), p2 = __ldg(pq + o + 2 * st),
+             p3 = __ldg(pq + o + 3 * st);
+      body(d0, p0);
+      body(d1, p1);
+      body(d2, p2);
+      body(d3, p3);
+    }
+    for (; w < OHW; w += L) {
+      const size_t o = (size_t)w * C4 + q;
+      body(__ldg(dq + o), __ldg(pq + o));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s1[threadIdx.x * 4 + j] = a[j];
+    s2[threadIdx.x * 4 + j] = b[j];
+  }
+  __syncthreads();
+  for (int half = L >> 1; half >= 1; half >>= 1) {
+    if (lane < half) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a[j] += s1[((lane + half) * CQ + ql) * 4 + j];
+        b[j] += s2[((lane + half) * CQ + ql) * 4 + j];
+        s1[threadIdx.x * 4 + j] = a[j];
+        s2[threadIdx.x * 4 + j] = b[j];
+      }
+    }
+    __syncthreads();
+  }
+  if (lane == 0 && q < C4) {
+    reinterpret_cast<float4*>(sum_g + (size_t)n * C)[q] =
+        make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
+    reinterpret_cast<float4*>(sum_gx + (size_t)n * C)[q] =
+        make_float4((float)b[0], (float)b[1], (float)b[2], (float)b[3]);
+  }
+}
+
+// One thread = a 2x2 pixel block x 4 channels.  The block's pixels are touched by the four
+// windows (a, b), (a, b+1), (a+1, b), (a+1, b+1) only (pixel (2a+i, 2b+j) by rows a..a+i, columns
+// b..b+j), so each window's (index, gradient) pair is loaded once per block instead of once per
+// pixel; per pixel the matching windows are summed in the order of maxpool_bwd_kernel.
+__global__ void __launch_bounds__(256)
+stem_pool_in_bwd_apply_kernel(const float* __restrict__ dp, const int32_t* __restrict__ idx,
+                              const float* __restrict__ x, long long total, int H, int W, int OH,
+                              int OW, int C, const float* __restrict__ mean,
+                              const float* __restrict__ rstd, const float* __restrict__ sum_g,
+                              const float* __restrict__ sum_gx, float* __restrict__ dx,
+                              __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int C4 = C >> 2;
+  const int cq = (int)(i % C4);
+  long long t = i / C4;
+  const int W2 = W >> 1, H2 = H >> 1;
+  const int b = (int)(t % W2);
+  t /= W2;
+  const int a = (int)(t % H2);
+  const int n = (int)(t / H2);
+  float wd[2][2][4];
+  int wi[2][2][4];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int oy = a + u, ox = b + v;
+      if (oy < OH && ox < OW) {
+        const size_t o = ((((size_t)n * OH + oy) * OW + ox) * C4 + cq);
+        const int4 id = __ldg(reinterpret_cast<const int4*>(idx) + o);
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dp) + o);
+        wi[u][v][0] = id.x; wi[u][v][1] = id.y; wi[u][v][2] = id.z; wi[u][v][3] = id.w;
+        wd[u][v][0] = d.x; wd[u][v][1] = d.y; wd[u][v][2] = d.z; wd[u][v][3] = d.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          wi[u][v][j] = -1;
+          wd[u][v][j] = 0.f;
+        }
+      }
+    }
+  const size_t sc4 = ((size_t)n * C4 + cq);
+  const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean) + sc4);
+  const float4 r4 = __ldg(reinterpret_cast<const float4*>(rstd) + sc4);
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(sum_g) + sc4);
+  const float4 x4 = __ldg(reinterpret_cast<const float4*>(sum_gx) + sc4);
+  const float m[4] = {m4.x, m4.y, m4.z, m4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w};
+  const float sg[4] = {g4.x, g4.y, g4.z, g4.w}, sx[4] = {x4.x, x4.y, x4.z, x4.w};
+  const float inv = 1.f / (float)(H * W);
+  float4 xin[2][2];
+#pragma unroll
+  for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+    for (int pw = 0; pw < 2; ++pw) {
+      const size_t o = (((size_t)n * H + 2 * a + ph) * W + 2 * b + pw) * C4 + cq;
+      xin[ph][pw] = __ldg(reinterpret_cast<const float4*>(x) + o);
+    }
+#pragma unroll
+  for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+    for (int pw = 0; pw < 2; ++pw) {
+      const int me = (2 * a + ph) * W + 2 * b + pw;
+      const size_t o = (((size_t)n * H + 2 * a + ph) * W + 2 * b + pw) * C4 + cq;
+      const float xs[4] = {xin[ph][pw].x, xin[ph][pw].y, xin[ph][pw].z, xin[ph][pw].w};
+      float out[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float g = 0.f;
+#pragma unroll
+        for (int u = 0; u <= ph; ++u)
+#pragma unroll
+          for (int v = 0; v <= pw; ++v)
+            if (wi[u][v][j] == me) g += wd[u][v][j];
+        const float xh = (xs[j] - m[j]) * r[j];
+        g *= act_grad(xh, ACT_RELU);
+        out[j] = r[j] * (g - sg[j] * inv - xh * sx[j] * inv);
+      }
+      if (dx) reinterpret_cast<float4*>(dx)[o] = make_float4(out[0], out[1], out[2], out[3]);
+      if (d_hi) {
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h[j] = __float2bfloat16_rn(out[j]);
+          l[j] = __float2bfloat16_rn(out[j] - __bfloat162float(h[j]));
+        }
+        reinterpret_cast<uint2*>(d_hi)[o] = *reinterpret_cast<uint2*>(h);
+        if (d_lo) reinterpret_cast<uint2*>(d_lo)[o] = *reinterpret_cast<uint2*>(l);
+      }
+    }
+}
+
 // channel quads per block: up to 16 (64 channels), never more than the tensor has.  Wide maps get
 // narrow channel groups (down to 2 quads = one 32-byte sector per pixel) so that the grid
 // (one block per image and channel group) covers the SMs several times over and each of the
@@ -497,6 +663,28 @@ int in_backward(const float* dy, const float* y_for_mask, const float* x, int N,
                                                        accumulate_affine ? 1 : 0);
     EVE_LAUNCH_CHECK();
   }
+  return EVE_OK;
+}
+
+int stem_pool_in_backward(const float* dpool, const float* pooled, const int32_t* idx,
+                          const float* x, int N, int H, int W, int C, const float* mean,
+                          const float* rstd, float* dx, uint16_t* d_hi, uint16_t* d_lo,
+                          float* scratch, cudaStream_t s) {
+  EVE_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, EVE_ERR_SHAPE,
+              "stem_pool_in_backward: C=%d must be a multiple of 4, H=%d and W=%d even", C, H, W);
+  EVE_REQUIRE(dx || d_hi, EVE_ERR_NULL, "stem_pool_in_backward: no output");
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  const int CQ = quad_block_wide(C);
+  float* sum_g = scratch;
+  float* sum_gx = scratch + (size_t)N * C;
+  dim3 grid(N, cdiv(C >> 2, CQ));
+  stem_pool_sums_kernel<<<grid, 256, 0, s>>>(dpool, pooled, OH * OW, C, CQ, sum_g, sum_gx);
+  EVE_LAUNCH_CHECK();
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
+  stem_pool_in_bwd_apply_kernel<<<cdiv(total, 256), 256, 0, s>>>(
+      dpool, idx, x, total, H, W, OH, OW, C, mean, rstd, sum_g, sum_gx, dx,
+      reinterpret_cast<__nv_bfloat16*>(d_hi), reinterpret_cast<__nv_bfloat16*>(d_lo));
+  EVE_LAUNCH_CHECK();
   return EVE_OK;
 }
 

@@ -95,6 +95,7 @@ SIGNATURES = {
     'eve_instnorm_fused_bwd': (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P,
                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     'eve_in_relu_maxpool_fwd': (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    'eve_in_relu_maxpool_bwd': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     'eve_adaptive_maxpool_fwd': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'eve_adaptive_maxpool_bwd': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     'eve_upsample_bilinear_fwd': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -139,6 +139,11 @@ int eve_get_conv_mode(void);
  *                                dy / x served by L2, two CTAs per SM): 0 = never, 1 = for maps whose
  *                                staged form needs one CTA per SM, 2 = always (default: measured
  *                                fastest inside the training step, where dy is usually still in L2)
+ *   "stem_fused_bwd"      0/1    EyeNet stem backward (max-pool -> ReLU -> InstanceNorm) without the
+ *                                dense un-pooled gradient map: the norm's two sums are taken over the
+ *                                pool windows, one pass gathers the pooled gradient per pixel and
+ *                                writes the weight gradient's bf16 dy planes.  0 = scatter, reduce,
+ *                                apply and split as four passes
  * Unknown names / out-of-range values return EVE_ERR_CONFIG. */
 int eve_set_option(const char* name, int value);
 int eve_get_option(const char* name, int* value);
@@ -199,6 +204,15 @@ int eve_instnorm_fused_bwd(const float* dy, const float* dy2, const float* ymask
  * (what ATen returns; padding never wins).  mean/rstd [n,c] are outputs. */
 int eve_in_relu_maxpool_fwd(const float* x, int n, int h, int w, int c, float* mean, float* rstd,
                             float* y, int32_t* idx, eve_stream_t stream);
+/* Its backward in two passes, without a dense un-pooled gradient map: dy[n,oh,ow,c] is the gradient
+ * of the pooled output, y / idx / mean / rstd what the forward call wrote, h and w even.  The
+ * gradient of x is written as fp32 (dx, may be NULL) and / or as bf16 hi + lo planes (dx_hi,
+ * dx_lo: the operand form of the stem convolution's weight gradient; NULL to skip, dx_lo alone may
+ * be NULL).  scratch: 2*n*c floats. */
+int eve_in_relu_maxpool_bwd(const float* dy, const float* y, const int32_t* idx, const float* x,
+                            int n, int h, int w, int c, const float* mean, const float* rstd,
+                            float* dx, uint16_t* dx_hi, uint16_t* dx_lo, float* scratch,
+                            eve_stream_t stream);
 
 /* nn.AdaptiveMaxPool2d (refine_net.py:93,121): idx = int32 flat h*W+w of the first maximum. */
 int eve_adaptive_maxpool_fwd(const float* x, int n, int h, int w, int c, int oh, int ow, float* y,

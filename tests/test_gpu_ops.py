@@ -84,6 +84,44 @@ def test_stem_forward_window_modes(mode, n, h, w):
         L.set_option('stem_windows', saved)
 
 
+@pytest.mark.parametrize('ties', [False, True])
+@pytest.mark.parametrize('n,c,h,w', [(3, 64, 64, 64), (2, 8, 6, 10)])
+def test_stem_norm_relu_maxpool_backward(ties, n, c, h, w):
+    """Backward of maxpool3x3s2p1(relu(InstanceNorm(x))) (torchvision ResNet bn1 / relu / maxpool
+    behind eye_net.py:48-50) in the gather form (eve_in_relu_maxpool_bwd: the norm's sums taken over
+    the pool windows, no dense un-pooled gradient) against fp64 autograd; `ties` draws x from three
+    values, so that most windows hold their maximum several times (the first one takes the gradient,
+    as in ATen).  Both output forms: fp32 and bf16 hi + lo planes."""
+    from eve_b200 import lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(5 + ties)
+    x = (torch.randint(0, 3, (n, c, h, w), generator=g).float() if ties
+         else torch.randn(n, c, h, w, generator=g) * 2.0 + 1.0)
+    oh, ow = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+    dy = torch.randn(n, c, oh, ow, generator=g)
+    xh, dyh = G.nhwc(x.cuda()), G.nhwc(dy.cuda())
+    y = torch.empty((n, oh, ow, c), device='cuda')
+    idx = torch.empty((n, oh, ow, c), dtype=torch.int32, device='cuda')
+    mean, rstd = torch.empty((n, c), device='cuda'), torch.empty((n, c), device='cuda')
+    L.check(lib.eve_in_relu_maxpool_fwd(L.ptr(xh), n, h, w, c, L.ptr(mean), L.ptr(rstd), L.ptr(y),
+                                        L.ptr(idx), L.stream_ptr()), 'in_relu_maxpool_fwd')
+    dx = torch.empty_like(xh)
+    hi = torch.empty(xh.shape, dtype=torch.bfloat16, device='cuda')
+    lo = torch.empty_like(hi)
+    scratch = torch.empty(2 * n * c, device='cuda')
+    L.check(lib.eve_in_relu_maxpool_bwd(L.ptr(dyh), L.ptr(y), L.ptr(idx), L.ptr(xh), n, h, w, c,
+                                        L.ptr(mean), L.ptr(rstd), L.ptr(dx), L.ptr(hi), L.ptr(lo),
+                                        L.ptr(scratch), L.stream_ptr()), 'in_relu_maxpool_bwd')
+    torch.cuda.synchronize()
+    xd = x.double().requires_grad_(True)
+    pooled = F.max_pool2d(F.relu(F.instance_norm(xd, eps=1e-5)), 3, 2, 1)
+    pooled.backward(dy.double())
+    assert G.rel(G.nchw(y), pooled.detach()) < 1e-5
+    assert G.rel(G.nchw(dx), xd.grad) < 2e-5
+    planes = hi.float() + lo.float()
+    assert float((planes - dx).abs().max()) <= 2.0 ** -15 * float(dx.abs().max())
+
+
 def test_conv2d_empty_batch():
     wt = torch.randn(8, 4, 3, 3).cuda()
     y = G.conv_fwd(torch.zeros(0, 4, 8, 8).cuda(), wt, None, 1, 1)

@@ -12,7 +12,8 @@ from eve_b200 import lib as L            # noqa: E402
 from tests import gpu_util as G          # noqa: E402
 
 OPTIONS = ('tc_stage_cap', 'tc_row_kernel', 'tc_row_strips', 'tc_row_wgrad', 'tc_wgrad_waves',
-           'fused_planes', 'fused_norm', 'tc_strip', 'cgru_persistent', 'tc_wgrad_strip', 'in_stream', 'stem_windows', 'tc_pair', 'tc_dual')
+           'fused_planes', 'fused_norm', 'tc_strip', 'cgru_persistent', 'tc_wgrad_strip', 'in_stream', 'stem_windows', 'tc_pair', 'tc_dual',
+           'stem_fused_bwd')
 
 
 @pytest.fixture()
@@ -167,6 +168,7 @@ def _eve_step(cfg, seed=5, B=2, T=3):
 
 
 VARIANTS = [
+    dict(stem_fused_bwd=0),
     dict(in_stream=0),
     dict(tc_pair=1),
     dict(tc_dual=1),
