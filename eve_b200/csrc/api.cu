@@ -189,7 +189,7 @@ static Opt g_opts[OPT_COUNT] = {
     {"tc_stage_cap", 24, 2, 24, "EVE_B200_TC_STAGE_CAP", false},
     {"tc_row_kernel", 1, 0, 1, "EVE_B200_TC_ROW_KERNEL", false},
     {"tc_row_strips", 0, 0, 128, "EVE_B200_TC_ROW_STRIPS", false},
-    {"tc_row_wgrad", 1, 0, 1, "EVE_B200_TC_ROW_WGRAD", false},
+    {"tc_row_wgrad", 2, 0, 2, "EVE_B200_TC_ROW_WGRAD", false},
     {"tc_wgrad_waves", 3, 1, 8, "EVE_B200_TC_WGRAD_WAVES", false},
     {"fused_planes", 1, 0, 1, "EVE_B200_FUSED_PLANES", false},
     {"fused_norm", 1, 0, 1, "EVE_B200_FUSED_NORM", false},

@@ -2284,6 +2284,271 @@ conv_tc_wgrad_row_kernel(const __grid_constant__ CUtensorMap tmD_hi,
   }
 }
 
+// ---- 3x3 variant with the three FILTER ROWS stacked along N.  Above, the x row h meets the dy
+// rows h-1, h, h+1 in three separate instruction groups of N = Cin (2 Cin stacked) columns: at 16 / 32
+// input channels every tcgen05.mma costs the ~43 cycles of its 4 KB dy-tile read whatever N is
+// (DESIGN 3b), so the kernel is paced by its instruction count.  Turned around -- the dy row g meets
+// the x rows g-1, g, g+1 -- the three products share the dy operand and become ONE instruction with
+// N = 3 Cin: B = three consecutive x slots (the x planes live in their own rings at a pitch of one row,
+// which is the descriptor's leading-dimension offset), D = [D_0 | D_1 | D_2].  The two halo entries of
+// an item carry a zero x row (TMA box outside the image), so every interior instruction is uniform;
+// the dy halo rows meet their single x row in two N = Cin instructions per item.  Where the three
+// slots wrap around the ring the instruction is issued in two parts.  3 instead of 6 instructions per
+// 16-pixel K step with split operands.
+template <int NPASS, int CIN, int COUT>
+struct WgRow3Cfg {
+  static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
+  static constexpr int kDRowBytes = (kRowBox * COUT * 2 + 1023) / 1024 * 1024;   // one dy plane
+  static constexpr int kXRowBytes = kTileM * CIN * 2;                            // one x plane
+  static constexpr int kSlotBytes = kPlanes * (kDRowBytes + kXRowBytes);
+  static constexpr int kSlotsRaw = (227 * 1024 - 1024 - kBarrierBytes) / kSlotBytes;
+  static constexpr int kSlots = kSlotsRaw > kMaxStages ? kMaxStages : kSlotsRaw;
+  // hi x hi and lo x hi share columns [0, 3 CIN); with stacked accumulators hi x lo goes to
+  // [3 CIN, 6 CIN) and the epilogue adds the halves
+  static constexpr bool kStack = NPASS == 3 && CIN <= 32;
+  static constexpr uint32_t kSetCols = (kStack ? 6u : 3u) * CIN;
+  static constexpr uint32_t kTmemCols = 2 * kSetCols <= 128 ? 128u : (2 * kSetCols <= 256 ? 256u : 512u);
+};
+
+template <int NPASS, int CIN, int COUT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_wgrad_row3_kernel(const __grid_constant__ CUtensorMap tmD_hi,
+                          const __grid_constant__ CUtensorMap tmD_lo,
+                          const __grid_constant__ CUtensorMap tmX_hi,
+                          const __grid_constant__ CUtensorMap tmX_lo, const TcWgRowParams p) {
+  using Cfg = WgRow3Cfg<NPASS, CIN, COUT>;
+  constexpr int kPlanes = Cfg::kPlanes;
+  constexpr int KS = 3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  const int slots = p.slots;
+  // [dy: slots x planes x kDRowBytes][x hi: slots x kXRowBytes][x lo: slots x kXRowBytes]
+  uint8_t* xring = ring + (size_t)slots * kPlanes * Cfg::kDRowBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)slots * Cfg::kSlotBytes);
+  uint64_t* empty = full + slots;
+  uint64_t* tmem_full = empty + slots;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tmap_prefetch(&tmD_hi);
+    tmap_prefetch(&tmX_hi);
+    if (NPASS == 3) {
+      tmap_prefetch(&tmD_lo);
+      tmap_prefetch(&tmX_lo);
+    }
+    for (int s = 0; s < slots; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int total_rows = 0;
+  for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    const int n = item / p.strips;
+    const int h0 = (item - n * p.strips) * p.rows_per_strip;
+    total_rows += min(p.H, h0 + p.rows_per_strip) - h0;
+  }
+
+  if (warp == 0) {
+    if (elect_one()) {
+      constexpr uint32_t tx = (uint32_t)(kRowBox * COUT * 2 + kTileM * CIN * 2) * kPlanes;
+      uint32_t g = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int n = item / p.strips;
+        const int h0 = (item - n * p.strips) * p.rows_per_strip;
+        const int h1 = min(p.H, h0 + p.rows_per_strip);
+        for (int hr = h0 - 1; hr < h1 + 1; ++hr, ++g) {
+          const int s = g % slots;
+          mbar_wait(&empty[s], ((g / slots) & 1) ^ 1);
+          uint8_t* dd = ring + (size_t)s * kPlanes * Cfg::kDRowBytes;
+          uint8_t* xd = xring + (size_t)s * Cfg::kXRowBytes;
+          // the x row of a halo entry belongs to the neighbouring strip: a box outside the image
+          // (row H) is all TMA zero fill
+          const int xr = (hr >= h0 && hr < h1) ? hr : p.H;
+          mbar_expect_tx(&full[s], tx);
+          tma_load_4d(dd, &tmD_hi, &full[s], 0, -1, hr, n);
+          tma_load_4d(xd, &tmX_hi, &full[s], 0, 0, xr, n);
+          if (NPASS == 3) {
+            tma_load_4d(dd + Cfg::kDRowBytes, &tmD_lo, &full[s], 0, -1, hr, n);
+            tma_load_4d(xd + (size_t)slots * Cfg::kXRowBytes, &tmX_lo, &full[s], 0, 0, xr, n);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // D fp32, A/B bf16, both MN-major, M = 128; N = nb * CIN
+    constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                ((uint32_t)(kTileM >> 4) << 24);
+    constexpr uint32_t idescN[4] = {0u, idesc0 | ((uint32_t)(CIN >> 3) << 17),
+                                    idesc0 | ((uint32_t)((2 * CIN) >> 3) << 17),
+                                    idesc0 | ((uint32_t)((3 * CIN) >> 3) << 17)};
+    constexpr uint32_t kDStep16 = (uint32_t)(16 * COUT * 2) >> 4;
+    constexpr uint32_t kXStep16 = (uint32_t)(16 * CIN * 2) >> 4;
+    constexpr uint32_t kDRow16 = (uint32_t)Cfg::kDRowBytes >> 4;
+    constexpr uint32_t kXRow16 = (uint32_t)Cfg::kXRowBytes >> 4;
+    const uint64_t d_desc0 = mnmajor_desc(0u, (uint32_t)(COUT * 2), COUT);
+    const uint64_t x_desc0 = mnmajor_desc(0u, (uint32_t)Cfg::kXRowBytes, CIN);
+    const uint32_t ring16 = smem_u32(ring) >> 4;
+    const uint32_t xring16 = smem_u32(xring) >> 4;
+    const uint32_t xlo16 = (uint32_t)slots * kXRow16;          // x lo ring behind the x hi ring
+    if (elect_one()) {
+      uint32_t sg = 0, pg = 0;
+      int confirmed = 0;
+      auto advance = [&](uint32_t& sl_, uint32_t& ph_) {
+        if (++sl_ == (uint32_t)slots) {
+          sl_ = 0;
+          ph_ ^= 1u;
+        }
+      };
+      // the dy row in slot sd against `nb` consecutive x rows from slot sx, into accumulator
+      // column block cb (of CIN columns), over the 128 pixels of the row
+      auto issue = [&](uint32_t tmem_set, uint32_t sd, uint32_t sx, int nb, uint32_t cb, uint32_t acc0) {
+        const uint64_t db = d_desc0 + (uint64_t)(ring16 + sd * (kPlanes * kDRow16));
+        const uint64_t xb = x_desc0 + (uint64_t)(xring16 + sx * kXRow16);
+        const uint32_t td = tmem_set + cb * CIN;
+        const uint32_t id = idescN[nb];
+#pragma unroll
+        for (int ks = 0; ks < kTileM / 16; ++ks) {
+          const uint64_t dah = db + (uint64_t)(ks * kDStep16);
+          const uint64_t dbh = xb + (uint64_t)(ks * kXStep16);
+          const uint32_t acc = ks == 0 ? acc0 : 1u;
+          if (Cfg::kStack) {
+            umma_bf16(td, dah, dbh, id, acc);
+            umma_bf16(td + 3 * CIN, dah, dbh + xlo16, id, acc);
+            umma_bf16(td, dah + kDRow16, dbh, id, 1);
+          } else if (NPASS == 3) {
+            umma_bf16(td, dah + kDRow16, dbh, id, acc);
+            umma_bf16(td, dah, dbh + xlo16, id, 1);
+            umma_bf16(td, dah, dbh, id, 1);
+          } else {
+            umma_bf16(td, dah, dbh, id, acc);
+          }
+        }
+      };
+      int row = 0;                 // rows accumulated so far by this CTA
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int n = item / p.strips;
+        const int h0 = (item - n * p.strips) * p.rows_per_strip;
+        const int h1 = min(p.H, h0 + p.rows_per_strip);
+        for (int h = h0; h < h1; ++h, ++row) {
+          const uint32_t chain = (uint32_t)(row / kWgFlushRows);
+          const uint32_t set = chain & 1;
+          const bool chain_start = row % kWgFlushRows == 0;
+          const bool chain_end = row % kWgFlushRows == kWgFlushRows - 1 || row == total_rows - 1;
+          if (chain_start) {
+            mbar_wait(&tmem_empty[set], ((chain >> 1) & 1) ^ 1);   // the epilogue drained this set
+            tc_fence_after();
+          }
+          // ring entries of rows h-1, h, h+1
+          uint32_t sl[KS];
+          {
+            uint32_t se = sg, pe = pg;
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+              sl[j] = se;
+              if (j >= confirmed) mbar_wait(&full[se], pe);
+              advance(se, pe);
+            }
+          }
+          tc_fence_after();
+          const uint32_t acc0 = chain_start ? 0u : 1u;
+          const uint32_t tmem_set = tmem_base + set * Cfg::kSetCols;
+          // dy row h x (x rows h-1, h, h+1) -> (D_0, D_1, D_2): D_r += dy[h'-r+1] x[h'] with h' = h+r-1
+          if (sl[2] == sl[0] + 2) {
+            issue(tmem_set, sl[1], sl[0], 3, 0, acc0);
+          } else if (sl[1] == sl[0] + 1) {
+            issue(tmem_set, sl[1], sl[0], 2, 0, acc0);
+            issue(tmem_set, sl[1], sl[2], 1, 2, acc0);
+          } else {
+            issue(tmem_set, sl[1], sl[0], 1, 0, acc0);
+            issue(tmem_set, sl[1], sl[1], 2, 1, acc0);
+          }
+          // the strip's dy halo rows: row h0-1 meets x row h0 in D_2, row h1 meets x row h1-1 in D_0
+          if (h == h0) issue(tmem_set, sl[0], sl[1], 1, 2, 1u);
+          if (h == h1 - 1) issue(tmem_set, sl[2], sl[1], 1, 0, 1u);
+          umma_commit(&empty[sl[0]]);
+          if (chain_end) umma_commit(&tmem_full[set]);
+          advance(sg, pg);
+          confirmed = KS - 1;
+        }
+        umma_commit(&empty[sg]);
+        advance(sg, pg);
+        umma_commit(&empty[sg]);
+        advance(sg, pg);
+        confirmed = 0;
+      }
+    }
+  } else {
+    // epilogue: as in conv_tc_wgrad_row_kernel, columns [r * CIN, (r+1) * CIN) (+ 3 CIN stacked)
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int b = m / COUT;                   // M block = horizontal shift
+    const int co = m - b * COUT;
+    const bool valid = b < KS;
+    const int q = KS - 1 - b;
+    constexpr size_t KK = (size_t)KS * KS * CIN;
+    const int chains = (total_rows + kWgFlushRows - 1) / kWgFlushRows;
+    for (int chain = 0; chain < chains; ++chain) {
+      const uint32_t set = (uint32_t)chain & 1;
+      mbar_wait(&tmem_full[set], ((uint32_t)chain >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int r = 0; r < KS; ++r) {
+        float* dst = p.part + ((size_t)blockIdx.x * COUT + co) * KK + (size_t)(r * KS + q) * CIN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < CIN; c0 += 32) {
+          constexpr int nc = CIN < 32 ? CIN : 32;
+          float v[32];
+          const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + set * Cfg::kSetCols +
+                              (uint32_t)(r * CIN + c0);
+          tmem_ld32(t0, v);                  // CIN = 16: the upper half is the next block, unused
+          if (Cfg::kStack) {
+            float u[32];
+            tmem_ld32(t0 + 3 * CIN, u);
+#pragma unroll
+            for (int j = 0; j < nc; ++j) v[j] += u[j];
+          }
+          if (valid) {
+            float4* o4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+            for (int j = 0; j < nc / 4; ++j) {
+              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (chain > 0) {
+                const float4 a = o4[j];
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              }
+              o4[j] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_relaxed(&tmem_empty[set]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // ====================================================== padded-strip weight gradient ==
 // dW of 3x3 stride-1 convolutions on maps narrower than 128 pixels (EyeNet layers 1-2, RefineNet
 // levels 1-2: the split-K kernel above re-loads the dy box once per filter tap and the x box once per
@@ -3465,10 +3730,27 @@ static int launch_wgrad_row(const CUtensorMap& d_hi, const CUtensorMap& d_lo, co
   return EVE_OK;
 }
 
+template <int NPASS, int CIN, int COUT>
+static int launch_wgrad_row3(const CUtensorMap& d_hi, const CUtensorMap& d_lo, const CUtensorMap& x_hi,
+                             const CUtensorMap& x_lo, TcWgRowParams p, int grid, cudaStream_t s) {
+  using Cfg = WgRow3Cfg<NPASS, CIN, COUT>;
+  static_assert(Cfg::kSlots >= 4, "halo-row wgrad: ring too shallow");
+  EVE_TRY(ensure_dynamic_smem((const void*)conv_tc_wgrad_row3_kernel<NPASS, CIN, COUT>, 227 * 1024));
+  p.slots = Cfg::kSlots;
+  const int smem_bytes = Cfg::kSlots * Cfg::kSlotBytes + 1024 + kBarrierBytes;
+  conv_tc_wgrad_row3_kernel<NPASS, CIN, COUT><<<grid, kThreads, smem_bytes, s>>>(d_hi, d_lo, x_hi, x_lo, p);
+  EVE_LAUNCH_CHECK();
+  return EVE_OK;
+}
+
 template <int CIN, int COUT>
 static int launch_wgrad_row_np(int ks, int npass, const CUtensorMap& d_hi, const CUtensorMap& d_lo,
                                const CUtensorMap& x_hi, const CUtensorMap& x_lo,
                                const TcWgRowParams& p, int grid, cudaStream_t s) {
+  // 3x3: filter rows stacked along N (tc_row_wgrad = 2, default); 1 = one instruction group per row
+  if (ks == 3 && get_option(OPT_TC_ROW_WGRAD) == 2)
+    return npass == 3 ? launch_wgrad_row3<3, CIN, COUT>(d_hi, d_lo, x_hi, x_lo, p, grid, s)
+                      : launch_wgrad_row3<1, CIN, COUT>(d_hi, d_lo, x_hi, x_lo, p, grid, s);
   if (ks == 3)
     return npass == 3 ? launch_wgrad_row<3, CIN, COUT, 3>(d_hi, d_lo, x_hi, x_lo, p, grid, s)
                       : launch_wgrad_row<1, CIN, COUT, 3>(d_hi, d_lo, x_hi, x_lo, p, grid, s);

@@ -364,6 +364,89 @@ upsample_bwd_kernel(const float* __restrict__ dy, int lddy, int coff, long long 
   *reinterpret_cast<float4*>(dx + i * 4) = make_float4(s[0], s[1], s[2], s[3]);
 }
 
+// ---- exact 2x upscale (RefineNet decoder levels 0-2: 36x64 -> 72x128, ...).  The general kernels
+// above spend their time on index arithmetic (one thread per output quad: three runtime divisions
+// and two source computations for one 16-byte store; the backward walks a computed candidate
+// range).  Here a thread owns one INPUT pixel quad: the forward writes the 2x2 outputs it is the
+// nearest source of from its 3x3 neighbourhood, the backward gathers the 4x4 outputs that read it.
+// Weights come from the same bilinear_src() and every output / sum is formed by the same
+// expression in the same order, so results are bit-identical to the general kernels.
+__global__ void __launch_bounds__(256)
+upsample2x_fwd_kernel(const float* __restrict__ x, int total4, int H, int W, int C4,
+                      float* __restrict__ y, int ldy, int coff) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int cq = i % C4;
+  int t = i / C4;
+  const int w = t % W;
+  t /= W;
+  const int h = t % H;
+  const int n = t / H;
+  const int OW = 2 * W;
+  const float4* xp = reinterpret_cast<const float4*>(x) + (size_t)n * H * W * C4 + cq;
+  const int rows[3] = {max(h - 1, 0), h, min(h + 1, H - 1)};
+  const int cols[3] = {max(w - 1, 0), w, min(w + 1, W - 1)};
+  F4 v[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) v[a][b] = F4(__ldg(xp + (size_t)(rows[a] * W + cols[b]) * C4));
+  // bilinear_src(2h, 0.5): sources (h-1, h), weights (0.25, 0.75); at h = 0 sources (0, 1), weights
+  // (1, 0) -- taken here from (rows[0], rows[1]) = (0, 0), the zero weight meets a finite value
+  // either way.  bilinear_src(2h+1, 0.5): sources (h, min(h+1, H-1)), weights (0.75, 0.25).
+  const float ly[2][2] = {{h == 0 ? 1.f : 0.25f, h == 0 ? 0.f : 0.75f}, {0.75f, 0.25f}};
+  const float lx[2][2] = {{w == 0 ? 1.f : 0.25f, w == 0 ? 0.f : 0.75f}, {0.75f, 0.25f}};
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      F4 o;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o.v[j] = ly[dy][0] * (lx[dx][0] * v[dy][dx].v[j] + lx[dx][1] * v[dy][dx + 1].v[j]) +
+                 ly[dy][1] * (lx[dx][0] * v[dy + 1][dx].v[j] + lx[dx][1] * v[dy + 1][dx + 1].v[j]);
+      st4(y + (((size_t)n * 2 * H + 2 * h + dy) * OW + 2 * w + dx) * ldy + coff + cq * 4, o);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const float* __restrict__ dy, int lddy, int coff, int total4, int H, int W,
+                      int C4, float* __restrict__ dx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int cq = i % C4;
+  int t = i / C4;
+  const int w = t % W;
+  t /= W;
+  const int h = t % H;
+  const int n = t / H;
+  const int OH = 2 * H, OW = 2 * W;
+  // the outputs that read input h are 2h-1 .. 2h+2, with the weights bilinear_src() gives them:
+  // 0.25 (if h > 0), 0.75 (1 at h = 0: clamped source), 0.75 (1 at h = H-1: both sources), 0.25
+  // (if h < H-1)
+  const float wy[4] = {h > 0 ? 0.25f : 0.f, h == 0 ? 1.f : 0.75f, h == H - 1 ? 1.f : 0.75f,
+                       h < H - 1 ? 0.25f : 0.f};
+  const float wx[4] = {w > 0 ? 0.25f : 0.f, w == 0 ? 1.f : 0.75f, w == W - 1 ? 1.f : 0.75f,
+                       w < W - 1 ? 0.25f : 0.f};
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* base = dy + coff + cq * 4;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (wy[a] == 0.f) continue;
+    const int oy = 2 * h - 1 + a;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (wx[b] == 0.f) continue;
+      const int ox = 2 * w - 1 + b;
+      const F4 d = ld4(base + (((size_t)n * OH + oy) * OW + ox) * lddy);
+      const float wt = wy[a] * wx[b];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[j] = fmaf(wt, d.v[j], s[j]);
+    }
+  }
+  *reinterpret_cast<float4*>(dx + (size_t)i * 4) = make_float4(s[0], s[1], s[2], s[3]);
+}
+
 __global__ void __launch_bounds__(256)
 copy_channels_kernel(const float* __restrict__ x, long long total, int C, int ldx, int xoff,
                      float* __restrict__ y, int ldy, int coff, int accumulate) {
@@ -485,6 +568,12 @@ int upsample_bilinear_fwd(const float* x, int N, int H, int W, int C, int OH, in
                           int ldy, int coff, cudaStream_t s) {
   EVE_REQUIRE(C % 4 == 0 && ldy % 4 == 0 && coff % 4 == 0, EVE_ERR_SHAPE,
               "upsample_bilinear: channel counts must be multiples of 4");
+  if (OH == 2 * H && OW == 2 * W && (long long)N * H * W * (C / 4) < (1ll << 31) && N > 0) {
+    const int total4 = N * H * W * (C / 4);
+    upsample2x_fwd_kernel<<<cdiv(total4, 256), 256, 0, s>>>(x, total4, H, W, C / 4, y, ldy, coff);
+    EVE_LAUNCH_CHECK();
+    return EVE_OK;
+  }
   long long total = (long long)N * OH * OW * (C / 4);
   float sh = (float)H / (float)OH, sw = (float)W / (float)OW;
   upsample_fwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, H, W, C, OH, OW, sh, sw, y, ldy,
@@ -497,6 +586,12 @@ int upsample_bilinear_bwd(const float* dy, int lddy, int coff, int N, int H, int
                           int OW, float* dx, cudaStream_t s) {
   EVE_REQUIRE(C % 4 == 0 && lddy % 4 == 0 && coff % 4 == 0, EVE_ERR_SHAPE,
               "upsample_bilinear: channel counts must be multiples of 4");
+  if (OH == 2 * H && OW == 2 * W && (long long)N * H * W * (C / 4) < (1ll << 31) && N > 0) {
+    const int total4 = N * H * W * (C / 4);
+    upsample2x_bwd_kernel<<<cdiv(total4, 256), 256, 0, s>>>(dy, lddy, coff, total4, H, W, C / 4, dx);
+    EVE_LAUNCH_CHECK();
+    return EVE_OK;
+  }
   long long total = (long long)N * H * W * (C / 4);
   float sh = (float)H / (float)OH, sw = (float)W / (float)OW;
   upsample_bwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(dy, lddy, coff, total, H, W, C, OH, OW, sh,

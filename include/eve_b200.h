@@ -96,7 +96,10 @@ int eve_get_conv_mode(void);
  *   "tc_row_kernel"       0/1    halo-row kernel (input rows staged once, filter taps taken as
  *                                shifted shared-memory descriptors) for 3x3 stride-1, W == 128
  *   "tc_row_strips"       0..128 row strips per image (0 = automatic)
- *   "tc_row_wgrad"        0/1    halo-row weight-gradient kernel
+ *   "tc_row_wgrad"        0..2   halo-row weight-gradient kernel (128-pixel-wide maps): 0 off, 1 one
+ *                                instruction group per filter row, 2 (default) the three filter rows
+ *                                of a 3x3 filter stacked along N (one instruction per dy row, K step
+ *                                and operand product)
  *   "tc_wgrad_waves"      1..8   full waves of CTAs the split-K weight gradient fills
  *   "fused_planes"        0/1    normalise+activate kernels write the consuming convolution's
  *                                16-bit operand planes directly (no fp32 activation, no split pass);

@@ -137,7 +137,7 @@ def test_tuning_options_round_trip_without_a_gpu():
     from eve_b200 import lib as L
     lib = L.load()
     for name, lo, hi in [('tc_stage_cap', 2, 24), ('tc_row_kernel', 0, 1), ('tc_row_strips', 0, 128),
-                         ('tc_row_wgrad', 0, 1), ('tc_wgrad_waves', 1, 8), ('fused_planes', 0, 1)]:
+                         ('tc_row_wgrad', 0, 2), ('tc_wgrad_waves', 1, 8), ('fused_planes', 0, 1)]:
         prev = L.get_option(name)
         assert lo <= prev <= hi
         L.set_option(name, lo)

@@ -175,7 +175,8 @@ def test_adaptive_maxpool_values_indices_and_backward(h, w, oh, ow):
     assert G.rel(dx, xd.grad) < 1e-6
 
 
-@pytest.mark.parametrize('h,w,oh,ow', [(5, 8, 9, 16), (9, 16, 18, 32), (36, 64, 72, 128), (3, 4, 7, 5)])
+@pytest.mark.parametrize('h,w,oh,ow', [(5, 8, 9, 16), (9, 16, 18, 32), (36, 64, 72, 128), (3, 4, 7, 5),
+                                          (1, 1, 2, 2), (1, 4, 2, 8), (2, 1, 4, 2)])
 def test_bilinear_upsample(h, w, oh, ow):
     g = torch.Generator().manual_seed(4)
     x = torch.randn(2, 12, h, w, generator=g)

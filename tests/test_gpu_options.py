@@ -32,8 +32,11 @@ ROW_CASES = [(16, 16, 3), (16, 32, 3), (32, 32, 3), (64, 16, 3), (32, 16, 3), (1
 
 @pytest.mark.parametrize('cin,cout,k', ROW_CASES)
 @pytest.mark.parametrize('strips', [0, 1, 3, 72])
-def test_halo_row_kernels_match_fp64(cin, cout, k, strips, options):
-    """strips = 1: one work item per image (rows h0-1 and H are pure TMA zero fill); 72: one output
+@pytest.mark.parametrize('wg', [1, 2])
+def test_halo_row_kernels_match_fp64(cin, cout, k, strips, wg, options):
+    """wg: weight gradient with one instruction group per filter row (1) or the three filter rows
+    stacked along N (2, 3x3 only: halo rows, ring wrap-around and chain flushes all differ).
+    strips = 1: one work item per image (rows h0-1 and H are pure TMA zero fill); 72: one output
     row per item (every staged row is a strip boundary); 3: the bench decomposition."""
     n, h, w = 3, 72, 128
     g = torch.Generator().manual_seed(1000 * cin + cout + k)
@@ -47,7 +50,7 @@ def test_halo_row_kernels_match_fp64(cin, cout, k, strips, options):
     y.backward(dy.double())
     L.load().eve_set_conv_mode(1)
     options('tc_row_kernel', 1)
-    options('tc_row_wgrad', 1)
+    options('tc_row_wgrad', wg)
     options('tc_row_strips', strips)
     got = G.conv_fwd(x.cuda(), wt.cuda(), b.cuda(), 1, k // 2)
     dx = G.conv_dgrad(dy.cuda(), wt.cuda(), (h, w), 1, k // 2)
@@ -169,6 +172,7 @@ def _eve_step(cfg, seed=5, B=2, T=3):
 
 VARIANTS = [
     dict(stem_fused_bwd=0),
+    dict(tc_row_wgrad=1),
     dict(in_stream=0),
     dict(tc_pair=1),
     dict(tc_dual=1),
