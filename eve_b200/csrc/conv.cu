@@ -737,7 +737,7 @@ struct PrepEntry {
   int Cout, Cin, KH, KW;
   int flip, fmt;
   float scale;
-  long long start, count;      // element range of this entry in the launch (start is 256-aligned)
+  long long start;             // first block of this entry in the launch
 };
 constexpr int kPrepBatch = 56;
 struct PrepTable {
@@ -745,33 +745,67 @@ struct PrepTable {
   PrepEntry e[kPrepBatch];
 };
 
+// One block = one tile of one entry, staged through shared memory so that both the OIHW reads and
+// the 16-bit writes are contiguous runs (one thread per output element read the weights with a stride
+// of `taps` floats -- or of a whole filter for the flipped layout -- and spent ~100 instructions on
+// 64-bit index arithmetic: 345 us per training step for 200 MB of traffic):
+//   forward  [co][tap][ci]        : one output channel x up to 512 input channels (its taps * Cin
+//                                   floats are one contiguous run of the source)
+//   flipped  [ci][flipped tap][co]: 64 output x 8 input channels (8 * taps contiguous floats per
+//                                   output channel in, 64 contiguous values per (ci, tap) out)
+constexpr int kPrepCi = 512, kPrepFlipCo = 64, kPrepFlipCi = 8;
+constexpr int kPrepPitch = kPrepFlipCi * 9 + 1;        // odd pitch: conflict-free transposed reads
+
+__host__ __device__ inline int prep_entry_blocks(int Cout, int Cin, int flip) {
+  return flip ? ((Cout + kPrepFlipCo - 1) / kPrepFlipCo) * ((Cin + kPrepFlipCi - 1) / kPrepFlipCi)
+              : Cout * ((Cin + kPrepCi - 1) / kPrepCi);
+}
+
 __global__ void __launch_bounds__(256)
 prep_weights_batch_kernel(const PrepTable tab) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  // block-uniform search (entry starts are multiples of the block size)
-  int k = 0;
-  while (k + 1 < tab.n && tab.e[k + 1].start <= (long long)blockIdx.x * blockDim.x) ++k;
+  __shared__ float tile[kPrepFlipCo * kPrepPitch > kPrepCi * 9 ? kPrepFlipCo * kPrepPitch : kPrepCi * 9];
+  int k = 0;                               // block-uniform search
+  while (k + 1 < tab.n && tab.e[k + 1].start <= (long long)blockIdx.x) ++k;
   const PrepEntry& e = tab.e[k];
-  const long long o = i - e.start;      // OUTPUT element: consecutive threads write consecutive bytes
-  if (o >= e.count) return;
+  const int b = (int)((long long)blockIdx.x - e.start);
   const int taps = e.KH * e.KW;
-  int co, ci, tap;
-  if (!e.flip) {                         // [co][tap][ci]
-    ci = (int)(o % e.Cin);
-    const long long t = o / e.Cin;
-    tap = (int)(t % taps);
-    co = (int)(t / taps);
-  } else {                               // [ci][flipped tap][co]
-    co = (int)(o % e.Cout);
-    const long long t = o / e.Cout;
-    tap = taps - 1 - (int)(t % taps);
-    ci = (int)(t / taps);
+  const float scale = e.scale;
+  if (!e.flip) {
+    const int chunks = (e.Cin + kPrepCi - 1) / kPrepCi;
+    const int co = b / chunks, ci0 = (b - co * chunks) * kPrepCi;
+    const int nci = min(kPrepCi, e.Cin - ci0);
+    const int n = nci * taps;
+    const float* src = e.w + ((size_t)co * e.Cin + ci0) * taps;
+    for (int i = threadIdx.x; i < n; i += 256) tile[i] = __ldg(src + i) * scale;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const int tap = i / nci, cl = i - tap * nci;
+      uint16_t h, l;
+      split16(tile[cl * taps + tap], e.fmt, h, l);
+      const size_t o = ((size_t)co * taps + tap) * e.Cin + ci0 + cl;
+      e.hi[o] = h;
+      if (e.lo) e.lo[o] = l;
+    }
+  } else {
+    const int cib = (e.Cin + kPrepFlipCi - 1) / kPrepFlipCi;
+    const int cot = b / cib, ci0 = (b - cot * cib) * kPrepFlipCi, co0 = cot * kPrepFlipCo;
+    const int nco = min(kPrepFlipCo, e.Cout - co0), nci = min(kPrepFlipCi, e.Cin - ci0);
+    const int run = nci * taps;            // contiguous source floats per output channel
+    for (int i = threadIdx.x; i < nco * run; i += 256) {
+      const int cl = i / run, j = i - cl * run;
+      tile[cl * kPrepPitch + j] = __ldg(e.w + ((size_t)(co0 + cl) * e.Cin + ci0) * taps + j) * scale;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nco * run; i += 256) {
+      const int j = i / nco, cl = i - j * nco;          // j = (local ci, flipped tap)
+      const int cil = j / taps, ftap = j - cil * taps;
+      uint16_t h, l;
+      split16(tile[cl * kPrepPitch + cil * taps + (taps - 1 - ftap)], e.fmt, h, l);
+      const size_t o = ((size_t)(ci0 + cil) * taps + ftap) * e.Cout + co0 + cl;
+      e.hi[o] = h;
+      if (e.lo) e.lo[o] = l;
+    }
   }
-  float v = __ldg(e.w + ((size_t)co * e.Cin + ci) * taps + tap) * e.scale;
-  uint16_t h, l;
-  split16(v, e.fmt, h, l);
-  e.hi[o] = h;
-  if (e.lo) e.lo[o] = l;
 }
 }  // namespace
 
@@ -802,7 +836,7 @@ int conv_prepare_batch(const ConvPrepReq* reqs, int n, bool dgrad, void* region,
   long long total = 0;
   auto flush = [&]() -> int {
     if (tab.n == 0) return EVE_OK;
-    prep_weights_batch_kernel<<<cdiv(total, 256), 256, 0, s>>>(tab);
+    prep_weights_batch_kernel<<<(unsigned)total, 256, 0, s>>>(tab);
     EVE_LAUNCH_CHECK();
     tab.n = 0;
     total = 0;
@@ -811,6 +845,7 @@ int conv_prepare_batch(const ConvPrepReq* reqs, int n, bool dgrad, void* region,
   for (int i = 0; i < n; ++i) {
     const ConvGeom& g = reqs[i].g;
     if (!reqs[i].w || !prep_wanted(g, dgrad) || g_nprepared >= kMaxPrepared) continue;
+    if (g.KH * g.KW > 9) continue;                                   // the kernel's tiles hold up to nine taps
     if (find_prepared(reqs[i].w, dgrad, npass)) continue;          // shared weights
     const size_t wel = (size_t)g.Cout * g.K();
     const size_t plane = align_up(wel * sizeof(uint16_t), 1024);
@@ -825,8 +860,7 @@ int conv_prepare_batch(const ConvPrepReq* reqs, int n, bool dgrad, void* region,
     e.fmt = (!dgrad && npass == 3) ? TC_F16 : TC_BF16;
     e.scale = (!dgrad && npass == 3) ? 64.f : 1.f;
     e.start = total;
-    e.count = (long long)wel;
-    total += (long long)align_up(wel, 256);
+    total += prep_entry_blocks(g.Cout, g.Cin, e.flip);
     tab.e[tab.n++] = e;
     g_prepared[g_nprepared++] = PreparedW{e.w, dgrad ? 1 : 0, npass, e.hi, e.lo ? e.lo : e.hi};
     if (tab.n == kPrepBatch) EVE_TRY(flush());
