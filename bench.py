@@ -638,7 +638,7 @@ def b200_arm(args):
     roofline = {
         'bound': 'tensor', 'kernel': 'conv_tc_kernel / conv_tc_strip_kernel / conv_tc_row_kernel / '
                                      'conv_tc_wgrad_kernel / conv_tc_wgrad_strip_kernel / '
-                                     'conv_tc_wgrad_row_kernel (tcgen05 implicit GEMM, split '
+                                     'conv_tc_wgrad_row_kernel / conv_tc_wgrad_row3_kernel (tcgen05 implicit GEMM, split '
                                      'fp16/bf16 operands = 2-3 MMAs per product) + the few CUDA-core '
                                      'convs left; all conv fwd + dgrad + wgrad launches',
         'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
