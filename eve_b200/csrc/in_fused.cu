@@ -96,6 +96,19 @@ int stream_cluster() {        // tuning knob: cluster size of the streaming back
   }
   return v;
 }
+// tuning knob: the same for maps of 8192+ pixels only (0 = no exception).  Their second read misses L2
+// with clusters of two (3.5 GB read for 1.7 GB of tensors on the 64-channel 72x128 launch); clusters of
+// four / eight would keep the tensors in flight below the L2 size -- measured in the training step:
+// 30.47 ms (2) vs 30.68 (4) vs 30.69 (8): the barrier and prologue cost outweighs the DRAM bytes saved
+int stream_cluster_big() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EVE_B200_IN_STREAM_CS_BIG");
+    v = e ? atoi(e) : 0;
+    if (v != 1 && v != 2 && v != 4 && v != 8) v = 0;
+  }
+  return v;
+}
 int max_cluster() {           // tuning knob (environment, read once)
   static int v = 0;
   if (!v) {
@@ -1074,6 +1087,7 @@ int in_bwd_fused(const float* dy, const float* dy2, const float* ymask, const fl
     // and clusters that pack the GPCs' CTA slots without remainder.  Never a function of N.
     int cs = stream_cluster();
     if (!cs) cs = 2;
+    if (HW >= 8192 && stream_cluster_big()) cs = stream_cluster_big();
     if (cs < p.CS) {
       p.CS = cs;
       p.ppc = cdiv(HW, p.CS);
