@@ -2307,6 +2307,10 @@ struct WgRow3Cfg {
   // [3 CIN, 6 CIN) and the epilogue adds the halves
   static constexpr bool kStack = NPASS == 3 && CIN <= 32;
   static constexpr uint32_t kSetCols = (kStack ? 6u : 3u) * CIN;
+  // 16 output channels: the three pixel-shifted M blocks fit an M = 64 instruction (four blocks, half
+  // the dy-tile read of M = 128, which is what an instruction costs at N <= 96).  Its accumulator row m
+  // sits in TMEM lane 32 (m / 16) + m % 16: M block b is lanes 0..15 of epilogue warp b.
+  static constexpr int kM = COUT == 16 ? 64 : kTileM;
   static constexpr uint32_t kTmemCols = 2 * kSetCols <= 128 ? 128u : (2 * kSetCols <= 256 ? 256u : 512u);
 };
 
@@ -2393,7 +2397,7 @@ conv_tc_wgrad_row3_kernel(const __grid_constant__ CUtensorMap tmD_hi,
   } else if (warp == 1) {
     // D fp32, A/B bf16, both MN-major, M = 128; N = nb * CIN
     constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                                ((uint32_t)(kTileM >> 4) << 24);
+                                ((uint32_t)(Cfg::kM >> 4) << 24);
     constexpr uint32_t idescN[4] = {0u, idesc0 | ((uint32_t)(CIN >> 3) << 17),
                                     idesc0 | ((uint32_t)((2 * CIN) >> 3) << 17),
                                     idesc0 | ((uint32_t)((3 * CIN) >> 3) << 17)};
@@ -2497,9 +2501,10 @@ conv_tc_wgrad_row3_kernel(const __grid_constant__ CUtensorMap tmD_hi,
     // epilogue: as in conv_tc_wgrad_row_kernel, columns [r * CIN, (r+1) * CIN) (+ 3 CIN stacked)
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
-    const int b = m / COUT;                   // M block = horizontal shift
-    const int co = m - b * COUT;
-    const bool valid = b < KS;
+    // M = 128: lane = accumulator row; M = 64 (16 output channels): block b = warp b, lanes 0..15
+    const int b = Cfg::kM == 64 ? quad : m / COUT;      // M block = horizontal shift
+    const int co = Cfg::kM == 64 ? (lane & 15) : m - b * COUT;
+    const bool valid = b < KS && (Cfg::kM != 64 || lane < 16);
     const int q = KS - 1 - b;
     constexpr size_t KK = (size_t)KS * KS * CIN;
     const int chains = (total_rows + kWgFlushRows - 1) / kWgFlushRows;
