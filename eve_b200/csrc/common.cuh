@@ -349,9 +349,11 @@ int avgpool_bwd(const float* dy, int N, int HW, int C, float* dx, cudaStream_t s
 // torch AdaptiveMaxPool2d semantics: window [floor(i*L/O), ceil((i+1)*L/O))
 int adaptive_maxpool_fwd(const float* x, int N, int H, int W, int C, int OH, int OW, float* y,
                          int32_t* idx, cudaStream_t s);
-// dx = scatter(dy) (+ addend, dx's layout: the skip-connection gradient)
+// dx = scatter(dy) (+ addend: the skip-connection gradient, dx's pixel order with rows of
+// addend_ld floats -- 0 = C -- so that it can be a channel slice of the concat's gradient)
 int adaptive_maxpool_bwd(const float* dy, const int32_t* idx, int N, int H, int W, int C, int OH,
-                         int OW, float* dx, cudaStream_t s, const float* addend = nullptr);
+                         int OW, float* dx, cudaStream_t s, const float* addend = nullptr,
+                         int addend_ld = 0);
 // bilinear (align_corners=False) upsample of x[N,H,W,C] to [OH,OW], written into
 // y[N,OH,OW,ldy] at channel offset coff (the concat of refine_net.py:123-126)
 int upsample_bilinear_fwd(const float* x, int N, int H, int W, int C, int OH, int OW, float* y,

@@ -196,7 +196,8 @@ template <int KH, int KW>
 __global__ void __launch_bounds__(256)
 adaptive_maxpool_bwd_exact_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx,
                                   long long total4, int W, int C, int OH, int OW,
-                                  const float* __restrict__ addend, float* __restrict__ dx) {
+                                  const float* __restrict__ addend, int ald,
+                                  float* __restrict__ dx) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int C4 = C >> 2;
@@ -221,8 +222,8 @@ adaptive_maxpool_bwd_exact_kernel(const float* __restrict__ dy, const int32_t* _
       v.v[1] = id.y == me ? d.v[1] : 0.f;
       v.v[2] = id.z == me ? d.v[2] : 0.f;
       v.v[3] = id.w == me ? d.v[3] : 0.f;
-      if (addend) {
-        const F4 a = ld4(addend + o);
+      if (addend) {                  // pixel rows of `ald` floats (a channel slice of a wider tensor)
+        const F4 a = ld4(addend + (((size_t)n * H + h) * W + w) * ald + c);
 #pragma unroll
         for (int j = 0; j < 4; ++j) v.v[j] += a.v[j];
       }
@@ -234,12 +235,13 @@ adaptive_maxpool_bwd_exact_kernel(const float* __restrict__ dy, const int32_t* _
 __global__ void __launch_bounds__(256)
 adaptive_maxpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx,
                             long long total4, int H, int W, int C, int OH, int OW,
-                            const float* __restrict__ addend, float* __restrict__ dx) {
+                            const float* __restrict__ addend, int ald, float* __restrict__ dx) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int C4 = C >> 2;
   int c = (int)(i % C4) * 4;
   long long t = i / C4;
+  const long long pix = t;
   int w = (int)(t % W);
   t /= W;
   int h = (int)(t % H);
@@ -262,7 +264,7 @@ adaptive_maxpool_bwd_kernel(const float* __restrict__ dy, const int32_t* __restr
     }
   }
   if (addend) {
-    const F4 a = ld4(addend + i * 4);
+    const F4 a = ld4(addend + (size_t)pix * ald + c);
 #pragma unroll
     for (int j = 0; j < 4; ++j) s[j] += a.v[j];
   }
@@ -548,18 +550,21 @@ int adaptive_maxpool_fwd(const float* x, int N, int H, int W, int C, int OH, int
 }
 
 int adaptive_maxpool_bwd(const float* dy, const int32_t* idx, int N, int H, int W, int C, int OH,
-                         int OW, float* dx, cudaStream_t s, const float* addend) {
+                         int OW, float* dx, cudaStream_t s, const float* addend, int addend_ld) {
   EVE_REQUIRE(C % 4 == 0, EVE_ERR_SHAPE, "adaptive_maxpool: C must be a multiple of 4");
+  const int ald = addend_ld ? addend_ld : C;
+  EVE_REQUIRE(!addend || (ald % 4 == 0 && ((uintptr_t)addend & 15) == 0), EVE_ERR_SHAPE,
+              "adaptive_maxpool_bwd: the addend's row pitch and start must be multiples of 4 floats");
   if (H == 2 * OH && W == 2 * OW) {
     long long total = (long long)N * OH * OW * (C / 4);
     adaptive_maxpool_bwd_exact_kernel<2, 2><<<cdiv(total, 256), 256, 0, s>>>(dy, idx, total, W, C, OH, OW,
-                                                                             addend, dx);
+                                                                             addend, ald, dx);
     EVE_LAUNCH_CHECK();
     return EVE_OK;
   }
   long long total = (long long)N * H * W * (C / 4);
   adaptive_maxpool_bwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(dy, idx, total, H, W, C, OH, OW,
-                                                               addend, dx);
+                                                               addend, ald, dx);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }

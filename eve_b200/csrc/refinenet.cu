@@ -741,7 +741,9 @@ bool build_fused_bwd(const RNet& n, Arena& ws, FusedBwd& f) {
 
 // Backward-only scratch beyond BwdScratch.
 struct BwdExtra {
-  float* dskip[kLevels];      // grad w.r.t. the encoder output of level l coming from the concat
+  float* dskip[kLevels];      // grad w.r.t. the encoder output of level l coming from the concat:
+  int dskip_ld[kLevels];      // levels 0-3 a channel slice of dcat[l] (read in place), level 4 its own copy
+  float* dcat[kLevels];       // levels 0-3: the gradient of the decoder block's concatenated input
   float* cb[6];               // bottleneck temporaries, each B*P*4nf
   float* dcarry[kMaxRCells];  // B*P*nf
   float *dby, *dbx;           // time-major [T][B][P][nf]
@@ -752,7 +754,20 @@ struct BwdExtra {
 bool build_bwd_extra(const RNet& n, Arena& ws, BwdExtra& e) {
   for (int l = 0; l < kLevels; ++l) {
     const RBlock& k = n.enc[l].back();
-    e.dskip[l] = n.p.use_skip ? ws.get<float>((size_t)n.N * k.H * k.W * k.oc) : nullptr;
+    e.dcat[l] = nullptr;
+    e.dskip_ld[l] = k.oc;
+    if (!n.p.use_skip) {
+      e.dskip[l] = nullptr;
+    } else if (l < kLevels - 1 && n.dec[l + 1].oc % 4 == 0 && n.dec[l].ic % 4 == 0) {
+      // the decoder block writes its input gradient here and it stays until the encoder's backward
+      // has added the skip half (channels [inner.oc, ic)) -- no copy out of a recycled buffer
+      const RBlock& d = n.dec[l];
+      e.dcat[l] = ws.get<float>((size_t)n.N * d.H * d.W * d.ic);
+      e.dskip[l] = e.dcat[l] ? e.dcat[l] + n.dec[l + 1].oc : nullptr;
+      e.dskip_ld[l] = d.ic;
+    } else {
+      e.dskip[l] = ws.get<float>((size_t)n.N * k.H * k.W * k.oc);
+    }
   }
   const int P = kLevelH[4] * kLevelW[4];
   for (int i = 0; i < 6; ++i) e.cb[i] = ws.get<float>((size_t)n.B * P * 4 * n.nf);
@@ -1114,15 +1129,16 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
     const RBlock& k = n.dec[l];
     const RBlock& inner = n.dec[l + 1];
     const RBlock& e = n.enc[l].back();
+    float* din = ex.dcat[l] ? ex.dcat[l] : other;   // gradient of cat[upsampled inner, skip]
     if (fusedn)
-      EVE_TRY(block_bwd_fused(k, N, w, gr, acc, cur, nullptr, other, nullptr, nullptr, nullptr, sc,
+      EVE_TRY(block_bwd_fused(k, N, w, gr, acc, cur, nullptr, din, nullptr, nullptr, nullptr, sc,
                               fb, s));
     else
-      EVE_TRY(block_bwd(k, N, w, gr, acc, cur, other, sc, s));
-    if (p->use_skip)
-      EVE_TRY(copy_channels(other, (long long)N * k.H * k.W, e.oc, k.ic, inner.oc, ex.dskip[l],
+      EVE_TRY(block_bwd(k, N, w, gr, acc, cur, din, sc, s));
+    if (p->use_skip && !ex.dcat[l])
+      EVE_TRY(copy_channels(din, (long long)N * k.H * k.W, e.oc, k.ic, inner.oc, ex.dskip[l],
                             e.oc, 0, false, s));
-    EVE_TRY(upsample_bilinear_bwd(other, k.ic, 0, N, inner.H, inner.W, inner.oc, k.H, k.W, cur, s));
+    EVE_TRY(upsample_bilinear_bwd(din, k.ic, 0, N, inner.H, inner.W, inner.oc, k.H, k.W, cur, s));
   }
   {
     const RBlock& k = n.dec[4];
@@ -1292,7 +1308,8 @@ extern "C" int eve_refinenet_bwd(const eve_refinenet_params* p, const float* dou
       const RBlock& e = n.enc[l - 1].back();
       // + the gradient that reached this encoder output through the skip connection
       EVE_TRY(adaptive_maxpool_bwd(cur, n.pidx[l - 1], N, e.H, e.W, e.oc, kLevelH[l], kLevelW[l],
-                                   other, s, p->use_skip ? ex.dskip[l - 1] : nullptr));
+                                   other, s, p->use_skip ? ex.dskip[l - 1] : nullptr,
+                                   ex.dskip_ld[l - 1]));
       float* tmp = cur; cur = other; other = tmp;
       have = false;
     }
