@@ -347,8 +347,10 @@ int maxpool_bwd_scatter(const float* dy, const int32_t* idx, int N, int H, int W
 int avgpool_fwd(const float* x, int N, int HW, int C, float* y, cudaStream_t s);
 int avgpool_bwd(const float* dy, int N, int HW, int C, float* dx, cudaStream_t s);
 // torch AdaptiveMaxPool2d semantics: window [floor(i*L/O), ceil((i+1)*L/O))
+// copy (optional): x is also written, in its own pixel order, into rows of copy_ld floats (the skip
+// half of the decoder's concat buffer: the kernel reads every input element anyway)
 int adaptive_maxpool_fwd(const float* x, int N, int H, int W, int C, int OH, int OW, float* y,
-                         int32_t* idx, cudaStream_t s);
+                         int32_t* idx, cudaStream_t s, float* copy = nullptr, int copy_ld = 0);
 // dx = scatter(dy) (+ addend: the skip-connection gradient, dx's pixel order with rows of
 // addend_ld floats -- 0 = C -- so that it can be a channel slice of the concat's gradient)
 int adaptive_maxpool_bwd(const float* dy, const int32_t* idx, int N, int H, int W, int C, int OH,

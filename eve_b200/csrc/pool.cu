@@ -155,7 +155,8 @@ __device__ __forceinline__ int win_end(int i, int L, int O) { return ((i + 1) * 
 
 __global__ void __launch_bounds__(256)
 adaptive_maxpool_fwd_kernel(const float* __restrict__ x, long long total4, int H, int W, int C,
-                            int OH, int OW, float* __restrict__ y, int32_t* __restrict__ idx) {
+                            int OH, int OW, float* __restrict__ y, int32_t* __restrict__ idx,
+                            float* __restrict__ copy, int cld) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int C4 = C >> 2;
@@ -174,6 +175,9 @@ adaptive_maxpool_fwd_kernel(const float* __restrict__ x, long long total4, int H
   for (int h = h0; h < h1; ++h)
     for (int w = w0; w < w1; ++w) {
       F4 xv = ld4(xp + (size_t)(h * W + w) * C);
+      // the input on its way into the concat buffer of the decoder (rows of cld floats); overlapping
+      // windows write the same value twice
+      if (copy) st4(copy + (((size_t)n * H + h) * W + w) * cld + c, xv);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float v = xv.v[j];
@@ -541,10 +545,13 @@ int avgpool_bwd(const float* dy, int N, int HW, int C, float* dx, cudaStream_t s
 }
 
 int adaptive_maxpool_fwd(const float* x, int N, int H, int W, int C, int OH, int OW, float* y,
-                         int32_t* idx, cudaStream_t s) {
+                         int32_t* idx, cudaStream_t s, float* copy, int copy_ld) {
   EVE_REQUIRE(C % 4 == 0, EVE_ERR_SHAPE, "adaptive_maxpool: C must be a multiple of 4");
   long long total = (long long)N * OH * OW * (C / 4);
-  adaptive_maxpool_fwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, H, W, C, OH, OW, y, idx);
+  EVE_REQUIRE(!copy || (copy_ld % 4 == 0 && ((uintptr_t)copy & 15) == 0), EVE_ERR_SHAPE,
+              "adaptive_maxpool_fwd: the copy's row pitch and start must be multiples of 4 floats");
+  adaptive_maxpool_fwd_kernel<<<cdiv(total, 256), 256, 0, s>>>(x, total, H, W, C, OH, OW, y, idx, copy,
+                                                               copy_ld);
   EVE_LAUNCH_CHECK();
   return EVE_OK;
 }

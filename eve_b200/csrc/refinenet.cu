@@ -904,12 +904,17 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
     return fusedn ? block_fwd_fused(k, N, w, cs, PA, PB, s) : block_fwd(k, N, w, cs, s);
   };
   // ---- encoder
+  bool skip_in_cat[kLevels] = {false, false, false, false, false};
   for (int l = 0; l < kLevels; ++l) {
     for (auto& k : n.enc[l]) EVE_TRY(run_block(k));
     if (l + 1 < kLevels) {
       const RBlock& k = n.enc[l].back();
+      // the skip connection's half of cat[l] (channels [inner.oc, ic)) is written by the same pass
+      const bool cp = p->use_skip && n.dec[l + 1].oc % 4 == 0 && n.dec[l].ic % 4 == 0;
+      skip_in_cat[l] = cp;
       EVE_TRY(adaptive_maxpool_fwd(k.out, N, k.H, k.W, k.oc, kLevelH[l + 1], kLevelW[l + 1],
-                                   n.pooled[l], n.pidx[l], s));
+                                   n.pooled[l], n.pidx[l], s, cp ? n.cat[l] + n.dec[l + 1].oc : nullptr,
+                                   n.dec[l].ic));
     }
   }
   // ---- bottleneck over time (time-major)
@@ -1053,7 +1058,7 @@ extern "C" int eve_refinenet_fwd(const eve_refinenet_params* p, const float* scr
     const RBlock& e = n.enc[l].back();
     EVE_TRY(upsample_bilinear_fwd(inner.out, N, inner.H, inner.W, inner.oc, k.H, k.W, n.cat[l],
                                   k.ic, 0, s));
-    if (p->use_skip)
+    if (p->use_skip && !skip_in_cat[l])
       EVE_TRY(copy_channels(e.out, (long long)N * k.H * k.W, e.oc, e.oc, 0, n.cat[l], k.ic,
                             inner.oc, false, s));
     EVE_TRY(run_block(k));
