@@ -94,3 +94,38 @@ def test_angular_error_and_its_vjp(hm):
                       _p(np.ascontiguousarray(gl.numpy())), _p(da))
     assert np.abs(got - want.detach().numpy()).max() < 1e-9
     assert np.abs(da - a.grad.numpy()).max() < 1e-8 * max(1.0, np.abs(da).max())
+
+
+@pytest.mark.parametrize('ties', [False, True])
+def test_stem_backward_window_sum_identity(ties):
+    """The algebra behind stem_pool_in_backward (eve_b200/csrc/norm.cu): behind
+    maxpool3x3s2p1(relu(InstanceNorm(x))) (torchvision bn1 / relu / maxpool, eye_net.py:48-50) the
+    two per-(n, c) sums of the norm's backward, sum g and sum g * xhat over the PIXELS with g the
+    un-pooled, ReLU-masked gradient, equal sums over the POOL WINDOWS of the pooled tensors alone:
+    sum dp [p > 0] and sum dp * p.  Checked in fp64 against torch autograd, with and without ties
+    (the first maximum of a window takes the gradient, a zero maximum passes none)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(21 + ties)
+    n, c, h, w = 2, 5, 12, 10
+    x = (torch.randint(0, 3, (n, c, h, w), generator=g).double() if ties
+         else torch.randn(n, c, h, w, generator=g, dtype=torch.float64))
+    mean = x.mean(dim=(2, 3), keepdim=True)
+    rstd = (x.var(dim=(2, 3), unbiased=False, keepdim=True) + 1e-5).rsqrt()
+    xhat = ((x - mean) * rstd).requires_grad_(True)
+    p = F.max_pool2d(F.relu(xhat), 3, 2, 1)
+    dp = torch.randn(p.shape, generator=g, dtype=torch.float64)
+    p.backward(dp)
+    gpix = xhat.grad                                   # dL/dxhat = un-pooled, masked gradient
+    sum_g = gpix.sum(dim=(2, 3))
+    sum_gx = (gpix * xhat.detach()).sum(dim=(2, 3))
+    pd = p.detach()
+    win_g = (dp * (pd > 0)).sum(dim=(2, 3))
+    win_gx = (dp * pd).sum(dim=(2, 3))
+    assert float((sum_g - win_g).abs().max()) < 1e-12 * max(1.0, float(sum_g.abs().max()))
+    assert float((sum_gx - win_gx).abs().max()) < 1e-12 * max(1.0, float(sum_gx.abs().max()))
+    # and the norm's input gradient built from them is what autograd gives for the whole chain
+    xd = x.clone().requires_grad_(True)
+    F.max_pool2d(F.relu(F.instance_norm(xd, eps=1e-5)), 3, 2, 1).backward(dp)
+    hw = h * w
+    dx = rstd * (gpix - win_g[..., None, None] / hw - xhat.detach() * win_gx[..., None, None] / hw)
+    assert float((dx - xd.grad).abs().max()) < 1e-10 * max(1.0, float(xd.grad.abs().max()))
