@@ -129,3 +129,52 @@ def test_stem_backward_window_sum_identity(ties):
     hw = h * w
     dx = rstd * (gpix - win_g[..., None, None] / hw - xhat.detach() * win_gx[..., None, None] / hw)
     assert float((dx - xd.grad).abs().max()) < 1e-10 * max(1.0, float(xd.grad.abs().max()))
+
+
+@pytest.mark.parametrize('h,w', [(1, 1), (1, 4), (2, 1), (5, 7), (9, 16)])
+def test_exact_2x_bilinear_weights(h, w):
+    """The constant weights of upsample2x_{fwd,bwd}_kernel (eve_b200/csrc/pool.cu) for
+    nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) (refine_net.py:101,124):
+    output 2k reads inputs (k-1, k) with (0.25, 0.75) -- (k, .) with weight 1 at k = 0 --, output
+    2k+1 reads (k, min(k+1, last)) with (0.75, 0.25); hence input k receives 0.25 / 0.75 / 0.75 /
+    0.25 from outputs 2k-1 .. 2k+2, with 1 instead of 0.75 where the source is clamped.  Restated
+    in numpy and compared with torch (forward) and its autograd (backward) in fp64."""
+    import torch.nn.functional as F
+
+    def axis_matrix(n):
+        m = np.zeros((2 * n, n))
+        for k in range(n):
+            if k == 0:
+                m[0, 0] = 1.0
+            else:
+                m[2 * k, k - 1], m[2 * k, k] = 0.25, 0.75
+            m[2 * k + 1, k] += 0.75
+            m[2 * k + 1, min(k + 1, n - 1)] += 0.25
+        return m
+
+    def gather_weights(n):
+        wts = np.zeros((n, 4))            # outputs 2k-1 .. 2k+2 -> input k
+        for k in range(n):
+            wts[k] = [0.25 if k > 0 else 0.0, 1.0 if k == 0 else 0.75,
+                      1.0 if k == n - 1 else 0.75, 0.25 if k < n - 1 else 0.0]
+        return wts
+
+    rng = np.random.RandomState(h * 31 + w)
+    x = rng.randn(2, 3, h, w)
+    my, mx = axis_matrix(h), axis_matrix(w)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    y = F.interpolate(xt, scale_factor=2, mode='bilinear', align_corners=False)
+    mine = np.einsum('ah,nchw,bw->ncab', my, x, mx)
+    assert np.abs(mine - y.detach().numpy()).max() < 1e-13
+    dy = rng.randn(*y.shape)
+    y.backward(torch.from_numpy(dy))
+    gy, gx = gather_weights(h), gather_weights(w)
+    dx = np.zeros_like(x)
+    for k in range(h):
+        for j in range(w):
+            for a in range(4):
+                for b in range(4):
+                    oy, ox = 2 * k - 1 + a, 2 * j - 1 + b
+                    if gy[k, a] and gx[j, b]:
+                        dx[:, :, k, j] += gy[k, a] * gx[j, b] * dy[:, :, oy, ox]
+    assert np.abs(dx - xt.grad.numpy()).max() < 1e-12
