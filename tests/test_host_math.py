@@ -178,3 +178,54 @@ def test_exact_2x_bilinear_weights(h, w):
                     if gy[k, a] and gx[j, b]:
                         dx[:, :, k, j] += gy[k, a] * gx[j, b] * dy[:, :, oy, ox]
     assert np.abs(dx - xt.grad.numpy()).max() < 1e-12
+
+
+@pytest.mark.parametrize('rows_per_strip', [1, 2, 3, 7])
+def test_row_stacked_weight_gradient_decomposition(rows_per_strip):
+    """The work decomposition of conv_tc_wgrad_row3_kernel (eve_b200/csrc/conv_tc.cu) restated in
+    numpy: an image is cut into strips of rows; ring entry e of a strip holds the dy row h0-1+e
+    (one zero pixel on each side, rows outside the image zero) and the x row of the same index --
+    ZERO for the two halo entries, whose x rows belong to the neighbouring strips.  For every row h
+    of the strip ONE product of the dy row h with the x rows (h-1, h, h+1) feeds the accumulators
+    (D_0, D_1, D_2) of the three filter rows; the strip's dy halo rows meet their single x row
+    separately (row h0-1 with x row h0 into D_2, row h1 with x row h1-1 into D_0).  M block b of a
+    product is the dy row shifted by b pixels, i.e. filter column q = 2 - b.  Summed over strips and
+    images this must be the weight gradient of a 3x3 stride-1 'same' convolution (fp64 autograd)."""
+    import torch.nn.functional as F
+    rng = np.random.RandomState(rows_per_strip)
+    n, cin, cout, H, W = 2, 2, 3, 7, 6
+    x = rng.randn(n, cin, H, W)
+    dy = rng.randn(n, cout, H, W)
+    xt = torch.from_numpy(x)
+    wt = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(xt, wt, padding=1).backward(torch.from_numpy(dy))
+    want = wt.grad.numpy()
+
+    def product(dyrow, xrow):
+        # dyrow [W + 2][cout] staged from pixel -1, xrow [W][cin] -> D[b][co][ci]
+        return np.stack([dyrow[b:b + W].T @ xrow for b in range(3)])
+
+    D = np.zeros((3, 3, cout, cin))                       # [filter row r][M block b][co][ci]
+    for img in range(n):
+        for h0 in range(0, H, rows_per_strip):
+            h1 = min(H, h0 + rows_per_strip)
+            ent_dy, ent_x = [], []
+            for hr in range(h0 - 1, h1 + 1):
+                row = np.zeros((W + 2, cout))
+                if 0 <= hr < H:
+                    row[1:W + 1] = dy[img, :, hr, :].T
+                ent_dy.append(row)
+                ent_x.append(x[img, :, hr, :].T if h0 <= hr < h1 else np.zeros((W, cin)))
+            for h in range(h0, h1):
+                e = h - h0 + 1                              # centre entry
+                for r in range(3):                          # one N = 3 Cin instruction on the device
+                    D[r] += product(ent_dy[e], ent_x[e - 1 + r])
+                if h == h0:
+                    D[2] += product(ent_dy[e - 1], ent_x[e])
+                if h == h1 - 1:
+                    D[0] += product(ent_dy[e + 1], ent_x[e])
+    got = np.zeros_like(want)
+    for r in range(3):
+        for q in range(3):
+            got[:, :, r, q] = D[r][2 - q]
+    assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
